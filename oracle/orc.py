@@ -1,0 +1,359 @@
+"""ctypes binding of the CPU ORACLE (oracle/liborc.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py -- never by tuvok_b200/.
+See oracle/orc.h for the reference citations of every entry point.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+U8, U16, F32 = 0, 1, 2
+RM_1DTRANS, RM_2DTRANS, RM_ISOSURFACE = 0, 1, 2
+BI_MISSING, BI_CHILD_EMPTY, BI_EMPTY, BI_FLAG_COUNT = 0, 1, 2, 3
+BS_ONLY_NEEDED, BS_REQUEST_ALL, BS_SKIP_ONE, BS_SKIP_TWO = 0, 1, 2, 3
+MAX_LOD = 32
+NP_DTYPE = {U8: np.uint8, U16: np.uint16, F32: np.float32}
+DTYPE_OF = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.float32): F32}
+
+u32x3 = C.c_uint32 * 3
+f32x3 = C.c_float * 3
+f32x4 = C.c_float * 4
+
+
+class RenderParams(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("model_view", C.c_float * 16), ("projection", C.c_float * 16),
+        ("vol", u32x3), ("scale", f32x3), ("dtype", C.c_int),
+        ("pool_size", u32x3), ("capacity", u32x3),
+        ("max_total_brick", u32x3), ("max_inner_brick", u32x3),
+        ("lod_count", C.c_uint32), ("lod_offset", C.c_uint32 * MAX_LOD),
+        ("meta_dim", u32x3),
+        ("mode", C.c_int), ("lighting", C.c_int),
+        ("sample_rate_modifier", C.c_float), ("trans_scale", C.c_float),
+        ("gradient_scale", C.c_float), ("isoval", C.c_float),
+        ("ambient", f32x4), ("diffuse", f32x4), ("specular", f32x4),
+        ("light_dir", f32x3), ("eye", f32x3), ("iso_color", f32x3),
+        ("lod_factor", C.c_float),
+        ("tf_w", C.c_uint32), ("tf_h", C.c_uint32),
+        ("hash_size", C.c_uint32), ("rehash_count", C.c_uint32), ("strategy", C.c_int),
+        ("clip_min", f32x3), ("clip_max", f32x3), ("nearest", C.c_int),
+    ]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64),
+                ("brick_visits", C.c_uint64), ("hash_entries", C.c_uint32)]
+
+
+def build(force=False):
+    """Compile liborc.so (and oracle/_ref when /root/reference is present)."""
+    so = os.path.join(_HERE, "liborc.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".cpp", ".h"))]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-j8", "liborc.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def build_ref():
+    """Build oracle/_ref tools from the reference sources, if they are present here."""
+    if not os.path.isdir("/root/reference/IO"):
+        return False
+    subprocess.check_call(["make", "-C", _HERE, "-j8", "ref"], stdout=subprocess.DEVNULL)
+    return True
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(_HERE, "liborc.so")
+    if not os.path.exists(so):
+        build()
+    L = C.CDLL(so)
+    P = C.c_void_p
+    sig = {
+        "orc_octree_new": (P, [u32x3, u32x3, C.c_uint32, C.c_int]),
+        "orc_octree_free": (None, [P]),
+        "orc_octree_build": (C.c_int, [P, P, C.c_int, C.c_int]),
+        "orc_octree_lod_count": (C.c_uint32, [P]),
+        "orc_octree_largest_single_brick_lod": (C.c_uint32, [P]),
+        "orc_octree_lod_size": (None, [P, C.c_uint32, u32x3]),
+        "orc_octree_brick_count": (None, [P, C.c_uint32, u32x3]),
+        "orc_octree_total_bricks": (C.c_uint64, [P]),
+        "orc_octree_brick_index": (C.c_uint64, [P] + [C.c_uint32] * 4),
+        "orc_octree_brick_size": (None, [P] + [C.c_uint32] * 4 + [u32x3]),
+        "orc_octree_get_brick": (C.c_int, [P] + [C.c_uint32] * 4 + [P]),
+        "orc_octree_minmax": (C.POINTER(C.c_double), [P]),
+        "orc_octree_lod_volume": (P, [P, C.c_uint32]),
+        "orc_tf1d_std": (None, [P, C.c_uint32, C.c_float, C.c_float]),
+        "orc_tf1d_bytes": (None, [P, C.c_uint32, P]),
+        "orc_tf1d_nonzero": (None, [P, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "orc_tf2d_nonzero": (None, [P, C.c_uint32, C.c_uint32, C.c_uint64 * 4]),
+        "orc_pool_size": (None, [C.c_uint64, C.c_uint64, C.c_uint64, u32x3, C.c_uint64, C.c_uint32, u32x3]),
+        "orc_fit_1d_to_3d": (C.c_int, [C.c_uint64, C.c_uint32, u32x3]),
+        "orc_pool_new": (P, [u32x3, u32x3, u32x3, C.c_uint32, C.c_uint32, C.c_uint32, P]),
+        "orc_pool_free": (None, [P]),
+        "orc_pool_total_bricks": (C.c_uint32, [P]),
+        "orc_pool_meta_count": (C.c_uint32, [P]),
+        "orc_pool_meta": (C.POINTER(C.c_uint32), [P]),
+        "orc_pool_meta_dim": (None, [P, u32x3]),
+        "orc_pool_capacity": (None, [P, u32x3]),
+        "orc_pool_lod_offsets": (None, [P, P]),
+        "orc_pool_brick_layout": (None, [P, C.c_uint32, u32x3]),
+        "orc_pool_float_layout": (None, [P, C.c_uint32, f32x3]),
+        "orc_pool_brick_id": (C.c_uint32, [P] + [C.c_uint32] * 4),
+        "orc_pool_vector_id": (None, [P, C.c_uint32, C.c_uint32 * 4]),
+        "orc_pool_upload_first": (C.c_uint32, [P]),
+        "orc_pool_recompute_visibility": (None, [P, C.c_int] + [C.c_double] * 4 + [C.c_uint32 * 4]),
+        "orc_pool_upload_bricks": (C.c_uint32, [P, P, C.c_uint32, P]),
+        "orc_pool_slot_count": (C.c_uint32, [P]),
+        "orc_pool_slots": (None, [P, P, P, P]),
+        "orc_ray_setup": (None, [C.POINTER(RenderParams), P, P, P]),
+        "orc_raycast": (None, [C.POINTER(RenderParams)] + [P] * 11 + [C.POINTER(RenderStats), C.c_int]),
+        "orc_iso_compose": (None, [C.POINTER(RenderParams), P, P, P]),
+        "orc_hash_decode": (C.c_uint32, [P, C.c_uint32, u32x3, P]),
+        "orc_rgba8": (None, [P, C.c_uint64, P]),
+        "orc_composite_over": (None, [P, P, C.c_uint64, P]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _LIB = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Octree:
+    """ExtendedOctree + converter restatement (orc_octree.c)."""
+
+    def __init__(self, flat, max_brick, overlap, clamp=False, median=False):
+        flat = np.ascontiguousarray(flat)
+        assert flat.ndim == 3, "flat volume is indexed [z, y, x]"
+        self.dtype = DTYPE_OF[flat.dtype]
+        self.vol = (flat.shape[2], flat.shape[1], flat.shape[0])
+        if np.isscalar(max_brick):
+            max_brick = (max_brick,) * 3
+        self.max_brick = tuple(int(b) for b in max_brick)
+        self.overlap = int(overlap)
+        L = lib()
+        self.h = L.orc_octree_new(u32x3(*self.vol), u32x3(*self.max_brick), self.overlap, self.dtype)
+        if not self.h:
+            raise ValueError("invalid octree geometry")
+        L.orc_octree_build(self.h, _p(flat), int(clamp), int(median))
+        self.lod_count = L.orc_octree_lod_count(self.h)
+        self.total_bricks = L.orc_octree_total_bricks(self.h)
+        self.largest_single_brick_lod = L.orc_octree_largest_single_brick_lod(self.h)
+        mm = L.orc_octree_minmax(self.h)
+        self.minmax = np.ctypeslib.as_array(mm, shape=(self.total_bricks, 4)).copy()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_octree_free(self.h)
+            self.h = None
+
+    def lod_size(self, lod):
+        o = u32x3()
+        lib().orc_octree_lod_size(self.h, lod, o)
+        return tuple(o)
+
+    def brick_count(self, lod):
+        o = u32x3()
+        lib().orc_octree_brick_count(self.h, lod, o)
+        return tuple(o)
+
+    def brick_index(self, x, y, z, lod):
+        return lib().orc_octree_brick_index(self.h, x, y, z, lod)
+
+    def brick_size(self, x, y, z, lod):
+        o = u32x3()
+        lib().orc_octree_brick_size(self.h, x, y, z, lod, o)
+        return tuple(o)
+
+    def brick(self, x, y, z, lod):
+        """Brick voxels incl. ghost as array [sz, sy, sx]."""
+        s = self.brick_size(x, y, z, lod)
+        out = np.empty((s[2], s[1], s[0]), NP_DTYPE[self.dtype])
+        lib().orc_octree_get_brick(self.h, x, y, z, lod, _p(out))
+        return out
+
+    def lod_volume(self, lod):
+        s = self.lod_size(lod)
+        n = s[0] * s[1] * s[2]
+        ptr = lib().orc_octree_lod_volume(self.h, lod)
+        buf = (C.c_char * (n * np.dtype(NP_DTYPE[self.dtype]).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, NP_DTYPE[self.dtype]).reshape(s[2], s[1], s[0]).copy()
+
+    def iter_bricks(self, max_lod=None):
+        n = self.lod_count if max_lod is None else max_lod + 1
+        for lod in range(n):
+            bc = self.brick_count(lod)
+            for z in range(bc[2]):
+                for y in range(bc[1]):
+                    for x in range(bc[0]):
+                        yield (x, y, z, lod)
+
+
+class Pool:
+    """GLVolumePool bookkeeping restatement (orc_pool.cpp)."""
+
+    def __init__(self, pool_size, vol, max_brick, overlap, pool_lod_count, minmax4, max_3d_dim=16384):
+        L = lib()
+        self.pool_size = tuple(int(v) for v in pool_size)
+        self.vol = tuple(vol)
+        self.max_brick = tuple(max_brick)
+        self.overlap = overlap
+        self.lod_count = pool_lod_count
+        mm = np.ascontiguousarray(minmax4, np.float64)
+        self.h = L.orc_pool_new(u32x3(*self.pool_size), u32x3(*self.vol), u32x3(*self.max_brick), overlap,
+                                pool_lod_count, max_3d_dim, _p(mm))
+        if not self.h:
+            raise ValueError("pool creation failed")
+        self.total_bricks = L.orc_pool_total_bricks(self.h)
+        o = u32x3(); L.orc_pool_capacity(self.h, o); self.capacity = tuple(o)
+        o = u32x3(); L.orc_pool_meta_dim(self.h, o); self.meta_dim = tuple(o)
+        offs = np.zeros(pool_lod_count, np.uint32)
+        L.orc_pool_lod_offsets(self.h, _p(offs))
+        self.lod_offsets = offs
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_pool_free(self.h)
+            self.h = None
+
+    @property
+    def meta(self):
+        L = lib()
+        n = L.orc_pool_meta_count(self.h)
+        return np.ctypeslib.as_array(L.orc_pool_meta(self.h), shape=(n,)).copy()
+
+    def brick_layout(self, lod):
+        o = u32x3(); lib().orc_pool_brick_layout(self.h, lod, o); return tuple(o)
+
+    def float_layout(self, lod):
+        o = f32x3(); lib().orc_pool_float_layout(self.h, lod, o); return tuple(o)
+
+    def brick_id(self, x, y, z, lod):
+        return lib().orc_pool_brick_id(self.h, x, y, z, lod)
+
+    def vector_id(self, i):
+        o = (C.c_uint32 * 4)(); lib().orc_pool_vector_id(self.h, i, o); return tuple(o)
+
+    def upload_first(self):
+        return lib().orc_pool_upload_first(self.h)
+
+    def recompute_visibility(self, mode, a, b=0.0, c=0.0, d=0.0):
+        counts = (C.c_uint32 * 4)()
+        lib().orc_pool_recompute_visibility(self.h, mode, a, b, c, d, counts)
+        return tuple(counts)
+
+    def upload_bricks(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint32).reshape(-1, 4)
+        out = np.zeros(len(ids), np.uint32)
+        n = lib().orc_pool_upload_bricks(self.h, _p(ids), len(ids), _p(out))
+        return n, out
+
+    def slots(self):
+        L = lib()
+        n = L.orc_pool_slot_count(self.h)
+        ids = np.zeros(n, np.int32); t = np.zeros(n, np.uint64); pos = np.zeros((n, 3), np.uint32)
+        L.orc_pool_slots(self.h, _p(ids), _p(t), _p(pos))
+        return ids, t, pos
+
+
+def pool_size(max_gpu_mem, bit_width, comp_count, max_brick, total_bricks, max_3d_dim=16384):
+    o = u32x3()
+    lib().orc_pool_size(max_gpu_mem, bit_width, comp_count, u32x3(*max_brick), total_bricks, max_3d_dim, o)
+    return tuple(o)
+
+
+def fit_1d_to_3d(n, max_dim):
+    o = u32x3()
+    if lib().orc_fit_1d_to_3d(n, max_dim, o) != 0:
+        raise ValueError("index exceeds array")
+    return tuple(o)
+
+
+def tf1d_std(n, center=0.5, inv_gradient=0.5):
+    rgba = np.zeros((n, 4), np.float32)
+    lib().orc_tf1d_std(_p(rgba), n, center, inv_gradient)
+    return rgba
+
+
+def tf1d_bytes(rgba):
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    out = np.zeros(rgba.shape, np.uint8)
+    lib().orc_tf1d_bytes(_p(rgba), rgba.shape[0], _p(out))
+    return out
+
+
+def tf1d_nonzero(rgba):
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    lo, hi = C.c_uint64(), C.c_uint64()
+    lib().orc_tf1d_nonzero(_p(rgba), rgba.shape[0], C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def tf2d_nonzero(rgba8):
+    rgba8 = np.ascontiguousarray(rgba8, np.uint8)
+    h, w = rgba8.shape[:2]
+    o = (C.c_uint64 * 4)()
+    lib().orc_tf2d_nonzero(_p(rgba8), w, h, o)
+    return tuple(o)
+
+
+def ray_setup(params):
+    n = params.width * params.height
+    entry = np.zeros((n, 4), np.float32); exit_ = np.zeros((n, 4), np.float32)
+    cov = np.zeros(n, np.uint8)
+    lib().orc_ray_setup(C.byref(params), _p(entry), _p(exit_), _p(cov))
+    return entry, exit_, cov
+
+
+def raycast(params, pool_atlas, meta, tf, ray_start, start_color, exit_, covered, hash_table=None, threads=1):
+    n = params.width * params.height
+    outs = [np.zeros((n, 4), np.float32) for _ in range(4)]
+    st = RenderStats()
+    meta = np.ascontiguousarray(meta, np.uint32)
+    tf = np.ascontiguousarray(tf, np.uint8)
+    hp = _p(hash_table) if hash_table is not None else None
+    lib().orc_raycast(C.byref(params), _p(pool_atlas), _p(meta), _p(tf), _p(ray_start), _p(start_color),
+                      _p(exit_), _p(covered), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]),
+                      hp, C.byref(st), threads)
+    return outs, st
+
+
+def iso_compose(params, hit_pos, hit_normal):
+    out = np.zeros_like(hit_pos)
+    lib().orc_iso_compose(C.byref(params), _p(hit_pos), _p(hit_normal), _p(out))
+    return out
+
+
+def hash_decode(hash_table, finest_layout):
+    out = np.zeros((len(hash_table), 4), np.uint32)
+    n = lib().orc_hash_decode(_p(hash_table), len(hash_table), u32x3(*finest_layout), _p(out))
+    return out[:n].copy()
+
+
+def rgba8(img):
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.zeros(img.shape, np.uint8)
+    lib().orc_rgba8(_p(img), img.size // 4, _p(out))
+    return out
+
+
+def composite_over(front, back):
+    out = np.zeros_like(front)
+    lib().orc_composite_over(_p(front), _p(back), front.size // 4, _p(out))
+    return out
