@@ -1,0 +1,234 @@
+/*
+ * tvk.h -- C ABI of libtvkcuda.so, the B200 (sm_100a) brick-pool volume raycaster
+ * that drops in for Tuvok's GLGridLeaper / GLRaycaster hot path.
+ *
+ * The reference (SCIInstitute/Tuvok) has no plugin/FFI mechanism: renderers are C++
+ * subclasses of tuvok::AbstrRenderer (Renderer/AbstrRenderer.h:112-881) created by
+ * MasterController::RequestNewVolumeRenderer (Controller/MasterController.cpp:144-212).
+ * A maintainer adds one enum value + one `case` there that creates the thin
+ * `CUDAGridLeaper : AbstrRenderer` shim shown in INTEGRATION.md; that shim (and the
+ * Python/ctypes test harness in tuvok_b200/) talks to this ABI only.
+ *
+ * Conventions: plain C, no exceptions cross the boundary, every call returns a
+ * tvk_status (0 = ok) and records a message retrievable with tvk_last_error().
+ * Input buffers are borrowed for the duration of the call, output buffers are
+ * caller-allocated.  One tvk_ctx per renderer; a ctx is NOT thread-safe (the reference
+ * renderer is bound to the one thread owning its GL context).  Matrices use
+ * Tuvok's storage: row-major float[16], ROW vectors, v' = v*M (Basics/Vectors.h:434-439,
+ * 855-864).  Every entry point cites the reference interface it replaces.
+ */
+#ifndef TVK_H
+#define TVK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVK_ABI_VERSION 1
+#define TVK_MAX_LOD 16
+
+typedef enum {
+  TVK_OK = 0,
+  TVK_ERR_INVALID = 1,      /* bad argument / call order (reference: T_ERROR + return false) */
+  TVK_ERR_CUDA = 2,         /* a CUDA runtime call failed */
+  TVK_ERR_NO_DEVICE = 3,    /* no sm_100 device: there is NO CPU fallback */
+  TVK_ERR_OOM = 4,
+  TVK_ERR_SOURCE = 5        /* the brick source callback failed (Dataset::GetBrick returned false) */
+} tvk_status;
+
+/* ExtendedOctree::COMPONENT_TYPE subset on the hot path (ExtendedOctree.h:137-148) */
+typedef enum { TVK_U8 = 0, TVK_U16 = 1, TVK_F32 = 2 } tvk_dtype;
+/* AbstrRenderer::ERenderMode (Renderer/AbstrRenderer.h:142-147) */
+typedef enum { TVK_RM_1DTRANS = 0, TVK_RM_2DTRANS = 1, TVK_RM_ISOSURFACE = 2 } tvk_render_mode;
+/* RendererState::BrickStrategy (Controller/MasterController.h:61-67) */
+typedef enum { TVK_BS_ONLY_NEEDED = 0, TVK_BS_REQUEST_ALL = 1, TVK_BS_SKIP_ONE_LEVEL = 2,
+               TVK_BS_SKIP_TWO_LEVELS = 3 } tvk_brick_strategy;
+/* page-table flags, BrickIDFlags (Renderer/GL/GLVolumePool.cpp:25-30); >= 3: pool slot + 3 */
+enum { TVK_BI_MISSING = 0, TVK_BI_CHILD_EMPTY = 1, TVK_BI_EMPTY = 2, TVK_BI_FLAG_COUNT = 3 };
+
+typedef struct tvk_ctx tvk_ctx;
+
+/* RendererState + SystemInfo knobs (MasterController.h:61-74, SystemInfo.h:48) */
+typedef struct {
+  int32_t  device;            /* CUDA device ordinal */
+  uint64_t max_gpu_mem;       /* pool budget in bytes, 0 = 8 GiB default of SystemInfo; GPUMemMan.cpp:766-844 */
+  uint32_t max_pool_dim;      /* stands in for GL_MAX_3D_TEXTURE_SIZE; 0 = 16384 */
+  uint32_t hash_table_size;   /* RState.HashTableSize, 0 = 509 */
+  uint32_t rehash_count;      /* RState.RehashCount, 0 = 10 */
+  int32_t  brick_strategy;    /* tvk_brick_strategy; MasterController.cpp:89 default SKIP_TWO_LEVELS */
+} tvk_device_cfg;
+
+/* What GLGridLeaper reads from LinearIndexDataset (SURVEY 8b "Data interfaces consumed") */
+typedef struct {
+  uint32_t domain_size[3];     /* GetDomainSize(0) */
+  float    scale[3];           /* GetScale() */
+  uint32_t max_brick_size[3];  /* GetMaxUsedBrickSizes() -- incl. ghost */
+  uint32_t overlap;            /* GetBrickOverlapSize() (same on all axes) */
+  int32_t  dtype;              /* tvk_dtype: GetBitWidth/GetIsFloat */
+  double   range_max;          /* GetRange().second (MaxValue, AbstrRenderer.cpp:860-866) */
+  float    max_gradient_magnitude; /* Dataset::MaxGradientMagnitude */
+  uint64_t brick_count;        /* GetTotalBrickCount(): entries in minmax */
+  const double* minmax;        /* MaxMinForKey for every brick in TOC order (LOD-major, z, y, x):
+                                  {minScalar, maxScalar, minGradient, maxGradient} */
+} tvk_volume_desc;
+
+/* Dataset::GetBrick(key, vector<T>&) (IO/Dataset.h:93-100).  dst is LIBRARY-OWNED PINNED
+ * memory of `cap` bytes; write the brick x-fastest at its own size (incl. ghost).
+ * Return 0 on success. */
+typedef int (*tvk_brick_cb)(void* user, uint32_t x, uint32_t y, uint32_t z, uint32_t lod,
+                            void* dst, size_t cap);
+/* AbstrDebugOut channel: 0 message, 1 warning, 2 error, 3 other (Controller/Controller.h:68-84) */
+typedef void (*tvk_log_cb)(void* user, int channel, const char* source, const char* msg);
+
+/* The per-frame state the GL renderer reads from AbstrRenderer */
+typedef struct {
+  uint32_t width, height;        /* AbstrRenderer::Resize */
+  float model_view[16];          /* rotation*translation*view, GLRenderer.cpp:627 */
+  float projection[16];          /* GLRenderer::ComputeViewAndProjection, GLRenderer.cpp:892-919 */
+  float lod_factor;              /* CullingLOD::GetLoDFactor, CullingLOD.cpp:57-67 */
+  int32_t mode;                  /* tvk_render_mode */
+  int32_t lighting;              /* m_bUseLighting */
+  float sample_rate_modifier;    /* m_fSampleRateModifier */
+  double isovalue;               /* m_fIsovalue in data units (GetIsoValue) */
+  float ambient[4], diffuse[4], specular[4]; /* m_cAmbient/m_cDiffuse/m_cSpecular: rgb, w = intensity */
+  float light_dir[3];            /* m_vLightDir */
+  float eye[3];                  /* m_vEye */
+  float iso_color[3];            /* m_vIsoColor */
+  int32_t nearest;               /* SetInterpolant(NearestNeighbor) */
+  float clip_min[3], clip_max[3];/* sort-last shard box in normalised volume space; {0,0,0},{1,1,1} = all */
+} tvk_render_params;
+
+/* mirrors PERF_* of Basics/PerfCounter.h:7-44 for the phases of GLGridLeaper::Render3DRegion */
+typedef struct {
+  int32_t  converged;            /* m_bConverged = hash.empty(), GLGridLeaper.cpp:1097-1099 */
+  uint32_t missing_reported;     /* decoded hash entries */
+  uint32_t bricks_paged;         /* UploadBricks count */
+  uint64_t samples;              /* ComputeColorFromVolume/GetVolumeHit evaluations (if counting enabled) */
+  uint64_t rays;                 /* pixels covered by the volume */
+  uint64_t brick_visits;         /* GetBrick calls */
+  float ms_raycast;              /* PERF_RAYCAST (CUDA events) */
+  float ms_read_htable;          /* PERF_READ_HTABLE + PERF_CONDENSE_HTABLE */
+  float ms_upload_bricks;        /* PERF_UPLOAD_BRICKS */
+  float ms_total;                /* PERF_RENDER */
+} tvk_frame_stats;
+
+typedef struct {
+  uint32_t lod_count;            /* all LODs down to 1^3 */
+  uint32_t pool_lod_count;       /* GetLargestSingleBrickLOD()+1, GLVolumePool.cpp:132 */
+  uint64_t total_bricks;         /* bricks of the pool LoDs = page-table entries */
+  uint32_t lod_size[TVK_MAX_LOD][3];
+  uint32_t brick_layout[TVK_MAX_LOD][3];
+  uint32_t lod_offset[TVK_MAX_LOD];
+  uint32_t pool_size[3];         /* atlas voxels = capacity * max brick */
+  uint32_t pool_capacity[3];     /* slots per axis */
+  uint32_t meta_dim[3];          /* Fit1DIndexTo3DArray shape of the page table, GLVolumePool.cpp:816-848 */
+  uint64_t meta_count;           /* meta_dim volume (>= total_bricks) */
+} tvk_info;
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+uint32_t    tvk_abi_version(void);
+/* MasterController::RequestNewVolumeRenderer + GLGridLeaper ctor (MasterController.cpp:144-212) */
+int         tvk_create(const tvk_device_cfg* cfg, tvk_ctx** out);
+/* GLGridLeaper::CleanupShaders/Cleanup (GLGridLeaper.cpp:134-160) */
+void        tvk_destroy(tvk_ctx* ctx);
+const char* tvk_last_error(const tvk_ctx* ctx);   /* ctx may be NULL: error of the last failed tvk_create */
+int         tvk_set_log_callback(tvk_ctx* ctx, tvk_log_cb cb, void* user);
+/* all kernels are launched on this cudaStream_t (default: the ctx's own stream) */
+int         tvk_set_stream(tvk_ctx* ctx, void* cuda_stream);
+int         tvk_synchronize(tvk_ctx* ctx);
+/* count samples/rays/brick visits in tvk_frame_stats (costs atomics; off by default) */
+int         tvk_enable_counters(tvk_ctx* ctx, int enable);
+
+/* ---- dataset --------------------------------------------------------------------- */
+/* GLGridLeaper::RegisterDataset (GLGridLeaper.cpp:105-132): host-described dataset whose bricks
+ * come from `cb` (Dataset::GetBrick).  Copies the min/max table (GLVolumePool.cpp:225-235). */
+int tvk_set_volume(tvk_ctx* ctx, const tvk_volume_desc* desc, tvk_brick_cb cb, void* user);
+/* Device-side data producer replacing ExtendedOctreeConverter::Convert
+ * (ExtendedOctreeConverter.cpp:128-280): bricks a raw x-fastest volume (host or device pointer),
+ * builds the 2x2x2-mean LOD pyramid, ghost cells and per-brick min/max on the GPU and keeps the
+ * brick store resident; it then acts as the brick source. range_max <= 0: 2^bits-1 (1 for f32). */
+int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uint32_t size[3],
+                     int dtype, const float scale[3], const uint32_t max_brick_size[3],
+                     uint32_t overlap, int clamp_to_edge, double range_max,
+                     float max_gradient_magnitude);
+/* seeded integer-arithmetic synthetic volumes (bit-identical to tuvok_b200.synth on the CPU);
+ * kind 0 = V_sph (shells), 1 = V_noise (value noise x falloff), 2 = V_ramp (x + 8y + 64z).
+ * Writes size[0]*size[1]*size[2] voxels to the DEVICE pointer dst. */
+int tvk_synth_volume(tvk_ctx* ctx, void* dst_device, int kind, const uint32_t size[3], int dtype,
+                     uint32_t seed);
+int tvk_get_info(const tvk_ctx* ctx, tvk_info* out);
+/* parity taps: MaxMinForKey table and one brick (x-fastest, own size incl. ghost) */
+int tvk_get_minmax(tvk_ctx* ctx, double* dst, uint64_t n_bricks);
+int tvk_get_brick_size(const tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, uint32_t out[3]);
+int tvk_read_brick(tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, void* dst, size_t cap);
+
+/* ---- transfer functions ---------------------------------------------------------- */
+/* AbstrRenderer::Set1DTrans/Changed1DTrans; rgba = TransferFunction1D::GetByteArray
+ * (TransferFunction1D.cpp:311-330), nz = GetNonZeroLimits (:362-371) */
+int tvk_set_tf1d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t n, uint64_t nz_lo, uint64_t nz_hi);
+/* Changed2DTrans; rgba = TransferFunction2D::GetByteArray (w x h), nz = GetNonZeroLimits
+ * (xmin, xmax, ymin, ymax) (TransferFunction2D.cpp:378-397) */
+int tvk_set_tf2d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, const uint64_t nz[4]);
+
+/* ---- pool / page table ----------------------------------------------------------- */
+/* GLGridLeaper::CreateVolumePool (GLGridLeaper.cpp:83-103): size the pool (GPUMemMan::GetVolumePool,
+ * GPUMemMan.cpp:766-844, unless pool_size != NULL), build slot + page tables, UploadFirstBrick,
+ * RecomputeBrickVisibility. */
+int tvk_create_pool(tvk_ctx* ctx, const uint32_t* pool_size /* [3] or NULL */);
+/* GLGridLeaper::RecomputeBrickVisibility (GLGridLeaper.cpp:647-687) ->
+ * GLVolumePool::RecomputeVisibility (GLVolumePool.cpp:1580-1718), always synchronous.
+ * counts = (total, empty, childEmpty, emptyLeaf).  force=0 honours VisibilityState::NeedsUpdate. */
+int tvk_recompute_visibility(tvk_ctx* ctx, int force, uint32_t counts[4]);
+/* GLVolumePool::UploadBricks (GLVolumePool.cpp:1720-1789) for an explicit request list
+ * ids[n][4] = (x,y,z,lod); out_slots[i] = linear pool coordinate or 0xFFFFFFFF. */
+int tvk_upload_bricks(tvk_ctx* ctx, const uint32_t* ids, uint32_t n, uint32_t* out_slots, uint32_t* n_paged);
+/* parity taps */
+int tvk_get_page_table(tvk_ctx* ctx, uint32_t* dst, uint64_t n);
+int tvk_get_slots(tvk_ctx* ctx, int32_t* brick_ids, uint64_t* times, uint32_t* pos3, uint32_t n_slots);
+int tvk_read_pool_slot(tvk_ctx* ctx, uint32_t slot, void* dst, size_t cap);
+/* GLHashTable::GetData of the last subframe (GLHashTable.cpp:90-105): ids[n][4] */
+int tvk_get_missing_list(tvk_ctx* ctx, uint32_t* ids, uint32_t cap, uint32_t* n);
+
+/* ---- rendering ------------------------------------------------------------------- */
+/* helper: GLRenderer::ComputeViewAndProjection + modelView = rotation*translation*view
+ * (GLRenderer.cpp:627,892-919) and CullingLOD::SetScreenParams (CullingLOD.cpp:57-67);
+ * fills model_view, projection, lod_factor, width, height, eye of `p`. */
+int tvk_compute_view(tvk_render_params* p, uint32_t width, uint32_t height,
+                     const float rotation[16], const float translation[16],
+                     const float eye[3], const float at[3], const float up[3],
+                     float fov_deg, float z_near, float z_far, float screen_space_error);
+/* AbstrRenderer defaults (AbstrRenderer.cpp:64-171) */
+int tvk_default_params(tvk_render_params* p, uint32_t width, uint32_t height);
+/* any view/mode change: marks the region blank (new ray-entry buffer, GLGridLeaper.cpp:925-945) */
+int tvk_set_params(tvk_ctx* ctx, const tvk_render_params* p);
+/* one subframe of GLGridLeaper::Render3DRegion (GLGridLeaper.cpp:914-1154): clear hash table,
+ * raycast, read + decode hash table, page missing bricks in.  stats may be NULL. */
+int tvk_render(tvk_ctx* ctx, tvk_frame_stats* stats);
+/* `while (CheckForRedraw()) Paint()` (GLGridLeaper.cpp:872-890); returns after convergence or
+ * max_subframes.  stats (may be NULL) accumulates over the subframes. */
+int tvk_paint(tvk_ctx* ctx, uint32_t max_subframes, tvk_frame_stats* stats);
+/* raycast pass only, no miss read-back / paging (for device-timed benchmarking of the kernel) */
+int tvk_raycast_only(tvk_ctx* ctx);
+/* GLFrameCapture read-back of GetLastFBO() (GLFrameCapture.cpp:72-85): bottom row first.
+ * pitch in bytes, 0 = tight.  dst is host memory. */
+int tvk_read_rgba8(tvk_ctx* ctx, uint8_t* dst, size_t pitch);
+int tvk_read_rgba32f(tvk_ctx* ctx, float* dst, size_t pitch);
+/* device pointer of the RGBA32F result (width*height float4, premultiplied) for zero-copy
+ * consumers such as the sort-last compositor */
+int tvk_get_device_image(tvk_ctx* ctx, void** dptr);
+/* iso mode parity taps: rayHitPos / rayHitNormal MRTs */
+int tvk_read_iso_buffers(tvk_ctx* ctx, float* hit_pos, float* hit_normal);
+
+/* ---- sort-last compositing (new) --------------------------------------- */
+/* out = front + (1-front.a)*back on n_pixels premultiplied RGBA32F device pixels
+ * (Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153). out may alias front or back. */
+int tvk_composite_over(tvk_ctx* ctx, const void* front, const void* back, void* out, uint64_t n_pixels);
+/* float -> unorm8 (GL read-back conversion) on device buffers */
+int tvk_quantize_rgba8(tvk_ctx* ctx, const void* rgba32f, void* rgba8, uint64_t n_pixels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVK_H */

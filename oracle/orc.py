@@ -117,7 +117,7 @@ def lib():
         "orc_pool_slot_count": (C.c_uint32, [P]),
         "orc_pool_slots": (None, [P, P, P, P]),
         "orc_ray_setup": (None, [C.POINTER(RenderParams), P, P, P]),
-        "orc_raycast": (None, [C.POINTER(RenderParams)] + [P] * 11 + [C.POINTER(RenderStats), C.c_int]),
+        "orc_raycast": (None, [C.POINTER(RenderParams)] + [P] * 12 + [C.POINTER(RenderStats), C.c_int]),
         "orc_iso_compose": (None, [C.POINTER(RenderParams), P, P, P]),
         "orc_hash_decode": (C.c_uint32, [P, C.c_uint32, u32x3, P]),
         "orc_rgba8": (None, [P, C.c_uint64, P]),

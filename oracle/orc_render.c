@@ -29,6 +29,8 @@
  *   - pow(x, 8) = ((x*x)^2)^2; pow(x, oc) is the identity for oc == 1, powf otherwise
  *   - unorm texels are filtered as raw integers and scaled once by 1/(2^bits-1)
  *   - x / normToPoolScale is evaluated as x * (1/normToPoolScale)
+ *   - gradient taps (centre +- sampleDelta, sampleDelta = one pool texel) are taken at texel
+ *     index +-1 with the centre sample's filter fractions
  *   - entry/exit positions come from an analytic ray/box slab test at the pixel
  *     centre instead of rasterised bounding-box faces
  */
@@ -243,20 +245,22 @@ static inline float texel(const ctx_t* c, int x, int y, int z) {
   }
 }
 
-/* texture(volumePool, coords).r -- GL_LINEAR, clamp-to-edge (GLVolumePool.cpp:637-639) */
-static float sample_pool(const ctx_t* c, v3 tc) {
+/* texture(volumePool, coords + (dx,dy,dz)*sampleDelta).r -- GL_LINEAR, clamp-to-edge
+ * (GLVolumePool.cpp:637-639).  sampleDelta = 1/poolSize is exactly one texel, so the offset
+ * is applied to the texel index and the filter fractions of the centre are reused. */
+static float sample_pool_off(const ctx_t* c, v3 tc, int dx, int dy, int dz) {
   const uni* u = c->u;
   if (c->p->nearest) {
     int x = (int)floorf(tc.x * u->pool_size_f.x), y = (int)floorf(tc.y * u->pool_size_f.y),
         z = (int)floorf(tc.z * u->pool_size_f.z);
-    return texel(c, x, y, z) * u->norm;
+    return texel(c, x + dx, y + dy, z + dz) * u->norm;
   }
   float ux = fmaf(tc.x, u->pool_size_f.x, -0.5f);
   float uy = fmaf(tc.y, u->pool_size_f.y, -0.5f);
   float uz = fmaf(tc.z, u->pool_size_f.z, -0.5f);
   float fx0 = floorf(ux), fy0 = floorf(uy), fz0 = floorf(uz);
   float fx = ux - fx0, fy = uy - fy0, fz = uz - fz0;
-  int x = (int)fx0, y = (int)fy0, z = (int)fz0;
+  int x = (int)fx0 + dx, y = (int)fy0 + dy, z = (int)fz0 + dz;
   float v000 = texel(c, x, y, z), v100 = texel(c, x + 1, y, z);
   float v010 = texel(c, x, y + 1, z), v110 = texel(c, x + 1, y + 1, z);
   float v001 = texel(c, x, y, z + 1), v101 = texel(c, x + 1, y, z + 1);
@@ -270,14 +274,17 @@ static float sample_pool(const ctx_t* c, v3 tc) {
   return fmaf(fz, c1 - c0, c0) * u->norm;
 }
 
+static float sample_pool(const ctx_t* c, v3 tc) { return sample_pool_off(c, tc, 0, 0, 0); }
+
 /* GLGridLeaper-GradientTools.glsl:6-16 (note the y taps: "Yp" is fetched at -delta) */
 static v3 gradient(const ctx_t* c, v3 ctr, v3 delta) {
-  float xp = sample_pool(c, V3(ctr.x + delta.x, ctr.y, ctr.z));
-  float xm = sample_pool(c, V3(ctr.x - delta.x, ctr.y, ctr.z));
-  float yp = sample_pool(c, V3(ctr.x, ctr.y - delta.y, ctr.z));
-  float ym = sample_pool(c, V3(ctr.x, ctr.y + delta.y, ctr.z));
-  float zp = sample_pool(c, V3(ctr.x, ctr.y, ctr.z + delta.z));
-  float zm = sample_pool(c, V3(ctr.x, ctr.y, ctr.z - delta.z));
+  (void)delta;
+  float xp = sample_pool_off(c, ctr, +1, 0, 0);
+  float xm = sample_pool_off(c, ctr, -1, 0, 0);
+  float yp = sample_pool_off(c, ctr, 0, -1, 0);
+  float ym = sample_pool_off(c, ctr, 0, +1, 0);
+  float zp = sample_pool_off(c, ctr, 0, 0, +1);
+  float zm = sample_pool_off(c, ctr, 0, 0, -1);
   return V3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
 }
 

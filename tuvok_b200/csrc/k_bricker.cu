@@ -1,0 +1,247 @@
+// k_bricker.cu -- device-side data producer: seeded synthetic volumes, the 2x2x2 LOD pyramid,
+// brick cutting with ghost cells and per-brick min/max.  Bit-exact with the reference converter
+// (checked against the reference's own ExtendedOctreeConverter through oracle/_ref/ref_octree).
+// Replaces (reference file:line):
+//   ExtendedOctreeConverter::GetInputBrick / ClampToEdge   ExtendedOctreeConverter.cpp:288-462
+//   DownsampleBricktoBrick / DownsampleBrick               ExtendedOctreeConverter.inc:1-356
+//   VolumeTools::Filter (mean: sum as double / n, truncating cast)  VolumeTools.h:168-262
+//   FillOverlap                                            ExtendedOctreeConverter.cpp:1203-1380
+//   ComputeBrickStats / BrickStat                          ExtendedOctreeConverter.inc:408-444, .cpp:954-1000
+//   MaxMinDataBlock::SetDataFromFlatVector                 IO/UVF/MaxMinDataBlock.cpp:175-195
+// HBM-bound integer work: coalesced x-fastest reads/writes, one CTA per brick.
+#include <cfloat>
+#include "tvk_dev.h"
+
+namespace tvk {
+namespace {
+
+constexpr int kSMs = 148;
+
+// ---------------------------------------------------------------------------------------------
+// synthetic volumes -- integer arithmetic only, so tuvok_b200/synth.py reproduces them bit for bit
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x, uint32_t y, uint32_t z, uint32_t seed) {
+  uint32_t h = seed ^ (x * 0x9E3779B1u) ^ (y * 0x85EBCA77u) ^ (z * 0xC2B2AE3Du);
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+
+__device__ __forceinline__ uint64_t lattice_noise(uint32_t x, uint32_t y, uint32_t z, uint32_t shift, uint32_t seed) {
+  const uint32_t ix = x >> shift, iy = y >> shift, iz = z >> shift;
+  const uint64_t one = 1ull << shift, m = one - 1;
+  const uint64_t fx = x & m, fy = y & m, fz = z & m;
+  uint64_t acc = 0;
+#pragma unroll
+  for (uint32_t dz = 0; dz < 2; dz++)
+#pragma unroll
+    for (uint32_t dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (uint32_t dx = 0; dx < 2; dx++) {
+        const uint64_t v = hash32(ix + dx, iy + dy, iz + dz, seed) >> 16;
+        const uint64_t w = (dx ? fx : one - fx) * (dy ? fy : one - fy) * (dz ? fz : one - fz);
+        acc += v * w;
+      }
+  return acc >> (3 * shift);   // 0..65535
+}
+
+__device__ __forceinline__ uint32_t synth_u16(int kind, uint32_t x, uint32_t y, uint32_t z, uint32_t nx, uint32_t ny,
+                                              uint32_t nz, uint32_t shift0, uint32_t seed) {
+  if (kind == 2) return (x + 8u * y + 64u * z) & 0xFFFFu;
+  const int64_t cx = 2 * (int64_t)x + 1 - nx, cy = 2 * (int64_t)y + 1 - ny, cz = 2 * (int64_t)z + 1 - nz;
+  const uint64_t ax = (uint64_t)(cx < 0 ? -cx : cx) * 4096u / nx;
+  const uint64_t ay = (uint64_t)(cy < 0 ? -cy : cy) * 4096u / ny;
+  const uint64_t az = (uint64_t)(cz < 0 ? -cz : cz) * 4096u / nz;
+  const uint64_t d2 = ax * ax + ay * ay + az * az;
+  const uint64_t R2 = 13589545ull;   // (0.9 * 4096)^2
+  if (d2 >= R2) return 0;
+  const uint64_t w = ((R2 - d2) << 16) / R2;   // 0..65536 falloff
+  if (kind == 0) {
+    const uint64_t t = (d2 << 16) / R2;         // 0..65535
+    const int64_t ph = (int64_t)((t * 3) & 0xFFFFu) - 32768;
+    const uint64_t tri = (uint64_t)(ph < 0 ? -ph : ph) * 2;   // 0..65536
+    uint64_t v = (w * tri) >> 16;
+    return (uint32_t)(v > 65535 ? 65535 : v);
+  }
+  uint64_t sum = 0;
+#pragma unroll
+  for (uint32_t o = 0; o < 4; o++) {
+    const uint32_t s = shift0 > o ? shift0 - o : 0;
+    sum += lattice_noise(x, y, z, s, seed + o) >> o;
+  }
+  const uint64_t noise = sum * 8 / 15;          // 0..65535
+  const uint64_t v = (noise * w) >> 16;
+  const uint64_t t0 = 14000;
+  if (v <= t0) return 0;
+  const uint64_t r = (v - t0) * 2;
+  return (uint32_t)(r > 65535 ? 65535 : r);
+}
+
+template <typename T> __device__ __forceinline__ T from_u16(uint32_t v);
+template <> __device__ __forceinline__ uint8_t from_u16<uint8_t>(uint32_t v) { return (uint8_t)(v >> 8); }
+template <> __device__ __forceinline__ uint16_t from_u16<uint16_t>(uint32_t v) { return (uint16_t)v; }
+template <> __device__ __forceinline__ float from_u16<float>(uint32_t v) { return (float)v / 65535.0f; }
+
+template <typename T>
+__global__ void synth_kernel(T* dst, int kind, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t shift0, uint32_t seed) {
+  const uint64_t n = (uint64_t)nx * ny * nz;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t x = (uint32_t)(i % nx), y = (uint32_t)((i / nx) % ny), z = (uint32_t)(i / ((uint64_t)nx * ny));
+    dst[i] = from_u16<T>(synth_u16(kind, x, y, z, nx, ny, nz, shift0, seed));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LOD pyramid: voxel of LOD l+1 = Filter over the existing voxels of the 2x2x2 block of LOD l
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void downsample_kernel(const T* __restrict__ src, uint32_t sx, uint32_t sy, uint32_t sz, T* dst,
+                                  uint32_t dx_, uint32_t dy_, uint32_t dz_) {
+  const uint64_t n = (uint64_t)dx_ * dy_ * dz_;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t x = (uint32_t)(i % dx_), y = (uint32_t)((i / dx_) % dy_), z = (uint32_t)(i / ((uint64_t)dx_ * dy_));
+    // axes of size 1 are not halved
+    const uint32_t bx = sx > 1 ? 2 * x : x, by = sy > 1 ? 2 * y : y, bz = sz > 1 ? 2 * z : z;
+    const uint32_t nx = (sx > 1 && bx + 1 < sx) ? 2 : 1;
+    const uint32_t ny = (sy > 1 && by + 1 < sy) ? 2 : 1;
+    const uint32_t nz = (sz > 1 && bz + 1 < sz) ? 2 : 1;
+    double s = 0.0;
+    T first = 0;
+    int cnt = 0;
+    for (uint32_t a = 0; a < nx; a++)        // p0..p7 order of the reference: x-major, z-minor
+      for (uint32_t b = 0; b < ny; b++)
+        for (uint32_t c = 0; c < nz; c++) {
+          const T v = src[(uint64_t)(bx + a) + (uint64_t)sx * ((by + b) + (uint64_t)sy * (bz + c))];
+          if (cnt == 0) { first = v; s = (double)v; } else s = s + (double)v;
+          cnt++;
+        }
+    dst[i] = cnt == 1 ? first : (T)(s / (double)cnt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// brick cutting + stats
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ vol, T* store, double* minmax,
+                                                         const CutConsts C, uint64_t slot_voxels) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t bx = b % C.layout[0], by = (b / C.layout[0]) % C.layout[1], bz = b / (C.layout[0] * C.layout[1]);
+  const uint32_t bc[3] = {bx, by, bz};
+  uint32_t bs[3];
+  bool lo_border[3], hi_border[3];
+  const int ov = (int)C.overlap;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {   // ExtendedOctree::ComputeBrickSize (ExtendedOctree.cpp:276-285)
+    const uint32_t core = C.brick[i] - 2 * C.overlap;
+    const bool last = bc[i] == C.layout[i] - 1;
+    const uint32_t rem = C.lod_size[i] % core;
+    bs[i] = (last && rem) ? 2 * C.overlap + rem : C.brick[i];
+    lo_border[i] = bc[i] == 0;
+    hi_border[i] = last;
+  }
+  const int64_t org[3] = {(int64_t)bx * (C.brick[0] - 2 * ov) - ov, (int64_t)by * (C.brick[1] - 2 * ov) - ov,
+                          (int64_t)bz * (C.brick[2] - 2 * ov) - ov};
+  T* dst = store + (uint64_t)(C.first_brick + b) * slot_voxels;
+  const uint32_t n = bs[0] * bs[1] * bs[2];
+  T mn = 0, mx = 0;
+  bool any = false;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    int l[3] = {(int)(i % bs[0]), (int)((i / bs[0]) % bs[1]), (int)(i / (bs[0] * bs[1]))};
+    const uint32_t di = (uint32_t)l[0] + C.brick[0] * ((uint32_t)l[1] + C.brick[1] * (uint32_t)l[2]);
+    int g[3];   // ghost class per axis: -1 low ghost, 0 inner, +1 high ghost
+    bool outside = false;
+    int64_t gc[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      g[a] = l[a] < ov ? -1 : l[a] >= (int)bs[a] - ov ? 1 : 0;
+      if (C.clamp) {   // ClampToEdge on the domain-border sides replicates the first/last inner plane
+        if (g[a] < 0 && lo_border[a]) { l[a] = ov; g[a] = 0; }
+        if (g[a] > 0 && hi_border[a]) { l[a] = (int)bs[a] - 1 - ov; g[a] = 0; }
+      }
+      gc[a] = org[a] + l[a];
+      if (gc[a] < 0 || gc[a] >= (int64_t)C.lod_size[a]) outside = true;
+    }
+    T v = 0;
+    // FillOverlap's copy order leaves three ghost corners of every LOD>=1 brick holding the still
+    // unfilled ghost of a later brick: (right,bottom,front), (right,top,back), (left,bottom,back)
+    const bool stale = C.lod > 0 && ((g[0] == 1 && g[1] == 1 && g[2] == -1) || (g[0] == 1 && g[1] == -1 && g[2] == 1) ||
+                                     (g[0] == -1 && g[1] == 1 && g[2] == 1));
+    if (!outside && !stale)
+      v = vol[(uint64_t)gc[0] + (uint64_t)C.lod_size[0] * ((uint64_t)gc[1] + (uint64_t)C.lod_size[1] * (uint64_t)gc[2])];
+    dst[di] = v;
+    if (!any) { mn = mx = v; any = true; }
+    else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+  }
+  // block min/max (every stored voxel incl. ghost)
+  __shared__ T s_mn[8], s_mx[8];
+  __shared__ int s_any[8];
+  const unsigned full = 0xffffffffu;
+  for (int o = 16; o > 0; o >>= 1) {
+    const T omn = __shfl_down_sync(full, mn, o), omx = __shfl_down_sync(full, mx, o);
+    const int oany = __shfl_down_sync(full, (int)any, o);
+    if (oany) {
+      if (!any) { mn = omn; mx = omx; any = true; }
+      else { mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx; }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; s_any[warp] = any; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool have = false;
+    T a = 0, c = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+      if (!s_any[w]) continue;
+      if (!have) { a = s_mn[w]; c = s_mx[w]; have = true; }
+      else { a = s_mn[w] < a ? s_mn[w] : a; c = s_mx[w] > c ? s_mx[w] : c; }
+    }
+    double* o = minmax + 4 * (uint64_t)(C.first_brick + b);
+    o[0] = (double)a; o[1] = (double)c; o[2] = -DBL_MAX; o[3] = DBL_MAX;
+  }
+}
+
+inline int grid_for(uint64_t n, int block) {
+  uint64_t g = (n + block - 1) / block;
+  const uint64_t cap = (uint64_t)kSMs * 16;
+  return (int)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+}  // namespace
+
+void launch_synth(void* dst, int kind, const uint32_t size[3], int dtype, uint32_t seed, cudaStream_t s) {
+  const uint64_t n = (uint64_t)size[0] * size[1] * size[2];
+  uint32_t mx = size[0] > size[1] ? size[0] : size[1];
+  mx = mx > size[2] ? mx : size[2];
+  uint32_t lg = 0;
+  while ((2u << lg) <= mx) lg++;          // floor(log2(max size))
+  const uint32_t shift0 = lg > 3 ? lg - 3 : 0;
+  const int g = grid_for(n, 256);
+  switch (dtype) {
+    case TVK_U8: synth_kernel<uint8_t><<<g, 256, 0, s>>>((uint8_t*)dst, kind, size[0], size[1], size[2], shift0, seed); break;
+    case TVK_U16: synth_kernel<uint16_t><<<g, 256, 0, s>>>((uint16_t*)dst, kind, size[0], size[1], size[2], shift0, seed); break;
+    default: synth_kernel<float><<<g, 256, 0, s>>>((float*)dst, kind, size[0], size[1], size[2], shift0, seed); break;
+  }
+}
+
+void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const uint32_t ds[3], int dtype,
+                       cudaStream_t s) {
+  const uint64_t n = (uint64_t)ds[0] * ds[1] * ds[2];
+  const int g = grid_for(n, 256);
+  switch (dtype) {
+    case TVK_U8: downsample_kernel<uint8_t><<<g, 256, 0, s>>>((const uint8_t*)src, ss[0], ss[1], ss[2], (uint8_t*)dst, ds[0], ds[1], ds[2]); break;
+    case TVK_U16: downsample_kernel<uint16_t><<<g, 256, 0, s>>>((const uint16_t*)src, ss[0], ss[1], ss[2], (uint16_t*)dst, ds[0], ds[1], ds[2]); break;
+    default: downsample_kernel<float><<<g, 256, 0, s>>>((const float*)src, ss[0], ss[1], ss[2], (float*)dst, ds[0], ds[1], ds[2]); break;
+  }
+}
+
+void launch_cut_bricks(const void* lod_vol, void* store, double* minmax, const CutConsts& cc, int dtype,
+                       uint64_t slot_bytes, cudaStream_t s) {
+  const uint32_t n = cc.layout[0] * cc.layout[1] * cc.layout[2];
+  switch (dtype) {
+    case TVK_U8: cut_bricks_kernel<uint8_t><<<n, 256, 0, s>>>((const uint8_t*)lod_vol, (uint8_t*)store, minmax, cc, slot_bytes); break;
+    case TVK_U16: cut_bricks_kernel<uint16_t><<<n, 256, 0, s>>>((const uint16_t*)lod_vol, (uint16_t*)store, minmax, cc, slot_bytes / 2); break;
+    default: cut_bricks_kernel<float><<<n, 256, 0, s>>>((const float*)lod_vol, (float*)store, minmax, cc, slot_bytes / 4); break;
+  }
+}
+
+}  // namespace tvk

@@ -1,0 +1,93 @@
+// k_image.cu -- image-space kernels: deferred isosurface shading, the GL float->unorm8 read-back
+// conversion and the over operator of the sort-last compositor.  HBM-bound streaming kernels:
+// 128-bit accesses, grid sized to a multiple of the 148 SMs with a grid-stride loop.
+// Replaces (reference file:line): Shaders/Compose-FS.glsl:49-76 + GLRenderer::ComposeSurfaceImage
+// (GLRenderer.cpp:2763-2830); GLFrameCapture.cpp:72-85 (glReadPixels GL_UNSIGNED_BYTE);
+// Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153.
+// Compiled with -fmad=false (same arithmetic contract as k_raycast.cu).
+#include "tvk_dev.h"
+
+namespace tvk {
+namespace {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+__device__ __forceinline__ float pow8(float x) { float a = x * x; float b = a * a; return b * b; }
+
+struct ComposeConsts { float amb[3], dif[3], spe[3], ldir[3]; };
+
+__global__ void iso_compose_kernel(const float4* __restrict__ hit_pos, const float4* __restrict__ hit_nrm,
+                                   float4* __restrict__ rgba, uint64_t n, const ComposeConsts C) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 hp = hit_pos[i];
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hp.w != 0.0f) {   // `discard` leaves the cleared texel
+      const float4 hn = hit_nrm[i];
+      const float nx = hn.x, ny = hn.y, nz = fabsf(hn.z);
+      float vx = 0.0f - hp.x, vy = 0.0f - hp.y, vz = 0.0f - hp.z;
+      float inv = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);
+      vx = vx * inv; vy = vy * inv; vz = vz * inv;
+      const float dn = nx * vx + ny * vy + nz * vz;
+      const float k = 2.0f * dn;
+      float rx = vx - nx * k, ry = vy - ny * k, rz = vz - nz * k;
+      inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
+      rx = rx * inv; ry = ry * inv; rz = rz * inv;
+      const float dl = fmaxf(fabsf(nx * (-C.ldir[0]) + ny * (-C.ldir[1]) + nz * (-C.ldir[2])), 0.0f);
+      const float sp = pow8(fmaxf(rx * C.ldir[0] + ry * C.ldir[1] + rz * C.ldir[2], 0.0f));
+      o.x = clamp01(C.amb[0] + C.dif[0] * dl + C.spe[0] * sp);
+      o.y = clamp01(C.amb[1] + C.dif[1] * dl + C.spe[1] * sp);
+      o.z = clamp01(C.amb[2] + C.dif[2] * dl + C.spe[2] * sp);
+      o.w = 1.0f;
+    }
+    rgba[i] = o;
+  }
+}
+
+__device__ __forceinline__ unsigned char unorm8(float v) {
+  v = v < 0.0f ? 0.0f : v > 1.0f ? 1.0f : v;
+  if (v != v) v = 0.0f;
+  return (unsigned char)(v * 255.0f + 0.5f);
+}
+
+__global__ void quantize_kernel(const float4* __restrict__ src, uchar4* __restrict__ dst, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = make_uchar4(unorm8(v.x), unorm8(v.y), unorm8(v.z), unorm8(v.w));
+  }
+}
+
+__global__ void over_kernel(const float4* front, const float4* back, float4* out, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 f = front[i], b = back[i];
+    const float oma = 1.0f - f.w;
+    out[i] = make_float4(f.x + oma * b.x, f.y + oma * b.y, f.z + oma * b.z, f.w + oma * b.w);
+  }
+}
+
+inline int grid_for(uint64_t n, int block) {
+  uint64_t g = (n + block - 1) / block;
+  const uint64_t cap = (uint64_t)kSMs * 8;   // 8 resident 256-thread CTAs per SM
+  return (int)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+}  // namespace
+
+void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rgba, uint32_t w, uint32_t h,
+                        const float amb[3], const float dif[3], const float spe[3], const float ldir[3],
+                        cudaStream_t s) {
+  ComposeConsts C;
+  for (int i = 0; i < 3; i++) { C.amb[i] = amb[i]; C.dif[i] = dif[i]; C.spe[i] = spe[i]; C.ldir[i] = ldir[i]; }
+  const uint64_t n = (uint64_t)w * h;
+  iso_compose_kernel<<<grid_for(n, 256), 256, 0, s>>>(hit_pos, hit_nrm, rgba, n, C);
+}
+
+void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s) {
+  quantize_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
+}
+
+void launch_composite_over(const float4* front, const float4* back, float4* out, uint64_t n, cudaStream_t s) {
+  over_kernel<<<grid_for(n, 256), 256, 0, s>>>(front, back, out, n);
+}
+
+}  // namespace tvk

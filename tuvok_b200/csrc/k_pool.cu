@@ -1,0 +1,182 @@
+// k_pool.cu -- page-table kernels: min/max-driven brick visibility (bit-exact with the reference's
+// CPU pass), page-table patches, brick paging into the slot-linear pool, miss-list compaction.
+// Replaces (reference file:line):
+//   ContainsData<mode>                 Renderer/GL/GLVolumePool.cpp:962-989
+//   RecomputeVisibilityForBrickPool    GLVolumePool.cpp:991-1018
+//   RecomputeVisibilityForOctree       GLVolumePool.cpp:1020-1359 (one launch per level: a level
+//                                      only reads the finished table of the level below)
+//   UploadMetadataTexel / UploadBrick  GLVolumePool.cpp:673-717,944-953 (batched per subframe)
+//   GLHashTable::GetData               Renderer/GL/GLHashTable.cpp:90-105 (device-side compaction
+//                                      instead of reading back the whole table)
+// All integer / fp64-compare work; HBM-bound, coalesced, grid-stride.
+#include "tvk_dev.h"
+
+namespace tvk {
+namespace {
+
+constexpr int kSMs = 148;
+inline int grid_for(uint64_t n, int block, int per_sm = 8) {
+  uint64_t g = (n + block - 1) / block;
+  const uint64_t cap = (uint64_t)kSMs * per_sm;
+  return (int)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+__device__ __forceinline__ bool contains(const VisConsts& V, const double* __restrict__ mm, uint32_t id) {
+  const double smin = mm[4 * (size_t)id + 0], smax = mm[4 * (size_t)id + 1];
+  switch (V.mode) {
+    case TVK_RM_1DTRANS: return V.v[1] >= smin && V.v[0] <= smax;
+    case TVK_RM_2DTRANS: {
+      const double gmin = mm[4 * (size_t)id + 2], gmax = mm[4 * (size_t)id + 3];
+      return (V.v[1] >= smin && V.v[0] <= smax) && (V.v[3] >= gmin && V.v[2] <= gmax);
+    }
+    default: return V.v[0] >= smin && V.v[0] <= smax;
+  }
+}
+
+__global__ void vis_clear_kernel(uint32_t* meta, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    meta[i] = TVK_BI_MISSING;
+}
+
+// resident bricks: slot+3 when visible, BI_EMPTY otherwise (slot index == linear pool coordinate)
+__global__ void vis_pool_kernel(uint32_t* meta, const int32_t* __restrict__ slot_brick, uint32_t n_slots,
+                                const double* __restrict__ mm, const VisConsts V) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+    const int32_t id = slot_brick[s];
+    if (id < 0) continue;
+    meta[id] = contains(V, mm, (uint32_t)id) ? s + TVK_BI_FLAG_COUNT : (uint32_t)TVK_BI_EMPTY;
+  }
+}
+
+// counts: 0 total, 1 empty, 2 childEmpty, 3 emptyLeaf
+__global__ void vis_level_kernel(uint32_t* meta, const double* __restrict__ mm, const VisConsts V, uint32_t lod,
+                                 uint32_t* counts) {
+  const uint32_t lx = V.layout[lod][0], ly = V.layout[lod][1], lz = V.layout[lod][2];
+  const uint32_t n = lx * ly * lz;
+  uint32_t c_empty = 0, c_child = 0, c_leaf = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t id = V.lod_offset[lod] + i;
+    if (meta[id] >= TVK_BI_FLAG_COUNT) continue;
+    if (contains(V, mm, id)) continue;
+    if (lod == 0) {
+      meta[id] = TVK_BI_CHILD_EMPTY;
+      c_leaf++;
+      continue;
+    }
+    const uint32_t x = i % lx, y = (i / lx) % ly, z = i / (lx * ly);
+    const uint32_t cx = V.layout[lod - 1][0], cy = V.layout[lod - 1][1], cz = V.layout[lod - 1][2];
+    bool all_child_empty = true;
+    for (uint32_t dz = 0; dz < 2; dz++)
+      for (uint32_t dy = 0; dy < 2; dy++)
+        for (uint32_t dx = 0; dx < 2; dx++) {
+          const uint32_t px = 2 * x + dx, py = 2 * y + dy, pz = 2 * z + dz;
+          if (px >= cx || py >= cy || pz >= cz) continue;   // odd layouts: missing children do not count
+          if (meta[V.lod_offset[lod - 1] + px + py * cx + pz * cx * cy] != TVK_BI_CHILD_EMPTY) all_child_empty = false;
+        }
+    if (all_child_empty) { meta[id] = TVK_BI_CHILD_EMPTY; c_child++; }
+    else { meta[id] = TVK_BI_EMPTY; c_empty++; }
+  }
+  // warp-aggregated counters
+  for (int o = 16; o > 0; o >>= 1) {
+    c_empty += __shfl_down_sync(0xffffffffu, c_empty, o);
+    c_child += __shfl_down_sync(0xffffffffu, c_child, o);
+    c_leaf += __shfl_down_sync(0xffffffffu, c_leaf, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c_empty) atomicAdd(counts + 1, c_empty);
+    if (c_child) atomicAdd(counts + 2, c_child);
+    if (c_leaf) atomicAdd(counts + 3, c_leaf);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counts + 0, n);
+}
+
+// final page-table values of the entries touched by one paging batch: ops[i].new_id <- ops[i].slot
+// (evict_id is used as "value" here: see host) -- plain scatter of (index, value) pairs
+__global__ void page_meta_kernel(uint32_t* meta, const PageOp* __restrict__ ops, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    meta[ops[i].new_id] = ops[i].slot;
+}
+
+// one CTA per paged brick: copy the brick (own size, x fastest) into its slot (strides of the max
+// brick size).  16-byte vector path when source and slot rows line up (full-size bricks).
+__global__ void page_copy_kernel(unsigned char* pool, const unsigned char* __restrict__ store,
+                                 const PageOp* __restrict__ ops, uint64_t slot_bytes, uint32_t esize,
+                                 uint32_t tx, uint32_t ty, uint32_t tz, int src_is_slot_layout) {
+  const PageOp op = ops[blockIdx.x];
+  unsigned char* dst = pool + (uint64_t)op.slot * slot_bytes;
+  const unsigned char* src = store + op.src_off;
+  const bool full = src_is_slot_layout || (op.size[0] == tx && op.size[1] == ty);
+  if (full) {
+    const uint64_t bytes = src_is_slot_layout ? slot_bytes : (uint64_t)op.size[0] * op.size[1] * op.size[2] * esize;
+    if (((uintptr_t)dst & 15) == 0 && ((uintptr_t)src & 15) == 0) {
+      const uint64_t n16 = bytes / 16;
+      const uint4* s4 = (const uint4*)src;
+      uint4* d4 = (uint4*)dst;
+      for (uint64_t i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+      for (uint64_t i = n16 * 16 + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+    } else {
+      for (uint64_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+    }
+    return;
+  }
+  const uint32_t row = op.size[0] * esize;
+  const uint32_t rows = op.size[1] * op.size[2];
+  for (uint32_t r = threadIdx.x / 32; r < rows; r += blockDim.x / 32) {
+    const uint32_t y = r % op.size[1], z = r / op.size[1];
+    const unsigned char* s = src + (uint64_t)r * row;
+    unsigned char* d = dst + ((uint64_t)z * ty + y) * tx * esize;
+    for (uint32_t b = threadIdx.x % 32; b < row; b += 32) d[b] = s[b];
+  }
+}
+
+// GLHashTable::GetData: gather the non-zero entries as (table index, value) pairs (the host orders
+// them by index = the reference's scan order).  Warp-aggregated append.
+__global__ void hash_compact_kernel(const uint32_t* __restrict__ hash, uint32_t n, uint32_t* out, uint32_t* count) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (n + stride - 1) / stride;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t r = 0; r < rounds; r++, i += stride) {
+    const uint32_t e = i < n ? hash[i] : 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, e != 0);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (e) {
+        const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
+        out[2 * k] = i;
+        out[2 * k + 1] = e;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void launch_vis_clear(uint32_t* meta, uint64_t n, cudaStream_t s) {
+  vis_clear_kernel<<<grid_for(n, 256), 256, 0, s>>>(meta, n);
+}
+void launch_vis_pool(uint32_t* meta, const int32_t* slot_brick, uint32_t n_slots, const double* minmax,
+                     const VisConsts& vc, cudaStream_t s) {
+  vis_pool_kernel<<<grid_for(n_slots, 256), 256, 0, s>>>(meta, slot_brick, n_slots, minmax, vc);
+}
+void launch_vis_level(uint32_t* meta, const double* minmax, const VisConsts& vc, uint32_t lod, uint32_t* counts,
+                      cudaStream_t s) {
+  const uint64_t n = (uint64_t)vc.layout[lod][0] * vc.layout[lod][1] * vc.layout[lod][2];
+  vis_level_kernel<<<grid_for(n, 256), 256, 0, s>>>(meta, minmax, vc, lod, counts);
+}
+void launch_page_meta(uint32_t* meta, const PageOp* ops, uint32_t n, cudaStream_t s) {
+  if (n) page_meta_kernel<<<grid_for(n, 256), 256, 0, s>>>(meta, ops, n);
+}
+void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t n, uint64_t slot_bytes,
+                      uint32_t esize, const uint32_t total[3], int src_is_slot_layout, cudaStream_t s) {
+  if (n)
+    page_copy_kernel<<<n, 256, 0, s>>>((unsigned char*)pool, (const unsigned char*)store, ops, slot_bytes, esize,
+                                       total[0], total[1], total[2], src_is_slot_layout);
+}
+void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s) {
+  hash_compact_kernel<<<grid_for(n, 256), 256, 0, s>>>(hash, n, out_list, out_count);
+}
+
+}  // namespace tvk

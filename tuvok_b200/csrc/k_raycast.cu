@@ -1,0 +1,581 @@
+// k_raycast.cu -- the GridLeaper traversal kernel for sm_100a.
+//
+// One thread = one ray (one fragment of GLGridLeaper-blend.glsl / -iso.glsl main()); a warp is
+// an 8x4 pixel tile so neighbouring rays walk the same bricks and share cache lines.  Replaces
+// (reference file:line):
+//   ray entry/exit     GLGridLeaper.cpp:560-620, GLGridLeaper-NearPlane-VS.glsl:9-14,
+//                      GLGridLeaper-entry-VS.glsl:10-14, GLGridLeaper-frontfaces-FS.glsl:6-8
+//   main() DVR / ISO   Shaders/GLGridLeaper-blend.glsl:65-228, GLGridLeaper-iso.glsl:68-200
+//   page-table walk    generated GLSL, Renderer/GL/GLVolumePool.cpp:484-656
+//   miss reports       generated GLSL, Renderer/GL/GLHashTable.cpp:136-182
+//   classification     GLGridLeaper-Method-{1D,1D-L,2D,2D-L,iso}.glsl, GLGridLeaper-GradientTools.glsl:6-23,
+//                      lighting.glsl:33-43, Compositing.glsl:33-38
+//
+// HBM layout: the pool is SLOT-LINEAR -- slot s (= the reference's linear pool coordinate
+// x + y*capX + z*capX*capY) is one contiguous maxTotalBrickSize^3 block, x fastest -- instead of
+// the reference's 3D-texture atlas.  The shader's pool texture coordinates are kept (virtual
+// atlas of capacity*brick voxels) so the arithmetic stays the reference's; only the final
+// texel address is slot-local.
+//
+// Arithmetic contract: IEEE fp32, no implicit FMA contraction (this file is compiled
+// with -fmad=false); fmaf() exactly where the contract names it (texel-coordinate map and the
+// trilinear lerps).  Gradient taps sit exactly +-1 texel from the centre sample and share its
+// filter fractions (the GLSL adds sampleDelta = 1/poolSize in texture coordinates, i.e. one
+// texel; the precision of that is implementation-defined in GL).
+#include "tvk_dev.h"
+
+namespace tvk {
+namespace {
+
+struct f3 { float x, y, z; };
+struct f4 { float x, y, z, w; };
+__device__ __forceinline__ f3 F3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 F3(const float* p) { return F3(p[0], p[1], p[2]); }
+__device__ __forceinline__ f3 add3(f3 a, f3 b) { return F3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return F3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 mul3(f3 a, f3 b) { return F3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ f3 div3(f3 a, f3 b) { return F3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ f3 scl3(f3 a, float s) { return F3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float len3(f3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ f3 norm3(f3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return scl3(a, inv); }
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// v' = v * M (row vectors, Basics/Vectors.h:434-439)
+__device__ __forceinline__ f4 xform4(const float* m, float x, float y, float z, float w) {
+  f4 r;
+  r.x = x * m[0] + y * m[4] + z * m[8] + w * m[12];
+  r.y = x * m[1] + y * m[5] + z * m[9] + w * m[13];
+  r.z = x * m[2] + y * m[6] + z * m[10] + w * m[14];
+  r.w = x * m[3] + y * m[7] + z * m[11] + w * m[15];
+  return r;
+}
+
+struct BrickRef {
+  f3 pool_entry, pool_exit, norm_exit, scale, trans;
+  bool empty;
+  uint32_t bx, by, bz, bl;
+  uint32_t ox, oy, oz;   // slot origin in virtual-atlas texels
+  uint64_t base;         // first voxel of the slot in the slot-linear pool
+};
+
+template <typename T> __device__ __forceinline__ float ldv(const T* p, uint64_t i) { return (float)__ldg(p + i); }
+
+// filter footprint of one sample position: 4 clamped slot-local indices per axis
+// ([X-1, X, X+1, X+2] as element offsets) and the shared fractions
+struct Foot {
+  uint32_t xo[4], yo[4], zo[4];
+  float fx, fy, fz;
+};
+
+__device__ __forceinline__ uint32_t clampi(int v, int hi) { return (uint32_t)min(max(v, 0), hi); }
+
+__device__ __forceinline__ void footprint(const RayConsts& P, const BrickRef& b, f3 tc, Foot& f) {
+  int X, Y, Z;
+  if (P.nearest) {
+    X = (int)floorf(tc.x * P.pool_size_f[0]);
+    Y = (int)floorf(tc.y * P.pool_size_f[1]);
+    Z = (int)floorf(tc.z * P.pool_size_f[2]);
+    f.fx = f.fy = f.fz = 0.0f;
+  } else {
+    float ux = fmaf(tc.x, P.pool_size_f[0], -0.5f);
+    float uy = fmaf(tc.y, P.pool_size_f[1], -0.5f);
+    float uz = fmaf(tc.z, P.pool_size_f[2], -0.5f);
+    float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
+    f.fx = ux - x0; f.fy = uy - y0; f.fz = uz - z0;
+    X = (int)x0; Y = (int)y0; Z = (int)z0;
+  }
+  X -= (int)b.ox; Y -= (int)b.oy; Z -= (int)b.oz;
+  const int tx = (int)P.total[0] - 1, ty = (int)P.total[1] - 1, tz = (int)P.total[2] - 1;
+  const uint32_t sy = P.total[0], sz = P.total[0] * P.total[1];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    f.xo[i] = clampi(X - 1 + i, tx);
+    f.yo[i] = clampi(Y - 1 + i, ty) * sy;
+    f.zo[i] = clampi(Z - 1 + i, tz) * sz;
+  }
+}
+
+__device__ __forceinline__ float tri(float v000, float v100, float v010, float v110, float v001, float v101,
+                                     float v011, float v111, float fx, float fy, float fz) {
+  float c00 = fmaf(fx, v100 - v000, v000);
+  float c10 = fmaf(fx, v110 - v010, v010);
+  float c01 = fmaf(fx, v101 - v001, v001);
+  float c11 = fmaf(fx, v111 - v011, v011);
+  float c0 = fmaf(fy, c10 - c00, c00);
+  float c1 = fmaf(fy, c11 - c01, c01);
+  return fmaf(fz, c1 - c0, c0);
+}
+
+// texture(volumePool, coords).r at texel offset (dx,dy,dz) from the footprint centre
+template <typename T>
+__device__ __forceinline__ float tap(const RayConsts& P, const T* vox, const Foot& f, int dx, int dy, int dz) {
+  if (P.nearest) return ldv(vox, (uint64_t)(f.xo[1 + dx] + f.yo[1 + dy] + f.zo[1 + dz])) * P.norm;
+  const uint32_t x0 = f.xo[1 + dx], x1 = f.xo[2 + dx];
+  const uint32_t y0 = f.yo[1 + dy], y1 = f.yo[2 + dy];
+  const uint32_t z0 = f.zo[1 + dz], z1 = f.zo[2 + dz];
+  return tri(ldv(vox, x0 + y0 + z0), ldv(vox, x1 + y0 + z0), ldv(vox, x0 + y1 + z0), ldv(vox, x1 + y1 + z0),
+             ldv(vox, x0 + y0 + z1), ldv(vox, x1 + y0 + z1), ldv(vox, x0 + y1 + z1), ldv(vox, x1 + y1 + z1),
+             f.fx, f.fy, f.fz) * P.norm;
+}
+
+// centre value + central-difference gradient (GLGridLeaper-GradientTools.glsl:6-16; the "Yp"
+// tap is fetched at -delta) from the 32 distinct voxels of the 7 overlapping footprints
+template <typename T>
+__device__ __forceinline__ void sample_with_gradient(const RayConsts& P, const T* vox, const Foot& f,
+                                                     float& data, f3& grad) {
+  if (P.nearest) {
+    data = tap(P, vox, f, 0, 0, 0);
+    float xp = tap(P, vox, f, 1, 0, 0), xm = tap(P, vox, f, -1, 0, 0);
+    float yp = tap(P, vox, f, 0, -1, 0), ym = tap(P, vox, f, 0, 1, 0);
+    float zp = tap(P, vox, f, 0, 0, 1), zm = tap(P, vox, f, 0, 0, -1);
+    grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+    return;
+  }
+  float c[2][2][2];   // [z][y][x] centre block
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int i = 0; i < 2; i++) c[k][j][i] = ldv(vox, f.xo[1 + i] + f.yo[1 + j] + f.zo[1 + k]);
+  float xl[2][2], xh[2][2], yl[2][2], yh[2][2], zl[2][2], zh[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      xl[a][b] = ldv(vox, f.xo[0] + f.yo[1 + b] + f.zo[1 + a]);   // [z][y]
+      xh[a][b] = ldv(vox, f.xo[3] + f.yo[1 + b] + f.zo[1 + a]);
+      yl[a][b] = ldv(vox, f.xo[1 + b] + f.yo[0] + f.zo[1 + a]);   // [z][x]
+      yh[a][b] = ldv(vox, f.xo[1 + b] + f.yo[3] + f.zo[1 + a]);
+      zl[a][b] = ldv(vox, f.xo[1 + b] + f.yo[1 + a] + f.zo[0]);   // [y][x]
+      zh[a][b] = ldv(vox, f.xo[1 + b] + f.yo[1 + a] + f.zo[3]);
+    }
+  const float fx = f.fx, fy = f.fy, fz = f.fz, n = P.norm;
+  data = tri(c[0][0][0], c[0][0][1], c[0][1][0], c[0][1][1], c[1][0][0], c[1][0][1], c[1][1][0], c[1][1][1],
+             fx, fy, fz) * n;
+  float xp = tri(c[0][0][1], xh[0][0], c[0][1][1], xh[0][1], c[1][0][1], xh[1][0], c[1][1][1], xh[1][1], fx, fy, fz) * n;
+  float xm = tri(xl[0][0], c[0][0][0], xl[0][1], c[0][1][0], xl[1][0], c[1][0][0], xl[1][1], c[1][1][0], fx, fy, fz) * n;
+  // +y footprint (fetched by the shader as "Ym"), -y footprint ("Yp")
+  float ym = tri(c[0][1][0], c[0][1][1], yh[0][0], yh[0][1], c[1][1][0], c[1][1][1], yh[1][0], yh[1][1], fx, fy, fz) * n;
+  float yp = tri(yl[0][0], yl[0][1], c[0][0][0], c[0][0][1], yl[1][0], yl[1][1], c[1][0][0], c[1][0][1], fx, fy, fz) * n;
+  float zp = tri(c[1][0][0], c[1][0][1], c[1][1][0], c[1][1][1], zh[0][0], zh[0][1], zh[1][0], zh[1][1], fx, fy, fz) * n;
+  float zm = tri(zl[0][0], zl[0][1], zl[1][0], zl[1][1], c[0][0][0], c[0][0][1], c[0][1][0], c[0][1][1], fx, fy, fz) * n;
+  grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+}
+
+__device__ __forceinline__ float pow8(float x) { float a = x * x; float b = a * a; return b * b; }
+
+// lighting.glsl:33-43
+__device__ __forceinline__ f3 lighting(f3 eye, f3 pos, f3 n, f3 amb, f3 dif, f3 spe, f3 ldir) {
+  f3 view = norm3(sub3(eye, pos));
+  float dn = dot3(n, view);
+  f3 refl = norm3(sub3(view, scl3(n, 2.0f * dn)));
+  float dl = fmaxf(fabsf(dot3(n, ldir)), 0.0f);
+  float sp = pow8(fmaxf(dot3(refl, ldir), 0.0f));
+  return F3(clampf(amb.x + dif.x * dl + spe.x * sp, 0.0f, 1.0f),
+            clampf(amb.y + dif.y * dl + spe.y * sp, 0.0f, 1.0f),
+            clampf(amb.z + dif.z * dl + spe.z * sp, 0.0f, 1.0f));
+}
+
+// RGBA8, GL_NEAREST, clamp-to-edge (GPUMemMan.cpp:398-401, GLTexture1D.h:48-51)
+template <bool SMEM_TF>
+__device__ __forceinline__ f4 tf_lookup(const RayConsts& P, const uchar4* s_tf, float s, float t) {
+  int w = (int)P.tf_w, h = (int)P.tf_h;
+  int ix = (int)floorf(s * (float)w);
+  ix = min(max(ix, 0), w - 1);
+  int iy = 0;
+  if (h > 1) {
+    iy = (int)floorf(t * (float)h);
+    iy = min(max(iy, 0), h - 1);
+  }
+  uchar4 q = SMEM_TF ? s_tf[iy * w + ix] : __ldg(P.tf + (size_t)iy * w + ix);
+  f4 r;
+  r.x = (float)q.x / 255.0f; r.y = (float)q.y / 255.0f; r.z = (float)q.z / 255.0f; r.w = (float)q.w / 255.0f;
+  return r;
+}
+
+__device__ __forceinline__ void brick_coords(const RayConsts& P, f3 pos, uint32_t lod, uint32_t& x, uint32_t& y,
+                                             uint32_t& z) {
+  x = (uint32_t)(pos.x * P.lod_layout[lod][0]);
+  y = (uint32_t)(pos.y * P.lod_layout[lod][1]);
+  z = (uint32_t)(pos.z * P.lod_layout[lod][2]);
+}
+__device__ __forceinline__ uint32_t brick_info(const RayConsts& P, uint32_t x, uint32_t y, uint32_t z, uint32_t lod) {
+  uint32_t idx = P.lod_offset[lod] + x + y * P.lod_layout_sz[lod][0] + z * P.lod_layout_sz[lod][1];
+  return __ldg(P.meta + idx);
+}
+
+// GLHashTable.cpp:140-182.  Rays of a warp that miss the same brick elect one reporter first
+// (warp vote) so the table sees one CAS chain per distinct brick per warp.
+__device__ __forceinline__ void report_missing(const RayConsts& P, uint32_t x, uint32_t y, uint32_t z, uint32_t lod) {
+  if (!P.hash || P.hash_size == 0) return;
+  const uint32_t ser = 1 + x + y * P.finest[0] + z * P.finest[0] * P.finest[1] +
+                       lod * P.finest[0] * P.finest[1] * P.finest[2];
+  const unsigned act = __activemask();
+  const unsigned same = __match_any_sync(act, ser);
+  if ((unsigned)(__ffs(same) - 1) != (threadIdx.x + threadIdx.y * blockDim.x) % 32u) return;
+  uint32_t rehash = 0;
+  do {
+    uint32_t h = (ser + rehash) % P.hash_size;
+    uint32_t old = atomicCAS(P.hash + h, 0u, ser);
+    if (old == 0 || old == ser) return;
+  } while (++rehash < P.rehash_count);
+}
+
+__device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& lod, f3 dir, BrickRef& o,
+                                          unsigned long long& n_bricks) {
+  const uint32_t max_lod = P.lod_count - 1;
+  n_bricks++;
+  pos = F3(clampf(pos.x, 0.0f, 1.0f), clampf(pos.y, 0.0f, 1.0f), clampf(pos.z, 0.0f, 1.0f));
+  bool found = true;
+  uint32_t bx, by, bz;
+  brick_coords(P, pos, lod, bx, by, bz);
+  uint32_t info = brick_info(P, bx, by, bz, lod);
+  if (info == TVK_BI_MISSING) {
+    const uint32_t start = lod;
+    report_missing(P, bx, by, bz, lod);
+    found = false;
+    // the reference loops `do {...} while (brickInfo == BI_MISSING)`: the coarsest brick is always
+    // resident (UploadFirstBrick), so the bound only guards a corrupted table
+    while (info == TVK_BI_MISSING && lod < max_lod) {
+      lod++;
+      brick_coords(P, pos, lod, bx, by, bz);
+      info = brick_info(P, bx, by, bz, lod);
+      if (info == TVK_BI_MISSING) {
+        if (P.strategy == TVK_BS_REQUEST_ALL) report_missing(P, bx, by, bz, lod);
+        else if (P.strategy == TVK_BS_SKIP_ONE_LEVEL && start + 1 == lod) report_missing(P, bx, by, bz, lod);
+        else if (P.strategy == TVK_BS_SKIP_TWO_LEVELS && start + 2 == lod) report_missing(P, bx, by, bz, lod);
+      }
+    }
+  }
+  o.empty = info <= TVK_BI_EMPTY;
+  if (o.empty) {
+    for (uint32_t lo = lod + 1; lo < max_lod; ++lo) {   // strict <, GLVolumePool.cpp:593
+      uint32_t lx, ly, lz;
+      brick_coords(P, pos, lo, lx, ly, lz);
+      uint32_t li = brick_info(P, lx, ly, lz, lo);
+      if (li == TVK_BI_CHILD_EMPTY) { bx = lx; by = ly; bz = lz; info = li; lod = lo; }
+      else break;
+    }
+  }
+  // GetBrickCorners / BrickExit
+  const f3 lay = F3(P.lod_layout[lod]);
+  const f3 c0 = div3(F3((float)bx, (float)by, (float)bz), lay);
+  const f3 c1 = div3(F3((float)(bx + 1), (float)(by + 1), (float)(bz + 1)), lay);
+  const f3 dv = F3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+  float tx = ((dv.x < 0.0f ? c0.x : c1.x) - pos.x) * dv.x;
+  float ty = ((dv.y < 0.0f ? c0.y : c1.y) - pos.y) * dv.y;
+  float tz = ((dv.z < 0.0f ? c0.z : c1.z) - pos.z) * dv.z;
+  float tm = fminf(fminf(tx, ty), tz);
+  o.norm_exit = add3(pos, scl3(dir, tm));
+  o.bx = bx; o.by = by; o.bz = bz; o.bl = lod;
+  if (o.empty) return found;
+  // InfoToCoords / BrickPoolCoords / NormCoordsToPoolCoords
+  const uint32_t index = info - TVK_BI_FLAG_COUNT;
+  const uint32_t sx = index % P.capacity[0], sy = (index / P.capacity[0]) % P.capacity[1],
+                 sz = index / (P.capacity[0] * P.capacity[1]);
+  o.ox = sx * P.total[0]; o.oy = sy * P.total[1]; o.oz = sz * P.total[2];
+  o.base = (uint64_t)index * P.slot_voxels;
+  const f3 ps = F3(P.pool_size_f), ov = F3(P.overlap_tc);
+  const f3 vp = F3((float)o.ox, (float)o.oy, (float)o.oz);
+  const f3 vq = F3((float)(o.ox + P.total[0]), (float)(o.oy + P.total[1]), (float)(o.oz + P.total[2]));
+  const f3 pc0 = add3(div3(vp, ps), ov);
+  const f3 pc1 = sub3(div3(vq, ps), ov);
+  o.scale = div3(sub3(pc1, pc0), sub3(c1, c0));
+  o.trans = sub3(pc0, mul3(c0, o.scale));
+  o.pool_entry = add3(mul3(pos, o.scale), o.trans);
+  o.pool_exit = add3(mul3(o.norm_exit, o.scale), o.trans);
+  return found;
+}
+
+// min(iMaxLOD, uint(log2(fLoDFactor*(-dist)/fLevelZeroWorldSpaceError))); uint(log2 x) = exponent of x
+__device__ __forceinline__ uint32_t compute_lod(const RayConsts& P, float dist) {
+  float x = P.lod_factor * (-dist) / P.lzwse;
+  const uint32_t max_lod = P.lod_count - 1;
+  if (!(x >= 1.0f)) return 0;
+  if (isinf(x)) return max_lod;
+  uint32_t l = ((__float_as_uint(x) >> 23) & 0xffu) - 127u;
+  return min(l, max_lod);
+}
+
+__device__ __forceinline__ float opacity_correct(const RayConsts& P, float a) {
+  if (P.oc == 1.0f) return a;
+  return 1.0f - powf(1.0f - a, P.oc);
+}
+
+// analytic ray/box entry + exit at the pixel centre (what the rasterised bbox front/back faces and
+// the near-plane quad deliver per fragment)
+__device__ __forceinline__ bool ray_setup(const RayConsts& P, uint32_t px, uint32_t py, f4& entry, f4& exit_) {
+  float nx = ((float)px + 0.5f) / (float)P.width * 2.0f - 1.0f;
+  float ny = ((float)py + 0.5f) / (float)P.height * 2.0f - 1.0f;
+  f4 nr = xform4(P.inv_proj, nx, ny, -1.0f, 1.0f);
+  f3 pn = F3(nr.x / nr.w, nr.y / nr.w, nr.z / nr.w);
+  f4 o4 = xform4(P.emm, 0.0f, 0.0f, 0.0f, 1.0f);
+  f4 n4 = xform4(P.emm, pn.x, pn.y, pn.z, 1.0f);
+  const float o[3] = {o4.x, o4.y, o4.z};
+  const float d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
+  float s_in = -INFINITY, s_out = INFINITY;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float lo = P.clip_min[i], hi = P.clip_max[i];
+    if (d[i] == 0.0f) {
+      if (o[i] < lo || o[i] > hi) return false;
+      continue;
+    }
+    float t0 = (lo - o[i]) / d[i], t1 = (hi - o[i]) / d[i];
+    s_in = fmaxf(s_in, fminf(t0, t1));
+    s_out = fminf(s_out, fmaxf(t0, t1));
+  }
+  const float s0 = fmaxf(s_in, 1.0f);
+  if (!(s_out > s0)) return false;
+  const f3 pe = scl3(pn, s0), px_ = scl3(pn, s_out);
+  f4 e = xform4(P.emm, pe.x, pe.y, pe.z, 1.0f);
+  f4 x = xform4(P.emm, px_.x, px_.y, px_.z, 1.0f);
+  entry.x = e.x; entry.y = e.y; entry.z = e.z; entry.w = pe.z;
+  exit_.x = x.x; exit_.y = x.y; exit_.z = x.z; exit_.w = px_.z;
+  return true;
+}
+
+__device__ __forceinline__ float4 to4(f4 v) { return make_float4(v.x, v.y, v.z, v.w); }
+__device__ __forceinline__ f4 from4(float4 v) { f4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+
+// MODE: 0 = 1D TF, 1 = 2D TF, 2 = isosurface
+template <typename T, int MODE, bool LIT, bool SMEM_TF>
+__global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ RayConsts P) {
+  extern __shared__ uchar4 s_tf[];
+  if (SMEM_TF) {
+    const uint32_t n = P.tf_w * P.tf_h;
+    for (uint32_t i = threadIdx.x + threadIdx.y * blockDim.x; i < n; i += blockDim.x * blockDim.y) s_tf[i] = P.tf[i];
+    __syncthreads();
+  }
+  const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t py = blockIdx.y * blockDim.y + threadIdx.y;
+  if (px >= P.width || py >= P.height) return;
+  const size_t pix = (size_t)py * P.width + px;
+  constexpr bool ISO = MODE == 2;
+  const T* pool = (const T*)P.pool;
+  unsigned long long n_samples = 0, n_bricks = 0;
+
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  f4 entry4, exit4;
+  const bool covered = ray_setup(P, px, py, entry4, exit4);
+  if (!covered) {   // render targets are cleared where no back face is rasterised (GLGridLeaper.cpp:837)
+    P.out0[pix] = zero4; P.out1[pix] = zero4; P.out2[pix] = zero4;
+    if (ISO) P.out3[pix] = zero4;
+    return;
+  }
+  f4 acc, resume_col, resume_pos;
+  f4 hit_pos = from4(zero4), hit_nrm = from4(zero4), resume_nrm = from4(zero4);
+  bool done = false;
+  if (P.first_pass) {
+    resume_pos = entry4;
+    acc = from4(zero4);
+  } else {
+    resume_pos = from4(P.ray_start[pix]);
+    acc = from4(P.start_color[pix]);
+  }
+  if (!ISO) {
+    resume_col = acc;
+    if (resume_pos.w == 1000.0f) done = true;
+  } else {
+    if (floorf(resume_pos.w) == 1000.0f) done = true;
+    else if (floorf(resume_pos.w) == 500.0f) {
+      hit_pos = xform4(P.m2e, resume_pos.x, resume_pos.y, resume_pos.z, 1.0f);
+      hit_pos.w = resume_pos.w - floorf(resume_pos.w) + 1.0f;
+      hit_nrm = acc;   // rayStartNormal
+      resume_nrm = hit_nrm;
+      done = true;
+    }
+  }
+  if (!done) {
+    const f3 entry = F3(resume_pos.x, resume_pos.y, resume_pos.z);
+    const float entry_depth = resume_pos.w;
+    const f3 nexit = F3(exit4.x, exit4.y, exit4.z);
+    const float exit_depth = exit4.w;
+    const f3 dir = sub3(nexit, entry);
+    const float ray_len = len3(dir);
+    // TransformToPoolSpace
+    const f3 ps = F3(P.pool_size_f);
+    f3 vdir = norm3(mul3(dir, F3(P.vol_f)));
+    vdir = div3(vdir, ps);
+    const float den = 2.0f * P.sample_rate;
+    vdir = F3(vdir.x / den, vdir.y / den, vdir.z / den);
+    const float step = len3(vdir);
+    float t = 0.0f;
+    bool optimal = true;
+    const float voxel_size = 0.125f / 2000.0f;
+    f3 cur = entry;
+    uint32_t lbx = 0, lby = 0, lbz = 0, lbl = 9999;
+    bool terminated = false;
+    const f3 dscale = F3(P.domain_scale), eye_m = F3(P.eye_m), la = F3(P.light_a), ld = F3(P.light_d),
+             ls = F3(P.light_s), ldir = F3(P.light_dir_m);
+    if (ray_len > voxel_size) {
+      for (uint32_t j = 0; j < 100 && !terminated; ++j) {
+        const float cur_depth = entry_depth * (1.0f - t) + exit_depth * t;
+        uint32_t lod = compute_lod(P, cur_depth);
+        BrickRef b;
+        const bool ok = get_brick(P, cur, lod, dir, b, n_bricks);
+        if (!ok && optimal) {
+          optimal = false;
+          resume_pos.x = cur.x; resume_pos.y = cur.y; resume_pos.z = cur.z; resume_pos.w = cur_depth;
+          if (!ISO) resume_col = acc;
+        }
+        if (!b.empty && !(lbx == b.bx && lby == b.by && lbz == b.bz && lbl == b.bl)) {
+          int steps = (int)ceilf(len3(sub3(b.pool_exit, b.pool_entry)) / step);
+          const int s2 = (int)ceilf(len3(mul3(sub3(nexit, cur), b.scale)) / step);
+          steps = min(steps, s2);
+          const f3 inv_scale = F3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
+          const T* vox = pool + b.base;
+          f3 pc = b.pool_entry;
+          n_samples += (unsigned long long)max(steps, 0);
+          for (int i = 0; i < steps; ++i) {
+            Foot f;
+            footprint(P, b, pc, f);
+            if (!ISO) {
+              f4 col;
+              if (MODE == 0 && !LIT) {
+                const float data = tap(P, vox, f, 0, 0, 0);
+                col = tf_lookup<SMEM_TF>(P, s_tf, data * P.trans_scale, 0.0f);
+              } else {
+                float data; f3 g;
+                sample_with_gradient(P, vox, f, data, g);
+                f3 n;
+                if (MODE == 0) {
+                  col = tf_lookup<SMEM_TF>(P, s_tf, data * P.trans_scale, 0.0f);
+                  n = mul3(g, dscale);   // ComputeNormal
+                  const float l = len3(n);
+                  if (l > 0.0f) n = F3(n.x / l, n.y / l, n.z / l);
+                } else {
+                  const float gm = len3(g);
+                  col = tf_lookup<SMEM_TF>(P, s_tf, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
+                  const f3 gn = gm > 0.0f ? F3(g.x / gm, g.y / gm, g.z / gm) : g;
+                  n = mul3(dscale, gn);
+                }
+                if (LIT) {
+                  const f3 mp = mul3(sub3(pc, b.trans), inv_scale);
+                  const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
+                  col.x = lit.x; col.y = lit.y; col.z = lit.z;
+                }
+              }
+              col.w = opacity_correct(P, col.w);
+              const float oma = 1.0f - acc.w;   // UnderCompositing
+              acc.x = acc.x + col.x * oma * col.w;
+              acc.y = acc.y + col.y * oma * col.w;
+              acc.z = acc.z + col.z * oma * col.w;
+              acc.w = acc.w + col.w * oma;
+              if (acc.w > 0.99f) {
+                n_samples -= (unsigned long long)(steps - 1 - i);
+                terminated = true;
+                break;
+              }
+            } else {
+              if (tap(P, vox, f, 0, 0, 0) >= P.isoval) {
+                n_samples -= (unsigned long long)(steps - 1 - i);
+                // RefineIsosurface
+                f3 rd = F3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
+                pc = sub3(pc, rd);
+#pragma unroll 1
+                for (int k = 0; k < 5; k++) {
+                  rd = F3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
+                  footprint(P, b, pc, f);
+                  if (tap(P, vox, f, 0, 0, 0) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
+                }
+                cur = mul3(sub3(pc, b.trans), inv_scale);
+                hit_pos = xform4(P.m2e, cur.x, cur.y, cur.z, 1.0f);
+                hit_pos.w = 1.0f + 1.0f;   // color.r + 1
+                footprint(P, b, pc, f);
+                float dummy; f3 g;
+                sample_with_gradient(P, vox, f, dummy, g);
+                f3 n = mul3(g, dscale);
+                const float l = len3(n);
+                if (l > 0.0f) n = F3(n.x / l, n.y / l, n.z / l);
+                const float* m = P.mv_inv;   // mModelViewIT * vec4(n, 0)
+                hit_nrm.x = m[0] * n.x + m[1] * n.y + m[2] * n.z;
+                hit_nrm.y = m[4] * n.x + m[5] * n.y + m[6] * n.z;
+                hit_nrm.z = m[8] * n.x + m[9] * n.y + m[10] * n.z;
+                hit_nrm.w = floorf(1.0f * 512.0f) + 1.0f;   // floor(color.g*512)+color.b
+                terminated = true;
+                break;
+              } else {
+                hit_pos = from4(zero4);
+              }
+            }
+            pc = add3(pc, vdir);
+          }
+          if (terminated) break;
+          cur = mul3(sub3(pc, b.trans), inv_scale);
+        } else {
+          cur = F3(b.norm_exit.x + voxel_size * dir.x / ray_len, b.norm_exit.y + voxel_size * dir.y / ray_len,
+                   b.norm_exit.z + voxel_size * dir.z / ray_len);
+        }
+        lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
+        t = len3(sub3(entry, b.norm_exit)) / ray_len;
+        if (t > 0.9999f) break;
+      }
+    }
+    // TerminateRay
+    if (!ISO) {
+      if (optimal) { resume_pos.w = 1000.0f; resume_col = acc; }
+    } else {
+      if (optimal) resume_pos.w = hit_pos.w == 0.0f ? 1000.0f : 499.0f + hit_pos.w;
+      resume_nrm = hit_nrm;
+    }
+  }
+  if (!ISO) {
+    P.out0[pix] = to4(acc); P.out1[pix] = to4(resume_col); P.out2[pix] = to4(resume_pos);
+  } else {
+    P.out0[pix] = to4(hit_pos); P.out1[pix] = to4(hit_nrm); P.out2[pix] = to4(resume_pos);
+    P.out3[pix] = to4(resume_nrm);
+  }
+  if (P.count) {
+    // warp-aggregate, one atomic per warp and counter
+    unsigned long long s = n_samples, r = 1, bk = n_bricks;
+    const unsigned act = __activemask();
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_down_sync(act, s, o);
+      r += __shfl_down_sync(act, r, o);
+      bk += __shfl_down_sync(act, bk, o);
+    }
+    if (act == 0xffffffffu) {
+      if (((threadIdx.x + threadIdx.y * blockDim.x) & 31) == 0) {
+        atomicAdd(P.counters + 0, s); atomicAdd(P.counters + 1, r); atomicAdd(P.counters + 2, bk);
+      }
+    } else {
+      atomicAdd(P.counters + 0, n_samples); atomicAdd(P.counters + 1, 1ull); atomicAdd(P.counters + 2, n_bricks);
+    }
+  }
+}
+
+template <typename T, int MODE, bool LIT>
+void launch_t(const RayConsts& rc, cudaStream_t s) {
+  dim3 block(8, 8);
+  dim3 grid((rc.width + 7) / 8, (rc.height + 7) / 8);
+  const size_t tf_bytes = (size_t)rc.tf_w * rc.tf_h * 4;
+  if (MODE != 2 && tf_bytes <= 64 * 1024) {
+    auto k = raycast_kernel<T, MODE, LIT, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    k<<<grid, block, tf_bytes, s>>>(rc);
+  } else {
+    raycast_kernel<T, MODE, LIT, false><<<grid, block, 0, s>>>(rc);
+  }
+}
+
+template <typename T>
+void launch_d(const RayConsts& rc, int mode, int lighting, cudaStream_t s) {
+  if (mode == TVK_RM_ISOSURFACE) launch_t<T, 2, false>(rc, s);
+  else if (mode == TVK_RM_1DTRANS) { if (lighting) launch_t<T, 0, true>(rc, s); else launch_t<T, 0, false>(rc, s); }
+  else { if (lighting) launch_t<T, 1, true>(rc, s); else launch_t<T, 1, false>(rc, s); }
+}
+
+}  // namespace
+
+void launch_raycast(const RayConsts& rc, int mode, int lighting, int dtype, cudaStream_t s) {
+  switch (dtype) {
+    case TVK_U8: launch_d<uint8_t>(rc, mode, lighting, s); break;
+    case TVK_U16: launch_d<uint16_t>(rc, mode, lighting, s); break;
+    default: launch_d<float>(rc, mode, lighting, s); break;
+  }
+}
+
+}  // namespace tvk

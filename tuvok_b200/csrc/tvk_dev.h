@@ -1,0 +1,100 @@
+// tvk_dev.h -- structs shared by the host layer and the sm_100a kernels of libtvkcuda.so.
+#ifndef TVK_DEV_H
+#define TVK_DEV_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tvk.h"
+
+namespace tvk {
+
+// Everything the traversal kernel reads that GLGridLeaper::SetupRaycastShader
+// (GLGridLeaper.cpp:690-752), GLVolumePool::Enable (GLVolumePool.cpp:790-803) and the
+// generated pool GLSL (#defines at GLVolumePool.cpp:364-463) hand to the shader.
+// Passed by value as a __grid_constant__ kernel parameter (constant bank, broadcast reads).
+struct RayConsts {
+  uint32_t width, height;
+  float emm[16];        // mEyeToModel
+  float inv_proj[16];   // inverse projection (near-plane entry, GLGridLeaper-NearPlane-VS.glsl)
+  float m2e[16];        // mModelToEye
+  float mv_inv[16];     // inverse(modelView): mModelViewIT is its transpose
+  float domain_scale[3];
+  float light_a[3], light_d[3], light_s[3], light_dir_m[3], eye_m[3];
+  float lzwse;          // fLevelZeroWorldSpaceError
+  float lod_factor;     // fLoDFactor
+  float pool_size_f[3]; // iPoolSize (virtual atlas = capacity * max brick)
+  float vol_f[3];       // volumeSize
+  float overlap_tc[3];  // overlap in pool texcoords
+  uint32_t capacity[3];
+  uint32_t total[3];    // maxTotalBrickSize
+  uint32_t lod_count;   // pool LoD count
+  uint32_t lod_offset[TVK_MAX_LOD];
+  float lod_layout[TVK_MAX_LOD][3];     // vLODLayout
+  uint32_t lod_layout_sz[TVK_MAX_LOD][2]; // iLODLayoutSize
+  float norm;           // unorm -> float
+  float oc;             // ocFactor = 1/sampleRateModifier
+  float sample_rate;
+  float trans_scale, gradient_scale, isoval;
+  uint32_t tf_w, tf_h;
+  uint32_t hash_size, rehash_count;
+  int32_t strategy;
+  uint32_t finest[3];   // finest brick layout (hash serialisation)
+  float clip_min[3], clip_max[3];
+  int32_t nearest;
+  int32_t first_pass;   // region is blank: ray entry computed, start colour = 0
+  int32_t count;        // accumulate counters
+  // device pointers
+  const void* pool;       // slot-linear brick pool
+  uint64_t slot_voxels;   // voxels per slot
+  const uint32_t* meta;   // page table
+  const uchar4* tf;       // RGBA8 table
+  uint32_t* hash;         // miss-report table
+  const float4* ray_start;   // resume position (in), ignored when first_pass
+  const float4* start_color; // resume colour / normal (in)
+  float4* out0;  // DVR accRayColor   | ISO rayHitPos
+  float4* out1;  // DVR rayResumeColor| ISO rayHitNormal
+  float4* out2;  // rayResumePos
+  float4* out3;  // ISO rayResumeNormal
+  unsigned long long* counters; // samples, rays, brick visits
+};
+
+// launchers (defined in the .cu files)
+void launch_raycast(const RayConsts& rc, int mode, int lighting, int dtype, cudaStream_t s);
+void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rgba, uint32_t w, uint32_t h,
+                        const float amb[3], const float dif[3], const float spe[3], const float ldir[3],
+                        cudaStream_t s);
+void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s);
+void launch_composite_over(const float4* front, const float4* back, float4* out, uint64_t n, cudaStream_t s);
+
+// page table / visibility (k_pool.cu)
+struct VisConsts {
+  int32_t mode;
+  double v[4];                   // 1D: min,max | 2D: min,max,gmin,gmax | ISO: iso
+  uint32_t lod_count;
+  uint32_t lod_offset[TVK_MAX_LOD];
+  uint32_t layout[TVK_MAX_LOD][3];
+};
+void launch_vis_clear(uint32_t* meta, uint64_t n, cudaStream_t s);
+void launch_vis_pool(uint32_t* meta, const int32_t* slot_brick, uint32_t n_slots, const double* minmax,
+                     const VisConsts& vc, cudaStream_t s);
+void launch_vis_level(uint32_t* meta, const double* minmax, const VisConsts& vc, uint32_t lod,
+                      uint32_t* counts, cudaStream_t s);
+struct PageOp { uint32_t evict_id; uint32_t new_id; uint32_t slot; uint32_t pad; uint64_t src_off; uint32_t size[3]; uint32_t pad2; };
+void launch_page_meta(uint32_t* meta, const PageOp* ops, uint32_t n, cudaStream_t s);
+void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t n, uint64_t slot_bytes,
+                      uint32_t esize, const uint32_t total[3], int src_is_slot_layout, cudaStream_t s);
+void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s);
+
+// bricker (k_bricker.cu)
+void launch_synth(void* dst, int kind, const uint32_t size[3], int dtype, uint32_t seed, cudaStream_t s);
+void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const uint32_t ds[3], int dtype,
+                       cudaStream_t s);
+struct CutConsts {
+  uint32_t lod_size[3], layout[3], brick[3], overlap;
+  int32_t clamp, lod;
+  uint64_t first_brick;   // TOC index of brick (0,0,0) of this LOD
+};
+void launch_cut_bricks(const void* lod_vol, void* store, double* minmax, const CutConsts& cc, int dtype,
+                       uint64_t slot_bytes, cudaStream_t s);
+
+}  // namespace tvk
+#endif

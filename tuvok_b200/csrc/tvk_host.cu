@@ -1,0 +1,1186 @@
+// tvk_host.cu -- the C ABI of libtvkcuda.so (include/tvk.h) and the host-side renderer logic:
+// dataset geometry, pool sizing, slot (LRU) table, paging, visibility scheduling, the per-frame
+// subframe loop.  Mirrors (reference file:line):
+//   GLGridLeaper::{CreateVolumePool,Initialize,RecomputeBrickVisibility,SetupRaycastShader,Raycast,
+//                  Render3DRegion}           Renderer/GL/GLGridLeaper.cpp:83-103,247-264,647-870,914-1154
+//   GLVolumePool ctor / UploadBrick / PrepareForPaging / RecomputeVisibility / UploadBricks
+//                                             Renderer/GL/GLVolumePool.cpp:119-259,673-778,955-959,1580-1789
+//   GPUMemMan::GetVolumePool                  Renderer/GPUMemMan/GPUMemMan.cpp:766-844
+//   GLHashTable::{ClearData,GetData,Int2Vector}  Renderer/GL/GLHashTable.cpp:65-110
+//   ExtendedOctree::ComputeMetadata           IO/UVF/ExtendedOctree/ExtendedOctree.cpp:188-243
+//   GLRenderer::ComputeViewAndProjection, CullingLOD::SetScreenParams
+// There is no CPU fallback: every data-path operation is a CUDA kernel in k_*.cu.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <limits>
+#include "tvk_host.h"
+
+using namespace tvk;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(tvk_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) {
+    c->err = buf;
+    if (c->log_cb) c->log_cb(c->log_user, 2, "tvk", buf);
+  } else {
+    g_create_err = buf;
+  }
+  return code;
+}
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? TVK_ERR_OOM : TVK_ERR_CUDA,     \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+uint32_t esize_of(int dtype) { return dtype == TVK_U8 ? 1u : dtype == TVK_U16 ? 2u : 4u; }
+
+// ExtendedOctree::ComputeMetadata: LOD sizes = ceil(prev/2) per axis (size-1 axes stay) until 1^3
+int compute_geometry(tvk_ctx* ctx) {
+  uint32_t s[3] = {ctx->vol[0], ctx->vol[1], ctx->vol[2]};
+  uint32_t l = 0;
+  ctx->toc_offset[0] = 0;
+  for (;;) {
+    if (l > 0)
+      for (int i = 0; i < 3; i++) if (s[i] > 1) s[i] = (s[i] + 1) / 2;
+    uint64_t n = 1;
+    for (int i = 0; i < 3; i++) {
+      ctx->lod_size[l][i] = s[i];
+      ctx->layout[l][i] = (s[i] + ctx->inner[i] - 1) / ctx->inner[i];
+      n *= ctx->layout[l][i];
+    }
+    ctx->toc_offset[l + 1] = ctx->toc_offset[l] + n;
+    l++;
+    if (!(s[0] > 1 || s[1] > 1 || s[2] > 1)) break;
+    if (l >= TVK_MAX_LOD) return fail(ctx, TVK_ERR_INVALID, "volume needs more than %d LODs", TVK_MAX_LOD);
+  }
+  ctx->lod_count = l;
+  ctx->n_bricks_all = ctx->toc_offset[l];
+  // GetLargestSingleBrickLOD: the finest LOD that is a single brick
+  uint32_t single = l - 1;
+  for (uint32_t i = 0; i < l; i++)
+    if (ctx->layout[i][0] * ctx->layout[i][1] * ctx->layout[i][2] == 1) { single = i; break; }
+  ctx->pool_lod_count = single + 1;
+  // pool brick layout (GLVolumePool.cpp:109-117): ceil(ceil(vol/inner) / 2^lod)
+  uint32_t off = 0;
+  for (uint32_t i = 0; i < ctx->pool_lod_count; i++) {
+    ctx->lod_offset[i] = off;
+    for (int a = 0; a < 3; a++) {
+      const uint32_t base = (uint32_t)std::ceil(double(ctx->vol[a]) / ctx->inner[a]);
+      ctx->pool_layout[i][a] = (uint32_t)std::ceil(double(base) / double(1u << i));
+      if (ctx->pool_layout[i][a] != ctx->layout[i][a])
+        return fail(ctx, TVK_ERR_INVALID, "pool and octree brick layouts disagree at LOD %u axis %d (%u vs %u)", i,
+                    a, ctx->pool_layout[i][a], ctx->layout[i][a]);
+    }
+    off += ctx->pool_layout[i][0] * ctx->pool_layout[i][1] * ctx->pool_layout[i][2];
+  }
+  ctx->total_bricks = ctx->lod_offset[ctx->pool_lod_count - 1] + 1;
+  ctx->slot_voxels = (uint64_t)ctx->brick[0] * ctx->brick[1] * ctx->brick[2];
+  ctx->slot_bytes = ctx->slot_voxels * ctx->esize;
+  return TVK_OK;
+}
+
+void brick_size(const tvk_ctx* ctx, const uint32_t co[3], uint32_t lod, uint32_t out[3]) {
+  for (int i = 0; i < 3; i++) {
+    const uint32_t core = ctx->inner[i];
+    const bool last = co[i] == ctx->layout[lod][i] - 1;
+    const uint32_t rem = ctx->lod_size[lod][i] % core;
+    out[i] = (last && rem) ? 2 * ctx->overlap + rem : ctx->brick[i];
+  }
+}
+
+void free_dataset(tvk_ctx* c) {
+  if (c->minmax_d) cudaFree(c->minmax_d);
+  if (c->store_d) cudaFree(c->store_d);
+  c->minmax_d = nullptr; c->store_d = nullptr;
+  c->minmax_h.clear();
+  c->have_volume = false;
+}
+
+void free_pool(tvk_ctx* c) {
+  void* p[] = {c->pool_d, c->meta_d, c->slot_brick_d, c->counts_d, c->ops_d, c->stage_d, c->hash_d, c->miss_d};
+  for (void* q : p) if (q) cudaFree(q);
+  if (c->stage_h) cudaFreeHost(c->stage_h);
+  if (c->miss_h) cudaFreeHost(c->miss_h);
+  c->pool_d = nullptr; c->meta_d = nullptr; c->slot_brick_d = nullptr; c->counts_d = nullptr; c->ops_d = nullptr;
+  c->stage_d = nullptr; c->stage_h = nullptr; c->hash_d = nullptr; c->miss_d = nullptr; c->miss_h = nullptr;
+  c->ops_cap = 0; c->stage_bricks = 0;
+  c->slots.clear(); c->meta_h.clear();
+  c->have_pool = false;
+}
+
+void free_frame(tvk_ctx* c) {
+  for (auto& b : c->buf) { if (b) cudaFree(b); b = nullptr; }
+  if (c->rgba8_d) cudaFree(c->rgba8_d);
+  c->rgba8_d = nullptr;
+  c->img_w = c->img_h = 0;
+}
+
+int ensure_frame(tvk_ctx* ctx, uint32_t w, uint32_t h) {
+  if (ctx->img_w == w && ctx->img_h == h) return TVK_OK;
+  free_frame(ctx);
+  const size_t n = (size_t)w * h;
+  for (int i = 0; i < 7; i++) CU(cudaMalloc(&ctx->buf[i], n * sizeof(float4)));
+  CU(cudaMalloc(&ctx->rgba8_d, n * 4));
+  ctx->img_w = w; ctx->img_h = h;
+  ctx->blank = true;
+  return TVK_OK;
+}
+
+int ensure_read(tvk_ctx* ctx, size_t bytes) {
+  if (ctx->read_cap >= bytes) return TVK_OK;
+  if (ctx->read_h) cudaFreeHost(ctx->read_h);
+  ctx->read_h = nullptr; ctx->read_cap = 0;
+  CU(cudaMallocHost(&ctx->read_h, bytes));
+  ctx->read_cap = bytes;
+  return TVK_OK;
+}
+
+uint32_t pool_coord(const tvk_ctx* c, const Slot& s) {
+  return s.pos[0] + s.pos[1] * c->capacity[0] + s.pos[2] * c->capacity[0] * c->capacity[1];
+}
+uint32_t brick_id(const tvk_ctx* c, uint32_t x, uint32_t y, uint32_t z, uint32_t lod) {
+  return x + y * c->pool_layout[lod][0] + z * c->pool_layout[lod][0] * c->pool_layout[lod][1] + c->lod_offset[lod];
+}
+
+bool contains_h(const tvk_ctx* c, const VisState& v, uint32_t id) {
+  const double* m = &c->minmax_h[4 * (size_t)id];
+  switch (v.mode) {
+    case TVK_RM_1DTRANS: return v.v[1] >= m[0] && v.v[0] <= m[1];
+    case TVK_RM_2DTRANS: return (v.v[1] >= m[0] && v.v[0] <= m[1]) && (v.v[3] >= m[2] && v.v[2] <= m[3]);
+    default: return v.v[0] >= m[0] && v.v[0] <= m[1];
+  }
+}
+
+// GPUMemMan::GetVolumePool sizing (GPUMemMan.cpp:766-844)
+void size_pool(uint64_t max_gpu_mem, uint64_t bit_width, const uint32_t bs[3], uint64_t brick_count, uint32_t max_dim,
+               uint32_t out[3]) {
+  const uint64_t max_voxels = max_gpu_mem / (bit_width / 8);
+  const uint64_t r3v = uint64_t(std::pow(double(max_voxels), 1.0 / 3.0));
+  uint64_t gpu[3], ds[3];
+  uint64_t m = uint64_t(((float)r3v / bs[0]) + 0.5f) * bs[0];
+  if (m > max_dim) m = (max_dim / bs[0]) * bs[0];
+  gpu[0] = uint32_t(m);
+  m = ((max_voxels / (gpu[0] * gpu[0])) / bs[1]) * bs[1];
+  if (m > max_dim) m = (max_dim / bs[1]) * bs[1];
+  gpu[1] = uint32_t(m);
+  m = ((max_voxels / (gpu[0] * gpu[1])) / bs[2]) * bs[2];
+  if (m > max_dim) m = (max_dim / bs[2]) * bs[2];
+  gpu[2] = uint32_t(m);
+  const uint64_t r3b = uint64_t(std::pow(double(brick_count), 1.0 / 3.0));
+  m = bs[0] * r3b;
+  if (m > max_dim) m = (max_dim / bs[0]) * bs[0];
+  ds[0] = uint32_t(m);
+  m = bs[1] * uint64_t(std::ceil(float(brick_count) / ((ds[0] / bs[0]) * (ds[0] / bs[0]))));
+  if (m > max_dim) m = (max_dim / bs[1]) * bs[1];
+  ds[1] = uint32_t(m);
+  m = bs[2] * uint64_t(std::ceil(float(brick_count) / ((ds[0] / bs[0]) * (ds[1] / bs[1]))));
+  if (m > max_dim) m = (max_dim / bs[2]) * bs[2];
+  ds[2] = uint32_t(m);
+  const bool use_ds = ds[0] * ds[1] * ds[2] < gpu[0] * gpu[1] * gpu[2];
+  for (int i = 0; i < 3; i++) out[i] = uint32_t(use_ds ? ds[i] : gpu[i]);
+}
+
+// Fit1DIndexTo3DArray (GLVolumePool.cpp:816-848)
+bool fit_1d_to_3d(uint64_t max_idx, uint32_t max_array, uint32_t out[3]) {
+  const uint64_t max_elems = uint64_t(max_array) * max_array * max_array;
+  if (max_idx > max_elems) return false;
+  if (max_idx < uint64_t(max_array)) {
+    out[0] = uint32_t(max_idx); out[1] = 1; out[2] = 1;
+  } else if (max_idx < uint64_t(max_array) * max_array) {
+    out[0] = uint32_t(std::ceil(std::sqrt(double(max_idx))));
+    out[1] = uint32_t(std::ceil(double(max_idx) / double(out[0])));
+    out[2] = 1;
+  } else {
+    out[0] = uint32_t(std::ceil(std::pow(double(max_idx), 1.0 / 3.0)));
+    out[1] = uint32_t(std::ceil(double(max_idx) / double(out[0] * out[0])));
+    out[2] = uint32_t(std::ceil(double(max_idx) / double(out[0] * out[1])));
+  }
+  return true;
+}
+
+int ensure_ops(tvk_ctx* ctx, size_t n) {
+  if (ctx->ops_cap >= n) return TVK_OK;
+  if (ctx->ops_d) cudaFree(ctx->ops_d);
+  ctx->ops_d = nullptr; ctx->ops_cap = 0;
+  const size_t cap = std::max<size_t>(n, 4096);
+  CU(cudaMalloc(&ctx->ops_d, cap * sizeof(PageOp)));
+  ctx->ops_cap = cap;
+  return TVK_OK;
+}
+
+// scatter (index,value) pairs into a device u32 array through the PageOp list
+int scatter_u32(tvk_ctx* ctx, uint32_t* dst, const std::vector<std::pair<uint32_t, uint32_t>>& kv) {
+  if (kv.empty()) return TVK_OK;
+  std::vector<PageOp> ops(kv.size());
+  for (size_t i = 0; i < kv.size(); i++) { ops[i] = PageOp{}; ops[i].new_id = kv[i].first; ops[i].slot = kv[i].second; }
+  int rc = ensure_ops(ctx, ops.size());
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->ops_d, ops.data(), ops.size() * sizeof(PageOp), cudaMemcpyHostToDevice, ctx->stream));
+  launch_page_meta(dst, ctx->ops_d, (uint32_t)ops.size(), ctx->stream);
+  CU(cudaStreamSynchronize(ctx->stream));   // ops (pageable host memory) must outlive the copy
+  return TVK_OK;
+}
+
+struct CopyReq { uint32_t id; uint32_t slot; uint32_t co[4]; };
+
+// move the voxels of the requested bricks into their slots
+int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
+  if (reqs.empty()) return TVK_OK;
+  if (ctx->store_d) {
+    std::vector<PageOp> ops(reqs.size());
+    for (size_t i = 0; i < reqs.size(); i++) {
+      ops[i] = PageOp{};
+      ops[i].slot = reqs[i].slot;
+      ops[i].src_off = (uint64_t)reqs[i].id * ctx->slot_bytes;   // pool id == TOC index for the pool LoDs
+    }
+    int rc = ensure_ops(ctx, ops.size());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->ops_d, ops.data(), ops.size() * sizeof(PageOp), cudaMemcpyHostToDevice, ctx->stream));
+    launch_page_copy(ctx->pool_d, ctx->store_d, ctx->ops_d, (uint32_t)ops.size(), ctx->slot_bytes, ctx->esize,
+                     ctx->brick, 1, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TVK_OK;
+  }
+  if (!ctx->cb) return fail(ctx, TVK_ERR_INVALID, "no brick source");
+  // Dataset::GetBrick -> pinned staging -> async H2D on the copy stream -> scatter into slots.
+  // Two half-buffers: the callback fills one half while the other is in flight.
+  const size_t half = ctx->stage_bricks / 2;
+  cudaEvent_t done[2];
+  CU(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+  std::vector<PageOp> ops;
+  int rc = TVK_OK;
+  size_t pos = 0;
+  int h = 0;
+  while (pos < reqs.size() && rc == TVK_OK) {
+    const size_t n = std::min(half, reqs.size() - pos);
+    cudaEventSynchronize(done[h]);   // the kernels that read this half last time have finished
+    unsigned char* hb = (unsigned char*)ctx->stage_h + (size_t)h * half * ctx->slot_bytes;
+    unsigned char* db = (unsigned char*)ctx->stage_d + (size_t)h * half * ctx->slot_bytes;
+    ops.assign(n, PageOp{});
+    for (size_t i = 0; i < n; i++) {
+      const CopyReq& r = reqs[pos + i];
+      uint32_t bs[3];
+      brick_size(ctx, r.co, r.co[3], bs);
+      if (ctx->cb(ctx->cb_user, r.co[0], r.co[1], r.co[2], r.co[3], hb + i * ctx->slot_bytes, ctx->slot_bytes) != 0) {
+        rc = fail(ctx, TVK_ERR_SOURCE, "brick source failed for (%u,%u,%u,%u)", r.co[0], r.co[1], r.co[2], r.co[3]);
+        break;
+      }
+      ops[i].slot = r.slot;
+      ops[i].src_off = (uint64_t)i * ctx->slot_bytes;
+      ops[i].size[0] = bs[0]; ops[i].size[1] = bs[1]; ops[i].size[2] = bs[2];
+    }
+    if (rc) break;
+    // ops travel in the same pinned half (tail) so the copy is truly asynchronous
+    const size_t ops_off = (ctx->stage_bricks * ctx->slot_bytes + 15) & ~size_t(15);
+    PageOp* hops = (PageOp*)((unsigned char*)ctx->stage_h + ops_off) + (size_t)h * half;
+    PageOp* dops = (PageOp*)((unsigned char*)ctx->stage_d + ops_off) + (size_t)h * half;
+    std::memcpy(hops, ops.data(), n * sizeof(PageOp));
+    cudaMemcpyAsync(db, hb, n * ctx->slot_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    cudaMemcpyAsync(dops, hops, n * sizeof(PageOp), cudaMemcpyHostToDevice, ctx->copy_stream);
+    launch_page_copy(ctx->pool_d, db, dops, (uint32_t)n, ctx->slot_bytes, ctx->esize, ctx->brick, 0, ctx->copy_stream);
+    cudaEventRecord(done[h], ctx->copy_stream);
+    pos += n;
+    h ^= 1;
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+  cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, TVK_ERR_CUDA, "brick upload failed: %s", cudaGetErrorString(e));
+  return TVK_OK;
+}
+
+// GLVolumePool::UploadBrick bookkeeping (GLVolumePool.cpp:673-717)
+void assign_slot(tvk_ctx* c, uint32_t id, size_t pos, uint64_t toc, std::vector<std::pair<uint32_t, uint32_t>>& meta_kv,
+                 std::vector<std::pair<uint32_t, uint32_t>>& slot_kv) {
+  Slot& s = c->slots[pos];
+  if (s.contains_visible()) {
+    c->meta_h[s.brick_id] = TVK_BI_MISSING;
+    meta_kv.emplace_back((uint32_t)s.brick_id, (uint32_t)TVK_BI_MISSING);
+  }
+  s.brick_id = (int32_t)id;
+  s.time = toc;
+  const uint32_t pc = pool_coord(c, s);
+  c->meta_h[id] = pc + TVK_BI_FLAG_COUNT;
+  meta_kv.emplace_back(id, pc + TVK_BI_FLAG_COUNT);
+  slot_kv.emplace_back(pc, id);
+}
+
+// later entries for the same index win (sequential semantics of the reference's texel uploads)
+void dedup_last(std::vector<std::pair<uint32_t, uint32_t>>& kv) {
+  std::vector<std::pair<uint32_t, uint32_t>> out;
+  std::stable_sort(kv.begin(), kv.end(), [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) {
+    return a.first < b.first;
+  });
+  for (size_t i = 0; i < kv.size(); i++)
+    if (i + 1 == kv.size() || kv[i + 1].first != kv[i].first) out.push_back(kv[i]);
+  kv.swap(out);
+}
+
+int upload_bricks(tvk_ctx* ctx, const uint32_t* ids, uint32_t n, uint32_t* out_slots, uint32_t* n_paged) {
+  uint32_t paged = 0;
+  if (out_slots) for (uint32_t i = 0; i < n; i++) out_slots[i] = 0xFFFFFFFFu;
+  if (n_paged) *n_paged = 0;
+  if (n == 0) return TVK_OK;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t* q = ids + 4 * i;
+    if (q[3] >= ctx->pool_lod_count || q[0] >= ctx->pool_layout[q[3]][0] || q[1] >= ctx->pool_layout[q[3]][1] ||
+        q[2] >= ctx->pool_layout[q[3]][2])
+      return fail(ctx, TVK_ERR_INVALID, "brick id (%u,%u,%u,%u) out of range", q[0], q[1], q[2], q[3]);
+  }
+  // PrepareForPaging: oldest first; never used = 0, flagged empty = 1, first brick = UINT64_MAX
+  std::sort(ctx->slots.begin(), ctx->slots.end(), [](const Slot& i, const Slot& j) { return i.time < j.time; });
+  ctx->insert_pos = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> meta_kv, slot_kv;
+  std::vector<CopyReq> reqs;
+  for (uint32_t i = 0; i < n; i++) {
+    if (ctx->insert_pos >= ctx->slots.size() - 1) break;   // all slots but the last replaced this frame
+    const uint32_t* q = ids + 4 * i;
+    const uint32_t id = brick_id(ctx, q[0], q[1], q[2], q[3]);
+    assign_slot(ctx, id, ctx->insert_pos, ctx->time_of_creation++, meta_kv, slot_kv);
+    const uint32_t pc = pool_coord(ctx, ctx->slots[ctx->insert_pos]);
+    if (out_slots) out_slots[i] = pc;
+    CopyReq r; r.id = id; r.slot = pc; r.co[0] = q[0]; r.co[1] = q[1]; r.co[2] = q[2]; r.co[3] = q[3];
+    reqs.push_back(r);
+    ctx->insert_pos++;
+    paged++;
+  }
+  dedup_last(meta_kv);
+  dedup_last(slot_kv);
+  int rc = copy_bricks(ctx, reqs);
+  if (rc) return rc;
+  rc = scatter_u32(ctx, ctx->meta_d, meta_kv);
+  if (rc) return rc;
+  rc = scatter_u32(ctx, (uint32_t*)ctx->slot_brick_d, slot_kv);
+  if (rc) return rc;
+  if (n_paged) *n_paged = paged;
+  return TVK_OK;
+}
+
+int recompute_visibility(tvk_ctx* ctx, int force, uint32_t counts[4]) {
+  if (counts) counts[0] = counts[1] = counts[2] = counts[3] = 0;
+  if (!ctx->have_pool) return fail(ctx, TVK_ERR_INVALID, "no pool");
+  if (!ctx->have_params) return fail(ctx, TVK_ERR_INVALID, "no render params");
+  if (!ctx->tf1d_d) return fail(ctx, TVK_ERR_INVALID, "no 1D transfer function (needed for the rescale factor)");
+  // GLGridLeaper::RecomputeBrickVisibility (GLGridLeaper.cpp:647-687); note the 1D TF size is used
+  // for the rescale factor in every mode
+  const double max_value = ctx->range_max;
+  const double rescale = max_value / double(ctx->tf1d_n - 1);
+  int mode = ctx->params.mode;
+  double a = 0, b = 0, c = 0, d = 0;
+  switch (mode) {
+    case TVK_RM_1DTRANS: a = double(ctx->tf1d_nz[0]) * rescale; b = double(ctx->tf1d_nz[1]) * rescale; break;
+    case TVK_RM_2DTRANS:
+      if (!ctx->tf2d_d) return fail(ctx, TVK_ERR_INVALID, "no 2D transfer function");
+      a = double(ctx->tf2d_nz[0]) * rescale; b = double(ctx->tf2d_nz[1]) * rescale;
+      c = double(ctx->tf2d_nz[2]); d = double(ctx->tf2d_nz[3]);
+      break;
+    case TVK_RM_ISOSURFACE: a = ctx->params.isovalue; break;
+    default: return fail(ctx, TVK_ERR_INVALID, "Unhandled rendering mode.");
+  }
+  if (!ctx->vis.needs_update(mode, a, b, c, d) && !force) return TVK_OK;
+
+  VisConsts vc{};
+  vc.mode = mode;
+  vc.v[0] = a; vc.v[1] = b; vc.v[2] = c; vc.v[3] = d;
+  vc.lod_count = ctx->pool_lod_count;
+  for (uint32_t l = 0; l < ctx->pool_lod_count; l++) {
+    vc.lod_offset[l] = ctx->lod_offset[l];
+    for (int i = 0; i < 3; i++) vc.layout[l][i] = ctx->pool_layout[l][i];
+  }
+  // host side of RecomputeVisibilityForBrickPool: only the LRU flags (the table is written on the device)
+  for (Slot& s : ctx->slots) {
+    if (!s.was_ever_used()) continue;
+    const bool has = contains_h(ctx, ctx->vis, (uint32_t)s.brick_id);
+    const bool had = s.contains_visible();
+    if (has) { if (!had) s.restore(); }
+    else { if (had) s.flag_empty(); }
+  }
+  CU(cudaMemsetAsync(ctx->counts_d, 0, 4 * sizeof(uint32_t), ctx->stream));
+  launch_vis_clear(ctx->meta_d, ctx->meta_count, ctx->stream);
+  launch_vis_pool(ctx->meta_d, ctx->slot_brick_d, ctx->n_slots, ctx->minmax_d, vc, ctx->stream);
+  for (uint32_t l = 0; l < ctx->pool_lod_count; l++)
+    launch_vis_level(ctx->meta_d, ctx->minmax_d, vc, l, ctx->counts_d, ctx->stream);
+  CU(cudaGetLastError());
+  uint32_t cnt[4];
+  CU(cudaMemcpyAsync(cnt, ctx->counts_d, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->meta_h.data(), ctx->meta_d, ctx->meta_count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (counts) std::memcpy(counts, cnt, sizeof(cnt));
+  ctx->blank = true;   // a new table invalidates the resume state
+  return TVK_OK;
+}
+
+// SetupRaycastShader + GLVolumePool::Enable + the #defines of the generated pool GLSL
+int derive(tvk_ctx* ctx, RayConsts& u) {
+  const tvk_render_params& p = ctx->params;
+  std::memset(&u, 0, sizeof(u));
+  u.width = p.width; u.height = p.height;
+  double mv[16], pr[16], imv[16], ipr[16], emm[16], m2e[16];
+  for (int i = 0; i < 16; i++) { mv[i] = p.model_view[i]; pr[i] = p.projection[i]; }
+  if (!inv4(mv, imv) || !inv4(pr, ipr)) return fail(ctx, TVK_ERR_INVALID, "singular view or projection matrix");
+  float ex[3], sc[3];
+  for (int i = 0; i < 3; i++) ex[i] = (float)ctx->vol[i] * ctx->scale[i];
+  const float mx = fmaxf(ex[0], fmaxf(ex[1], ex[2]));
+  for (int i = 0; i < 3; i++) ex[i] = ex[i] / mx;
+  const float mn = fminf(ctx->scale[0], fminf(ctx->scale[1], ctx->scale[2]));
+  for (int i = 0; i < 3; i++) sc[i] = ctx->scale[i] / mn;
+  for (int i = 0; i < 3; i++) u.domain_scale[i] = 1.0f / sc[i];
+  // mEyeToModel = inverse(MV) * T(-centre = 0) * S(1/extend) * T(.5)  (GLGridLeaper.cpp:560-573)
+  double s[16] = {0}, t[16] = {0};
+  s[0] = (double)(1.0f / ex[0]); s[5] = (double)(1.0f / ex[1]); s[10] = (double)(1.0f / ex[2]); s[15] = 1;
+  t[0] = t[5] = t[10] = t[15] = 1; t[12] = t[13] = t[14] = 0.5;
+  mul4(imv, s, emm);
+  mul4(emm, t, emm);
+  if (!inv4(emm, m2e)) return fail(ctx, TVK_ERR_INVALID, "singular eye-to-model matrix");
+  for (int i = 0; i < 16; i++) {
+    u.emm[i] = (float)emm[i]; u.inv_proj[i] = (float)ipr[i]; u.m2e[i] = (float)m2e[i]; u.mv_inv[i] = (float)imv[i];
+  }
+  for (int i = 0; i < 3; i++) {
+    u.light_a[i] = p.ambient[i] * p.ambient[3];
+    u.light_d[i] = p.diffuse[i] * p.diffuse[3];
+    u.light_s[i] = p.specular[i] * p.specular[3];
+  }
+  {  // (vec4(lightDir,0) * emm).xyz normalised; (vec4(eye,1) * emm).xyz  (GLGridLeaper.cpp:741-742)
+    const float* m = u.emm;
+    float l[3], e[3];
+    for (int c = 0; c < 3; c++) {
+      l[c] = p.light_dir[0] * m[c] + p.light_dir[1] * m[4 + c] + p.light_dir[2] * m[8 + c] + 0.0f * m[12 + c];
+      e[c] = p.eye[0] * m[c] + p.eye[1] * m[4 + c] + p.eye[2] * m[8 + c] + 1.0f * m[12 + c];
+    }
+    const float inv = 1.0f / sqrtf(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    for (int c = 0; c < 3; c++) { u.light_dir_m[c] = l[c] * inv; u.eye_m[c] = e[c]; }
+  }
+  u.lzwse = fmaxf(ex[0] / (float)ctx->vol[0], fmaxf(ex[1] / (float)ctx->vol[1], ex[2] / (float)ctx->vol[2]));
+  u.lod_factor = p.lod_factor;
+  for (int i = 0; i < 3; i++) {
+    u.pool_size_f[i] = (float)ctx->pool_size[i];
+    u.vol_f[i] = (float)ctx->vol[i];
+    u.overlap_tc[i] = (ctx->brick[i] - ctx->inner[i]) / (2.0f * ctx->pool_size[i]);
+    u.capacity[i] = ctx->capacity[i];
+    u.total[i] = ctx->brick[i];
+    u.finest[i] = ctx->pool_layout[0][i];
+    u.clip_min[i] = p.clip_min[i]; u.clip_max[i] = p.clip_max[i];
+  }
+  u.lod_count = ctx->pool_lod_count;
+  for (uint32_t l = 0; l < ctx->pool_lod_count; l++) {
+    u.lod_offset[l] = ctx->lod_offset[l];
+    float c[3];
+    for (int i = 0; i < 3; i++) {   // GetFloatBrickLayout (GLVolumePool.cpp:89-107)
+      c[i] = (float)ctx->vol[i] / ctx->inner[i];
+      c[i] = c[i] / (float)(1u << l);
+      if ((float)(uint32_t)c[i] == c[i]) c[i] = c[i] - c[i] * std::numeric_limits<float>::epsilon();
+      u.lod_layout[l][i] = c[i];
+    }
+    u.lod_layout_sz[l][0] = (uint32_t)ceilf(c[0]);
+    u.lod_layout_sz[l][1] = (uint32_t)ceilf(c[0]) * (uint32_t)ceilf(c[1]);
+  }
+  u.norm = ctx->dtype == TVK_U8 ? 1.0f / 255.0f : ctx->dtype == TVK_U16 ? 1.0f / 65535.0f : 1.0f;
+  u.sample_rate = p.sample_rate_modifier;
+  u.oc = 1.0f / p.sample_rate_modifier;
+  // GLRenderer::CalculateScaling (GLRenderer.cpp:1813-1819): (2^bits - 1) / maxValue; float data: 1/maxValue (H7)
+  const double full = ctx->dtype == TVK_U8 ? 255.0 : ctx->dtype == TVK_U16 ? 65535.0 : 1.0;
+  u.trans_scale = (float)(full / ctx->range_max);
+  u.gradient_scale = ctx->max_grad == 0.0f ? 1.0f : 1.0f / ctx->max_grad;
+  // GetNormalizedIsovalue (AbstrRenderer.cpp:412-424): iso / 2^bits; float data: iso itself (H7)
+  u.isoval = ctx->dtype == TVK_U8 ? (float)(p.isovalue / 256.0) : ctx->dtype == TVK_U16 ? (float)(p.isovalue / 65536.0)
+                                                                                       : (float)p.isovalue;
+  if (p.mode == TVK_RM_2DTRANS) { u.tf = ctx->tf2d_d; u.tf_w = ctx->tf2d_w; u.tf_h = ctx->tf2d_h; }
+  else { u.tf = ctx->tf1d_d; u.tf_w = ctx->tf1d_n; u.tf_h = 1; }
+  u.hash_size = ctx->hash_size;
+  u.rehash_count = ctx->cfg.rehash_count;
+  u.strategy = ctx->cfg.brick_strategy;
+  u.nearest = p.nearest;
+  u.count = ctx->counters_on ? 1 : 0;
+  u.pool = ctx->pool_d;
+  u.slot_voxels = ctx->slot_voxels;
+  u.meta = ctx->meta_d;
+  u.hash = ctx->hash_d;
+  u.counters = ctx->counters_d;
+  return TVK_OK;
+}
+
+int check_renderable(tvk_ctx* ctx) {
+  if (!ctx->have_volume) return fail(ctx, TVK_ERR_INVALID, "no dataset registered");
+  if (!ctx->have_pool) return fail(ctx, TVK_ERR_INVALID, "no volume pool");
+  if (!ctx->have_params) return fail(ctx, TVK_ERR_INVALID, "no render params");
+  const int m = ctx->params.mode;
+  if (m == TVK_RM_1DTRANS && !ctx->tf1d_d) return fail(ctx, TVK_ERR_INVALID, "no 1D transfer function");
+  if (m == TVK_RM_2DTRANS && !ctx->tf2d_d) return fail(ctx, TVK_ERR_INVALID, "no 2D transfer function");
+  return TVK_OK;
+}
+
+// one raycast pass into the frame buffers (GLGridLeaper::Raycast, GLGridLeaper.cpp:754-870)
+int raycast_pass(tvk_ctx* ctx, bool with_hash) {
+  int rc = ensure_frame(ctx, ctx->params.width, ctx->params.height);
+  if (rc) return rc;
+  RayConsts u;
+  rc = derive(ctx, u);
+  if (rc) return rc;
+  if (!with_hash) { u.hash = nullptr; u.hash_size = 0; }
+  const bool iso = ctx->params.mode == TVK_RM_ISOSURFACE;
+  const int cur = ctx->cur, nxt = cur ^ 1;
+  u.first_pass = ctx->blank ? 1 : 0;
+  u.ray_start = ctx->buf[3 + cur];
+  u.start_color = ctx->buf[1 + cur];
+  u.out0 = ctx->buf[0];
+  if (!iso) { u.out1 = ctx->buf[1 + nxt]; u.out2 = ctx->buf[3 + nxt]; u.out3 = nullptr; }
+  else { u.out1 = ctx->buf[5]; u.out2 = ctx->buf[3 + nxt]; u.out3 = ctx->buf[1 + nxt]; }
+  launch_raycast(u, ctx->params.mode, ctx->params.lighting, ctx->dtype, ctx->stream);
+  CU(cudaGetLastError());
+  if (iso) {   // GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2763-2830)
+    const tvk_render_params& p = ctx->params;
+    float a[3], d[3], s[3];
+    for (int i = 0; i < 3; i++) {
+      a[i] = p.ambient[i] * p.ambient[3];
+      d[i] = p.diffuse[i] * p.diffuse[3] * p.iso_color[i];
+      s[i] = p.specular[i] * p.specular[3];
+    }
+    launch_iso_compose(ctx->buf[0], ctx->buf[5], ctx->buf[6], p.width, p.height, a, d, s, p.light_dir, ctx->stream);
+    CU(cudaGetLastError());
+  }
+  ctx->cur = nxt;      // swap current/next resume buffers (GLGridLeaper.cpp:861-862)
+  ctx->blank = false;
+  return TVK_OK;
+}
+
+float4* result_image(tvk_ctx* ctx) { return ctx->params.mode == TVK_RM_ISOSURFACE ? ctx->buf[6] : ctx->buf[0]; }
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+uint32_t tvk_abi_version(void) { return TVK_ABI_VERSION; }
+
+const char* tvk_last_error(const tvk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int tvk_create(const tvk_device_cfg* cfg, tvk_ctx** out) {
+  if (!out) return fail(nullptr, TVK_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, TVK_ERR_NO_DEVICE, "no CUDA device (%s); libtvkcuda has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  tvk_ctx* ctx = new tvk_ctx();
+  if (cfg) ctx->cfg = *cfg;
+  if (ctx->cfg.device < 0 || ctx->cfg.device >= n_dev) {
+    fail(nullptr, TVK_ERR_INVALID, "device %d out of range (0..%d)", ctx->cfg.device, n_dev - 1);
+    delete ctx;
+    return TVK_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, ctx->cfg.device);
+  if (prop.major != 10) {
+    fail(nullptr, TVK_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", ctx->cfg.device,
+         prop.major, prop.minor);
+    delete ctx;
+    return TVK_ERR_NO_DEVICE;
+  }
+  if (ctx->cfg.max_gpu_mem == 0) ctx->cfg.max_gpu_mem = 8ull << 30;   // SystemInfo default
+  if (ctx->cfg.max_pool_dim == 0) ctx->cfg.max_pool_dim = 16384;
+  if (ctx->cfg.hash_table_size == 0) ctx->cfg.hash_table_size = 509;
+  if (ctx->cfg.rehash_count == 0) ctx->cfg.rehash_count = 10;
+  if (!cfg) ctx->cfg.brick_strategy = TVK_BS_SKIP_TWO_LEVELS;
+  bool ok = cudaSetDevice(ctx->cfg.device) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->counters_d, 4 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->counters_h, 4 * sizeof(unsigned long long)) == cudaSuccess;
+  if (!ok) {
+    fail(nullptr, TVK_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return TVK_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return TVK_OK;
+}
+
+void tvk_destroy(tvk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaDeviceSynchronize();
+  free_frame(ctx);
+  free_pool(ctx);
+  free_dataset(ctx);
+  if (ctx->tf1d_d) cudaFree(ctx->tf1d_d);
+  if (ctx->tf2d_d) cudaFree(ctx->tf2d_d);
+  if (ctx->read_h) cudaFreeHost(ctx->read_h);
+  if (ctx->counters_d) cudaFree(ctx->counters_d);
+  if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+int tvk_set_log_callback(tvk_ctx* ctx, tvk_log_cb cb, void* user) {
+  if (!ctx) return TVK_ERR_INVALID;
+  ctx->log_cb = cb; ctx->log_user = user;
+  return TVK_OK;
+}
+
+int tvk_set_stream(tvk_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return TVK_ERR_INVALID;
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return TVK_OK;
+}
+
+int tvk_synchronize(tvk_ctx* ctx) {
+  if (!ctx) return TVK_ERR_INVALID;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TVK_OK;
+}
+
+int tvk_enable_counters(tvk_ctx* ctx, int enable) {
+  if (!ctx) return TVK_ERR_INVALID;
+  ctx->counters_on = enable != 0;
+  return TVK_OK;
+}
+
+// ---- dataset ------------------------------------------------------------------------------------
+static int set_geometry(tvk_ctx* ctx, const uint32_t size[3], const float scale[3], const uint32_t max_brick[3],
+                        uint32_t overlap, int dtype, double range_max, float max_grad) {
+  if (dtype < TVK_U8 || dtype > TVK_F32) return fail(ctx, TVK_ERR_INVALID, "unsupported dtype %d", dtype);
+  for (int i = 0; i < 3; i++) {
+    if (size[i] == 0) return fail(ctx, TVK_ERR_INVALID, "empty domain");
+    if (max_brick[i] <= 2 * overlap) return fail(ctx, TVK_ERR_INVALID, "brick size must exceed 2*overlap");
+    if ((max_brick[i] - 2 * overlap) % 2) return fail(ctx, TVK_ERR_INVALID, "odd inner brick sizes are not supported");
+  }
+  cudaSetDevice(ctx->cfg.device);
+  free_pool(ctx);
+  free_dataset(ctx);
+  for (int i = 0; i < 3; i++) {
+    ctx->vol[i] = size[i]; ctx->scale[i] = scale ? scale[i] : 1.0f; ctx->brick[i] = max_brick[i];
+    ctx->inner[i] = max_brick[i] - 2 * overlap;
+  }
+  ctx->overlap = overlap;
+  ctx->dtype = dtype;
+  ctx->esize = esize_of(dtype);
+  ctx->range_max = range_max > 0 ? range_max : (dtype == TVK_U8 ? 255.0 : dtype == TVK_U16 ? 65535.0 : 1.0);
+  ctx->max_grad = max_grad;
+  return compute_geometry(ctx);
+}
+
+int tvk_set_volume(tvk_ctx* ctx, const tvk_volume_desc* d, tvk_brick_cb cb, void* user) {
+  if (!ctx || !d || !cb || !d->minmax) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  int rc = set_geometry(ctx, d->domain_size, d->scale, d->max_brick_size, d->overlap, d->dtype, d->range_max,
+                        d->max_gradient_magnitude);
+  if (rc) return rc;
+  if (d->brick_count < ctx->total_bricks)
+    return fail(ctx, TVK_ERR_INVALID, "min/max table has %llu entries, the pool LoDs need %u",
+                (unsigned long long)d->brick_count, ctx->total_bricks);
+  ctx->n_bricks_all = d->brick_count;
+  ctx->minmax_h.assign(d->minmax, d->minmax + 4 * (size_t)ctx->total_bricks);
+  CU(cudaMalloc(&ctx->minmax_d, ctx->minmax_h.size() * sizeof(double)));
+  CU(cudaMemcpy(ctx->minmax_d, ctx->minmax_h.data(), ctx->minmax_h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->cb = cb; ctx->cb_user = user;
+  ctx->have_volume = true;
+  return TVK_OK;
+}
+
+int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uint32_t size[3], int dtype,
+                     const float scale[3], const uint32_t max_brick_size[3], uint32_t overlap, int clamp_to_edge,
+                     double range_max, float max_gradient_magnitude) {
+  if (!ctx || !raw || !size || !max_brick_size) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  int rc = set_geometry(ctx, size, scale, max_brick_size, overlap, dtype, range_max, max_gradient_magnitude);
+  if (rc) return rc;
+  ctx->cb = nullptr; ctx->cb_user = nullptr;
+  const uint64_t n0 = (uint64_t)size[0] * size[1] * size[2];
+  void* lod_prev = nullptr;
+  void* lod_own0 = nullptr;
+  if (raw_on_device) lod_prev = const_cast<void*>(raw);
+  else {
+    CU(cudaMalloc(&lod_own0, n0 * ctx->esize));
+    CU(cudaMemcpyAsync(lod_own0, raw, n0 * ctx->esize, cudaMemcpyHostToDevice, ctx->stream));
+    lod_prev = lod_own0;
+  }
+  cudaError_t e = cudaMalloc(&ctx->store_d, ctx->n_bricks_all * ctx->slot_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->minmax_d, ctx->n_bricks_all * 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->store_d, 0, ctx->n_bricks_all * ctx->slot_bytes, ctx->stream);
+  void* lod_cur = nullptr;
+  for (uint32_t l = 0; l < ctx->lod_count && e == cudaSuccess; l++) {
+    if (l > 0) {
+      const uint64_t n = (uint64_t)ctx->lod_size[l][0] * ctx->lod_size[l][1] * ctx->lod_size[l][2];
+      e = cudaMalloc(&lod_cur, n * ctx->esize);
+      if (e != cudaSuccess) break;
+      launch_downsample(lod_prev, ctx->lod_size[l - 1], lod_cur, ctx->lod_size[l], dtype, ctx->stream);
+      if (lod_prev != raw) { cudaStreamSynchronize(ctx->stream); cudaFree(lod_prev); }
+      lod_prev = lod_cur;
+    }
+    CutConsts cc{};
+    for (int i = 0; i < 3; i++) { cc.lod_size[i] = ctx->lod_size[l][i]; cc.layout[i] = ctx->layout[l][i]; cc.brick[i] = ctx->brick[i]; }
+    cc.overlap = overlap; cc.clamp = clamp_to_edge; cc.lod = (int32_t)l; cc.first_brick = ctx->toc_offset[l];
+    launch_cut_bricks(lod_prev, ctx->store_d, ctx->minmax_d, cc, dtype, ctx->slot_bytes, ctx->stream);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (lod_prev && lod_prev != raw) cudaFree(lod_prev);
+  if (e != cudaSuccess) {
+    free_dataset(ctx);
+    return fail(ctx, e == cudaErrorMemoryAllocation ? TVK_ERR_OOM : TVK_ERR_CUDA, "tvk_build_volume: %s",
+                cudaGetErrorString(e));
+  }
+  ctx->minmax_h.resize(4 * (size_t)ctx->n_bricks_all);
+  CU(cudaMemcpy(ctx->minmax_h.data(), ctx->minmax_d, ctx->minmax_h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  ctx->have_volume = true;
+  return TVK_OK;
+}
+
+int tvk_synth_volume(tvk_ctx* ctx, void* dst_device, int kind, const uint32_t size[3], int dtype, uint32_t seed) {
+  if (!ctx || !dst_device || !size) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  if (kind < 0 || kind > 2 || dtype < TVK_U8 || dtype > TVK_F32) return fail(ctx, TVK_ERR_INVALID, "bad kind/dtype");
+  cudaSetDevice(ctx->cfg.device);
+  launch_synth(dst_device, kind, size, dtype, seed, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TVK_OK;
+}
+
+int tvk_get_info(const tvk_ctx* ctx, tvk_info* o) {
+  if (!ctx || !o) return TVK_ERR_INVALID;
+  std::memset(o, 0, sizeof(*o));
+  if (!ctx->have_volume) return TVK_ERR_INVALID;
+  o->lod_count = ctx->lod_count; o->pool_lod_count = ctx->pool_lod_count; o->total_bricks = ctx->total_bricks;
+  for (uint32_t l = 0; l < ctx->lod_count; l++)
+    for (int i = 0; i < 3; i++) { o->lod_size[l][i] = ctx->lod_size[l][i]; o->brick_layout[l][i] = ctx->layout[l][i]; }
+  for (uint32_t l = 0; l < ctx->pool_lod_count; l++) o->lod_offset[l] = ctx->lod_offset[l];
+  for (int i = 0; i < 3; i++) { o->pool_size[i] = ctx->pool_size[i]; o->pool_capacity[i] = ctx->capacity[i]; o->meta_dim[i] = ctx->meta_dim[i]; }
+  o->meta_count = ctx->meta_count;
+  return TVK_OK;
+}
+
+int tvk_get_minmax(tvk_ctx* ctx, double* dst, uint64_t n_bricks) {
+  if (!ctx || !dst || !ctx->have_volume) return fail(ctx, TVK_ERR_INVALID, "no dataset");
+  if (4 * n_bricks > ctx->minmax_h.size()) return fail(ctx, TVK_ERR_INVALID, "only %zu bricks", ctx->minmax_h.size() / 4);
+  std::memcpy(dst, ctx->minmax_h.data(), 4 * n_bricks * sizeof(double));
+  return TVK_OK;
+}
+
+int tvk_get_brick_size(const tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, uint32_t out[3]) {
+  if (!ctx || !ctx->have_volume || lod >= ctx->lod_count) return TVK_ERR_INVALID;
+  const uint32_t co[3] = {x, y, z};
+  for (int i = 0; i < 3; i++) if (co[i] >= ctx->layout[lod][i]) return TVK_ERR_INVALID;
+  brick_size(ctx, co, lod, out);
+  return TVK_OK;
+}
+
+int tvk_read_brick(tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, void* dst, size_t cap) {
+  uint32_t bs[3];
+  if (!ctx || !dst) return TVK_ERR_INVALID;
+  if (tvk_get_brick_size(ctx, x, y, z, lod, bs) != TVK_OK) return fail(ctx, TVK_ERR_INVALID, "bad brick coordinates");
+  if (!ctx->store_d) return fail(ctx, TVK_ERR_INVALID, "no device brick store (dataset comes from a callback)");
+  const size_t bytes = (size_t)bs[0] * bs[1] * bs[2] * ctx->esize;
+  if (cap < bytes) return fail(ctx, TVK_ERR_INVALID, "buffer too small");
+  const uint64_t idx = ctx->toc_offset[lod] + x + (uint64_t)y * ctx->layout[lod][0] +
+                       (uint64_t)z * ctx->layout[lod][0] * ctx->layout[lod][1];
+  cudaMemcpy3DParms p{};
+  p.srcPtr = make_cudaPitchedPtr((unsigned char*)ctx->store_d + idx * ctx->slot_bytes, ctx->brick[0] * ctx->esize,
+                                 ctx->brick[0] * ctx->esize, ctx->brick[1]);
+  p.dstPtr = make_cudaPitchedPtr(dst, bs[0] * ctx->esize, bs[0] * ctx->esize, bs[1]);
+  p.extent = make_cudaExtent(bs[0] * ctx->esize, bs[1], bs[2]);
+  p.kind = cudaMemcpyDeviceToHost;
+  CU(cudaMemcpy3D(&p));
+  return TVK_OK;
+}
+
+// ---- transfer functions -------------------------------------------------------------------------
+int tvk_set_tf1d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t n, uint64_t nz_lo, uint64_t nz_hi) {
+  if (!ctx || !rgba || n < 2) return fail(ctx, TVK_ERR_INVALID, "bad 1D transfer function");
+  cudaSetDevice(ctx->cfg.device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->tf1d_n != n) {
+    if (ctx->tf1d_d) cudaFree(ctx->tf1d_d);
+    ctx->tf1d_d = nullptr;
+    CU(cudaMalloc(&ctx->tf1d_d, (size_t)n * 4));
+  }
+  CU(cudaMemcpy(ctx->tf1d_d, rgba, (size_t)n * 4, cudaMemcpyHostToDevice));
+  ctx->tf1d_n = n; ctx->tf1d_nz[0] = nz_lo; ctx->tf1d_nz[1] = nz_hi;
+  ctx->blank = true;
+  return TVK_OK;
+}
+
+int tvk_set_tf2d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, const uint64_t nz[4]) {
+  if (!ctx || !rgba || !nz || w == 0 || h == 0) return fail(ctx, TVK_ERR_INVALID, "bad 2D transfer function");
+  cudaSetDevice(ctx->cfg.device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->tf2d_w != w || ctx->tf2d_h != h) {
+    if (ctx->tf2d_d) cudaFree(ctx->tf2d_d);
+    ctx->tf2d_d = nullptr;
+    CU(cudaMalloc(&ctx->tf2d_d, (size_t)w * h * 4));
+  }
+  CU(cudaMemcpy(ctx->tf2d_d, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice));
+  ctx->tf2d_w = w; ctx->tf2d_h = h;
+  for (int i = 0; i < 4; i++) ctx->tf2d_nz[i] = nz[i];
+  ctx->blank = true;
+  return TVK_OK;
+}
+
+// ---- pool ---------------------------------------------------------------------------------------
+int tvk_create_pool(tvk_ctx* ctx, const uint32_t* pool_size) {
+  if (!ctx || !ctx->have_volume) return fail(ctx, TVK_ERR_INVALID, "no dataset registered");
+  cudaSetDevice(ctx->cfg.device);
+  free_pool(ctx);
+  if (pool_size) for (int i = 0; i < 3; i++) ctx->pool_size[i] = pool_size[i];
+  else size_pool(ctx->cfg.max_gpu_mem, ctx->esize * 8, ctx->brick, ctx->n_bricks_all, ctx->cfg.max_pool_dim, ctx->pool_size);
+  for (int i = 0; i < 3; i++) {
+    ctx->capacity[i] = ctx->pool_size[i] / ctx->brick[i];
+    if (ctx->capacity[i] == 0) return fail(ctx, TVK_ERR_INVALID, "pool smaller than one brick");
+  }
+  ctx->n_slots = ctx->capacity[0] * ctx->capacity[1] * ctx->capacity[2];
+  if (ctx->n_slots < 2) return fail(ctx, TVK_ERR_INVALID, "pool needs at least two slots");
+  ctx->slots.clear();
+  ctx->slots.reserve(ctx->n_slots);
+  for (uint32_t z = 0; z < ctx->capacity[2]; z++)
+    for (uint32_t y = 0; y < ctx->capacity[1]; y++)
+      for (uint32_t x = 0; x < ctx->capacity[0]; x++) ctx->slots.push_back(Slot{-1, 0, 0, {x, y, z}});
+  ctx->time_of_creation = 2;
+  ctx->insert_pos = 0;
+  if (!fit_1d_to_3d(ctx->total_bricks, ctx->cfg.max_pool_dim, ctx->meta_dim))
+    return fail(ctx, TVK_ERR_INVALID, "Unable to create brick metadata texture, as it needs more than the max texture size");
+  ctx->meta_count = (uint64_t)ctx->meta_dim[0] * ctx->meta_dim[1] * ctx->meta_dim[2];
+  ctx->meta_h.assign(ctx->meta_count, TVK_BI_MISSING);
+  // one extra slot of padding so a vector load at the very end never leaves the allocation
+  CU(cudaMalloc(&ctx->pool_d, ((uint64_t)ctx->n_slots + 1) * ctx->slot_bytes));
+  CU(cudaMalloc(&ctx->meta_d, ctx->meta_count * 4));
+  CU(cudaMalloc(&ctx->slot_brick_d, (size_t)ctx->n_slots * 4));
+  CU(cudaMalloc(&ctx->counts_d, 4 * sizeof(uint32_t)));
+  CU(cudaMemset(ctx->meta_d, 0, ctx->meta_count * 4));
+  CU(cudaMemset(ctx->slot_brick_d, 0xFF, (size_t)ctx->n_slots * 4));
+  CU(cudaMemset(ctx->pool_d, 0, ((uint64_t)ctx->n_slots + 1) * ctx->slot_bytes));
+  // miss-report table (GLGridLeaper::InitHashTable, GLGridLeaper.cpp:266-291)
+  ctx->hash_size = ctx->cfg.hash_table_size;
+  CU(cudaMalloc(&ctx->hash_d, (size_t)ctx->hash_size * 4));
+  CU(cudaMalloc(&ctx->miss_d, ((size_t)ctx->hash_size * 2 + 1) * 4));
+  CU(cudaMallocHost(&ctx->miss_h, ((size_t)ctx->hash_size * 2 + 1) * 4));
+  if (ctx->cb) {   // pinned + device staging for callback-sourced bricks: <= 64 MiB, >= 2 bricks
+    size_t nb = (64ull << 20) / ctx->slot_bytes;
+    nb = std::max<size_t>(2, nb & ~size_t(1));
+    ctx->stage_bricks = nb;
+    const size_t bytes = ((nb * ctx->slot_bytes + 15) & ~size_t(15)) + nb * sizeof(PageOp);
+    CU(cudaMallocHost(&ctx->stage_h, bytes));
+    CU(cudaMalloc(&ctx->stage_d, bytes));
+  }
+  ctx->have_pool = true;
+  ctx->vis = VisState();
+  // UploadFirstBrick: the single coarsest brick goes to the last slot and is never evicted
+  {
+    const uint32_t last_id = ctx->lod_offset[ctx->pool_lod_count - 1];
+    std::vector<std::pair<uint32_t, uint32_t>> meta_kv, slot_kv;
+    assign_slot(ctx, last_id, ctx->slots.size() - 1, std::numeric_limits<uint64_t>::max(), meta_kv, slot_kv);
+    CopyReq r; r.id = last_id; r.slot = slot_kv[0].first; r.co[0] = r.co[1] = r.co[2] = 0; r.co[3] = ctx->pool_lod_count - 1;
+    int rc = copy_bricks(ctx, std::vector<CopyReq>(1, r));
+    if (rc == TVK_OK) rc = scatter_u32(ctx, ctx->meta_d, meta_kv);
+    if (rc == TVK_OK) rc = scatter_u32(ctx, (uint32_t*)ctx->slot_brick_d, slot_kv);
+    if (rc) { free_pool(ctx); return rc; }
+  }
+  ctx->blank = true;
+  // RecomputeBrickVisibility() follows in the reference; it needs TF + mode, so it runs here only
+  // when they are already known and otherwise with the first tvk_set_params / tvk_render
+  if (ctx->have_params && ctx->tf1d_d) {
+    uint32_t counts[4];
+    if (!(ctx->params.mode == TVK_RM_2DTRANS && !ctx->tf2d_d)) return recompute_visibility(ctx, 1, counts);
+  }
+  return TVK_OK;
+}
+
+int tvk_recompute_visibility(tvk_ctx* ctx, int force, uint32_t counts[4]) {
+  if (!ctx) return TVK_ERR_INVALID;
+  cudaSetDevice(ctx->cfg.device);
+  return recompute_visibility(ctx, force, counts);
+}
+
+int tvk_upload_bricks(tvk_ctx* ctx, const uint32_t* ids, uint32_t n, uint32_t* out_slots, uint32_t* n_paged) {
+  if (!ctx || !ctx->have_pool || (!ids && n)) return fail(ctx, TVK_ERR_INVALID, "no pool");
+  cudaSetDevice(ctx->cfg.device);
+  int rc = upload_bricks(ctx, ids, n, out_slots, n_paged);
+  return rc;
+}
+
+int tvk_get_page_table(tvk_ctx* ctx, uint32_t* dst, uint64_t n) {
+  if (!ctx || !dst || !ctx->have_pool) return fail(ctx, TVK_ERR_INVALID, "no pool");
+  if (n > ctx->meta_count) return fail(ctx, TVK_ERR_INVALID, "table has %llu entries", (unsigned long long)ctx->meta_count);
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(dst, ctx->meta_d, n * 4, cudaMemcpyDeviceToHost));   // the DEVICE table, not the host mirror
+  return TVK_OK;
+}
+
+int tvk_get_slots(tvk_ctx* ctx, int32_t* brick_ids, uint64_t* times, uint32_t* pos3, uint32_t n_slots) {
+  if (!ctx || !ctx->have_pool || n_slots > ctx->slots.size()) return fail(ctx, TVK_ERR_INVALID, "no pool / too many slots");
+  for (uint32_t i = 0; i < n_slots; i++) {
+    if (brick_ids) brick_ids[i] = ctx->slots[i].brick_id;
+    if (times) times[i] = ctx->slots[i].time;
+    if (pos3) std::memcpy(pos3 + 3 * i, ctx->slots[i].pos, 12);
+  }
+  return TVK_OK;
+}
+
+int tvk_read_pool_slot(tvk_ctx* ctx, uint32_t slot, void* dst, size_t cap) {
+  if (!ctx || !dst || !ctx->have_pool || slot >= ctx->n_slots || cap < ctx->slot_bytes)
+    return fail(ctx, TVK_ERR_INVALID, "bad slot / buffer");
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(dst, (unsigned char*)ctx->pool_d + (uint64_t)slot * ctx->slot_bytes, ctx->slot_bytes, cudaMemcpyDeviceToHost));
+  return TVK_OK;
+}
+
+int tvk_get_missing_list(tvk_ctx* ctx, uint32_t* ids, uint32_t cap, uint32_t* n) {
+  if (!ctx || !n) return TVK_ERR_INVALID;
+  const uint32_t have = (uint32_t)(ctx->last_missing.size() / 4);
+  *n = have;
+  if (ids) std::memcpy(ids, ctx->last_missing.data(), (size_t)std::min(have, cap) * 16);
+  return TVK_OK;
+}
+
+// ---- rendering ----------------------------------------------------------------------------------
+int tvk_default_params(tvk_render_params* p, uint32_t width, uint32_t height) {
+  if (!p) return TVK_ERR_INVALID;
+  std::memset(p, 0, sizeof(*p));
+  p->mode = TVK_RM_1DTRANS;
+  p->lighting = 1;                       // m_bUseLighting(true)
+  p->sample_rate_modifier = 1.0f;
+  const float amb[4] = {1, 1, 1, 0.1f}, dif[4] = {1, 1, 1, 1.0f}, spe[4] = {1, 1, 1, 1.0f};
+  std::memcpy(p->ambient, amb, 16); std::memcpy(p->diffuse, dif, 16); std::memcpy(p->specular, spe, 16);
+  p->light_dir[0] = 0; p->light_dir[1] = 0; p->light_dir[2] = -1;
+  p->iso_color[0] = p->iso_color[1] = p->iso_color[2] = 0.5f;
+  for (int i = 0; i < 3; i++) { p->clip_min[i] = 0.0f; p->clip_max[i] = 1.0f; }
+  const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  const float eye[3] = {0, 0, 1.6f}, at[3] = {0, 0, 0}, up[3] = {0, 1, 0};
+  return tvk_compute_view(p, width, height, ident, ident, eye, at, up, 50.0f, 0.01f, 1000.0f, 1.0f);
+}
+
+int tvk_compute_view(tvk_render_params* p, uint32_t width, uint32_t height, const float rotation[16],
+                     const float translation[16], const float eye[3], const float at[3], const float up[3],
+                     float fov_deg, float z_near, float z_far, float screen_space_error) {
+  if (!p || !rotation || !translation || !eye || !at || !up || width == 0 || height == 0) return TVK_ERR_INVALID;
+  // FLOATMATRIX4::BuildLookAt (Basics/Vectors.h:1250-1265), float arithmetic like the reference
+  float F[3] = {at[0] - eye[0], at[1] - eye[1], at[2] - eye[2]};
+  float U[3] = {up[0], up[1], up[2]};
+  float S[3] = {F[1] * U[2] - F[2] * U[1], F[2] * U[0] - F[0] * U[2], F[0] * U[1] - F[1] * U[0]};
+  U[0] = S[1] * F[2] - S[2] * F[1]; U[1] = S[2] * F[0] - S[0] * F[2]; U[2] = S[0] * F[1] - S[1] * F[0];
+  auto normalize = [](float* v) {
+    const float l = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (l != 0.0f) { v[0] /= l; v[1] /= l; v[2] /= l; }
+  };
+  normalize(F); normalize(U); normalize(S);
+  auto dot = [](const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+  float view[16];
+  view[0] = S[0]; view[4] = S[1]; view[8] = S[2]; view[12] = -dot(S, eye);
+  view[1] = U[0]; view[5] = U[1]; view[9] = U[2]; view[13] = -dot(U, eye);
+  view[2] = -F[0]; view[6] = -F[1]; view[10] = -F[2]; view[14] = dot(F, eye);
+  view[3] = 0; view[7] = 0; view[11] = 0; view[15] = 1;
+  // Perspective (Vectors.h:1267-1277)
+  const float aspect = (float)width / (float)height;
+  const float fovy = fov_deg * float(3.14159265358979323846 / 180.0);
+  const float cotan = float(1.0 / tan(double(fovy) / 2.0));
+  float* pr = p->projection;
+  std::memset(pr, 0, 64);
+  pr[0] = cotan / aspect; pr[5] = cotan;
+  pr[10] = -(z_far + z_near) / (z_far - z_near); pr[14] = -2.0f * (z_far * z_near) / (z_far - z_near);
+  pr[11] = -1.0f;
+  // modelView = rotation * translation * view (GLRenderer.cpp:627), float products like FLOATMATRIX4::operator*
+  auto mulf = [](const float* a, const float* b, float* o) {
+    float t[16];
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) {
+        float s = 0.0f;
+        for (int k = 0; k < 4; k++) s += a[r * 4 + k] * b[k * 4 + c];
+        t[r * 4 + c] = s;
+      }
+    std::memcpy(o, t, 64);
+  };
+  float rt[16];
+  mulf(rotation, translation, rt);
+  mulf(rt, view, p->model_view);
+  // CullingLOD::SetScreenParams (CullingLOD.cpp:57-67), incl. its 3.1416 literal
+  p->lod_factor = 2.0f * tanf(fov_deg * ((3.1416f / 180.0f) / 2.0f)) * screen_space_error / float(height);
+  p->width = width; p->height = height;
+  p->eye[0] = eye[0]; p->eye[1] = eye[1]; p->eye[2] = eye[2];
+  return TVK_OK;
+}
+
+int tvk_set_params(tvk_ctx* ctx, const tvk_render_params* p) {
+  if (!ctx || !p) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  if (p->width == 0 || p->height == 0 || p->width > 32768 || p->height > 32768) return fail(ctx, TVK_ERR_INVALID, "bad image size");
+  if (p->mode < TVK_RM_1DTRANS || p->mode > TVK_RM_ISOSURFACE) return fail(ctx, TVK_ERR_INVALID, "Unhandled rendering mode.");
+  if (!(p->sample_rate_modifier > 0.0f)) return fail(ctx, TVK_ERR_INVALID, "sample rate modifier must be > 0");
+  ctx->params = *p;
+  ctx->have_params = true;
+  ctx->blank = true;
+  return TVK_OK;
+}
+
+int tvk_raycast_only(tvk_ctx* ctx) {
+  if (!ctx) return TVK_ERR_INVALID;
+  cudaSetDevice(ctx->cfg.device);
+  int rc = check_renderable(ctx);
+  if (rc) return rc;
+  ctx->blank = true;
+  return raycast_pass(ctx, false);
+}
+
+int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
+  if (!ctx) return TVK_ERR_INVALID;
+  cudaSetDevice(ctx->cfg.device);
+  if (st) std::memset(st, 0, sizeof(*st));
+  int rc = check_renderable(ctx);
+  if (rc) return rc;
+  // visibility follows TF / mode / isovalue changes (Changed1DTrans etc. -> RecomputeBrickVisibility)
+  uint32_t counts[4];
+  rc = recompute_visibility(ctx, 0, counts);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  CU(cudaEventRecord(ctx->ev[0], s));
+  CU(cudaMemsetAsync(ctx->hash_d, 0, (size_t)ctx->hash_size * 4, s));           // GLHashTable::ClearData
+  CU(cudaMemsetAsync(ctx->miss_d + 2 * (size_t)ctx->hash_size, 0, 4, s));
+  if (ctx->counters_on) CU(cudaMemsetAsync(ctx->counters_d, 0, 4 * sizeof(unsigned long long), s));
+  rc = raycast_pass(ctx, true);
+  if (rc) return rc;
+  CU(cudaEventRecord(ctx->ev[1], s));
+  // GLHashTable::GetData: compact on the device, read back count + (index,value) pairs
+  launch_hash_compact(ctx->hash_d, ctx->hash_size, ctx->miss_d, ctx->miss_d + 2 * (size_t)ctx->hash_size, s);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ctx->miss_h + 2 * (size_t)ctx->hash_size, ctx->miss_d + 2 * (size_t)ctx->hash_size, 4,
+                     cudaMemcpyDeviceToHost, s));
+  if (ctx->counters_on)
+    CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const uint32_t n_miss = ctx->miss_h[2 * (size_t)ctx->hash_size];
+  ctx->last_missing.clear();
+  if (n_miss) {
+    CU(cudaMemcpyAsync(ctx->miss_h, ctx->miss_d, (size_t)n_miss * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    // table order (ascending slot index) is the reference's request order
+    std::vector<std::pair<uint32_t, uint32_t>> kv(n_miss);
+    for (uint32_t i = 0; i < n_miss; i++) kv[i] = std::make_pair(ctx->miss_h[2 * i], ctx->miss_h[2 * i + 1]);
+    std::sort(kv.begin(), kv.end());
+    const uint32_t* f = ctx->pool_layout[0];
+    ctx->last_missing.resize((size_t)n_miss * 4);
+    for (uint32_t i = 0; i < n_miss; i++) {   // GLHashTable::Int2Vector (GLHashTable.cpp:65-77)
+      uint32_t idx = kv[i].second - 1;
+      const uint32_t v = f[0] * f[1] * f[2];
+      const uint32_t w = idx / v; idx -= w * v;
+      const uint32_t z = idx / (f[0] * f[1]); idx -= z * (f[0] * f[1]);
+      const uint32_t y = idx / f[0]; idx -= y * f[0];
+      uint32_t* o = &ctx->last_missing[4 * (size_t)i];
+      o[0] = idx; o[1] = y; o[2] = z; o[3] = w;
+    }
+  }
+  CU(cudaEventRecord(ctx->ev[2], s));
+  uint32_t paged = 0;
+  if (n_miss) {
+    rc = upload_bricks(ctx, ctx->last_missing.data(), n_miss, nullptr, &paged);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(ctx->ev[3], s));
+  CU(cudaEventSynchronize(ctx->ev[3]));
+  if (st) {
+    st->converged = n_miss == 0;
+    st->missing_reported = n_miss;
+    st->bricks_paged = paged;
+    if (ctx->counters_on) { st->samples = ctx->counters_h[0]; st->rays = ctx->counters_h[1]; st->brick_visits = ctx->counters_h[2]; }
+    cudaEventElapsedTime(&st->ms_raycast, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st->ms_read_htable, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&st->ms_upload_bricks, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
+  }
+  return TVK_OK;
+}
+
+int tvk_paint(tvk_ctx* ctx, uint32_t max_subframes, tvk_frame_stats* st) {
+  if (!ctx) return TVK_ERR_INVALID;
+  tvk_frame_stats acc{}, one{};
+  if (max_subframes == 0) max_subframes = 1u << 20;
+  for (uint32_t i = 0; i < max_subframes; i++) {
+    int rc = tvk_render(ctx, &one);
+    if (rc) return rc;
+    acc.converged = one.converged;
+    acc.missing_reported += one.missing_reported;
+    acc.bricks_paged += one.bricks_paged;
+    acc.samples += one.samples; acc.rays = one.rays; acc.brick_visits += one.brick_visits;
+    acc.ms_raycast += one.ms_raycast; acc.ms_read_htable += one.ms_read_htable;
+    acc.ms_upload_bricks += one.ms_upload_bricks; acc.ms_total += one.ms_total;
+    if (one.converged) break;
+    if (one.bricks_paged == 0) break;   // nothing could be paged (pool exhausted this frame): avoid spinning
+  }
+  if (st) *st = acc;
+  return TVK_OK;
+}
+
+int tvk_read_rgba8(tvk_ctx* ctx, uint8_t* dst, size_t pitch) {
+  if (!ctx || !dst || !ctx->img_w) return fail(ctx, TVK_ERR_INVALID, "nothing rendered");
+  cudaSetDevice(ctx->cfg.device);
+  const size_t n = (size_t)ctx->img_w * ctx->img_h, row = (size_t)ctx->img_w * 4;
+  if (pitch == 0) pitch = row;
+  if (pitch < row) return fail(ctx, TVK_ERR_INVALID, "pitch too small");
+  int rc = ensure_read(ctx, n * 4);
+  if (rc) return rc;
+  launch_quantize_rgba8(result_image(ctx), ctx->rgba8_d, n, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ctx->read_h, ctx->rgba8_d, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (pitch == row) std::memcpy(dst, ctx->read_h, n * 4);
+  else for (uint32_t y = 0; y < ctx->img_h; y++) std::memcpy(dst + y * pitch, (uint8_t*)ctx->read_h + y * row, row);
+  return TVK_OK;
+}
+
+int tvk_read_rgba32f(tvk_ctx* ctx, float* dst, size_t pitch) {
+  if (!ctx || !dst || !ctx->img_w) return fail(ctx, TVK_ERR_INVALID, "nothing rendered");
+  cudaSetDevice(ctx->cfg.device);
+  const size_t row = (size_t)ctx->img_w * 16;
+  if (pitch == 0) pitch = row;
+  if (pitch < row) return fail(ctx, TVK_ERR_INVALID, "pitch too small");
+  CU(cudaMemcpy2DAsync(dst, pitch, result_image(ctx), row, row, ctx->img_h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TVK_OK;
+}
+
+int tvk_get_device_image(tvk_ctx* ctx, void** dptr) {
+  if (!ctx || !dptr || !ctx->img_w) return fail(ctx, TVK_ERR_INVALID, "nothing rendered");
+  *dptr = result_image(ctx);
+  return TVK_OK;
+}
+
+int tvk_read_iso_buffers(tvk_ctx* ctx, float* hit_pos, float* hit_normal) {
+  if (!ctx || !ctx->img_w || ctx->params.mode != TVK_RM_ISOSURFACE) return fail(ctx, TVK_ERR_INVALID, "no iso frame");
+  const size_t bytes = (size_t)ctx->img_w * ctx->img_h * 16;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (hit_pos) CU(cudaMemcpy(hit_pos, ctx->buf[0], bytes, cudaMemcpyDeviceToHost));
+  if (hit_normal) CU(cudaMemcpy(hit_normal, ctx->buf[5], bytes, cudaMemcpyDeviceToHost));
+  return TVK_OK;
+}
+
+int tvk_composite_over(tvk_ctx* ctx, const void* front, const void* back, void* out, uint64_t n_pixels) {
+  if (!ctx || !front || !back || !out) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  cudaSetDevice(ctx->cfg.device);
+  launch_composite_over((const float4*)front, (const float4*)back, (float4*)out, n_pixels, ctx->stream);
+  CU(cudaGetLastError());
+  return TVK_OK;
+}
+
+int tvk_quantize_rgba8(tvk_ctx* ctx, const void* rgba32f, void* rgba8, uint64_t n_pixels) {
+  if (!ctx || !rgba32f || !rgba8) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  cudaSetDevice(ctx->cfg.device);
+  launch_quantize_rgba8((const float4*)rgba32f, (uchar4*)rgba8, n_pixels, ctx->stream);
+  CU(cudaGetLastError());
+  return TVK_OK;
+}
+
+}  // extern "C"

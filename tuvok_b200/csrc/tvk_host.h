@@ -1,0 +1,144 @@
+// tvk_host.h -- host-side state of one renderer (tvk_ctx) and small math helpers.
+#ifndef TVK_HOST_H
+#define TVK_HOST_H
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "tvk_dev.h"
+
+namespace tvk {
+
+// ---- double precision 4x4, Tuvok storage (row vectors) --------------------------------------
+inline bool inv4(const double* a, double* out) {   // Gauss-Jordan, partial pivoting
+  double m[4][8];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) { m[r][c] = a[r * 4 + c]; m[r][4 + c] = r == c ? 1.0 : 0.0; }
+  for (int c = 0; c < 4; c++) {
+    int p = c;
+    for (int r = c + 1; r < 4; r++) if (std::fabs(m[r][c]) > std::fabs(m[p][c])) p = r;
+    if (m[p][c] == 0.0) return false;
+    if (p != c) for (int k = 0; k < 8; k++) { double t = m[c][k]; m[c][k] = m[p][k]; m[p][k] = t; }
+    const double d = m[c][c];
+    for (int k = 0; k < 8; k++) m[c][k] = m[c][k] / d;
+    for (int r = 0; r < 4; r++) if (r != c) {
+      const double f = m[r][c];
+      for (int k = 0; k < 8; k++) m[r][k] = m[r][k] - f * m[c][k];
+    }
+  }
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) out[r * 4 + c] = m[r][4 + c];
+  return true;
+}
+inline void mul4(const double* a, const double* b, double* out) {
+  double t[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      double s = 0.0;
+      for (int k = 0; k < 4; k++) s = s + a[r * 4 + k] * b[k * 4 + c];
+      t[r * 4 + c] = s;
+    }
+  std::memcpy(out, t, sizeof(t));
+}
+
+// PoolSlotData (Renderer/GL/GLVolumePool.h:26-60)
+struct Slot {
+  int32_t brick_id;
+  uint64_t time;
+  uint64_t orig_time;
+  uint32_t pos[3];
+  bool was_ever_used() const { return brick_id != -1; }
+  bool contains_visible() const { return time > 1; }
+  void flag_empty() { orig_time = time; time = 1; }
+  void restore() { time = orig_time; }
+};
+
+// VisibilityState (Renderer/VisibilityState.h:15-50)
+struct VisState {
+  int mode = -1;
+  double v[4] = {0, 0, 0, 0};
+  bool needs_update(int m, double a, double b, double c, double d) {
+    const bool changed = m != mode || a != v[0] || b != v[1] || c != v[2] || d != v[3];
+    mode = m; v[0] = a; v[1] = b; v[2] = c; v[3] = d;
+    return changed;
+  }
+};
+
+}  // namespace tvk
+
+struct tvk_ctx {
+  tvk_device_cfg cfg{};
+  std::string err;
+  tvk_log_cb log_cb = nullptr;
+  void* log_user = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool counters_on = false;
+
+  // ---- dataset ----
+  bool have_volume = false;
+  uint32_t vol[3] = {0, 0, 0}, brick[3] = {0, 0, 0}, inner[3] = {0, 0, 0}, overlap = 0;
+  float scale[3] = {1, 1, 1};
+  int dtype = 0;
+  uint32_t esize = 1;
+  double range_max = 0;
+  float max_grad = 0;
+  uint32_t lod_count = 0, pool_lod_count = 0;
+  uint32_t lod_size[TVK_MAX_LOD][3]{};
+  uint32_t layout[TVK_MAX_LOD][3]{};      // octree brick counts per LOD
+  uint64_t toc_offset[TVK_MAX_LOD + 1]{}; // first TOC index of each LOD
+  uint64_t n_bricks_all = 0;              // all LODs
+  std::vector<double> minmax_h;           // 4 per brick, TOC order
+  double* minmax_d = nullptr;
+  tvk_brick_cb cb = nullptr;
+  void* cb_user = nullptr;
+  void* store_d = nullptr;                // device brick store (slot layout, TOC order) or null
+  uint64_t slot_voxels = 0, slot_bytes = 0;
+
+  // ---- transfer functions ----
+  uchar4* tf1d_d = nullptr; uint32_t tf1d_n = 0; uint64_t tf1d_nz[2] = {0, 0};
+  uchar4* tf2d_d = nullptr; uint32_t tf2d_w = 0, tf2d_h = 0; uint64_t tf2d_nz[4] = {0, 0, 0, 0};
+
+  // ---- pool ----
+  bool have_pool = false;
+  uint32_t pool_size[3] = {0, 0, 0}, capacity[3] = {0, 0, 0}, n_slots = 0;
+  void* pool_d = nullptr;
+  uint32_t lod_offset[TVK_MAX_LOD]{};     // pool brick-id offsets
+  uint32_t pool_layout[TVK_MAX_LOD][3]{};
+  uint32_t total_bricks = 0;
+  uint32_t meta_dim[3] = {0, 0, 0};
+  uint64_t meta_count = 0;
+  uint32_t* meta_d = nullptr;
+  std::vector<uint32_t> meta_h;
+  std::vector<tvk::Slot> slots;
+  int32_t* slot_brick_d = nullptr;
+  uint64_t time_of_creation = 2;
+  size_t insert_pos = 0;
+  tvk::VisState vis;
+  uint32_t* counts_d = nullptr;
+  tvk::PageOp* ops_d = nullptr; size_t ops_cap = 0;
+  // staging for callback-sourced bricks
+  void* stage_h = nullptr; void* stage_d = nullptr; size_t stage_bricks = 0;
+
+  // ---- miss reports ----
+  uint32_t hash_size = 0;
+  uint32_t* hash_d = nullptr;
+  uint32_t* miss_d = nullptr;       // (index, value) pairs + count at [2*hash_size]
+  uint32_t* miss_h = nullptr;       // pinned mirror
+  std::vector<uint32_t> last_missing;   // decoded (x,y,z,lod)
+
+  // ---- frame ----
+  tvk_render_params params{};
+  bool have_params = false;
+  bool blank = true;
+  uint32_t img_w = 0, img_h = 0;
+  float4* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // buf: 0 acc/hitpos, 1,2 resume colour/normal ping-pong, 3,4 resume pos ping-pong, 5 hit normal,
+  //      6 composed iso image, 7 unused
+  int cur = 0;
+  uchar4* rgba8_d = nullptr;
+  void* read_h = nullptr; size_t read_cap = 0;   // pinned read-back staging
+  unsigned long long* counters_d = nullptr;
+  unsigned long long* counters_h = nullptr;
+};
+
+#endif

@@ -1,0 +1,391 @@
+"""CudaGridLeaper -- host-side mirror of the reference renderer interface for the hot path.
+
+Method names and argument meaning follow tuvok::AbstrRenderer / GLGridLeaper
+(Renderer/AbstrRenderer.h:112-881, Renderer/GL/GLGridLeaper.h) so the parity tests read like
+client code of the reference: LoadDataset/RegisterDataset, Set1DTrans/Changed1DTrans,
+SetRendermode, SetUseLighting, SetSampleRateModifier, SetIsoValue, Resize, SetRotation /
+SetTranslation, Paint, CheckForRedraw, RecomputeBrickVisibility.  Everything below the method
+bodies is a call into the C ABI of libtvkcuda.so (include/tvk.h); no pixel, voxel or page-table
+entry is computed in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .tf import TransferFunction1D, TransferFunction2D
+
+RM_1DTRANS, RM_2DTRANS, RM_ISOSURFACE = L.RM_1DTRANS, L.RM_2DTRANS, L.RM_ISOSURFACE
+_NP_OF = {L.U8: np.uint8, L.U16: np.uint16, L.F32: np.float32}
+_DT_OF = {np.dtype(np.uint8): L.U8, np.dtype(np.uint16): L.U16, np.dtype(np.float32): L.F32}
+IDENTITY = np.eye(4, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def rotation_x(deg):
+    """FLOATMATRIX4::RotationX (Basics/Vectors.h), row-vector convention."""
+    a = np.float32(np.deg2rad(deg))
+    c, s = np.cos(a, dtype=np.float32), np.sin(a, dtype=np.float32)
+    m = np.eye(4, dtype=np.float32)
+    m[1, 1] = c; m[1, 2] = s; m[2, 1] = -s; m[2, 2] = c
+    return m
+
+
+def rotation_y(deg):
+    a = np.float32(np.deg2rad(deg))
+    c, s = np.cos(a, dtype=np.float32), np.sin(a, dtype=np.float32)
+    m = np.eye(4, dtype=np.float32)
+    m[0, 0] = c; m[0, 2] = -s; m[2, 0] = s; m[2, 2] = c
+    return m
+
+
+def translation(x, y, z):
+    m = np.eye(4, dtype=np.float32)
+    m[3, :3] = (x, y, z)
+    return m
+
+
+class CudaGridLeaper:
+    """One renderer == one tvk_ctx (MasterController::RequestNewVolumeRenderer + GLGridLeaper)."""
+
+    def __init__(self, device=0, max_gpu_mem=0, max_pool_dim=0, hash_table_size=0, rehash_count=0,
+                 brick_strategy=L.BS_SKIP_TWO_LEVELS):
+        self._lib = L.lib()
+        cfg = L.DeviceCfg(device, max_gpu_mem, max_pool_dim, hash_table_size, rehash_count, brick_strategy)
+        h = C.c_void_p()
+        rc = self._lib.tvk_create(C.byref(cfg), C.byref(h))
+        if rc != L.OK:
+            raise L.TvkError(rc, (self._lib.tvk_last_error(None) or b"").decode())
+        self._h = h
+        self._cb = None
+        self._keep = []
+        self.params = L.RenderParams()
+        self._lib.tvk_default_params(C.byref(self.params), 512, 512)
+        # AbstrRenderer view state (AbstrRenderer.cpp:64-69)
+        self._eye, self._at, self._up = (0.0, 0.0, 1.6), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)
+        self._fov, self._znear, self._zfar = 50.0, 0.01, 1000.0
+        self._rotation, self._translation = IDENTITY.copy(), IDENTITY.copy()
+        self._user_matrices = None
+        self._dirty = True
+        self._converged = False
+        self.tf1d = None
+        self.tf2d = None
+        self.last_stats = L.FrameStats()
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != L.OK:
+            raise L.TvkError(rc, (self._lib.tvk_last_error(self._h) or b"").decode())
+
+    def Cleanup(self):
+        if getattr(self, "_h", None):
+            self._lib.tvk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Cleanup()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        """Launch all kernels on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ck(self._lib.tvk_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self._lib.tvk_synchronize(self._h))
+
+    def enable_counters(self, on=True):
+        self._ck(self._lib.tvk_enable_counters(self._h, int(on)))
+
+    # ------------------------------------------------------------------ dataset
+    def RegisterDataset(self, domain_size, max_brick_size, overlap, dtype, minmax, get_brick, scale=(1, 1, 1),
+                        range_max=0.0, max_gradient_magnitude=0.0):
+        """LinearIndexDataset stand-in: `get_brick(x, y, z, lod) -> ndarray [sz, sy, sx]` plays
+        Dataset::GetBrick, `minmax` is MaxMinForKey for all bricks in TOC order (n, 4)."""
+        mm = np.ascontiguousarray(minmax, np.float64).reshape(-1, 4)
+        if np.isscalar(max_brick_size):
+            max_brick_size = (max_brick_size,) * 3
+        d = L.VolumeDesc()
+        d.domain_size = L.u32x3(*domain_size)
+        d.scale = L.f32x3(*scale)
+        d.max_brick_size = L.u32x3(*max_brick_size)
+        d.overlap = overlap
+        d.dtype = dtype
+        d.range_max = range_max if range_max > 0 else {L.U8: 255.0, L.U16: 65535.0, L.F32: 1.0}[dtype]
+        d.max_gradient_magnitude = max_gradient_magnitude
+        d.brick_count = mm.shape[0]
+        d.minmax = mm.ctypes.data_as(C.POINTER(C.c_double))
+        np_dt = _NP_OF[dtype]
+
+        def _cb(user, x, y, z, lod, dst, cap):
+            try:
+                b = np.ascontiguousarray(get_brick(x, y, z, lod), np_dt)
+                if b.nbytes > cap:
+                    return 2
+                C.memmove(dst, b.ctypes.data, b.nbytes)
+                return 0
+            except Exception:   # Dataset::GetBrick returning false
+                return 1
+
+        self._cb = L.BRICK_CB(_cb)
+        self._ck(self._lib.tvk_set_volume(self._h, C.byref(d), self._cb, None))
+        self._dirty = True
+
+    def BuildVolume(self, raw, max_brick_size, overlap, scale=(1, 1, 1), clamp_to_edge=False, range_max=0.0,
+                    max_gradient_magnitude=0.0, size=None, dtype=None):
+        """Brick a raw volume on the GPU (replaces the offline ExtendedOctreeConverter).  `raw` is a
+        numpy array [z, y, x] (host) or an int device pointer with `size=(nx,ny,nz)` and `dtype`."""
+        if np.isscalar(max_brick_size):
+            max_brick_size = (max_brick_size,) * 3
+        if isinstance(raw, np.ndarray):
+            raw = np.ascontiguousarray(raw)
+            size = (raw.shape[2], raw.shape[1], raw.shape[0])
+            dtype = _DT_OF[raw.dtype]
+            ptr, on_dev = _ptr(raw), 0
+        else:
+            ptr, on_dev = C.c_void_p(int(raw)), 1
+        self._ck(self._lib.tvk_build_volume(self._h, ptr, on_dev, L.u32x3(*size), dtype, L.f32x3(*scale),
+                                            L.u32x3(*max_brick_size), overlap, int(clamp_to_edge), range_max,
+                                            max_gradient_magnitude))
+        self._dirty = True
+
+    def synth_volume(self, dst_device_ptr, kind, size, dtype, seed=0x5EED):
+        self._ck(self._lib.tvk_synth_volume(self._h, C.c_void_p(int(dst_device_ptr)), kind, L.u32x3(*size), dtype, seed))
+
+    def info(self):
+        o = L.Info()
+        self._ck(self._lib.tvk_get_info(self._h, C.byref(o)))
+        return o
+
+    def minmax(self, n=None):
+        n = int(self.info().total_bricks) if n is None else int(n)
+        out = np.zeros((n, 4), np.float64)
+        self._ck(self._lib.tvk_get_minmax(self._h, _ptr(out), n))
+        return out
+
+    def brick_size(self, x, y, z, lod):
+        o = L.u32x3()
+        self._ck(self._lib.tvk_get_brick_size(self._h, x, y, z, lod, o))
+        return tuple(o)
+
+    def brick(self, x, y, z, lod, dtype):
+        s = self.brick_size(x, y, z, lod)
+        out = np.zeros((s[2], s[1], s[0]), _NP_OF[dtype])
+        self._ck(self._lib.tvk_read_brick(self._h, x, y, z, lod, _ptr(out), out.nbytes))
+        return out
+
+    # ------------------------------------------------------------------ transfer functions
+    def Set1DTrans(self, tf):
+        """tf: TransferFunction1D, or float rgba array (n, 4)."""
+        if not isinstance(tf, TransferFunction1D):
+            t = TransferFunction1D(len(tf))
+            t.Set(tf)
+            tf = t
+        self.tf1d = tf
+        self.Changed1DTrans()
+
+    def Changed1DTrans(self):
+        b = np.ascontiguousarray(self.tf1d.GetByteArray())
+        lo, hi = self.tf1d.GetNonZeroLimits()
+        self._ck(self._lib.tvk_set_tf1d(self._h, _ptr(b), b.shape[0], lo, hi))
+        self._dirty = True
+
+    def Set2DTrans(self, tf):
+        if not isinstance(tf, TransferFunction2D):
+            tf = TransferFunction2D(tf)
+        self.tf2d = tf
+        self.Changed2DTrans()
+
+    def Changed2DTrans(self):
+        b = np.ascontiguousarray(self.tf2d.GetByteArray())
+        nz = (C.c_uint64 * 4)(*self.tf2d.GetNonZeroLimits())
+        self._ck(self._lib.tvk_set_tf2d(self._h, _ptr(b), b.shape[1], b.shape[0], nz))
+        self._dirty = True
+
+    # ------------------------------------------------------------------ pool
+    def CreateVolumePool(self, pool_size=None):
+        p = L.u32x3(*pool_size) if pool_size is not None else None
+        self._ck(self._lib.tvk_create_pool(self._h, p))
+        self._dirty = True
+
+    def RecomputeBrickVisibility(self, force=True):
+        self._push_params()
+        counts = (C.c_uint32 * 4)()
+        self._ck(self._lib.tvk_recompute_visibility(self._h, int(force), counts))
+        return tuple(counts)
+
+    def UploadBricks(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint32).reshape(-1, 4)
+        out = np.zeros(len(ids), np.uint32)
+        n = C.c_uint32()
+        self._ck(self._lib.tvk_upload_bricks(self._h, _ptr(ids), len(ids), _ptr(out), C.byref(n)))
+        return n.value, out
+
+    def page_table(self):
+        n = int(self.info().meta_count)
+        out = np.zeros(n, np.uint32)
+        self._ck(self._lib.tvk_get_page_table(self._h, _ptr(out), n))
+        return out
+
+    def slots(self):
+        i = self.info()
+        n = int(i.pool_capacity[0]) * int(i.pool_capacity[1]) * int(i.pool_capacity[2])
+        ids = np.zeros(n, np.int32); t = np.zeros(n, np.uint64); pos = np.zeros((n, 3), np.uint32)
+        self._ck(self._lib.tvk_get_slots(self._h, _ptr(ids), _ptr(t), _ptr(pos), n))
+        return ids, t, pos
+
+    def pool_slot(self, slot, dtype, brick):
+        out = np.zeros((brick[2], brick[1], brick[0]), _NP_OF[dtype])
+        self._ck(self._lib.tvk_read_pool_slot(self._h, slot, _ptr(out), out.nbytes))
+        return out
+
+    def missing_list(self):
+        n = C.c_uint32()
+        self._ck(self._lib.tvk_get_missing_list(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), np.uint32)
+        if n.value:
+            self._ck(self._lib.tvk_get_missing_list(self._h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    # ------------------------------------------------------------------ AbstrRenderer state
+    def Resize(self, w, h):
+        self.params.width, self.params.height = int(w), int(h)
+        self._dirty = True
+
+    def SetRendermode(self, mode):
+        self.params.mode = int(mode)
+        self._dirty = True
+
+    def SetUseLighting(self, on):
+        self.params.lighting = int(bool(on))
+        self._dirty = True
+
+    def SetSampleRateModifier(self, v):
+        self.params.sample_rate_modifier = float(v)
+        self._dirty = True
+
+    def SetIsoValue(self, v):
+        self.params.isovalue = float(v)
+        self._dirty = True
+
+    def SetInterpolant(self, nearest):
+        self.params.nearest = int(bool(nearest))
+        self._dirty = True
+
+    def SetLightColors(self, ambient, diffuse, specular, direction):
+        self.params.ambient = L.f32x4(*ambient)
+        self.params.diffuse = L.f32x4(*diffuse)
+        self.params.specular = L.f32x4(*specular)
+        self.params.light_dir = L.f32x3(*direction)
+        self._dirty = True
+
+    def SetIsosurfaceColor(self, rgb):
+        self.params.iso_color = L.f32x3(*rgb)
+        self._dirty = True
+
+    def SetRotation(self, m):
+        self._rotation = np.ascontiguousarray(m, np.float32).reshape(4, 4)
+        self._dirty = True
+
+    def SetTranslation(self, m):
+        self._translation = np.ascontiguousarray(m, np.float32).reshape(4, 4)
+        self._dirty = True
+
+    def SetViewParameters(self, fov, znear, zfar, eye, ref, vup):
+        self._fov, self._znear, self._zfar = float(fov), float(znear), float(zfar)
+        self._eye, self._at, self._up = tuple(eye), tuple(ref), tuple(vup)
+        self._user_matrices = None
+        self._dirty = True
+
+    def SetUserMatrices(self, view, projection, lod_factor=None):
+        """AbstrRenderer::SetUserMatrices (AbstrRenderer.cpp:1557-1575): bypass BuildLookAt/Perspective."""
+        self._user_matrices = (np.ascontiguousarray(view, np.float32).reshape(4, 4),
+                               np.ascontiguousarray(projection, np.float32).reshape(4, 4), lod_factor)
+        self._dirty = True
+
+    def SetShardBox(self, clip_min, clip_max):
+        """Sort-last: restrict rays to this rank's convex brick block (normalised volume coords)."""
+        self.params.clip_min = L.f32x3(*clip_min)
+        self.params.clip_max = L.f32x3(*clip_max)
+        self._dirty = True
+
+    def _push_params(self):
+        if not self._dirty:
+            return
+        p = self.params
+        w, h = p.width, p.height
+        rot = L.f32x16(*self._rotation.reshape(-1))
+        tra = L.f32x16(*self._translation.reshape(-1))
+        self._ck(self._lib.tvk_compute_view(C.byref(p), w, h, rot, tra, L.f32x3(*self._eye), L.f32x3(*self._at),
+                                            L.f32x3(*self._up), self._fov, self._znear, self._zfar, 1.0))
+        if self._user_matrices is not None:
+            view, proj, lf = self._user_matrices
+            mv = (self._rotation @ self._translation @ view).astype(np.float32)
+            p.model_view = L.f32x16(*mv.reshape(-1))
+            p.projection = L.f32x16(*proj.reshape(-1))
+            if lf is not None:
+                p.lod_factor = lf
+        self._ck(self._lib.tvk_set_params(self._h, C.byref(p)))
+        self._dirty = False
+        self._converged = False
+
+    # ------------------------------------------------------------------ frame
+    def Paint(self):
+        """One subframe (GLGridLeaper::Render3DRegion)."""
+        self._push_params()
+        st = L.FrameStats()
+        self._ck(self._lib.tvk_render(self._h, C.byref(st)))
+        self.last_stats = st
+        self._converged = bool(st.converged)
+        return st
+
+    def CheckForRedraw(self):
+        return self._dirty or not self._converged
+
+    def PaintUntilConverged(self, max_subframes=0):
+        """`while (ren.checkForRedraw()) paint()` done inside the library."""
+        self._push_params()
+        st = L.FrameStats()
+        self._ck(self._lib.tvk_paint(self._h, max_subframes, C.byref(st)))
+        self.last_stats = st
+        self._converged = bool(st.converged)
+        return st
+
+    def RaycastOnly(self):
+        self._push_params()
+        self._ck(self._lib.tvk_raycast_only(self._h))
+
+    def ReadRGBA8(self, out=None):
+        w, h = self.params.width, self.params.height
+        if out is None:
+            out = np.zeros((h, w, 4), np.uint8)
+        self._ck(self._lib.tvk_read_rgba8(self._h, _ptr(out), 0))
+        return out
+
+    def ReadRGBA32F(self):
+        w, h = self.params.width, self.params.height
+        out = np.zeros((h, w, 4), np.float32)
+        self._ck(self._lib.tvk_read_rgba32f(self._h, _ptr(out), 0))
+        return out
+
+    def ReadIsoBuffers(self):
+        w, h = self.params.width, self.params.height
+        a = np.zeros((h, w, 4), np.float32); b = np.zeros((h, w, 4), np.float32)
+        self._ck(self._lib.tvk_read_iso_buffers(self._h, _ptr(a), _ptr(b)))
+        return a, b
+
+    def device_image_ptr(self):
+        p = C.c_void_p()
+        self._ck(self._lib.tvk_get_device_image(self._h, C.byref(p)))
+        return p.value
+
+    def composite_over(self, front_ptr, back_ptr, out_ptr, n_pixels):
+        self._ck(self._lib.tvk_composite_over(self._h, C.c_void_p(front_ptr), C.c_void_p(back_ptr),
+                                              C.c_void_p(out_ptr), n_pixels))
+
+    def quantize_rgba8(self, src_ptr, dst_ptr, n_pixels):
+        self._ck(self._lib.tvk_quantize_rgba8(self._h, C.c_void_p(src_ptr), C.c_void_p(dst_ptr), n_pixels))
