@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s and Gsamples/s of the GridLeaper hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA renderer
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement (oracle/) on host cores
+
+A "step" is one converged frame (one GLGridLeaper::Render3DRegion subframe with a fully resident
+working set) of the workload `--config` (default c3: 2048^3 u16, 36^3 bricks, 2D TF + gradient
+lighting, 1920x1080) from the next camera of a 36-step orbit.  N > 1 (torchrun): sort-last, the
+brick blocks are sharded over the ranks and the partial images binary-swap composited
+(tuvok_b200/sortlast.py); total work is fixed => "scaling": "strong".
+
+`value`   frames/s with everything resident in HBM (device-timed with CUDA events, max over ranks)
+`e2e`     frames/s through the public API with host buffers: per frame the render parameters go in
+          (host) and the RGBA8 image comes back to host memory inside the timed region
+`roofline` the traversal kernel's ALGORITHMIC HBM bytes / its measured duration vs the measured
+          HBM peak (MEASURED_PEAKS.json); the kernel is L1/LSU-bound, see DESIGN.md
+`cpu_baseline` the oracle (CPU port of the reference shader) timed on the host cores on a bounded
+          sample (down-scaled volume, same TF/mode/camera), rank 0, N=1 only
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=36)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="tvk", choices=["tvk", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--vol", type=int, default=0, help="override the cubic volume size (debugging)")
+    ap.add_argument("--cpu-vol", type=int, default=256, help="volume size of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle on the host cores
+# ------------------------------------------------------------------------------------------------
+class CpuSample:
+    """The CPU oracle (restatement of the reference GLSL, oracle/orc_render.c) on a down-scaled copy of
+    the workload: same generator / TF / mode / camera, every 4th pixel of the frame in x and y."""
+
+    def __init__(self, cfg_name, cpu_vol, threads):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle import orc
+        from scene import Scene
+        from tuvok_b200 import workloads
+        self.orc = orc
+        w = workloads.WORKLOADS[cfg_name]
+        n = min(cpu_vol, w["size"][0])
+        t1, t2 = workloads.transfer_functions(w)
+        iso = w.get("iso", 0.5) * {0: 255.0, 1: 65535.0, 2: 1.0}[w["dtype"]]
+        sw, sh = max(64, w["width"] // 4), max(64, w["height"] // 4)
+        s = Scene(kind=w["kind"], size=(n, n, n), dtype=w["dtype"], brick=min(w["brick"], n + 4),
+                  overlap=w["overlap"], mode=w["mode"], lighting=w["lighting"], width=sw, height=sh,
+                  rotation=workloads.orbit_rotation(3), tf2d=t2, isovalue=iso, max_gpu_mem=8 << 30)
+        s.tf1d = t1
+        self.threads = threads
+        self.st = s.oracle_render(threads=threads)        # paging loop until converged (untimed)
+        self.zeros = np.zeros_like(self.st["entry"])
+        # the full frame has 16x the rays and (volume / cpu_vol)x the samples per ray of the sample
+        self.scale = 16.0 * (w["size"][0] / float(n))
+        self.desc = ("%d^3 down-scale of the workload volume (same generator/TF/mode/camera), %dx%d rays "
+                     "(every 4th pixel of the frame), converged frame, %d threads" % (n, sw, sh, threads))
+
+    def frame(self):
+        """one converged oracle pass; returns (seconds, samples)"""
+        st = self.st
+        t0 = time.perf_counter()
+        _, rs = self.orc.raycast(st["params"], st["atlas"], st["meta"], st["tf"], st["entry"], self.zeros,
+                                 st["exit"], st["covered"], None, self.threads)
+        return time.perf_counter() - t0, int(rs.samples)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's algorithm on the host cores (the reference GL renderer cannot
+    be built or run: no GL/Qt/bison here or on the GPU box) == the oracle port, all threads."""
+    if rank != 0:
+        return
+    from tuvok_b200 import workloads
+    threads = os.cpu_count() or 1
+    cs = CpuSample(args.config, args.cpu_vol, threads)
+    t_begin = time.perf_counter()
+    for _ in range(args.warmup):
+        cs.frame()
+        if time.perf_counter() - t_begin > 60:
+            break
+    times, samples = [], 0
+    t_begin = time.perf_counter()
+    for _ in range(args.steps):
+        dt, samples = cs.frame()
+        times.append(dt)
+        if time.perf_counter() - t_begin > 150:
+            break
+    frame_s = float(np.mean(times))
+    sps = samples / frame_s
+    fps_equiv = 1.0 / (frame_s * cs.scale)
+    w = workloads.WORKLOADS[args.config]
+    line = {"impl": "reference", "metric": "frames_per_s", "value": fps_equiv, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": frame_s * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "gsamples_per_s": sps / 1e9,
+            "config": {"workload": w["label"], "bounded_sample": cs.desc,
+                       "note": "each step = one bounded-sample frame; value = 1 / (step time x %.0f), the frame "
+                               "rate of the full-resolution, full-size workload at the measured CPU sample rate"
+                               % cs.scale},
+            "cpu_baseline": {"value": fps_equiv, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": cs.desc, "gsamples_per_s": sps / 1e9},
+            "e2e": {"value": fps_equiv, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_tvk(args, rank, world, local_rank):
+    import torch
+    import tuvok_b200 as tb
+    from tuvok_b200 import _lib as L
+    from tuvok_b200 import sortlast, workloads
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    w = dict(workloads.WORKLOADS[args.config])
+    if args.vol:
+        w["size"] = (args.vol,) * 3
+        w["label"] = w["label"].replace(str(workloads.WORKLOADS[args.config]["size"][0]) + "^3", "%d^3" % args.vol)
+    nx, ny, nz = w["size"]
+    esize = {L.U8: 1, L.U16: 2, L.F32: 4}[w["dtype"]]
+    brick = min(w["brick"], max(w["size"]) + 2 * w["overlap"])
+    inner = brick - 2 * w["overlap"]
+    finest = [-(-v // inner) for v in w["size"]]
+    n_lods = 1
+    while max(-(-f // (1 << (n_lods - 1))) for f in finest) > 1:
+        n_lods += 1
+    hash_size = finest[0] * finest[1] * finest[2] * n_lods + 8   # collision-free: one slot per serialised id
+
+    stream = torch.cuda.current_stream()
+    r = tb.CudaGridLeaper(device=local_rank, max_gpu_mem=96 << 30, hash_table_size=hash_size)
+    r.set_stream(stream.cuda_stream)
+    t_setup = time.perf_counter()
+    raw = torch.empty(nx * ny * nz * esize, dtype=torch.uint8, device="cuda")
+    r.synth_volume(raw.data_ptr(), w["kind"], w["size"], w["dtype"], 0x5EED)
+    r.BuildVolume(raw.data_ptr(), brick, w["overlap"], size=w["size"], dtype=w["dtype"], max_gradient_magnitude=0.25)
+    del raw
+    torch.cuda.empty_cache()
+    t1, t2 = workloads.transfer_functions(w)
+    r.Set1DTrans(t1)
+    r.Set2DTrans(t2)
+    r.SetRendermode(w["mode"])
+    r.SetUseLighting(w["lighting"])
+    if "iso" in w:
+        r.SetIsoValue(w["iso"] * {L.U8: 255.0, L.U16: 65535.0, L.F32: 1.0}[w["dtype"]])
+    r.Resize(w["width"], w["height"])
+    r.CreateVolumePool()
+    info = r.info()
+    n_pixels = w["width"] * w["height"]
+    ext = np.array(w["size"], np.float64)
+    ext = ext / ext.max()
+    flayout = [np.float32(v) / np.float32(inner) for v in w["size"]]
+    flayout = [f - f * np.finfo(np.float32).eps if float(int(f)) == float(f) else f for f in flayout]
+    sl = sortlast.SortLastRenderer(r, rank, world, finest, flayout, ext) if world > 1 else None
+    n_views = 36
+
+    def set_view(i):
+        r.SetRotation(workloads.orbit_rotation(i % n_views, n_views))
+
+    def frame(i):
+        """one step on this rank; returns the stats of the (single) subframe"""
+        set_view(i)
+        if sl is None:
+            return r.Paint()
+        lo, hi, img, st = sl.render()
+        sl.gather(lo, hi, img)
+        return st
+
+    # ---- setup (untimed): page the working set of every orbit view in --------------------------
+    paged = 0
+    for i in range(n_views):
+        set_view(i)
+        st = r.PaintUntilConverged()
+        paged += st.bricks_paged
+        if not st.converged:
+            raise RuntimeError("view %d did not converge (pool too small?)" % i)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    # ---- counting pass (untimed): samples / bricks touched per view -----------------------------
+    r.enable_counters(True)
+    samples, rays, touched, visits = [], [], [], []
+    for i in range(n_views):
+        set_view(i)
+        st = r.Paint()
+        samples.append(st.samples); rays.append(st.rays); touched.append(st.bricks_touched); visits.append(st.brick_visits)
+    r.enable_counters(False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-timed resident frames ----------------------------------------------------
+    for i in range(args.warmup):
+        frame(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_ray, not_conv = 0.0, 0
+    e0.record(stream)
+    for i in range(args.steps):
+        st = frame(args.warmup + i)
+        ms_ray += st.ms_raycast
+        not_conv += 0 if st.converged else 1
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if not_conv:
+        raise RuntimeError("%d timed frames were not converged" % not_conv)
+
+    # ---- e2e: public API with host buffers (params in, RGBA8 image out to host) ----------------
+    host_img = np.zeros((w["height"], w["width"], 4), np.uint8)
+    gather_dev = None
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        set_view(args.warmup + i)
+        if sl is None:
+            r.Paint()
+            r.ReadRGBA8(host_img)
+        else:
+            lo, hi, img, _ = sl.render()
+            full = sl.gather(lo, hi, img)
+            if rank == 0:
+                if gather_dev is None:
+                    gather_dev = torch.empty(n_pixels * 4, dtype=torch.uint8, device="cuda")
+                r.quantize_rgba8(full.data_ptr(), gather_dev.data_ptr(), n_pixels)
+                host_img[...] = gather_dev.view(w["height"], w["width"], 4).cpu().numpy()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([ms_total, ms_ray, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(np.sum(samples)), float(np.sum(touched))], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total, ms_ray, e2e_ms = (float(v) for v in times.cpu())
+    samples_per_orbit, touched_per_orbit = (float(v) for v in tot.cpu())
+
+    if rank == 0:
+        k = args.steps
+        fps = k / (ms_total * 1e-3)
+        # samples of the timed steps: views cycle through the orbit
+        view_ids = [(args.warmup + i) % n_views for i in range(k)]
+        if world == 1:
+            step_samples = float(sum(samples[v] for v in view_ids))
+            step_touched = float(sum(touched[v] for v in view_ids))
+        else:
+            step_samples = samples_per_orbit * k / n_views
+            step_touched = touched_per_orbit * k / n_views
+        gsps = step_samples / (ms_total * 1e-3) / 1e9
+        slot_bytes = brick ** 3 * esize
+        # algorithmic HBM bytes per launch: every sampled brick once + page-table entries of the
+        # visited bricks + the kernel's per-pixel outputs (acc colour, resume colour, resume position)
+        alg_bytes = (step_touched * slot_bytes + step_touched * 4 + k * n_pixels * 48.0) / k / world
+        ray_ms = ms_ray / k
+        peak, which = peaks()
+        achieved = alg_bytes / (ray_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "raycast_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.config)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": k,
+            "warmup": args.warmup, "ms_per_step": ms_total / k, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": {L.U8: "u8", L.U16: "u16", L.F32: "f32"}[w["dtype"]] + "->f32",
+            "data": "synthetic", "gsamples_per_s": gsps,
+            "config": {"workload": w["label"], "volume": "V_noise seed 0x5EED" if w["kind"] == 1 else "V_sph",
+                       "camera": "36-step orbit (Ry 10deg steps, Rx 20deg), eye (0,0,1.6) fov 50",
+                       "parallelism": "sort-last x%d (binary swap)" % world if world > 1 else "single GPU",
+                       "l2_policy": "inputs larger than L2 (pool %.1f GB, %.0f MB of bricks touched per frame)" %
+                                    (info.pool_capacity[0] * info.pool_capacity[1] * info.pool_capacity[2] * slot_bytes / 1e9,
+                                     step_touched / k * slot_bytes / 1e6),
+                       "bricks_paged_in_setup": paged, "setup_s": round(setup_s, 2),
+                       "samples_per_frame": step_samples / k, "rays_per_frame": float(np.mean(rays)),
+                       "bricks_touched_per_frame": step_touched / k},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": which, "kernel": "raycast_kernel",
+                         "kernel_ms": ray_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "fetch_gbs": step_samples / k * (7 if (w["lighting"] or w["mode"] == 1) else 1) * 8 * esize
+                                      / (ray_ms * 1e-3) / 1e9 / world},
+            "e2e": {"value": k / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(C_sizeof_params()),
+                    "d2h_bytes_per_step": n_pixels * 4 + 8},
+            "gpu_launches": k * (2 if sl is None else 2 + int(np.log2(world))),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            cs = CpuSample(args.config, args.cpu_vol, threads)
+            best, n_s = min(cs.frame() for _ in range(3))
+            cpu_sps = n_s / best
+            line["cpu_baseline"] = {"value": cpu_sps / (step_samples / k), "unit": "frames/s", "cores": threads,
+                                    "kind": "port", "gsamples_per_s": cpu_sps / 1e9,
+                                    "sample": cs.desc + "; value = CPU samples/s / samples of one GPU frame"}
+        print(json.dumps(line), flush=True)
+    r.Cleanup()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def C_sizeof_params():
+    import ctypes
+    from tuvok_b200 import _lib as L
+    return ctypes.sizeof(L.RenderParams)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    run_tvk(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

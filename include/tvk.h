@@ -108,6 +108,7 @@ typedef struct {
   uint64_t samples;              /* ComputeColorFromVolume/GetVolumeHit evaluations (if counting enabled) */
   uint64_t rays;                 /* pixels covered by the volume */
   uint64_t brick_visits;         /* GetBrick calls */
+  uint64_t bricks_touched;       /* distinct non-empty bricks sampled this subframe (if counting enabled) */
   float ms_raycast;              /* PERF_RAYCAST (CUDA events) */
   float ms_read_htable;          /* PERF_READ_HTABLE + PERF_CONDENSE_HTABLE */
   float ms_upload_bricks;        /* PERF_UPLOAD_BRICKS */
@@ -223,7 +224,8 @@ int tvk_read_iso_buffers(tvk_ctx* ctx, float* hit_pos, float* hit_normal);
 
 /* ---- sort-last compositing (new) --------------------------------------- */
 /* out = front + (1-front.a)*back on n_pixels premultiplied RGBA32F device pixels
- * (Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153). out may alias front or back. */
+ * (Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153); a front pixel with alpha > 0.99
+ * (early ray termination, GLGridLeaper-blend.glsl:180) is kept as is. out may alias front or back. */
 int tvk_composite_over(tvk_ctx* ctx, const void* front, const void* back, void* out, uint64_t n_pixels);
 /* float -> unorm8 (GL read-back conversion) on device buffers */
 int tvk_quantize_rgba8(tvk_ctx* ctx, const void* rgba32f, void* rgba8, uint64_t n_pixels);

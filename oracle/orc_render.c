@@ -693,7 +693,8 @@ void orc_composite_over(const float* front, const float* back, uint64_t n_pixels
   for (uint64_t i = 0; i < n_pixels; i++) {
     const float* f = front + 4 * i;
     const float* b = back + 4 * i;
-    float oma = 1.0f - f[3];
+    /* early-terminated front rays (alpha > 0.99, GLGridLeaper-blend.glsl:180) hide what lies behind */
+    float oma = f[3] > 0.99f ? 0.0f : 1.0f - f[3];
     out[4 * i + 0] = f[0] + oma * b[0];
     out[4 * i + 1] = f[1] + oma * b[1];
     out[4 * i + 2] = f[2] + oma * b[2];

@@ -74,7 +74,8 @@ class Scene:
         n_tf = tf1d_size or {orc.U8: 256, orc.U16: 4096, orc.F32: 4096}[dtype]
         self.tf1d = TransferFunction1D(n_tf)
         self.tf1d.SetStdFunction(tf_center, tf_inv_gradient)
-        self.tf2d = tf2d if tf2d is not None else TransferFunction2D.rectangle()
+        # the reference sizes the 2D TF like the 1D one along the value axis (Get2DHistogram()->GetFilledSize())
+        self.tf2d = tf2d if tf2d is not None else TransferFunction2D.rectangle(w=n_tf, h=64)
         self.volume = synth.synth_volume(kind, self.size, dtype, seed)
         self._pool_size = pool_size
         self._hash_size = hash_size
@@ -227,7 +228,7 @@ class Scene:
         image = image.reshape(self.height, self.width, 4)
         return dict(image=image, rgba8=orc.rgba8(image), pool=pool, meta=pool.meta, stats=total, counts=counts,
                     subframes=subframes, paged=paged_total, requests=requests, outs=outs, params=p, atlas=atlas,
-                    covered=cov)
+                    covered=cov, entry=entry, exit=exit_, tf=tf, last_stats=st)
 
     # ------------------------------------------------------------- product side
     def make_renderer(self, source="device", device=0):

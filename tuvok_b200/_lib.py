@@ -47,6 +47,7 @@ class RenderParams(C.Structure):
 class FrameStats(C.Structure):
     _fields_ = [("converged", C.c_int32), ("missing_reported", C.c_uint32), ("bricks_paged", C.c_uint32),
                 ("samples", C.c_uint64), ("rays", C.c_uint64), ("brick_visits", C.c_uint64),
+                ("bricks_touched", C.c_uint64),
                 ("ms_raycast", C.c_float), ("ms_read_htable", C.c_float), ("ms_upload_bricks", C.c_float),
                 ("ms_total", C.c_float)]
 

@@ -60,7 +60,9 @@ __global__ void quantize_kernel(const float4* __restrict__ src, uchar4* __restri
 __global__ void over_kernel(const float4* front, const float4* back, float4* out, uint64_t n) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const float4 f = front[i], b = back[i];
-    const float oma = 1.0f - f.w;
+    // a front ray that terminated early (alpha > 0.99, GLGridLeaper-blend.glsl:180) hides everything behind it,
+    // exactly as the single-GPU ray would have stopped there
+    const float oma = f.w > 0.99f ? 0.0f : 1.0f - f.w;
     out[i] = make_float4(f.x + oma * b.x, f.y + oma * b.y, f.z + oma * b.z, f.w + oma * b.w);
   }
 }

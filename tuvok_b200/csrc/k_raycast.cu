@@ -271,6 +271,10 @@ __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& 
   o.norm_exit = add3(pos, scl3(dir, tm));
   o.bx = bx; o.by = by; o.bz = bz; o.bl = lod;
   if (o.empty) return found;
+  if (P.count && P.visited) {
+    const uint32_t id = P.lod_offset[lod] + bx + by * P.lod_layout_sz[lod][0] + bz * P.lod_layout_sz[lod][1];
+    atomicOr(P.visited + (id >> 5), 1u << (id & 31));
+  }
   // InfoToCoords / BrickPoolCoords / NormCoordsToPoolCoords
   const uint32_t index = info - TVK_BI_FLAG_COUNT;
   const uint32_t sx = index % P.capacity[0], sy = (index / P.capacity[0]) % P.capacity[1],

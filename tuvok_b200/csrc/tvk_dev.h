@@ -55,6 +55,7 @@ struct RayConsts {
   float4* out2;  // rayResumePos
   float4* out3;  // ISO rayResumeNormal
   unsigned long long* counters; // samples, rays, brick visits
+  uint32_t* visited;            // bitmap over page-table indices of sampled bricks (counting only)
 };
 
 // launchers (defined in the .cu files)

@@ -110,7 +110,8 @@ void free_dataset(tvk_ctx* c) {
 }
 
 void free_pool(tvk_ctx* c) {
-  void* p[] = {c->pool_d, c->meta_d, c->slot_brick_d, c->counts_d, c->ops_d, c->stage_d, c->hash_d, c->miss_d};
+  void* p[] = {c->pool_d, c->meta_d, c->slot_brick_d, c->counts_d, c->ops_d, c->stage_d, c->hash_d, c->miss_d, c->visited_d};
+  c->visited_d = nullptr;
   for (void* q : p) if (q) cudaFree(q);
   if (c->stage_h) cudaFreeHost(c->stage_h);
   if (c->miss_h) cudaFreeHost(c->miss_h);
@@ -511,6 +512,7 @@ int derive(tvk_ctx* ctx, RayConsts& u) {
   u.meta = ctx->meta_d;
   u.hash = ctx->hash_d;
   u.counters = ctx->counters_d;
+  u.visited = ctx->visited_d;
   return TVK_OK;
 }
 
@@ -863,6 +865,8 @@ int tvk_create_pool(tvk_ctx* ctx, const uint32_t* pool_size) {
   CU(cudaMalloc(&ctx->meta_d, ctx->meta_count * 4));
   CU(cudaMalloc(&ctx->slot_brick_d, (size_t)ctx->n_slots * 4));
   CU(cudaMalloc(&ctx->counts_d, 4 * sizeof(uint32_t)));
+  CU(cudaMalloc(&ctx->visited_d, (ctx->meta_count / 32 + 1) * 4));
+  ctx->visited_h.assign(ctx->meta_count / 32 + 1, 0);
   CU(cudaMemset(ctx->meta_d, 0, ctx->meta_count * 4));
   CU(cudaMemset(ctx->slot_brick_d, 0xFF, (size_t)ctx->n_slots * 4));
   CU(cudaMemset(ctx->pool_d, 0, ((uint64_t)ctx->n_slots + 1) * ctx->slot_bytes));
@@ -1050,7 +1054,10 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
   CU(cudaEventRecord(ctx->ev[0], s));
   CU(cudaMemsetAsync(ctx->hash_d, 0, (size_t)ctx->hash_size * 4, s));           // GLHashTable::ClearData
   CU(cudaMemsetAsync(ctx->miss_d + 2 * (size_t)ctx->hash_size, 0, 4, s));
-  if (ctx->counters_on) CU(cudaMemsetAsync(ctx->counters_d, 0, 4 * sizeof(unsigned long long), s));
+  if (ctx->counters_on) {
+    CU(cudaMemsetAsync(ctx->counters_d, 0, 4 * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(ctx->visited_d, 0, ctx->visited_h.size() * 4, s));
+  }
   rc = raycast_pass(ctx, true);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[1], s));
@@ -1059,8 +1066,10 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ctx->miss_h + 2 * (size_t)ctx->hash_size, ctx->miss_d + 2 * (size_t)ctx->hash_size, 4,
                      cudaMemcpyDeviceToHost, s));
-  if (ctx->counters_on)
+  if (ctx->counters_on) {
     CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ctx->visited_h.data(), ctx->visited_d, ctx->visited_h.size() * 4, cudaMemcpyDeviceToHost, s));
+  }
   CU(cudaStreamSynchronize(s));
   const uint32_t n_miss = ctx->miss_h[2 * (size_t)ctx->hash_size];
   ctx->last_missing.clear();
@@ -1095,7 +1104,12 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
     st->converged = n_miss == 0;
     st->missing_reported = n_miss;
     st->bricks_paged = paged;
-    if (ctx->counters_on) { st->samples = ctx->counters_h[0]; st->rays = ctx->counters_h[1]; st->brick_visits = ctx->counters_h[2]; }
+    if (ctx->counters_on) {
+      st->samples = ctx->counters_h[0]; st->rays = ctx->counters_h[1]; st->brick_visits = ctx->counters_h[2];
+      uint64_t t = 0;
+      for (uint32_t w : ctx->visited_h) t += (uint64_t)__builtin_popcount(w);
+      st->bricks_touched = t;
+    }
     cudaEventElapsedTime(&st->ms_raycast, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&st->ms_read_htable, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&st->ms_upload_bricks, ctx->ev[2], ctx->ev[3]);
@@ -1115,6 +1129,7 @@ int tvk_paint(tvk_ctx* ctx, uint32_t max_subframes, tvk_frame_stats* st) {
     acc.missing_reported += one.missing_reported;
     acc.bricks_paged += one.bricks_paged;
     acc.samples += one.samples; acc.rays = one.rays; acc.brick_visits += one.brick_visits;
+    acc.bricks_touched = one.bricks_touched;
     acc.ms_raycast += one.ms_raycast; acc.ms_read_htable += one.ms_read_htable;
     acc.ms_upload_bricks += one.ms_upload_bricks; acc.ms_total += one.ms_total;
     if (one.converged) break;

@@ -139,6 +139,8 @@ struct tvk_ctx {
   void* read_h = nullptr; size_t read_cap = 0;   // pinned read-back staging
   unsigned long long* counters_d = nullptr;
   unsigned long long* counters_h = nullptr;
+  uint32_t* visited_d = nullptr;
+  std::vector<uint32_t> visited_h;
 };
 
 #endif

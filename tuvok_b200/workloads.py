@@ -1,0 +1,40 @@
+"""The BASELINE.json configurations as data (no oracle imports: bench.py's GPU arm uses this)."""
+from . import _lib as L
+from . import synth
+from .tf import TransferFunction1D, TransferFunction2D
+
+# name -> dict.  Cameras: reference defaults (eye (0,0,1.6), fov 50) + a 36-step orbit
+# (rotation about Y in 10 degree steps, then 20 degrees about X), SURVEY 8d.
+WORKLOADS = {
+    # configs[0]: GLRaycaster 1D-TF, 256^3 u8 single brick, 512x512
+    "c1": dict(kind=synth.V_SPH, size=(256, 256, 256), dtype=L.U8, brick=260, overlap=2, mode=L.RM_1DTRANS,
+               lighting=False, width=512, height=512, tf=(0.3, 0.3), label="256^3 u8 single brick 1D-TF 512x512"),
+    # configs[1]: 512^3 u16 bricked 32^3+ghost, 1D TF + ERT, 1024x1024
+    "c2": dict(kind=synth.V_NOISE, size=(512, 512, 512), dtype=L.U16, brick=36, overlap=2, mode=L.RM_1DTRANS,
+               lighting=False, width=1024, height=1024, tf=(0.3, 0.4),
+               label="512^3 u16 bricked 36^3 1D-TF 1024x1024"),
+    # configs[2]: 2048^3 u16 GridLeaper, 2D TF + gradient lighting, 1920x1080 (the headline)
+    "c3": dict(kind=synth.V_NOISE, size=(2048, 2048, 2048), dtype=L.U16, brick=36, overlap=2, mode=L.RM_2DTRANS,
+               lighting=True, width=1920, height=1080, tf=(0.3, 0.4),
+               label="2048^3 u16 bricked 36^3 GridLeaper 2D-TF+lighting 1920x1080"),
+    # configs[3]: 1024^3 f32 isosurface + lighting
+    "c4": dict(kind=synth.V_SPH, size=(1024, 1024, 1024), dtype=L.F32, brick=36, overlap=2, mode=L.RM_ISOSURFACE,
+               lighting=True, width=1920, height=1080, tf=(0.3, 0.4), iso=0.35,
+               label="1024^3 f32 bricked 36^3 isosurface+lighting 1920x1080"),
+}
+
+
+def transfer_functions(w):
+    """(TransferFunction1D, TransferFunction2D) of a workload: SetStdFunction ramp on 4096 (256 for u8)
+    entries; 2D TF = one rectangular swatch, as wide as the 1D table, 256 gradient bins."""
+    n = 256 if w["dtype"] == L.U8 else 4096
+    t1 = TransferFunction1D(n)
+    t1.SetStdFunction(*w["tf"])
+    t2 = TransferFunction2D.rectangle(w=n, h=256, x0=0.02, x1=0.9, alpha_max=40)
+    return t1, t2
+
+
+def orbit_rotation(step, n_steps=36):
+    from .renderer import rotation_x, rotation_y
+    import numpy as np
+    return (rotation_y(360.0 * step / n_steps) @ rotation_x(20.0)).astype(np.float32)
