@@ -58,12 +58,12 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
@@ -71,10 +71,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -248,10 +248,12 @@ def run_tvk(args, rank, world, local_rank):
     # ---- counting pass (untimed): samples / bricks touched per view -----------------------------
     r.enable_counters(True)
     samples, rays, touched, visits = [], [], [], []
+    alive_it, warp_it = 0, 0
     for i in range(n_views):
         set_view(i)
         st = r.Paint()
         samples.append(st.samples); rays.append(st.rays); touched.append(st.bricks_touched); visits.append(st.brick_visits)
+        alive_it += st.alive_lane_iters; warp_it += st.warp_iters
     r.enable_counters(False)
 
     def barrier():
@@ -349,7 +351,9 @@ def run_tvk(args, rank, world, local_rank):
                                      step_touched / k * slot_bytes / 1e6),
                        "bricks_paged_in_setup": paged, "setup_s": round(setup_s, 2),
                        "samples_per_frame": step_samples / k, "rays_per_frame": float(np.mean(rays)),
-                       "bricks_touched_per_frame": step_touched / k},
+                       "bricks_touched_per_frame": step_touched / k,
+                       "lane_utilisation": {"sampling": float(np.sum(samples)) / max(1.0, 32.0 * warp_it),
+                                            "alive": alive_it / max(1.0, 32.0 * warp_it)}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which, "kernel": "raycast_kernel",
                          "kernel_ms": ray_ms, "algorithmic_bytes_per_launch": alg_bytes,

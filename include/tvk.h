@@ -109,6 +109,8 @@ typedef struct {
   uint64_t rays;                 /* pixels covered by the volume */
   uint64_t brick_visits;         /* GetBrick calls */
   uint64_t bricks_touched;       /* distinct non-empty bricks sampled this subframe (if counting enabled) */
+  uint64_t alive_lane_iters;     /* diagnostics: sum over lanes of loop turns with a live ray */
+  uint64_t warp_iters;           /* diagnostics: loop turns summed over warps (x32 = lane slots) */
   float ms_raycast;              /* PERF_RAYCAST (CUDA events) */
   float ms_read_htable;          /* PERF_READ_HTABLE + PERF_CONDENSE_HTABLE */
   float ms_upload_bricks;        /* PERF_UPLOAD_BRICKS */

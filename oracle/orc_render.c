@@ -23,8 +23,9 @@
  * arithmetic (documented in DESIGN.md "Arithmetic contract") that the CUDA
  * kernels restate independently:
  *   - all float ops IEEE single, evaluated left to right, no implicit FMA;
- *     explicit fmaf() only in the trilinear lerps and the texel-coordinate map
- *   - normalize(v) = v * (1/sqrt(dot(v,v))), length = sqrt(dot)
+ *     explicit fmaf() only in the trilinear lerps, the texel-coordinate map, dot products
+ *     (fma(z,z', fma(y,y', x*x'))) and the under-compositing update
+ *   - normalize(v) = v * (1/sqrt(dot(v,v))), length = sqrt(dot), v/len = v * (1/len)
  *   - uint(log2(x)) = exponent of x (0 for x < 1)
  *   - pow(x, 8) = ((x*x)^2)^2; pow(x, oc) is the identity for oc == 1, powf otherwise
  *   - unorm texels are filtered as raw integers and scaled once by 1/(2^bits-1)
@@ -51,7 +52,7 @@ static inline v3 sub3(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); 
 static inline v3 mul3(v3 a, v3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline v3 div3(v3 a, v3 b) { return V3(a.x / b.x, a.y / b.y, a.z / b.z); }
 static inline v3 scl3(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
-static inline float dot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline float dot3(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 static inline float len3(v3 a) { return sqrtf(dot3(a, a)); }
 static inline v3 norm3(v3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return scl3(a, inv); }
 static inline float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -292,7 +293,7 @@ static v3 compute_normal(const ctx_t* c, v3 ctr, v3 delta, v3 domain_scale) {
   v3 g = gradient(c, ctr, delta);
   v3 n = mul3(g, domain_scale);
   float l = len3(n);
-  if (l > 0.0f) n = V3(n.x / l, n.y / l, n.z / l);
+  if (l > 0.0f) n = scl3(n, 1.0f / l);
   return n;
 }
 
@@ -344,7 +345,7 @@ static v4 color_from_volume(ctx_t* c, v3 pc, v3 model_pos, v3 delta) {
   float gm = len3(g);
   col = tf_lookup(c, data * p->trans_scale, 1.0f - gm * p->gradient_scale);
   if (!p->lighting) return col;
-  v3 gn = gm > 0.0f ? V3(g.x / gm, g.y / gm, g.z / gm) : g;
+  v3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
   v3 n = mul3(u->domain_scale, gn);
   v3 lit = lighting(u->eye_m, model_pos, n, u->light_a,
                     mul3(V3(col.x, col.y, col.z), u->light_d), u->light_s, u->light_dir_m);
@@ -536,10 +537,10 @@ static void trace_pixel(ctx_t* c, const float* ray_start, const float* start_col
               col.w = opacity_correct(u, col.w);
               /* UnderCompositing */
               float oma = 1.0f - acc.w;
-              acc.x = acc.x + col.x * oma * col.w;
-              acc.y = acc.y + col.y * oma * col.w;
-              acc.z = acc.z + col.z * oma * col.w;
-              acc.w = acc.w + col.w * oma;
+              acc.x = fmaf(col.x * oma, col.w, acc.x);
+              acc.y = fmaf(col.y * oma, col.w, acc.y);
+              acc.z = fmaf(col.z * oma, col.w, acc.z);
+              acc.w = fmaf(col.w, oma, acc.w);
               if (acc.w > 0.99f) { terminated = 1; break; }
             } else {
               c->samples++;

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvkcuda.so")
+# TVK_LIB: developer override to A/B-test kernel build variants (still an in-tree libtvkcuda build)
+LIB_PATH = os.environ.get("TVK_LIB") or os.path.join(_HERE, "libtvkcuda.so")
 
 TVK_MAX_LOD = 16
 U8, U16, F32 = 0, 1, 2
@@ -47,7 +48,7 @@ class RenderParams(C.Structure):
 class FrameStats(C.Structure):
     _fields_ = [("converged", C.c_int32), ("missing_reported", C.c_uint32), ("bricks_paged", C.c_uint32),
                 ("samples", C.c_uint64), ("rays", C.c_uint64), ("brick_visits", C.c_uint64),
-                ("bricks_touched", C.c_uint64),
+                ("bricks_touched", C.c_uint64), ("alive_lane_iters", C.c_uint64), ("warp_iters", C.c_uint64),
                 ("ms_raycast", C.c_float), ("ms_read_htable", C.c_float), ("ms_upload_bricks", C.c_float),
                 ("ms_total", C.c_float)]
 

@@ -15,6 +15,11 @@ constexpr int kSMs = 148;
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 __device__ __forceinline__ float pow8(float x) { float a = x * x; float b = a * a; return b * b; }
 
+// dot products follow the arithmetic contract: fma(z,z', fma(y,y', x*x'))
+__device__ __forceinline__ float dot(float ax, float ay, float az, float bx, float by, float bz) {
+  return fmaf(az, bz, fmaf(ay, by, ax * bx));
+}
+
 struct ComposeConsts { float amb[3], dif[3], spe[3], ldir[3]; };
 
 __global__ void iso_compose_kernel(const float4* __restrict__ hit_pos, const float4* __restrict__ hit_nrm,
@@ -26,15 +31,15 @@ __global__ void iso_compose_kernel(const float4* __restrict__ hit_pos, const flo
       const float4 hn = hit_nrm[i];
       const float nx = hn.x, ny = hn.y, nz = fabsf(hn.z);
       float vx = 0.0f - hp.x, vy = 0.0f - hp.y, vz = 0.0f - hp.z;
-      float inv = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);
+      float inv = 1.0f / sqrtf(dot(vx, vy, vz, vx, vy, vz));
       vx = vx * inv; vy = vy * inv; vz = vz * inv;
-      const float dn = nx * vx + ny * vy + nz * vz;
+      const float dn = dot(nx, ny, nz, vx, vy, vz);
       const float k = 2.0f * dn;
       float rx = vx - nx * k, ry = vy - ny * k, rz = vz - nz * k;
-      inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
+      inv = 1.0f / sqrtf(dot(rx, ry, rz, rx, ry, rz));
       rx = rx * inv; ry = ry * inv; rz = rz * inv;
-      const float dl = fmaxf(fabsf(nx * (-C.ldir[0]) + ny * (-C.ldir[1]) + nz * (-C.ldir[2])), 0.0f);
-      const float sp = pow8(fmaxf(rx * C.ldir[0] + ry * C.ldir[1] + rz * C.ldir[2], 0.0f));
+      const float dl = fmaxf(fabsf(dot(nx, ny, nz, -C.ldir[0], -C.ldir[1], -C.ldir[2])), 0.0f);
+      const float sp = pow8(fmaxf(dot(rx, ry, rz, C.ldir[0], C.ldir[1], C.ldir[2]), 0.0f));
       o.x = clamp01(C.amb[0] + C.dif[0] * dl + C.spe[0] * sp);
       o.y = clamp01(C.amb[1] + C.dif[1] * dl + C.spe[1] * sp);
       o.z = clamp01(C.amb[2] + C.dif[2] * dl + C.spe[2] * sp);

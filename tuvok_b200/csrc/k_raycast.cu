@@ -17,11 +17,16 @@
 // atlas of capacity*brick voxels) so the arithmetic stays the reference's; only the final
 // texel address is slot-local.
 //
+// Control flow: the shader's nested loops (bricks along the ray / samples inside a brick) are run
+// as one flat per-warp loop with a "fetch next brick" phase and a "take one sample" phase, so
+// lanes whose brick ends early do not idle until the slowest lane of the warp finishes its brick;
+// per ray the sequence of operations is exactly the shader's.
+//
 // Arithmetic contract: IEEE fp32, no implicit FMA contraction (this file is compiled
-// with -fmad=false); fmaf() exactly where the contract names it (texel-coordinate map and the
-// trilinear lerps).  Gradient taps sit exactly +-1 texel from the centre sample and share its
-// filter fractions (the GLSL adds sampleDelta = 1/poolSize in texture coordinates, i.e. one
-// texel; the precision of that is implementation-defined in GL).
+// with -fmad=false); fmaf() exactly where the contract names it (texel-coordinate map, trilinear
+// lerps, dot products, under-compositing).  Gradient taps sit exactly +-1 texel from the centre
+// sample and share its filter fractions (the GLSL adds sampleDelta = 1/poolSize in texture
+// coordinates, i.e. one texel; the precision of that is implementation-defined in GL).
 #include "tvk_dev.h"
 
 namespace tvk {
@@ -36,7 +41,7 @@ __device__ __forceinline__ f3 sub3(f3 a, f3 b) { return F3(a.x - b.x, a.y - b.y,
 __device__ __forceinline__ f3 mul3(f3 a, f3 b) { return F3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ f3 div3(f3 a, f3 b) { return F3(a.x / b.x, a.y / b.y, a.z / b.z); }
 __device__ __forceinline__ f3 scl3(f3 a, float s) { return F3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 __device__ __forceinline__ float len3(f3 a) { return sqrtf(dot3(a, a)); }
 __device__ __forceinline__ f3 norm3(f3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return scl3(a, inv); }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -59,42 +64,11 @@ struct BrickRef {
   uint64_t base;         // first voxel of the slot in the slot-linear pool
 };
 
-template <typename T> __device__ __forceinline__ float ldv(const T* p, uint64_t i) { return (float)__ldg(p + i); }
-
-// filter footprint of one sample position: 4 clamped slot-local indices per axis
-// ([X-1, X, X+1, X+2] as element offsets) and the shared fractions
-struct Foot {
-  uint32_t xo[4], yo[4], zo[4];
-  float fx, fy, fz;
-};
-
-__device__ __forceinline__ uint32_t clampi(int v, int hi) { return (uint32_t)min(max(v, 0), hi); }
-
-__device__ __forceinline__ void footprint(const RayConsts& P, const BrickRef& b, f3 tc, Foot& f) {
-  int X, Y, Z;
-  if (P.nearest) {
-    X = (int)floorf(tc.x * P.pool_size_f[0]);
-    Y = (int)floorf(tc.y * P.pool_size_f[1]);
-    Z = (int)floorf(tc.z * P.pool_size_f[2]);
-    f.fx = f.fy = f.fz = 0.0f;
-  } else {
-    float ux = fmaf(tc.x, P.pool_size_f[0], -0.5f);
-    float uy = fmaf(tc.y, P.pool_size_f[1], -0.5f);
-    float uz = fmaf(tc.z, P.pool_size_f[2], -0.5f);
-    float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
-    f.fx = ux - x0; f.fy = uy - y0; f.fz = uz - z0;
-    X = (int)x0; Y = (int)y0; Z = (int)z0;
-  }
-  X -= (int)b.ox; Y -= (int)b.oy; Z -= (int)b.oz;
-  const int tx = (int)P.total[0] - 1, ty = (int)P.total[1] - 1, tz = (int)P.total[2] - 1;
-  const uint32_t sy = P.total[0], sz = P.total[0] * P.total[1];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    f.xo[i] = clampi(X - 1 + i, tx);
-    f.yo[i] = clampi(Y - 1 + i, ty) * sy;
-    f.zo[i] = clampi(Z - 1 + i, tz) * sz;
-  }
-}
+// voxel -> float.  Integer voxels are converted with the 2^23 magic number (exact below 2^23) on the
+// FMA/ALU pipes instead of the quarter-rate I2F conversion pipe.
+__device__ __forceinline__ float cvt(uint8_t v) { return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.0f; }
+__device__ __forceinline__ float cvt(uint16_t v) { return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.0f; }
+__device__ __forceinline__ float cvt(float v) { return v; }
 
 __device__ __forceinline__ float tri(float v000, float v100, float v010, float v110, float v001, float v101,
                                      float v011, float v111, float fx, float fy, float fz) {
@@ -107,62 +81,111 @@ __device__ __forceinline__ float tri(float v000, float v100, float v010, float v
   return fmaf(fz, c1 - c0, c0);
 }
 
-// texture(volumePool, coords).r at texel offset (dx,dy,dz) from the footprint centre
-template <typename T>
-__device__ __forceinline__ float tap(const RayConsts& P, const T* vox, const Foot& f, int dx, int dy, int dz) {
-  if (P.nearest) return ldv(vox, (uint64_t)(f.xo[1 + dx] + f.yo[1 + dy] + f.zo[1 + dz])) * P.norm;
-  const uint32_t x0 = f.xo[1 + dx], x1 = f.xo[2 + dx];
-  const uint32_t y0 = f.yo[1 + dy], y1 = f.yo[2 + dy];
-  const uint32_t z0 = f.zo[1 + dz], z1 = f.zo[2 + dz];
-  return tri(ldv(vox, x0 + y0 + z0), ldv(vox, x1 + y0 + z0), ldv(vox, x0 + y1 + z0), ldv(vox, x1 + y1 + z0),
-             ldv(vox, x0 + y0 + z1), ldv(vox, x1 + y0 + z1), ldv(vox, x0 + y1 + z1), ldv(vox, x1 + y1 + z1),
-             f.fx, f.fy, f.fz) * P.norm;
-}
+// Filter footprint of one sample position inside a slot.
+//   FAST  (linear filter, ghost >= 2): the 4x4x4 neighbourhood [X-1..X+2]^3 always lies inside the
+//         slot, so one clamped centre address + uniform row strides address all 32 voxels.
+//         BS != 0 bakes a cubic brick size in (like the #defines of the reference's generated GLSL,
+//         GLVolumePool.cpp:364-400), turning the 32 voxel addresses into immediate offsets.
+//   !FAST (nearest filter or ghost < 2): every texel index is clamped to the slot like
+//         GL_CLAMP_TO_EDGE clamps it to the texture.
+template <typename T, bool FAST, int BS>
+struct Foot {
+  const T* c;            // FAST: voxel (X, Y, Z)
+  uint32_t xo[4], yo[4], zo[4];   // !FAST: clamped element offsets of X-1..X+2 etc.
+  float fx, fy, fz;
+  int sy, sz;            // row / slice stride in elements
+  bool nearest;
 
-// centre value + central-difference gradient (GLGridLeaper-GradientTools.glsl:6-16; the "Yp"
-// tap is fetched at -delta) from the 32 distinct voxels of the 7 overlapping footprints
-template <typename T>
-__device__ __forceinline__ void sample_with_gradient(const RayConsts& P, const T* vox, const Foot& f,
-                                                     float& data, f3& grad) {
-  if (P.nearest) {
-    data = tap(P, vox, f, 0, 0, 0);
-    float xp = tap(P, vox, f, 1, 0, 0), xm = tap(P, vox, f, -1, 0, 0);
-    float yp = tap(P, vox, f, 0, -1, 0), ym = tap(P, vox, f, 0, 1, 0);
-    float zp = tap(P, vox, f, 0, 0, 1), zm = tap(P, vox, f, 0, 0, -1);
-    grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
-    return;
-  }
-  float c[2][2][2];   // [z][y][x] centre block
-#pragma unroll
-  for (int k = 0; k < 2; k++)
-#pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-      for (int i = 0; i < 2; i++) c[k][j][i] = ldv(vox, f.xo[1 + i] + f.yo[1 + j] + f.zo[1 + k]);
-  float xl[2][2], xh[2][2], yl[2][2], yh[2][2], zl[2][2], zh[2][2];
-#pragma unroll
-  for (int a = 0; a < 2; a++)
-#pragma unroll
-    for (int b = 0; b < 2; b++) {
-      xl[a][b] = ldv(vox, f.xo[0] + f.yo[1 + b] + f.zo[1 + a]);   // [z][y]
-      xh[a][b] = ldv(vox, f.xo[3] + f.yo[1 + b] + f.zo[1 + a]);
-      yl[a][b] = ldv(vox, f.xo[1 + b] + f.yo[0] + f.zo[1 + a]);   // [z][x]
-      yh[a][b] = ldv(vox, f.xo[1 + b] + f.yo[3] + f.zo[1 + a]);
-      zl[a][b] = ldv(vox, f.xo[1 + b] + f.yo[1 + a] + f.zo[0]);   // [y][x]
-      zh[a][b] = ldv(vox, f.xo[1 + b] + f.yo[1 + a] + f.zo[3]);
+  __device__ __forceinline__ void set(const RayConsts& P, const T* vox, uint32_t ox, uint32_t oy, uint32_t oz, f3 tc) {
+    int X, Y, Z;
+    nearest = !FAST && P.nearest;
+    if (nearest) {
+      X = (int)floorf(tc.x * P.pool_size_f[0]);
+      Y = (int)floorf(tc.y * P.pool_size_f[1]);
+      Z = (int)floorf(tc.z * P.pool_size_f[2]);
+      fx = fy = fz = 0.0f;
+    } else {
+      const float ux = fmaf(tc.x, P.pool_size_f[0], -0.5f);
+      const float uy = fmaf(tc.y, P.pool_size_f[1], -0.5f);
+      const float uz = fmaf(tc.z, P.pool_size_f[2], -0.5f);
+      const float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
+      fx = ux - x0; fy = uy - y0; fz = uz - z0;
+      X = (int)x0; Y = (int)y0; Z = (int)z0;
     }
-  const float fx = f.fx, fy = f.fy, fz = f.fz, n = P.norm;
-  data = tri(c[0][0][0], c[0][0][1], c[0][1][0], c[0][1][1], c[1][0][0], c[1][0][1], c[1][1][0], c[1][1][1],
-             fx, fy, fz) * n;
-  float xp = tri(c[0][0][1], xh[0][0], c[0][1][1], xh[0][1], c[1][0][1], xh[1][0], c[1][1][1], xh[1][1], fx, fy, fz) * n;
-  float xm = tri(xl[0][0], c[0][0][0], xl[0][1], c[0][1][0], xl[1][0], c[1][0][0], xl[1][1], c[1][1][0], fx, fy, fz) * n;
-  // +y footprint (fetched by the shader as "Ym"), -y footprint ("Yp")
-  float ym = tri(c[0][1][0], c[0][1][1], yh[0][0], yh[0][1], c[1][1][0], c[1][1][1], yh[1][0], yh[1][1], fx, fy, fz) * n;
-  float yp = tri(yl[0][0], yl[0][1], c[0][0][0], c[0][0][1], yl[1][0], yl[1][1], c[1][0][0], c[1][0][1], fx, fy, fz) * n;
-  float zp = tri(c[1][0][0], c[1][0][1], c[1][1][0], c[1][1][1], zh[0][0], zh[0][1], zh[1][0], zh[1][1], fx, fy, fz) * n;
-  float zm = tri(zl[0][0], zl[0][1], zl[1][0], zl[1][1], c[0][0][0], c[0][0][1], c[0][1][0], c[0][1][1], fx, fy, fz) * n;
-  grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
-}
+    X -= (int)ox; Y -= (int)oy; Z -= (int)oz;
+    sy = BS ? BS : (int)P.total[0];
+    sz = BS ? BS * BS : (int)(P.total[0] * P.total[1]);
+    if (FAST) {
+      X = min(max(X, 1), (BS ? BS : (int)P.total[0]) - 3);
+      Y = min(max(Y, 1), (BS ? BS : (int)P.total[1]) - 3);
+      Z = min(max(Z, 1), (BS ? BS : (int)P.total[2]) - 3);
+      c = vox + (X + Y * sy + Z * sz);
+    } else {
+      c = vox;
+      const int tx = (int)P.total[0] - 1, ty = (int)P.total[1] - 1, tz = (int)P.total[2] - 1;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        xo[i] = (uint32_t)min(max(X - 1 + i, 0), tx);
+        yo[i] = (uint32_t)min(max(Y - 1 + i, 0), ty) * (uint32_t)sy;
+        zo[i] = (uint32_t)min(max(Z - 1 + i, 0), tz) * (uint32_t)sz;
+      }
+    }
+  }
+  // voxel at texel offset (i, j, k) in [-1, 2]^3 from the footprint origin
+  __device__ __forceinline__ float v(int i, int j, int k) const {
+    if (FAST && BS) return cvt(__ldg(c + (i + j * BS + k * BS * BS)));   // immediate offsets
+    if (FAST) return cvt(__ldg(c + (i + j * sy + k * sz)));
+    return cvt(__ldg(c + (xo[1 + i] + yo[1 + j] + zo[1 + k])));
+  }
+  // texture(volumePool, coords).r at texel offset (dx,dy,dz)
+  __device__ __forceinline__ float tap(const RayConsts& P, int dx, int dy, int dz) const {
+    if (nearest) return v(dx, dy, dz) * P.norm;
+    return tri(v(dx, dy, dz), v(dx + 1, dy, dz), v(dx, dy + 1, dz), v(dx + 1, dy + 1, dz), v(dx, dy, dz + 1),
+               v(dx + 1, dy, dz + 1), v(dx, dy + 1, dz + 1), v(dx + 1, dy + 1, dz + 1), fx, fy, fz) * P.norm;
+  }
+  // centre value + central-difference gradient (GLGridLeaper-GradientTools.glsl:6-16; the "Yp" tap is
+  // fetched at -delta) from the 32 distinct voxels of the 7 overlapping footprints
+  __device__ __forceinline__ void sample_with_gradient(const RayConsts& P, float& data, f3& grad) const {
+    if (nearest) {
+      data = tap(P, 0, 0, 0);
+      const float xp = tap(P, 1, 0, 0), xm = tap(P, -1, 0, 0);
+      const float yp = tap(P, 0, -1, 0), ym = tap(P, 0, 1, 0);
+      const float zp = tap(P, 0, 0, 1), zm = tap(P, 0, 0, -1);
+      grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+      return;
+    }
+    float cc[2][2][2];   // [z][y][x] centre block
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int i = 0; i < 2; i++) cc[k][j][i] = v(i, j, k);
+    float xl[2][2], xh[2][2], yl[2][2], yh[2][2], zl[2][2], zh[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        xl[a][b] = v(-1, b, a);   // [z][y]
+        xh[a][b] = v(2, b, a);
+        yl[a][b] = v(b, -1, a);   // [z][x]
+        yh[a][b] = v(b, 2, a);
+        zl[a][b] = v(b, a, -1);   // [y][x]
+        zh[a][b] = v(b, a, 2);
+      }
+    const float n = P.norm;
+    data = tri(cc[0][0][0], cc[0][0][1], cc[0][1][0], cc[0][1][1], cc[1][0][0], cc[1][0][1], cc[1][1][0], cc[1][1][1],
+               fx, fy, fz) * n;
+    const float xp = tri(cc[0][0][1], xh[0][0], cc[0][1][1], xh[0][1], cc[1][0][1], xh[1][0], cc[1][1][1], xh[1][1], fx, fy, fz) * n;
+    const float xm = tri(xl[0][0], cc[0][0][0], xl[0][1], cc[0][1][0], xl[1][0], cc[1][0][0], xl[1][1], cc[1][1][0], fx, fy, fz) * n;
+    // +y footprint (fetched by the shader as "Ym"), -y footprint ("Yp")
+    const float ym = tri(cc[0][1][0], cc[0][1][1], yh[0][0], yh[0][1], cc[1][1][0], cc[1][1][1], yh[1][0], yh[1][1], fx, fy, fz) * n;
+    const float yp = tri(yl[0][0], yl[0][1], cc[0][0][0], cc[0][0][1], yl[1][0], yl[1][1], cc[1][0][0], cc[1][0][1], fx, fy, fz) * n;
+    const float zp = tri(cc[1][0][0], cc[1][0][1], cc[1][1][0], cc[1][1][1], zh[0][0], zh[0][1], zh[1][0], zh[1][1], fx, fy, fz) * n;
+    const float zm = tri(zl[0][0], zl[0][1], zl[1][0], zl[1][1], cc[0][0][0], cc[0][0][1], cc[0][1][0], cc[0][1][1], fx, fy, fz) * n;
+    grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+  }
+};
 
 __device__ __forceinline__ float pow8(float x) { float a = x * x; float b = a * a; return b * b; }
 
@@ -178,10 +201,10 @@ __device__ __forceinline__ f3 lighting(f3 eye, f3 pos, f3 n, f3 amb, f3 dif, f3 
             clampf(amb.z + dif.z * dl + spe.z * sp, 0.0f, 1.0f));
 }
 
-// RGBA8, GL_NEAREST, clamp-to-edge (GPUMemMan.cpp:398-401, GLTexture1D.h:48-51)
-template <bool SMEM_TF>
-__device__ __forceinline__ f4 tf_lookup(const RayConsts& P, const uchar4* s_tf, float s, float t) {
-  int w = (int)P.tf_w, h = (int)P.tf_h;
+// RGBA8 table, GL_NEAREST, clamp-to-edge (GPUMemMan.cpp:398-401, GLTexture1D.h:48-51).  The table is
+// kept as float4 = byte/255.0f (the unorm8 -> float conversion of the texture unit, done once on upload).
+__device__ __forceinline__ f4 tf_lookup(const RayConsts& P, float s, float t) {
+  const int w = (int)P.tf_w, h = (int)P.tf_h;
   int ix = (int)floorf(s * (float)w);
   ix = min(max(ix, 0), w - 1);
   int iy = 0;
@@ -189,9 +212,8 @@ __device__ __forceinline__ f4 tf_lookup(const RayConsts& P, const uchar4* s_tf, 
     iy = (int)floorf(t * (float)h);
     iy = min(max(iy, 0), h - 1);
   }
-  uchar4 q = SMEM_TF ? s_tf[iy * w + ix] : __ldg(P.tf + (size_t)iy * w + ix);
-  f4 r;
-  r.x = (float)q.x / 255.0f; r.y = (float)q.y / 255.0f; r.z = (float)q.z / 255.0f; r.w = (float)q.w / 255.0f;
+  const float4 q = __ldg(P.tf + (size_t)iy * w + ix);
+  f4 r; r.x = q.x; r.y = q.y; r.z = q.z; r.w = q.w;
   return r;
 }
 
@@ -201,9 +223,11 @@ __device__ __forceinline__ void brick_coords(const RayConsts& P, f3 pos, uint32_
   y = (uint32_t)(pos.y * P.lod_layout[lod][1]);
   z = (uint32_t)(pos.z * P.lod_layout[lod][2]);
 }
+__device__ __forceinline__ uint32_t brick_index(const RayConsts& P, uint32_t x, uint32_t y, uint32_t z, uint32_t lod) {
+  return P.lod_offset[lod] + x + y * P.lod_layout_sz[lod][0] + z * P.lod_layout_sz[lod][1];
+}
 __device__ __forceinline__ uint32_t brick_info(const RayConsts& P, uint32_t x, uint32_t y, uint32_t z, uint32_t lod) {
-  uint32_t idx = P.lod_offset[lod] + x + y * P.lod_layout_sz[lod][0] + z * P.lod_layout_sz[lod][1];
-  return __ldg(P.meta + idx);
+  return __ldg(P.meta + brick_index(P, x, y, z, lod));
 }
 
 // GLHashTable.cpp:140-182.  Rays of a warp that miss the same brick elect one reporter first
@@ -223,10 +247,8 @@ __device__ __forceinline__ void report_missing(const RayConsts& P, uint32_t x, u
   } while (++rehash < P.rehash_count);
 }
 
-__device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& lod, f3 dir, BrickRef& o,
-                                          unsigned long long& n_bricks) {
+__device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& lod, f3 dir, f3 dv, BrickRef& o) {
   const uint32_t max_lod = P.lod_count - 1;
-  n_bricks++;
   pos = F3(clampf(pos.x, 0.0f, 1.0f), clampf(pos.y, 0.0f, 1.0f), clampf(pos.z, 0.0f, 1.0f));
   bool found = true;
   uint32_t bx, by, bz;
@@ -263,7 +285,6 @@ __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& 
   const f3 lay = F3(P.lod_layout[lod]);
   const f3 c0 = div3(F3((float)bx, (float)by, (float)bz), lay);
   const f3 c1 = div3(F3((float)(bx + 1), (float)(by + 1), (float)(bz + 1)), lay);
-  const f3 dv = F3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
   float tx = ((dv.x < 0.0f ? c0.x : c1.x) - pos.x) * dv.x;
   float ty = ((dv.y < 0.0f ? c0.y : c1.y) - pos.y) * dv.y;
   float tz = ((dv.z < 0.0f ? c0.z : c1.z) - pos.z) * dv.z;
@@ -271,8 +292,8 @@ __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& 
   o.norm_exit = add3(pos, scl3(dir, tm));
   o.bx = bx; o.by = by; o.bz = bz; o.bl = lod;
   if (o.empty) return found;
-  if (P.count && P.visited) {
-    const uint32_t id = P.lod_offset[lod] + bx + by * P.lod_layout_sz[lod][0] + bz * P.lod_layout_sz[lod][1];
+  if (P.count && P.visited) {   // only set by the counting launch
+    const uint32_t id = brick_index(P, bx, by, bz, lod);
     atomicOr(P.visited + (id >> 5), 1u << (id & 31));
   }
   // InfoToCoords / BrickPoolCoords / NormCoordsToPoolCoords
@@ -344,15 +365,17 @@ __device__ __forceinline__ bool ray_setup(const RayConsts& P, uint32_t px, uint3
 __device__ __forceinline__ float4 to4(f4 v) { return make_float4(v.x, v.y, v.z, v.w); }
 __device__ __forceinline__ f4 from4(float4 v) { f4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
 
+#ifndef TVK_FETCH_LANES
+#define TVK_FETCH_LANES 32
+#endif
+constexpr int kFetchLanes = TVK_FETCH_LANES;
+#ifndef TVK_MIN_BLOCKS
+#define TVK_MIN_BLOCKS 8
+#endif
+
 // MODE: 0 = 1D TF, 1 = 2D TF, 2 = isosurface
-template <typename T, int MODE, bool LIT, bool SMEM_TF>
-__global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ RayConsts P) {
-  extern __shared__ uchar4 s_tf[];
-  if (SMEM_TF) {
-    const uint32_t n = P.tf_w * P.tf_h;
-    for (uint32_t i = threadIdx.x + threadIdx.y * blockDim.x; i < n; i += blockDim.x * blockDim.y) s_tf[i] = P.tf[i];
-    __syncthreads();
-  }
+template <typename T, int MODE, bool LIT, bool FAST, int BS, bool COUNT>
+__global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RayConsts P) {
   const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t py = blockIdx.y * blockDim.y + threadIdx.y;
   if (px >= P.width || py >= P.height) return;
@@ -360,6 +383,7 @@ __global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ Ray
   constexpr bool ISO = MODE == 2;
   const T* pool = (const T*)P.pool;
   unsigned long long n_samples = 0, n_bricks = 0;
+  unsigned long long n_alive_iters = 0, n_warp_iters = 0;   // lane-utilisation diagnostics (count mode)
 
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   f4 entry4, exit4;
@@ -411,111 +435,145 @@ __global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ Ray
     const float voxel_size = 0.125f / 2000.0f;
     f3 cur = entry;
     uint32_t lbx = 0, lby = 0, lbz = 0, lbl = 9999;
-    bool terminated = false;
     const f3 dscale = F3(P.domain_scale), eye_m = F3(P.eye_m), la = F3(P.light_a), ld = F3(P.light_d),
              ls = F3(P.light_s), ldir = F3(P.light_dir_m);
-    if (ray_len > voxel_size) {
-      for (uint32_t j = 0; j < 100 && !terminated; ++j) {
+
+    const f3 dv = F3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);   // BrickExit's 1.0/dir
+    // the empty-brick advance voxelSize*direction/rayLength
+    const f3 nudge = F3(voxel_size * dir.x / ray_len, voxel_size * dir.y / ray_len, voxel_size * dir.z / ray_len);
+    // flat brick/sample loop state
+    bool alive = ray_len > voxel_size;
+    uint32_t j = 0;          // bricks visited (the shader's j < 100 bound)
+    int steps_left = 0;      // samples left in the current brick
+    f3 pc = entry, b_trans = entry, b_inv = entry, b_exit = entry;
+    uint32_t b_ox = 0, b_oy = 0, b_oz = 0;
+    const T* vox = pool;
+
+    while (alive) {
+      // ---- fetch phase: advance to the next brick that has samples (a few empty ones per turn).
+      // The warp only pays for it when enough lanes starve (or nobody can sample).
+      const unsigned act = __activemask();
+      const unsigned starving = __ballot_sync(act, steps_left == 0);
+      const bool do_fetch = __popc(starving) >= kFetchLanes || starving == act;
+#pragma unroll 1
+      for (int f = 0; do_fetch && f < 4 && alive && steps_left == 0; f++) {
+        if (j >= 100) { alive = false; break; }
         const float cur_depth = entry_depth * (1.0f - t) + exit_depth * t;
         uint32_t lod = compute_lod(P, cur_depth);
+        n_bricks++;
         BrickRef b;
-        const bool ok = get_brick(P, cur, lod, dir, b, n_bricks);
+        const bool ok = get_brick(P, cur, lod, dir, dv, b);
         if (!ok && optimal) {
           optimal = false;
           resume_pos.x = cur.x; resume_pos.y = cur.y; resume_pos.z = cur.z; resume_pos.w = cur_depth;
           if (!ISO) resume_col = acc;
         }
+        b_exit = b.norm_exit;
         if (!b.empty && !(lbx == b.bx && lby == b.by && lbz == b.bz && lbl == b.bl)) {
           int steps = (int)ceilf(len3(sub3(b.pool_exit, b.pool_entry)) / step);
           const int s2 = (int)ceilf(len3(mul3(sub3(nexit, cur), b.scale)) / step);
           steps = min(steps, s2);
-          const f3 inv_scale = F3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
-          const T* vox = pool + b.base;
-          f3 pc = b.pool_entry;
-          n_samples += (unsigned long long)max(steps, 0);
-          for (int i = 0; i < steps; ++i) {
-            Foot f;
-            footprint(P, b, pc, f);
-            if (!ISO) {
-              f4 col;
-              if (MODE == 0 && !LIT) {
-                const float data = tap(P, vox, f, 0, 0, 0);
-                col = tf_lookup<SMEM_TF>(P, s_tf, data * P.trans_scale, 0.0f);
-              } else {
-                float data; f3 g;
-                sample_with_gradient(P, vox, f, data, g);
-                f3 n;
-                if (MODE == 0) {
-                  col = tf_lookup<SMEM_TF>(P, s_tf, data * P.trans_scale, 0.0f);
-                  n = mul3(g, dscale);   // ComputeNormal
-                  const float l = len3(n);
-                  if (l > 0.0f) n = F3(n.x / l, n.y / l, n.z / l);
-                } else {
-                  const float gm = len3(g);
-                  col = tf_lookup<SMEM_TF>(P, s_tf, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
-                  const f3 gn = gm > 0.0f ? F3(g.x / gm, g.y / gm, g.z / gm) : g;
-                  n = mul3(dscale, gn);
-                }
-                if (LIT) {
-                  const f3 mp = mul3(sub3(pc, b.trans), inv_scale);
-                  const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
-                  col.x = lit.x; col.y = lit.y; col.z = lit.z;
-                }
-              }
-              col.w = opacity_correct(P, col.w);
-              const float oma = 1.0f - acc.w;   // UnderCompositing
-              acc.x = acc.x + col.x * oma * col.w;
-              acc.y = acc.y + col.y * oma * col.w;
-              acc.z = acc.z + col.z * oma * col.w;
-              acc.w = acc.w + col.w * oma;
-              if (acc.w > 0.99f) {
-                n_samples -= (unsigned long long)(steps - 1 - i);
-                terminated = true;
-                break;
-              }
-            } else {
-              if (tap(P, vox, f, 0, 0, 0) >= P.isoval) {
-                n_samples -= (unsigned long long)(steps - 1 - i);
-                // RefineIsosurface
-                f3 rd = F3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
-                pc = sub3(pc, rd);
-#pragma unroll 1
-                for (int k = 0; k < 5; k++) {
-                  rd = F3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
-                  footprint(P, b, pc, f);
-                  if (tap(P, vox, f, 0, 0, 0) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
-                }
-                cur = mul3(sub3(pc, b.trans), inv_scale);
-                hit_pos = xform4(P.m2e, cur.x, cur.y, cur.z, 1.0f);
-                hit_pos.w = 1.0f + 1.0f;   // color.r + 1
-                footprint(P, b, pc, f);
-                float dummy; f3 g;
-                sample_with_gradient(P, vox, f, dummy, g);
-                f3 n = mul3(g, dscale);
-                const float l = len3(n);
-                if (l > 0.0f) n = F3(n.x / l, n.y / l, n.z / l);
-                const float* m = P.mv_inv;   // mModelViewIT * vec4(n, 0)
-                hit_nrm.x = m[0] * n.x + m[1] * n.y + m[2] * n.z;
-                hit_nrm.y = m[4] * n.x + m[5] * n.y + m[6] * n.z;
-                hit_nrm.z = m[8] * n.x + m[9] * n.y + m[10] * n.z;
-                hit_nrm.w = floorf(1.0f * 512.0f) + 1.0f;   // floor(color.g*512)+color.b
-                terminated = true;
-                break;
-              } else {
-                hit_pos = from4(zero4);
-              }
-            }
-            pc = add3(pc, vdir);
-          }
-          if (terminated) break;
-          cur = mul3(sub3(pc, b.trans), inv_scale);
+          b_inv = F3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
+          b_trans = b.trans;
+          b_ox = b.ox; b_oy = b.oy; b_oz = b.oz;
+          vox = pool + b.base;
+          pc = b.pool_entry;
+          lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
+          if (steps > 0) { steps_left = steps; n_samples += (unsigned long long)steps; break; }
+          cur = mul3(sub3(pc, b_trans), b_inv);   // zero-step brick
         } else {
-          cur = F3(b.norm_exit.x + voxel_size * dir.x / ray_len, b.norm_exit.y + voxel_size * dir.y / ray_len,
-                   b.norm_exit.z + voxel_size * dir.z / ray_len);
+          cur = add3(b.norm_exit, nudge);
+          lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
         }
-        lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
         t = len3(sub3(entry, b.norm_exit)) / ray_len;
-        if (t > 0.9999f) break;
+        j++;
+        if (t > 0.9999f) alive = false;
+      }
+      if (COUNT) {
+        n_alive_iters += alive ? 1 : 0;
+        if (__ffs(__activemask()) - 1 == (int)((threadIdx.x + threadIdx.y * blockDim.x) & 31)) n_warp_iters++;
+      }
+      // ---- sample phase: one sample for every lane that is inside a brick ----
+      if (alive && steps_left > 0) {
+        Foot<T, FAST, BS> f;
+        f.set(P, vox, b_ox, b_oy, b_oz, pc);
+        bool terminated = false;
+        if (!ISO) {
+          f4 col;
+          if (MODE == 0 && !LIT) {
+            const float data = f.tap(P, 0, 0, 0);
+            col = tf_lookup(P, data * P.trans_scale, 0.0f);
+          } else {
+            float data; f3 g;
+            f.sample_with_gradient(P, data, g);
+            f3 n;
+            if (MODE == 0) {
+              col = tf_lookup(P, data * P.trans_scale, 0.0f);
+              n = mul3(g, dscale);   // ComputeNormal
+              const float l = len3(n);
+              if (l > 0.0f) n = scl3(n, 1.0f / l);
+            } else {
+              const float gm = len3(g);
+              col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
+              const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
+              n = mul3(dscale, gn);
+            }
+            if (LIT) {
+              const f3 mp = mul3(sub3(pc, b_trans), b_inv);
+              const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
+              col.x = lit.x; col.y = lit.y; col.z = lit.z;
+            }
+          }
+          col.w = opacity_correct(P, col.w);
+          const float oma = 1.0f - acc.w;   // UnderCompositing
+          acc.x = fmaf(col.x * oma, col.w, acc.x);
+          acc.y = fmaf(col.y * oma, col.w, acc.y);
+          acc.z = fmaf(col.z * oma, col.w, acc.z);
+          acc.w = fmaf(col.w, oma, acc.w);
+          if (acc.w > 0.99f) terminated = true;
+        } else {
+          if (f.tap(P, 0, 0, 0) >= P.isoval) {
+            // RefineIsosurface
+            f3 rd = F3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
+            pc = sub3(pc, rd);
+#pragma unroll 1
+            for (int k = 0; k < 5; k++) {
+              rd = F3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
+              f.set(P, vox, b_ox, b_oy, b_oz, pc);
+              if (f.tap(P, 0, 0, 0) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
+            }
+            cur = mul3(sub3(pc, b_trans), b_inv);
+            hit_pos = xform4(P.m2e, cur.x, cur.y, cur.z, 1.0f);
+            hit_pos.w = 1.0f + 1.0f;   // color.r + 1
+            f.set(P, vox, b_ox, b_oy, b_oz, pc);
+            float dummy; f3 g;
+            f.sample_with_gradient(P, dummy, g);
+            f3 n = mul3(g, dscale);
+            const float l = len3(n);
+            if (l > 0.0f) n = scl3(n, 1.0f / l);
+            const float* m = P.mv_inv;   // mModelViewIT * vec4(n, 0)
+            hit_nrm.x = m[0] * n.x + m[1] * n.y + m[2] * n.z;
+            hit_nrm.y = m[4] * n.x + m[5] * n.y + m[6] * n.z;
+            hit_nrm.z = m[8] * n.x + m[9] * n.y + m[10] * n.z;
+            hit_nrm.w = floorf(1.0f * 512.0f) + 1.0f;   // floor(color.g*512)+color.b
+            terminated = true;
+          } else {
+            hit_pos = from4(zero4);
+          }
+        }
+        steps_left--;
+        if (terminated) {
+          n_samples -= (unsigned long long)steps_left;   // samples of this brick that were never taken
+          alive = false;
+        } else {
+          pc = add3(pc, vdir);
+          if (steps_left == 0) {   // brick done: the shader's post-loop bookkeeping
+            cur = mul3(sub3(pc, b_trans), b_inv);
+            t = len3(sub3(entry, b_exit)) / ray_len;
+            j++;
+            if (t > 0.9999f) alive = false;
+          }
+        }
       }
     }
     // TerminateRay
@@ -532,22 +590,9 @@ __global__ void __launch_bounds__(64) raycast_kernel(const __grid_constant__ Ray
     P.out0[pix] = to4(hit_pos); P.out1[pix] = to4(hit_nrm); P.out2[pix] = to4(resume_pos);
     P.out3[pix] = to4(resume_nrm);
   }
-  if (P.count) {
-    // warp-aggregate, one atomic per warp and counter
-    unsigned long long s = n_samples, r = 1, bk = n_bricks;
-    const unsigned act = __activemask();
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_down_sync(act, s, o);
-      r += __shfl_down_sync(act, r, o);
-      bk += __shfl_down_sync(act, bk, o);
-    }
-    if (act == 0xffffffffu) {
-      if (((threadIdx.x + threadIdx.y * blockDim.x) & 31) == 0) {
-        atomicAdd(P.counters + 0, s); atomicAdd(P.counters + 1, r); atomicAdd(P.counters + 2, bk);
-      }
-    } else {
-      atomicAdd(P.counters + 0, n_samples); atomicAdd(P.counters + 1, 1ull); atomicAdd(P.counters + 2, n_bricks);
-    }
+  if (COUNT) {
+    atomicAdd(P.counters + 0, n_samples); atomicAdd(P.counters + 1, 1ull); atomicAdd(P.counters + 2, n_bricks);
+    atomicAdd(P.counters + 3, n_alive_iters); atomicAdd(P.counters + 4, n_warp_iters);
   }
 }
 
@@ -555,14 +600,16 @@ template <typename T, int MODE, bool LIT>
 void launch_t(const RayConsts& rc, cudaStream_t s) {
   dim3 block(8, 8);
   dim3 grid((rc.width + 7) / 8, (rc.height + 7) / 8);
-  const size_t tf_bytes = (size_t)rc.tf_w * rc.tf_h * 4;
-  if (MODE != 2 && tf_bytes <= 64 * 1024) {
-    auto k = raycast_kernel<T, MODE, LIT, true>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    k<<<grid, block, tf_bytes, s>>>(rc);
-  } else {
-    raycast_kernel<T, MODE, LIT, false><<<grid, block, 0, s>>>(rc);
-  }
+  // FAST addressing needs the +-1 gradient taps of every legal sample position inside the slot
+  bool fast = !rc.nearest;
+  for (int i = 0; i < 3; i++) fast = fast && rc.total[i] >= 4 && rc.ghost[i] >= 2;
+  const bool b36 = rc.total[0] == 36 && rc.total[1] == 36 && rc.total[2] == 36;
+  if (rc.count) {
+    if (fast) raycast_kernel<T, MODE, LIT, true, 0, true><<<grid, block, 0, s>>>(rc);
+    else raycast_kernel<T, MODE, LIT, false, 0, true><<<grid, block, 0, s>>>(rc);
+  } else if (fast && b36) raycast_kernel<T, MODE, LIT, true, 36, false><<<grid, block, 0, s>>>(rc);
+  else if (fast) raycast_kernel<T, MODE, LIT, true, 0, false><<<grid, block, 0, s>>>(rc);
+  else raycast_kernel<T, MODE, LIT, false, 0, false><<<grid, block, 0, s>>>(rc);
 }
 
 template <typename T>

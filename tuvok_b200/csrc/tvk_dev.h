@@ -26,6 +26,7 @@ struct RayConsts {
   float overlap_tc[3];  // overlap in pool texcoords
   uint32_t capacity[3];
   uint32_t total[3];    // maxTotalBrickSize
+  uint32_t ghost[3];    // brick overlap per side
   uint32_t lod_count;   // pool LoD count
   uint32_t lod_offset[TVK_MAX_LOD];
   float lod_layout[TVK_MAX_LOD][3];     // vLODLayout
@@ -46,7 +47,7 @@ struct RayConsts {
   const void* pool;       // slot-linear brick pool
   uint64_t slot_voxels;   // voxels per slot
   const uint32_t* meta;   // page table
-  const uchar4* tf;       // RGBA8 table
+  const float4* tf;       // RGBA8 table as float4 (byte / 255.0f)
   uint32_t* hash;         // miss-report table
   const float4* ray_start;   // resume position (in), ignored when first_pass
   const float4* start_color; // resume colour / normal (in)

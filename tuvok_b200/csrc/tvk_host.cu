@@ -45,6 +45,15 @@ int fail(tvk_ctx* c, int code, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// RGBA8 texel -> the float4 a GL_RGBA8 texture fetch returns (byte / 255.0f, IEEE division)
+std::vector<float4> tf_to_float(const uint8_t* rgba, size_t n) {
+  std::vector<float4> f(n);
+  for (size_t i = 0; i < n; i++)
+    f[i] = make_float4((float)rgba[4 * i] / 255.0f, (float)rgba[4 * i + 1] / 255.0f, (float)rgba[4 * i + 2] / 255.0f,
+                       (float)rgba[4 * i + 3] / 255.0f);
+  return f;
+}
+
 uint32_t esize_of(int dtype) { return dtype == TVK_U8 ? 1u : dtype == TVK_U16 ? 2u : 4u; }
 
 // ExtendedOctree::ComputeMetadata: LOD sizes = ceil(prev/2) per axis (size-1 axes stay) until 1^3
@@ -474,6 +483,7 @@ int derive(tvk_ctx* ctx, RayConsts& u) {
     u.overlap_tc[i] = (ctx->brick[i] - ctx->inner[i]) / (2.0f * ctx->pool_size[i]);
     u.capacity[i] = ctx->capacity[i];
     u.total[i] = ctx->brick[i];
+    u.ghost[i] = ctx->overlap;
     u.finest[i] = ctx->pool_layout[0][i];
     u.clip_min[i] = p.clip_min[i]; u.clip_max[i] = p.clip_max[i];
   }
@@ -603,8 +613,8 @@ int tvk_create(const tvk_device_cfg* cfg, tvk_ctx** out) {
   ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto& ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
-  ok = ok && cudaMalloc(&ctx->counters_d, 4 * sizeof(unsigned long long)) == cudaSuccess;
-  ok = ok && cudaMallocHost(&ctx->counters_h, 4 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->counters_d, 8 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->counters_h, 8 * sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) {
     fail(nullptr, TVK_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
@@ -812,9 +822,12 @@ int tvk_set_tf1d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t n, uint64_t nz_lo, 
   if (ctx->tf1d_n != n) {
     if (ctx->tf1d_d) cudaFree(ctx->tf1d_d);
     ctx->tf1d_d = nullptr;
-    CU(cudaMalloc(&ctx->tf1d_d, (size_t)n * 4));
+    CU(cudaMalloc(&ctx->tf1d_d, (size_t)n * sizeof(float4)));
   }
-  CU(cudaMemcpy(ctx->tf1d_d, rgba, (size_t)n * 4, cudaMemcpyHostToDevice));
+  {
+    std::vector<float4> f = tf_to_float(rgba, n);
+    CU(cudaMemcpy(ctx->tf1d_d, f.data(), f.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  }
   ctx->tf1d_n = n; ctx->tf1d_nz[0] = nz_lo; ctx->tf1d_nz[1] = nz_hi;
   ctx->blank = true;
   return TVK_OK;
@@ -827,9 +840,12 @@ int tvk_set_tf2d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, cons
   if (ctx->tf2d_w != w || ctx->tf2d_h != h) {
     if (ctx->tf2d_d) cudaFree(ctx->tf2d_d);
     ctx->tf2d_d = nullptr;
-    CU(cudaMalloc(&ctx->tf2d_d, (size_t)w * h * 4));
+    CU(cudaMalloc(&ctx->tf2d_d, (size_t)w * h * sizeof(float4)));
   }
-  CU(cudaMemcpy(ctx->tf2d_d, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice));
+  {
+    std::vector<float4> f = tf_to_float(rgba, (size_t)w * h);
+    CU(cudaMemcpy(ctx->tf2d_d, f.data(), f.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  }
   ctx->tf2d_w = w; ctx->tf2d_h = h;
   for (int i = 0; i < 4; i++) ctx->tf2d_nz[i] = nz[i];
   ctx->blank = true;
@@ -1055,7 +1071,7 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
   CU(cudaMemsetAsync(ctx->hash_d, 0, (size_t)ctx->hash_size * 4, s));           // GLHashTable::ClearData
   CU(cudaMemsetAsync(ctx->miss_d + 2 * (size_t)ctx->hash_size, 0, 4, s));
   if (ctx->counters_on) {
-    CU(cudaMemsetAsync(ctx->counters_d, 0, 4 * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(ctx->counters_d, 0, 8 * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(ctx->visited_d, 0, ctx->visited_h.size() * 4, s));
   }
   rc = raycast_pass(ctx, true);
@@ -1067,7 +1083,7 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
   CU(cudaMemcpyAsync(ctx->miss_h + 2 * (size_t)ctx->hash_size, ctx->miss_d + 2 * (size_t)ctx->hash_size, 4,
                      cudaMemcpyDeviceToHost, s));
   if (ctx->counters_on) {
-    CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(ctx->visited_h.data(), ctx->visited_d, ctx->visited_h.size() * 4, cudaMemcpyDeviceToHost, s));
   }
   CU(cudaStreamSynchronize(s));
@@ -1106,6 +1122,7 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
     st->bricks_paged = paged;
     if (ctx->counters_on) {
       st->samples = ctx->counters_h[0]; st->rays = ctx->counters_h[1]; st->brick_visits = ctx->counters_h[2];
+      st->alive_lane_iters = ctx->counters_h[3]; st->warp_iters = ctx->counters_h[4];
       uint64_t t = 0;
       for (uint32_t w : ctx->visited_h) t += (uint64_t)__builtin_popcount(w);
       st->bricks_touched = t;

@@ -95,8 +95,8 @@ struct tvk_ctx {
   uint64_t slot_voxels = 0, slot_bytes = 0;
 
   // ---- transfer functions ----
-  uchar4* tf1d_d = nullptr; uint32_t tf1d_n = 0; uint64_t tf1d_nz[2] = {0, 0};
-  uchar4* tf2d_d = nullptr; uint32_t tf2d_w = 0, tf2d_h = 0; uint64_t tf2d_nz[4] = {0, 0, 0, 0};
+  float4* tf1d_d = nullptr; uint32_t tf1d_n = 0; uint64_t tf1d_nz[2] = {0, 0};
+  float4* tf2d_d = nullptr; uint32_t tf2d_w = 0, tf2d_h = 0; uint64_t tf2d_nz[4] = {0, 0, 0, 0};
 
   // ---- pool ----
   bool have_pool = false;

@@ -30,7 +30,7 @@ def transfer_functions(w):
     n = 256 if w["dtype"] == L.U8 else 4096
     t1 = TransferFunction1D(n)
     t1.SetStdFunction(*w["tf"])
-    t2 = TransferFunction2D.rectangle(w=n, h=256, x0=0.02, x1=0.9, alpha_max=40)
+    t2 = TransferFunction2D.rectangle(w=n, h=256, x0=0.02, x1=0.9, alpha_max=16)
     return t1, t2
 
 
