@@ -75,7 +75,7 @@ class Scene:
         self.tf1d = TransferFunction1D(n_tf)
         self.tf1d.SetStdFunction(tf_center, tf_inv_gradient)
         # the reference sizes the 2D TF like the 1D one along the value axis (Get2DHistogram()->GetFilledSize())
-        self.tf2d = tf2d if tf2d is not None else TransferFunction2D.rectangle(w=n_tf, h=64)
+        self.tf2d = tf2d if tf2d is not None else TransferFunction2D.rectangle(w=n_tf, h=64, x0=0.02, x1=0.9, alpha_max=64)
         self.volume = synth.synth_volume(kind, self.size, dtype, seed)
         self._pool_size = pool_size
         self._hash_size = hash_size

@@ -1,0 +1,166 @@
+"""Sort-last host logic (tuvok_b200/sortlast.py) on the CPU: sharding, the binary-swap schedule, and a
+world_size-2 gloo run.  The blend used here is the ORACLE's over operator (test infrastructure); on GPU
+ranks the same schedule drives the CUDA kernel tvk_composite_over (tests/test_gpu_sortlast.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import golden_scenes
+from oracle import orc
+from scene import image_diff
+from tuvok_b200 import sortlast
+
+
+def scene_layout(s):
+    inner = [b - 2 * s.overlap for b in s.brick]
+    finest = [-(-v // i) for v, i in zip(s.size, inner)]
+    fl = []
+    for v, i in zip(s.size, inner):
+        c = np.float32(v) / np.float32(i)
+        if np.float32(int(c)) == c:
+            c = c - c * np.finfo(np.float32).eps
+        fl.append(np.float32(c))
+    ext = np.array(s.size, np.float64) * np.array(s.scale, np.float64)
+    return finest, fl, ext / ext.max()
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_shard_boxes_tile_the_brick_grid(n):
+    boxes, splits = sortlast.shard_boxes((7, 4, 5), n)
+    assert len(boxes) == n and len(splits) == int(np.log2(n))
+    cover = np.zeros((7, 4, 5), np.int32)
+    for lo, hi in boxes:
+        assert all(h > l for l, h in zip(lo, hi))
+        cover[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] += 1
+    assert (cover == 1).all()           # disjoint and complete
+
+
+def test_non_power_of_two_is_refused():
+    with pytest.raises(ValueError):
+        sortlast.shard_boxes((4, 4, 4), 3)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_swap_plan_is_consistent(n):
+    finest, fl = (6, 5, 4), (np.float32(5.9), np.float32(4.7), np.float32(3.9))
+    boxes, splits = sortlast.shard_boxes(finest, n)
+    eye = np.array([1.7, -0.3, 0.4])
+    n_pix = 1001
+    plans = [sortlast.swap_plan(r, n, splits, boxes, finest, fl, eye, n_pix) for r in range(n)]
+    for r in range(n):
+        for k, rd in enumerate(plans[r]):
+            other = plans[rd["partner"]][k]
+            assert other["partner"] == r
+            assert rd["keep"] == other["send"] and rd["send"] == other["keep"]
+            assert rd["i_am_front"] != other["i_am_front"]
+    ranges = sortlast.final_ranges(n, n_pix)
+    assert sorted(ranges)[0][0] == 0 and sorted(ranges)[-1][1] == n_pix
+    assert sum(b - a for a, b in ranges) == n_pix
+    for r in range(n):
+        assert plans[r][-1]["keep"] == ranges[r]
+
+
+class FakeDist:
+    """In-process stand-in for torch.distributed P2P: all ranks advance round by round."""
+
+    class P2POp:
+        def __init__(self, op, tensor, peer):
+            self.op, self.tensor, self.peer = op, tensor, peer
+
+    isend, irecv = "isend", "irecv"
+
+
+def run_in_process(images, plans):
+    """Execute the schedules of all ranks in lock step with numpy; returns the per-rank final ranges."""
+    n = len(images)
+    imgs = [im.copy() for im in images]
+    for k in range(len(plans[0])):
+        sends = {r: imgs[r][plans[r][k]["send"][0]:plans[r][k]["send"][1]].copy() for r in range(n)}
+        for r in range(n):
+            rd = plans[r][k]
+            recv = sends[rd["partner"]]
+            lo, hi = rd["keep"]
+            mine = imgs[r][lo:hi]
+            imgs[r][lo:hi] = orc.composite_over(mine, recv) if rd["i_am_front"] else orc.composite_over(recv, mine)
+    return imgs
+
+
+def partial_images(s, n):
+    finest, fl, ext = scene_layout(s)
+    boxes, splits = sortlast.shard_boxes(finest, n)
+    outs = []
+    for r in range(n):
+        cmin, cmax = sortlast.box_to_clip(boxes[r], finest, fl)
+        sr = golden_scenes.make(s._name, clip=(cmin, cmax))
+        outs.append(sr.oracle_render()["image"].reshape(-1, 4).copy())
+    mv, _ = s.matrices()
+    eye = sortlast.eye_in_volume(mv, ext)
+    n_pix = s.width * s.height
+    plans = [sortlast.swap_plan(r, n, splits, boxes, finest, fl, eye, n_pix) for r in range(n)]
+    return outs, plans
+
+
+@pytest.mark.parametrize("name,n", [("c2_bricked36_1d_ert", 2), ("ragged_1d_lit", 4), ("inside_aniso_2d", 8),
+                                    ("c3_bricked36_2d_lit", 2)])
+def test_sort_last_image_matches_single_renderer(name, n):
+    s = golden_scenes.make(name)
+    s._name = name
+    single = s.oracle_render()
+    parts, plans = partial_images(s, n)
+    done = run_in_process(parts, plans)
+    n_pix = s.width * s.height
+    final = np.zeros((n_pix, 4), np.float32)
+    for r, (a, b) in enumerate(sortlast.final_ranges(n, n_pix)):
+        final[a:b] = done[r][a:b]
+    mx, psnr = image_diff(orc.rgba8(final), single["rgba8"].reshape(-1, 4))
+    assert mx <= 2 and psnr >= 45.0, (mx, psnr)
+    assert orc.rgba8(final)[:, 3].any()
+
+
+def _worker(rank, world, port, name, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = golden_scenes.make(name)
+        s._name = name
+        parts, plans = partial_images(s, world)
+        img = torch.from_numpy(parts[rank].copy())
+        recv = torch.empty((img.shape[0] // 2 + 1, 4), dtype=torch.float32)
+
+        def over(front, back, out):
+            out.copy_(torch.from_numpy(orc.composite_over(front.numpy().copy(), back.numpy().copy())))
+
+        lo, hi = sortlast.binary_swap(img, plans[rank], dist, over, recv)
+        q.put((rank, lo, hi, img[lo:hi].numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_binary_swap_over_gloo_world_size_2():
+    name, world = "c2_bricked36_1d_ert", 2
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    s = golden_scenes.make(name)
+    s._name = name
+    parts, plans = partial_images(s, world)
+    expect = run_in_process(parts, plans)
+    n_pix = s.width * s.height
+    assert sorted((lo, hi) for _, lo, hi, _ in got) == sorted(sortlast.final_ranges(world, n_pix))
+    for rank, lo, hi, px in got:
+        np.testing.assert_array_equal(px, expect[rank][lo:hi])
