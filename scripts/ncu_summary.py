@@ -45,7 +45,7 @@ h = rows[hi[0]]
 ci, si = h.index('Instructions Executed'), h.index('# Samples')
 fn = [i for i, r in enumerate(rows) if r and r[0] == 'Function Name']
 end = fn[which + 1] if len(fn) > which + 1 else len(rows)
-start = fn[which]
+start = fn[which] - 1   # the 'File Path' row precedes 'Function Name'
 cur, lines = None, []
 for r in rows[start:end]:
     if r and r[0] == 'File Path':

@@ -139,7 +139,9 @@ def test_default_509_entry_hash_table_converges_to_the_same_image():
     res = lambda m: set(np.nonzero(m >= orc.BI_FLAG_COUNT)[0].tolist())
     assert res(r.page_table()) == res(ref["meta"])
     check_images(r.ReadRGBA8(), ref["rgba8"])
-    assert np.array_equal(r.ReadRGBA32F(), ref["image"])
+    # a different paging history restarts rays at different resume points (GLGridLeaper-blend.glsl:130-137):
+    # the direction is re-derived from (exit - resumePos), so the floats agree to rounding, not bit for bit
+    assert float(np.abs(r.ReadRGBA32F() - ref["image"]).max()) < 1e-4
     r.Cleanup()
 
 
@@ -166,7 +168,11 @@ def test_view_change_reuses_resident_bricks_and_is_deterministic():
     r.SetRotation(s.rotation)
     st = r.PaintUntilConverged()
     assert st.converged and st.bricks_paged == 0          # everything still resident
-    assert np.array_equal(r.ReadRGBA32F(), a)             # idempotent
+    b = r.ReadRGBA32F()
+    assert float(np.abs(b - a).max()) < 1e-4              # single pass now vs resumed passes before: rounding only
+    assert not r.CheckForRedraw()
+    st = r.Paint()                                        # same state, same pass structure: bit-identical
+    assert np.array_equal(r.ReadRGBA32F(), b)
     r.Cleanup()
 
 

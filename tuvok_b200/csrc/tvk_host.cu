@@ -472,7 +472,8 @@ int derive(tvk_ctx* ctx, RayConsts& u) {
       l[c] = p.light_dir[0] * m[c] + p.light_dir[1] * m[4 + c] + p.light_dir[2] * m[8 + c] + 0.0f * m[12 + c];
       e[c] = p.eye[0] * m[c] + p.eye[1] * m[4 + c] + p.eye[2] * m[8 + c] + 1.0f * m[12 + c];
     }
-    const float inv = 1.0f / sqrtf(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    // normalize() of the arithmetic contract: v * (1 / sqrt(fma(z,z, fma(y,y, x*x))))
+    const float inv = 1.0f / sqrtf(fmaf(l[2], l[2], fmaf(l[1], l[1], l[0] * l[0])));
     for (int c = 0; c < 3; c++) { u.light_dir_m[c] = l[c] * inv; u.eye_m[c] = e[c]; }
   }
   u.lzwse = fmaxf(ex[0] / (float)ctx->vol[0], fmaxf(ex[1] / (float)ctx->vol[1], ex[2] / (float)ctx->vol[2]));
