@@ -147,7 +147,10 @@ typedef struct {
   /* miss reporting */
   uint32_t hash_size, rehash_count;
   int      strategy;           /* ORC_BS_* */
-  /* sort-last shard clip box in normalised volume coords ([0,1]^3 = whole volume) */
+  /* sort-last shard box in normalised volume coords ([0,1]^3 = whole volume).  Rays are NOT clipped to it:
+   * they walk the brick chain of the whole volume from their true entry (so sample positions equal the
+   * single-GPU ray's) and only samples inside [clip_min, clip_max) are taken; bricks that do not touch the
+   * box are stepped through without sampling or paging */
   float clip_min[3], clip_max[3];
   int   nearest;               /* SetInterpolant(NEAREST) */
 } orc_render_params;
@@ -188,7 +191,8 @@ uint32_t orc_hash_decode(const uint32_t* hash, uint32_t hash_size, const uint32_
 /* GL float -> unorm8 read-back (GLFrameCapture.cpp:72-85) */
 void orc_rgba8(const float* rgba, uint64_t n_pixels, uint8_t* out);
 
-/* over-operator used by the sort-last compositor: front + (1-front.a)*back */
+/* over-operator of the sort-last compositor: front + (1-front.a)*back, aware of early ray termination
+ * (a terminated front hides the back; a back image that would push alpha past 0.995 is cut there) */
 void orc_composite_over(const float* front, const float* back, uint64_t n_pixels, float* out);
 
 #ifdef __cplusplus

@@ -174,6 +174,28 @@ static void derive(const orc_render_params* p, uni* u) {
 /* ------------------------------------------------------------------ */
 /* ray setup                                                           */
 /* ------------------------------------------------------------------ */
+/* slab test of the ray o + s*d against [lo,hi]; returns 0 if the ray is parallel to and outside a slab */
+static int slab3(const float o[3], const float d[3], const float lo[3], const float hi[3], float* s_in, float* s_out) {
+  float a_in = -INFINITY, a_out = INFINITY;
+  for (int i = 0; i < 3; i++) {
+    if (d[i] == 0.0f) {
+      if (o[i] < lo[i] || o[i] > hi[i]) return 0;
+      continue;
+    }
+    float t0 = (lo[i] - o[i]) / d[i], t1 = (hi[i] - o[i]) / d[i];
+    float a = fminf(t0, t1), b = fmaxf(t0, t1);
+    a_in = fmaxf(a_in, a);
+    a_out = fminf(a_out, b);
+  }
+  *s_in = a_in; *s_out = a_out;
+  return 1;
+}
+
+static int shard_active(const orc_render_params* p) {
+  for (int i = 0; i < 3; i++) if (p->clip_min[i] > 0.0f || p->clip_max[i] < 1.0f) return 1;
+  return 0;
+}
+
 static int ray_setup_px(const orc_render_params* p, const uni* u, uint32_t px, uint32_t py,
                         v4* entry, v4* exit_) {
   float nx = ((float)px + 0.5f) / (float)p->width * 2.0f - 1.0f;
@@ -184,20 +206,18 @@ static int ray_setup_px(const orc_render_params* p, const uni* u, uint32_t px, u
   v4 n4 = xform4(u->emm, pn.x, pn.y, pn.z, 1.0f);
   float o[3] = {o4.x, o4.y, o4.z};
   float d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
-  float s_in = -INFINITY, s_out = INFINITY;
-  for (int i = 0; i < 3; i++) {
-    float lo = p->clip_min[i], hi = p->clip_max[i];
-    if (d[i] == 0.0f) {
-      if (o[i] < lo || o[i] > hi) return 0;
-      continue;
-    }
-    float t0 = (lo - o[i]) / d[i], t1 = (hi - o[i]) / d[i];
-    float a = fminf(t0, t1), b = fmaxf(t0, t1);
-    s_in = fmaxf(s_in, a);
-    s_out = fminf(s_out, b);
-  }
+  const float zero[3] = {0.0f, 0.0f, 0.0f}, one[3] = {1.0f, 1.0f, 1.0f};
+  float s_in, s_out;
+  if (!slab3(o, d, zero, one, &s_in, &s_out)) return 0;
   float s0 = fmaxf(s_in, 1.0f);              /* near plane where the camera is inside / in front */
   if (!(s_out > s0)) return 0;               /* no back-face fragment in front of the near plane */
+  if (shard_active(p)) {
+    /* sort-last: the ray keeps its whole-volume entry/exit (so its sample positions are those of the
+     * single-GPU ray); a pixel whose ray never meets this rank's brick block is simply not shaded */
+    float a_in, a_out;
+    if (!slab3(o, d, p->clip_min, p->clip_max, &a_in, &a_out)) return 0;
+    if (!(fminf(a_out, s_out) > fmaxf(a_in, s0))) return 0;
+  }
   v3 pe = scl3(pn, s0), px_ = scl3(pn, s_out);
   v4 e = xform4(u->emm, pe.x, pe.y, pe.z, 1.0f);
   v4 x = xform4(u->emm, px_.x, px_.y, px_.z, 1.0f);
@@ -231,6 +251,8 @@ typedef struct {
   uint32_t* hash;
   uint32_t finest[3];
   uint64_t samples, bricks;
+  int shard;                 /* sort-last: only samples inside [sh_lo, sh_hi) are taken */
+  float sh_lo[3], sh_hi[3];  /* the shard box with faces on the volume border pushed to -/+inf */
 } ctx_t;
 
 static inline float texel(const ctx_t* c, int x, int y, int z) {
@@ -385,8 +407,28 @@ static void report_missing(ctx_t* c, u4 b) {
 typedef struct {
   v3 pool_entry, pool_exit, norm_exit, scale, trans;
   int empty;
+  int where;   /* sort-last: 0 = brick inside the shard box, 1 = straddles it, 2 = outside (never sampled) */
   u4 bc;
 } brick_t;
+
+enum { IN_SHARD = 0, PARTLY_IN_SHARD = 1, OUTSIDE_SHARD = 2 };
+
+/* position of the brick's box [c0,c1] relative to the shard box */
+static int classify_brick(const ctx_t* c, v3 c0, v3 c1) {
+  if (!c->shard) return IN_SHARD;
+  const float a0[3] = {c0.x, c0.y, c0.z}, a1[3] = {c1.x, c1.y, c1.z};
+  int inside = 1;
+  for (int i = 0; i < 3; i++) {
+    if (a1[i] <= c->sh_lo[i] || a0[i] >= c->sh_hi[i]) return OUTSIDE_SHARD;
+    if (a0[i] < c->sh_lo[i] || a1[i] > c->sh_hi[i]) inside = 0;
+  }
+  return inside ? IN_SHARD : PARTLY_IN_SHARD;
+}
+static void brick_corners(const uni* u, u4 bc, v3* c0, v3* c1) {
+  v3 lay = u->lod_layout[bc.w];
+  *c0 = div3(V3((float)bc.x, (float)bc.y, (float)bc.z), lay);
+  *c1 = div3(V3((float)(bc.x + 1), (float)(bc.y + 1), (float)(bc.z + 1)), lay);
+}
 
 static int get_brick(ctx_t* c, v3 pos, uint32_t* lod, v3 dir, brick_t* o) {
   const orc_render_params* p = c->p;
@@ -397,7 +439,16 @@ static int get_brick(ctx_t* c, v3 pos, uint32_t* lod, v3 dir, brick_t* o) {
   int found = 1;
   u4 bc = brick_coords(u, pos, *lod);
   uint32_t info = brick_info(c, bc);
-  if (info == ORC_BI_MISSING) {
+  int foreign = 0;
+  if (info == ORC_BI_MISSING && c->shard) {
+    /* sort-last: a brick that does not touch this rank's block lives on another rank.  It is walked
+     * through (same step arithmetic, nominal slot 0) but never requested, sampled or replaced by a
+     * coarser level, so the ray reaches this rank's block at the single-GPU ray's sample phase. */
+    v3 f0, f1;
+    brick_corners(u, bc, &f0, &f1);
+    foreign = classify_brick(c, f0, f1) == OUTSIDE_SHARD;
+  }
+  if (info == ORC_BI_MISSING && !foreign) {
     uint32_t start = *lod;
     report_missing(c, bc);
     found = 0;
@@ -412,7 +463,7 @@ static int get_brick(ctx_t* c, v3 pos, uint32_t* lod, v3 dir, brick_t* o) {
       }
     } while (info == ORC_BI_MISSING);
   }
-  o->empty = info <= ORC_BI_EMPTY;
+  o->empty = !foreign && info <= ORC_BI_EMPTY;
   if (o->empty) {
     for (uint32_t lo = *lod + 1; lo < max_lod; ++lo) {   /* strict <: coarsest level never leapt to (H5) */
       u4 lb = brick_coords(u, pos, lo);
@@ -422,9 +473,8 @@ static int get_brick(ctx_t* c, v3 pos, uint32_t* lod, v3 dir, brick_t* o) {
     }
   }
   /* GetBrickCorners */
-  v3 lay = u->lod_layout[bc.w];
-  v3 c0 = div3(V3((float)bc.x, (float)bc.y, (float)bc.z), lay);
-  v3 c1 = div3(V3((float)(bc.x + 1), (float)(bc.y + 1), (float)(bc.z + 1)), lay);
+  v3 c0, c1;
+  brick_corners(u, bc, &c0, &c1);
   /* BrickExit */
   v3 dv = V3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
   float tx = ((dv.x < 0.0f ? c0.x : c1.x) - pos.x) * dv.x;
@@ -433,9 +483,11 @@ static int get_brick(ctx_t* c, v3 pos, uint32_t* lod, v3 dir, brick_t* o) {
   float tm = fminf(fminf(tx, ty), tz);
   o->norm_exit = add3(pos, scl3(dir, tm));
   o->bc = bc;
+  o->where = IN_SHARD;
   if (o->empty) return found;
+  o->where = foreign ? OUTSIDE_SHARD : classify_brick(c, c0, c1);
   /* NormCoordsToPoolCoords / BrickPoolCoords / InfoToCoords */
-  uint32_t index = info - ORC_BI_FLAG_COUNT;
+  uint32_t index = foreign ? 0u : info - ORC_BI_FLAG_COUNT;
   uint32_t sx = index % p->capacity[0], sy = (index / p->capacity[0]) % p->capacity[1],
            sz = index / (p->capacity[0] * p->capacity[1]);
   v3 vp = V3((float)(sx * p->max_total_brick[0]), (float)(sy * p->max_total_brick[1]),
@@ -514,6 +566,13 @@ static void trace_pixel(ctx_t* c, const float* ray_start, const float* start_col
     int terminated = 0;
     if (ray_len > voxel_size) {
       for (uint32_t j = 0; j < 100 && !terminated; ++j) {
+        if (c->shard) {   /* the block is convex: once the ray has left it, nothing more to do on this rank */
+          const float cp[3] = {cur.x, cur.y, cur.z}, dd[3] = {dir.x, dir.y, dir.z};
+          int gone = 0;
+          for (int i = 0; i < 3; i++)
+            gone |= (dd[i] > 0.0f && cp[i] >= c->sh_hi[i]) || (dd[i] < 0.0f && cp[i] <= c->sh_lo[i]);
+          if (gone) break;
+        }
         float cur_depth = entry_depth * (1.0f - t) + exit_depth * t;
         uint32_t lod = compute_lod(c, cur_depth);
         brick_t b;
@@ -530,7 +589,19 @@ static void trace_pixel(ctx_t* c, const float* ray_start, const float* start_col
           steps = steps < s2 ? steps : s2;
           v3 inv_scale = V3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
           v3 pc = b.pool_entry;
+          if (b.where == OUTSIDE_SHARD) {   /* another rank's brick: advance by its steps, take no sample */
+            float n = (float)(steps > 0 ? steps : 0);
+            pc = V3(fmaf(n, vdir.x, pc.x), fmaf(n, vdir.y, pc.y), fmaf(n, vdir.z, pc.z));
+            steps = 0;
+          }
           for (int i = 0; i < steps; ++i) {
+            if (b.where == PARTLY_IN_SHARD) {   /* brick straddles the block face: ownership per sample */
+              v3 mq = mul3(sub3(pc, b.trans), inv_scale);
+              const float q[3] = {mq.x, mq.y, mq.z};
+              int mine = 1;
+              for (int a = 0; a < 3; a++) mine &= q[a] >= c->sh_lo[a] && q[a] < c->sh_hi[a];
+              if (!mine) { pc = add3(pc, vdir); continue; }
+            }
             if (!iso) {
               v3 mp = mul3(sub3(pc, b.trans), inv_scale);
               v4 col = color_from_volume(c, pc, mp, delta);
@@ -621,6 +692,11 @@ void orc_raycast(const orc_render_params* p, const void* pool, const uint32_t* m
     c.p = p; c.u = &u; c.pool = pool; c.meta = meta; c.tf = tf; c.hash = hash;
     memcpy(c.finest, finest, sizeof(finest));
     c.samples = 0; c.bricks = 0;
+    c.shard = shard_active(p);
+    for (int i = 0; i < 3; i++) {
+      c.sh_lo[i] = p->clip_min[i] > 0.0f ? p->clip_min[i] : -INFINITY;
+      c.sh_hi[i] = p->clip_max[i] < 1.0f ? p->clip_max[i] : INFINITY;
+    }
     for (uint32_t x = 0; x < p->width; x++) {
       size_t i = (size_t)y * p->width + x;
       if (!covered[i]) continue;
@@ -696,6 +772,10 @@ void orc_composite_over(const float* front, const float* back, uint64_t n_pixels
     const float* b = back + 4 * i;
     /* early-terminated front rays (alpha > 0.99, GLGridLeaper-blend.glsl:180) hide what lies behind */
     float oma = f[3] > 0.99f ? 0.0f : 1.0f - f[3];
+    /* a ray that would have crossed 0.99 inside the back block stops there as well: cut the back image at
+     * the middle of (0.99, 1.0], the interval in which the single-GPU ray ends (alpha error <= 0.005) */
+    float add = oma * b[3];
+    if (oma > 0.0f && f[3] + add > 0.995f) oma = oma * ((0.995f - f[3]) / add);
     out[4 * i + 0] = f[0] + oma * b[0];
     out[4 * i + 1] = f[1] + oma * b[1];
     out[4 * i + 2] = f[2] + oma * b[2];

@@ -106,7 +106,7 @@ def partial_images(s, n):
 
 
 @pytest.mark.parametrize("name,n", [("c2_bricked36_1d_ert", 2), ("ragged_1d_lit", 4), ("inside_aniso_2d", 8),
-                                    ("c3_bricked36_2d_lit", 2)])
+                                    ("c3_bricked36_2d_lit", 2), ("c4_f32_iso", 4)])
 def test_sort_last_image_matches_single_renderer(name, n):
     s = golden_scenes.make(name)
     s._name = name

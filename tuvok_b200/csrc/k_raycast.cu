@@ -59,6 +59,7 @@ __device__ __forceinline__ f4 xform4(const float* m, float x, float y, float z, 
 struct BrickRef {
   f3 pool_entry, pool_exit, norm_exit, scale, trans;
   bool empty;
+  int where;             // sort-last: 0 brick inside the shard box, 1 straddles it, 2 outside (never sampled)
   uint32_t bx, by, bz, bl;
   uint32_t ox, oy, oz;   // slot origin in virtual-atlas texels
   uint64_t base;         // first voxel of the slot in the slot-linear pool
@@ -86,17 +87,20 @@ __device__ __forceinline__ float tri(float v000, float v100, float v010, float v
 //         slot, so one clamped centre address + uniform row strides address all 32 voxels.
 //         BS != 0 bakes a cubic brick size in (like the #defines of the reference's generated GLSL,
 //         GLVolumePool.cpp:364-400), turning the 32 voxel addresses into immediate offsets.
-//   !FAST (nearest filter or ghost < 2): every texel index is clamped to the slot like
-//         GL_CLAMP_TO_EDGE clamps it to the texture.
+//   !FAST (nearest filter or ghost < 2): texel indices are taken in the reference's VIRTUAL ATLAS
+//         (capacity * brick texels, clamp-to-edge at the atlas border like GL_CLAMP_TO_EDGE) and then
+//         split into (slot, texel-in-slot), so taps that leave a brick with a 1-voxel ghost read the
+//         atlas neighbour exactly as the reference's 3D texture does.
 template <typename T, bool FAST, int BS>
 struct Foot {
-  const T* c;            // FAST: voxel (X, Y, Z)
-  uint32_t xo[4], yo[4], zo[4];   // !FAST: clamped element offsets of X-1..X+2 etc.
+  const T* c;            // FAST: voxel (X, Y, Z); !FAST: first voxel of the pool
+  uint64_t xo[4], yo[4], zo[4];   // !FAST: element offsets (slot part + in-slot part) of X-1..X+2 etc.
   float fx, fy, fz;
   int sy, sz;            // row / slice stride in elements
   bool nearest;
 
-  __device__ __forceinline__ void set(const RayConsts& P, const T* vox, uint32_t ox, uint32_t oy, uint32_t oz, f3 tc) {
+  __device__ __forceinline__ void set(const RayConsts& P, const T* pool, const T* vox, uint32_t ox, uint32_t oy,
+                                      uint32_t oz, f3 tc) {
     int X, Y, Z;
     nearest = !FAST && P.nearest;
     if (nearest) {
@@ -112,22 +116,26 @@ struct Foot {
       fx = ux - x0; fy = uy - y0; fz = uz - z0;
       X = (int)x0; Y = (int)y0; Z = (int)z0;
     }
-    X -= (int)ox; Y -= (int)oy; Z -= (int)oz;
     sy = BS ? BS : (int)P.total[0];
     sz = BS ? BS * BS : (int)(P.total[0] * P.total[1]);
     if (FAST) {
+      X -= (int)ox; Y -= (int)oy; Z -= (int)oz;
       X = min(max(X, 1), (BS ? BS : (int)P.total[0]) - 3);
       Y = min(max(Y, 1), (BS ? BS : (int)P.total[1]) - 3);
       Z = min(max(Z, 1), (BS ? BS : (int)P.total[2]) - 3);
       c = vox + (X + Y * sy + Z * sz);
     } else {
-      c = vox;
-      const int tx = (int)P.total[0] - 1, ty = (int)P.total[1] - 1, tz = (int)P.total[2] - 1;
+      c = pool;
+      const int ax = (int)(P.capacity[0] * P.total[0]) - 1, ay = (int)(P.capacity[1] * P.total[1]) - 1,
+                az = (int)(P.capacity[2] * P.total[2]) - 1;
+      const uint64_t slot_y = (uint64_t)P.capacity[0] * P.slot_voxels, slot_z = slot_y * P.capacity[1];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        xo[i] = (uint32_t)min(max(X - 1 + i, 0), tx);
-        yo[i] = (uint32_t)min(max(Y - 1 + i, 0), ty) * (uint32_t)sy;
-        zo[i] = (uint32_t)min(max(Z - 1 + i, 0), tz) * (uint32_t)sz;
+        const uint32_t gx = (uint32_t)min(max(X - 1 + i, 0), ax), gy = (uint32_t)min(max(Y - 1 + i, 0), ay),
+                       gz = (uint32_t)min(max(Z - 1 + i, 0), az);
+        xo[i] = (uint64_t)(gx / P.total[0]) * P.slot_voxels + gx % P.total[0];
+        yo[i] = (uint64_t)(gy / P.total[1]) * slot_y + (uint64_t)(gy % P.total[1]) * (uint32_t)sy;
+        zo[i] = (uint64_t)(gz / P.total[2]) * slot_z + (uint64_t)(gz % P.total[2]) * (uint32_t)sz;
       }
     }
   }
@@ -247,6 +255,19 @@ __device__ __forceinline__ void report_missing(const RayConsts& P, uint32_t x, u
   } while (++rehash < P.rehash_count);
 }
 
+enum { IN_SHARD = 0, PARTLY_IN_SHARD = 1, OUTSIDE_SHARD = 2 };
+
+// position of the brick box [c0,c1] relative to the sort-last shard box
+__device__ __forceinline__ int classify_brick(const RayConsts& P, f3 c0, f3 c1) {
+  if (!P.shard) return IN_SHARD;
+  if (c1.x <= P.sh_lo[0] || c0.x >= P.sh_hi[0] || c1.y <= P.sh_lo[1] || c0.y >= P.sh_hi[1] || c1.z <= P.sh_lo[2] ||
+      c0.z >= P.sh_hi[2])
+    return OUTSIDE_SHARD;
+  const bool inside = c0.x >= P.sh_lo[0] && c1.x <= P.sh_hi[0] && c0.y >= P.sh_lo[1] && c1.y <= P.sh_hi[1] &&
+                      c0.z >= P.sh_lo[2] && c1.z <= P.sh_hi[2];
+  return inside ? IN_SHARD : PARTLY_IN_SHARD;
+}
+
 __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& lod, f3 dir, f3 dv, BrickRef& o) {
   const uint32_t max_lod = P.lod_count - 1;
   pos = F3(clampf(pos.x, 0.0f, 1.0f), clampf(pos.y, 0.0f, 1.0f), clampf(pos.z, 0.0f, 1.0f));
@@ -254,7 +275,16 @@ __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& 
   uint32_t bx, by, bz;
   brick_coords(P, pos, lod, bx, by, bz);
   uint32_t info = brick_info(P, bx, by, bz, lod);
-  if (info == TVK_BI_MISSING) {
+  // sort-last: a missing brick that does not touch this rank's block lives on another rank.  It is walked
+  // through (same step arithmetic, nominal slot 0) but never requested, sampled or replaced by a coarser
+  // level, so the ray reaches this rank's block at the single-GPU ray's sample phase.
+  bool foreign = false;
+  if (P.shard && info == TVK_BI_MISSING) {
+    const f3 fl = F3(P.lod_layout[lod]);
+    foreign = classify_brick(P, div3(F3((float)bx, (float)by, (float)bz), fl),
+                             div3(F3((float)(bx + 1), (float)(by + 1), (float)(bz + 1)), fl)) == OUTSIDE_SHARD;
+  }
+  if (info == TVK_BI_MISSING && !foreign) {
     const uint32_t start = lod;
     report_missing(P, bx, by, bz, lod);
     found = false;
@@ -271,7 +301,7 @@ __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& 
       }
     }
   }
-  o.empty = info <= TVK_BI_EMPTY;
+  o.empty = !foreign && info <= TVK_BI_EMPTY;
   if (o.empty) {
     for (uint32_t lo = lod + 1; lo < max_lod; ++lo) {   // strict <, GLVolumePool.cpp:593
       uint32_t lx, ly, lz;
@@ -291,13 +321,15 @@ __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& 
   float tm = fminf(fminf(tx, ty), tz);
   o.norm_exit = add3(pos, scl3(dir, tm));
   o.bx = bx; o.by = by; o.bz = bz; o.bl = lod;
+  o.where = IN_SHARD;
   if (o.empty) return found;
-  if (P.count && P.visited) {   // only set by the counting launch
+  o.where = foreign ? OUTSIDE_SHARD : classify_brick(P, c0, c1);
+  if (P.count && P.visited && o.where != OUTSIDE_SHARD) {   // only set by the counting launch
     const uint32_t id = brick_index(P, bx, by, bz, lod);
     atomicOr(P.visited + (id >> 5), 1u << (id & 31));
   }
   // InfoToCoords / BrickPoolCoords / NormCoordsToPoolCoords
-  const uint32_t index = info - TVK_BI_FLAG_COUNT;
+  const uint32_t index = foreign ? 0u : info - TVK_BI_FLAG_COUNT;
   const uint32_t sx = index % P.capacity[0], sy = (index / P.capacity[0]) % P.capacity[1],
                  sz = index / (P.capacity[0] * P.capacity[1]);
   o.ox = sx * P.total[0]; o.oy = sy * P.total[1]; o.oz = sz * P.total[2];
@@ -343,17 +375,33 @@ __device__ __forceinline__ bool ray_setup(const RayConsts& P, uint32_t px, uint3
   float s_in = -INFINITY, s_out = INFINITY;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    const float lo = P.clip_min[i], hi = P.clip_max[i];
     if (d[i] == 0.0f) {
-      if (o[i] < lo || o[i] > hi) return false;
+      if (o[i] < 0.0f || o[i] > 1.0f) return false;
       continue;
     }
-    float t0 = (lo - o[i]) / d[i], t1 = (hi - o[i]) / d[i];
+    float t0 = (0.0f - o[i]) / d[i], t1 = (1.0f - o[i]) / d[i];
     s_in = fmaxf(s_in, fminf(t0, t1));
     s_out = fminf(s_out, fmaxf(t0, t1));
   }
   const float s0 = fmaxf(s_in, 1.0f);
   if (!(s_out > s0)) return false;
+  if (P.shard) {
+    // sort-last: the ray keeps its whole-volume entry/exit (its sample positions are those of the single-GPU
+    // ray); a pixel whose ray never meets this rank's brick block is simply not shaded
+    float a_in = -INFINITY, a_out = INFINITY;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float lo = P.clip_min[i], hi = P.clip_max[i];
+      if (d[i] == 0.0f) {
+        if (o[i] < lo || o[i] > hi) return false;
+        continue;
+      }
+      float t0 = (lo - o[i]) / d[i], t1 = (hi - o[i]) / d[i];
+      a_in = fmaxf(a_in, fminf(t0, t1));
+      a_out = fminf(a_out, fmaxf(t0, t1));
+    }
+    if (!(fminf(a_out, s_out) > fmaxf(a_in, s0))) return false;
+  }
   const f3 pe = scl3(pn, s0), px_ = scl3(pn, s_out);
   f4 e = xform4(P.emm, pe.x, pe.y, pe.z, 1.0f);
   f4 x = xform4(P.emm, px_.x, px_.y, px_.z, 1.0f);
@@ -445,6 +493,7 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
     bool alive = ray_len > voxel_size;
     uint32_t j = 0;          // bricks visited (the shader's j < 100 bound)
     int steps_left = 0;      // samples left in the current brick
+    bool b_partial = false;  // sort-last: the current brick straddles the shard box (ownership per sample)
     f3 pc = entry, b_trans = entry, b_inv = entry, b_exit = entry;
     uint32_t b_ox = 0, b_oy = 0, b_oz = 0;
     const T* vox = pool;
@@ -458,6 +507,12 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
 #pragma unroll 1
       for (int f = 0; do_fetch && f < 4 && alive && steps_left == 0; f++) {
         if (j >= 100) { alive = false; break; }
+        if (P.shard) {   // the block is convex: once the ray has left it there is nothing more to do on this rank
+          const bool gone = (dir.x > 0.0f && cur.x >= P.sh_hi[0]) || (dir.x < 0.0f && cur.x <= P.sh_lo[0]) ||
+                            (dir.y > 0.0f && cur.y >= P.sh_hi[1]) || (dir.y < 0.0f && cur.y <= P.sh_lo[1]) ||
+                            (dir.z > 0.0f && cur.z >= P.sh_hi[2]) || (dir.z < 0.0f && cur.z <= P.sh_lo[2]);
+          if (gone) { alive = false; break; }
+        }
         const float cur_depth = entry_depth * (1.0f - t) + exit_depth * t;
         uint32_t lod = compute_lod(P, cur_depth);
         n_bricks++;
@@ -479,8 +534,14 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
           vox = pool + b.base;
           pc = b.pool_entry;
           lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
-          if (steps > 0) { steps_left = steps; n_samples += (unsigned long long)steps; break; }
-          cur = mul3(sub3(pc, b_trans), b_inv);   // zero-step brick
+          b_partial = b.where == PARTLY_IN_SHARD;
+          if (b.where == OUTSIDE_SHARD) {   // another rank's brick: advance by its steps, take no sample
+            const float n = (float)max(steps, 0);
+            pc = F3(fmaf(n, vdir.x, pc.x), fmaf(n, vdir.y, pc.y), fmaf(n, vdir.z, pc.z));
+            steps = 0;
+          }
+          if (steps > 0) { steps_left = steps; break; }
+          cur = mul3(sub3(pc, b_trans), b_inv);   // zero-step (or foreign) brick
         } else {
           cur = add3(b.norm_exit, nudge);
           lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
@@ -495,9 +556,17 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
       }
       // ---- sample phase: one sample for every lane that is inside a brick ----
       if (alive && steps_left > 0) {
-        Foot<T, FAST, BS> f;
-        f.set(P, vox, b_ox, b_oy, b_oz, pc);
         bool terminated = false;
+        bool mine = true;
+        if (b_partial) {
+          const f3 mq = mul3(sub3(pc, b_trans), b_inv);
+          mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
+                 mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
+        }
+        if (mine) {
+        Foot<T, FAST, BS> f;
+        f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
+        if (COUNT) n_samples++;
         if (!ISO) {
           f4 col;
           if (MODE == 0 && !LIT) {
@@ -539,13 +608,13 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
 #pragma unroll 1
             for (int k = 0; k < 5; k++) {
               rd = F3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
-              f.set(P, vox, b_ox, b_oy, b_oz, pc);
+              f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
               if (f.tap(P, 0, 0, 0) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
             }
             cur = mul3(sub3(pc, b_trans), b_inv);
             hit_pos = xform4(P.m2e, cur.x, cur.y, cur.z, 1.0f);
             hit_pos.w = 1.0f + 1.0f;   // color.r + 1
-            f.set(P, vox, b_ox, b_oy, b_oz, pc);
+            f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
             float dummy; f3 g;
             f.sample_with_gradient(P, dummy, g);
             f3 n = mul3(g, dscale);
@@ -561,9 +630,9 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
             hit_pos = from4(zero4);
           }
         }
+        }   // mine
         steps_left--;
         if (terminated) {
-          n_samples -= (unsigned long long)steps_left;   // samples of this brick that were never taken
           alive = false;
         } else {
           pc = add3(pc, vdir);

@@ -39,7 +39,9 @@ struct RayConsts {
   uint32_t hash_size, rehash_count;
   int32_t strategy;
   uint32_t finest[3];   // finest brick layout (hash serialisation)
-  float clip_min[3], clip_max[3];
+  float clip_min[3], clip_max[3];   // sort-last shard box (ray hit test)
+  int32_t shard;                    // shard box != whole volume
+  float sh_lo[3], sh_hi[3];         // shard box with faces on the volume border pushed to -/+inf
   int32_t nearest;
   int32_t first_pass;   // region is blank: ray entry computed, start colour = 0
   int32_t count;        // accumulate counters

@@ -487,6 +487,9 @@ int derive(tvk_ctx* ctx, RayConsts& u) {
     u.ghost[i] = ctx->overlap;
     u.finest[i] = ctx->pool_layout[0][i];
     u.clip_min[i] = p.clip_min[i]; u.clip_max[i] = p.clip_max[i];
+    if (p.clip_min[i] > 0.0f || p.clip_max[i] < 1.0f) u.shard = 1;
+    u.sh_lo[i] = p.clip_min[i] > 0.0f ? p.clip_min[i] : -INFINITY;
+    u.sh_hi[i] = p.clip_max[i] < 1.0f ? p.clip_max[i] : INFINITY;
   }
   u.lod_count = ctx->pool_lod_count;
   for (uint32_t l = 0; l < ctx->pool_lod_count; l++) {

@@ -2,7 +2,9 @@
 
 New design (the reference is single-GPU): the volume is cut into G = 2^k convex
 axis-aligned blocks by recursive bisection along the longest axis (in finest-level brick units, so
-block faces coincide with brick faces).  Rank g renders only rays clipped to its block into a
+block faces coincide with brick faces).  Rank g walks every ray that meets its block from the ray's true
+entry point (so its sample positions are those of the single-GPU ray; bricks of other ranks are stepped
+through without sampling or paging) and takes only the samples inside its block, into a
 full-resolution premultiplied RGBA32F image; log2(G) binary-swap rounds then exchange half of the
 remaining image region with partner `rank ^ 2^r` (torch.distributed P2P = ncclSend/ncclRecv in one
 group) and blend with the library's over-operator kernel in the front-to-back order given by the
