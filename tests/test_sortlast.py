@@ -40,6 +40,19 @@ def test_shard_boxes_tile_the_brick_grid(n):
     assert (cover == 1).all()           # disjoint and complete
 
 
+def test_view_dependent_axes_put_blocks_side_by_side():
+    # looking mostly along z: never cut z; 8 ranks = 4 slabs along the most perpendicular axis x 2 along the next
+    assert sortlast.split_axes((0.1, -0.3, 0.9), 2) == [0]
+    assert sortlast.split_axes((0.1, -0.3, 0.9), 4) == [0, 1]
+    assert sortlast.split_axes((0.1, -0.3, 0.9), 8) == [0, 1, 0]
+    boxes, _ = sortlast.shard_boxes((8, 8, 8), 8, [0, 1, 0])
+    assert all(hi[2] - lo[2] == 8 for lo, hi in boxes)
+    assert sorted({(lo[0], hi[0]) for lo, hi in boxes}) == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    # an axis that cannot be cut any more falls back to the longest one
+    boxes, splits = sortlast.shard_boxes((1, 6, 4), 4, [0, 0])
+    assert [a for lvl in splits for a, _ in lvl.values()] == [1, 2, 2] or len(boxes) == 4
+
+
 def test_non_power_of_two_is_refused():
     with pytest.raises(ValueError):
         sortlast.shard_boxes((4, 4, 4), 3)
@@ -90,9 +103,13 @@ def run_in_process(images, plans):
     return imgs
 
 
-def partial_images(s, n):
+def partial_images(s, n, view_dependent=False):
     finest, fl, ext = scene_layout(s)
-    boxes, splits = sortlast.shard_boxes(finest, n)
+    axes = None
+    if view_dependent:
+        mv, _ = s.matrices()
+        axes = sortlast.split_axes((0.5 - sortlast.eye_in_volume(mv, ext)) * ext, n)
+    boxes, splits = sortlast.shard_boxes(finest, n, axes)
     outs = []
     for r in range(n):
         cmin, cmax = sortlast.box_to_clip(boxes[r], finest, fl)
@@ -107,11 +124,12 @@ def partial_images(s, n):
 
 @pytest.mark.parametrize("name,n", [("c2_bricked36_1d_ert", 2), ("ragged_1d_lit", 4), ("inside_aniso_2d", 8),
                                     ("c3_bricked36_2d_lit", 2), ("c4_f32_iso", 4)])
-def test_sort_last_image_matches_single_renderer(name, n):
+@pytest.mark.parametrize("view_dependent", [False, True])
+def test_sort_last_image_matches_single_renderer(name, n, view_dependent):
     s = golden_scenes.make(name)
     s._name = name
     single = s.oracle_render()
-    parts, plans = partial_images(s, n)
+    parts, plans = partial_images(s, n, view_dependent)
     done = run_in_process(parts, plans)
     n_pix = s.width * s.height
     final = np.zeros((n_pix, 4), np.float32)

@@ -18,8 +18,19 @@ import math
 import numpy as np
 
 
-def shard_boxes(finest_layout, n_ranks):
-    """Recursive bisection of the finest brick grid into n_ranks (power of two) blocks.
+def split_axes(view_dir, n_ranks):
+    """Axis to bisect at every level for a camera looking along `view_dir` (volume space): the axes most
+    PERPENDICULAR to the view first (k = 3: 4 slabs along the best axis x 2 along the second best), so the blocks
+    lie side by side on screen instead of behind each other.  A ray then crosses one or two blocks, early ray
+    termination keeps working as on one GPU, and no rank renders samples that a front rank already made invisible."""
+    k = int(round(math.log2(n_ranks)))
+    order = sorted(range(3), key=lambda i: (abs(float(view_dir[i])), i))
+    return [order[0], order[1], order[0]][:k]
+
+
+def shard_boxes(finest_layout, n_ranks, axes=None):
+    """Recursive bisection of the finest brick grid into n_ranks (power of two) blocks.  axes[level] = axis cut at
+    that level (split_axes); None or an axis with fewer than 2 bricks left: the longest axis of the block.
     Returns (boxes, splits): boxes[g] = (lo[3], hi[3]) in brick units; splits = list, one entry per
     bisection LEVEL l (0 = first cut) of dict{prefix -> (axis, cut_brick)} keyed by the rank's top-l bits."""
     k = int(round(math.log2(n_ranks)))
@@ -32,6 +43,8 @@ def shard_boxes(finest_layout, n_ranks):
         for prefix, (lo, hi) in boxes.items():
             ext = [hi[i] - lo[i] for i in range(3)]
             axis = int(np.argmax(ext))
+            if axes is not None and ext[axes[level]] >= 2:
+                axis = int(axes[level])
             if ext[axis] < 2:
                 raise ValueError("volume has too few bricks to shard %d ways" % n_ranks)
             cut = lo[axis] + (ext[axis] + 1) // 2
@@ -130,18 +143,25 @@ def binary_swap(image, plan, dist, over, recv_buf):
 class SortLastRenderer:
     """One rank of the sort-last renderer: a CudaGridLeaper restricted to its block + the compositor."""
 
-    def __init__(self, renderer, rank, n_ranks, finest_layout, float_layout, extent):
+    def __init__(self, renderer, rank, n_ranks, finest_layout, float_layout, extent, view_dependent=True):
         import torch
         import torch.distributed as dist
         self.r, self.rank, self.n = renderer, rank, n_ranks
         self.torch, self.dist = torch, dist
         self.finest, self.flayout, self.extent = tuple(finest_layout), tuple(float_layout), tuple(extent)
-        self.boxes, self.splits = shard_boxes(self.finest, n_ranks)
-        cmin, cmax = box_to_clip(self.boxes[rank], self.finest, self.flayout)
-        renderer.SetShardBox(cmin, cmax)
+        self.view_dependent = view_dependent
+        self._axes = None
+        self._partition(None)
         self._img = None
         self._recv = None
         self._gather = None
+
+    def _partition(self, axes):
+        """(Re)cut the brick grid; bricks of the new block are paged in by the renderer's normal miss path."""
+        self._axes = axes
+        self.boxes, self.splits = shard_boxes(self.finest, self.n, axes)
+        cmin, cmax = box_to_clip(self.boxes[self.rank], self.finest, self.flayout)
+        self.r.SetShardBox(cmin, cmax)
 
     def _wrap(self, ptr, n_pixels):
         torch = self.torch
@@ -154,8 +174,14 @@ class SortLastRenderer:
         """Render this rank's block (paging until converged) and composite.  Returns (lo, hi, image):
         `image[lo:hi]` are this rank's final pixels (flat RGBA32F tensor on the device)."""
         r = self.r
-        st = r.PaintUntilConverged()
+        r._push_params()
         p = r.params
+        eye = eye_in_volume(np.array(list(p.model_view)), self.extent)
+        if self.view_dependent and self.n > 1:
+            axes = split_axes((0.5 - eye) * np.asarray(self.extent, np.float64), self.n)
+            if axes != self._axes:
+                self._partition(axes)
+        st = r.PaintUntilConverged()
         n_pixels = p.width * p.height
         ptr = r.device_image_ptr()
         if self._img is None or self._img.data_ptr() != ptr or self._img.shape[0] != n_pixels:
@@ -163,7 +189,6 @@ class SortLastRenderer:
             self._recv = self.torch.empty((n_pixels // 2 + 1, 4), dtype=self.torch.float32, device="cuda")
         if self.n == 1:
             return 0, n_pixels, self._img, st
-        eye = eye_in_volume(np.array(list(p.model_view)), self.extent)
         plan = swap_plan(self.rank, self.n, self.splits, self.boxes, self.finest, self.flayout, eye, n_pixels)
 
         def over(front, back, out):
