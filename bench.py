@@ -224,6 +224,8 @@ def run_tvk(args, rank, world, local_rank):
 
     def set_view(i):
         r.SetRotation(workloads.orbit_rotation(i % n_views, n_views))
+        if sl is not None:
+            sl.update_partition()     # view-dependent brick blocks (side by side on screen)
 
     def frame(i):
         """one step on this rank; returns the stats of the (single) subframe"""

@@ -163,6 +163,18 @@ class SortLastRenderer:
         cmin, cmax = box_to_clip(self.boxes[self.rank], self.finest, self.flayout)
         self.r.SetShardBox(cmin, cmax)
 
+    def update_partition(self):
+        """Re-cut the brick grid for the renderer's current view if the view-dependent axes changed; returns the
+        camera position in normalised volume space.  Every rank derives the same cut from the same view."""
+        r = self.r
+        r._push_params()
+        eye = eye_in_volume(np.array(list(r.params.model_view)), self.extent)
+        if self.view_dependent and self.n > 1:
+            axes = split_axes((0.5 - eye) * np.asarray(self.extent, np.float64), self.n)
+            if axes != self._axes:
+                self._partition(axes)
+        return eye
+
     def _wrap(self, ptr, n_pixels):
         torch = self.torch
 
@@ -174,14 +186,9 @@ class SortLastRenderer:
         """Render this rank's block (paging until converged) and composite.  Returns (lo, hi, image):
         `image[lo:hi]` are this rank's final pixels (flat RGBA32F tensor on the device)."""
         r = self.r
-        r._push_params()
-        p = r.params
-        eye = eye_in_volume(np.array(list(p.model_view)), self.extent)
-        if self.view_dependent and self.n > 1:
-            axes = split_axes((0.5 - eye) * np.asarray(self.extent, np.float64), self.n)
-            if axes != self._axes:
-                self._partition(axes)
+        eye = self.update_partition()
         st = r.PaintUntilConverged()
+        p = r.params
         n_pixels = p.width * p.height
         ptr = r.device_image_ptr()
         if self._img is None or self._img.data_ptr() != ptr or self._img.shape[0] != n_pixels:
