@@ -62,7 +62,8 @@ struct BrickRef {
   int where;             // sort-last: 0 brick inside the shard box, 1 straddles it, 2 outside (never sampled)
   uint32_t bx, by, bz, bl;
   uint32_t ox, oy, oz;   // slot origin in virtual-atlas texels
-  uint64_t base;         // first voxel of the slot in the slot-linear pool
+  uint32_t id;           // page-table index
+  uint32_t slot;         // linear pool coordinate (slot s starts at voxel s * slot_voxels)
 };
 
 // voxel -> float.  Integer voxels are converted with the 2^23 magic number (exact below 2^23) on the
@@ -268,10 +269,14 @@ __device__ __forceinline__ int classify_brick(const RayConsts& P, f3 c0, f3 c1) 
   return inside ? IN_SHARD : PARTLY_IN_SHARD;
 }
 
-__device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& lod, f3 dir, f3 dv, BrickRef& o) {
+// Returns 1 (brick of the requested LOD present), 0 (it was missing: reported, a coarser one is returned) or
+// -1 (SPEC only: the brick is missing and this is a look-ahead call -- nothing was reported or changed; the
+// caller retries when the ray really stands at this brick, so miss reports keep the shader's order).
+template <bool SPEC>
+__device__ __forceinline__ int get_brick(const RayConsts& P, f3 pos, uint32_t& lod, f3 dir, f3 dv, BrickRef& o) {
   const uint32_t max_lod = P.lod_count - 1;
   pos = F3(clampf(pos.x, 0.0f, 1.0f), clampf(pos.y, 0.0f, 1.0f), clampf(pos.z, 0.0f, 1.0f));
-  bool found = true;
+  int found = 1;
   uint32_t bx, by, bz;
   brick_coords(P, pos, lod, bx, by, bz);
   uint32_t info = brick_info(P, bx, by, bz, lod);
@@ -285,9 +290,10 @@ __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& 
                              div3(F3((float)(bx + 1), (float)(by + 1), (float)(bz + 1)), fl)) == OUTSIDE_SHARD;
   }
   if (info == TVK_BI_MISSING && !foreign) {
+    if (SPEC) return -1;
     const uint32_t start = lod;
     report_missing(P, bx, by, bz, lod);
-    found = false;
+    found = 0;
     // the reference loops `do {...} while (brickInfo == BI_MISSING)`: the coarsest brick is always
     // resident (UploadFirstBrick), so the bound only guards a corrupted table
     while (info == TVK_BI_MISSING && lod < max_lod) {
@@ -324,16 +330,13 @@ __device__ __forceinline__ bool get_brick(const RayConsts& P, f3 pos, uint32_t& 
   o.where = IN_SHARD;
   if (o.empty) return found;
   o.where = foreign ? OUTSIDE_SHARD : classify_brick(P, c0, c1);
-  if (P.count && P.visited && o.where != OUTSIDE_SHARD) {   // only set by the counting launch
-    const uint32_t id = brick_index(P, bx, by, bz, lod);
-    atomicOr(P.visited + (id >> 5), 1u << (id & 31));
-  }
+  o.id = brick_index(P, bx, by, bz, lod);   // only used by the counting kernels
   // InfoToCoords / BrickPoolCoords / NormCoordsToPoolCoords
   const uint32_t index = foreign ? 0u : info - TVK_BI_FLAG_COUNT;
   const uint32_t sx = index % P.capacity[0], sy = (index / P.capacity[0]) % P.capacity[1],
                  sz = index / (P.capacity[0] * P.capacity[1]);
   o.ox = sx * P.total[0]; o.oy = sy * P.total[1]; o.oz = sz * P.total[2];
-  o.base = (uint64_t)index * P.slot_voxels;
+  o.slot = index;
   const f3 ps = F3(P.pool_size_f), ov = F3(P.overlap_tc);
   const f3 vp = F3((float)o.ox, (float)o.oy, (float)o.oz);
   const f3 vq = F3((float)(o.ox + P.total[0]), (float)(o.oy + P.total[1]), (float)(o.oz + P.total[2]));
@@ -489,73 +492,118 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
     const f3 dv = F3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);   // BrickExit's 1.0/dir
     // the empty-brick advance voxelSize*direction/rayLength
     const f3 nudge = F3(voxel_size * dir.x / ray_len, voxel_size * dir.y / ray_len, voxel_size * dir.z / ray_len);
-    // flat brick/sample loop state
-    bool alive = ray_len > voxel_size;
-    uint32_t j = 0;          // bricks visited (the shader's j < 100 bound)
+    // ---- flat loop state ---------------------------------------------------------------------
+    // The shader's nested loops (bricks along the ray / samples inside a brick) run as ONE per-warp loop with
+    // two decoupled parts: a brick CHAIN that walks the page table one segment ahead of the sampling (the next
+    // segment waits in shared memory), and the SAMPLE phase.  A chain step needs no voxel data -- the position
+    // after a brick is its entry + steps sequential adds of the step vector, repeated here exactly as the
+    // sample loop does -- so all lanes of a warp can look ahead TOGETHER whenever one lane runs dry, and a lane
+    // that finishes its brick early just picks up its waiting segment instead of idling until the slowest lane
+    // is done.  Look-ahead never has side effects: a missing brick is only processed (reported, resume state)
+    // when the ray really stands at it, so reports, resume points and counters are the shader's.
+    __shared__ float seg_f[9][64];       // next segment: pool entry, trans, 1/scale
+    __shared__ uint32_t seg_u[COUNT ? 7 : 6][64];    // slot origin (3), slot index, steps, flags (, page-table index)
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    bool ray_live = ray_len > voxel_size;   // the ray has not terminated (ERT / iso hit)
+    bool chain = ray_live;                  // the brick chain has not reached the end of the ray
+    bool have_next = false;                 // a prefetched segment waits in shared memory
+    uint32_t j = 0;          // bricks visited by the chain (the shader's j < 100 bound)
     int steps_left = 0;      // samples left in the current brick
     bool b_partial = false;  // sort-last: the current brick straddles the shard box (ownership per sample)
-    f3 pc = entry, b_trans = entry, b_inv = entry, b_exit = entry;
+    f3 pc = entry, b_trans = entry, b_inv = entry;
     uint32_t b_ox = 0, b_oy = 0, b_oz = 0;
     const T* vox = pool;
+    unsigned long long pend = 0;   // COUNT: brick visits of the chain that the sampling has not reached yet
 
-    while (alive) {
-      // ---- fetch phase: advance to the next brick that has samples (a few empty ones per turn).
-      // The warp only pays for it when enough lanes starve (or nobody can sample).
+    while (ray_live) {
+      // ---- chain phase: runs for the whole warp when some lane can neither sample nor pick up a segment
       const unsigned act = __activemask();
-      const unsigned starving = __ballot_sync(act, steps_left == 0);
-      const bool do_fetch = __popc(starving) >= kFetchLanes || starving == act;
+      const bool need = steps_left == 0 && !have_next && chain;
+      if (__ballot_sync(act, need) != 0u) {
 #pragma unroll 1
-      for (int f = 0; do_fetch && f < 4 && alive && steps_left == 0; f++) {
-        if (j >= 100) { alive = false; break; }
-        if (P.shard) {   // the block is convex: once the ray has left it there is nothing more to do on this rank
-          const bool gone = (dir.x > 0.0f && cur.x >= P.sh_hi[0]) || (dir.x < 0.0f && cur.x <= P.sh_lo[0]) ||
-                            (dir.y > 0.0f && cur.y >= P.sh_hi[1]) || (dir.y < 0.0f && cur.y <= P.sh_lo[1]) ||
-                            (dir.z > 0.0f && cur.z >= P.sh_hi[2]) || (dir.z < 0.0f && cur.z <= P.sh_lo[2]);
-          if (gone) { alive = false; break; }
-        }
-        const float cur_depth = entry_depth * (1.0f - t) + exit_depth * t;
-        uint32_t lod = compute_lod(P, cur_depth);
-        n_bricks++;
-        BrickRef b;
-        const bool ok = get_brick(P, cur, lod, dir, dv, b);
-        if (!ok && optimal) {
-          optimal = false;
-          resume_pos.x = cur.x; resume_pos.y = cur.y; resume_pos.z = cur.z; resume_pos.w = cur_depth;
-          if (!ISO) resume_col = acc;
-        }
-        b_exit = b.norm_exit;
-        if (!b.empty && !(lbx == b.bx && lby == b.by && lbz == b.bz && lbl == b.bl)) {
-          int steps = (int)ceilf(len3(sub3(b.pool_exit, b.pool_entry)) / step);
-          const int s2 = (int)ceilf(len3(mul3(sub3(nexit, cur), b.scale)) / step);
-          steps = min(steps, s2);
-          b_inv = F3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
-          b_trans = b.trans;
-          b_ox = b.ox; b_oy = b.oy; b_oz = b.oz;
-          vox = pool + b.base;
-          pc = b.pool_entry;
-          lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
-          b_partial = b.where == PARTLY_IN_SHARD;
-          if (b.where == OUTSIDE_SHARD) {   // another rank's brick: advance by its steps, take no sample
-            const float n = (float)max(steps, 0);
-            pc = F3(fmaf(n, vdir.x, pc.x), fmaf(n, vdir.y, pc.y), fmaf(n, vdir.z, pc.z));
-            steps = 0;
+        for (int f = 0; f < 4 && chain && !have_next; f++) {
+          if (j >= 100) { chain = false; break; }
+          if (P.shard) {   // the block is convex: once the ray has left it there is nothing more to do on this rank
+            const bool gone = (dir.x > 0.0f && cur.x >= P.sh_hi[0]) || (dir.x < 0.0f && cur.x <= P.sh_lo[0]) ||
+                              (dir.y > 0.0f && cur.y >= P.sh_hi[1]) || (dir.y < 0.0f && cur.y <= P.sh_lo[1]) ||
+                              (dir.z > 0.0f && cur.z >= P.sh_hi[2]) || (dir.z < 0.0f && cur.z <= P.sh_lo[2]);
+            if (gone) { chain = false; break; }
           }
-          if (steps > 0) { steps_left = steps; break; }
-          cur = mul3(sub3(pc, b_trans), b_inv);   // zero-step (or foreign) brick
-        } else {
-          cur = add3(b.norm_exit, nudge);
-          lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
+          const float cur_depth = entry_depth * (1.0f - t) + exit_depth * t;
+          uint32_t lod = compute_lod(P, cur_depth);
+          BrickRef b;
+          int ok;
+          if (steps_left > 0) {   // look-ahead: the ray is still sampling the previous segment
+            ok = get_brick<true>(P, cur, lod, dir, dv, b);
+            if (ok < 0) break;    // missing brick: handled when the ray stands here
+          } else {
+            ok = get_brick<false>(P, cur, lod, dir, dv, b);
+            if (!ok && optimal) {
+              optimal = false;
+              resume_pos.x = cur.x; resume_pos.y = cur.y; resume_pos.z = cur.z; resume_pos.w = cur_depth;
+              if (!ISO) resume_col = acc;
+            }
+          }
+          if (COUNT) pend++;
+          if (!b.empty && !(lbx == b.bx && lby == b.by && lbz == b.bz && lbl == b.bl)) {
+            int steps = (int)ceilf(len3(sub3(b.pool_exit, b.pool_entry)) / step);
+            const int s2 = (int)ceilf(len3(mul3(sub3(nexit, cur), b.scale)) / step);
+            steps = min(steps, s2);
+            const f3 inv = F3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
+            f3 pe = b.pool_entry;
+            lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
+            if (b.where == OUTSIDE_SHARD) {   // another rank's brick: advance by its steps, take no sample
+              const float n = (float)max(steps, 0);
+              pe = F3(fmaf(n, vdir.x, pe.x), fmaf(n, vdir.y, pe.y), fmaf(n, vdir.z, pe.z));
+              steps = 0;
+            }
+            if (steps > 0) {
+              seg_f[0][tid] = pe.x; seg_f[1][tid] = pe.y; seg_f[2][tid] = pe.z;
+              seg_f[3][tid] = b.trans.x; seg_f[4][tid] = b.trans.y; seg_f[5][tid] = b.trans.z;
+              seg_f[6][tid] = inv.x; seg_f[7][tid] = inv.y; seg_f[8][tid] = inv.z;
+              seg_u[0][tid] = b.ox; seg_u[1][tid] = b.oy; seg_u[2][tid] = b.oz;
+              seg_u[3][tid] = b.slot; seg_u[4][tid] = (uint32_t)steps;
+              seg_u[5][tid] = b.where == PARTLY_IN_SHARD ? 1u : 0u;
+              if (COUNT) seg_u[6][tid] = b.id;
+              have_next = true;
+#pragma unroll 1
+              for (int i = 0; i < steps; i++) pe = add3(pe, vdir);   // where the sample loop will leave pc
+            }
+            cur = mul3(sub3(pe, b.trans), inv);
+          } else {
+            cur = add3(b.norm_exit, nudge);
+            lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
+          }
+          t = len3(sub3(entry, b.norm_exit)) / ray_len;
+          j++;
+          if (t > 0.9999f) chain = false;
         }
-        t = len3(sub3(entry, b.norm_exit)) / ray_len;
-        j++;
-        if (t > 0.9999f) alive = false;
+      }
+      // ---- pick up the waiting segment
+      if (steps_left == 0 && have_next) {
+        pc = F3(seg_f[0][tid], seg_f[1][tid], seg_f[2][tid]);
+        b_trans = F3(seg_f[3][tid], seg_f[4][tid], seg_f[5][tid]);
+        b_inv = F3(seg_f[6][tid], seg_f[7][tid], seg_f[8][tid]);
+        b_ox = seg_u[0][tid]; b_oy = seg_u[1][tid]; b_oz = seg_u[2][tid];
+        vox = pool + (uint64_t)seg_u[3][tid] * P.slot_voxels;
+        steps_left = (int)seg_u[4][tid];
+        b_partial = seg_u[5][tid] != 0u;
+        have_next = false;
+        if (COUNT) {
+          n_bricks += pend; pend = 0;
+          if (P.visited) { const uint32_t id = seg_u[6][tid]; atomicOr(P.visited + (id >> 5), 1u << (id & 31)); }
+        }
+      }
+      if (steps_left == 0 && !chain) {   // the ray left the volume (or its 100-brick budget) unterminated
+        if (COUNT) n_bricks += pend;
+        ray_live = false;
       }
       if (COUNT) {
-        n_alive_iters += alive ? 1 : 0;
-        if (__ffs(__activemask()) - 1 == (int)((threadIdx.x + threadIdx.y * blockDim.x) & 31)) n_warp_iters++;
+        n_alive_iters += ray_live ? 1 : 0;
+        if (__ffs(__activemask()) - 1 == (tid & 31)) n_warp_iters++;
       }
       // ---- sample phase: one sample for every lane that is inside a brick ----
-      if (alive && steps_left > 0) {
+      if (ray_live && steps_left > 0) {
         bool terminated = false;
         bool mine = true;
         if (b_partial) {
@@ -611,8 +659,8 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
               f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
               if (f.tap(P, 0, 0, 0) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
             }
-            cur = mul3(sub3(pc, b_trans), b_inv);
-            hit_pos = xform4(P.m2e, cur.x, cur.y, cur.z, 1.0f);
+            const f3 hp = mul3(sub3(pc, b_trans), b_inv);
+            hit_pos = xform4(P.m2e, hp.x, hp.y, hp.z, 1.0f);
             hit_pos.w = 1.0f + 1.0f;   // color.r + 1
             f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
             float dummy; f3 g;
@@ -632,17 +680,8 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
         }
         }   // mine
         steps_left--;
-        if (terminated) {
-          alive = false;
-        } else {
-          pc = add3(pc, vdir);
-          if (steps_left == 0) {   // brick done: the shader's post-loop bookkeeping
-            cur = mul3(sub3(pc, b_trans), b_inv);
-            t = len3(sub3(entry, b_exit)) / ray_len;
-            j++;
-            if (t > 0.9999f) alive = false;
-          }
-        }
+        if (terminated) ray_live = false;
+        else pc = add3(pc, vdir);
       }
     }
     // TerminateRay
