@@ -224,6 +224,23 @@ int tvk_get_device_image(tvk_ctx* ctx, void** dptr);
 /* iso mode parity taps: rayHitPos / rayHitNormal MRTs */
 int tvk_read_iso_buffers(tvk_ctx* ctx, float* hit_pos, float* hit_normal);
 
+/* ---- classic per-brick raycaster (GLRaycaster) ---------------------------------------- */
+/* one entry of AbstrRenderer::m_vCurrentBrickList (Renderer/AbstrRenderer.h:69-108) */
+typedef struct {
+  uint32_t index;        /* BrickKey index inside the LoD: z*bx*by + y*bx + x */
+  uint32_t x, y, z;
+  float    distance;     /* brick_distance (AbstrRenderer.cpp:808-841) */
+  int32_t  empty;        /* bIsEmpty: inside the frustum but ContainsData() is false */
+} tvk_classic_brick;
+/* One converged frame of the classic path: AbstrRenderer::PlanFrame at ComputeMinLODForCurrentView
+ * (AbstrRenderer.cpp:789-803,1125-1212), BuildSubFrameBrickList (:999-1100: frustum culling, legacy
+ * ContainsData, depth sort), then GLRenderer::Render3DView's brick loop with GLRaycaster::Render3DPreLoop /
+ * Render3DInLoop per brick (GLRenderer.cpp:2663-2748, GLRaycaster.cpp:348-478) and GL under-blending.
+ * 1D / 2D transfer function modes with and without lighting; the result is read with tvk_read_rgba8/32f. */
+int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* stats);
+/* parity tap: the brick list of the last classic frame (depth sorted) and its LoD */
+int tvk_get_classic_brick_list(tvk_ctx* ctx, uint32_t* lod, tvk_classic_brick* dst, uint32_t cap, uint32_t* n);
+
 /* ---- sort-last compositing (new) --------------------------------------- */
 /* out = front + (1-front.a)*back on n_pixels premultiplied RGBA32F device pixels
  * (Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153); a front pixel with alpha > 0.99

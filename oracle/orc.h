@@ -191,6 +191,28 @@ uint32_t orc_hash_decode(const uint32_t* hash, uint32_t hash_size, const uint32_
 /* GL float -> unorm8 read-back (GLFrameCapture.cpp:72-85) */
 void orc_rgba8(const float* rgba, uint64_t n_pixels, uint8_t* out);
 
+/* ------------------------------------------------------------------ */
+/* classic per-brick raycaster (GLRaycaster) -- orc_classic.cpp          */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  float center[3], ext[3];        /* world box = center +- ext/2 (AbstrRenderer.cpp:1003-1028) */
+  float tex_min[3], tex_max[3];   /* UVFDataset::GetTextCoords */
+  uint32_t n_vox[3];              /* brick size incl. ghost */
+  uint32_t coord[3];
+  uint32_t index;                 /* z*bx*by + y*bx + x inside the LoD (BrickKey index) */
+  float distance;                 /* brick_distance */
+  int32_t empty;                  /* bIsEmpty: in the frustum but ContainsData() == false */
+} orc_classic_brick;
+/* AbstrRenderer::ComputeMinLODForCurrentView, clamped to [0, lod_count-1] */
+uint32_t orc_classic_lod(const orc_render_params*, uint32_t lod_count);
+/* AbstrRenderer::BuildSubFrameBrickList for one LoD (frustum culled, min/max tested, depth sorted) */
+uint32_t orc_classic_brick_list(const orc_render_params*, uint32_t lod, uint32_t overlap, const double* minmax_lod,
+                                const double vis[4], orc_classic_brick* out, uint32_t cap);
+/* GLRenderer::Render3DView brick loop + GLRaycaster::Render3DInLoop + GL blending */
+void orc_classic_render(const orc_render_params*, uint32_t lod, const orc_classic_brick* list, uint32_t n_bricks,
+                        const void* const* brick_data, const uint8_t* tf, float* out, orc_render_stats* stats,
+                        int n_threads);
+
 /* over-operator of the sort-last compositor: front + (1-front.a)*back, aware of early ray termination
  * (a terminated front hides the back; a back image that would push alpha past 0.995 is cut there) */
 void orc_composite_over(const float* front, const float* back, uint64_t n_pixels, float* out);

@@ -47,6 +47,11 @@ class RenderParams(C.Structure):
     ]
 
 
+class ClassicBrick(C.Structure):
+    _fields_ = [("center", f32x3), ("ext", f32x3), ("tex_min", f32x3), ("tex_max", f32x3), ("n_vox", u32x3),
+                ("coord", u32x3), ("index", C.c_uint32), ("distance", C.c_float), ("empty", C.c_int32)]
+
+
 class RenderStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64),
                 ("brick_visits", C.c_uint64), ("hash_entries", C.c_uint32)]
@@ -122,6 +127,11 @@ def lib():
         "orc_hash_decode": (C.c_uint32, [P, C.c_uint32, u32x3, P]),
         "orc_rgba8": (None, [P, C.c_uint64, P]),
         "orc_composite_over": (None, [P, P, C.c_uint64, P]),
+        "orc_classic_lod": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32]),
+        "orc_classic_brick_list": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, P, C.c_double * 4, P,
+                                                C.c_uint32]),
+        "orc_classic_render": (None, [C.POINTER(RenderParams), C.c_uint32, P, C.c_uint32, P, P, P,
+                                      C.POINTER(RenderStats), C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -357,3 +367,30 @@ def composite_over(front, back):
     out = np.zeros_like(front)
     lib().orc_composite_over(_p(front), _p(back), front.size // 4, _p(out))
     return out
+
+
+def classic_lod(params, lod_count):
+    """AbstrRenderer::ComputeMinLODForCurrentView."""
+    return int(lib().orc_classic_lod(C.byref(params), lod_count))
+
+
+def classic_brick_list(params, lod, overlap, minmax_lod, vis):
+    """AbstrRenderer::BuildSubFrameBrickList for one LoD -> ctypes array of ClassicBrick (depth sorted)."""
+    mm = np.ascontiguousarray(minmax_lod, np.float64)
+    v = (C.c_double * 4)(*[float(x) for x in vis])
+    n = lib().orc_classic_brick_list(C.byref(params), lod, overlap, _p(mm), v, None, 0)
+    arr = (ClassicBrick * max(n, 1))()
+    lib().orc_classic_brick_list(C.byref(params), lod, overlap, _p(mm), v, C.cast(arr, C.c_void_p), n)
+    return arr, n
+
+
+def classic_render(params, lod, bricks, n, brick_arrays, tf, threads=1):
+    """One classic GLRaycaster frame.  brick_arrays[i]: ndarray of list entry i (None for empty bricks)."""
+    keep = [np.ascontiguousarray(a) if a is not None else None for a in brick_arrays]
+    ptrs = (C.c_void_p * max(n, 1))(*[(a.ctypes.data if a is not None else None) for a in keep])
+    out = np.zeros((params.height * params.width, 4), np.float32)
+    st = RenderStats()
+    tfb = np.ascontiguousarray(tf, np.uint8)
+    lib().orc_classic_render(C.byref(params), lod, C.cast(bricks, C.c_void_p), n, C.cast(ptrs, C.c_void_p), _p(tfb), _p(out),
+                             C.byref(st), threads)
+    return out, st

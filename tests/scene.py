@@ -230,6 +230,24 @@ class Scene:
                     subframes=subframes, paged=paged_total, requests=requests, outs=outs, params=p, atlas=atlas,
                     covered=cov, entry=entry, exit=exit_, tf=tf, last_stats=st)
 
+    def oracle_classic(self, threads=8):
+        """The classic GLRaycaster frame (AbstrRenderer::PlanFrame at the converged LoD + per-brick passes)."""
+        o = self.octree
+        pool, _ = self.oracle_pool()
+        p = self.oracle_params(pool)
+        lod = orc.classic_lod(p, self.pool_lod_count())
+        bc = o.brick_count(lod)
+        first = o.brick_index(0, 0, 0, lod)
+        mm = o.minmax[first:first + bc[0] * bc[1] * bc[2]]
+        vis = self.visibility_args()
+        bricks, n = orc.classic_brick_list(p, lod, self.overlap, mm, vis)
+        data = [None if bricks[i].empty else o.brick(*bricks[i].coord, lod) for i in range(n)]
+        img, st = orc.classic_render(p, lod, bricks, n, data, self.tf_bytes(), threads)
+        img = img.reshape(self.height, self.width, 4)
+        order = np.array([[bricks[i].index, bricks[i].empty] for i in range(n)], np.int64).reshape(-1, 2)
+        dist = np.array([bricks[i].distance for i in range(n)], np.float32)
+        return dict(image=img, rgba8=orc.rgba8(img), lod=lod, order=order, distance=dist, samples=st.samples)
+
     # ------------------------------------------------------------- product side
     def make_renderer(self, source="device", device=0):
         """CUDA renderer for the same scene.  source: 'device' = GPU bricker (tvk_build_volume),

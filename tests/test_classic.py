@@ -1,0 +1,100 @@
+"""Classic per-brick raycaster (GLRaycaster): CPU checks of the oracle's frame planning (LoD choice, brick list,
+min/max culling, depth order) and -m gpu parity of the CUDA path (tvk_render_classic) with the oracle."""
+import numpy as np
+import pytest
+
+import golden_scenes
+import tuvok_b200 as tb
+from oracle import orc
+from scene import Scene, image_diff
+from tuvok_b200 import synth
+
+CLASSIC_SCENES = {
+    "c1_single_brick_1d": {},
+    "c2_bricked36_1d_ert": {},
+    "ragged_1d_lit": {},
+    "inside_aniso_2d": {},
+    "c3_bricked36_2d_lit": {},
+    # zoomed out: the planner picks a coarser LoD, fStepScale = 2 (powf opacity correction)
+    "c2_far_lod1": dict(base="c2_bricked36_1d_ert", translation=tb.translation(0.0, 0.0, -2.2)),
+    # 2D TF + lighting on ragged u8 bricks, off-axis
+    "ragged_2d_lit": dict(base="ragged_1d_lit", mode=orc.RM_2DTRANS, lighting=True),
+}
+
+
+def make(name):
+    kw = dict(CLASSIC_SCENES[name])
+    base = kw.pop("base", name)
+    return golden_scenes.make(base, **kw)
+
+
+def test_lod_follows_screen_space_error():
+    near = make("c2_bricked36_1d_ert").oracle_classic()
+    far = make("c2_far_lod1").oracle_classic()
+    assert near["lod"] == 0 and far["lod"] >= 1
+
+
+@pytest.mark.parametrize("name", ["c2_bricked36_1d_ert", "ragged_1d_lit", "inside_aniso_2d"])
+def test_brick_list_is_culled_and_depth_sorted(name):
+    s = make(name)
+    r = s.oracle_classic()
+    o = s.octree
+    bc = o.brick_count(r["lod"])
+    n_lod = bc[0] * bc[1] * bc[2]
+    idx, empty = r["order"][:, 0], r["order"][:, 1]
+    assert len(set(idx.tolist())) == len(idx) <= n_lod            # every brick at most once
+    d = r["distance"][empty == 0]
+    assert (np.diff(d) >= 0).all()                                 # front to back
+    # bIsEmpty is the legacy one-sided/two-sided min/max test of UVFDataset::ContainsData
+    first = o.brick_index(0, 0, 0, r["lod"])
+    lo, hi = s.visibility_args()[:2]
+    for i, e in zip(idx, empty):
+        mn, mx = o.minmax[first + i][:2]
+        if s.mode == orc.RM_1DTRANS:
+            assert bool(e) == (not (hi >= mn and lo <= mx))
+
+
+def test_frustum_culling_drops_bricks_outside_the_view():
+    s = golden_scenes.make("c2_bricked36_1d_ert", translation=tb.translation(0.9, 0.0, 1.0))   # volume half off screen
+    r = s.oracle_classic()
+    bc = s.octree.brick_count(r["lod"])
+    assert 0 < len(r["order"]) < bc[0] * bc[1] * bc[2]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CLASSIC_SCENES))
+def test_cuda_classic_matches_oracle(name):
+    s = make(name)
+    ref = s.oracle_classic()
+    r = s.make_renderer("device")
+    r.enable_counters(True)
+    st = r.PaintClassic()
+    lod, order, dist = r.classic_brick_list()
+    assert lod == ref["lod"]
+    assert np.array_equal(order, ref["order"])                     # visibility list: same bricks, same flags, same order
+    assert np.array_equal(dist, ref["distance"])
+    img = r.ReadRGBA8()
+    mx, psnr = image_diff(img, ref["rgba8"])
+    assert mx <= 2 and psnr >= 45.0, (mx, psnr)
+    f = r.ReadRGBA32F()
+    if ref["lod"] == 0:                                            # no powf (libm vs CUDA) involved: identical floats
+        assert np.array_equal(f, ref["image"])
+        assert st.samples == ref["samples"]
+    else:
+        assert float(np.abs(f - ref["image"]).max()) < 1e-4
+    r.Cleanup()
+
+
+@pytest.mark.gpu
+def test_cuda_classic_callback_source_and_gridleaper_coexist():
+    # the classic path pages through the same pool as GridLeaper; both can be used on one renderer
+    s = make("ragged_1d_lit")
+    ref_c, ref_g = s.oracle_classic(), s.oracle_render()
+    r = s.make_renderer("callback")
+    assert r.PaintUntilConverged().converged
+    assert image_diff(r.ReadRGBA8(), ref_g["rgba8"])[0] <= 2
+    r.PaintClassic()
+    assert np.array_equal(r.ReadRGBA32F(), ref_c["image"])
+    assert r.PaintUntilConverged().converged
+    assert image_diff(r.ReadRGBA8(), ref_g["rgba8"])[0] <= 2
+    r.Cleanup()

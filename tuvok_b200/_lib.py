@@ -60,6 +60,11 @@ class Info(C.Structure):
                 ("pool_size", u32x3), ("pool_capacity", u32x3), ("meta_dim", u32x3), ("meta_count", C.c_uint64)]
 
 
+class ClassicBrick(C.Structure):
+    _fields_ = [("index", C.c_uint32), ("x", C.c_uint32), ("y", C.c_uint32), ("z", C.c_uint32),
+                ("distance", C.c_float), ("empty", C.c_int32)]
+
+
 BRICK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t)
 LOG_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p)
 
@@ -102,6 +107,8 @@ SIGNATURES = {
     "tvk_read_rgba32f": (C.c_int, [P, P, C.c_size_t]),
     "tvk_get_device_image": (C.c_int, [P, C.POINTER(P)]),
     "tvk_read_iso_buffers": (C.c_int, [P, P, P]),
+    "tvk_render_classic": (C.c_int, [P, C.POINTER(FrameStats)]),
+    "tvk_get_classic_brick_list": (C.c_int, [P, C.POINTER(C.c_uint32), P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "tvk_composite_over": (C.c_int, [P, P, P, P, C.c_uint64]),
     "tvk_quantize_rgba8": (C.c_int, [P, P, P, C.c_uint64]),
 }

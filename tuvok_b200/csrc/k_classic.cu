@@ -1,0 +1,254 @@
+// k_classic.cu -- the CLASSIC per-brick raycaster (GLRaycaster) as one sm_100a kernel.
+//
+// The reference renders one LoD brick by brick: CPU-sorted brick list, per brick a front-face pass into an
+// RGBA16F ray-entry FBO and a back-face pass that marches the brick's own 3D texture, GL blending
+// `dst += (1 - dst.a) * src` between bricks and a glFinish after every brick
+// (Renderer/GL/GLRaycaster.cpp:348-478, Renderer/GL/GLRenderer.cpp:151-153,2663-2748).  Here one thread is
+// one pixel ray: it walks the LoD's brick grid front to back (cell to cell across the shared box planes --
+// for a regular grid that IS the depth-sorted order restricted to the bricks the ray meets), and for every
+// listed, non-empty brick does what the brick's two GL passes do for that pixel:
+//   ray entry/exit          analytic slab test against the brick's world box center +- extension/2
+//                           (RenderBox, GLRaycaster.cpp:302-345); the entry goes through the FBO semantics:
+//                           half-precision rounding (GLRaycaster.cpp:97) and "keeps its previous content where
+//                           no front face is visible" (near plane first, Render3DPreLoop :348-381)
+//   eye -> texture          ComputeEyeToTextureMatrix (GLRaycaster.cpp:589-612)
+//   march                   GLRaycaster-1D-FS.glsl:51-82, -1D-light-FS.glsl:84-134, -2D-FS.glsl:53-94,
+//                           -2D-light-FS.glsl:61-117 with VRender1D(.Lit).glsl, Volume3D.glsl:39-60,
+//                           lighting.glsl:33-50 (eye at the origin), Compositing.glsl:33-38
+//   per-brick step / opacity exponent   SetBrickDepShaderVars (GLRaycaster.cpp:239-300)
+// The bricks live in the same slot-linear pool as the GridLeaper path (the reference keeps one 3D texture per
+// brick in GPUMemMan's LRU cache, GPUMemMan.cpp:846-996); the per-brick table maps a brick of the LoD to its
+// slot.  Same arithmetic contract as k_raycast.cu (-fmad=false, explicit fmaf in lerps / dots / compositing).
+#include <cuda_fp16.h>
+#include "tvk_dev.h"
+
+namespace tvk {
+namespace {
+
+#include "tvk_math.cuh"
+
+__device__ __forceinline__ float half_round(float v) { return __half2float(__float2half_rn(v)); }
+
+// texture3D(texVolume, tc) of ONE brick: GL_LINEAR / GL_NEAREST, clamp-to-edge on the brick's own size,
+// voxels at slot strides.  Gradient taps sit +-1 texel from the centre and share its filter fractions.
+template <typename T>
+struct BrickTex {
+  const T* base;
+  uint32_t xo[4], yo[4], zo[4];
+  float fx, fy, fz, norm;
+  bool nearest;
+  __device__ __forceinline__ void set(const T* b, const uint32_t n[3], uint32_t sy, uint32_t sz, f3 tc, bool nn, float nrm) {
+    base = b; nearest = nn; norm = nrm;
+    int X, Y, Z;
+    if (nn) {
+      X = (int)floorf(tc.x * (float)n[0]); Y = (int)floorf(tc.y * (float)n[1]); Z = (int)floorf(tc.z * (float)n[2]);
+      fx = fy = fz = 0.0f;
+    } else {
+      const float ux = fmaf(tc.x, (float)n[0], -0.5f), uy = fmaf(tc.y, (float)n[1], -0.5f), uz = fmaf(tc.z, (float)n[2], -0.5f);
+      const float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
+      fx = ux - x0; fy = uy - y0; fz = uz - z0;
+      X = (int)x0; Y = (int)y0; Z = (int)z0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      xo[i] = (uint32_t)min(max(X - 1 + i, 0), (int)n[0] - 1);
+      yo[i] = (uint32_t)min(max(Y - 1 + i, 0), (int)n[1] - 1) * sy;
+      zo[i] = (uint32_t)min(max(Z - 1 + i, 0), (int)n[2] - 1) * sz;
+    }
+  }
+  __device__ __forceinline__ float v(int i, int j, int k) const { return cvt(__ldg(base + (xo[1 + i] + yo[1 + j] + zo[1 + k]))); }
+  __device__ __forceinline__ float tap(int dx, int dy, int dz) const {
+    if (nearest) return v(dx, dy, dz) * norm;
+    return tri(v(dx, dy, dz), v(dx + 1, dy, dz), v(dx, dy + 1, dz), v(dx + 1, dy + 1, dz), v(dx, dy, dz + 1),
+               v(dx + 1, dy, dz + 1), v(dx, dy + 1, dz + 1), v(dx + 1, dy + 1, dz + 1), fx, fy, fz) * norm;
+  }
+  // ComputeGradient (Volume3D.glsl:43-53; the "Yp" tap is fetched at -delta)
+  __device__ __forceinline__ f3 gradient() const {
+    const float xp = tap(1, 0, 0), xm = tap(-1, 0, 0);
+    const float yp = tap(0, -1, 0), ym = tap(0, 1, 0);
+    const float zp = tap(0, 0, 1), zm = tap(0, 0, -1);
+    return F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+  }
+};
+
+__device__ __forceinline__ f4 tf_fetch(const ClassicConsts& P, float s, float t) {
+  const int w = (int)P.tf_w, h = (int)P.tf_h;
+  int ix = (int)floorf(s * (float)w);
+  ix = min(max(ix, 0), w - 1);
+  int iy = 0;
+  if (h > 1) { iy = (int)floorf(t * (float)h); iy = min(max(iy, 0), h - 1); }
+  const float4 q = __ldg(P.tf + (size_t)iy * w + ix);
+  f4 r; r.x = q.x; r.y = q.y; r.z = q.z; r.w = q.w;
+  return r;
+}
+
+// MODE: 0 = 1D TF, 1 = 2D TF
+template <typename T, int MODE, bool LIT>
+__global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ ClassicConsts P) {
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const uint32_t px = blockIdx.x * 8 + (lane & 7);
+  const uint32_t py = blockIdx.y * 8 + wid * 4 + (lane >> 3);
+  if (px >= P.width || py >= P.height) return;
+  const size_t pix = (size_t)py * P.width + px;
+  const uint32_t S = P.axis_stride;
+  f4 acc; acc.x = acc.y = acc.z = acc.w = 0.0f;
+  unsigned long long n_samples = 0;
+
+  // the eye ray through the pixel centre: eye-space points s * pn, world-space o + s * d
+  const float nx = ((float)px + 0.5f) / (float)P.width * 2.0f - 1.0f;
+  const float ny = ((float)py + 0.5f) / (float)P.height * 2.0f - 1.0f;
+  const f4 nr = xform4(P.inv_proj, nx, ny, -1.0f, 1.0f);
+  const f3 pn = F3(nr.x / nr.w, nr.y / nr.w, nr.z / nr.w);
+  const f4 o4 = xform4(P.imv, 0.0f, 0.0f, 0.0f, 1.0f);
+  const f4 n4 = xform4(P.imv, pn.x, pn.y, pn.z, 1.0f);
+  const float o[3] = {o4.x, o4.y, o4.z};
+  const float d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
+  const uint32_t lay[3] = {P.layout[0], P.layout[1], P.layout[2]};
+
+  // enter the brick grid (its outer planes), not before the near plane
+  float g_in = -INFINITY, g_out = INFINITY;
+  bool hit = true;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float lo = P.plane[a * S], hi = P.plane[a * S + lay[a]];
+    if (d[a] == 0.0f) { if (o[a] < lo || o[a] > hi) hit = false; continue; }
+    const float t0 = (lo - o[a]) / d[a], t1 = (hi - o[a]) / d[a];
+    g_in = fmaxf(g_in, fminf(t0, t1));
+    g_out = fminf(g_out, fmaxf(t0, t1));
+  }
+  const float s_start = fmaxf(g_in, 1.0f);
+  if (hit && g_out > s_start) {
+    int cell[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {   // cell that holds the entry point (planes are monotone)
+      const float w = o[a] + s_start * d[a];
+      int i = 0;
+      while (i + 1 < (int)lay[a] && w >= P.plane[a * S + i + 1]) i++;
+      cell[a] = i;
+    }
+    f3 fbo = F3(half_round(pn.x), half_round(pn.y), half_round(pn.z));   // near-plane pass (Render3DPreLoop)
+    const f3 dscale = F3(P.domain_scale), la = F3(P.light_a), ld = F3(P.light_d), ls = F3(P.light_s), ldir = F3(P.light_dir);
+    const T* pool = (const T*)P.pool;
+    const uint32_t sy = P.total[0], sz = P.total[0] * P.total[1];
+    const int max_cells = (int)(lay[0] + lay[1] + lay[2]);
+#pragma unroll 1
+    for (int it = 0; it < max_cells; it++) {
+      const uint32_t slot1 = __ldg(P.table + ((size_t)cell[2] * lay[1] + cell[1]) * lay[0] + cell[0]);
+      if (slot1 != 0u) {
+        float lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) { lo[a] = P.pmin[a * S + cell[a]]; hi[a] = P.pmax[a * S + cell[a]]; }
+        float s_in = -INFINITY, s_out = INFINITY;
+        bool miss = false;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          if (d[a] == 0.0f) { if (o[a] < lo[a] || o[a] > hi[a]) miss = true; continue; }
+          const float t0 = (lo[a] - o[a]) / d[a], t1 = (hi[a] - o[a]) / d[a];
+          s_in = fmaxf(s_in, fminf(t0, t1));
+          s_out = fminf(s_out, fmaxf(t0, t1));
+        }
+        if (!miss && s_out > fmaxf(s_in, 1.0f)) {
+          if (s_in > 1.0f) {   // a visible front face overwrites the ray-entry FBO
+            const f3 fe = scl3(pn, s_in);
+            fbo = F3(half_round(fe.x), half_round(fe.y), half_round(fe.z));
+          }
+          const f3 entry = fbo, exit_ = scl3(pn, s_out);
+          const f3 pmax = F3(hi[0], hi[1], hi[2]);
+          const f3 tsc = F3(P.tsc[cell[0]], P.tsc[S + cell[1]], P.tsc[2 * S + cell[2]]);
+          const f3 tmax = F3(P.tmax[cell[0]], P.tmax[S + cell[1]], P.tmax[2 * S + cell[2]]);
+          const uint32_t nv[3] = {P.nvox[cell[0]], P.nvox[S + cell[1]], P.nvox[2 * S + cell[2]]};
+          const float ray_step = fminf(P.rstep[cell[0]], fminf(P.rstep[S + cell[1]], P.rstep[2 * S + cell[2]]));
+          const f4 we = xform4(P.imv, entry.x, entry.y, entry.z, 1.0f), wx = xform4(P.imv, exit_.x, exit_.y, exit_.z, 1.0f);
+          const f3 et = add3(mul3(sub3(F3(we.x, we.y, we.z), pmax), tsc), tmax);
+          const f3 xt = add3(mul3(sub3(F3(wx.x, wx.y, wx.z), pmax), tsc), tmax);
+          f3 rd = sub3(exit_, entry);
+          const float len = len3(rd);
+          const float nsteps = len / ray_step;
+          const int count = (int)nsteps + 1;
+          const f3 inc_tex = F3((xt.x - et.x) / nsteps, (xt.y - et.y) / nsteps, (xt.z - et.z) / nsteps);
+          rd = F3(rd.x / len, rd.y / len, rd.z / len);
+          const f3 inc = scl3(rd, ray_step);
+          const T* vox = pool + (uint64_t)(slot1 - 1u) * P.slot_voxels;
+          f4 col; col.x = col.y = col.z = col.w = 0.0f;
+          f3 ct = et, cp = entry;
+#pragma unroll 1
+          for (int s = 0; s < count; s++) {
+            n_samples++;
+            BrickTex<T> tx;
+            tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+            const float data = tx.tap(0, 0, 0);
+            f4 sc;
+            if (MODE == 0 && !LIT) {
+              sc = tf_fetch(P, data * P.trans_scale, 0.0f);
+            } else {
+              const f3 g = tx.gradient();
+              if (MODE == 0) sc = tf_fetch(P, data * P.trans_scale, 0.0f);
+              else sc = tf_fetch(P, data * P.trans_scale, 1.0f - len3(g) * P.gradient_scale);
+              if (LIT) {
+                // ComputeNormal: gl_NormalMatrix * (gradient * domainScale), safe-normalised
+                const f3 gs = mul3(g, dscale);
+                const float* m = P.imv;
+                f3 nrm = F3(m[0] * gs.x + m[1] * gs.y + m[2] * gs.z, m[4] * gs.x + m[5] * gs.y + m[6] * gs.z,
+                            m[8] * gs.x + m[9] * gs.y + m[10] * gs.z);
+                const float l = len3(nrm);
+                if (l > 0.0f) nrm = scl3(nrm, 1.0f / l);
+                f3 lit = lighting(F3(0.0f, 0.0f, 0.0f), cp, nrm, la, mul3(F3(sc.x, sc.y, sc.z), ld), ls, ldir);
+                if (MODE == 1) lit = F3(clampf(lit.x, 0.0f, 1.0f), clampf(lit.y, 0.0f, 1.0f), clampf(lit.z, 0.0f, 1.0f));
+                sc.x = lit.x; sc.y = lit.y; sc.z = lit.z;
+              }
+            }
+            sc.w = P.step_scale == 1.0f ? sc.w : 1.0f - powf(1.0f - sc.w, P.step_scale);
+            const float oma = 1.0f - col.w;   // UnderCompositing
+            col.x = fmaf(sc.x * oma, sc.w, col.x); col.y = fmaf(sc.y * oma, sc.w, col.y);
+            col.z = fmaf(sc.z * oma, sc.w, col.z); col.w = fmaf(sc.w, oma, col.w);
+            if (col.w >= 0.99f) break;
+            cp = add3(cp, inc);
+            ct = add3(ct, inc_tex);
+          }
+          // GL blending ONE_MINUS_DST_ALPHA, ONE
+          const float k = 1.0f - acc.w;
+          acc.x = fmaf(k, col.x, acc.x); acc.y = fmaf(k, col.y, acc.y);
+          acc.z = fmaf(k, col.z, acc.z); acc.w = fmaf(k, col.w, acc.w);
+        }
+      }
+      // leave the cell through the nearest of its far planes
+      float best = INFINITY; int ax = -1;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        if (d[a] == 0.0f) continue;
+        const float pl = P.plane[a * S + cell[a] + (d[a] > 0.0f ? 1 : 0)];
+        const float t = (pl - o[a]) / d[a];
+        if (t < best) { best = t; ax = a; }
+      }
+      if (ax < 0) break;
+      cell[ax] += d[ax] > 0.0f ? 1 : -1;
+      if (cell[ax] < 0 || cell[ax] >= (int)lay[ax]) break;
+    }
+  }
+  P.out[pix] = make_float4(acc.x, acc.y, acc.z, acc.w);
+  if (P.count) atomicAdd(P.counters, n_samples);
+}
+
+template <typename T>
+void launch_t(const ClassicConsts& c, int mode, int lighting, cudaStream_t s) {
+  const dim3 block(64), grid((c.width + 7) / 8, (c.height + 7) / 8);
+  if (mode == TVK_RM_1DTRANS) {
+    if (lighting) classic_kernel<T, 0, true><<<grid, block, 0, s>>>(c);
+    else classic_kernel<T, 0, false><<<grid, block, 0, s>>>(c);
+  } else {
+    if (lighting) classic_kernel<T, 1, true><<<grid, block, 0, s>>>(c);
+    else classic_kernel<T, 1, false><<<grid, block, 0, s>>>(c);
+  }
+}
+
+}  // namespace
+
+void launch_classic(const ClassicConsts& c, int mode, int lighting, int dtype, cudaStream_t s) {
+  switch (dtype) {
+    case TVK_U8: launch_t<uint8_t>(c, mode, lighting, s); break;
+    case TVK_U16: launch_t<uint16_t>(c, mode, lighting, s); break;
+    default: launch_t<float>(c, mode, lighting, s); break;
+  }
+}
+
+}  // namespace tvk

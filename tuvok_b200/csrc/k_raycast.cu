@@ -32,29 +32,7 @@
 namespace tvk {
 namespace {
 
-struct f3 { float x, y, z; };
-struct f4 { float x, y, z, w; };
-__device__ __forceinline__ f3 F3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ f3 F3(const float* p) { return F3(p[0], p[1], p[2]); }
-__device__ __forceinline__ f3 add3(f3 a, f3 b) { return F3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return F3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ f3 mul3(f3 a, f3 b) { return F3(a.x * b.x, a.y * b.y, a.z * b.z); }
-__device__ __forceinline__ f3 div3(f3 a, f3 b) { return F3(a.x / b.x, a.y / b.y, a.z / b.z); }
-__device__ __forceinline__ f3 scl3(f3 a, float s) { return F3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float dot3(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
-__device__ __forceinline__ float len3(f3 a) { return sqrtf(dot3(a, a)); }
-__device__ __forceinline__ f3 norm3(f3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return scl3(a, inv); }
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
-
-// v' = v * M (row vectors, Basics/Vectors.h:434-439)
-__device__ __forceinline__ f4 xform4(const float* m, float x, float y, float z, float w) {
-  f4 r;
-  r.x = x * m[0] + y * m[4] + z * m[8] + w * m[12];
-  r.y = x * m[1] + y * m[5] + z * m[9] + w * m[13];
-  r.z = x * m[2] + y * m[6] + z * m[10] + w * m[14];
-  r.w = x * m[3] + y * m[7] + z * m[11] + w * m[15];
-  return r;
-}
+#include "tvk_math.cuh"
 
 struct BrickRef {
   f3 pool_entry, pool_exit, norm_exit, scale, trans;
@@ -65,23 +43,6 @@ struct BrickRef {
   uint32_t id;           // page-table index
   uint32_t slot;         // linear pool coordinate (slot s starts at voxel s * slot_voxels)
 };
-
-// voxel -> float.  Integer voxels are converted with the 2^23 magic number (exact below 2^23) on the
-// FMA/ALU pipes instead of the quarter-rate I2F conversion pipe.
-__device__ __forceinline__ float cvt(uint8_t v) { return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.0f; }
-__device__ __forceinline__ float cvt(uint16_t v) { return __uint_as_float(0x4B000000u | (uint32_t)v) - 8388608.0f; }
-__device__ __forceinline__ float cvt(float v) { return v; }
-
-__device__ __forceinline__ float tri(float v000, float v100, float v010, float v110, float v001, float v101,
-                                     float v011, float v111, float fx, float fy, float fz) {
-  float c00 = fmaf(fx, v100 - v000, v000);
-  float c10 = fmaf(fx, v110 - v010, v010);
-  float c01 = fmaf(fx, v101 - v001, v001);
-  float c11 = fmaf(fx, v111 - v011, v011);
-  float c0 = fmaf(fy, c10 - c00, c00);
-  float c1 = fmaf(fy, c11 - c01, c01);
-  return fmaf(fz, c1 - c0, c0);
-}
 
 // Filter footprint of one sample position inside a slot.
 //   FAST  (linear filter, ghost >= 2): the 4x4x4 neighbourhood [X-1..X+2]^3 always lies inside the
@@ -196,20 +157,6 @@ struct Foot {
   }
 };
 
-__device__ __forceinline__ float pow8(float x) { float a = x * x; float b = a * a; return b * b; }
-
-// lighting.glsl:33-43
-__device__ __forceinline__ f3 lighting(f3 eye, f3 pos, f3 n, f3 amb, f3 dif, f3 spe, f3 ldir) {
-  f3 view = norm3(sub3(eye, pos));
-  float dn = dot3(n, view);
-  f3 refl = norm3(sub3(view, scl3(n, 2.0f * dn)));
-  float dl = fmaxf(fabsf(dot3(n, ldir)), 0.0f);
-  float sp = pow8(fmaxf(dot3(refl, ldir), 0.0f));
-  return F3(clampf(amb.x + dif.x * dl + spe.x * sp, 0.0f, 1.0f),
-            clampf(amb.y + dif.y * dl + spe.y * sp, 0.0f, 1.0f),
-            clampf(amb.z + dif.z * dl + spe.z * sp, 0.0f, 1.0f));
-}
-
 // RGBA8 table, GL_NEAREST, clamp-to-edge (GPUMemMan.cpp:398-401, GLTexture1D.h:48-51).  The table is
 // kept as float4 = byte/255.0f (the unorm8 -> float conversion of the texture unit, done once on upload).
 __device__ __forceinline__ f4 tf_lookup(const RayConsts& P, float s, float t) {
@@ -247,7 +194,7 @@ __device__ __forceinline__ void report_missing(const RayConsts& P, uint32_t x, u
                        lod * P.finest[0] * P.finest[1] * P.finest[2];
   const unsigned act = __activemask();
   const unsigned same = __match_any_sync(act, ser);
-  if ((unsigned)(__ffs(same) - 1) != (threadIdx.x + threadIdx.y * blockDim.x) % 32u) return;
+  if ((unsigned)(__ffs(same) - 1) != (threadIdx.x & 31u)) return;
   uint32_t rehash = 0;
   do {
     uint32_t h = (ser + rehash) % P.hash_size;
@@ -423,12 +370,74 @@ constexpr int kFetchLanes = TVK_FETCH_LANES;
 #ifndef TVK_MIN_BLOCKS
 #define TVK_MIN_BLOCKS 8
 #endif
+#ifndef TVK_ILP
+#define TVK_ILP 1
+#endif
+// CTA = TVK_WX x TVK_WY warps, each an 8x4 pixel tile (CTA covers 8*WX x 4*WY pixels)
+#ifndef TVK_WX
+#define TVK_WX 1
+#endif
+#ifndef TVK_WY
+#define TVK_WY 2
+#endif
+constexpr int kWX = TVK_WX, kWY = TVK_WY, kThreads = 32 * TVK_WX * TVK_WY;
+constexpr int kIlp = TVK_ILP;   // samples per lane per loop turn (1 or 2)
+
+// State of the brick chain (page-table walk).  None of it is needed while a lane samples, so between two chain
+// phases it is PARKED in shared memory (TVK_PARK) instead of occupying ~37 registers of every thread for the
+// whole kernel; the sample phase then fits a smaller register budget and more warps are resident per SM.
+struct ChainSt {
+  f3 entry, nexit, dir, dv, nudge, cur;
+  float ray_len, step, entry_depth, exit_depth, t;
+  f4 resume_pos, resume_col;
+  uint32_t j, lbx, lby, lbz, lbl;
+  bool optimal;
+};
+#ifndef TVK_PARK
+#define TVK_PARK 0   // measured on B200 (gpurun_out/r1_ab3.log): parking + more resident warps is SLOWER (the extra
+#endif               // shared memory shrinks L1 and more warps thrash it): 229 fps vs 238; 10/12 CTAs: 179/167 fps
+constexpr bool kPark = TVK_PARK != 0;
+constexpr int kChainWords = 37;
+__device__ __forceinline__ void park_const(const ChainSt& c, float (*m)[kThreads], int tid) {   // written once per ray
+  m[0][tid] = c.entry.x; m[1][tid] = c.entry.y; m[2][tid] = c.entry.z;
+  m[3][tid] = c.nexit.x; m[4][tid] = c.nexit.y; m[5][tid] = c.nexit.z;
+  m[6][tid] = c.dir.x; m[7][tid] = c.dir.y; m[8][tid] = c.dir.z;
+  m[9][tid] = c.dv.x; m[10][tid] = c.dv.y; m[11][tid] = c.dv.z;
+  m[12][tid] = c.nudge.x; m[13][tid] = c.nudge.y; m[14][tid] = c.nudge.z;
+  m[15][tid] = c.ray_len; m[16][tid] = c.step; m[17][tid] = c.entry_depth; m[18][tid] = c.exit_depth;
+}
+__device__ __forceinline__ void park_var(const ChainSt& c, float (*m)[kThreads], int tid) {     // after every chain phase
+  m[19][tid] = c.cur.x; m[20][tid] = c.cur.y; m[21][tid] = c.cur.z; m[22][tid] = c.t;
+  m[23][tid] = c.resume_pos.x; m[24][tid] = c.resume_pos.y; m[25][tid] = c.resume_pos.z; m[26][tid] = c.resume_pos.w;
+  m[27][tid] = c.resume_col.x; m[28][tid] = c.resume_col.y; m[29][tid] = c.resume_col.z; m[30][tid] = c.resume_col.w;
+  m[31][tid] = __uint_as_float(c.j); m[32][tid] = __uint_as_float(c.lbx); m[33][tid] = __uint_as_float(c.lby);
+  m[34][tid] = __uint_as_float(c.lbz); m[35][tid] = __uint_as_float(c.lbl);
+  m[36][tid] = __uint_as_float(c.optimal ? 1u : 0u);
+}
+__device__ __forceinline__ void unpark_result(ChainSt& c, float (*m)[kThreads], int tid) {      // what TerminateRay needs
+  c.resume_pos.x = m[23][tid]; c.resume_pos.y = m[24][tid]; c.resume_pos.z = m[25][tid]; c.resume_pos.w = m[26][tid];
+  c.resume_col.x = m[27][tid]; c.resume_col.y = m[28][tid]; c.resume_col.z = m[29][tid]; c.resume_col.w = m[30][tid];
+  c.optimal = __float_as_uint(m[36][tid]) != 0u;
+}
+__device__ __forceinline__ void unpark(ChainSt& c, float (*m)[kThreads], int tid) {
+  c.entry = F3(m[0][tid], m[1][tid], m[2][tid]);
+  c.nexit = F3(m[3][tid], m[4][tid], m[5][tid]);
+  c.dir = F3(m[6][tid], m[7][tid], m[8][tid]);
+  c.dv = F3(m[9][tid], m[10][tid], m[11][tid]);
+  c.nudge = F3(m[12][tid], m[13][tid], m[14][tid]);
+  c.ray_len = m[15][tid]; c.step = m[16][tid]; c.entry_depth = m[17][tid]; c.exit_depth = m[18][tid];
+  c.cur = F3(m[19][tid], m[20][tid], m[21][tid]); c.t = m[22][tid];
+  c.j = __float_as_uint(m[31][tid]); c.lbx = __float_as_uint(m[32][tid]); c.lby = __float_as_uint(m[33][tid]);
+  c.lbz = __float_as_uint(m[34][tid]); c.lbl = __float_as_uint(m[35][tid]);
+  unpark_result(c, m, tid);
+}
 
 // MODE: 0 = 1D TF, 1 = 2D TF, 2 = isosurface
 template <typename T, int MODE, bool LIT, bool FAST, int BS, bool COUNT>
-__global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __grid_constant__ RayConsts P) {
-  const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t py = blockIdx.y * blockDim.y + threadIdx.y;
+__global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) raycast_kernel(const __grid_constant__ RayConsts P) {
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const uint32_t px = blockIdx.x * (8 * kWX) + (wid % kWX) * 8 + (lane & 7);
+  const uint32_t py = blockIdx.y * (4 * kWY) + (wid / kWX) * 4 + (lane >> 3);
   if (px >= P.width || py >= P.height) return;
   const size_t pix = (size_t)py * P.width + px;
   constexpr bool ISO = MODE == 2;
@@ -444,7 +453,11 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
     if (ISO) P.out3[pix] = zero4;
     return;
   }
-  f4 acc, resume_col, resume_pos;
+  __shared__ float park[kPark ? kChainWords : 1][kThreads];
+  ChainSt c;
+  f4 acc;
+  f4& resume_col = c.resume_col;
+  f4& resume_pos = c.resume_pos;
   f4 hit_pos = from4(zero4), hit_nrm = from4(zero4), resume_nrm = from4(zero4);
   bool done = false;
   if (P.first_pass) {
@@ -468,30 +481,31 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
     }
   }
   if (!done) {
-    const f3 entry = F3(resume_pos.x, resume_pos.y, resume_pos.z);
-    const float entry_depth = resume_pos.w;
-    const f3 nexit = F3(exit4.x, exit4.y, exit4.z);
-    const float exit_depth = exit4.w;
-    const f3 dir = sub3(nexit, entry);
-    const float ray_len = len3(dir);
+    c.entry = F3(resume_pos.x, resume_pos.y, resume_pos.z);
+    c.entry_depth = resume_pos.w;
+    c.nexit = F3(exit4.x, exit4.y, exit4.z);
+    c.exit_depth = exit4.w;
+    c.dir = sub3(c.nexit, c.entry);
+    c.ray_len = len3(c.dir);
     // TransformToPoolSpace
     const f3 ps = F3(P.pool_size_f);
-    f3 vdir = norm3(mul3(dir, F3(P.vol_f)));
+    f3 vdir = norm3(mul3(c.dir, F3(P.vol_f)));
     vdir = div3(vdir, ps);
     const float den = 2.0f * P.sample_rate;
     vdir = F3(vdir.x / den, vdir.y / den, vdir.z / den);
-    const float step = len3(vdir);
-    float t = 0.0f;
-    bool optimal = true;
+    c.step = len3(vdir);
+    c.t = 0.0f;
+    c.optimal = true;
     const float voxel_size = 0.125f / 2000.0f;
-    f3 cur = entry;
-    uint32_t lbx = 0, lby = 0, lbz = 0, lbl = 9999;
+    c.cur = c.entry;
+    c.j = 0;   // bricks visited by the chain (the shader's j < 100 bound)
+    c.lbx = 0; c.lby = 0; c.lbz = 0; c.lbl = 9999;
     const f3 dscale = F3(P.domain_scale), eye_m = F3(P.eye_m), la = F3(P.light_a), ld = F3(P.light_d),
              ls = F3(P.light_s), ldir = F3(P.light_dir_m);
 
-    const f3 dv = F3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);   // BrickExit's 1.0/dir
+    c.dv = F3(1.0f / c.dir.x, 1.0f / c.dir.y, 1.0f / c.dir.z);   // BrickExit's 1.0/dir
     // the empty-brick advance voxelSize*direction/rayLength
-    const f3 nudge = F3(voxel_size * dir.x / ray_len, voxel_size * dir.y / ray_len, voxel_size * dir.z / ray_len);
+    c.nudge = F3(voxel_size * c.dir.x / c.ray_len, voxel_size * c.dir.y / c.ray_len, voxel_size * c.dir.z / c.ray_len);
     // ---- flat loop state ---------------------------------------------------------------------
     // The shader's nested loops (bricks along the ray / samples inside a brick) run as ONE per-warp loop with
     // two decoupled parts: a brick CHAIN that walks the page table one segment ahead of the sampling (the next
@@ -501,57 +515,57 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
     // that finishes its brick early just picks up its waiting segment instead of idling until the slowest lane
     // is done.  Look-ahead never has side effects: a missing brick is only processed (reported, resume state)
     // when the ray really stands at it, so reports, resume points and counters are the shader's.
-    __shared__ float seg_f[9][64];       // next segment: pool entry, trans, 1/scale
-    __shared__ uint32_t seg_u[COUNT ? 7 : 6][64];    // slot origin (3), slot index, steps, flags (, page-table index)
-    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
-    bool ray_live = ray_len > voxel_size;   // the ray has not terminated (ERT / iso hit)
+    __shared__ float seg_f[9][kThreads];       // next segment: pool entry, trans, 1/scale
+    __shared__ uint32_t seg_u[COUNT ? 7 : 6][kThreads];    // slot origin (3), slot index, steps, flags (, page-table index)
+    bool ray_live = c.ray_len > voxel_size;   // the ray has not terminated (ERT / iso hit)
     bool chain = ray_live;                  // the brick chain has not reached the end of the ray
     bool have_next = false;                 // a prefetched segment waits in shared memory
-    uint32_t j = 0;          // bricks visited by the chain (the shader's j < 100 bound)
     int steps_left = 0;      // samples left in the current brick
     bool b_partial = false;  // sort-last: the current brick straddles the shard box (ownership per sample)
-    f3 pc = entry, b_trans = entry, b_inv = entry;
+    f3 pc = c.entry, b_trans = c.entry, b_inv = c.entry;
     uint32_t b_ox = 0, b_oy = 0, b_oz = 0;
     const T* vox = pool;
     unsigned long long pend = 0;   // COUNT: brick visits of the chain that the sampling has not reached yet
 
+    if (kPark) { park_const(c, park, tid); park_var(c, park, tid); }
     while (ray_live) {
       // ---- chain phase: runs for the whole warp when some lane can neither sample nor pick up a segment
       const unsigned act = __activemask();
       const bool need = steps_left == 0 && !have_next && chain;
-      if (__ballot_sync(act, need) != 0u) {
+      if (__ballot_sync(act, need) != 0u && chain && !have_next) {
+        if (kPark) unpark(c, park, tid);
 #pragma unroll 1
         for (int f = 0; f < 4 && chain && !have_next; f++) {
-          if (j >= 100) { chain = false; break; }
+          if (c.j >= 100) { chain = false; break; }
           if (P.shard) {   // the block is convex: once the ray has left it there is nothing more to do on this rank
-            const bool gone = (dir.x > 0.0f && cur.x >= P.sh_hi[0]) || (dir.x < 0.0f && cur.x <= P.sh_lo[0]) ||
-                              (dir.y > 0.0f && cur.y >= P.sh_hi[1]) || (dir.y < 0.0f && cur.y <= P.sh_lo[1]) ||
-                              (dir.z > 0.0f && cur.z >= P.sh_hi[2]) || (dir.z < 0.0f && cur.z <= P.sh_lo[2]);
+            const bool gone = (c.dir.x > 0.0f && c.cur.x >= P.sh_hi[0]) || (c.dir.x < 0.0f && c.cur.x <= P.sh_lo[0]) ||
+                              (c.dir.y > 0.0f && c.cur.y >= P.sh_hi[1]) || (c.dir.y < 0.0f && c.cur.y <= P.sh_lo[1]) ||
+                              (c.dir.z > 0.0f && c.cur.z >= P.sh_hi[2]) || (c.dir.z < 0.0f && c.cur.z <= P.sh_lo[2]);
             if (gone) { chain = false; break; }
           }
-          const float cur_depth = entry_depth * (1.0f - t) + exit_depth * t;
+          const float cur_depth = c.entry_depth * (1.0f - c.t) + c.exit_depth * c.t;
           uint32_t lod = compute_lod(P, cur_depth);
           BrickRef b;
           int ok;
           if (steps_left > 0) {   // look-ahead: the ray is still sampling the previous segment
-            ok = get_brick<true>(P, cur, lod, dir, dv, b);
+            ok = get_brick<true>(P, c.cur, lod, c.dir, c.dv, b);
             if (ok < 0) break;    // missing brick: handled when the ray stands here
           } else {
-            ok = get_brick<false>(P, cur, lod, dir, dv, b);
-            if (!ok && optimal) {
-              optimal = false;
-              resume_pos.x = cur.x; resume_pos.y = cur.y; resume_pos.z = cur.z; resume_pos.w = cur_depth;
+            ok = get_brick<false>(P, c.cur, lod, c.dir, c.dv, b);
+            if (!ok && c.optimal) {
+              c.optimal = false;
+              resume_pos.x = c.cur.x; resume_pos.y = c.cur.y; resume_pos.z = c.cur.z; resume_pos.w = cur_depth;
               if (!ISO) resume_col = acc;
             }
           }
           if (COUNT) pend++;
-          if (!b.empty && !(lbx == b.bx && lby == b.by && lbz == b.bz && lbl == b.bl)) {
-            int steps = (int)ceilf(len3(sub3(b.pool_exit, b.pool_entry)) / step);
-            const int s2 = (int)ceilf(len3(mul3(sub3(nexit, cur), b.scale)) / step);
+          if (!b.empty && !(c.lbx == b.bx && c.lby == b.by && c.lbz == b.bz && c.lbl == b.bl)) {
+            int steps = (int)ceilf(len3(sub3(b.pool_exit, b.pool_entry)) / c.step);
+            const int s2 = (int)ceilf(len3(mul3(sub3(c.nexit, c.cur), b.scale)) / c.step);
             steps = min(steps, s2);
             const f3 inv = F3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
             f3 pe = b.pool_entry;
-            lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
+            c.lbx = b.bx; c.lby = b.by; c.lbz = b.bz; c.lbl = b.bl;
             if (b.where == OUTSIDE_SHARD) {   // another rank's brick: advance by its steps, take no sample
               const float n = (float)max(steps, 0);
               pe = F3(fmaf(n, vdir.x, pe.x), fmaf(n, vdir.y, pe.y), fmaf(n, vdir.z, pe.z));
@@ -569,15 +583,16 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
 #pragma unroll 1
               for (int i = 0; i < steps; i++) pe = add3(pe, vdir);   // where the sample loop will leave pc
             }
-            cur = mul3(sub3(pe, b.trans), inv);
+            c.cur = mul3(sub3(pe, b.trans), inv);
           } else {
-            cur = add3(b.norm_exit, nudge);
-            lbx = b.bx; lby = b.by; lbz = b.bz; lbl = b.bl;
+            c.cur = add3(b.norm_exit, c.nudge);
+            c.lbx = b.bx; c.lby = b.by; c.lbz = b.bz; c.lbl = b.bl;
           }
-          t = len3(sub3(entry, b.norm_exit)) / ray_len;
-          j++;
-          if (t > 0.9999f) chain = false;
+          c.t = len3(sub3(c.entry, b.norm_exit)) / c.ray_len;
+          c.j++;
+          if (c.t > 0.9999f) chain = false;
         }
+        if (kPark) park_var(c, park, tid);
       }
       // ---- pick up the waiting segment
       if (steps_left == 0 && have_next) {
@@ -602,53 +617,89 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
         n_alive_iters += ray_live ? 1 : 0;
         if (__ffs(__activemask()) - 1 == (tid & 31)) n_warp_iters++;
       }
-      // ---- sample phase: one sample for every lane that is inside a brick ----
+      // ---- sample phase: TVK_ILP samples for every lane that is inside a brick ----
       if (ray_live && steps_left > 0) {
         bool terminated = false;
-        bool mine = true;
-        if (b_partial) {
-          const f3 mq = mul3(sub3(pc, b_trans), b_inv);
-          mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
-                 mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
-        }
-        if (mine) {
-        Foot<T, FAST, BS> f;
-        f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
-        if (COUNT) n_samples++;
+        int taken = 1;
         if (!ISO) {
-          f4 col;
-          if (MODE == 0 && !LIT) {
-            const float data = f.tap(P, 0, 0, 0);
-            col = tf_lookup(P, data * P.trans_scale, 0.0f);
-          } else {
-            float data; f3 g;
-            f.sample_with_gradient(P, data, g);
-            f3 n;
-            if (MODE == 0) {
+          // ComputeColorFromVolume + OpacityCorrectColor at pool position q
+          auto shade = [&](f3 q) -> f4 {
+            Foot<T, FAST, BS> f;
+            f.set(P, pool, vox, b_ox, b_oy, b_oz, q);
+            f4 col;
+            if (MODE == 0 && !LIT) {
+              const float data = f.tap(P, 0, 0, 0);
               col = tf_lookup(P, data * P.trans_scale, 0.0f);
-              n = mul3(g, dscale);   // ComputeNormal
-              const float l = len3(n);
-              if (l > 0.0f) n = scl3(n, 1.0f / l);
             } else {
-              const float gm = len3(g);
-              col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
-              const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
-              n = mul3(dscale, gn);
+              float data; f3 g;
+              f.sample_with_gradient(P, data, g);
+              f3 n;
+              if (MODE == 0) {
+                col = tf_lookup(P, data * P.trans_scale, 0.0f);
+                n = mul3(g, dscale);   // ComputeNormal
+                const float l = len3(n);
+                if (l > 0.0f) n = scl3(n, 1.0f / l);
+              } else {
+                const float gm = len3(g);
+                col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
+                const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
+                n = mul3(dscale, gn);
+              }
+              if (LIT) {
+                const f3 mp = mul3(sub3(q, b_trans), b_inv);
+                const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
+                col.x = lit.x; col.y = lit.y; col.z = lit.z;
+              }
             }
-            if (LIT) {
-              const f3 mp = mul3(sub3(pc, b_trans), b_inv);
-              const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
-              col.x = lit.x; col.y = lit.y; col.z = lit.z;
+            col.w = opacity_correct(P, col.w);
+            return col;
+          };
+          auto blend = [&](f4 col) {   // UnderCompositing
+            const float oma = 1.0f - acc.w;
+            acc.x = fmaf(col.x * oma, col.w, acc.x);
+            acc.y = fmaf(col.y * oma, col.w, acc.y);
+            acc.z = fmaf(col.z * oma, col.w, acc.z);
+            acc.w = fmaf(col.w, oma, acc.w);
+          };
+          if (kIlp == 2 && !b_partial) {
+            // two consecutive samples of the ray are classified and shaded as independent instruction streams
+            // (the second one speculatively) and composited in order; a lane on the last sample of its brick
+            // shades that sample twice and drops the copy
+            const bool two = steps_left >= 2;
+            const f4 c0 = shade(pc);
+            const f4 c1 = shade(two ? add3(pc, vdir) : pc);
+            blend(c0);
+            if (acc.w > 0.99f) terminated = true;
+            else if (two) {
+              blend(c1);
+              taken = 2;
+              if (acc.w > 0.99f) terminated = true;
+            }
+            if (COUNT) n_samples += (unsigned long long)taken;
+          } else {
+            bool mine = true;
+            if (b_partial) {
+              const f3 mq = mul3(sub3(pc, b_trans), b_inv);
+              mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
+                     mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
+            }
+            if (mine) {
+              if (COUNT) n_samples++;
+              blend(shade(pc));
+              if (acc.w > 0.99f) terminated = true;
             }
           }
-          col.w = opacity_correct(P, col.w);
-          const float oma = 1.0f - acc.w;   // UnderCompositing
-          acc.x = fmaf(col.x * oma, col.w, acc.x);
-          acc.y = fmaf(col.y * oma, col.w, acc.y);
-          acc.z = fmaf(col.z * oma, col.w, acc.z);
-          acc.w = fmaf(col.w, oma, acc.w);
-          if (acc.w > 0.99f) terminated = true;
         } else {
+          bool mine = true;
+          if (b_partial) {
+            const f3 mq = mul3(sub3(pc, b_trans), b_inv);
+            mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
+                   mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
+          }
+          if (mine) {
+          Foot<T, FAST, BS> f;
+          f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
+          if (COUNT) n_samples++;
           if (f.tap(P, 0, 0, 0) >= P.isoval) {
             // RefineIsosurface
             f3 rd = F3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
@@ -677,18 +728,22 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
           } else {
             hit_pos = from4(zero4);
           }
+          }   // mine
         }
-        }   // mine
-        steps_left--;
+        steps_left -= taken;
         if (terminated) ray_live = false;
-        else pc = add3(pc, vdir);
+        else {
+          pc = add3(pc, vdir);
+          if (taken == 2) pc = add3(pc, vdir);
+        }
       }
     }
+    if (kPark) unpark_result(c, park, tid);
     // TerminateRay
     if (!ISO) {
-      if (optimal) { resume_pos.w = 1000.0f; resume_col = acc; }
+      if (c.optimal) { resume_pos.w = 1000.0f; resume_col = acc; }
     } else {
-      if (optimal) resume_pos.w = hit_pos.w == 0.0f ? 1000.0f : 499.0f + hit_pos.w;
+      if (c.optimal) resume_pos.w = hit_pos.w == 0.0f ? 1000.0f : 499.0f + hit_pos.w;
       resume_nrm = hit_nrm;
     }
   }
@@ -706,8 +761,8 @@ __global__ void __launch_bounds__(64, TVK_MIN_BLOCKS) raycast_kernel(const __gri
 
 template <typename T, int MODE, bool LIT>
 void launch_t(const RayConsts& rc, cudaStream_t s) {
-  dim3 block(8, 8);
-  dim3 grid((rc.width + 7) / 8, (rc.height + 7) / 8);
+  dim3 block(kThreads);
+  dim3 grid((rc.width + 8 * kWX - 1) / (8 * kWX), (rc.height + 4 * kWY - 1) / (4 * kWY));
   // FAST addressing needs the +-1 gradient taps of every legal sample position inside the slot
   bool fast = !rc.nearest;
   for (int i = 0; i < 3; i++) fast = fast && rc.total[i] >= 4 && rc.ghost[i] >= 2;

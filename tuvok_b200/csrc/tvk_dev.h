@@ -69,6 +69,33 @@ void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rg
 void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s);
 void launch_composite_over(const float4* front, const float4* back, float4* out, uint64_t n, cudaStream_t s);
 
+// classic per-brick raycaster (k_classic.cu): uniforms of GLRaycaster::SetBrickDepShaderVars / RenderBox plus the
+// per-axis brick tables of the LoD (the brick boxes of one LoD are a tensor-product grid, so everything the
+// per-brick passes need is stored per axis: [3][axis_stride])
+struct ClassicConsts {
+  uint32_t width, height;
+  float inv_proj[16], imv[16];      // inverse projection, inverse(modelView)
+  float domain_scale[3], light_a[3], light_d[3], light_s[3], light_dir[3];
+  float norm, trans_scale, gradient_scale, step_scale;
+  uint32_t tf_w, tf_h;
+  const float4* tf;
+  int32_t nearest, count;
+  uint32_t layout[3];               // bricks per axis of the LoD
+  uint32_t total[3];                // slot strides (max brick size)
+  uint32_t axis_stride;
+  const float* plane;               // [3][n+1] cell planes shared by neighbouring bricks
+  const float* pmin; const float* pmax;   // [3][n] brick box center -+ extension/2
+  const float* tmax; const float* tsc;    // [3][n] texcoord of the max corner, (tMin - tMax) / (pMin - pMax)
+  const float* rstep;               // [3][n] extension * (1/voxelCount) * (0.5/sampleRate); the ray step is their min
+  const uint32_t* nvox;             // [3][n] brick size incl. ghost
+  const uint32_t* table;            // per brick of the LoD (x fastest): 0 = not rendered, else pool slot + 1
+  const void* pool;
+  uint64_t slot_voxels;
+  float4* out;
+  unsigned long long* counters;
+};
+void launch_classic(const ClassicConsts& c, int mode, int lighting, int dtype, cudaStream_t s);
+
 // page table / visibility (k_pool.cu)
 struct VisConsts {
   int32_t mode;

@@ -136,6 +136,9 @@ void free_frame(tvk_ctx* c) {
   if (c->rgba8_d) cudaFree(c->rgba8_d);
   c->rgba8_d = nullptr;
   c->img_w = c->img_h = 0;
+  if (c->classic_axis_d) cudaFree(c->classic_axis_d);
+  if (c->classic_table_d) cudaFree(c->classic_table_d);
+  c->classic_axis_d = nullptr; c->classic_table_d = nullptr; c->classic_axis_cap = c->classic_table_cap = 0;
 }
 
 int ensure_frame(tvk_ctx* ctx, uint32_t w, uint32_t h) {
@@ -1216,6 +1219,315 @@ int tvk_quantize_rgba8(tvk_ctx* ctx, const void* rgba32f, void* rgba8, uint64_t 
   cudaSetDevice(ctx->cfg.device);
   launch_quantize_rgba8((const float4*)rgba32f, (uchar4*)rgba8, n_pixels, ctx->stream);
   CU(cudaGetLastError());
+  return TVK_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// classic per-brick path (GLRaycaster): frame planning on the host, one traversal kernel
+// =================================================================================================
+namespace {
+
+struct F3h { float x, y, z; };
+inline float maxv(F3h a) { return std::fmax(a.x, std::fmax(a.y, a.z)); }
+
+// ExtendedOctree::ComputeMetadata's per-LoD aspect (anisotropic downsampling, ExtendedOctree.cpp:188-243)
+void lod_aspect(const tvk_ctx* ctx, uint32_t lod, double out[3]) {
+  double asp[3] = {1.0, 1.0, 1.0};
+  for (uint32_t l = 1; l <= lod; l++) {
+    for (int i = 0; i < 3; i++) {
+      const uint64_t s = ctx->lod_size[l - 1][i], n = ctx->lod_size[l][i];
+      if (s > 1) asp[i] *= (s % 2) ? float(s) / float(n) : 2;
+    }
+    const double mx = std::max(asp[0], std::max(asp[1], asp[2]));
+    for (int i = 0; i < 3; i++) asp[i] /= mx;
+  }
+  for (int i = 0; i < 3; i++) out[i] = asp[i];
+}
+
+// vScale of BuildSubFrameBrickList / RegionNeedsBrick for a given domain size (AbstrRenderer.cpp:1003-1012,886-891)
+F3h corrected_scale(const tvk_ctx* ctx, const uint32_t dom[3]) {
+  const float dmax = (float)std::max(dom[0], std::max(dom[1], dom[2]));
+  F3h c = {ctx->scale[0] * (float)dom[0] / dmax, ctx->scale[1] * (float)dom[1] / dmax, ctx->scale[2] * (float)dom[2] / dmax};
+  const float m = maxv(c);
+  return F3h{ctx->scale[0] / m, ctx->scale[1] / m, ctx->scale[2] / m};
+}
+
+struct AxisTab { std::vector<float> center_md, ext_md; std::vector<uint32_t> nvox; };
+
+// UVFDataset::ComputeMetadataTOC (IO/uvfDataset.cpp:242-288) per axis: the x/y/z loops accumulate the brick
+// corner independently per axis, so centre and extent of brick (x,y,z) are (cx[x], cy[y], cz[z]) etc.
+void axis_tables(const tvk_ctx* ctx, uint32_t lod, AxisTab tab[3], float asp_f[3]) {
+  double asp[3];
+  lod_aspect(ctx, lod, asp);
+  float nds[3];
+  for (int i = 0; i < 3; i++) { asp_f[i] = (float)asp[i]; nds[i] = (float)ctx->lod_size[lod][i] * asp_f[i]; }
+  const float max_val = std::fmax(nds[0], std::fmax(nds[1], nds[2]));
+  for (int i = 0; i < 3; i++) nds[i] = nds[i] / max_val;
+  for (int a = 0; a < 3; a++) {
+    const uint32_t n = ctx->layout[lod][a];
+    tab[a].center_md.resize(n); tab[a].ext_md.resize(n); tab[a].nvox.resize(n);
+    float corner = 0.0f;
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t co[3] = {0, 0, 0};
+      co[a] = i;
+      uint32_t bs[3];
+      brick_size(ctx, co, lod, bs);
+      const float eff = (float)(bs[a] - 2 * ctx->overlap);
+      const float ext = eff * asp_f[a] / max_val;
+      tab[a].nvox[i] = bs[a];
+      tab[a].ext_md[i] = ext;
+      tab[a].center_md[i] = (corner + ext / 2.0f) - nds[a] * 0.5f;
+      corner += ext;
+    }
+  }
+}
+
+int ensure_classic(tvk_ctx* ctx, size_t axis_words, size_t table_words) {
+  if (ctx->classic_axis_cap < axis_words) {
+    if (ctx->classic_axis_d) cudaFree(ctx->classic_axis_d);
+    ctx->classic_axis_d = nullptr; ctx->classic_axis_cap = 0;
+    CU(cudaMalloc(&ctx->classic_axis_d, axis_words * 4));
+    ctx->classic_axis_cap = axis_words;
+  }
+  if (ctx->classic_table_cap < table_words) {
+    if (ctx->classic_table_d) cudaFree(ctx->classic_table_d);
+    ctx->classic_table_d = nullptr; ctx->classic_table_cap = 0;
+    CU(cudaMalloc(&ctx->classic_table_d, table_words * 4));
+    ctx->classic_table_cap = table_words;
+  }
+  return TVK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
+  if (!ctx) return TVK_ERR_INVALID;
+  cudaSetDevice(ctx->cfg.device);
+  if (st) std::memset(st, 0, sizeof(*st));
+  int rc = check_renderable(ctx);
+  if (rc) return rc;
+  const tvk_render_params& p = ctx->params;
+  if (p.mode == TVK_RM_ISOSURFACE) return fail(ctx, TVK_ERR_INVALID, "classic path: isosurface mode is not built yet");
+  rc = ensure_frame(ctx, p.width, p.height);
+  if (rc) return rc;
+  // ---- AbstrRenderer::ComputeMinLODForCurrentView (AbstrRenderer.cpp:789-803, CullingLOD.cpp:126-138) ----
+  float ex[3];
+  for (int i = 0; i < 3; i++) ex[i] = (float)ctx->vol[i] * ctx->scale[i];
+  const float emax = std::fmax(ex[0], std::fmax(ex[1], ex[2]));
+  for (int i = 0; i < 3; i++) ex[i] = ex[i] / emax;
+  const float lzwse = std::fmax(ex[0] / (float)ctx->vol[0], std::fmax(ex[1] / (float)ctx->vol[1], ex[2] / (float)ctx->vol[2]));
+  const float z_near = (float)((double)p.projection[14] / ((double)p.projection[10] - 1.0));
+  const float fz = std::fmax(z_near, -p.model_view[14]);
+  int lod_i = (int)floorf(logf(p.lod_factor * fz / lzwse) / logf(2.0f));
+  lod_i = std::max(0, std::min(lod_i, (int)ctx->pool_lod_count - 1));   // the brick store holds the pool LoDs
+  const uint32_t lod = (uint32_t)lod_i;
+
+  // ---- AbstrRenderer::BuildSubFrameBrickList (AbstrRenderer.cpp:999-1100) ----
+  AxisTab tab[3];
+  float asp[3];
+  axis_tables(ctx, lod, tab, asp);
+  const F3h s_list = corrected_scale(ctx, ctx->lod_size[0]), s_cull = corrected_scale(ctx, ctx->lod_size[lod]);
+  const float sl[3] = {s_list.x, s_list.y, s_list.z}, sc[3] = {s_cull.x, s_cull.y, s_cull.z};
+  float mvp[16], planes[6][4];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      float s = 0.0f;
+      for (int k = 0; k < 4; k++) s += p.model_view[r * 4 + k] * p.projection[k * 4 + c];
+      mvp[r * 4 + c] = s;
+    }
+  {   // CullingLOD::Update (CullingLOD.cpp:89-124): right, left, top, bottom, far, near
+    const int col[6] = {0, 0, 1, 1, 2, 2};
+    const float sg[6] = {-1.0f, 1.0f, -1.0f, 1.0f, 1.0f, -1.0f};
+    for (int i = 0; i < 6; i++)
+      for (int r = 0; r < 4; r++) planes[i][r] = sg[i] * mvp[r * 4 + col[i]] + mvp[r * 4 + 3];
+  }
+  // AbstrRenderer::ContainsData (AbstrRenderer.cpp:953-997) with the dataset's legacy tests (uvfDataset.cpp:1201-1227)
+  const double rescale = ctx->range_max / double(ctx->tf1d_n - 1);
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+  if (p.mode == TVK_RM_1DTRANS) { v0 = double(ctx->tf1d_nz[0]) * rescale; v1 = double(ctx->tf1d_nz[1]) * rescale; }
+  else { v0 = double(ctx->tf2d_nz[0]) * rescale; v1 = double(ctx->tf2d_nz[1]) * rescale; v2 = double(ctx->tf2d_nz[2]); v3 = double(ctx->tf2d_nz[3]); }
+  const uint32_t* lay = ctx->layout[lod];
+  std::vector<tvk_classic_brick>& list = ctx->classic_list;
+  list.clear();
+  for (uint32_t z = 0; z < lay[2]; z++)
+    for (uint32_t y = 0; y < lay[1]; y++)
+      for (uint32_t x = 0; x < lay[0]; x++) {   // TOC index order == BrickTable key order
+        const uint32_t ci[3] = {x, y, z};
+        float cm[3], em[3];
+        for (int a = 0; a < 3; a++) { cm[a] = tab[a].center_md[ci[a]]; em[a] = tab[a].ext_md[ci[a]]; }
+        // CullingLOD::IsVisible (CullingLOD.cpp:141-160) on the box scaled like RegionNeedsBrick does
+        bool visible = true;
+        for (int i = 0; i < 6 && visible; i++) {
+          const float* pl = planes[i];
+          const float cx = cm[0] * sc[0], cy = cm[1] * sc[1], cz = cm[2] * sc[2];
+          const float hx = 0.5f * (em[0] * sc[0]), hy = 0.5f * (em[1] * sc[1]), hz = 0.5f * (em[2] * sc[2]);
+          if (pl[0] * cx + pl[1] * cy + pl[2] * cz + pl[3] <= -(hx * std::fabs(pl[0]) + hy * std::fabs(pl[1]) + hz * std::fabs(pl[2])))
+            visible = false;
+        }
+        if (!visible) continue;
+        tvk_classic_brick b;
+        b.index = z * lay[0] * lay[1] + y * lay[0] + x;
+        b.x = x; b.y = y; b.z = z;
+        const double* mm = &ctx->minmax_h[4 * (ctx->toc_offset[lod] + b.index)];
+        bool has;
+        if (p.mode == TVK_RM_1DTRANS) has = v1 >= mm[0] && v0 <= mm[1];
+        else has = (v1 >= mm[0] && v0 <= mm[1]) && (v3 >= mm[2] && v2 <= mm[3]);
+        b.empty = has ? 0 : 1;
+        b.distance = 0.0f;
+        if (has) {   // brick_distance (AbstrRenderer.cpp:808-841)
+          float dmin = std::numeric_limits<float>::max();
+          for (int k = 0; k < 8; k++) {
+            float q[3];
+            for (int a = 0; a < 3; a++) {
+              const float sg = (k >> (2 - a)) & 1 ? 1.0f : -1.0f;
+              q[a] = cm[a] * sl[a] + (sg * (em[a] * sl[a])) * 0.4999f;
+            }
+            const float* m = p.model_view;
+            const float tx = q[0] * m[0] + q[1] * m[4] + q[2] * m[8] + 1.0f * m[12];
+            const float ty = q[0] * m[1] + q[1] * m[5] + q[2] * m[9] + 1.0f * m[13];
+            const float tz = q[0] * m[2] + q[1] * m[6] + q[2] * m[10] + 1.0f * m[14];
+            dmin = std::fmin(dmin, sqrtf(fmaf(tz, tz, fmaf(ty, ty, tx * tx))));
+          }
+          b.distance = dmin;
+        }
+        list.push_back(b);
+      }
+  // depth sort; bricks at the same distance keep key order (the reference's std::sort leaves ties open)
+  std::stable_sort(list.begin(), list.end(), [](const tvk_classic_brick& a, const tvk_classic_brick& b) { return a.distance < b.distance; });
+  ctx->classic_lod = lod;
+
+  // ---- residency: every listed, non-empty brick must sit in the pool (GPUMemMan::GetVolume's job) ----
+  cudaStream_t s = ctx->stream;
+  CU(cudaEventRecord(ctx->ev[0], s));
+  std::vector<uint32_t> want;
+  size_t n_needed = 0;
+  for (const tvk_classic_brick& b : list) {
+    if (b.empty) continue;
+    n_needed++;
+    const uint32_t id = brick_id(ctx, b.x, b.y, b.z, lod);
+    if (ctx->meta_h[id] >= TVK_BI_FLAG_COUNT) continue;
+    want.push_back(b.x); want.push_back(b.y); want.push_back(b.z); want.push_back(lod);
+  }
+  if (n_needed > ctx->slots.size() - 1)
+    return fail(ctx, TVK_ERR_OOM, "classic path: %zu bricks of LoD %u do not fit the pool (%zu slots)", n_needed, lod,
+                ctx->slots.size());
+  uint32_t paged = 0;
+  if (!want.empty()) {
+    // LRU touch: bricks of this frame that are already resident must not be the ones replaced
+    for (tvk::Slot& sl_ : ctx->slots) {
+      if (!sl_.was_ever_used() || sl_.time == UINT64_MAX) continue;
+      // pool ids of one LoD are contiguous
+      const uint32_t first = ctx->lod_offset[lod], count = lay[0] * lay[1] * lay[2];
+      if ((uint32_t)sl_.brick_id >= first && (uint32_t)sl_.brick_id < first + count && sl_.contains_visible())
+        sl_.time = ctx->time_of_creation++;
+    }
+    rc = upload_bricks(ctx, want.data(), (uint32_t)(want.size() / 4), nullptr, &paged);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(ctx->ev[1], s));
+
+  // ---- per-brick uniforms as per-axis tables + the brick -> slot table ----
+  uint32_t nmax = std::max(lay[0], std::max(lay[1], lay[2]));
+  const uint32_t S = nmax + 1;
+  std::vector<float> ax((size_t)6 * 3 * S, 0.0f);
+  std::vector<uint32_t> nv((size_t)3 * S, 1u);
+  float* plane = ax.data(); float* pmin = plane + 3 * S; float* pmax = pmin + 3 * S;
+  float* tmax = pmax + 3 * S; float* tsc = tmax + 3 * S; float* rstep = tsc + 3 * S;
+  for (int a = 0; a < 3; a++) {
+    for (uint32_t i = 0; i < lay[a]; i++) {
+      const float c = tab[a].center_md[i] * sl[a], e = tab[a].ext_md[i] * sl[a];   // Brick::vCenter / vExtension
+      const float lo = c - e / 2.0f, hi = c + e / 2.0f;                           // RenderBox (GLRaycaster.cpp:309-311)
+      pmin[a * S + i] = lo; pmax[a * S + i] = hi;
+      plane[a * S + i] = lo;
+      if (i + 1 == lay[a]) plane[a * S + i + 1] = hi;
+      const float tmin_ = (float)ctx->overlap / (float)tab[a].nvox[i];            // UVFDataset::GetTextCoords
+      const float tmax_ = (1.0f - tmin_) * asp[a];
+      tmax[a * S + i] = tmax_;
+      tsc[a * S + i] = (tmin_ - tmax_) / (lo - hi);                                // ComputeEyeToTextureMatrix
+      rstep[a * S + i] = (e * (1.0f / (float)tab[a].nvox[i])) * (0.5f * 1.0f / p.sample_rate_modifier);
+      nv[a * S + i] = tab[a].nvox[i];
+    }
+  }
+  const size_t n_cells = (size_t)lay[0] * lay[1] * lay[2];
+  std::vector<uint32_t> table(n_cells, 0u);
+  for (const tvk_classic_brick& b : list) {
+    if (b.empty) continue;
+    const uint32_t m = ctx->meta_h[brick_id(ctx, b.x, b.y, b.z, lod)];
+    if (m < TVK_BI_FLAG_COUNT) return fail(ctx, TVK_ERR_OOM, "classic path: brick (%u,%u,%u,%u) could not be paged in", b.x, b.y, b.z, lod);
+    table[b.index] = (m - TVK_BI_FLAG_COUNT) + 1u;
+  }
+  rc = ensure_classic(ctx, ax.size() + nv.size(), n_cells);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->classic_axis_d, ax.data(), ax.size() * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->classic_axis_d + ax.size(), nv.data(), nv.size() * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(ctx->classic_table_d, table.data(), n_cells * 4, cudaMemcpyHostToDevice, s));
+
+  ClassicConsts c;
+  std::memset(&c, 0, sizeof(c));
+  c.width = p.width; c.height = p.height;
+  double mv[16], pr[16], imv[16], ipr[16];
+  for (int i = 0; i < 16; i++) { mv[i] = p.model_view[i]; pr[i] = p.projection[i]; }
+  if (!inv4(mv, imv) || !inv4(pr, ipr)) return fail(ctx, TVK_ERR_INVALID, "singular view or projection matrix");
+  for (int i = 0; i < 16; i++) { c.imv[i] = (float)imv[i]; c.inv_proj[i] = (float)ipr[i]; }
+  const float mn = std::fmin(ctx->scale[0], std::fmin(ctx->scale[1], ctx->scale[2]));
+  for (int i = 0; i < 3; i++) {
+    c.domain_scale[i] = 1.0f / (ctx->scale[i] / mn);
+    c.light_a[i] = p.ambient[i] * p.ambient[3];
+    c.light_d[i] = p.diffuse[i] * p.diffuse[3];
+    c.light_s[i] = p.specular[i] * p.specular[3];
+    c.light_dir[i] = p.light_dir[i];
+    c.layout[i] = lay[i];
+    c.total[i] = ctx->brick[i];
+  }
+  c.norm = ctx->dtype == TVK_U8 ? 1.0f / 255.0f : ctx->dtype == TVK_U16 ? 1.0f / 65535.0f : 1.0f;
+  const double full = ctx->dtype == TVK_U8 ? 255.0 : ctx->dtype == TVK_U16 ? 65535.0 : 1.0;
+  c.trans_scale = (float)(full / ctx->range_max);
+  c.gradient_scale = ctx->max_grad == 0.0f ? 1.0f : 1.0f / ctx->max_grad;
+  // fStepScale = 1/sampleRate * max(domain(0)/domain(lod)) (GLRaycaster.cpp:257)
+  c.step_scale = 1.0f / p.sample_rate_modifier *
+                 std::fmax((float)ctx->vol[0] / (float)ctx->lod_size[lod][0],
+                           std::fmax((float)ctx->vol[1] / (float)ctx->lod_size[lod][1], (float)ctx->vol[2] / (float)ctx->lod_size[lod][2]));
+  if (p.mode == TVK_RM_2DTRANS) { c.tf = ctx->tf2d_d; c.tf_w = ctx->tf2d_w; c.tf_h = ctx->tf2d_h; }
+  else { c.tf = ctx->tf1d_d; c.tf_w = ctx->tf1d_n; c.tf_h = 1; }
+  c.nearest = p.nearest;
+  c.count = ctx->counters_on ? 1 : 0;
+  c.axis_stride = S;
+  const float* base = ctx->classic_axis_d;
+  c.plane = base; c.pmin = base + 3 * S; c.pmax = base + 6 * S; c.tmax = base + 9 * S; c.tsc = base + 12 * S;
+  c.rstep = base + 15 * S;
+  c.nvox = (const uint32_t*)(base + 18 * S);
+  c.table = ctx->classic_table_d;
+  c.pool = ctx->pool_d;
+  c.slot_voxels = ctx->slot_voxels;
+  c.out = ctx->buf[0];
+  c.counters = ctx->counters_d;
+  if (ctx->counters_on) CU(cudaMemsetAsync(ctx->counters_d, 0, 8 * sizeof(unsigned long long), s));
+  launch_classic(c, p.mode, p.lighting, ctx->dtype, s);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev[2], s));
+  if (ctx->counters_on) CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));   // the host tables above must outlive their copies
+  ctx->blank = true;              // the GridLeaper resume buffers no longer describe this image
+  if (st) {
+    st->converged = 1;
+    st->bricks_paged = paged;
+    if (ctx->counters_on) st->samples = ctx->counters_h[0];
+    cudaEventElapsedTime(&st->ms_upload_bricks, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st->ms_raycast, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[2]);
+  }
+  return TVK_OK;
+}
+
+int tvk_get_classic_brick_list(tvk_ctx* ctx, uint32_t* lod, tvk_classic_brick* dst, uint32_t cap, uint32_t* n) {
+  if (!ctx || !n) return TVK_ERR_INVALID;
+  if (lod) *lod = ctx->classic_lod;
+  *n = (uint32_t)ctx->classic_list.size();
+  if (dst) std::memcpy(dst, ctx->classic_list.data(), std::min<size_t>(cap, ctx->classic_list.size()) * sizeof(tvk_classic_brick));
   return TVK_OK;
 }
 

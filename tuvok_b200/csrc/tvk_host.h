@@ -126,6 +126,12 @@ struct tvk_ctx {
   uint32_t* miss_h = nullptr;       // pinned mirror
   std::vector<uint32_t> last_missing;   // decoded (x,y,z,lod)
 
+  // ---- classic per-brick path (GLRaycaster) ----
+  std::vector<tvk_classic_brick> classic_list;   // last planned brick list (depth sorted)
+  uint32_t classic_lod = 0;
+  float* classic_axis_d = nullptr; size_t classic_axis_cap = 0;   // per-axis tables (floats + nvox)
+  uint32_t* classic_table_d = nullptr; size_t classic_table_cap = 0;
+
   // ---- frame ----
   tvk_render_params params{};
   bool have_params = false;

@@ -343,6 +343,27 @@ class CudaGridLeaper:
         self._converged = bool(st.converged)
         return st
 
+    def PaintClassic(self):
+        """One converged frame of the classic per-brick raycaster (GLRaycaster): AbstrRenderer::PlanFrame at
+        ComputeMinLODForCurrentView + the brick loop of GLRenderer::Render3DView / GLRaycaster::Render3DInLoop."""
+        self._push_params()
+        st = L.FrameStats()
+        self._ck(self._lib.tvk_render_classic(self._h, C.byref(st)))
+        self.last_stats = st
+        self._converged = True
+        return st
+
+    def classic_brick_list(self):
+        """(lod, ndarray [n, 2] of (BrickKey index, bIsEmpty), distances) of the last classic frame, depth sorted
+        (AbstrRenderer::m_vCurrentBrickList)."""
+        n, lod = C.c_uint32(0), C.c_uint32(0)
+        self._ck(self._lib.tvk_get_classic_brick_list(self._h, C.byref(lod), None, 0, C.byref(n)))
+        arr = (L.ClassicBrick * max(1, n.value))()
+        self._ck(self._lib.tvk_get_classic_brick_list(self._h, C.byref(lod), C.cast(arr, C.c_void_p), n.value, C.byref(n)))
+        order = np.array([[arr[i].index, arr[i].empty] for i in range(n.value)], np.int64).reshape(-1, 2)
+        dist = np.array([arr[i].distance for i in range(n.value)], np.float32)
+        return lod.value, order, dist
+
     def CheckForRedraw(self):
         return self._dirty or not self._converged
 
