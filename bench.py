@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="tvk", choices=["tvk", "reference"])
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--path", default="gridleaper", choices=["gridleaper", "classic"],
+                    help="gridleaper: GLGridLeaper page-table traversal (default); classic: per-brick GLRaycaster path")
     ap.add_argument("--vol", type=int, default=0, help="override the cubic volume size (debugging)")
     ap.add_argument("--cpu-vol", type=int, default=256, help="volume size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -221,6 +223,9 @@ def run_tvk(args, rank, world, local_rank):
     flayout = [f - f * np.finfo(np.float32).eps if float(int(f)) == float(f) else f for f in flayout]
     sl = sortlast.SortLastRenderer(r, rank, world, finest, flayout, ext) if world > 1 else None
     n_views = 36
+    classic = args.path == "classic"
+    if classic and world > 1:
+        raise SystemExit("the classic path is single-GPU (sort-last shards the GridLeaper path)")
 
     def set_view(i):
         r.SetRotation(workloads.orbit_rotation(i % n_views, n_views))
@@ -231,7 +236,7 @@ def run_tvk(args, rank, world, local_rank):
         """one step on this rank; returns the stats of the (single) subframe"""
         set_view(i)
         if sl is None:
-            return r.Paint()
+            return r.PaintClassic() if classic else r.Paint()
         lo, hi, img, st = sl.render()
         sl.gather(lo, hi, img)
         return st
@@ -240,7 +245,7 @@ def run_tvk(args, rank, world, local_rank):
     paged = 0
     for i in range(n_views):
         set_view(i)
-        st = r.PaintUntilConverged()
+        st = r.PaintClassic() if classic else r.PaintUntilConverged()
         paged += st.bricks_paged
         if not st.converged:
             raise RuntimeError("view %d did not converge (pool too small?)" % i)
@@ -253,7 +258,7 @@ def run_tvk(args, rank, world, local_rank):
     alive_it, warp_it = 0, 0
     for i in range(n_views):
         set_view(i)
-        st = r.Paint()
+        st = r.PaintClassic() if classic else r.Paint()
         samples.append(st.samples); rays.append(st.rays); touched.append(st.bricks_touched); visits.append(st.brick_visits)
         alive_it += st.alive_lane_iters; warp_it += st.warp_iters
     r.enable_counters(False)
@@ -287,14 +292,24 @@ def run_tvk(args, rank, world, local_rank):
 
     # ---- e2e: public API with host buffers (params in, RGBA8 image out to host) ----------------
     host_img = np.zeros((w["height"], w["width"], 4), np.uint8)
+    pinned = [r.host_alloc((w["height"], w["width"], 4)) for _ in range(2)] if sl is None else None
     gather_dev = None
+    checksum = 0
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         set_view(args.warmup + i)
         if sl is None:
-            r.Paint()
-            r.ReadRGBA8(host_img)
+            # PBO-style double-buffered read-back: frame i is copied to pinned host memory while frame i+1 renders;
+            # every frame's RGBA8 image is in host memory (and touched) before the timed region ends
+            if classic:
+                r.PaintClassic()
+            else:
+                r.Paint()
+            r.ReadRGBA8Async(pinned[i % 2])
+            r.WaitRead(pending_allowed=1)
+            if i > 0:
+                checksum += int(pinned[(i - 1) % 2][w["height"] // 2, w["width"] // 2, 3])
         else:
             lo, hi, img, _ = sl.render()
             full = sl.gather(lo, hi, img)
@@ -303,6 +318,9 @@ def run_tvk(args, rank, world, local_rank):
                     gather_dev = torch.empty(n_pixels * 4, dtype=torch.uint8, device="cuda")
                 r.quantize_rgba8(full.data_ptr(), gather_dev.data_ptr(), n_pixels)
                 host_img[...] = gather_dev.view(w["height"], w["width"], 4).cpu().numpy()
+    if sl is None:
+        r.WaitRead(0)
+        checksum += int(pinned[(args.steps - 1) % 2][w["height"] // 2, w["width"] // 2, 3])
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -348,6 +366,7 @@ def run_tvk(args, rank, world, local_rank):
             "config": {"workload": w["label"], "volume": "V_noise seed 0x5EED" if w["kind"] == 1 else "V_sph",
                        "camera": "36-step orbit (Ry 10deg steps, Rx 20deg), eye (0,0,1.6) fov 50",
                        "parallelism": "sort-last x%d (binary swap)" % world if world > 1 else "single GPU",
+                       "path": "classic per-brick GLRaycaster" if classic else "GridLeaper page-table traversal",
                        "l2_policy": "inputs larger than L2 (pool %.1f GB, %.0f MB of bricks touched per frame)" %
                                     (info.pool_capacity[0] * info.pool_capacity[1] * info.pool_capacity[2] * slot_bytes / 1e9,
                                      step_touched / k * slot_bytes / 1e6),
@@ -357,7 +376,7 @@ def run_tvk(args, rank, world, local_rank):
                        "lane_utilisation": {"sampling": float(np.sum(samples)) / max(1.0, 32.0 * warp_it),
                                             "alive": alive_it / max(1.0, 32.0 * warp_it)}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": which, "kernel": "raycast_kernel",
+                         "traffic": traffic, "peak_source": which, "kernel": "classic_kernel" if classic else "raycast_kernel",
                          "kernel_ms": ray_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "fetch_gbs": step_samples / k * (7 if (w["lighting"] or w["mode"] == 1) else 1) * 8 * esize
                                       / (ray_ms * 1e-3) / 1e9 / world},

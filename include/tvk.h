@@ -218,6 +218,16 @@ int tvk_raycast_only(tvk_ctx* ctx);
  * pitch in bytes, 0 = tight.  dst is host memory. */
 int tvk_read_rgba8(tvk_ctx* ctx, uint8_t* dst, size_t pitch);
 int tvk_read_rgba32f(tvk_ctx* ctx, float* dst, size_t pitch);
+/* Asynchronous variant (the analogue of a GL pixel-buffer-object read-back): the float -> unorm8 conversion is
+ * queued behind the frame on the render stream and the copy runs on the library's copy stream, so it overlaps
+ * the next frame's traversal.  dst must be page-locked (tvk_host_alloc); at most two reads may be in flight.
+ * tvk_read_wait returns when at most `pending_allowed` (0 or 1) queued reads have not yet landed in host memory
+ * (1 = wait for the previous frame while the newest one is still being copied). */
+int tvk_read_rgba8_async(tvk_ctx* ctx, uint8_t* dst_pinned, size_t pitch);
+int tvk_read_wait(tvk_ctx* ctx, int pending_allowed);
+/* page-locked host memory for brick sources and read-backs (cudaMallocHost / cudaFreeHost) */
+int tvk_host_alloc(tvk_ctx* ctx, size_t bytes, void** out);
+int tvk_host_free(tvk_ctx* ctx, void* p);
 /* device pointer of the RGBA32F result (width*height float4, premultiplied) for zero-copy
  * consumers such as the sort-last compositor */
 int tvk_get_device_image(tvk_ctx* ctx, void** dptr);

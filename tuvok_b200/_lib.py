@@ -105,6 +105,10 @@ SIGNATURES = {
     "tvk_raycast_only": (C.c_int, [P]),
     "tvk_read_rgba8": (C.c_int, [P, P, C.c_size_t]),
     "tvk_read_rgba32f": (C.c_int, [P, P, C.c_size_t]),
+    "tvk_read_rgba8_async": (C.c_int, [P, P, C.c_size_t]),
+    "tvk_read_wait": (C.c_int, [P, C.c_int]),
+    "tvk_host_alloc": (C.c_int, [P, C.c_size_t, C.POINTER(P)]),
+    "tvk_host_free": (C.c_int, [P, P]),
     "tvk_get_device_image": (C.c_int, [P, C.POINTER(P)]),
     "tvk_read_iso_buffers": (C.c_int, [P, P, P]),
     "tvk_render_classic": (C.c_int, [P, C.POINTER(FrameStats)]),

@@ -135,6 +135,7 @@ void free_frame(tvk_ctx* c) {
   for (auto& b : c->buf) { if (b) cudaFree(b); b = nullptr; }
   if (c->rgba8_d) cudaFree(c->rgba8_d);
   c->rgba8_d = nullptr;
+  for (auto& b : c->rgba8_async_d) { if (b) cudaFree(b); b = nullptr; }
   c->img_w = c->img_h = 0;
   if (c->classic_axis_d) cudaFree(c->classic_axis_d);
   if (c->classic_table_d) cudaFree(c->classic_table_d);
@@ -647,6 +648,8 @@ void tvk_destroy(tvk_ctx* ctx) {
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& e : ctx->read_ev) if (e) cudaEventDestroy(e);
+  if (ctx->quant_ev) cudaEventDestroy(ctx->quant_ev);
   delete ctx;
 }
 
@@ -1180,6 +1183,57 @@ int tvk_read_rgba8(tvk_ctx* ctx, uint8_t* dst, size_t pitch) {
   return TVK_OK;
 }
 
+int tvk_read_rgba8_async(tvk_ctx* ctx, uint8_t* dst, size_t pitch) {
+  if (!ctx || !dst || !ctx->img_w) return fail(ctx, TVK_ERR_INVALID, "nothing rendered");
+  cudaSetDevice(ctx->cfg.device);
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, dst) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+    cudaGetLastError();
+    return fail(ctx, TVK_ERR_INVALID, "tvk_read_rgba8_async needs page-locked memory (tvk_host_alloc)");
+  }
+  const size_t n = (size_t)ctx->img_w * ctx->img_h, row = (size_t)ctx->img_w * 4;
+  if (pitch == 0) pitch = row;
+  if (pitch < row) return fail(ctx, TVK_ERR_INVALID, "pitch too small");
+  const int k = ctx->read_slot;
+  if (!ctx->rgba8_async_d[k]) CU(cudaMalloc(&ctx->rgba8_async_d[k], n * 4));
+  if (!ctx->read_ev[k]) CU(cudaEventCreateWithFlags(&ctx->read_ev[k], cudaEventDisableTiming));
+  if (!ctx->quant_ev) CU(cudaEventCreateWithFlags(&ctx->quant_ev, cudaEventDisableTiming));
+  // the copy that last used this staging image must be done before it is overwritten
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->read_ev[k], 0));
+  launch_quantize_rgba8(result_image(ctx), ctx->rgba8_async_d[k], n, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->quant_ev, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->quant_ev, 0));
+  CU(cudaMemcpy2DAsync(dst, pitch, ctx->rgba8_async_d[k], row, row, ctx->img_h, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CU(cudaEventRecord(ctx->read_ev[k], ctx->copy_stream));
+  ctx->read_slot = k ^ 1;
+  return TVK_OK;
+}
+
+int tvk_read_wait(tvk_ctx* ctx, int pending_allowed) {
+  if (!ctx) return TVK_ERR_INVALID;
+  cudaSetDevice(ctx->cfg.device);
+  if (pending_allowed >= 1) {   // everything but the newest read: the slot that will be reused next
+    if (ctx->read_ev[ctx->read_slot]) CU(cudaEventSynchronize(ctx->read_ev[ctx->read_slot]));
+  } else {
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+  }
+  return TVK_OK;
+}
+
+int tvk_host_alloc(tvk_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out || !bytes) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  cudaSetDevice(ctx->cfg.device);
+  CU(cudaMallocHost(out, bytes));
+  return TVK_OK;
+}
+
+int tvk_host_free(tvk_ctx* ctx, void* p) {
+  if (!ctx) return TVK_ERR_INVALID;
+  if (p) CU(cudaFreeHost(p));
+  return TVK_OK;
+}
+
 int tvk_read_rgba32f(tvk_ctx* ctx, float* dst, size_t pitch) {
   if (!ctx || !dst || !ctx->img_w) return fail(ctx, TVK_ERR_INVALID, "nothing rendered");
   cudaSetDevice(ctx->cfg.device);
@@ -1516,6 +1570,7 @@ int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
     st->converged = 1;
     st->bricks_paged = paged;
     if (ctx->counters_on) st->samples = ctx->counters_h[0];
+    st->bricks_touched = n_needed;   // listed, non-empty bricks (each is raycast once)
     cudaEventElapsedTime(&st->ms_upload_bricks, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&st->ms_raycast, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[2]);

@@ -142,6 +142,9 @@ struct tvk_ctx {
   //      6 composed iso image, 7 unused
   int cur = 0;
   uchar4* rgba8_d = nullptr;
+  uchar4* rgba8_async_d[2] = {nullptr, nullptr};   // double-buffered unorm8 images of the async read-back
+  cudaEvent_t read_ev[2] = {nullptr, nullptr}; cudaEvent_t quant_ev = nullptr;
+  int read_slot = 0;
   void* read_h = nullptr; size_t read_cap = 0;   // pinned read-back staging
   unsigned long long* counters_d = nullptr;
   unsigned long long* counters_h = nullptr;

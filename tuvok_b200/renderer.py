@@ -82,6 +82,10 @@ class CudaGridLeaper:
 
     def Cleanup(self):
         if getattr(self, "_h", None):
+            for k in getattr(self, "_keep", []):
+                if isinstance(k, tuple) and k[0] == "pinned":
+                    self._lib.tvk_host_free(self._h, C.c_void_p(k[1]))
+            self._keep = []
             self._lib.tvk_destroy(self._h)
             self._h = None
 
@@ -386,6 +390,23 @@ class CudaGridLeaper:
             out = np.zeros((h, w, 4), np.uint8)
         self._ck(self._lib.tvk_read_rgba8(self._h, _ptr(out), 0))
         return out
+
+    def host_alloc(self, shape, dtype=np.uint8):
+        """ndarray over page-locked host memory owned by the library (freed with the renderer)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._ck(self._lib.tvk_host_alloc(self._h, n, C.byref(p)))
+        self._keep.append(("pinned", p.value))
+        buf = (C.c_uint8 * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def ReadRGBA8Async(self, out_pinned):
+        """Queue the read-back of the last frame into page-locked memory (PBO-style); overlaps the next Paint()."""
+        self._ck(self._lib.tvk_read_rgba8_async(self._h, _ptr(out_pinned), 0))
+
+    def WaitRead(self, pending_allowed=0):
+        """Block until at most `pending_allowed` queued read-backs are still in flight."""
+        self._ck(self._lib.tvk_read_wait(self._h, int(pending_allowed)))
 
     def ReadRGBA32F(self):
         w, h = self.params.width, self.params.height
