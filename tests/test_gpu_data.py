@@ -184,3 +184,67 @@ def test_full_size_c2_conservation(torch_cuda):
     assert got == want
     assert vol_sum > 0
     r.Cleanup()
+
+
+@pytest.mark.parametrize("mode", [tb.RM_1DTRANS, tb.RM_ISOSURFACE])
+def test_paging_and_visibility_match_reference_glvolumepool(tmp_path, mode):
+    """libtvkcuda.so against the UNMODIFIED reference GLVolumePool.cpp (oracle/_ref/ref_pool, built from
+    /root/reference over a recording null-GL; the binary travels to the GPU box): page table == the R32UI
+    metadata texture the reference uploaded, slot table in the reference's sorted order, visibility counts,
+    and the voxels of every slot == the reference's atlas region."""
+    import pool_ref
+    if not pool_ref.have_ref_pool():
+        pytest.skip("oracle/_ref/ref_pool not built")
+    s = Scene(kind=synth.V_NOISE, size=(100, 90, 70), dtype=orc.U16, brick=20, overlap=2, mode=mode, isovalue=21000,
+              pool_size=(100, 60, 40))
+    o = s.octree
+    keys = [k for k in o.iter_bricks(max_lod=s.pool_lod_count() - 1)]
+    rng = np.random.default_rng(11 + mode)
+    vname = {tb.RM_1DTRANS: "vis1d", tb.RM_ISOSURFACE: "visiso"}[mode]
+    nargs = {tb.RM_1DTRANS: 2, tb.RM_ISOSURFACE: 1}[mode]
+
+    r = s.make_renderer("device")          # RegisterDataset: pool created, first brick uploaded
+    ops = [("first",), ("dump",)]
+    got = [("state", r.page_table(), r.slots())]
+    counts = r.RecomputeBrickVisibility(force=True)
+    ops += [(vname,) + tuple(s.visibility_args()[:nargs]), ("dump",)]
+    got.append(("counts", counts, r.page_table(), r.slots()))
+    for rnd in range(7):
+        pick = rng.choice(len(keys), size=int(rng.integers(2, 12)), replace=False)
+        ids = np.array([keys[i] for i in pick], np.uint32)
+        n, slots = r.UploadBricks(ids)
+        ops += [("upload", ids), ("dump",)]
+        got.append(("paged", n, r.page_table(), r.slots()))
+        if rnd == 3:
+            s.tf1d.SetStdFunction(0.7, 0.1)
+            s.isovalue = 43000
+            r.Set1DTrans(s.tf1d)
+            r.SetIsoValue(s.isovalue)
+            counts = r.RecomputeBrickVisibility(force=False)
+            ops += [(vname,) + tuple(s.visibility_args()[:nargs]), ("dump",)]
+            got.append(("counts", counts, r.page_table(), r.slots()))
+    ref = pool_ref.run(tmp_path, o, s.size, 20, 2, orc.U16, s.pool_size(), ops)
+    ev = iter(ref.events)
+    for step, g in enumerate(got):
+        e = next(ev)
+        if g[0] == "counts":
+            assert e == ("counts", g[1]), "step %d" % step
+        elif g[0] == "paged":
+            assert e == ("paged", g[1]), "step %d" % step
+        kind, d = next(ev)
+        table, (ids_, times_, pos_) = g[-2], g[-1]
+        assert np.array_equal(table, d["meta"]), "step %d: page table vs reference metadata texture" % step
+        assert np.array_equal(ids_, d["slot_brick"]) and np.array_equal(times_, d["slot_time"]), "step %d" % step
+        assert np.array_equal(pos_, d["slot_pos"]), "step %d" % step
+    atlas = ref.dumps()[-1]["atlas"]
+    cap = tuple(r.info().pool_capacity)
+    geo = s.oracle_pool()[0]
+    for bid, p in zip(ids_, pos_):
+        if bid < 0:
+            continue
+        x, y, z = (int(v) for v in p)
+        slot = x + y * cap[0] + z * cap[0] * cap[1]
+        bx, by, bz = o.brick_size(*geo.vector_id(int(bid)))     # beyond the brick's own extent a slot keeps stale texels
+        want = atlas[z * 20:z * 20 + bz, y * 20:y * 20 + by, x * 20:x * 20 + bx]
+        assert np.array_equal(r.pool_slot(slot, orc.U16, s.brick)[:bz, :by, :bx], want), "slot %d" % slot
+    r.Cleanup()
