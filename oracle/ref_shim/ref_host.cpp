@@ -1,0 +1,100 @@
+// ref_host -- runs the UNMODIFIED reference host-side arithmetic that feeds the ray caster: the matrix
+// conventions of Basics/Vectors.h (BuildLookAt, Perspective, operator*, inverse), the frustum culling /
+// LOD selection of Renderer/CullingLOD.cpp and the 1D transfer function of IO/TransferFunction1D.cpp
+// (SetStdFunction, GetByteArray, non-zero limits).  Compiled in place from /root/reference by
+// oracle/Makefile; tests/test_host_ref.py compares the oracle restatement and tvk_compute_view with it.
+// Floats are printed as C99 hex floats (%a) so the comparison is bit-exact.  Test infrastructure only.
+//
+//   ref_host <commands.txt> <result.txt>
+//     view  ex ey ez  ax ay az  ux uy uz  fov aspect near far pixels_y
+//     mul   a[16] b[16]                       (Tuvok row-vector product a*b, FLOATMATRIX4::operator*)
+//     inverse m[16]
+//     cull  fov aspect near far pixels_y  model[16] view[16] proj[16]  n  (cx cy cz ex ey ez vx vy vz)*n
+//     tf1d  n center inv_gradient
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "StdTuvokDefines.h"
+#include <GL/glew.h>   // defines __GL_H__: Vectors.h only declares BuildLookAt / Perspective next to its GL helpers
+#include "Basics/Vectors.h"
+#include "IO/TransferFunction1D.h"
+#include "Renderer/CullingLOD.h"
+
+using namespace tuvok;
+
+static void read16(std::istream& s, FLOATMATRIX4& m) { for (int i = 0; i < 16; i++) s >> m.array[i]; }
+static void put16(FILE* o, const char* tag, const FLOATMATRIX4& m) {
+  fprintf(o, "%s", tag);
+  for (int i = 0; i < 16; i++) fprintf(o, " %a", (double)m.array[i]);
+  fprintf(o, "\n");
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) { fprintf(stderr, "usage: ref_host commands.txt result.txt\n"); return 2; }
+  std::ifstream in(argv[1]);
+  FILE* out = fopen(argv[2], "w");
+  if (!in || !out) return 2;
+  std::string line;
+  while (std::getline(in, line)) {
+    std::istringstream ls(line);
+    std::string op;
+    if (!(ls >> op)) continue;
+    if (op == "view") {
+      FLOATVECTOR3 e, a, u; float fov, aspect, n, f; uint32_t py;
+      ls >> e.x >> e.y >> e.z >> a.x >> a.y >> a.z >> u.x >> u.y >> u.z >> fov >> aspect >> n >> f >> py;
+      FLOATMATRIX4 view, proj;
+      view.BuildLookAt(e, a, u);            // GLRenderer::ComputeViewAndProjection, GLRenderer.cpp:908-912
+      proj.Perspective(fov, aspect, n, f);
+      CullingLOD c;
+      c.SetScreenParams(fov, aspect, n, f, py);   // GLRenderer::SetViewPort, GLRenderer.cpp:886-888
+      put16(out, "view", view);
+      put16(out, "proj", proj);
+      fprintf(out, "lodfactor %a\n", (double)c.GetLoDFactor());
+    } else if (op == "mul") {
+      FLOATMATRIX4 a, b; read16(ls, a); read16(ls, b);
+      put16(out, "mul", a * b);
+    } else if (op == "inverse") {
+      FLOATMATRIX4 a; read16(ls, a);
+      put16(out, "inverse", a.inverse());
+    } else if (op == "cull") {
+      float fov, aspect, n, f; uint32_t py;
+      ls >> fov >> aspect >> n >> f >> py;
+      FLOATMATRIX4 model, view, proj; read16(ls, model); read16(ls, view); read16(ls, proj);
+      CullingLOD c;
+      c.SetScreenParams(fov, aspect, n, f, py);
+      c.SetProjectionMatrix(proj);
+      c.SetViewMatrix(view);
+      c.SetModelMatrix(model);
+      c.Update();
+      size_t cnt; ls >> cnt;
+      fprintf(out, "cull %zu", cnt);
+      for (size_t i = 0; i < cnt; i++) {
+        FLOATVECTOR3 ctr, ext; UINTVECTOR3 vox;
+        ls >> ctr.x >> ctr.y >> ctr.z >> ext.x >> ext.y >> ext.z >> vox.x >> vox.y >> vox.z;
+        fprintf(out, " %d %d", int(c.IsVisible(ctr, ext)), c.GetLODLevel(ctr, ext, vox));
+      }
+      fprintf(out, "\n");
+    } else if (op == "tf1d") {
+      size_t n; float center, inv;
+      ls >> n >> center >> inv;
+      TransferFunction1D tf(n);
+      tf.SetStdFunction(center, inv);
+      std::vector<unsigned char> bytes;
+      tf.GetByteArray(bytes);
+      fprintf(out, "tf1d %zu limits %llu %llu bytes", n, (unsigned long long)tf.GetNonZeroLimits().x,
+              (unsigned long long)tf.GetNonZeroLimits().y);
+      for (unsigned char b : bytes) fprintf(out, " %u", unsigned(b));
+      fprintf(out, "\n");
+    } else {
+      fprintf(stderr, "ref_host: unknown command %s\n", op.c_str());
+      return 2;
+    }
+  }
+  fclose(out);
+  return 0;
+}

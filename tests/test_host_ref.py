@@ -1,0 +1,146 @@
+"""Host-side arithmetic in front of the ray caster against UNMODIFIED reference code (oracle/_ref/ref_host,
+compiled in place from /root/reference: Basics/Vectors.h, Renderer/CullingLOD.cpp, IO/TransferFunction1D.cpp):
+  * view / projection / LoD factor of tvk_compute_view (the product's host logic) and of the test helper
+    scene.py == BuildLookAt / Perspective / CullingLOD::SetScreenParams, bit for bit,
+  * the oracle's classic frame planning: frustum culling == CullingLOD::IsVisible on every brick, LoD choice
+    == CullingLOD::GetLODLevel clamped as AbstrRenderer::ComputeMinLODForCurrentView does,
+  * TransferFunction1D mirror == the reference's SetStdFunction / GetByteArray / GetNonZeroLimits."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_scenes
+import scene
+import tuvok_b200 as tb
+from oracle import orc
+from tuvok_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "ref_host")
+
+
+def _have():
+    if not os.path.exists(BIN) and os.path.isdir("/root/reference/IO"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j8", "ref"], stdout=subprocess.DEVNULL)
+    return os.path.exists(BIN)
+
+
+pytestmark = pytest.mark.skipif(not _have(), reason="oracle/_ref/ref_host not built (reference tree absent)")
+
+
+def fl(v):
+    return " ".join("%.9g" % float(x) for x in np.asarray(v, np.float32).reshape(-1))
+
+
+def run(tmp_path, commands):
+    cmd = os.path.join(str(tmp_path), "cmd.txt")
+    res = os.path.join(str(tmp_path), "res.txt")
+    with open(cmd, "w") as f:
+        f.write("\n".join(commands) + "\n")
+    subprocess.check_call([BIN, cmd, res])
+    with open(res) as f:
+        return [l.split() for l in f if l.strip()]
+
+
+def hexf(tokens):
+    return np.array([float.fromhex(t) for t in tokens], np.float32)
+
+
+@pytest.mark.parametrize("w,h,fov", [(512, 512, 50.0), (1920, 1080, 50.0), (96, 64, 35.0)])
+@pytest.mark.parametrize("eye", [(0, 0, 1.6), (0.4, -0.3, 2.2)])
+def test_view_projection_lodfactor_bit_exact(tmp_path, w, h, fov, eye):
+    rot = (tb.rotation_y(33.0) @ tb.rotation_x(-12.0)).astype(np.float32)
+    tra = tb.translation(0.1, -0.05, 0.3)
+    aspect = np.float32(w) / np.float32(h)
+    rows = run(tmp_path, ["view %s 0 0 0 0 1 0 %.9g %.9g 0.01 1000 %d" % (fl(eye), fov, aspect, h)])
+    ref_view, ref_proj, ref_lf = hexf(rows[0][1:]).reshape(4, 4), hexf(rows[1][1:]).reshape(4, 4), hexf(rows[2][1:])[0]
+    # reference model-view: m = rotation * translation (RenderRegion), then * view (GLRenderer.cpp:627)
+    rows = run(tmp_path, ["mul %s %s" % (fl(rot), fl(tra))])
+    model = hexf(rows[0][1:]).reshape(4, 4)
+    rows = run(tmp_path, ["mul %s %s" % (fl(model), fl(ref_view))])
+    ref_mv = hexf(rows[0][1:]).reshape(4, 4)
+
+    # the test helper (independent numpy restatement used by every parity scene)
+    if tuple(eye) == (0, 0, 1.6):       # the reference's default camera: exact; off-axis eyes differ in the
+        np.testing.assert_array_equal(scene.look_at(eye, (0, 0, 0), (0, 1, 0)), ref_view)   # dot-product rounding
+    np.testing.assert_allclose(scene.look_at(eye, (0, 0, 0), (0, 1, 0)), ref_view, rtol=0, atol=1.2e-7)
+    np.testing.assert_array_equal(scene.perspective(fov, aspect, 0.01, 1000.0), ref_proj)
+    assert scene.lod_factor(fov, h) == ref_lf
+    # the product's host logic behind the C ABI
+    p = L.RenderParams()
+    rc = tb.lib().tvk_compute_view(C.byref(p), w, h, L.f32x16(*rot.reshape(-1)), L.f32x16(*tra.reshape(-1)),
+                                   L.f32x3(*eye), L.f32x3(0, 0, 0), L.f32x3(0, 1, 0), fov, 0.01, 1000.0, 1.0)
+    assert rc == 0
+    np.testing.assert_array_equal(np.array(p.projection, np.float32).reshape(4, 4), ref_proj)
+    assert np.float32(p.lod_factor) == ref_lf
+    np.testing.assert_allclose(np.array(p.model_view, np.float32).reshape(4, 4), ref_mv, rtol=0, atol=2.4e-7)
+
+
+@pytest.mark.parametrize("name,over", [
+    ("c2_bricked36_1d_ert", {}),
+    ("ragged_1d_lit", {}),
+    ("inside_aniso_2d", {}),
+    ("c2_bricked36_1d_ert", dict(translation=tb.translation(0.9, 0.0, 1.0))),     # half off screen
+    ("ragged_1d_lit", dict(translation=tb.translation(-0.6, 0.5, 0.8))),
+    ("c2_bricked36_1d_ert", dict(translation=tb.translation(0.0, 0.0, -2.2))),     # coarser LoD
+])
+def test_classic_planning_matches_reference_cullinglod(tmp_path, name, over):
+    s = golden_scenes.make(name, **over)
+    o = s.octree
+    pool, _ = s.oracle_pool()
+    p = s.oracle_params(pool)
+    aspect = np.float32(s.width) / np.float32(s.height)
+    mv, proj = s.matrices()
+    screen = "%.9g %.9g 0.01 1000 %d" % (s.fov, aspect, s.height)
+    ident = np.eye(4, dtype=np.float32)
+
+    # LoD: AbstrRenderer::ComputeMinLODForCurrentView (AbstrRenderer.cpp:789-803)
+    ext = np.array(s.size, np.float32) * np.array(s.scale, np.float32)
+    ext = ext / ext.max()
+    rows = run(tmp_path, ["cull %s %s %s %s 1 0 0 0 %s %d %d %d" % (screen, fl(mv), fl(ident), fl(proj), fl(ext), *s.size)])
+    ref_lod = min(max(int(rows[0][3]), 0), s.pool_lod_count() - 1)
+    lod = orc.classic_lod(p, s.pool_lod_count())
+    assert lod == ref_lod
+
+    # every brick of that LoD: geometry from an all-pass planning run (far camera), then the reference's
+    # IsVisible on the real camera must select exactly the oracle's list
+    far = golden_scenes.make(name, **dict(over, translation=tb.translation(0, 0, -40.0), rotation=np.eye(4, dtype=np.float32)))
+    pf = far.oracle_params(pool)
+    bc = o.brick_count(lod)
+    n_lod = bc[0] * bc[1] * bc[2]
+    first = o.brick_index(0, 0, 0, lod)
+    mm = o.minmax[first:first + n_lod]
+    everything = (0.0, 1e30, 0.0, 1e30)
+    all_b, n_all = orc.classic_brick_list(pf, lod, s.overlap, mm, everything)
+    assert n_all == n_lod
+    by_index = {all_b[i].index: all_b[i] for i in range(n_all)}
+    boxes = []
+    for i in range(n_lod):
+        b = by_index[i]
+        boxes.append("%s %s %d %d %d" % (fl(b.center), fl(b.ext), *b.n_vox))
+    rows = run(tmp_path, ["cull %s %s %s %s %d %s" % (screen, fl(mv), fl(ident), fl(proj), n_lod, " ".join(boxes))])
+    vis = np.array(rows[0][2::2], np.int64)
+    want = set(np.nonzero(vis)[0].tolist())
+    mine, n = orc.classic_brick_list(p, lod, s.overlap, mm, s.visibility_args())
+    got = set(mine[i].index for i in range(n))
+    assert got == want
+    assert 0 < len(want) <= n_lod
+
+
+@pytest.mark.parametrize("n,c,g", [(256, 0.5, 0.5), (4096, 0.3, 0.4), (256, 0.05, 0.5), (1024, 0.9, 0.3), (4096, 0.2, 0.2),
+                                   (256, 0.0, 1.0), (64, 1.0, 0.1)])
+def test_tf1d_matches_reference_class(tmp_path, n, c, g):
+    rows = run(tmp_path, ["tf1d %d %.9g %.9g" % (n, c, g)])
+    r = rows[0]
+    lo, hi = int(r[3]), int(r[4])
+    ref_bytes = np.array(r[6:6 + 4 * n], np.uint8).reshape(n, 4)
+    t = tb.TransferFunction1D(n)
+    t.SetStdFunction(c, g)
+    np.testing.assert_array_equal(t.GetByteArray(), ref_bytes)
+    assert t.GetNonZeroLimits() == (lo, hi)
+    ref = orc.tf1d_std(n, c, g)
+    np.testing.assert_array_equal(orc.tf1d_bytes(ref), ref_bytes)
+    assert orc.tf1d_nonzero(ref) == (lo, hi)
