@@ -111,6 +111,7 @@ typedef struct {
   uint64_t bricks_touched;       /* distinct non-empty bricks sampled this subframe (if counting enabled) */
   uint64_t alive_lane_iters;     /* diagnostics: sum over lanes of loop turns with a live ray */
   uint64_t warp_iters;           /* diagnostics: loop turns summed over warps (x32 = lane slots) */
+  uint64_t max_lane_iters;       /* diagnostics: loop turns of the longest ray = the kernel's critical path */
   float ms_raycast;              /* PERF_RAYCAST (CUDA events) */
   float ms_read_htable;          /* PERF_READ_HTABLE + PERF_CONDENSE_HTABLE */
   float ms_upload_bricks;        /* PERF_UPLOAD_BRICKS */

@@ -19,7 +19,7 @@ del raw; torch.cuda.empty_cache()
 t1, t2 = workloads.transfer_functions(w); r.Set1DTrans(t1); r.Set2DTrans(t2); r.SetRendermode(w["mode"]); r.SetUseLighting(True)
 r.Resize(w["width"], w["height"]); r.CreateVolumePool()
 fl = [np.float32(v) / np.float32(inner) for v in w["size"]]; fl = [f - f * np.finfo(np.float32).eps for f in fl]
-sl = sortlast.SortLastRenderer(r, rank, world, finest, fl, (1.0, 1.0, 1.0), view_dependent=bool(vd))
+sl = sortlast.SortLastRenderer(r, rank, world, finest, fl, (1.0, 1.0, 1.0), view_dependent=bool(vd), policy=os.environ.get("SPLIT", "screen"))
 rows = []
 for i in range(36):
     r.SetRotation(workloads.orbit_rotation(i)); sl.update_partition(); r.PaintUntilConverged()

@@ -40,7 +40,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(L.RenderParams) == 272
     assert C.sizeof(L.VolumeDesc) == 80
     assert C.sizeof(L.Info) == 8 + 8 + 16 * 12 * 2 + 64 + 36 + 4 + 8
-    assert C.sizeof(L.FrameStats) == 4 * 3 + 4 + 8 * 6 + 16
+    assert C.sizeof(L.FrameStats) == 4 * 3 + 4 + 8 * 7 + 16
 
 
 def test_sass_is_sm100a_only():

@@ -49,6 +49,7 @@ class FrameStats(C.Structure):
     _fields_ = [("converged", C.c_int32), ("missing_reported", C.c_uint32), ("bricks_paged", C.c_uint32),
                 ("samples", C.c_uint64), ("rays", C.c_uint64), ("brick_visits", C.c_uint64),
                 ("bricks_touched", C.c_uint64), ("alive_lane_iters", C.c_uint64), ("warp_iters", C.c_uint64),
+                ("max_lane_iters", C.c_uint64),
                 ("ms_raycast", C.c_float), ("ms_read_htable", C.c_float), ("ms_upload_bricks", C.c_float),
                 ("ms_total", C.c_float)]
 

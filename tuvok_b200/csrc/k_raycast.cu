@@ -382,6 +382,15 @@ constexpr int kFetchLanes = TVK_FETCH_LANES;
 #endif
 constexpr int kWX = TVK_WX, kWY = TVK_WY, kThreads = 32 * TVK_WX * TVK_WY;
 constexpr int kIlp = TVK_ILP;   // samples per lane per loop turn (1 or 2)
+#ifndef TVK_CENTRE_OUT
+#define TVK_CENTRE_OUT 1
+#endif
+constexpr bool kCentreOut = TVK_CENTRE_OUT != 0;
+// k-th element of the sequence c, c-1, c+1, c-2, c+2, ... (c = n/2): a bijection of [0, n)
+__device__ __forceinline__ uint32_t centre_out(uint32_t k, uint32_t n) {
+  const uint32_t c = n >> 1, d = (k + 1) >> 1;
+  return (k & 1u) ? c - d : c + d;
+}
 
 // State of the brick chain (page-table walk).  None of it is needed while a lane samples, so between two chain
 // phases it is PARKED in shared memory (TVK_PARK) instead of occupying ~37 registers of every thread for the
@@ -436,8 +445,13 @@ __device__ __forceinline__ void unpark(ChainSt& c, float (*m)[kThreads], int tid
 template <typename T, int MODE, bool LIT, bool FAST, int BS, bool COUNT>
 __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) raycast_kernel(const __grid_constant__ RayConsts P) {
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  const uint32_t px = blockIdx.x * (8 * kWX) + (wid % kWX) * 8 + (lane & 7);
-  const uint32_t py = blockIdx.y * (4 * kWY) + (wid / kWX) * 4 + (lane >> 3);
+  // CTAs are dispatched in blockIdx order (x fastest).  The rays through the middle of the volume are the
+  // longest: tile rows / columns are mapped centre-out so those start first (measured: +1 % on C3, the launch
+  // is bound by per-warp latency, not by its tail; kept because it costs nothing).
+  const uint32_t tx = kCentreOut ? centre_out(blockIdx.x, gridDim.x) : blockIdx.x;
+  const uint32_t ty = kCentreOut ? centre_out(blockIdx.y, gridDim.y) : blockIdx.y;
+  const uint32_t px = tx * (8 * kWX) + (wid % kWX) * 8 + (lane & 7);
+  const uint32_t py = ty * (4 * kWY) + (wid / kWX) * 4 + (lane >> 3);
   if (px >= P.width || py >= P.height) return;
   const size_t pix = (size_t)py * P.width + px;
   constexpr bool ISO = MODE == 2;
@@ -756,6 +770,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
   if (COUNT) {
     atomicAdd(P.counters + 0, n_samples); atomicAdd(P.counters + 1, 1ull); atomicAdd(P.counters + 2, n_bricks);
     atomicAdd(P.counters + 3, n_alive_iters); atomicAdd(P.counters + 4, n_warp_iters);
+    atomicMax(P.counters + 5, n_alive_iters);
   }
 }
 

@@ -1,0 +1,58 @@
+// octree_file.h -- reader of the ExtendedOctree on-disk layout (the payload of a UVF TOC block) for the
+// streaming path: header + table of contents are parsed once, bricks are pread() straight into the
+// library's pinned staging memory (no std::vector hop of Dataset::GetBrick) and decoded there when the
+// TOC marks them compressed.  Replaces (reference file:line):
+//   ExtendedOctree::Open            IO/UVF/ExtendedOctree/ExtendedOctree.cpp:87-165
+//   ExtendedOctree::ComputeMetadata IO/UVF/ExtendedOctree/ExtendedOctree.cpp:188-243
+//   ExtendedOctree::GetBrickData    IO/UVF/ExtendedOctree/ExtendedOctree.cpp:313-360
+//   UVFDataset::GetBrick (TOC path) IO/uvfDataset.cpp:1690-1712
+//   zDecompress / lz4Decompress     IO/UVF/ExtendedOctree/ZlibCompression.cpp, Lz4Compression.cpp
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace tvk {
+
+// ExtendedOctree.h:65-73
+enum OctreeCodec : uint32_t { OC_NONE = 0, OC_ZLIB = 1, OC_LZMA = 2, OC_LZ4 = 3, OC_BZLIB = 4, OC_LZHAM = 5 };
+
+struct OctreeToc {
+  uint64_t offset, length, valid_length;
+  uint32_t codec, atlas_w, atlas_h;
+};
+
+struct OctreeFile {
+  int fd = -1;
+  uint64_t base = 0;                // offset of the octree header inside the file (the TOC block payload)
+  uint32_t component_type = 0;      // ExtendedOctree::COMPONENT_TYPE
+  uint64_t component_count = 0;
+  bool precomputed_normals = false;
+  uint64_t vol[3] = {0, 0, 0};
+  double aspect[3] = {1, 1, 1};
+  uint64_t brick[3] = {0, 0, 0};    // max brick size incl. ghost
+  uint32_t overlap = 0, version = 0, compression_level = 0;
+  uint64_t total_size = 0;
+  std::vector<uint64_t> lod_size;   // 3 per LoD
+  std::vector<uint64_t> lod_layout; // 3 per LoD
+  std::vector<uint64_t> lod_first;  // first TOC index of each LoD
+  std::vector<OctreeToc> toc;
+  std::string error;
+
+  ~OctreeFile();
+  bool open(const char* path, uint64_t offset, uint64_t uvf_file_version);
+  void close();
+  uint32_t lod_count() const { return (uint32_t)lod_first.size(); }
+  size_t element_bytes() const;
+  uint64_t brick_index(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const;
+  void brick_size(uint32_t x, uint32_t y, uint32_t z, uint32_t lod, uint32_t out[3]) const;
+  // voxels of one brick (x fastest, own size incl. ghost) into dst; thread-safe (pread + private scratch).
+  // Returns false and sets `err` on IO / codec errors.
+  bool read_brick(uint64_t index, size_t uncompressed_bytes, void* dst, size_t cap, std::string* err) const;
+};
+
+// LZ4 block format (the reference calls LZ4_decompress_fast: the decoder knows only the output size)
+bool lz4_block_decode(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len);
+
+}  // namespace tvk

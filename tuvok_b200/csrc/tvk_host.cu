@@ -1133,6 +1133,7 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
     if (ctx->counters_on) {
       st->samples = ctx->counters_h[0]; st->rays = ctx->counters_h[1]; st->brick_visits = ctx->counters_h[2];
       st->alive_lane_iters = ctx->counters_h[3]; st->warp_iters = ctx->counters_h[4];
+      st->max_lane_iters = ctx->counters_h[5];
       uint64_t t = 0;
       for (uint32_t w : ctx->visited_h) t += (uint64_t)__builtin_popcount(w);
       st->bricks_touched = t;

@@ -18,13 +18,26 @@ import math
 import numpy as np
 
 
-def split_axes(view_dir, n_ranks):
-    """Axis to bisect at every level for a camera looking along `view_dir` (volume space): the axes most
-    PERPENDICULAR to the view first (k = 3: 4 slabs along the best axis x 2 along the second best), so the blocks
-    lie side by side on screen instead of behind each other.  A ray then crosses one or two blocks, early ray
-    termination keeps working as on one GPU, and no rank renders samples that a front rank already made invisible."""
+def split_axes(view_dir, n_ranks, policy="screen"):
+    """Axis to bisect at every level for a camera looking along `view_dir` (volume space).
+
+    policy "screen": the axes most PERPENDICULAR to the view first (k = 3: 4 slabs along the best axis x 2 along
+    the second best), so the blocks lie side by side on screen.  A ray crosses one or two blocks, early ray
+    termination works as on one GPU and no rank renders samples a front rank already made invisible -- but every
+    rank still traverses full-length rays, and the launch is bound by the latency of its longest rays
+    (DESIGN.md section 5), so this does not scale.
+    policy "depth": every cut along the axis most PARALLEL to the view: the blocks are slabs behind each other, each
+    rank sees all pixels but only 1/G of every ray, which divides the critical path by G.  Costs the samples that a
+    single GPU would have skipped behind an early-terminated front slab.
+    policy "octant": longest axis of the block at every level (view independent)."""
     k = int(round(math.log2(n_ranks)))
+    if policy == "octant":
+        return None
     order = sorted(range(3), key=lambda i: (abs(float(view_dir[i])), i))
+    if policy == "depth":
+        return [order[2]] * k
+    if policy == "depth2":      # two cuts in depth, the third across the screen
+        return [order[2], order[2], order[0]][:k]
     return [order[0], order[1], order[0]][:k]
 
 
@@ -143,18 +156,25 @@ def binary_swap(image, plan, dist, over, recv_buf):
 class SortLastRenderer:
     """One rank of the sort-last renderer: a CudaGridLeaper restricted to its block + the compositor."""
 
-    def __init__(self, renderer, rank, n_ranks, finest_layout, float_layout, extent, view_dependent=True):
+    def __init__(self, renderer, rank, n_ranks, finest_layout, float_layout, extent, view_dependent=True,
+                 policy="screen"):
         import torch
         import torch.distributed as dist
         self.r, self.rank, self.n = renderer, rank, n_ranks
         self.torch, self.dist = torch, dist
         self.finest, self.flayout, self.extent = tuple(finest_layout), tuple(float_layout), tuple(extent)
-        self.view_dependent = view_dependent
+        self.view_dependent = view_dependent and policy != "octant"
+        self.policy = policy
         self._axes = None
         self._partition(None)
         self._img = None
         self._recv = None
         self._gather = None
+        self._rb = None
+        # one stream for the traversal, the blend kernels and the NCCL exchange: ordering comes from the stream,
+        # not from host synchronisation
+        self.stream = torch.cuda.current_stream()
+        renderer.set_stream(self.stream.cuda_stream)
 
     def _partition(self, axes):
         """(Re)cut the brick grid; bricks of the new block are paged in by the renderer's normal miss path."""
@@ -170,7 +190,7 @@ class SortLastRenderer:
         r._push_params()
         eye = eye_in_volume(np.array(list(r.params.model_view)), self.extent)
         if self.view_dependent and self.n > 1:
-            axes = split_axes((0.5 - eye) * np.asarray(self.extent, np.float64), self.n)
+            axes = split_axes((0.5 - eye) * np.asarray(self.extent, np.float64), self.n, self.policy)
             if axes != self._axes:
                 self._partition(axes)
         return eye
@@ -201,7 +221,6 @@ class SortLastRenderer:
         def over(front, back, out):
             r.composite_over(front.data_ptr(), back.data_ptr(), out.data_ptr(), front.shape[0])
 
-        r.synchronize()   # the image was rendered on the library's stream; NCCL runs on torch's
         lo, hi = binary_swap(self._img, plan, self.dist, over, self._recv)
         return lo, hi, self._img, st
 
@@ -211,7 +230,6 @@ class SortLastRenderer:
         n_pixels = image.shape[0]
         if self.n == 1:
             return image
-        self.r.synchronize()
         ranges = final_ranges(self.n, n_pixels)
         if self.rank == dst_rank:
             if self._gather is None or self._gather.shape[0] != n_pixels:
@@ -225,3 +243,31 @@ class SortLastRenderer:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         return full
+
+    def read_rgba8_async(self, full):
+        """PBO-style read-back of the gathered frame on the destination rank: float -> unorm8 on the device, then an
+        asynchronous copy into one of two page-locked host images on a side stream, so the copy overlaps the next
+        frame's traversal.  Returns (host_image_uint8[n_pixels, 4], event); the image is valid once the event has
+        completed (event.synchronize()).  At most two reads are in flight: a buffer is reused two calls later."""
+        torch = self.torch
+        n_pixels = full.shape[0]
+        if self._rb is None or self._rb["n"] != n_pixels:
+            self._rb = dict(n=n_pixels, i=0, copy=torch.cuda.Stream(),
+                            dev=[torch.empty((n_pixels, 4), dtype=torch.uint8, device=full.device) for _ in range(2)],
+                            host=[torch.empty((n_pixels, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)],
+                            done=[None, None])
+        rb = self._rb
+        k = rb["i"] % 2
+        rb["i"] += 1
+        if rb["done"][k] is not None:
+            rb["done"][k].synchronize()       # the copy that last used this buffer pair has landed
+        self.r.quantize_rgba8(full.data_ptr(), rb["dev"][k].data_ptr(), n_pixels)
+        ready = torch.cuda.Event()
+        ready.record(self.stream)
+        rb["copy"].wait_event(ready)
+        with torch.cuda.stream(rb["copy"]):
+            rb["host"][k].copy_(rb["dev"][k], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(rb["copy"])
+        rb["done"][k] = done
+        return rb["host"][k].numpy(), done
