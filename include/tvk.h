@@ -162,6 +162,35 @@ int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uin
  * Writes size[0]*size[1]*size[2] voxels to the DEVICE pointer dst. */
 int tvk_synth_volume(tvk_ctx* ctx, void* dst_device, int kind, const uint32_t size[3], int dtype,
                      uint32_t seed);
+/* ExtendedOctree file source: the payload of a UVF TOC block -- or the file
+ * ExtendedOctreeConverter::Convert writes -- becomes the brick source of the streaming path.  Replaces
+ * ExtendedOctree::Open / GetBrickData (IO/UVF/ExtendedOctree/ExtendedOctree.cpp:87-165,313-360) and
+ * UVFDataset::GetBrick (IO/uvfDataset.cpp:1690-1712): header + table of contents are parsed once, bricks are
+ * read with parallel pread() straight into the library's pinned staging memory (zlib / lz4 bricks are decoded
+ * there; LZMA / bzip2 are refused) and copied to the pool on the side stream.  `offset` = byte offset of the
+ * octree header in the file, `uvf_file_version` as UVF::ms_ulReaderVersion (>= 5: versioned octree header).
+ * scale NULL: the octree's volume aspect.  minmax = MaxMinDataBlock contents (TOC order) or NULL: the table is then
+ * computed on the device in one streaming pass over all bricks.  info may be NULL. */
+typedef struct {
+  uint32_t domain_size[3];
+  double   aspect[3];
+  uint32_t max_brick_size[3];
+  uint32_t overlap;
+  int32_t  dtype;
+  uint32_t version;              /* octree version (0: UVF <= 4) */
+  uint32_t lod_count;
+  uint64_t brick_count;          /* all LoDs */
+  uint64_t payload_bytes;        /* stored (compressed) bytes of all bricks */
+  uint64_t bricks_by_codec[6];   /* ExtendedOctree COMPRESSION_TYPE histogram: none, zlib, lzma, lz4, bzlib, other */
+} tvk_octree_file_info;
+int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64_t uvf_file_version,
+                         const float scale[3], const double* minmax, uint64_t n_minmax, double range_max,
+                         float max_gradient_magnitude, tvk_octree_file_info* info);
+/* host-only helpers (no device, no ctx; errors via tvk_last_error(NULL)): parse header + table of contents,
+ * read one brick (x fastest, own size incl. ghost, decoded) into host memory */
+int tvk_octree_file_probe(const char* path, uint64_t offset, uint64_t uvf_file_version, tvk_octree_file_info* info);
+int tvk_octree_file_read_brick(const char* path, uint64_t offset, uint64_t uvf_file_version, uint32_t x, uint32_t y,
+                               uint32_t z, uint32_t lod, void* dst, size_t cap, uint32_t out_size[3]);
 int tvk_get_info(const tvk_ctx* ctx, tvk_info* out);
 /* parity taps: MaxMinForKey table and one brick (x-fastest, own size incl. ghost) */
 int tvk_get_minmax(tvk_ctx* ctx, double* dst, uint64_t n_bricks);

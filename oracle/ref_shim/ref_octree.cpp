@@ -5,6 +5,9 @@
 // into oracle/_ref/ (git-ignored).  No reference source is copied here.
 //
 // usage: ref_octree <in.raw> <out.bin> <dtype u8|u16|f32> X Y Z brick overlap clamp median
+//                   [octree_out [compression 0 none|1 zlib|3 lz4 [layout 0 scanline|1 morton|2 hilbert|3 random]]]
+// octree_out: the ExtendedOctree file the converter wrote (= payload of a UVF TOC block) is kept there, so the
+// product's file reader (tvk_open_octree_file) can be tested on reference-written data.
 // out.bin: u64 lodCount, u64 brickCount, then per brick (TOC order):
 //          u64 sx,sy,sz, f64 min,max, raw voxels
 #include <cstdio>
@@ -23,7 +26,7 @@ public:
 };
 
 int main(int argc, char** argv) {
-  if (argc != 11) { fprintf(stderr, "bad args\n"); return 2; }
+  if (argc < 11 || argc > 14) { fprintf(stderr, "bad args\n"); return 2; }
   std::string in = argv[1], out = argv[2], dt = argv[3];
   UINT64VECTOR3 vol(strtoull(argv[4], 0, 10), strtoull(argv[5], 0, 10), strtoull(argv[6], 0, 10));
   uint64_t brick = strtoull(argv[7], 0, 10);
@@ -33,12 +36,15 @@ int main(int argc, char** argv) {
       dt == "u8" ? ExtendedOctree::CT_UINT8 : dt == "u16" ? ExtendedOctree::CT_UINT16 : ExtendedOctree::CT_FLOAT32;
 
   NullOut dbg;
-  std::string tmp = out + ".octree";
+  const bool keep = argc > 11;
+  std::string tmp = keep ? std::string(argv[11]) : out + ".octree";
+  const COMPRESSION_TYPE comp = argc > 12 ? (COMPRESSION_TYPE)atoi(argv[12]) : CT_NONE;
+  const LAYOUT_TYPE layout = argc > 13 ? (LAYOUT_TYPE)atoi(argv[13]) : LT_SCANLINE;
   BrickStatVec stats;
   {
     ExtendedOctreeConverter c(UINT64VECTOR3(brick, brick, brick), overlap, 1ull << 30, dbg);
-    if (!c.Convert(in, 0, ct, 1, vol, DOUBLEVECTOR3(1, 1, 1), tmp, 0, &stats, CT_NONE, 0,
-                   median, clamp, LT_SCANLINE)) {
+    if (!c.Convert(in, 0, ct, 1, vol, DOUBLEVECTOR3(1, 1, 1), tmp, 0, &stats, comp, comp == CT_LZ4 ? 1 : 6,
+                   median, clamp, layout)) {
       fprintf(stderr, "convert failed\n");
       return 1;
     }
@@ -71,6 +77,6 @@ int main(int argc, char** argv) {
   }
   fclose(f);
   e.Close();
-  remove(tmp.c_str());
+  if (!keep) remove(tmp.c_str());
   return 0;
 }

@@ -1,0 +1,37 @@
+"""Writes tests/golden/octree_*.bin: ExtendedOctree files produced by the UNMODIFIED reference converter
+(oracle/_ref/ref_octree = ExtendedOctreeConverter compiled in place from /root/reference, with the reference's own
+zlib / LZ4 wrappers) from the seeded synthetic volume below.  The reader tests (tests/test_octree_file.py) open these
+on machines without the reference tree.  Run from the repo root:  python tests/golden/make_octree_golden.py"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from tuvok_b200 import synth  # noqa: E402
+
+CASES = {   # name: (kind, (x, y, z), dtype code, dtype name, brick, overlap, compression, layout)
+    "octree_u16_none": (synth.V_NOISE, (26, 22, 18), 1, "u16", 12, 2, 0, 0),
+    "octree_u16_lz4_morton": (synth.V_NOISE, (44, 36, 28), 1, "u16", 16, 2, 3, 1),
+    "octree_u8_zlib_hilbert": (synth.V_SPH, (40, 40, 24), 0, "u8", 12, 2, 1, 2),
+    "octree_f32_none": (synth.V_SPH, (18, 14, 12), 2, "f32", 12, 2, 0, 0),
+}
+
+
+def volume(name):
+    kind, size, dt, _, _, _, _, _ = CASES[name]
+    return synth.synth_volume(kind, size, dt, 0x5EED)
+
+
+if __name__ == "__main__":
+    tool = os.path.join(ROOT, "oracle", "_ref", "ref_octree")
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for name, (kind, size, dt, dname, brick, ov, comp, layout) in CASES.items():
+        raw = "/tmp/%s.raw" % name
+        volume(name).tofile(raw)
+        dst = os.path.join(out_dir, name + ".bin")
+        subprocess.check_call([tool, raw, "/tmp/%s.dump" % name, dname, str(size[0]), str(size[1]), str(size[2]), str(brick),
+                               str(ov), "0", "0", dst, str(comp), str(layout)], stdout=subprocess.DEVNULL)
+        print(name, os.path.getsize(dst), "bytes")

@@ -61,6 +61,12 @@ class Info(C.Structure):
                 ("pool_size", u32x3), ("pool_capacity", u32x3), ("meta_dim", u32x3), ("meta_count", C.c_uint64)]
 
 
+class OctreeFileInfo(C.Structure):
+    _fields_ = [("domain_size", u32x3), ("aspect", C.c_double * 3), ("max_brick_size", u32x3), ("overlap", C.c_uint32),
+                ("dtype", C.c_int32), ("version", C.c_uint32), ("lod_count", C.c_uint32), ("brick_count", C.c_uint64),
+                ("payload_bytes", C.c_uint64), ("bricks_by_codec", C.c_uint64 * 6)]
+
+
 class ClassicBrick(C.Structure):
     _fields_ = [("index", C.c_uint32), ("x", C.c_uint32), ("y", C.c_uint32), ("z", C.c_uint32),
                 ("distance", C.c_float), ("empty", C.c_int32)]
@@ -83,6 +89,11 @@ SIGNATURES = {
     "tvk_set_volume": (C.c_int, [P, C.POINTER(VolumeDesc), BRICK_CB, P]),
     "tvk_build_volume": (C.c_int, [P, P, C.c_int, u32x3, C.c_int, f32x3, u32x3, C.c_uint32, C.c_int,
                                    C.c_double, C.c_float]),
+    "tvk_open_octree_file": (C.c_int, [P, C.c_char_p, C.c_uint64, C.c_uint64, P, P, C.c_uint64, C.c_double, C.c_float,
+                                       C.POINTER(OctreeFileInfo)]),
+    "tvk_octree_file_probe": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(OctreeFileInfo)]),
+    "tvk_octree_file_read_brick": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                             C.c_uint32, P, C.c_size_t, u32x3]),
     "tvk_synth_volume": (C.c_int, [P, P, C.c_int, u32x3, C.c_int, C.c_uint32]),
     "tvk_get_info": (C.c_int, [P, C.POINTER(Info)]),
     "tvk_get_minmax": (C.c_int, [P, P, C.c_uint64]),

@@ -200,6 +200,38 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ v
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// min/max of bricks that arrive through the streaming path (file reader / callback) without a MaxMin block:
+// one CTA per staged brick (tightly packed at its own size), every stored voxel incl. ghost, as doubles
+// (ComputeBrickStats, ExtendedOctreeConverter.inc:408-444; MaxMinDataBlock layout)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) brick_minmax_kernel(const unsigned char* __restrict__ staged, const PageOp* ops,
+                                                           double* minmax) {
+  const PageOp op = ops[blockIdx.x];
+  const T* src = reinterpret_cast<const T*>(staged + op.src_off);
+  const uint32_t n = op.size[0] * op.size[1] * op.size[2];
+  T mn = src[0], mx = src[0];
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const T v = src[i];
+    mn = v < mn ? v : mn; mx = v > mx ? v : mx;
+  }
+  const unsigned full = 0xffffffffu;
+  for (int o = 16; o > 0; o >>= 1) {
+    const T omn = __shfl_down_sync(full, mn, o), omx = __shfl_down_sync(full, mx, o);
+    mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx;
+  }
+  __shared__ T s_mn[8], s_mx[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { mn = s_mn[w] < mn ? s_mn[w] : mn; mx = s_mx[w] > mx ? s_mx[w] : mx; }
+    double* o = minmax + 4 * (uint64_t)op.new_id;
+    o[0] = (double)mn; o[1] = (double)mx; o[2] = -DBL_MAX; o[3] = DBL_MAX;
+  }
+}
+
 inline int grid_for(uint64_t n, int block) {
   uint64_t g = (n + block - 1) / block;
   const uint64_t cap = (uint64_t)kSMs * 16;
@@ -231,6 +263,15 @@ void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const u
     case TVK_U8: downsample_kernel<uint8_t><<<g, 256, 0, s>>>((const uint8_t*)src, ss[0], ss[1], ss[2], (uint8_t*)dst, ds[0], ds[1], ds[2]); break;
     case TVK_U16: downsample_kernel<uint16_t><<<g, 256, 0, s>>>((const uint16_t*)src, ss[0], ss[1], ss[2], (uint16_t*)dst, ds[0], ds[1], ds[2]); break;
     default: downsample_kernel<float><<<g, 256, 0, s>>>((const float*)src, ss[0], ss[1], ss[2], (float*)dst, ds[0], ds[1], ds[2]); break;
+  }
+}
+
+void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, double* minmax, int dtype, cudaStream_t s) {
+  const unsigned char* p = static_cast<const unsigned char*>(staged);
+  switch (dtype) {
+    case TVK_U8: brick_minmax_kernel<uint8_t><<<n, 256, 0, s>>>(p, ops, minmax); break;
+    case TVK_U16: brick_minmax_kernel<uint16_t><<<n, 256, 0, s>>>(p, ops, minmax); break;
+    default: brick_minmax_kernel<float><<<n, 256, 0, s>>>(p, ops, minmax); break;
   }
 }
 

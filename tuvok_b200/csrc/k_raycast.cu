@@ -382,6 +382,10 @@ constexpr int kFetchLanes = TVK_FETCH_LANES;
 #endif
 constexpr int kWX = TVK_WX, kWY = TVK_WY, kThreads = 32 * TVK_WX * TVK_WY;
 constexpr int kIlp = TVK_ILP;   // samples per lane per loop turn (1 or 2)
+#ifndef TVK_SKIP_CLEAR
+#define TVK_SKIP_CLEAR 1
+#endif
+constexpr bool kSkipClear = TVK_SKIP_CLEAR != 0;   // A/B switch for the zero-alpha shortcut in shade()
 #ifndef TVK_CENTRE_OUT
 #define TVK_CENTRE_OUT 1
 #endif
@@ -641,25 +645,33 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
             Foot<T, FAST, BS> f;
             f.set(P, pool, vox, b_ox, b_oy, b_oz, q);
             f4 col;
+            // A sample whose transfer-function alpha is exactly 0 leaves the ray unchanged bit for bit
+            // (UnderCompositing adds colour * (1-a) * 0 = 0 to every channel; table colours and lit colours are
+            // finite, and opacity correction maps 0 to 0), so its normal, lighting -- and with a 1D table its six
+            // gradient taps -- are not computed.  The shader cannot branch this cheaply; the result is identical.
             if (MODE == 0 && !LIT) {
               const float data = f.tap(P, 0, 0, 0);
               col = tf_lookup(P, data * P.trans_scale, 0.0f);
+            } else if (MODE == 0) {
+              col = tf_lookup(P, f.tap(P, 0, 0, 0) * P.trans_scale, 0.0f);
+              if (kSkipClear && col.w == 0.0f) return col;
+              float data; f3 g;
+              f.sample_with_gradient(P, data, g);
+              f3 n = mul3(g, dscale);   // ComputeNormal
+              const float l = len3(n);
+              if (l > 0.0f) n = scl3(n, 1.0f / l);
+              const f3 mp = mul3(sub3(q, b_trans), b_inv);
+              const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
+              col.x = lit.x; col.y = lit.y; col.z = lit.z;
             } else {
               float data; f3 g;
               f.sample_with_gradient(P, data, g);
-              f3 n;
-              if (MODE == 0) {
-                col = tf_lookup(P, data * P.trans_scale, 0.0f);
-                n = mul3(g, dscale);   // ComputeNormal
-                const float l = len3(n);
-                if (l > 0.0f) n = scl3(n, 1.0f / l);
-              } else {
-                const float gm = len3(g);
-                col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
-                const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
-                n = mul3(dscale, gn);
-              }
+              const float gm = len3(g);
+              col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
+              if (kSkipClear && col.w == 0.0f) return col;
               if (LIT) {
+                const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
+                const f3 n = mul3(dscale, gn);
                 const f3 mp = mul3(sub3(q, b_trans), b_inv);
                 const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
                 col.x = lit.x; col.y = lit.y; col.z = lit.z;

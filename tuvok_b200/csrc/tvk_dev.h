@@ -124,6 +124,8 @@ struct CutConsts {
   int32_t clamp, lod;
   uint64_t first_brick;   // TOC index of brick (0,0,0) of this LOD
 };
+// min/max of n staged bricks (ops[i]: src_off, size, new_id = TOC index) -> minmax[4 * new_id]
+void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, double* minmax, int dtype, cudaStream_t s);
 void launch_cut_bricks(const void* lod_vol, void* store, double* minmax, const CutConsts& cc, int dtype,
                        uint64_t slot_bytes, cudaStream_t s);
 

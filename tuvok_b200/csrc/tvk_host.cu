@@ -11,9 +11,13 @@
 //   GLRenderer::ComputeViewAndProjection, CullingLOD::SetScreenParams
 // There is no CPU fallback: every data-path operation is a CUDA kernel in k_*.cu.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <limits>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include "tvk_host.h"
 
 using namespace tvk;
@@ -115,6 +119,8 @@ void free_dataset(tvk_ctx* c) {
   if (c->store_d) cudaFree(c->store_d);
   c->minmax_d = nullptr; c->store_d = nullptr;
   c->minmax_h.clear();
+  if (c->file) { delete c->file; c->file = nullptr; }
+  c->cb = nullptr; c->cb_user = nullptr;
   c->have_volume = false;
 }
 
@@ -250,6 +256,45 @@ int scatter_u32(tvk_ctx* ctx, uint32_t* dst, const std::vector<std::pair<uint32_
 
 struct CopyReq { uint32_t id; uint32_t slot; uint32_t co[4]; };
 
+// Dataset::GetBrick stand-in of the file source: brick (x,y,z,lod) of the open ExtendedOctree file into dst
+int file_brick_cb(void* user, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, void* dst, size_t cap) {
+  tvk_ctx* ctx = static_cast<tvk_ctx*>(user);
+  const OctreeFile* f = ctx->file;
+  uint32_t bs[3];
+  f->brick_size(x, y, z, lod, bs);
+  std::string err;
+  if (!f->read_brick(f->brick_index(x, y, z, lod), (size_t)bs[0] * bs[1] * bs[2] * ctx->esize, dst, cap, &err)) {
+    static std::mutex m;
+    std::lock_guard<std::mutex> g(m);
+    ctx->file->error = err;
+    return 1;
+  }
+  return 0;
+}
+
+// bricks reqs[0..n) -> hb + i * slot_bytes.  Returns the index of the first failed brick or -1.
+long fill_stage(tvk_ctx* ctx, const CopyReq* reqs, size_t n, unsigned char* hb) {
+  auto one = [&](size_t i) {
+    const CopyReq& r = reqs[i];
+    return ctx->cb(ctx->cb_user, r.co[0], r.co[1], r.co[2], r.co[3], hb + i * ctx->slot_bytes, ctx->slot_bytes) == 0;
+  };
+  const size_t workers = ctx->file ? std::min<size_t>(ctx->io_threads, n) : 1;
+  if (workers <= 1) {
+    for (size_t i = 0; i < n; i++) if (!one(i)) return (long)i;
+    return -1;
+  }
+  std::atomic<size_t> next{0};
+  std::atomic<long> bad{-1};
+  std::vector<std::thread> pool;
+  for (size_t t = 0; t < workers; t++)
+    pool.emplace_back([&] {
+      for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1))
+        if (!one(i)) { long exp = -1; bad.compare_exchange_strong(exp, (long)i); }
+    });
+  for (std::thread& th : pool) th.join();
+  return bad.load();
+}
+
 // move the voxels of the requested bricks into their slots
 int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
   if (reqs.empty()) return TVK_OK;
@@ -290,15 +335,19 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
       const CopyReq& r = reqs[pos + i];
       uint32_t bs[3];
       brick_size(ctx, r.co, r.co[3], bs);
-      if (ctx->cb(ctx->cb_user, r.co[0], r.co[1], r.co[2], r.co[3], hb + i * ctx->slot_bytes, ctx->slot_bytes) != 0) {
-        rc = fail(ctx, TVK_ERR_SOURCE, "brick source failed for (%u,%u,%u,%u)", r.co[0], r.co[1], r.co[2], r.co[3]);
-        break;
-      }
       ops[i].slot = r.slot;
       ops[i].src_off = (uint64_t)i * ctx->slot_bytes;
       ops[i].size[0] = bs[0]; ops[i].size[1] = bs[1]; ops[i].size[2] = bs[2];
     }
-    if (rc) break;
+    // fill the pinned half: the file source reads (pread + decode) with several workers straight into pinned
+    // memory; a user callback (Dataset::GetBrick) is called from this thread, one brick at a time
+    const long bad = fill_stage(ctx, &reqs[pos], n, hb);
+    if (bad >= 0) {
+      const CopyReq& r = reqs[pos + (size_t)bad];
+      rc = fail(ctx, TVK_ERR_SOURCE, "brick source failed for (%u,%u,%u,%u)%s%s", r.co[0], r.co[1], r.co[2], r.co[3],
+                ctx->file ? ": " : "", ctx->file ? ctx->file->error.c_str() : "");
+      break;
+    }
     // ops travel in the same pinned half (tail) so the copy is truly asynchronous
     const size_t ops_off = (ctx->stage_bricks * ctx->slot_bytes + 15) & ~size_t(15);
     PageOp* hops = (PageOp*)((unsigned char*)ctx->stage_h + ops_off) + (size_t)h * half;
@@ -716,6 +765,167 @@ int tvk_set_volume(tvk_ctx* ctx, const tvk_volume_desc* d, tvk_brick_cb cb, void
   CU(cudaMemcpy(ctx->minmax_d, ctx->minmax_h.data(), ctx->minmax_h.size() * sizeof(double), cudaMemcpyHostToDevice));
   ctx->cb = cb; ctx->cb_user = user;
   ctx->have_volume = true;
+  return TVK_OK;
+}
+
+static void fill_file_info(const OctreeFile& g, tvk_octree_file_info* info);
+
+// min/max table of a streamed dataset that comes without a MaxMin block: every brick of the pool LoDs goes once
+// through the pinned staging path (double buffered, parallel reads) and is reduced on the device
+static int minmax_from_source(tvk_ctx* ctx) {
+  const size_t nb_total = ctx->total_bricks;
+  size_t nb = std::max<size_t>(2, ((64ull << 20) / ctx->slot_bytes) & ~size_t(1));
+  nb = std::min(nb, std::max<size_t>(2, (nb_total + 1) & ~size_t(1)));
+  const size_t half = nb / 2;
+  const size_t ops_off = (nb * ctx->slot_bytes + 15) & ~size_t(15);
+  const size_t bytes = ops_off + nb * sizeof(PageOp);
+  unsigned char *sh = nullptr, *sd = nullptr;
+  CU(cudaMallocHost(&sh, bytes));
+  if (cudaMalloc(&sd, bytes) != cudaSuccess) { cudaFreeHost(sh); return fail(ctx, TVK_ERR_OOM, "staging allocation failed"); }
+  cudaEvent_t done[2];
+  cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+  int rc = TVK_OK;
+  std::vector<CopyReq> reqs;
+  size_t pos = 0;
+  int h = 0;
+  while (pos < nb_total && rc == TVK_OK) {
+    const size_t n = std::min(half, nb_total - pos);
+    cudaEventSynchronize(done[h]);
+    unsigned char* hb = sh + (size_t)h * half * ctx->slot_bytes;
+    PageOp* hops = (PageOp*)(sh + ops_off) + (size_t)h * half;
+    reqs.assign(n, CopyReq{});
+    for (size_t i = 0; i < n; i++) {
+      const uint32_t id = (uint32_t)(pos + i);
+      uint32_t lod = 0;
+      while (lod + 1 < ctx->pool_lod_count && id >= ctx->lod_offset[lod + 1]) lod++;
+      const uint32_t local = id - ctx->lod_offset[lod];
+      const uint32_t* l = ctx->pool_layout[lod];
+      CopyReq& r = reqs[i];
+      r.id = id; r.slot = 0;
+      r.co[0] = local % l[0]; r.co[1] = (local / l[0]) % l[1]; r.co[2] = local / (l[0] * l[1]); r.co[3] = lod;
+      uint32_t bs[3];
+      brick_size(ctx, r.co, lod, bs);
+      hops[i] = PageOp{};
+      hops[i].new_id = id;
+      hops[i].src_off = (uint64_t)i * ctx->slot_bytes;
+      hops[i].size[0] = bs[0]; hops[i].size[1] = bs[1]; hops[i].size[2] = bs[2];
+    }
+    const long bad = fill_stage(ctx, reqs.data(), n, hb);
+    if (bad >= 0) {
+      const CopyReq& r = reqs[(size_t)bad];
+      rc = fail(ctx, TVK_ERR_SOURCE, "brick source failed for (%u,%u,%u,%u)%s%s", r.co[0], r.co[1], r.co[2], r.co[3],
+                ctx->file ? ": " : "", ctx->file ? ctx->file->error.c_str() : "");
+      break;
+    }
+    unsigned char* db = sd + (size_t)h * half * ctx->slot_bytes;
+    PageOp* dops = (PageOp*)(sd + ops_off) + (size_t)h * half;
+    cudaMemcpyAsync(db, hb, n * ctx->slot_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    cudaMemcpyAsync(dops, hops, n * sizeof(PageOp), cudaMemcpyHostToDevice, ctx->copy_stream);
+    launch_brick_minmax(db, dops, (uint32_t)n, ctx->minmax_d, ctx->dtype, ctx->copy_stream);
+    cudaEventRecord(done[h], ctx->copy_stream);
+    pos += n;
+    h ^= 1;
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+  cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+  cudaFreeHost(sh); cudaFree(sd);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, TVK_ERR_CUDA, "min/max pass failed: %s", cudaGetErrorString(e));
+  return TVK_OK;
+}
+
+int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64_t uvf_file_version, const float scale[3],
+                         const double* minmax, uint64_t n_minmax, double range_max, float max_gradient_magnitude,
+                         tvk_octree_file_info* info) {
+  if (!ctx || !path) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  std::unique_ptr<OctreeFile> f(new OctreeFile());
+  if (!f->open(path, offset, uvf_file_version)) return fail(ctx, TVK_ERR_SOURCE, "%s: %s", path, f->error.c_str());
+  int dtype = -1;
+  switch (f->component_type) {   // ExtendedOctree::COMPONENT_TYPE (ExtendedOctree.h:137-148)
+    case 0: dtype = TVK_U8; break;
+    case 1: dtype = TVK_U16; break;
+    case 8: dtype = TVK_F32; break;
+    default: break;
+  }
+  if (dtype < 0 || f->component_count != 1)
+    return fail(ctx, TVK_ERR_INVALID, "%s: component type %u x %llu is not on the hot path (u8 / u16 / f32 scalar)", path,
+                f->component_type, (unsigned long long)f->component_count);
+  uint32_t size[3], brick[3];
+  float sc[3];
+  for (int i = 0; i < 3; i++) {
+    if (f->vol[i] > 0xffffffffull || f->brick[i] > 0xffffffffull) return fail(ctx, TVK_ERR_INVALID, "%s: size overflow", path);
+    size[i] = (uint32_t)f->vol[i]; brick[i] = (uint32_t)f->brick[i];
+    sc[i] = scale ? scale[i] : (float)f->aspect[i];      // UVFDataset: domain scale = the octree's volume aspect
+  }
+  int rc = set_geometry(ctx, size, sc, brick, f->overlap, dtype, range_max, max_gradient_magnitude);
+  if (rc) return rc;
+  if (f->toc.size() != ctx->n_bricks_all || f->lod_count() != ctx->lod_count)
+    return fail(ctx, TVK_ERR_INVALID, "%s: table of contents has %zu bricks / %u LoDs, the geometry implies %llu / %u", path,
+                f->toc.size(), f->lod_count(), (unsigned long long)ctx->n_bricks_all, ctx->lod_count);
+  ctx->file = f.release();
+  ctx->cb = file_brick_cb; ctx->cb_user = ctx;
+  CU(cudaMalloc(&ctx->minmax_d, 4 * (size_t)ctx->total_bricks * sizeof(double)));
+  ctx->minmax_h.resize(4 * (size_t)ctx->total_bricks);
+  if (minmax) {
+    if (n_minmax < ctx->total_bricks) {
+      free_dataset(ctx);
+      return fail(ctx, TVK_ERR_INVALID, "min/max table has %llu entries, the pool LoDs need %u",
+                  (unsigned long long)n_minmax, ctx->total_bricks);
+    }
+    std::memcpy(ctx->minmax_h.data(), minmax, ctx->minmax_h.size() * sizeof(double));
+    CU(cudaMemcpy(ctx->minmax_d, ctx->minmax_h.data(), ctx->minmax_h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  } else {
+    rc = minmax_from_source(ctx);
+    if (rc) { free_dataset(ctx); return rc; }
+    CU(cudaMemcpy(ctx->minmax_h.data(), ctx->minmax_d, ctx->minmax_h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (info) { fill_file_info(*ctx->file, info); info->dtype = dtype; }
+  ctx->have_volume = true;
+  return TVK_OK;
+}
+
+static void fill_file_info(const OctreeFile& g, tvk_octree_file_info* info) {
+  std::memset(info, 0, sizeof(*info));
+  for (int i = 0; i < 3; i++) {
+    info->domain_size[i] = (uint32_t)g.vol[i]; info->aspect[i] = g.aspect[i]; info->max_brick_size[i] = (uint32_t)g.brick[i];
+  }
+  info->overlap = g.overlap; info->version = g.version; info->lod_count = g.lod_count();
+  info->dtype = g.component_count != 1 ? -1 : g.component_type == 0 ? TVK_U8 : g.component_type == 1 ? TVK_U16
+              : g.component_type == 8 ? TVK_F32 : -1;
+  info->brick_count = g.toc.size();
+  for (const OctreeToc& t : g.toc) {
+    info->payload_bytes += t.length;
+    info->bricks_by_codec[t.codec < 6 ? t.codec : 5]++;
+  }
+}
+
+// host-only helpers (no device, no ctx): header/TOC probe and single-brick read of an ExtendedOctree file
+int tvk_octree_file_probe(const char* path, uint64_t offset, uint64_t uvf_file_version, tvk_octree_file_info* info) {
+  if (!path || !info) return TVK_ERR_INVALID;
+  OctreeFile f;
+  if (!f.open(path, offset, uvf_file_version)) { g_create_err = std::string(path) + ": " + f.error; return TVK_ERR_SOURCE; }
+  fill_file_info(f, info);
+  return TVK_OK;
+}
+
+int tvk_octree_file_read_brick(const char* path, uint64_t offset, uint64_t uvf_file_version, uint32_t x, uint32_t y,
+                               uint32_t z, uint32_t lod, void* dst, size_t cap, uint32_t out_size[3]) {
+  if (!path || !dst) return TVK_ERR_INVALID;
+  OctreeFile f;
+  if (!f.open(path, offset, uvf_file_version)) { g_create_err = std::string(path) + ": " + f.error; return TVK_ERR_SOURCE; }
+  if (lod >= f.lod_count() || x >= f.lod_layout[3 * lod] || y >= f.lod_layout[3 * lod + 1] || z >= f.lod_layout[3 * lod + 2]) {
+    g_create_err = "brick coordinates out of range";
+    return TVK_ERR_INVALID;
+  }
+  uint32_t bs[3];
+  f.brick_size(x, y, z, lod, bs);
+  if (out_size) { out_size[0] = bs[0]; out_size[1] = bs[1]; out_size[2] = bs[2]; }
+  std::string err;
+  if (!f.read_brick(f.brick_index(x, y, z, lod), (size_t)bs[0] * bs[1] * bs[2] * f.element_bytes(), dst, cap, &err)) {
+    g_create_err = std::string(path) + ": " + err;
+    return TVK_ERR_SOURCE;
+  }
   return TVK_OK;
 }
 

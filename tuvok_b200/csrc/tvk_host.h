@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "tvk_dev.h"
+#include "octree_file.h"
 
 namespace tvk {
 
@@ -91,6 +92,8 @@ struct tvk_ctx {
   double* minmax_d = nullptr;
   tvk_brick_cb cb = nullptr;
   void* cb_user = nullptr;
+  tvk::OctreeFile* file = nullptr;        // ExtendedOctree file source (tvk_open_octree_file); cb then points at it
+  uint32_t io_threads = 8;                // parallel pread/decode workers of the file source
   void* store_d = nullptr;                // device brick store (slot layout, TOC order) or null
   uint64_t slot_voxels = 0, slot_bytes = 0;
 

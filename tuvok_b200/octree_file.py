@@ -1,0 +1,36 @@
+"""Host-side access to ExtendedOctree files (the payload of a UVF TOC block) through the C ABI's host-only helpers
+tvk_octree_file_probe / tvk_octree_file_read_brick -- no device needed.  Mirrors what a Tuvok client gets from
+ExtendedOctree::Open / GetBrickData (IO/UVF/ExtendedOctree/ExtendedOctree.cpp:87-165,313-360)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+_NP = {L.U8: np.uint8, L.U16: np.uint16, L.F32: np.float32}
+
+
+def probe(path, offset=0, uvf_file_version=5):
+    """Parse header + table of contents.  Returns OctreeFileInfo; raises TvkError on a malformed file."""
+    info = L.OctreeFileInfo()
+    rc = L.lib().tvk_octree_file_probe(os.fsencode(path), int(offset), int(uvf_file_version), C.byref(info))
+    if rc:
+        raise L.TvkError(rc, (L.lib().tvk_last_error(None) or b"").decode())
+    return info
+
+
+def read_brick(path, x, y, z, lod, info=None, offset=0, uvf_file_version=5):
+    """One decoded brick as ndarray [sz, sy, sx] (own size incl. ghost)."""
+    info = info or probe(path, offset, uvf_file_version)
+    if info.dtype not in _NP:
+        raise ValueError("component type not on the hot path")
+    cap = int(np.prod(list(info.max_brick_size))) * np.dtype(_NP[info.dtype]).itemsize
+    buf = np.zeros(cap, np.uint8)
+    size = L.u32x3()
+    rc = L.lib().tvk_octree_file_read_brick(os.fsencode(path), int(offset), int(uvf_file_version), x, y, z, lod,
+                                            buf.ctypes.data_as(C.c_void_p), cap, size)
+    if rc:
+        raise L.TvkError(rc, (L.lib().tvk_last_error(None) or b"").decode())
+    sx, sy, sz = (int(v) for v in size)
+    return np.frombuffer(buf.tobytes(), _NP[info.dtype], sx * sy * sz).reshape(sz, sy, sx)

@@ -9,6 +9,7 @@ bodies is a call into the C ABI of libtvkcuda.so (include/tvk.h); no pixel, voxe
 entry is computed in Python.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -106,6 +107,25 @@ class CudaGridLeaper:
         self._ck(self._lib.tvk_enable_counters(self._h, int(on)))
 
     # ------------------------------------------------------------------ dataset
+    def OpenOctreeFile(self, path, offset=0, uvf_file_version=5, scale=None, minmax=None, range_max=0.0,
+                       max_gradient_magnitude=0.0):
+        """UVFDataset stand-in for a TOC block: the ExtendedOctree file at `path` (header at byte `offset`) becomes the
+        brick source of the streaming path (parallel pread into pinned staging, zlib / lz4 decoded there).  minmax:
+        MaxMinDataBlock table (n, 4) in TOC order, or None to compute it on the device in one streaming pass.
+        Returns the parsed header (OctreeFileInfo)."""
+        info = L.OctreeFileInfo()
+        sc = L.f32x3(*scale) if scale is not None else None
+        mm, n = None, 0
+        if minmax is not None:
+            mm = np.ascontiguousarray(minmax, np.float64).reshape(-1, 4)
+            n = mm.shape[0]
+        self._ck(self._lib.tvk_open_octree_file(self._h, os.fsencode(path), int(offset), int(uvf_file_version),
+                                                C.cast(sc, C.c_void_p) if sc is not None else None,
+                                                mm.ctypes.data_as(C.c_void_p) if mm is not None else None, n,
+                                                float(range_max), float(max_gradient_magnitude), C.byref(info)))
+        self._dirty = True
+        return info
+
     def RegisterDataset(self, domain_size, max_brick_size, overlap, dtype, minmax, get_brick, scale=(1, 1, 1),
                         range_max=0.0, max_gradient_magnitude=0.0):
         """LinearIndexDataset stand-in: `get_brick(x, y, z, lod) -> ndarray [sz, sy, sx]` plays
