@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4"])
     ap.add_argument("--path", default="gridleaper", choices=["gridleaper", "classic"],
                     help="gridleaper: GLGridLeaper page-table traversal (default); classic: per-brick GLRaycaster path")
+    ap.add_argument("--split", default="auto", choices=["auto", "screen", "depth", "depth2", "octant"],
+                    help="sort-last partition policy (tuvok_b200/sortlast.py); auto = screen for N <= 4, octant for N = 8 "
+                         "(measured best, DESIGN.md section 5)")
     ap.add_argument("--vol", type=int, default=0, help="override the cubic volume size (debugging)")
     ap.add_argument("--cpu-vol", type=int, default=256, help="volume size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -153,16 +156,21 @@ def run_reference(args, rank):
             break
     frame_s = float(np.mean(times))
     sps = samples / frame_s
-    fps_equiv = 1.0 / (frame_s * cs.scale)
+    # frames/s of the FULL workload at the measured CPU sample rate: samples/s / samples of one full frame (a
+    # device-counted constant of the seeded workload, tuvok_b200/workloads.py) -- the same conversion as the
+    # cpu_baseline object of the GPU arm.  Fallback for workloads without a recorded count: rays x depth scaling.
+    spf = workloads.SAMPLES_PER_FRAME.get(args.config) if not args.vol else None
+    fps_equiv = sps / spf if spf else 1.0 / (frame_s * cs.scale)
+    how = ("value = CPU samples/s / %.4g samples of one full frame" % spf) if spf else \
+          ("value = 1 / (step time x %.0f)" % cs.scale)
     w = workloads.WORKLOADS[args.config]
     line = {"impl": "reference", "metric": "frames_per_s", "value": fps_equiv, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": frame_s * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "gsamples_per_s": sps / 1e9,
             "config": {"workload": w["label"], "bounded_sample": cs.desc,
-                       "note": "each step = one bounded-sample frame; value = 1 / (step time x %.0f), the frame "
-                               "rate of the full-resolution, full-size workload at the measured CPU sample rate"
-                               % cs.scale},
+                       "note": "each step = one bounded-sample frame; " + how + ", the frame rate of the "
+                               "full-resolution, full-size workload at the measured CPU sample rate"},
             "cpu_baseline": {"value": fps_equiv, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": cs.desc, "gsamples_per_s": sps / 1e9},
             "e2e": {"value": fps_equiv, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -221,7 +229,8 @@ def run_tvk(args, rank, world, local_rank):
     ext = ext / ext.max()
     flayout = [np.float32(v) / np.float32(inner) for v in w["size"]]
     flayout = [f - f * np.finfo(np.float32).eps if float(int(f)) == float(f) else f for f in flayout]
-    sl = sortlast.SortLastRenderer(r, rank, world, finest, flayout, ext) if world > 1 else None
+    split = args.split if args.split != "auto" else ("octant" if world >= 8 else "screen")
+    sl = sortlast.SortLastRenderer(r, rank, world, finest, flayout, ext, policy=split) if world > 1 else None
     n_views = 36
     classic = args.path == "classic"
     if classic and world > 1:
@@ -370,7 +379,7 @@ def run_tvk(args, rank, world, local_rank):
             "data": "synthetic", "gsamples_per_s": gsps,
             "config": {"workload": w["label"], "volume": "V_noise seed 0x5EED" if w["kind"] == 1 else "V_sph",
                        "camera": "36-step orbit (Ry 10deg steps, Rx 20deg), eye (0,0,1.6) fov 50",
-                       "parallelism": "sort-last x%d (binary swap)" % world if world > 1 else "single GPU",
+                       "parallelism": "sort-last x%d (binary swap, %s partition)" % (world, split) if world > 1 else "single GPU",
                        "path": "classic per-brick GLRaycaster" if classic else "GridLeaper page-table traversal",
                        "l2_policy": "inputs larger than L2 (pool %.1f GB, %.0f MB of bricks touched per frame)" %
                                     (info.pool_capacity[0] * info.pool_capacity[1] * info.pool_capacity[2] * slot_bytes / 1e9,

@@ -24,6 +24,14 @@ WORKLOADS = {
 }
 
 
+# Samples (ComputeColorFromVolume / GetVolumeHit evaluations) of one converged frame, mean over the 36-view orbit, as
+# counted on the device by the counting variant of the traversal kernel (bench.py reports the live count in
+# config.samples_per_frame; these are the values of profiles/r1d_bench_*.json).  The workloads are seeded and the
+# arithmetic is fixed, so this is a constant of the workload; the CPU reference arm (bench.py --impl reference), which
+# cannot render the full frame in bounded time, converts its measured samples/s to frames/s with it.
+SAMPLES_PER_FRAME = {"c2": 44081668.6, "c3": 99164900.1, "c4": 19898366.8}
+
+
 def transfer_functions(w):
     """(TransferFunction1D, TransferFunction2D) of a workload: SetStdFunction ramp on 4096 (256 for u8)
     entries; 2D TF = one rectangular swatch, as wide as the 1D table, 256 gradient bins."""
