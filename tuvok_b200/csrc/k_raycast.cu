@@ -598,8 +598,10 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
               seg_u[5][tid] = b.where == PARTLY_IN_SHARD ? 1u : 0u;
               if (COUNT) seg_u[6][tid] = b.id;
               have_next = true;
-#pragma unroll 1
-              for (int i = 0; i < steps; i++) pe = add3(pe, vdir);   // where the sample loop will leave pc
+              // where the sample loop will leave pc: `steps` SEQUENTIAL adds (fp32 addition is not associative, so
+              // there is no closed form); 4x unrolled -- this loop was 6.5 % of the launch's warp instructions
+#pragma unroll 4
+              for (int i = 0; i < steps; i++) pe = add3(pe, vdir);
             }
             c.cur = mul3(sub3(pe, b.trans), inv);
           } else {
