@@ -39,6 +39,7 @@ BRICK_CASES = [
     ((33, 64, 17), tb.U16, 12, 2, False),
     ((48, 48, 48), tb.F32, 12, 2, False),      # float mean: summation order matters
     ((96, 96, 96), tb.U16, 36, 2, False),
+    ((160, 160, 128), tb.U16, 36, 2, False),   # interior 36^3 bricks at LoD 0 and 1: the word-vectorised cut and pyramid paths
     ((1, 8, 8)[::-1], tb.U8, 16, 2, False),    # 8x8x1, the rebricking.h volume
     ((40, 40, 40), tb.U8, 12, 2, True),        # clamp-to-edge, LOD 0 and the restated LOD >= 1 rule
     ((36, 36, 36), tb.U16, 10, 1, False),      # 1-voxel ghost

@@ -118,6 +118,30 @@ __global__ void downsample_kernel(const T* __restrict__ src, uint32_t sx, uint32
   }
 }
 
+// 16-bit fast path of the pyramid (all three source extents even, x extent a multiple of 4): one thread makes two
+// x-adjacent voxels of the coarser level from four 8-byte loads (4 voxels of each of the 4 source rows) and writes
+// them as one 32-bit word.  The eight summands are integers < 2^16, their sum is exact in double in any order, so
+// T(sum / 8.0) equals the generic kernel's result bit for bit.
+__global__ void downsample_u16x2_kernel(const uint2* __restrict__ src, uint32_t sx, uint32_t sy, uint32_t* dst,
+                                        uint32_t dx_, uint32_t dy_, uint32_t dz_) {
+  const uint32_t hx = dx_ / 2;                 // output words per row
+  const uint64_t n = (uint64_t)hx * dy_ * dz_;
+  const uint64_t row8 = sx / 4;                // uint2 per source row
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t x = (uint32_t)(i % hx), y = (uint32_t)((i / hx) % dy_), z = (uint32_t)(i / ((uint64_t)hx * dy_));
+    const uint64_t r00 = ((uint64_t)(2 * z) * sy + 2 * y) * row8 + x;
+    const uint2 a = __ldg(src + r00), b = __ldg(src + r00 + row8);
+    const uint2 c = __ldg(src + r00 + (uint64_t)sy * row8), d = __ldg(src + r00 + (uint64_t)sy * row8 + row8);
+    // .x holds voxels 0,1 (low, high half), .y voxels 2,3 of the 4-voxel run
+    const uint32_t s0 = (a.x & 0xffffu) + (a.x >> 16) + (b.x & 0xffffu) + (b.x >> 16) + (c.x & 0xffffu) + (c.x >> 16) +
+                        (d.x & 0xffffu) + (d.x >> 16);
+    const uint32_t s1 = (a.y & 0xffffu) + (a.y >> 16) + (b.y & 0xffffu) + (b.y >> 16) + (c.y & 0xffffu) + (c.y >> 16) +
+                        (d.y & 0xffffu) + (d.y >> 16);
+    const uint32_t v0 = (uint32_t)(uint16_t)((double)s0 / 8.0), v1 = (uint32_t)(uint16_t)((double)s1 / 8.0);
+    dst[i] = v0 | (v1 << 16);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // brick cutting + stats
 // ---------------------------------------------------------------------------------------------
@@ -145,6 +169,31 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ v
   const uint32_t n = bs[0] * bs[1] * bs[2];
   T mn = 0, mx = 0;
   bool any = false;
+  // Fast path (the bulk of a large 16-bit volume): a full 36^3 brick with a 2-voxel ghost that touches no domain
+  // border.  Its slot is one contiguous 93 312-byte block and every source row is a 4-byte-aligned run of 72 bytes,
+  // so the brick is moved as 32-bit words (two voxels each): coalesced 128-byte stores, no per-voxel div/mod.
+  // Same voxels, same stale-corner rule, same min/max as the generic loop below.
+  if (sizeof(T) == 2 && ov == 2 && C.brick[0] == 36 && C.brick[1] == 36 && C.brick[2] == 36 && bs[0] == 36 &&
+      bs[1] == 36 && bs[2] == 36 && !lo_border[0] && !lo_border[1] && !lo_border[2] && !hi_border[0] && !hi_border[1] &&
+      !hi_border[2] && (C.lod_size[0] & 1u) == 0u) {
+    const uint64_t row_words = C.lod_size[0] / 2;
+    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(vol) +
+                            ((uint64_t)org[2] * C.lod_size[1] + (uint64_t)org[1]) * row_words + (uint64_t)org[0] / 2;
+    uint32_t* dst32 = reinterpret_cast<uint32_t*>(dst);
+    uint32_t wmn = 0xffffu, wmx = 0u;
+    for (uint32_t w = threadIdx.x; w < 36u * 36u * 18u; w += blockDim.x) {
+      const uint32_t row = w / 18u, i = w - row * 18u, lz = row / 36u, ly = row - lz * 36u;
+      const int gx = i == 0u ? -1 : i == 17u ? 1 : 0, gy = ly < 2u ? -1 : ly >= 34u ? 1 : 0, gz = lz < 2u ? -1 : lz >= 34u ? 1 : 0;
+      const bool stale = C.lod > 0 && ((gx == 1 && gy == 1 && gz == -1) || (gx == 1 && gy == -1 && gz == 1) ||
+                                       (gx == -1 && gy == 1 && gz == 1));
+      const uint32_t v = stale ? 0u : __ldg(src32 + ((uint64_t)lz * C.lod_size[1] + ly) * row_words + i);
+      dst32[w] = v;
+      const uint32_t lo = v & 0xffffu, hi = v >> 16;
+      wmn = min(wmn, min(lo, hi));
+      wmx = max(wmx, max(lo, hi));
+    }
+    mn = (T)wmn; mx = (T)wmx; any = true;
+  } else
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     int l[3] = {(int)(i % bs[0]), (int)((i / bs[0]) % bs[1]), (int)(i / (bs[0] * bs[1]))};
     const uint32_t di = (uint32_t)l[0] + C.brick[0] * ((uint32_t)l[1] + C.brick[1] * (uint32_t)l[2]);
@@ -258,6 +307,10 @@ void launch_synth(void* dst, int kind, const uint32_t size[3], int dtype, uint32
 void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const uint32_t ds[3], int dtype,
                        cudaStream_t s) {
   const uint64_t n = (uint64_t)ds[0] * ds[1] * ds[2];
+  if (dtype == TVK_U16 && ss[0] % 4 == 0 && ss[1] % 2 == 0 && ss[2] % 2 == 0 && ss[0] > 1 && ss[1] > 1 && ss[2] > 1) {
+    downsample_u16x2_kernel<<<grid_for(n / 2, 256), 256, 0, s>>>((const uint2*)src, ss[0], ss[1], (uint32_t*)dst, ds[0], ds[1], ds[2]);
+    return;
+  }
   const int g = grid_for(n, 256);
   switch (dtype) {
     case TVK_U8: downsample_kernel<uint8_t><<<g, 256, 0, s>>>((const uint8_t*)src, ss[0], ss[1], ss[2], (uint8_t*)dst, ds[0], ds[1], ds[2]); break;
