@@ -387,7 +387,8 @@ def run_tvk(args, rank, world, local_rank):
                        "bricks_paged_in_setup": paged, "setup_s": round(setup_s, 2),
                        "samples_per_frame": step_samples / k, "rays_per_frame": float(np.mean(rays)),
                        "bricks_touched_per_frame": step_touched / k,
-                       "lane_utilisation": {"sampling": float(np.sum(samples)) / max(1.0, 32.0 * warp_it),
+                       "lane_utilisation": None if classic else
+                                           {"sampling": float(np.sum(samples)) / max(1.0, 32.0 * warp_it),
                                             "alive": alive_it / max(1.0, 32.0 * warp_it)}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which, "kernel": "classic_kernel" if classic else "raycast_kernel",

@@ -159,6 +159,39 @@ def test_small_pool_evicts_and_still_matches():
     r.Cleanup()
 
 
+def test_c5_shape_big_bricks_streamed_from_the_host():
+    """BASELINE configs[4] in miniature: u8 volume in 128^3 bricks (inner 124, 2 MiB each) that never sit on the
+    device as a whole -- the host source (Dataset::GetBrick stand-in) is asked brick by brick through the pinned
+    double-buffered staging path, and the pool holds only 6 of the 21 bricks, so the frame converges over 5 paging
+    subframes with eviction (12 bricks paged).  Page table, paging count and the float image equal the oracle's."""
+    s = Scene(kind=synth.V_NOISE, size=(250, 200, 180), dtype=orc.U8, brick=128, overlap=2, width=320, height=400,
+              rotation=golden_scenes.ROT, translation=tb.translation(0, 0, 0.3), pool_size=(384, 256, 128),
+              tf_center=0.25, tf_inv_gradient=0.3)
+    assert s.octree.total_bricks == 21
+    ref = s.oracle_render(max_subframes=128)
+    assert ref["paged"] > 6 and ref["subframes"] >= 4
+    asked = []
+    o = s.octree
+    r = tb.CudaGridLeaper(max_gpu_mem=s.max_gpu_mem, hash_table_size=s.hash_size(), brick_strategy=s.strategy)
+
+    def get_brick(x, y, z, lod):
+        asked.append((x, y, z, lod))
+        return o.brick(x, y, z, lod)
+
+    r.RegisterDataset(s.size, s.brick, s.overlap, s.dtype, o.minmax, get_brick, scale=s.scale,
+                      max_gradient_magnitude=s.max_grad)
+    r.Set1DTrans(s.tf1d); r.Set2DTrans(s.tf2d); r.SetRendermode(s.mode); r.SetUseLighting(s.lighting)
+    r.Resize(s.width, s.height); r.SetRotation(s.rotation); r.SetTranslation(s.translation)
+    r.CreateVolumePool(s._pool_size)
+    assert tuple(r.info().pool_capacity) == (3, 2, 1)
+    st = r.PaintUntilConverged(max_subframes=128)
+    assert st.converged and st.bricks_paged == ref["paged"] and len(asked) == st.bricks_paged + 1   # + UploadFirstBrick
+    assert np.array_equal(r.page_table(), ref["meta"])
+    check_images(r.ReadRGBA8(), ref["rgba8"])
+    assert np.array_equal(r.ReadRGBA32F(), ref["image"])
+    r.Cleanup()
+
+
 def test_view_change_reuses_resident_bricks_and_is_deterministic():
     s = golden_scenes.make("c3_bricked36_2d_lit")
     r = s.make_renderer("device")
