@@ -186,6 +186,15 @@ typedef struct {
 int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64_t uvf_file_version,
                          const float scale[3], const double* minmax, uint64_t n_minmax, double range_max,
                          float max_gradient_magnitude, tvk_octree_file_info* info);
+/* The same for a whole .uvf file: walks the container (magic, global header, data-block list; UVF.cpp:140-290,
+ * GlobalHeader.cpp:39-47, DataBlock.cpp:60-72), takes the `timestep`-th TOC block as the brick source and the
+ * `timestep`-th MaxMin block (if any) as the min/max table -- what UVFDataset::Open does for TOC-based files
+ * (IO/uvfDataset.cpp:640-700).  Legacy raster-data-block UVFs are refused (use tvk_set_volume with GetBrick). */
+int tvk_open_uvf(tvk_ctx* ctx, const char* path, uint64_t timestep, const float scale[3], double range_max,
+                 float max_gradient_magnitude, tvk_octree_file_info* info);
+/* host-only: container walk result; maxmin (4 doubles per brick, TOC order) is filled up to maxmin_cap bricks */
+int tvk_uvf_probe(const char* path, uint64_t timestep, uint64_t* toc_payload_offset, uint64_t* file_version,
+                  uint64_t* n_blocks, uint64_t* n_timesteps, double* maxmin, uint64_t maxmin_cap, uint64_t* n_maxmin);
 /* host-only helpers (no device, no ctx; errors via tvk_last_error(NULL)): parse header + table of contents,
  * read one brick (x fastest, own size incl. ghost, decoded) into host memory */
 int tvk_octree_file_probe(const char* path, uint64_t offset, uint64_t uvf_file_version, tvk_octree_file_info* info);

@@ -25,6 +25,13 @@ def volume(name):
     return synth.synth_volume(kind, size, dt, 0x5EED)
 
 
+# complete .uvf containers written by the reference's UVF / TOCBlock / Histogram1DDataBlock / MaxMinDataBlock /
+# KeyValuePairDataBlock classes (oracle/_ref/ref_uvf): name: (volume case, compression, layout, timesteps)
+UVF_CASES = {
+    "volume_u8_zlib.uvf": ("octree_u8_zlib_hilbert", 1, 2, 1),
+}
+
+
 if __name__ == "__main__":
     tool = os.path.join(ROOT, "oracle", "_ref", "ref_octree")
     out_dir = os.path.dirname(os.path.abspath(__file__))
@@ -34,4 +41,13 @@ if __name__ == "__main__":
         dst = os.path.join(out_dir, name + ".bin")
         subprocess.check_call([tool, raw, "/tmp/%s.dump" % name, dname, str(size[0]), str(size[1]), str(size[2]), str(brick),
                                str(ov), "0", "0", dst, str(comp), str(layout)], stdout=subprocess.DEVNULL)
+        print(name, os.path.getsize(dst), "bytes")
+    tool = os.path.join(ROOT, "oracle", "_ref", "ref_uvf")
+    for name, (case, comp, layout, ts) in UVF_CASES.items():
+        kind, size, dt, dname, brick, ov, _, _ = CASES[case]
+        raw = "/tmp/%s.raw" % case
+        volume(case).tofile(raw)
+        dst = os.path.join(out_dir, name)
+        subprocess.check_call([tool, raw, dst, dname, str(size[0]), str(size[1]), str(size[2]), str(brick), str(ov), str(comp),
+                               str(layout), str(ts)], stdout=subprocess.DEVNULL)
         print(name, os.path.getsize(dst), "bytes")

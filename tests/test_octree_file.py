@@ -209,6 +209,54 @@ def test_lz4_decoder_against_python_roundtrip(tmp_path):
         assert np.array_equal(octree_file.read_brick(str(p), 0, 0, 0, lod, info=info), b)
 
 
+# ------------------------------------------------------------------------------------------------ UVF container
+def check_uvf(path, vol, brick, overlap, dtype, timesteps=1):
+    o = orc.Octree(vol, brick, overlap)
+    for ts in range(timesteps):
+        u = octree_file.uvf_probe(path, ts)
+        assert u["file_version"] == 5 and u["n_timesteps"] == timesteps
+        assert u["n_blocks"] >= 2 * timesteps + 1                 # TOC + MaxMin per timestep (+ histogram), key/value block
+        # the MaxMin block is the oracle's (= the reference converter's BrickStatVec) min/max table, TOC order
+        assert u["maxmin"].shape == (o.total_bricks, 4)
+        assert np.array_equal(u["maxmin"], o.minmax)
+        info = octree_file.probe(path, offset=u["toc_payload_offset"], uvf_file_version=u["file_version"])
+        assert info.brick_count == o.total_bricks and info.dtype == dtype
+        for key in list(o.iter_bricks())[::3]:
+            got = octree_file.read_brick(path, *key, info=info, offset=u["toc_payload_offset"])
+            assert np.array_equal(got, o.brick(*key)), key
+    with pytest.raises(L.TvkError):
+        octree_file.uvf_probe(path, timesteps)                    # timestep out of range
+
+
+def test_golden_uvf_container():
+    case, comp, layout, ts = golden.UVF_CASES["volume_u8_zlib.uvf"]
+    kind, size, dt, _, brick, ov, _, _ = golden.CASES[case]
+    check_uvf(os.path.join(GOLDEN, "volume_u8_zlib.uvf"), golden.volume(case), brick, ov, dt, ts)
+
+
+def test_fresh_uvf_with_two_timesteps(tmp_path):
+    tool = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "ref_uvf")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/ref_uvf not built (reference tree absent)")
+    vol = synth.synth_volume(synth.V_NOISE, (44, 36, 28), orc.U16, 0x5EED)
+    raw = tmp_path / "in.raw"
+    vol.tofile(raw)
+    dst = tmp_path / "two.uvf"
+    subprocess.check_call([tool, str(raw), str(dst), "u16", "44", "36", "28", "16", "2", "3", "1", "2"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    check_uvf(str(dst), vol, 16, 2, orc.U16, timesteps=2)
+
+
+def test_uvf_walk_refuses_garbage(tmp_path):
+    src = open(os.path.join(GOLDEN, "volume_u8_zlib.uvf"), "rb").read()
+    for name, data in [("magic", b"UVF-DATB" + src[8:]), ("trunc", src[:70]), ("octree_only", open(os.path.join(
+            GOLDEN, "octree_u16_none.bin"), "rb").read())]:
+        p = tmp_path / (name + ".uvf")
+        p.write_bytes(data)
+        with pytest.raises(L.TvkError):
+            octree_file.uvf_probe(str(p))
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["octree_u16_lz4_morton", "octree_u8_zlib_hilbert", "octree_f32_none"])
@@ -243,3 +291,27 @@ def test_file_source_streams_into_the_pool(name):
     assert np.array_equal(r2.minmax(len(mm)), mm)
     for rr in (r, r2, dev):
         rr.Cleanup()
+
+
+@pytest.mark.gpu
+def test_uvf_file_renders_like_the_gpu_bricked_volume():
+    from scene import Scene
+    case, comp, layout, ts = golden.UVF_CASES["volume_u8_zlib.uvf"]
+    kind, size, dt, _, brick, ov, _, _ = golden.CASES[case]
+    s = Scene(kind=kind, size=size, dtype=dt, brick=brick, overlap=ov, width=72, height=56, lighting=True,
+              rotation=(tb.rotation_y(30.0) @ tb.rotation_x(20.0)).astype(np.float32), tf_center=0.25,
+              tf_inv_gradient=0.3, seed=0x5EED)
+    dev = s.make_renderer("device")
+    dev.PaintUntilConverged()
+    r = tb.CudaGridLeaper(max_gpu_mem=s.max_gpu_mem, hash_table_size=s.hash_size(), brick_strategy=s.strategy)
+    info = r.OpenUVF(os.path.join(GOLDEN, "volume_u8_zlib.uvf"), max_gradient_magnitude=s.max_grad)
+    assert info.brick_count == s.octree.total_bricks and info.bricks_by_codec[1] > 0
+    n = r.info().total_bricks
+    assert np.array_equal(r.minmax(n), s.octree.minmax[:n])          # from the file's MaxMin block
+    r.Set1DTrans(s.tf1d); r.Set2DTrans(s.tf2d); r.SetRendermode(s.mode); r.SetUseLighting(s.lighting)
+    r.Resize(s.width, s.height); r.SetRotation(s.rotation)
+    r.CreateVolumePool(s._pool_size)
+    assert r.PaintUntilConverged().converged
+    assert np.array_equal(r.ReadRGBA32F(), dev.ReadRGBA32F())
+    assert np.array_equal(r.page_table(), dev.page_table())
+    r.Cleanup(); dev.Cleanup()

@@ -91,6 +91,9 @@ SIGNATURES = {
                                    C.c_double, C.c_float]),
     "tvk_open_octree_file": (C.c_int, [P, C.c_char_p, C.c_uint64, C.c_uint64, P, P, C.c_uint64, C.c_double, C.c_float,
                                        C.POINTER(OctreeFileInfo)]),
+    "tvk_open_uvf": (C.c_int, [P, C.c_char_p, C.c_uint64, P, C.c_double, C.c_float, C.POINTER(OctreeFileInfo)]),
+    "tvk_uvf_probe": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "tvk_octree_file_probe": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(OctreeFileInfo)]),
     "tvk_octree_file_read_brick": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                              C.c_uint32, P, C.c_size_t, u32x3]),

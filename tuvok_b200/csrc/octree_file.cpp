@@ -155,6 +155,64 @@ void OctreeFile::brick_size(uint32_t x, uint32_t y, uint32_t z, uint32_t lod, ui
   }
 }
 
+bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out) {
+  *out = UvfScan();
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0) { out->error = std::string("cannot open ") + path; return false; }
+  struct stat st;
+  fstat(fd, &st);
+  const uint64_t fsize = (uint64_t)st.st_size;
+  char magic[8] = {0};
+  bool ok = pread_all(fd, magic, 8, 0) && std::memcmp(magic, "UVF-DATA", 8) == 0;
+  if (!ok) { out->error = "not a UVF file (magic)"; ::close(fd); return false; }
+  Cursor c{fd, 8};
+  const uint8_t big_endian = c.get<uint8_t>();
+  out->file_version = c.get<uint64_t>();
+  c.get<uint64_t>();                                   // checksum semantics
+  const uint64_t cs_len = c.get<uint64_t>();
+  if (!c.ok || big_endian || cs_len > 1024) { out->error = big_endian ? "big-endian UVF files are not supported" : "corrupt global header"; ::close(fd); return false; }
+  c.pos += cs_len;
+  const uint64_t to_first = c.get<uint64_t>();
+  uint64_t off = c.pos + to_first;                     // GlobalHeader::GetDataPos
+  uint64_t toc_seen = 0, mm_seen = 0;
+  for (;;) {
+    if (off + 32 > fsize) { out->error = "data block list runs past the end of the file"; ::close(fd); return false; }
+    Cursor b{fd, off};
+    const uint64_t id_len = b.get<uint64_t>();
+    if (id_len > 65536) { out->error = "corrupt data block header"; ::close(fd); return false; }
+    b.pos += id_len;
+    const uint64_t semantics = b.get<uint64_t>();
+    b.get<uint64_t>();                                 // compression scheme of the block (none is ever written)
+    const uint64_t to_next = b.get<uint64_t>();
+    if (!b.ok) { out->error = "short read in a data block header"; ::close(fd); return false; }
+    out->n_blocks++;
+    if (semantics == 9) {                              // UVFTables::BS_TOC_BLOCK
+      if (toc_seen == timestep) out->toc_payload_offset = b.pos;
+      toc_seen++;
+    } else if (semantics == 7) {                       // UVFTables::BS_MAXMIN_VALUES (MaxMinDataBlock.cpp:67-95)
+      if (mm_seen == timestep) {
+        const uint64_t n = b.get<uint64_t>(), comps = b.get<uint64_t>();
+        if (!b.ok || comps == 0 || comps > 16 || b.pos + n * comps * 32 > fsize) { out->error = "corrupt MaxMin block"; ::close(fd); return false; }
+        out->maxmin_components = comps;
+        std::vector<double> all((size_t)(n * comps * 4));
+        if (!pread_all(fd, all.data(), all.size() * 8, b.pos)) { out->error = "short read in the MaxMin block"; ::close(fd); return false; }
+        const uint64_t pick = comps == 4 ? 3 : 0;      // UVFDataset::MaxMinForKey, IO/uvfDataset.cpp:1183-1188
+        out->maxmin.resize((size_t)n * 4);
+        for (uint64_t i = 0; i < n; i++)
+          std::memcpy(&out->maxmin[(size_t)i * 4], &all[(size_t)((i * comps + pick) * 4)], 32);
+        out->have_maxmin = true;
+      }
+      mm_seen++;
+    }
+    if (to_next == 0) break;
+    off += to_next;
+  }
+  ::close(fd);
+  out->n_toc = toc_seen;
+  if (toc_seen <= timestep) { out->error = toc_seen ? "timestep out of range" : "no TOC block (legacy raster-data UVF: use the generic brick source)"; return false; }
+  return true;
+}
+
 // LZ4 block format: token (literal length | match length), literals, 16-bit offset, 255-continued lengths.
 // The block ends with literals only.
 bool lz4_block_decode(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len) {

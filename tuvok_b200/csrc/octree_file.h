@@ -52,6 +52,20 @@ struct OctreeFile {
   bool read_brick(uint64_t index, size_t uncompressed_bytes, void* dst, size_t cap, std::string* err) const;
 };
 
+// UVF container walk (IO/UVF/UVF.cpp:140-290, GlobalHeader.cpp:39-47, DataBlock.cpp:60-72): magic "UVF-DATA", global
+// header, linked list of data blocks.  Finds the `timestep`-th TOC block (UVFTables::BS_TOC_BLOCK) and the
+// `timestep`-th MaxMin block (BS_MAXMIN_VALUES; UVFDataset pairs them by order, IO/uvfDataset.cpp:640-700).
+struct UvfScan {
+  uint64_t file_version = 0;
+  uint64_t toc_payload_offset = 0;   // byte offset of the ExtendedOctree header
+  uint64_t n_blocks = 0, n_toc = 0;
+  bool have_maxmin = false;
+  uint64_t maxmin_components = 0;
+  std::vector<double> maxmin;        // 4 doubles per brick (component 0; component 3 of RGBA data), TOC order
+  std::string error;
+};
+bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out);
+
 // LZ4 block format (the reference calls LZ4_decompress_fast: the decoder knows only the output size)
 bool lz4_block_decode(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len);
 

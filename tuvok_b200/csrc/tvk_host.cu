@@ -885,6 +885,30 @@ int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64
   return TVK_OK;
 }
 
+int tvk_open_uvf(tvk_ctx* ctx, const char* path, uint64_t timestep, const float scale[3], double range_max,
+                 float max_gradient_magnitude, tvk_octree_file_info* info) {
+  if (!ctx || !path) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  UvfScan sc;
+  if (!uvf_scan(path, timestep, &sc)) return fail(ctx, TVK_ERR_SOURCE, "%s: %s", path, sc.error.c_str());
+  return tvk_open_octree_file(ctx, path, sc.toc_payload_offset, sc.file_version, scale,
+                              sc.have_maxmin ? sc.maxmin.data() : nullptr, sc.maxmin.size() / 4, range_max,
+                              max_gradient_magnitude, info);
+}
+
+int tvk_uvf_probe(const char* path, uint64_t timestep, uint64_t* toc_payload_offset, uint64_t* file_version,
+                  uint64_t* n_blocks, uint64_t* n_timesteps, double* maxmin, uint64_t maxmin_cap, uint64_t* n_maxmin) {
+  if (!path) return TVK_ERR_INVALID;
+  UvfScan sc;
+  if (!uvf_scan(path, timestep, &sc)) { g_create_err = std::string(path) + ": " + sc.error; return TVK_ERR_SOURCE; }
+  if (toc_payload_offset) *toc_payload_offset = sc.toc_payload_offset;
+  if (file_version) *file_version = sc.file_version;
+  if (n_blocks) *n_blocks = sc.n_blocks;
+  if (n_timesteps) *n_timesteps = sc.n_toc;
+  if (n_maxmin) *n_maxmin = sc.maxmin.size() / 4;
+  if (maxmin && maxmin_cap) std::memcpy(maxmin, sc.maxmin.data(), std::min<size_t>(maxmin_cap, sc.maxmin.size() / 4) * 32);
+  return TVK_OK;
+}
+
 static void fill_file_info(const OctreeFile& g, tvk_octree_file_info* info) {
   std::memset(info, 0, sizeof(*info));
   for (int i = 0; i < 3; i++) {

@@ -34,3 +34,19 @@ def read_brick(path, x, y, z, lod, info=None, offset=0, uvf_file_version=5):
         raise L.TvkError(rc, (L.lib().tvk_last_error(None) or b"").decode())
     sx, sy, sz = (int(v) for v in size)
     return np.frombuffer(buf.tobytes(), _NP[info.dtype], sx * sy * sz).reshape(sz, sy, sx)
+
+
+def uvf_probe(path, timestep=0):
+    """Walk a .uvf container: dict(toc_payload_offset, file_version, n_blocks, n_timesteps, maxmin (n, 4) or None)."""
+    off, ver, nb, nt, nm = (C.c_uint64() for _ in range(5))
+    lib = L.lib()
+    rc = lib.tvk_uvf_probe(os.fsencode(path), int(timestep), C.byref(off), C.byref(ver), C.byref(nb), C.byref(nt), None, 0,
+                           C.byref(nm))
+    if rc:
+        raise L.TvkError(rc, (lib.tvk_last_error(None) or b"").decode())
+    mm = None
+    if nm.value:
+        mm = np.zeros((nm.value, 4), np.float64)
+        lib.tvk_uvf_probe(os.fsencode(path), int(timestep), None, None, None, None, mm.ctypes.data_as(C.c_void_p),
+                          nm.value, None)
+    return dict(toc_payload_offset=off.value, file_version=ver.value, n_blocks=nb.value, n_timesteps=nt.value, maxmin=mm)

@@ -126,6 +126,16 @@ class CudaGridLeaper:
         self._dirty = True
         return info
 
+    def OpenUVF(self, path, timestep=0, scale=None, range_max=0.0, max_gradient_magnitude=0.0):
+        """UVFDataset stand-in: walk the .uvf container and stream the `timestep`-th TOC block (with its MaxMin block)."""
+        info = L.OctreeFileInfo()
+        sc = L.f32x3(*scale) if scale is not None else None
+        self._ck(self._lib.tvk_open_uvf(self._h, os.fsencode(path), int(timestep),
+                                        C.cast(sc, C.c_void_p) if sc is not None else None, float(range_max),
+                                        float(max_gradient_magnitude), C.byref(info)))
+        self._dirty = True
+        return info
+
     def RegisterDataset(self, domain_size, max_brick_size, overlap, dtype, minmax, get_brick, scale=(1, 1, 1),
                         range_max=0.0, max_gradient_magnitude=0.0):
         """LinearIndexDataset stand-in: `get_brick(x, y, z, lod) -> ndarray [sz, sy, sx]` plays
