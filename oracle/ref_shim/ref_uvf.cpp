@@ -2,7 +2,8 @@
 // FlatDataToBrickedLOD = ExtendedOctreeConverter, Histogram1DDataBlock, MaxMinDataBlock, KeyValuePairDataBlock;
 // compiled in place from /root/reference by oracle/Makefile) the way RAWConverter::ConvertRAWDataset assembles one
 // (IO/RAWConverter.cpp:553-690): per timestep a TOC block, a 1D histogram block and a MaxMin block, then a
-// key/value block.  The product's container walk (tvk_open_uvf) is tested on these files.  Test infrastructure only.
+// key/value block.  A 1D and a 2D histogram block accompany every TOC block: UVFDataset only accepts files whose block
+// counts match (IO/uvfDataset.cpp:484-497).  The 2D histogram is computed with 16 value bins to keep the file small.  The product's container walk (tvk_open_uvf) is tested on these files.  Test infrastructure only.
 //
 // usage: ref_uvf <in.raw> <out.uvf> <dtype u8|u16|f32> X Y Z brick overlap compression(0|1|3) layout(0..3) [timesteps]
 #include <cstdio>
@@ -16,6 +17,7 @@
 #include "IO/UVF/TOCBlock.h"
 #include "IO/UVF/MaxMinDataBlock.h"
 #include "IO/UVF/Histogram1DDataBlock.h"
+#include "IO/UVF/Histogram2DDataBlock.h"
 #include "IO/UVF/KeyValuePairDataBlock.h"
 #include "DebugOut/AbstrDebugOut.h"
 
@@ -47,6 +49,7 @@ int main(int argc, char** argv) {
   std::vector<std::shared_ptr<TOCBlock>> tocs;
   std::vector<std::shared_ptr<MaxMinDataBlock>> mms;
   std::vector<std::shared_ptr<Histogram1DDataBlock>> hists;
+  std::vector<std::shared_ptr<Histogram2DDataBlock>> hists2;
   for (int ts = 0; ts < timesteps; ts++) {
     std::shared_ptr<MaxMinDataBlock> mm(new MaxMinDataBlock(1));
     std::shared_ptr<TOCBlock> toc(new TOCBlock(UVF::ms_ulReaderVersion));
@@ -61,7 +64,12 @@ int main(int argc, char** argv) {
     uvf.AddDataBlock(toc);
     if (dt != "f32") {
       std::shared_ptr<Histogram1DDataBlock> h(new Histogram1DDataBlock());
-      if (h->Compute(toc.get(), 0)) { uvf.AddDataBlock(h); hists.push_back(h); }
+      if (h->Compute(toc.get(), 0)) {
+        uvf.AddDataBlock(h);
+        hists.push_back(h);
+        std::shared_ptr<Histogram2DDataBlock> h2(new Histogram2DDataBlock());
+        if (h2->Compute(toc.get(), 0, 16, mm->GetGlobalValue().maxScalar)) { uvf.AddDataBlock(h2); hists2.push_back(h2); }
+      }
     }
     uvf.AddDataBlock(mm);
     tocs.push_back(toc); mms.push_back(mm);
