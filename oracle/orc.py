@@ -124,7 +124,10 @@ def lib():
         "orc_ray_setup": (None, [C.POINTER(RenderParams), P, P, P]),
         "orc_raycast": (None, [C.POINTER(RenderParams)] + [P] * 12 + [C.POINTER(RenderStats), C.c_int]),
         "orc_iso_compose": (None, [C.POINTER(RenderParams), P, P, P]),
+        "orc_ray_exit_eye": (None, [P, P]),
+        "orc_uniforms": (None, [P, P]),
         "orc_hash_decode": (C.c_uint32, [P, C.c_uint32, u32x3, P]),
+        "orc_hash_insert": (C.c_uint32, [P, C.c_uint32, C.c_uint32, u32x3, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
         "orc_rgba8": (None, [P, C.c_uint64, P]),
         "orc_composite_over": (None, [P, P, C.c_uint64, P]),
         "orc_classic_lod": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32]),
@@ -331,6 +334,20 @@ def ray_setup(params):
     return entry, exit_, cov
 
 
+def ray_exit_eye(params):
+    out = np.zeros((params.height * params.width, 3), np.float32)
+    lib().orc_ray_exit_eye(C.byref(params), _p(out))
+    return out
+
+
+def uniforms(params):
+    o = np.zeros(68, np.float32)
+    lib().orc_uniforms(C.byref(params), _p(o))
+    return dict(emm=o[:16].copy(), domain_scale=o[16:19].copy(), ambient=o[19:22].copy(), diffuse=o[22:25].copy(),
+                specular=o[25:28].copy(), light_dir_m=o[28:31].copy(), eye_m=o[31:34].copy(), lzwse=float(o[34]),
+                norm=float(o[35]), model_to_eye=o[36:52].copy(), mv_inv=o[52:68].copy())
+
+
 def raycast(params, pool_atlas, meta, tf, ray_start, start_color, exit_, covered, hash_table=None, threads=1):
     n = params.width * params.height
     outs = [np.zeros((n, 4), np.float32) for _ in range(4)]
@@ -348,6 +365,11 @@ def iso_compose(params, hit_pos, hit_normal):
     out = np.zeros_like(hit_pos)
     lib().orc_iso_compose(C.byref(params), _p(hit_pos), _p(hit_normal), _p(out))
     return out
+
+
+def hash_insert(hash_table, rehash_count, finest_layout, x, y, z, lod):
+    """One miss report into the u32 table (in place); returns the rehash count used."""
+    return lib().orc_hash_insert(_p(hash_table), len(hash_table), rehash_count, u32x3(*finest_layout), x, y, z, lod)
 
 
 def hash_decode(hash_table, finest_layout):

@@ -239,6 +239,49 @@ void orc_ray_setup(const orc_render_params* p, float* entry, float* exit_, uint8
     }
 }
 
+/* For tests/glsl_ref.py (the reference GLSL executed on the CPU needs the SAME inputs): the eye-space position of the
+ * back-face fragment of every covered pixel (what the rasteriser interpolates into vPosInViewCoords) ... */
+void orc_ray_exit_eye(const orc_render_params* p, float* exit_eye /* w*h*3 */) {
+  uni u;
+  derive(p, &u);
+  for (uint32_t y = 0; y < p->height; y++)
+    for (uint32_t x = 0; x < p->width; x++) {
+      size_t i = (size_t)y * p->width + x;
+      v4 e, q;
+      exit_eye[3 * i] = exit_eye[3 * i + 1] = exit_eye[3 * i + 2] = 0.0f;
+      if (!ray_setup_px(p, &u, x, y, &e, &q)) continue;
+      float nx = ((float)x + 0.5f) / (float)p->width * 2.0f - 1.0f;
+      float ny = ((float)y + 0.5f) / (float)p->height * 2.0f - 1.0f;
+      v4 nr = xform4(u.inv_proj, nx, ny, -1.0f, 1.0f);
+      v3 pn = V3(nr.x / nr.w, nr.y / nr.w, nr.z / nr.w);
+      float s = q.w / pn.z;                 /* exit.w = (pn * s_out).z */
+      (void)s;
+      /* recompute s_out exactly as ray_setup_px did */
+      v4 o4 = xform4(u.emm, 0.0f, 0.0f, 0.0f, 1.0f), n4 = xform4(u.emm, pn.x, pn.y, pn.z, 1.0f);
+      float o[3] = {o4.x, o4.y, o4.z}, d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
+      const float zero[3] = {0.0f, 0.0f, 0.0f}, one[3] = {1.0f, 1.0f, 1.0f};
+      float s_in, s_out;
+      slab3(o, d, zero, one, &s_in, &s_out);
+      v3 px_ = scl3(pn, s_out);
+      exit_eye[3 * i] = px_.x; exit_eye[3 * i + 1] = px_.y; exit_eye[3 * i + 2] = px_.z;
+    }
+}
+/* ... and the uniforms GLGridLeaper::SetupRaycastShader would upload (GLGridLeaper.cpp:690-752):
+ * out[0..15] mEyeToModel, [16..18] vDomainScale, [19..21] ambient, [22..24] diffuse, [25..27] specular (rgb * w),
+ * [28..30] vModelSpaceLightDir, [31..33] vModelSpaceEyePos, [34] fLevelZeroWorldSpaceError, [35] unorm factor,
+ * [36..51] mModelToEye, [52..67] inverse(modelView) */
+void orc_uniforms(const orc_render_params* p, float* out) {
+  uni u;
+  derive(p, &u);
+  memcpy(out, u.emm, 64);
+  const v3* v[6] = {&u.domain_scale, &u.light_a, &u.light_d, &u.light_s, &u.light_dir_m, &u.eye_m};
+  for (int i = 0; i < 6; i++) { out[16 + 3 * i] = v[i]->x; out[17 + 3 * i] = v[i]->y; out[18 + 3 * i] = v[i]->z; }
+  out[34] = u.lzwse;
+  out[35] = u.norm;
+  memcpy(out + 36, u.model_to_eye, 64);   /* mModelToEye */
+  memcpy(out + 52, u.mv_inv, 64);         /* inverse(modelView): mModelViewIT * v == column-vector product with it */
+}
+
 /* ------------------------------------------------------------------ */
 /* pool sampling                                                       */
 /* ------------------------------------------------------------------ */
@@ -739,6 +782,20 @@ void orc_iso_compose(const orc_render_params* p, const float* hit_pos, const flo
     o[2] = clampf(a.z + d.z * dl + s.z * sp, 0.0f, 1.0f);
     o[3] = 1.0f;
   }
+}
+
+/* one miss report outside a render pass (same arithmetic as report_missing above): returns the number of rehashes, or
+ * rehash_count when the probe chain is exhausted -- the return value of the generated GLSL `Hash(uvec4)` */
+uint32_t orc_hash_insert(uint32_t* hash, uint32_t hash_size, uint32_t rehash_count, const uint32_t f[3], uint32_t x,
+                         uint32_t y, uint32_t z, uint32_t lod) {
+  uint32_t ser = 1 + x + y * f[0] + z * f[0] * f[1] + lod * f[0] * f[1] * f[2];
+  uint32_t rehash = 0;
+  do {
+    uint32_t h = (ser + rehash) % hash_size;
+    uint32_t old = __sync_val_compare_and_swap(&hash[h], 0u, ser);
+    if (old == 0 || old == ser) return rehash;
+  } while (++rehash < rehash_count);
+  return rehash_count;
 }
 
 uint32_t orc_hash_decode(const uint32_t* hash, uint32_t hash_size, const uint32_t f[3], uint32_t* out) {

@@ -18,7 +18,7 @@ struct Tex {
 };
 std::map<GLuint, Tex> g_tex;
 GLuint g_next = 1, g_bound = 0;
-int g_max3d = 2048;
+int g_max3d = 2048, g_max2d = 16384;
 
 uint32_t texel_bytes(GLenum format, GLenum type) {
   uint32_t comps = 1;
@@ -37,6 +37,8 @@ uint32_t texel_bytes(GLenum format, GLenum type) {
 }
 
 void GLAPIENTRY nullActiveTexture(GLenum) {}
+void GLAPIENTRY nullBindImageTexture(GLuint, GLuint, GLint, GLboolean, GLint, GLenum, GLenum) {}
+void GLAPIENTRY nullMemoryBarrier(GLbitfield) {}
 
 void GLAPIENTRY recTexImage3D(GLenum, GLint, GLint, GLsizei w, GLsizei h, GLsizei d, GLint, GLenum format,
                               GLenum type, const void* pixels) {
@@ -65,6 +67,8 @@ void GLAPIENTRY recTexSubImage3D(GLenum, GLint, GLint x, GLint y, GLint z, GLsiz
 extern "C" {
 PFNGLACTIVETEXTUREPROC __glewActiveTexture = nullActiveTexture;
 PFNGLTEXIMAGE3DPROC __glewTexImage3D = recTexImage3D;
+PFNGLBINDIMAGETEXTUREPROC __glewBindImageTexture = nullBindImageTexture;
+PFNGLMEMORYBARRIERPROC __glewMemoryBarrier = nullMemoryBarrier;
 PFNGLTEXSUBIMAGE3DPROC __glewTexSubImage3D = recTexSubImage3D;
 
 void GLAPIENTRY glBindTexture(GLenum, GLuint id) { g_bound = id; }
@@ -72,7 +76,21 @@ void GLAPIENTRY glDeleteTextures(GLsizei n, const GLuint* ids) { for (GLsizei i 
 void GLAPIENTRY glGenTextures(GLsizei n, GLuint* ids) { for (GLsizei i = 0; i < n; i++) { ids[i] = g_next++; g_tex[ids[i]]; } }
 GLenum GLAPIENTRY glGetError(void) { return GL_NO_ERROR; }
 void GLAPIENTRY glGetIntegerv(GLenum pname, GLint* v) {
-  *v = (pname == GL_MAX_3D_TEXTURE_SIZE_EXT) ? g_max3d : (pname == GL_TEXTURE_BINDING_3D) ? GLint(g_bound) : 0;
+  *v = (pname == GL_MAX_3D_TEXTURE_SIZE_EXT) ? g_max3d : (pname == GL_MAX_TEXTURE_SIZE) ? g_max2d
+     : (pname == GL_TEXTURE_BINDING_3D || pname == GL_TEXTURE_BINDING_2D || pname == GL_TEXTURE_BINDING_1D) ? GLint(g_bound) : 0;
+}
+// 1D / 2D textures (the miss-report hash table) live in the same store with d = 1 (and h = 1)
+void GLAPIENTRY glTexImage2D(GLenum, GLint, GLint, GLsizei w, GLsizei h, GLint, GLenum format, GLenum type, const void* px) {
+  recTexImage3D(0, 0, 0, w, h, 1, 0, format, type, px);
+}
+void GLAPIENTRY glTexImage1D(GLenum, GLint, GLint, GLsizei w, GLint, GLenum format, GLenum type, const void* px) {
+  recTexImage3D(0, 0, 0, w, 1, 1, 0, format, type, px);
+}
+void GLAPIENTRY glTexSubImage2D(GLenum, GLint, GLint x, GLint y, GLsizei w, GLsizei h, GLenum format, GLenum type, const void* px) {
+  recTexSubImage3D(0, 0, x, y, 0, w, h, 1, format, type, px);
+}
+void GLAPIENTRY glTexSubImage1D(GLenum, GLint, GLint x, GLsizei w, GLenum format, GLenum type, const void* px) {
+  recTexSubImage3D(0, 0, x, 0, 0, w, 1, 1, format, type, px);
 }
 void GLAPIENTRY glGetTexImage(GLenum, GLint, GLenum, GLenum, void* dst) {
   const Tex& t = g_tex[g_bound];
@@ -83,6 +101,11 @@ void GLAPIENTRY glTexParameteri(GLenum, GLenum, GLint) {}
 }
 
 void glnull_set_max_3d(int v) { g_max3d = v; }
+void glnull_set_max_2d(int v) { g_max2d = v; }
+void glnull_write_texture(unsigned id, const void* src, size_t bytes) {
+  auto it = g_tex.find(id);
+  if (it != g_tex.end()) memcpy(it->second.data.data(), src, bytes < it->second.data.size() ? bytes : it->second.data.size());
+}
 const uint8_t* glnull_texture(unsigned id, uint32_t dim[3], uint32_t* bytes_per_texel) {
   auto it = g_tex.find(id);
   if (it == g_tex.end()) return nullptr;

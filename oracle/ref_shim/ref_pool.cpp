@@ -15,7 +15,7 @@
 //   minmax <file>  f64[4] per brick, TOC order
 //   bricks <file>  optional: tightly packed voxels of every brick, TOC order
 //   create                                     (constructs the pool, DM_SYNC)
-//   first | vis1d a b | vis2d a b c d | visiso v | upload n (x y z lod)*n | dump
+//   first | vis1d a b | vis2d a b c d | visiso v | upload n (x y z lod)*n | dump | glsl <strategy 0..3> <out file>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -205,6 +205,12 @@ int main(int argc, char** argv) {
       for (uint32_t i = 0; i < n; i++) ls >> ids[i].x >> ids[i].y >> ids[i].z >> ids[i].w;
       const uint32_t paged = pool->UploadBricks(ids, false);
       fprintf(out, "paged %u\n", paged);
+    } else if (op == "glsl") {
+      // the GLSL the pool generates for the shader side (GetBrick, ComputeLOD, TransformToPoolSpace, samplePool, ...)
+      int strategy; std::string path; ls >> strategy >> path;
+      const std::string g = pool->GetShaderFragment(0, 1, (GLVolumePool::MissingBrickStrategy)strategy, "");
+      std::ofstream f(path); f << g; f.close();
+      fprintf(out, "glsl %zu\n", g.size());
     } else if (op == "dump") {
       uint32_t dim[3], bpt;
       const uint32_t* tex = reinterpret_cast<const uint32_t*>(glnull_texture(pool->MetaTex(), dim, &bpt));

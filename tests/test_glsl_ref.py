@@ -1,0 +1,143 @@
+"""Image-side parity pinned to the reference's OWN shader code: the GridLeaper fragment shader
+(Shaders/GLGridLeaper-blend.glsl + Method-{1D,1D-L,2D,2D-L} + GradientTools + lighting + Compositing), the GLSL generated
+by the unmodified GLVolumePool (GetBrick page-table walk, ComputeLOD, TransformToPoolSpace, samplePool) and by
+GLHashTable (miss reports) are compiled as C++ against oracle/glsl/glsl_emu.h (a minimal GLSL emulation with IEEE fp32
+semantics) and EXECUTED per fragment (tests/glsl_ref.py) -- on the same page table, pool atlas, transfer function, ray
+entry points and uniforms as the oracle restatement (oracle/orc_render.c), which the CUDA kernel is compared with bit
+for bit on the GPU.
+
+What must agree: every brick decision and miss report (integer, exact), the sample counts, and the float images to
+rounding (the shader text compiled by g++ evaluates `a*b+c` unfused where the contract fuses the compositing update and
+takes gradient taps through texture coordinates instead of texel offsets): |delta| of the RGBA32F image <= 5e-5 on >= 99 %
+of the pixels (a few early-terminated rays stop one sample apart: <= 4e-3), RGBA8 images identical or 1/255 apart -- far inside the 2/255 / 45 dB budget of BASELINE.json."""
+import numpy as np
+import pytest
+
+import glsl_ref
+import golden_scenes
+import tuvok_b200 as tb
+from oracle import orc
+from scene import Scene, image_diff
+from tuvok_b200 import synth
+
+pytestmark = pytest.mark.skipif(not glsl_ref.available(), reason="reference shaders / oracle/_ref tools absent")
+
+
+def execute_reference_glsl(tmp_path, s, state, ray_start, start_color, meta):
+    p = state["params"]
+    o = s.octree
+    pool = state["pool"]
+    pool_glsl, hash_glsl = glsl_ref.generated_glsl(tmp_path, o, s.size, s.brick[0], s.overlap, s.dtype, pool.pool_size,
+                                                   s.strategy, o.brick_count(0), p.hash_size, p.rehash_count)
+    exe = glsl_ref.build(tmp_path, s.mode, s.lighting, pool_glsl, hash_glsl)
+    u = orc.uniforms(p)
+    return glsl_ref.run(exe, tmp_path, p, u["emm"], orc.ray_exit_eye(p), ray_start, start_color, state["covered"], meta,
+                        pool.meta_dim, state["atlas"], state["tf"], u["norm"], u, u["domain_scale"])
+
+
+SCENES = ["c1_single_brick_1d", "c2_bricked36_1d_ert", "c3_bricked36_2d_lit", "ragged_1d_lit", "inside_aniso_2d"]
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_converged_frame_matches_executed_reference_shader(tmp_path, name):
+    s = golden_scenes.make(name)
+    st = s.oracle_render()                                    # paging loop until converged
+    p = st["params"]
+    zeros = np.zeros_like(st["entry"])
+    hash_o = np.zeros(p.hash_size, np.uint32)
+    outs, rs = orc.raycast(p, st["atlas"], st["meta"], st["tf"], st["entry"], zeros, st["exit"], st["covered"], hash_o, 1)
+    g0, g1, g2, hash_g = execute_reference_glsl(tmp_path, s, st, st["entry"], zeros, st["meta"])
+    assert not hash_g.any() and not hash_o.any()              # converged: nothing is reported missing
+    a, b = outs[0].reshape(-1, 4), g0
+    d = np.abs(a - b).max(axis=1)
+    # rounding-level agreement everywhere, except where early ray termination (alpha > 0.99) trips one sample apart
+    # because the shader text's compositing update is unfused: such a pixel differs by at most that sample's
+    # contribution (< 0.01 of a colour), and there are only a handful of them
+    assert float(d.max()) <= 4e-3 and float((d > 5e-5).mean()) <= 0.01, (float(d.max()), float((d > 5e-5).mean()))
+    print("executed reference GLSL vs oracle: max |d| %.3g, pixels > 5e-5: %d of %d" % (d.max(), int((d > 5e-5).sum()), len(d)))
+    mx, psnr = image_diff(orc.rgba8(a.reshape(s.height, s.width, 4)), orc.rgba8(b.reshape(s.height, s.width, 4)))
+    assert mx <= 1 and psnr >= 60.0
+    # resume buffers of a converged frame: every covered ray finished (w = 1000), resume colour = final colour
+    cov = st["covered"].reshape(-1).astype(bool)
+    assert (g2[cov, 3] == 1000.0).all() and np.array_equal(outs[2].reshape(-1, 4)[:, 3], g2[:, 3])
+    assert float(np.abs(outs[1].reshape(-1, 4) - g1).max()) <= 4e-3
+    assert (b[~cov] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["c2_bricked36_1d_ert", "c3_bricked36_2d_lit", "inside_aniso_2d"])
+def test_first_pass_miss_reports_and_resume_state(tmp_path, name):
+    """Only the coarsest brick is resident: every ray falls back to it and reports what it misses.  The miss table
+    (integer, sequential execution in pixel order on both sides) must be IDENTICAL, and so must the resume positions'
+    bookkeeping (which rays stopped being optimal and where)."""
+    s = golden_scenes.make(name, hash_size=509)
+    pool, _ = s.oracle_pool()
+    p = s.oracle_params(pool)
+    o = s.octree
+    ps = pool.pool_size
+    atlas = np.zeros((ps[2], ps[1], ps[0]), orc.NP_DTYPE[s.dtype])
+    cap = pool.capacity
+    last = cap[0] * cap[1] * cap[2] - 1
+    b = o.brick(0, 0, 0, pool.lod_count - 1)
+    sx, sy, sz = last % cap[0], (last // cap[0]) % cap[1], last // (cap[0] * cap[1])
+    atlas[sz * s.brick[2]:sz * s.brick[2] + b.shape[0], sy * s.brick[1]:sy * s.brick[1] + b.shape[1],
+          sx * s.brick[0]:sx * s.brick[0] + b.shape[2]] = b
+    entry, exit_, cov = orc.ray_setup(p)
+    zeros = np.zeros_like(entry)
+    hash_o = np.zeros(p.hash_size, np.uint32)
+    tf = s.tf_bytes()
+    outs, rs = orc.raycast(p, atlas, pool.meta, tf, entry, zeros, exit_, cov, hash_o, 1)
+    state = dict(params=p, pool=pool, atlas=atlas, tf=tf, covered=cov)
+    g0, g1, g2, hash_g = execute_reference_glsl(tmp_path, s, state, entry, zeros, pool.meta)
+    assert hash_o.any()
+    assert np.array_equal(hash_g, hash_o)                                     # miss reports: bit-exact
+    assert np.array_equal(orc.hash_decode(hash_g, o.brick_count(0)), orc.hash_decode(hash_o, o.brick_count(0)))
+    o2, o1, o0 = outs[2].reshape(-1, 4), outs[1].reshape(-1, 4), outs[0].reshape(-1, 4)
+    assert np.array_equal(o2[:, 3] == 1000.0, g2[:, 3] == 1000.0)             # the same rays ended optimally
+    assert float(np.abs(o2 - g2).max()) <= 1e-5                               # resume positions
+    assert float(np.abs(o0 - g0).max()) <= 2e-5 and float(np.abs(o1 - g1).max()) <= 2e-5
+
+
+def test_sample_rate_and_ragged_bricks(tmp_path):
+    """sampleRateModifier != 1 (opacity correction through pow) on ragged u8 bricks with lighting."""
+    s = golden_scenes.make("ragged_1d_lit", sample_rate=1.7)
+    st = s.oracle_render()
+    p = st["params"]
+    zeros = np.zeros_like(st["entry"])
+    outs, _ = orc.raycast(p, st["atlas"], st["meta"], st["tf"], st["entry"], zeros, st["exit"], st["covered"], None, 1)
+    g0, _, _, _ = execute_reference_glsl(tmp_path, s, st, st["entry"], zeros, st["meta"])
+    assert float(np.abs(outs[0].reshape(-1, 4) - g0).max()) <= 5e-5
+
+
+def test_isosurface_shader_and_deferred_compose(tmp_path):
+    """GLGridLeaper-iso.glsl (first hit, 5-step refinement, eye-space hit position, normal through mModelViewIT, resume
+    encoding) and Compose-FS.glsl (deferred lighting) executed vs the oracle's restatement, f32 volume."""
+    s = golden_scenes.make("c4_f32_iso")
+    st = s.oracle_render()
+    p = st["params"]
+    o = s.octree
+    pool = st["pool"]
+    zeros = np.zeros_like(st["entry"])
+    outs, _ = orc.raycast(p, st["atlas"], st["meta"], st["tf"], st["entry"], zeros, st["exit"], st["covered"], None, 1)
+    pool_glsl, hash_glsl = glsl_ref.generated_glsl(tmp_path, o, s.size, s.brick[0], s.overlap, s.dtype, pool.pool_size,
+                                                   s.strategy, o.brick_count(0), p.hash_size, p.rehash_count)
+    exe = glsl_ref.build_iso(tmp_path, pool_glsl, hash_glsl)
+    u = orc.uniforms(p)
+    g, hash_g = glsl_ref.run_iso(exe, tmp_path, p, u, orc.ray_exit_eye(p), st["entry"], zeros, st["covered"], st["meta"],
+                                 pool.meta_dim, st["atlas"])
+    assert not hash_g.any()
+    hit_o, nrm_o = outs[0].reshape(-1, 4), outs[1].reshape(-1, 4)
+    assert np.array_equal(hit_o[:, 3] != 0, g[0][:, 3] != 0)                  # the same rays hit the surface
+    assert (hit_o[:, 3] != 0).sum() > 300
+    assert float(np.abs(hit_o - g[0]).max()) <= 2e-5                          # eye-space hit positions
+    assert float(np.abs(nrm_o - g[1]).max()) <= 2e-4                          # normals (normalised gradients)
+    assert np.array_equal(outs[2].reshape(-1, 4)[:, 3], g[2][:, 3])           # resume encoding 1000 / 499 + alpha
+    # deferred compose: the reference shader on the REFERENCE shader's buffers vs the oracle on the oracle's
+    cexe = glsl_ref.build_compose(tmp_path)
+    amb = [p.ambient[i] * p.ambient[3] for i in range(3)]
+    dif = [p.diffuse[i] * p.diffuse[3] * p.iso_color[i] for i in range(3)]
+    spe = [p.specular[i] * p.specular[3] for i in range(3)]
+    img_g = glsl_ref.run_compose(cexe, tmp_path, s.width, s.height, amb, dif, spe, list(p.light_dir), g[0], g[1])
+    img_o = orc.iso_compose(p, outs[0], outs[1]).reshape(-1, 4)
+    assert float(np.abs(img_o - img_g).max()) <= 2e-4
+    mx, psnr = image_diff(orc.rgba8(img_o.reshape(s.height, s.width, 4)), orc.rgba8(img_g.reshape(s.height, s.width, 4)))
+    assert mx <= 1 and psnr >= 60.0
