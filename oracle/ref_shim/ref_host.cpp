@@ -11,6 +11,7 @@
 //     inverse m[16]
 //     cull  fov aspect near far pixels_y  model[16] view[16] proj[16]  n  (cx cy cz ex ey ez vx vy vz)*n
 //     tf1d  n center inv_gradient
+//     uniforms mv[16] vol[3] scale[3] light_dir[3] eye[3]   (SetupRaycastShader / ComputeEyeToModelMatrix)
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -79,6 +80,30 @@ int main(int argc, char** argv) {
         fprintf(out, " %d %d", int(c.IsVisible(ctr, ext)), c.GetLODLevel(ctr, ext, vox));
       }
       fprintf(out, "\n");
+    } else if (op == "uniforms") {
+      // the statement sequence of GLGridLeaper::SetupRaycastShader / ComputeEyeToModelMatrix (GLGridLeaper.cpp:560-573,
+      // 690-752) and AbstrRenderer::GetVolumeAABB (AbstrRenderer.cpp:1102-1109) on the reference's own vector classes
+      FLOATMATRIX4 mv; read16(ls, mv);
+      UINTVECTOR3 vDomainSize; FLOATVECTOR3 vScale, vLightDir, vEye;
+      ls >> vDomainSize.x >> vDomainSize.y >> vDomainSize.z >> vScale.x >> vScale.y >> vScale.z;
+      ls >> vLightDir.x >> vLightDir.y >> vLightDir.z >> vEye.x >> vEye.y >> vEye.z;
+      FLOATVECTOR3 vExtend = FLOATVECTOR3(vDomainSize) * vScale;
+      vExtend /= vExtend.maxVal();
+      vScale /= vScale.minVal();
+      FLOATVECTOR3 vCenter(0, 0, 0);
+      FLOATMATRIX4 mTrans, mScale, mNormalize;
+      mTrans.Translation(-vCenter);
+      mScale.Scaling(1.0f / vExtend);
+      mNormalize.Translation(0.5f, 0.5f, 0.5f);
+      const FLOATMATRIX4 emm = mv.inverse() * mTrans * mScale * mNormalize;
+      const FLOATVECTOR3 scale = 1.0f / vScale;
+      const FLOATVECTOR3 l = (FLOATVECTOR4(vLightDir, 0.0f) * emm).xyz().normalized();
+      const FLOATVECTOR3 e = (FLOATVECTOR4(vEye, 1.0f) * emm).xyz();
+      put16(out, "emm", emm);
+      put16(out, "m2e", emm.inverse());
+      put16(out, "mvinv", mv.inverse());
+      fprintf(out, "vecs %a %a %a %a %a %a %a %a %a %a %a %a\n", (double)scale.x, (double)scale.y, (double)scale.z, (double)l.x,
+              (double)l.y, (double)l.z, (double)e.x, (double)e.y, (double)e.z, (double)vExtend.x, (double)vExtend.y, (double)vExtend.z);
     } else if (op == "tf1d") {
       size_t n; float center, inv;
       ls >> n >> center >> inv;

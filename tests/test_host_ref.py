@@ -144,3 +144,27 @@ def test_tf1d_matches_reference_class(tmp_path, n, c, g):
     ref = orc.tf1d_std(n, c, g)
     np.testing.assert_array_equal(orc.tf1d_bytes(ref), ref_bytes)
     assert orc.tf1d_nonzero(ref) == (lo, hi)
+
+
+@pytest.mark.parametrize("name", ["c2_bricked36_1d_ert", "c3_bricked36_2d_lit", "inside_aniso_2d", "c4_f32_iso"])
+def test_raycast_uniforms_follow_setupraycastshader(tmp_path, name):
+    """mEyeToModel, mModelToEye, inverse(modelView), vDomainScale, model-space light direction and eye position: the
+    oracle's derivation (double-precision inverse, rounded once) vs the statement sequence of
+    GLGridLeaper::SetupRaycastShader / ComputeEyeToModelMatrix run on the reference's own FLOATMATRIX4 (fp32 inverse).
+    Same quantities to fp32 rounding -- and the product's host code derives them like the oracle (images are bit-identical)."""
+    s = golden_scenes.make(name)
+    pool, _ = s.oracle_pool()
+    p = s.oracle_params(pool)
+    u = orc.uniforms(p)
+    mv, _ = s.matrices()
+    rows = run(tmp_path, ["uniforms %s %d %d %d %s %s %s" % (fl(mv), s.size[0], s.size[1], s.size[2], fl(s.scale),
+                                                             fl(list(p.light_dir)), fl(list(p.eye)))])
+    emm, m2e, mvinv, vecs = hexf(rows[0][1:]), hexf(rows[1][1:]), hexf(rows[2][1:]), hexf(rows[3][1:])
+    np.testing.assert_allclose(u["emm"], emm, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(u["model_to_eye"], m2e, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(u["mv_inv"], mvinv, rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(u["domain_scale"], vecs[0:3])
+    np.testing.assert_allclose(u["light_dir_m"], vecs[3:6], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(u["eye_m"], vecs[6:9], rtol=0, atol=2e-6)
+    ext = np.array(s.size, np.float32) * np.array(s.scale, np.float32)
+    assert np.float32(u["lzwse"]) == np.max((ext / ext.max()).astype(np.float32) / np.array(s.size, np.float32))
