@@ -122,6 +122,13 @@ inline vec4 operator*(const mat4x4& m, const vec4& v) {
               a[2] * v.x + a[6] * v.y + a[10] * v.z + a[14] * v.w, a[3] * v.x + a[7] * v.y + a[11] * v.z + a[15] * v.w);
 }
 
+// compatibility-profile matrices: gl_NormalMatrix (mat3, rows filled by the driver) and gl_TextureMatrix[] (as mat4x4)
+struct mat3 { float a[9]; };
+inline vec3 operator*(const mat3& m, const vec3& v) {
+  return vec3(m.a[0] * v.x + m.a[1] * v.y + m.a[2] * v.z, m.a[3] * v.x + m.a[4] * v.y + m.a[5] * v.z,
+              m.a[6] * v.x + m.a[7] * v.y + m.a[8] * v.z);
+}
+
 // ---- built-ins -------------------------------------------------------------------------------------------------
 inline float dot(const vec3& a, const vec3& b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 inline float length(const vec3& a) { return sqrtf(dot(a, a)); }
@@ -130,6 +137,7 @@ inline vec3 reflect(const vec3& i, const vec3& n) { const float d = dot(n, i); r
 inline float mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 inline float clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 inline vec3 clamp(const vec3& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
+inline vec4 clamp(const vec4& v, float lo, float hi) { return vec4(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi), clamp(v.w, lo, hi)); }
 inline vec3 step(float edge, const vec3& v) { return vec3(v.x < edge ? 0.0f : 1.0f, v.y < edge ? 0.0f : 1.0f, v.z < edge ? 0.0f : 1.0f); }
 inline float min(float a, float b) { return fminf(a, b); }
 inline float max(float a, float b) { return fmaxf(a, b); }
@@ -178,6 +186,7 @@ inline vec4 texture2D(const sampler2D& s, const vec2& c) {
   int i = (int)floorf(c.x * (float)s.w), j = (int)floorf(c.y * (float)s.h);
   i = i < 0 ? 0 : i >= s.w ? s.w - 1 : i;
   j = j < 0 ? 0 : j >= s.h ? s.h - 1 : j;
+  if (!s.f32) return rgba8_texel(s.rgba8 + 4 * ((size_t)j * s.w + i));      // RGBA8 2D transfer function
   const float* q = s.f32 + 4 * ((size_t)j * s.w + i);
   return vec4(q[0], q[1], q[2], q[3]);
 }
@@ -216,3 +225,6 @@ inline vec4 texture(const sampler3D& s, const vec3& c) {
   }
   return vec4(v, v, v, 1.0f);
 }
+// compatibility-profile spellings
+inline vec4 texture1D(const sampler1D& s, float c) { return texture(s, c); }
+inline vec4 texture3D(const sampler3D& s, const vec3& c) { return texture(s, c); }

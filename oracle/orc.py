@@ -125,6 +125,7 @@ def lib():
         "orc_raycast": (None, [C.POINTER(RenderParams)] + [P] * 12 + [C.POINTER(RenderStats), C.c_int]),
         "orc_iso_compose": (None, [C.POINTER(RenderParams), P, P, P]),
         "orc_ray_exit_eye": (None, [P, P]),
+        "orc_classic_step_scale": (C.c_float, [P, C.c_uint32]),
         "orc_uniforms": (None, [P, P]),
         "orc_hash_decode": (C.c_uint32, [P, C.c_uint32, u32x3, P]),
         "orc_hash_insert": (C.c_uint32, [P, C.c_uint32, C.c_uint32, u32x3, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
@@ -341,11 +342,12 @@ def ray_exit_eye(params):
 
 
 def uniforms(params):
-    o = np.zeros(68, np.float32)
+    o = np.zeros(84, np.float32)
     lib().orc_uniforms(C.byref(params), _p(o))
     return dict(emm=o[:16].copy(), domain_scale=o[16:19].copy(), ambient=o[19:22].copy(), diffuse=o[22:25].copy(),
                 specular=o[25:28].copy(), light_dir_m=o[28:31].copy(), eye_m=o[31:34].copy(), lzwse=float(o[34]),
-                norm=float(o[35]), model_to_eye=o[36:52].copy(), mv_inv=o[52:68].copy())
+                norm=float(o[35]), model_to_eye=o[36:52].copy(), mv_inv=o[52:68].copy(),
+                inv_proj=o[68:84].copy())
 
 
 def raycast(params, pool_atlas, meta, tf, ray_start, start_color, exit_, covered, hash_table=None, threads=1):
@@ -394,6 +396,10 @@ def composite_over(front, back):
 def classic_lod(params, lod_count):
     """AbstrRenderer::ComputeMinLODForCurrentView."""
     return int(lib().orc_classic_lod(C.byref(params), lod_count))
+
+
+def classic_step_scale(params, lod):
+    return float(lib().orc_classic_step_scale(C.byref(params), lod))
 
 
 def classic_brick_list(params, lod, overlap, minmax_lod, vis):

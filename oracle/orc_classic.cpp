@@ -346,6 +346,13 @@ v4 tf_lookup(const uint8_t* tf, int w, int h, float s, float t) {
 
 extern "C" {
 
+float orc_classic_step_scale(const orc_render_params* p, uint32_t lod) {
+  std::vector<lod_geo> lt = lod_table(p->vol, p->max_total_brick, (p->max_total_brick[0] - p->max_inner_brick[0]) / 2);
+  const lod_geo& L = lt[lod];
+  return 1.0f / p->sample_rate_modifier *
+         fmaxf((float)p->vol[0] / (float)L.size[0], fmaxf((float)p->vol[1] / (float)L.size[1], (float)p->vol[2] / (float)L.size[2]));
+}
+
 /* One classic frame: bricks in list order, each raycast per pixel and blended `dst += (1 - dst.a) * src`.
  * brick_data[i]: voxels of list[i] (x fastest, the brick's own size incl. ghost), NULL for empty bricks.
  * out: w*h*4 floats (premultiplied RGBA, cleared to 0).  stats->samples counts VRender* evaluations. */

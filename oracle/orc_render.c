@@ -269,7 +269,7 @@ void orc_ray_exit_eye(const orc_render_params* p, float* exit_eye /* w*h*3 */) {
 /* ... and the uniforms GLGridLeaper::SetupRaycastShader would upload (GLGridLeaper.cpp:690-752):
  * out[0..15] mEyeToModel, [16..18] vDomainScale, [19..21] ambient, [22..24] diffuse, [25..27] specular (rgb * w),
  * [28..30] vModelSpaceLightDir, [31..33] vModelSpaceEyePos, [34] fLevelZeroWorldSpaceError, [35] unorm factor,
- * [36..51] mModelToEye, [52..67] inverse(modelView) */
+ * [36..51] mModelToEye, [52..67] inverse(modelView), [68..83] inverse(projection) */
 void orc_uniforms(const orc_render_params* p, float* out) {
   uni u;
   derive(p, &u);
@@ -280,6 +280,7 @@ void orc_uniforms(const orc_render_params* p, float* out) {
   out[35] = u.norm;
   memcpy(out + 36, u.model_to_eye, 64);   /* mModelToEye */
   memcpy(out + 52, u.mv_inv, 64);         /* inverse(modelView): mModelViewIT * v == column-vector product with it */
+  memcpy(out + 68, u.inv_proj, 64);       /* inverse(projection) */
 }
 
 /* ------------------------------------------------------------------ */

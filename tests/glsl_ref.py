@@ -49,6 +49,7 @@ def rewrite(text, main_name="shader_main"):
     text = re.sub(r"^\s*layout\s*\([^)]*\)\s*(?:coherent\s+)?uniform\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)
     text = re.sub(r"^\s*layout\s*\(location\s*=\s*\d+\)\s*out\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)
     text = re.sub(r"^in\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)      # fragment shader inputs
+    text = re.sub(r"^\s*varying\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)
     text = _array_ctor(text)
     text = re.sub(r"^\s*uniform\s+(\w+)\s+(\w+(?:\[\d+\])?)\s*=", r"\1 \2 =", text, flags=re.M)   # initialised uniforms
     text = re.sub(r"^\s*uniform\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)
@@ -63,7 +64,7 @@ def rewrite(text, main_name="shader_main"):
 
 
 def read_shader(name):
-    with open(os.path.join(SHADERS, name)) as f:
+    with open(os.path.join(SHADERS, name), encoding="latin-1") as f:     # author names in the comment headers
         return f.read()
 
 
@@ -354,5 +355,164 @@ def run_compose(exe, tmp, w, h, ambient, diffuse, specular, light_dir, hit_pos, 
         f.write(np.asarray(list(ambient) + list(diffuse) + list(specular) + list(light_dir) + [0.0, 0.0], np.float32).tobytes())
         f.write(np.ascontiguousarray(hit_pos, np.float32).tobytes())
         f.write(np.ascontiguousarray(hit_normal, np.float32).tobytes())
+    subprocess.check_call([exe, fin, fout])
+    return np.fromfile(fout, np.float32).reshape(h * w, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# classic per-brick raycaster (GLRaycaster): the fragment shaders are the reference's; the per-brick pass setup around
+# them (near-plane / front-face entry FBO in RGBA16F, back-face fragments, GL under-blending) is restated in the driver
+# ---------------------------------------------------------------------------------------------------------------------
+CLASSIC_FILES = {
+    (0, False): ["Compositing.glsl", "Volume3D.glsl", "VRender1D.glsl", "VRender1D-BScale.glsl", "VRender1DProxy.glsl",
+                 "GLRaycaster-1D-FS.glsl"],
+    (0, True): ["Compositing.glsl", "Volume3D.glsl", "lighting.glsl", "VRender1DLit.glsl", "GLRaycaster-1D-light-FS.glsl"],
+    (1, False): ["Compositing.glsl", "Volume3D.glsl", "GLRaycaster-2D-FS.glsl"],
+    (1, True): ["Compositing.glsl", "Volume3D.glsl", "lighting.glsl", "GLRaycaster-2D-light-FS.glsl"],
+}
+
+CLASSIC_DRIVER = r"""
+sampler3D texVolume; @TF_TYPE@ texTrans; sampler2D texRayExitPos, texRayExit;
+float fTransScale, fGradientScale, fStepScale, fRayStepsize, TFuncBias; int ScaleMethod;
+vec2 vScreensize; vec3 vVoxelStepsize, vDomainScale, vLightAmbient, vLightDiffuse, vLightSpecular, vLightDir, vEyePos;
+vec4 gl_FragCoord, gl_FragColor; mat4x4 gl_TextureMatrix[1]; mat3 gl_NormalMatrix;
+#include <cstdio>
+#include <cstdlib>
+static std::vector<char> slurp(const char* p) {
+  FILE* f = fopen(p, "rb"); fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+  std::vector<char> b(n); if (fread(b.data(), 1, n, f) != (size_t)n) abort(); fclose(f); return b;
+}
+static void mul4(const float* a, const float* b, float* o) {     // row-vector convention: o = a * b
+  float t[16];
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { float s = 0.0f; for (int k = 0; k < 4; k++) s = s + a[r * 4 + k] * b[k * 4 + c]; t[r * 4 + c] = s; }
+  memcpy(o, t, 64);
+}
+static float half_round(float f) {                                // what a GL_RGBA16F render target stores
+  uint32_t x; memcpy(&x, &f, 4);
+  const uint32_t sign = x & 0x80000000u; uint32_t a = x & 0x7fffffffu;
+  if (a >= 0x7f800000u) return f;
+  if (a >= 0x477ff000u) { uint32_t r = sign | 0x7f800000u; float o; memcpy(&o, &r, 4); return o; }
+  if (a < 0x33000001u) { uint32_t r = sign; float o; memcpy(&o, &r, 4); return o; }
+  float af; memcpy(&af, &a, 4);
+  int e; frexpf(af, &e);
+  const int ulp = (e - 1 < -14 ? -14 : e - 1) - 10;
+  float q = ldexpf(nearbyintf(ldexpf(af, -ulp)), ulp);
+  uint32_t r; memcpy(&r, &q, 4); r |= sign; float o; memcpy(&o, &r, 4); return o;
+}
+int main(int argc, char** argv) {
+  std::vector<char> in = slurp(argv[1]);
+  const char* p = in.data();
+  auto u32 = [&]() { uint32_t v; memcpy(&v, p, 4); p += 4; return v; };
+  auto f32 = [&]() { float v; memcpy(&v, p, 4); p += 4; return v; };
+  auto v3 = [&]() { vec3 v; v.x = f32(); v.y = f32(); v.z = f32(); return v; };
+  const uint32_t W = u32(), H = u32();
+  float inv_proj[16], imv[16];
+  for (int i = 0; i < 16; i++) inv_proj[i] = f32();
+  for (int i = 0; i < 16; i++) imv[i] = f32();
+  fTransScale = f32(); fGradientScale = f32(); fStepScale = f32();
+  const float sample_rate = f32(), norm = f32();
+  vDomainScale = v3(); vLightAmbient = v3(); vLightDiffuse = v3(); vLightSpecular = v3(); vLightDir = v3();
+  const uint32_t dtype = u32(), nearest = u32(), tfw = u32(), tfh = u32(), n_bricks = u32();
+  ScaleMethod = 0; TFuncBias = 0.0f;
+  vScreensize = vec2((float)W, (float)H);
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gl_NormalMatrix.a[r * 3 + c] = imv[r * 4 + c];   // transpose(inverse(MV)) rows
+  texTrans.rgba8 = (const uint8_t*)p; texTrans.w = tfw; set_tf_height(texTrans, tfh); p += (size_t)tfw * tfh * 4;
+  const size_t npx = (size_t)W * H;
+  std::vector<float> out(npx * 4, 0.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3);
+  for (uint32_t y = 0; y < H; y++)
+    for (uint32_t x = 0; x < W; x++) {               // Render3DPreLoop: the near plane fills the entry FBO first
+      const float nx = ((float)x + 0.5f) / (float)W * 2.0f - 1.0f, ny = ((float)y + 0.5f) / (float)H * 2.0f - 1.0f;
+      const float* m = inv_proj;
+      const float rx = nx * m[0] + ny * m[4] + -1.0f * m[8] + 1.0f * m[12], ry = nx * m[1] + ny * m[5] + -1.0f * m[9] + 1.0f * m[13];
+      const float rz = nx * m[2] + ny * m[6] + -1.0f * m[10] + 1.0f * m[14], rw = nx * m[3] + ny * m[7] + -1.0f * m[11] + 1.0f * m[15];
+      const size_t i = (size_t)y * W + x;
+      near_pt[3 * i] = rx / rw; near_pt[3 * i + 1] = ry / rw; near_pt[3 * i + 2] = rz / rw;
+      for (int k = 0; k < 3; k++) fbo[4 * i + k] = half_round(near_pt[3 * i + k]);
+    }
+  texRayExitPos.f32 = fbo.data(); texRayExitPos.w = W; texRayExitPos.h = H;
+  auto xf = [&](const float* m, float x, float y, float z) { return vec3(x * m[0] + y * m[4] + z * m[8] + 1.0f * m[12], x * m[1] + y * m[5] + z * m[9] + 1.0f * m[13], x * m[2] + y * m[6] + z * m[10] + 1.0f * m[14]); };
+  const vec3 o4 = xf(imv, 0.0f, 0.0f, 0.0f);
+  unsigned long long frags = 0;
+  for (uint32_t bi = 0; bi < n_bricks; bi++) {
+    const vec3 c = v3(), e = v3(), tmin = v3(), tmax = v3();
+    const uint32_t nv[3] = {u32(), u32(), u32()}, empty = u32();
+    const size_t es = dtype == 0 ? 1 : dtype == 1 ? 2 : 4;
+    const char* data = p;
+    if (!empty) p += (size_t)nv[0] * nv[1] * nv[2] * es;
+    if (empty) continue;
+    texVolume.d = data; texVolume.w = nv[0]; texVolume.h = nv[1]; texVolume.z = nv[2]; texVolume.dtype = dtype;
+    texVolume.norm = norm; texVolume.nearest = nearest != 0;
+    const vec3 pmin = c - vec3(e.x / 2.0f, e.y / 2.0f, e.z / 2.0f), pmax = c + vec3(e.x / 2.0f, e.y / 2.0f, e.z / 2.0f);
+    const vec3 tsc = (tmin - tmax) / (pmin - pmax);
+    vVoxelStepsize = vec3(1.0f / (float)nv[0], 1.0f / (float)nv[1], 1.0f / (float)nv[2]);
+    const vec3 rs = (e * vVoxelStepsize) * (0.5f * 1.0f / sample_rate);
+    fRayStepsize = fminf(rs.x, fminf(rs.y, rs.z));
+    // GLRaycaster::ComputeEyeToTextureMatrix: eye -> world -> texture, as ONE matrix in gl_TextureMatrix[0]
+    float t1[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, -pmax.x, -pmax.y, -pmax.z, 1};
+    float sc[16] = {tsc.x, 0, 0, 0, 0, tsc.y, 0, 0, 0, 0, tsc.z, 0, 0, 0, 0, 1};
+    float t2[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, tmax.x, tmax.y, tmax.z, 1};
+    float m[16]; mul4(imv, t1, m); mul4(m, sc, m); mul4(m, t2, m);
+    memcpy(gl_TextureMatrix[0].a, m, 64);
+    const float lo[3] = {pmin.x, pmin.y, pmin.z}, hi[3] = {pmax.x, pmax.y, pmax.z};
+    for (uint32_t y = 0; y < H; y++)
+      for (uint32_t x = 0; x < W; x++) {
+        const size_t i = (size_t)y * W + x;
+        const vec3 pn(near_pt[3 * i], near_pt[3 * i + 1], near_pt[3 * i + 2]);
+        const vec3 n4 = xf(imv, pn.x, pn.y, pn.z);
+        const float o[3] = {o4.x, o4.y, o4.z}, d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
+        float s_in = -INFINITY, s_out = INFINITY; bool miss = false;
+        for (int k = 0; k < 3; k++) {
+          if (d[k] == 0.0f) { if (o[k] < lo[k] || o[k] > hi[k]) miss = true; continue; }
+          const float t0 = (lo[k] - o[k]) / d[k], t1_ = (hi[k] - o[k]) / d[k];
+          s_in = fmaxf(s_in, fminf(t0, t1_)); s_out = fminf(s_out, fmaxf(t0, t1_));
+        }
+        if (miss || !(s_out > fmaxf(s_in, 1.0f))) continue;
+        if (s_in > 1.0f) { const vec3 fe = pn * s_in; fbo[4 * i] = half_round(fe.x); fbo[4 * i + 1] = half_round(fe.y); fbo[4 * i + 2] = half_round(fe.z); }
+        vEyePos = pn * s_out;                                    // interpolated back-face position (eye space)
+        gl_FragCoord = vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
+        gl_FragColor = vec4();
+        classic_main();
+        frags++;
+        float* dst = &out[4 * i];                               // GL blending ONE_MINUS_DST_ALPHA, ONE
+        const float k = 1.0f - dst[3];
+        dst[0] = fmaf(k, gl_FragColor.x, dst[0]); dst[1] = fmaf(k, gl_FragColor.y, dst[1]);
+        dst[2] = fmaf(k, gl_FragColor.z, dst[2]); dst[3] = fmaf(k, gl_FragColor.w, dst[3]);
+      }
+  }
+  FILE* f = fopen(argv[2], "wb");
+  fwrite(out.data(), 4, out.size(), f);
+  fclose(f);
+  return 0;
+}
+"""
+
+
+def build_classic(tmp, mode, lighting):
+    pre = PRELUDE + "extern vec4 gl_FragCoord, gl_FragColor; extern mat4x4 gl_TextureMatrix[1]; extern mat3 gl_NormalMatrix;\n"
+    parts = [pre]
+    for n in CLASSIC_FILES[(mode, bool(lighting))]:
+        parts.append("// ---- %s\n" % n + rewrite(read_shader(n), "classic_main"))
+    tf_type = "sampler2D" if mode == 1 else "sampler1D"
+    return _compile(tmp, "classic_as_cpp", "\n".join(parts) + CLASSIC_DRIVER.replace("@TF_TYPE@", tf_type))
+
+
+def run_classic(exe, tmp, params, inv_proj, imv, step_scale, norm, domain_scale, light, bricks, n_bricks, brick_arrays, tf):
+    w, h = params.width, params.height
+    buf = [struct.pack("<II", w, h), np.asarray(inv_proj, np.float32).tobytes(), np.asarray(imv, np.float32).tobytes(),
+           struct.pack("<5f", params.trans_scale, params.gradient_scale, step_scale, params.sample_rate_modifier, norm),
+           np.asarray(domain_scale, np.float32).tobytes()]
+    for k in ("ambient", "diffuse", "specular", "dir"):
+        buf.append(np.asarray(light[k], np.float32).tobytes())
+    buf.append(struct.pack("<5I", params.dtype, params.nearest, params.tf_w, params.tf_h, n_bricks))
+    buf.append(np.ascontiguousarray(tf, np.uint8).tobytes())
+    for i in range(n_bricks):
+        b = bricks[i]
+        buf.append(np.asarray(list(b.center) + list(b.ext) + list(b.tex_min) + list(b.tex_max), np.float32).tobytes())
+        buf.append(struct.pack("<4I", b.n_vox[0], b.n_vox[1], b.n_vox[2], int(b.empty)))
+        if not b.empty:
+            buf.append(np.ascontiguousarray(brick_arrays[i]).tobytes())
+    fin, fout = os.path.join(str(tmp), "classic.bin"), os.path.join(str(tmp), "classic_out.bin")
+    with open(fin, "wb") as f:
+        f.write(b"".join(buf))
     subprocess.check_call([exe, fin, fout])
     return np.fromfile(fout, np.float32).reshape(h * w, 4)

@@ -141,3 +141,38 @@ def test_isosurface_shader_and_deferred_compose(tmp_path):
     assert float(np.abs(img_o - img_g).max()) <= 2e-4
     mx, psnr = image_diff(orc.rgba8(img_o.reshape(s.height, s.width, 4)), orc.rgba8(img_g.reshape(s.height, s.width, 4)))
     assert mx <= 1 and psnr >= 60.0
+
+
+CLASSIC = [("c2_bricked36_1d_ert", {}), ("ragged_1d_lit", {}), ("inside_aniso_2d", {}),
+           ("ragged_1d_lit", dict(mode=orc.RM_2DTRANS, lighting=True)),
+           ("c2_bricked36_1d_ert", dict(translation=tb.translation(0.0, 0.0, -2.2)))]      # coarser LoD: fStepScale = 2
+
+
+@pytest.mark.parametrize("name,over", CLASSIC)
+def test_classic_per_brick_shaders_executed(tmp_path, name, over):
+    """the classic GLRaycaster fragment shaders (GLRaycaster-{1D,1D-light,2D,2D-light}-FS.glsl with
+    VRender1D*.glsl, Volume3D.glsl, lighting.glsl, Compositing.glsl) executed per brick in the oracle's brick order,
+    with the per-brick pass setup (RGBA16F entry FBO, back-face fragments, eye->texture matrix in gl_TextureMatrix[0],
+    gl_NormalMatrix, GL under-blending) supplied by the driver, vs orc_classic_render."""
+    s = golden_scenes.make(name, **over)
+    ref = s.oracle_classic()
+    o = s.octree
+    pool, _ = s.oracle_pool()
+    p = s.oracle_params(pool)
+    lod = ref["lod"]
+    bc = o.brick_count(lod)
+    first = o.brick_index(0, 0, 0, lod)
+    mm = o.minmax[first:first + bc[0] * bc[1] * bc[2]]
+    bricks, n = orc.classic_brick_list(p, lod, s.overlap, mm, s.visibility_args())
+    data = [None if bricks[i].empty else o.brick(*bricks[i].coord, lod) for i in range(n)]
+    u = orc.uniforms(p)
+    light = dict(ambient=u["ambient"], diffuse=u["diffuse"], specular=u["specular"], dir=list(p.light_dir))
+    exe = glsl_ref.build_classic(tmp_path, s.mode, s.lighting)
+    img = glsl_ref.run_classic(exe, tmp_path, p, u["inv_proj"], u["mv_inv"], orc.classic_step_scale(p, lod), u["norm"],
+                               u["domain_scale"], light, bricks, n, data, s.tf_bytes())
+    a = ref["image"].reshape(-1, 4)
+    d = np.abs(a - img).max(axis=1)
+    print("classic shaders executed vs oracle: max |d| %.3g, pixels > 5e-5: %d of %d" % (d.max(), int((d > 5e-5).sum()), len(d)))
+    assert float(d.max()) <= 8e-3 and float((d > 5e-5).mean()) <= 0.01, (float(d.max()), float((d > 5e-5).mean()))
+    mx, psnr = image_diff(orc.rgba8(a.reshape(s.height, s.width, 4)), orc.rgba8(img.reshape(s.height, s.width, 4)))
+    assert mx <= 2 and psnr >= 55.0
