@@ -105,33 +105,85 @@ class CpuSample:
     def __init__(self, cfg_name, cpu_vol, threads):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from oracle import orc
-        from scene import Scene
-        from tuvok_b200 import workloads
         self.orc = orc
-        w = workloads.WORKLOADS[cfg_name]
-        n = min(cpu_vol, w["size"][0])
-        t1, t2 = workloads.transfer_functions(w)
-        iso = w.get("iso", 0.5) * {0: 255.0, 1: 65535.0, 2: 1.0}[w["dtype"]]
-        sw, sh = max(64, w["width"] // 4), max(64, w["height"] // 4)
-        s = Scene(kind=w["kind"], size=(n, n, n), dtype=w["dtype"], brick=min(w["brick"], n + 4),
-                  overlap=w["overlap"], mode=w["mode"], lighting=w["lighting"], width=sw, height=sh,
-                  rotation=workloads.orbit_rotation(3), tf2d=t2, isovalue=iso, max_gpu_mem=8 << 30)
-        s.tf1d = t1
+        s, w, n = cpu_sample_scene(cfg_name, cpu_vol)
         self.threads = threads
         self.st = s.oracle_render(threads=threads)        # paging loop until converged (untimed)
         self.zeros = np.zeros_like(self.st["entry"])
         # the full frame has 16x the rays and (volume / cpu_vol)x the samples per ray of the sample
         self.scale = 16.0 * (w["size"][0] / float(n))
+        self.kind = "port"
         self.desc = ("%d^3 down-scale of the workload volume (same generator/TF/mode/camera), %dx%d rays "
-                     "(every 4th pixel of the frame), converged frame, %d threads" % (n, sw, sh, threads))
+                     "(every 4th pixel of the frame), converged frame, %d threads" % (n, s.width, s.height, threads))
+        # the reference's OWN shader text compiled for the host cores (oracle/_ref/glsl_baseline_<cfg>, built where the
+        # reference tree is mounted by oracle/build_glsl_baseline.py): preferred over the port when it matches this scene
+        self.glsl = None
+        exe = os.path.join(ROOT, "oracle", "_ref", "glsl_baseline_%s" % cfg_name)
+        sig = baseline_signature(s, self.st, cfg_name, n)
+        try:
+            if os.path.exists(exe) and json.load(open(exe + ".json")) == sig:
+                import glsl_ref
+                import tempfile
+                self._tmp = tempfile.mkdtemp(prefix="tvk_glsl_")
+                p = self.st["params"]
+                u = orc.uniforms(p)
+                glsl_ref.scene_file(os.path.join(self._tmp, "scene.bin"), p, u, orc.ray_exit_eye(p), self.st["entry"], self.zeros,
+                                    self.st["covered"], self.st["meta"], self.st["pool"].meta_dim, self.st["atlas"], self.st["tf"])
+                self.glsl = exe
+                self.kind = "reference"
+                _, rs = orc.raycast(p, self.st["atlas"], self.st["meta"], self.st["tf"], self.st["entry"], self.zeros,
+                                    self.st["exit"], self.st["covered"], None, threads)
+                self.samples = int(rs.samples)            # identical sample sequence (tests/test_glsl_ref.py)
+                self.desc = ("the reference's GLGridLeaper GLSL (blend + Method + GradientTools + lighting + Compositing + the "
+                             "GLSL generated by GLVolumePool/GLHashTable) compiled for the host cores (OpenMP over fragments, "
+                             "oracle/glsl/glsl_emu.h) on a " + self.desc)
+        except Exception as e:      # fall back to the port, say why
+            self.desc += " [executed-GLSL baseline unavailable: %s]" % e
 
     def frame(self):
-        """one converged oracle pass; returns (seconds, samples)"""
+        """one converged pass on the host cores; returns (seconds, samples)"""
+        st = self.st
+        if self.glsl:
+            env = dict(os.environ, OMP_NUM_THREADS=str(self.threads))
+            out = subprocess.run([self.glsl, os.path.join(self._tmp, "scene.bin"), os.path.join(self._tmp, "out.bin"), "1"],
+                                 capture_output=True, text=True, check=True, env=env).stdout.split()
+            return float(out[0]), self.samples
+        return self.frame_port()
+
+    def frame_port(self):
+        """the same pass through the oracle port (C restatement, OpenMP); returns (seconds, samples)"""
         st = self.st
         t0 = time.perf_counter()
         _, rs = self.orc.raycast(st["params"], st["atlas"], st["meta"], st["tf"], st["entry"], self.zeros,
                                  st["exit"], st["covered"], None, self.threads)
         return time.perf_counter() - t0, int(rs.samples)
+
+
+def cpu_sample_scene(cfg_name, cpu_vol):
+    """The bounded CPU sample of a workload: down-scaled volume, every 4th pixel, same generator / TF / mode / camera."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from scene import Scene
+    from tuvok_b200 import workloads
+    w = workloads.WORKLOADS[cfg_name]
+    n = min(cpu_vol, w["size"][0])
+    t1, t2 = workloads.transfer_functions(w)
+    iso = w.get("iso", 0.5) * {0: 255.0, 1: 65535.0, 2: 1.0}[w["dtype"]]
+    sw, sh = max(64, w["width"] // 4), max(64, w["height"] // 4)
+    s = Scene(kind=w["kind"], size=(n, n, n), dtype=w["dtype"], brick=min(w["brick"], n + 4),
+              overlap=w["overlap"], mode=w["mode"], lighting=w["lighting"], width=sw, height=sh,
+              rotation=workloads.orbit_rotation(3), tf2d=t2, isovalue=iso, max_gpu_mem=8 << 30)
+    s.tf1d = t1
+    return s, w, n
+
+
+def baseline_signature(s, st, cfg_name, n):
+    """What the scene-specific generated GLSL depends on; stored next to the prebuilt executable."""
+    pool = st["pool"]
+    p = st["params"]
+    return {"config": cfg_name, "volume": n, "brick": int(s.brick[0]), "overlap": int(s.overlap), "dtype": int(s.dtype),
+            "pool_size": [int(v) for v in pool.pool_size], "meta_dim": [int(v) for v in pool.meta_dim],
+            "mode": int(s.mode), "lighting": bool(s.lighting), "hash_size": int(p.hash_size), "rehash": int(p.rehash_count),
+            "strategy": int(s.strategy), "image": [int(s.width), int(s.height)]}
 
 
 def run_reference(args, rank):
@@ -164,6 +216,11 @@ def run_reference(args, rank):
     how = ("value = CPU samples/s / %.4g samples of one full frame" % spf) if spf else \
           ("value = 1 / (step time x %.0f)" % cs.scale)
     w = workloads.WORKLOADS[args.config]
+    port = {}
+    if cs.kind == "reference":      # the restated port on the same sample, reported beside the executed GLSL
+        pt, ps = min(cs.frame_port() for _ in range(2))
+        port = {"port_gsamples_per_s": ps / pt / 1e9,
+                "port_value": (ps / pt / spf) if spf else 1.0 / (pt * cs.scale)}
     line = {"impl": "reference", "metric": "frames_per_s", "value": fps_equiv, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": frame_s * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -171,8 +228,8 @@ def run_reference(args, rank):
             "config": {"workload": w["label"], "bounded_sample": cs.desc,
                        "note": "each step = one bounded-sample frame; " + how + ", the frame rate of the "
                                "full-resolution, full-size workload at the measured CPU sample rate"},
-            "cpu_baseline": {"value": fps_equiv, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": cs.desc, "gsamples_per_s": sps / 1e9},
+            "cpu_baseline": {"value": fps_equiv, "unit": "frames/s", "cores": threads, "kind": cs.kind,
+                             "sample": cs.desc, "gsamples_per_s": sps / 1e9, **port},
             "e2e": {"value": fps_equiv, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -406,8 +463,12 @@ def run_tvk(args, rank, world, local_rank):
             best, n_s = min(cs.frame() for _ in range(3))
             cpu_sps = n_s / best
             line["cpu_baseline"] = {"value": cpu_sps / (step_samples / k), "unit": "frames/s", "cores": threads,
-                                    "kind": "port", "gsamples_per_s": cpu_sps / 1e9,
+                                    "kind": cs.kind, "gsamples_per_s": cpu_sps / 1e9,
                                     "sample": cs.desc + "; value = CPU samples/s / samples of one GPU frame"}
+            if cs.kind == "reference":
+                pt, ps = min(cs.frame_port() for _ in range(2))
+                line["cpu_baseline"]["port_gsamples_per_s"] = ps / pt / 1e9
+                line["cpu_baseline"]["port_value"] = (ps / pt) / (step_samples / k)
         print(json.dumps(line), flush=True)
     r.Cleanup()
     if dist is not None:

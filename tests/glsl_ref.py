@@ -41,14 +41,15 @@ def _array_ctor(text):
     return "".join(out)
 
 
-def rewrite(text, main_name="shader_main"):
+def rewrite(text, main_name="shader_main", tls=False):
     """GLSL 4.20 -> C++ (syntax only; every statement and expression is kept as written)."""
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)                                   # licence blocks
     text = re.sub(r"^\s*#version.*$", "", text, flags=re.M)
-    text = re.sub(r"^\s*layout\s*\(pixel_center_integer\).*$", "extern vec4 gl_FragCoord;", text, flags=re.M)
+    frag = "extern thread_local" if tls else "extern"        # per-fragment state (inputs / outputs of one invocation)
+    text = re.sub(r"^\s*layout\s*\(pixel_center_integer\).*$", frag + " vec4 gl_FragCoord;", text, flags=re.M)
     text = re.sub(r"^\s*layout\s*\([^)]*\)\s*(?:coherent\s+)?uniform\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)
-    text = re.sub(r"^\s*layout\s*\(location\s*=\s*\d+\)\s*out\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)
-    text = re.sub(r"^in\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)      # fragment shader inputs
+    text = re.sub(r"^\s*layout\s*\(location\s*=\s*\d+\)\s*out\s+(\w+)\s+(\w+)\s*;", frag + r" \1 \2;", text, flags=re.M)
+    text = re.sub(r"^in\s+(\w+)\s+(\w+)\s*;", frag + r" \1 \2;", text, flags=re.M)      # fragment shader inputs
     text = re.sub(r"^\s*varying\s+(\w+)\s+(\w+)\s*;", r"extern \1 \2;", text, flags=re.M)
     text = _array_ctor(text)
     text = re.sub(r"^\s*uniform\s+(\w+)\s+(\w+(?:\[\d+\])?)\s*=", r"\1 \2 =", text, flags=re.M)   # initialised uniforms
@@ -516,3 +517,50 @@ def run_classic(exe, tmp, params, inv_proj, imv, step_scale, norm, domain_scale,
         f.write(b"".join(buf))
     subprocess.check_call([exe, fin, fout])
     return np.fromfile(fout, np.float32).reshape(h * w, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the same executed reference GLSL, all host cores (what bench.py times as cpu_baseline kind "reference").
+# The per-fragment globals become thread_local and the fragments of a frame are distributed with OpenMP; the binary
+# takes the scene file of run(), renders `reps` frames and prints the seconds of the fastest one.
+# ---------------------------------------------------------------------------------------------------------------------
+def build_baseline(tmp, out_exe, mode, lighting, pool_glsl, hash_glsl):
+    parts = [PRELUDE, rewrite(hash_glsl, tls=True), rewrite(pool_glsl, tls=True)]
+    for n in ["Compositing.glsl", "lighting.glsl", "GLGridLeaper-GradientTools.glsl", METHOD[(mode, bool(lighting))],
+              "GLGridLeaper-blend.glsl"]:
+        parts.append("// ---- %s\n" % n + rewrite(read_shader(n), tls=True))
+    drv = DRIVER.replace("@TF_TYPE@", "sampler2D" if mode == 1 else "sampler1D")
+    drv = drv.replace("vec4 gl_FragCoord, accRayColor, rayResumeColor, rayResumePos; vec3 vPosInViewCoords;",
+                      "thread_local vec4 gl_FragCoord, accRayColor, rayResumeColor, rayResumePos; thread_local vec3 vPosInViewCoords;")
+    drv = drv.replace("#include <cstdio>", "#include <cstdio>\n#include <omp.h>")
+    drv = drv.replace("  for (uint32_t y = 0; y < H; y++)\n    for (uint32_t x = 0; x < W; x++) {\n      const size_t i = (size_t)y * W + x;\n      if (!covered[i]) continue;",
+                      "  const int reps = argc > 3 ? atoi(argv[3]) : 1;\n  double best = 1e30;\n  for (int rep = 0; rep < reps; rep++) {\n  const double t0 = omp_get_wtime();\n#pragma omp parallel for schedule(dynamic, 1)\n  for (int64_t y = 0; y < (int64_t)H; y++)\n    for (uint32_t x = 0; x < W; x++) {\n      const size_t i = (size_t)y * W + x;\n      if (!covered[i]) continue;")
+    drv = drv.replace("      memcpy(&out[npx * 8 + i * 4], &rayResumePos.x, 16);\n    }\n",
+                      "      memcpy(&out[npx * 8 + i * 4], &rayResumePos.x, 16);\n    }\n  const double dt = omp_get_wtime() - t0; if (dt < best) best = dt;\n  }\n  printf(\"%.9f %d\\n\", best, omp_get_max_threads());\n", 1)
+    assert "omp_get_wtime() - t0" in drv and "#pragma omp parallel for" in drv
+    src = os.path.join(str(tmp), "baseline_as_cpp.cpp")
+    with open(src, "w") as f:
+        f.write("\n".join(parts) + drv)
+    subprocess.check_call(["g++", "-std=c++14", "-O3", "-fopenmp", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", EMU,
+                           "-o", out_exe, src])
+    return out_exe
+
+
+def scene_file(path, params, u, exit_eye, entry, start_color, covered, meta, meta_dim, atlas, tf):
+    """Writes the input file of the DRIVER (same layout as run())."""
+    w, h = params.width, params.height
+    buf = [struct.pack("<II", w, h), np.asarray(u["emm"], np.float32).tobytes(),
+           struct.pack("<5f", params.sample_rate_modifier, params.trans_scale, params.gradient_scale, params.lod_factor, u["lzwse"])]
+    for k in ("ambient", "diffuse", "specular", "light_dir_m", "eye_m", "domain_scale"):
+        buf.append(np.asarray(u[k], np.float32).tobytes())
+    buf.append(struct.pack("<3I", *meta_dim))
+    buf.append(struct.pack("<3I", atlas.shape[2], atlas.shape[1], atlas.shape[0]))
+    buf.append(struct.pack("<5I", params.dtype, params.nearest, params.tf_w, params.tf_h, params.hash_size))
+    buf.append(struct.pack("<f", u["norm"]))
+    buf += [np.ascontiguousarray(entry, np.float32).tobytes(), np.ascontiguousarray(start_color, np.float32).tobytes(),
+            np.ascontiguousarray(exit_eye, np.float32).tobytes(), np.ascontiguousarray(covered, np.uint8).tobytes()]
+    m = np.zeros(meta_dim[0] * meta_dim[1] * meta_dim[2], np.uint32)
+    m[:len(meta)] = meta
+    buf += [m.tobytes(), np.ascontiguousarray(atlas).tobytes(), np.ascontiguousarray(tf, np.uint8).tobytes()]
+    with open(path, "wb") as f:
+        f.write(b"".join(buf))

@@ -176,3 +176,28 @@ def test_classic_per_brick_shaders_executed(tmp_path, name, over):
     assert float(d.max()) <= 8e-3 and float((d > 5e-5).mean()) <= 0.01, (float(d.max()), float((d > 5e-5).mean()))
     mx, psnr = image_diff(orc.rgba8(a.reshape(s.height, s.width, 4)), orc.rgba8(img.reshape(s.height, s.width, 4)))
     assert mx <= 2 and psnr >= 55.0
+
+
+def test_openmp_baseline_binary_equals_sequential_execution(tmp_path):
+    """bench.py's cpu_baseline of kind "reference" (glsl_ref.build_baseline: the same shader text, per-fragment globals
+    thread_local, fragments distributed with OpenMP) renders bit for bit what the sequential executed shader renders."""
+    import os
+    import subprocess
+    s = golden_scenes.make("c3_bricked36_2d_lit")
+    st = s.oracle_render()
+    p, pool = st["params"], st["pool"]
+    zeros = np.zeros_like(st["entry"])
+    g0, g1, g2, _ = execute_reference_glsl(tmp_path, s, st, st["entry"], zeros, st["meta"])
+    pool_glsl, hash_glsl = glsl_ref.generated_glsl(tmp_path, s.octree, s.size, s.brick[0], s.overlap, s.dtype, pool.pool_size,
+                                                   s.strategy, s.octree.brick_count(0), p.hash_size, p.rehash_count)
+    exe = glsl_ref.build_baseline(tmp_path, os.path.join(str(tmp_path), "baseline"), s.mode, s.lighting, pool_glsl, hash_glsl)
+    u = orc.uniforms(p)
+    fin, fout = os.path.join(str(tmp_path), "b_scene.bin"), os.path.join(str(tmp_path), "b_out.bin")
+    glsl_ref.scene_file(fin, p, u, orc.ray_exit_eye(p), st["entry"], zeros, st["covered"], st["meta"], pool.meta_dim,
+                        st["atlas"], st["tf"])
+    out = subprocess.run([exe, fin, fout, "2"], capture_output=True, text=True, check=True,
+                         env=dict(os.environ, OMP_NUM_THREADS="4")).stdout.split()
+    assert float(out[0]) > 0.0
+    npx = p.width * p.height
+    img = np.fromfile(fout, np.float32, count=npx * 12).reshape(3, npx, 4)
+    assert np.array_equal(img[0], g0) and np.array_equal(img[1], g1) and np.array_equal(img[2], g2)
