@@ -287,7 +287,20 @@ typedef struct {
  * Render3DInLoop per brick (GLRenderer.cpp:2663-2748, GLRaycaster.cpp:348-478) and GL under-blending.
  * 1D / 2D transfer function modes with and without lighting; the result is read with tvk_read_rgba8/32f. */
 int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* stats);
-/* parity tap: the brick list of the last classic frame (depth sorted) and its LoD */
+/* One HQ MIP frame of a 2D window (RenderRegion2D with GetUseMIP()): AbstrRenderer::PlanHQMIPFrame
+ * (AbstrRenderer.cpp:1214-1245: no frustum culling; LoD 0, or with use_mip_lod = m_bMIPLOD the coarsest LoD whose
+ * smallest extent still covers the larger window side, stepped back by one), the brick loop of
+ * GLRenderer.cpp:1183-1230 with GLRaycaster::RenderHQMIPInLoop per non-empty brick (GLRaycaster.cpp:494-530:
+ * GLRaycaster-MIP-Rot-FS.glsl, BE_MAX blending) and the Transfer-MIP-FS.glsl pass over the blended maximum
+ * (GLRenderer.cpp:1232-1250).  The caller sets model_view = m_maMIPRotation * view as RenderHQMIPPreLoop does
+ * (GLRenderer.cpp:1256-1285, GLRaycaster.cpp:481-492; perspective rays -- the m_bOrthoView switch is not built).
+ * Brick emptiness follows the current render mode (ContainsData); the colour always comes from the 1D transfer
+ * function.  The RGBA result (alpha 1) is read with tvk_read_rgba8/32f. */
+int tvk_render_mip(tvk_ctx* ctx, int use_mip_lod, tvk_frame_stats* stats);
+/* parity tap: the blended maximum image of the last MIP frame, width*height*(maximum, coverage) floats --
+ * what Transfer-MIP-FS reads from m_pFBO3DImageNext[1] */
+int tvk_read_mip_max(tvk_ctx* ctx, float* dst);
+/* parity tap: the brick list of the last classic / MIP frame (depth sorted; MIP: key order) and its LoD */
 int tvk_get_classic_brick_list(tvk_ctx* ctx, uint32_t* lod, tvk_classic_brick* dst, uint32_t cap, uint32_t* n);
 
 /* ---- sort-last compositing (new) --------------------------------------- */

@@ -72,8 +72,9 @@ struct uvec3 {
 inline vec3::vec3(const ivec3& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
 inline vec3::vec3(const uvec3& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
 
+struct swz_xw { float v[4]; operator vec2() const { return vec2(v[0], v[3]); } };   // read-only .xw (Transfer-MIP-FS.glsl)
 struct vec4 {
-  union { struct { float x, y, z, w; }; struct { float r, g, b, a; }; swz<vec3, float, 3> xyz; swz<vec3, float, 3> rgb; swz<vec2, float, 2> xy; };
+  union { struct { float x, y, z, w; }; struct { float r, g, b, a; }; swz<vec3, float, 3> xyz; swz<vec3, float, 3> rgb; swz<vec2, float, 2> xy; swz_xw xw; };
   vec4() : x(0), y(0), z(0), w(0) {}
   vec4(float a_, float b_, float c_, float d_) : x(a_), y(b_), z(c_), w(d_) {}
   vec4(const vec3& v, float d_) : x(v.x), y(v.y), z(v.z), w(d_) {}

@@ -136,6 +136,11 @@ def lib():
                                                 C.c_uint32]),
         "orc_classic_render": (None, [C.POINTER(RenderParams), C.c_uint32, P, C.c_uint32, P, P, P,
                                       C.POINTER(RenderStats), C.c_int]),
+        "orc_mip_lod": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_int]),
+        "orc_mip_brick_list": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, P, C.c_double * 4, P,
+                                            C.c_uint32]),
+        "orc_mip_render": (None, [C.POINTER(RenderParams), C.c_uint32, P, C.c_uint32, P, P, C.c_uint32, P, P,
+                                  C.POINTER(RenderStats), C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -422,3 +427,31 @@ def classic_render(params, lod, bricks, n, brick_arrays, tf, threads=1):
     lib().orc_classic_render(C.byref(params), lod, C.cast(bricks, C.c_void_p), n, C.cast(ptrs, C.c_void_p), _p(tfb), _p(out),
                              C.byref(st), threads)
     return out, st
+
+
+def mip_lod(params, lod_count, use_mip_lod=True):
+    """AbstrRenderer::PlanHQMIPFrame's LoD."""
+    return int(lib().orc_mip_lod(C.byref(params), lod_count, 1 if use_mip_lod else 0))
+
+
+def mip_brick_list(params, lod, overlap, minmax_lod, vis):
+    """BuildSubFrameBrickList(true) of a HQ MIP frame (no culling, key order) -> ctypes array of ClassicBrick."""
+    mm = np.ascontiguousarray(minmax_lod, np.float64)
+    v = (C.c_double * 4)(*[float(x) for x in vis])
+    n = lib().orc_mip_brick_list(C.byref(params), lod, overlap, _p(mm), v, None, 0)
+    arr = (ClassicBrick * max(n, 1))()
+    lib().orc_mip_brick_list(C.byref(params), lod, overlap, _p(mm), v, C.cast(arr, C.c_void_p), n)
+    return arr, n
+
+
+def mip_render(params, lod, bricks, n, brick_arrays, tf1d, threads=1):
+    """One HQ MIP frame.  Returns (rgba [h*w, 4], max image [h*w, 2] = (maximum, coverage), stats)."""
+    keep = [np.ascontiguousarray(a) if a is not None else None for a in brick_arrays]
+    ptrs = (C.c_void_p * max(n, 1))(*[(a.ctypes.data if a is not None else None) for a in keep])
+    out = np.zeros((params.height * params.width, 4), np.float32)
+    mx = np.zeros((params.height * params.width, 2), np.float32)
+    st = RenderStats()
+    tfb = np.ascontiguousarray(tf1d, np.uint8).reshape(-1, 4)
+    lib().orc_mip_render(C.byref(params), lod, C.cast(bricks, C.c_void_p), n, C.cast(ptrs, C.c_void_p), _p(tfb), len(tfb),
+                         _p(mx), _p(out), C.byref(st), threads)
+    return out, mx, st

@@ -191,8 +191,8 @@ uint32_t orc_classic_lod(const orc_render_params* p, uint32_t lod_count) {
 
 /* BuildSubFrameBrickList for one LoD.  minmax: 4 doubles per brick of THIS LoD in TOC order (x fastest).
  * vis = {tfMin, tfMax, gradMin, gradMax} (1D/2D, already rescaled) or {iso}.  Returns the list length. */
-uint32_t orc_classic_brick_list(const orc_render_params* p, uint32_t lod, uint32_t overlap, const double* minmax,
-                                const double vis[4], orc_classic_brick* out, uint32_t cap) {
+static uint32_t brick_list_impl(const orc_render_params* p, uint32_t lod, uint32_t overlap, const double* minmax,
+                                const double vis[4], orc_classic_brick* out, uint32_t cap, bool pass_all) {
   std::vector<lod_geo> lt = lod_table(p->vol, p->max_total_brick, overlap);
   if (lod >= lt.size()) return 0;
   const lod_geo& L = lt[lod];
@@ -235,7 +235,7 @@ uint32_t orc_classic_brick_list(const orc_render_params* p, uint32_t lod, uint32
         for (int i = 0; i < 3; i++) b.n_vox[i] = n[i];
         /* RegionNeedsBrick: frustum test with the current LoD's scale */
         const v3 ce = mul3(ctr, scale_cull), ee = mul3(ext_md, scale_cull);
-        bool needed = is_visible(P, ce, ee);
+        bool needed = pass_all || is_visible(P, ce, ee);   /* CullingLOD::SetPassAll(true) for HQ MIP frames */
         if (needed) {
           const double* mm = minmax + 4 * (size_t)b.index;
           bool has;
@@ -259,7 +259,7 @@ uint32_t orc_classic_brick_list(const orc_render_params* p, uint32_t lod, uint32
               const v4 t = xform4(p->model_view, q.x, q.y, q.z, 1.0f);
               dmin = fminf(dmin, len3(V3(t.x, t.y, t.z)));
             }
-            b.distance = dmin;
+            b.distance = pass_all ? 0.0f : dmin;   /* bUseResidencyAsDistanceCriterion: every brick is resident here */
           }
           list.push_back(b);
         }
@@ -275,6 +275,33 @@ uint32_t orc_classic_brick_list(const orc_render_params* p, uint32_t lod, uint32
   const uint32_t n = (uint32_t)std::min<size_t>(list.size(), cap);
   if (out) memcpy(out, list.data(), n * sizeof(orc_classic_brick));
   return (uint32_t)list.size();
+}
+
+uint32_t orc_classic_brick_list(const orc_render_params* p, uint32_t lod, uint32_t overlap, const double* minmax,
+                                const double vis[4], orc_classic_brick* out, uint32_t cap) {
+  return brick_list_impl(p, lod, overlap, minmax, vis, out, cap, false);
+}
+
+/* AbstrRenderer::PlanHQMIPFrame (AbstrRenderer.cpp:1214-1245): LoD 0, or with m_bMIPLOD the coarsest LoD whose
+ * smallest extent is still >= the largest window side, stepped back by one */
+uint32_t orc_mip_lod(const orc_render_params* p, uint32_t lod_count, int use_mip_lod) {
+  uint32_t vc[3] = {p->vol[0], p->vol[1], p->vol[2]};
+  uint64_t lod = 0;
+  if (use_mip_lod) {
+    const uint32_t win = std::max(p->width, p->height);
+    while (std::min(vc[0], std::min(vc[1], vc[2])) >= win) {
+      for (int i = 0; i < 3; i++) vc[i] /= 2;
+      lod++;
+    }
+  }
+  if (lod > 0) lod = std::min<uint64_t>(lod_count - 1, lod - 1);
+  return (uint32_t)lod;
+}
+
+/* BuildSubFrameBrickList(true) of a HQ MIP frame: no frustum culling, key order */
+uint32_t orc_mip_brick_list(const orc_render_params* p, uint32_t lod, uint32_t overlap, const double* minmax,
+                            const double vis[4], orc_classic_brick* out, uint32_t cap) {
+  return brick_list_impl(p, lod, overlap, minmax, vis, out, cap, true);
 }
 
 }  // extern "C"
@@ -479,6 +506,106 @@ void orc_classic_render(const orc_render_params* p, uint32_t lod, const orc_clas
         dst[0] = fmaf(k, col.x, dst[0]); dst[1] = fmaf(k, col.y, dst[1]);
         dst[2] = fmaf(k, col.z, dst[2]); dst[3] = fmaf(k, col.w, dst[3]);
       }
+  }
+  if (stats) { memset(stats, 0, sizeof(*stats)); stats->samples = samples; }
+}
+
+
+/* One HQ MIP frame (GLRenderer.cpp:1183-1253): per non-empty brick the front faces go into the RGBA16F ray-entry
+ * FBO, the back-face pass marches GLRaycaster-MIP-Rot-FS.glsl:47-77 (max of texture3D(texVolume).x at
+ * iStepCount = int(len / fRayStepsize) + 1 positions, step = min(ext / voxels) * 0.5 / sampleRate,
+ * GLRaycaster.cpp:494-530) and GL blends with BE_MAX into (max, max, max, 1); Transfer-MIP-FS.glsl:43-52 then
+ * maps the maximum through the 1D transfer function, ignoring its opacity.
+ * The view is whatever model_view / projection hold (the caller passes m_maMIPRotation * view, GLRaycaster.cpp:481-492;
+ * perspective rays from the eye -- m_bOrthoView defaults to false, AbstrRenderer.cpp:127).  The entry FBO starts out as
+ * the near-plane points, as in orc_classic_render (the reference leaves it with the previous 3D frame's content).
+ * out_max: w*h*2 floats (maximum, coverage flag = the blended alpha); out: w*h*4 floats RGBA. */
+void orc_mip_render(const orc_render_params* p, uint32_t lod, const orc_classic_brick* list, uint32_t n_bricks,
+                    const void* const* brick_data, const uint8_t* tf1d, uint32_t tf_n, float* out_max, float* out,
+                    orc_render_stats* stats, int n_threads) {
+  (void)lod;
+  double mv[16], pr[16], imv_d[16], ipr_d[16];
+  float imv[16], inv_proj[16];
+  for (int i = 0; i < 16; i++) { mv[i] = p->model_view[i]; pr[i] = p->projection[i]; }
+  inv4d(mv, imv_d); inv4d(pr, ipr_d);
+  for (int i = 0; i < 16; i++) { imv[i] = (float)imv_d[i]; inv_proj[i] = (float)ipr_d[i]; }
+  const float norm = p->dtype == ORC_U8 ? 1.0f / 255.0f : p->dtype == ORC_U16 ? 1.0f / 65535.0f : 1.0f;
+  const size_t n_pix = (size_t)p->width * p->height;
+  memset(out_max, 0, n_pix * 8);
+  std::vector<float> fbo(n_pix * 3), near_pt(n_pix * 3);
+  for (uint32_t y = 0; y < p->height; y++)
+    for (uint32_t x = 0; x < p->width; x++) {
+      float nx = ((float)x + 0.5f) / (float)p->width * 2.0f - 1.0f;
+      float ny = ((float)y + 0.5f) / (float)p->height * 2.0f - 1.0f;
+      v4 nr = xform4(inv_proj, nx, ny, -1.0f, 1.0f);
+      size_t i = (size_t)y * p->width + x;
+      near_pt[3 * i] = nr.x / nr.w; near_pt[3 * i + 1] = nr.y / nr.w; near_pt[3 * i + 2] = nr.z / nr.w;
+      for (int k = 0; k < 3; k++) fbo[3 * i + k] = half_round(near_pt[3 * i + k]);
+    }
+  uint64_t samples = 0;
+  const v4 o4 = xform4(imv, 0.0f, 0.0f, 0.0f, 1.0f);
+  for (uint32_t bi = 0; bi < n_bricks; bi++) {
+    const orc_classic_brick& b = list[bi];
+    if (b.empty) continue;                 /* "for MIP we do not consider empty bricks" GLRenderer.cpp:1209-1211 */
+    btex T; T.data = brick_data[bi]; T.dtype = p->dtype; T.nearest = p->nearest;
+    for (int i = 0; i < 3; i++) T.n[i] = b.n_vox[i];
+    const v3 c = V3(b.center[0], b.center[1], b.center[2]), e = V3(b.ext[0], b.ext[1], b.ext[2]);
+    const v3 pmin = sub3(c, V3(e.x / 2.0f, e.y / 2.0f, e.z / 2.0f)), pmax = add3(c, V3(e.x / 2.0f, e.y / 2.0f, e.z / 2.0f));
+    const v3 tmin = V3(b.tex_min[0], b.tex_min[1], b.tex_min[2]), tmax = V3(b.tex_max[0], b.tex_max[1], b.tex_max[2]);
+    const v3 tsc = div3(sub3(tmin, tmax), sub3(pmin, pmax));
+    const v3 vstep = V3(1.0f / (float)b.n_vox[0], 1.0f / (float)b.n_vox[1], 1.0f / (float)b.n_vox[2]);
+    const float ray_step = min3(scl3(mul3(e, vstep), 0.5f * 1.0f / p->sample_rate_modifier));
+    const float lo[3] = {pmin.x, pmin.y, pmin.z}, hi[3] = {pmax.x, pmax.y, pmax.z};
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads < 1 ? 1 : n_threads) reduction(+ : samples)
+    for (int64_t py = 0; py < (int64_t)p->height; py++)
+      for (uint32_t px = 0; px < p->width; px++) {
+        const size_t i = (size_t)py * p->width + px;
+        const v3 pn = V3(near_pt[3 * i], near_pt[3 * i + 1], near_pt[3 * i + 2]);
+        const v4 n4 = xform4(imv, pn.x, pn.y, pn.z, 1.0f);
+        const float o[3] = {o4.x, o4.y, o4.z}, d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
+        float s_in = -INFINITY, s_out = INFINITY;
+        bool miss = false;
+        for (int k = 0; k < 3; k++) {
+          if (d[k] == 0.0f) { if (o[k] < lo[k] || o[k] > hi[k]) miss = true; continue; }
+          float t0 = (lo[k] - o[k]) / d[k], t1 = (hi[k] - o[k]) / d[k];
+          s_in = fmaxf(s_in, fminf(t0, t1));
+          s_out = fminf(s_out, fmaxf(t0, t1));
+        }
+        if (miss || !(s_out > fmaxf(s_in, 1.0f))) continue;
+        if (s_in > 1.0f) {
+          const v3 fe = scl3(pn, s_in);
+          fbo[3 * i] = half_round(fe.x); fbo[3 * i + 1] = half_round(fe.y); fbo[3 * i + 2] = half_round(fe.z);
+        }
+        const v3 entry = V3(fbo[3 * i], fbo[3 * i + 1], fbo[3 * i + 2]);
+        const v3 exit_ = scl3(pn, s_out);
+        auto to_tex = [&](v3 q) {
+          v4 w = xform4(imv, q.x, q.y, q.z, 1.0f);
+          return add3(mul3(sub3(V3(w.x, w.y, w.z), pmax), tsc), tmax);
+        };
+        const v3 et = to_tex(entry), xt = to_tex(exit_);
+        const float len = len3(sub3(exit_, entry));
+        const float nsteps = len / ray_step;
+        const int count = (int)nsteps + 1;
+        const v3 inc_tex = V3((xt.x - et.x) / nsteps, (xt.y - et.y) / nsteps, (xt.z - et.z) / nsteps);
+        float mx = 0.0f;
+        v3 ct = et;
+        for (int s = 0; s < count; s++) {
+          samples++;
+          mx = fmaxf(mx, T.sample(ct, 0, 0, 0, norm));
+          ct = add3(ct, inc_tex);
+        }
+        float* dst = out_max + 2 * i;      /* BE_MAX of (max, max, max, 1) */
+        dst[0] = fmaxf(dst[0], mx);
+        dst[1] = 1.0f;
+      }
+  }
+  for (size_t i = 0; i < n_pix; i++) {     /* Transfer-MIP-FS.glsl */
+    float* q = out + 4 * i;
+    q[0] = q[1] = q[2] = 0.0f; q[3] = 1.0f;
+    if (out_max[2 * i + 1] > 0.5f) {
+      const v4 t = tf_lookup(tf1d, (int)tf_n, 1, out_max[2 * i] * p->trans_scale, 0.0f);
+      q[0] = t.x; q[1] = t.y; q[2] = t.z;
+    }
   }
   if (stats) { memset(stats, 0, sizeof(*stats)); stats->samples = samples; }
 }

@@ -12,6 +12,8 @@
 //     cull  fov aspect near far pixels_y  model[16] view[16] proj[16]  n  (cx cy cz ex ey ez vx vy vz)*n
 //     tf1d  n center inv_gradient
 //     uniforms mv[16] vol[3] scale[3] light_dir[3] eye[3]   (SetupRaycastShader / ComputeEyeToModelMatrix)
+//     miprot window(0 sagittal,1 axial,2 coronal) flipx flipy angle_deg region_rotation[16] view[16]
+//           (the statements of GLRenderer::RenderHQMIPPreLoop + GLRaycaster::RenderHQMIPPreLoop on FLOATMATRIX4)
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -59,6 +61,21 @@ int main(int argc, char** argv) {
     } else if (op == "mul") {
       FLOATMATRIX4 a, b; read16(ls, a); read16(ls, b);
       put16(out, "mul", a * b);
+    } else if (op == "miprot") {
+      int wm, fx, fy; float angle;
+      ls >> wm >> fx >> fy >> angle;
+      FLOATMATRIX4 region_rotation, view; read16(ls, region_rotation); read16(ls, view);
+      // GLRenderer::RenderHQMIPPreLoop, GLRenderer.cpp:1256-1285
+      double dPI = 3.141592653589793238462643383;
+      FLOATMATRIX4 matRotDir, matFlipX, matFlipY, maMIPRotation;
+      if (wm == 0) { FLOATMATRIX4 matTemp; matRotDir.RotationX(-dPI/2.0); matTemp.RotationY(-dPI/2.0); matRotDir = matRotDir * matTemp; }
+      else if (wm == 1) matRotDir.RotationX(-dPI/2.0);
+      if (fx) matFlipY.Scaling(-1,1,1);
+      if (fy) matFlipX.Scaling(1,-1,1);
+      maMIPRotation.RotationY(dPI*double(angle)/180.0);
+      maMIPRotation = matRotDir * region_rotation * matFlipX * matFlipY * maMIPRotation;
+      put16(out, "miprot", maMIPRotation);
+      put16(out, "mipmv", maMIPRotation * view);   // GLRaycaster::RenderHQMIPPreLoop, GLRaycaster.cpp:489 (perspective)
     } else if (op == "inverse") {
       FLOATMATRIX4 a; read16(ls, a);
       put16(out, "inverse", a.inverse());

@@ -564,3 +564,74 @@ def scene_file(path, params, u, exit_eye, entry, start_color, covered, meta, met
     buf += [m.tobytes(), np.ascontiguousarray(atlas).tobytes(), np.ascontiguousarray(tf, np.uint8).tobytes()]
     with open(path, "wb") as f:
         f.write(b"".join(buf))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# HQ MIP frames: GLRaycaster-MIP-Rot-FS.glsl + Volume3D.glsl executed per brick with the pass setup of
+# GLRaycaster::RenderHQMIPInLoop (front faces into the RGBA16F entry FBO, back-face fragments, BE_MAX blending), then
+# Transfer-MIP-FS.glsl over the blended maximum image.  The driver is the classic one with the blend equation and
+# the final pass exchanged.
+# ---------------------------------------------------------------------------------------------------------------------
+def _mip_driver():
+    d = CLASSIC_DRIVER.replace("@TF_TYPE@", "sampler1D")
+    subs = [
+        ("sampler2D texRayExitPos, texRayExit;", "sampler2D texRayExitPos, texRayExit, texLast; vec4 gl_TexCoord[1];"),
+        ("        classic_main();\n", "        mip_main();\n"),
+        ("        float* dst = &out[4 * i];                               // GL blending ONE_MINUS_DST_ALPHA, ONE\n"
+         "        const float k = 1.0f - dst[3];\n"
+         "        dst[0] = fmaf(k, gl_FragColor.x, dst[0]); dst[1] = fmaf(k, gl_FragColor.y, dst[1]);\n"
+         "        dst[2] = fmaf(k, gl_FragColor.z, dst[2]); dst[3] = fmaf(k, gl_FragColor.w, dst[3]);\n",
+         "        float* dst = &out[4 * i];                               // GL blending BF_ONE, BE_MAX\n"
+         "        dst[0] = fmaxf(dst[0], gl_FragColor.x); dst[1] = fmaxf(dst[1], gl_FragColor.y);\n"
+         "        dst[2] = fmaxf(dst[2], gl_FragColor.z); dst[3] = fmaxf(dst[3], gl_FragColor.w);\n"),
+        ("  FILE* f = fopen(argv[2], \"wb\");\n  fwrite(out.data(), 4, out.size(), f);\n",
+         "  std::vector<float> fin(npx * 4, 0.0f);                       // Transfer-MIP-FS over a full-screen quad\n"
+         "  texLast.f32 = out.data(); texLast.w = W; texLast.h = H;\n"
+         "  for (uint32_t y = 0; y < H; y++)\n"
+         "    for (uint32_t x = 0; x < W; x++) {\n"
+         "      gl_TexCoord[0] = vec4(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H, 0.0f, 1.0f);\n"
+         "      gl_FragColor = vec4();\n"
+         "      transfer_main();\n"
+         "      memcpy(&fin[4 * ((size_t)y * W + x)], &gl_FragColor.x, 16);\n"
+         "    }\n"
+         "  FILE* f = fopen(argv[2], \"wb\");\n  fwrite(fin.data(), 4, fin.size(), f);\n  fwrite(out.data(), 4, out.size(), f);\n"),
+    ]
+    for a, b in subs:
+        assert a in d, a
+        d = d.replace(a, b, 1)
+    return d
+
+
+def build_mip(tmp):
+    pre = PRELUDE + ("extern vec4 gl_FragCoord, gl_FragColor, gl_TexCoord[1]; extern mat4x4 gl_TextureMatrix[1]; "
+                     "extern mat3 gl_NormalMatrix;\n")
+    parts = [pre]
+    for n, main in (("Volume3D.glsl", "unused_main"), ("GLRaycaster-MIP-Rot-FS.glsl", "mip_main"),
+                    ("Transfer-MIP-FS.glsl", "transfer_main")):
+        parts.append("// ---- %s\n" % n + rewrite(read_shader(n), main))
+    return _compile(tmp, "mip_as_cpp", "\n".join(parts) + _mip_driver())
+
+
+def run_mip(exe, tmp, params, inv_proj, imv, norm, bricks, n_bricks, brick_arrays, tf1d):
+    """Returns (rgba [h*w, 4], blended maximum image [h*w, 4] = (max, max, max, coverage))."""
+    w, h = params.width, params.height
+    zero3 = [0.0, 0.0, 0.0]
+    tf = np.ascontiguousarray(tf1d, np.uint8).reshape(-1, 4)
+    buf = [struct.pack("<II", w, h), np.asarray(inv_proj, np.float32).tobytes(), np.asarray(imv, np.float32).tobytes(),
+           struct.pack("<5f", params.trans_scale, 1.0, 1.0, params.sample_rate_modifier, norm)]
+    for _ in range(5):                                             # domain scale + light terms: unused by the MIP shaders
+        buf.append(np.asarray(zero3, np.float32).tobytes())
+    buf.append(struct.pack("<5I", params.dtype, params.nearest, len(tf), 1, n_bricks))
+    buf.append(tf.tobytes())
+    for i in range(n_bricks):
+        b = bricks[i]
+        buf.append(np.asarray(list(b.center) + list(b.ext) + list(b.tex_min) + list(b.tex_max), np.float32).tobytes())
+        buf.append(struct.pack("<4I", b.n_vox[0], b.n_vox[1], b.n_vox[2], int(b.empty)))
+        if not b.empty:
+            buf.append(np.ascontiguousarray(brick_arrays[i]).tobytes())
+    fin, fout = os.path.join(str(tmp), "mip.bin"), os.path.join(str(tmp), "mip_out.bin")
+    with open(fin, "wb") as f:
+        f.write(b"".join(buf))
+    subprocess.check_call([exe, fin, fout])
+    raw = np.fromfile(fout, np.float32).reshape(2, h * w, 4)
+    return raw[0], raw[1]

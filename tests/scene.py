@@ -248,6 +248,23 @@ class Scene:
         dist = np.array([bricks[i].distance for i in range(n)], np.float32)
         return dict(image=img, rgba8=orc.rgba8(img), lod=lod, order=order, distance=dist, samples=st.samples)
 
+    def oracle_mip(self, use_mip_lod=True, threads=8):
+        """One HQ MIP frame (AbstrRenderer::PlanHQMIPFrame + GLRaycaster::RenderHQMIPInLoop per brick + Transfer-MIP)."""
+        o = self.octree
+        pool, _ = self.oracle_pool()
+        p = self.oracle_params(pool)
+        lod = orc.mip_lod(p, self.pool_lod_count(), use_mip_lod)
+        bc = o.brick_count(lod)
+        first = o.brick_index(0, 0, 0, lod)
+        mm = o.minmax[first:first + bc[0] * bc[1] * bc[2]]
+        bricks, n = orc.mip_brick_list(p, lod, self.overlap, mm, self.visibility_args())
+        data = [None if bricks[i].empty else o.brick(*bricks[i].coord, lod) for i in range(n)]
+        img, mx, st = orc.mip_render(p, lod, bricks, n, data, self.tf1d.GetByteArray(), threads)
+        img = img.reshape(self.height, self.width, 4)
+        order = np.array([[bricks[i].index, bricks[i].empty] for i in range(n)], np.int64).reshape(-1, 2)
+        return dict(image=img, rgba8=orc.rgba8(img), max=mx.reshape(self.height, self.width, 2), lod=lod, order=order,
+                    samples=st.samples, bricks=bricks, n=n, data=data, params=p)
+
     # ------------------------------------------------------------- product side
     def make_renderer(self, source="device", device=0):
         """CUDA renderer for the same scene.  source: 'device' = GPU bricker (tvk_build_volume),

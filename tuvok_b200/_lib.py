@@ -127,6 +127,8 @@ SIGNATURES = {
     "tvk_get_device_image": (C.c_int, [P, C.POINTER(P)]),
     "tvk_read_iso_buffers": (C.c_int, [P, P, P]),
     "tvk_render_classic": (C.c_int, [P, C.POINTER(FrameStats)]),
+    "tvk_render_mip": (C.c_int, [P, C.c_int, C.POINTER(FrameStats)]),
+    "tvk_read_mip_max": (C.c_int, [P, P]),
     "tvk_get_classic_brick_list": (C.c_int, [P, C.POINTER(C.c_uint32), P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "tvk_composite_over": (C.c_int, [P, P, P, P, C.c_uint64]),
     "tvk_quantize_rgba8": (C.c_int, [P, P, P, C.c_uint64]),

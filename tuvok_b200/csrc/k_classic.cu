@@ -16,6 +16,11 @@
 //                           -2D-light-FS.glsl:61-117 with VRender1D(.Lit).glsl, Volume3D.glsl:39-60,
 //                           lighting.glsl:33-50 (eye at the origin), Compositing.glsl:33-38
 //   per-brick step / opacity exponent   SetBrickDepShaderVars (GLRaycaster.cpp:239-300)
+// MODE 2 is the HQ MIP frame of the 2D windows (GLRenderer.cpp:1183-1253, GLRaycaster::RenderHQMIPInLoop
+// GLRaycaster.cpp:494-530): the same two passes per brick, but the back-face pass runs
+// GLRaycaster-MIP-Rot-FS.glsl:47-77 (maximum of texture3D(texVolume).x along the ray), bricks are blended with
+// BE_MAX (order-free, so the cell walk needs no sorting argument at all), and Transfer-MIP-FS.glsl:43-52
+// maps the blended maximum through the 1D transfer function (opacity ignored) -- fused into the same thread.
 // The bricks live in the same slot-linear pool as the GridLeaper path (the reference keeps one 3D texture per
 // brick in GPUMemMan's LRU cache, GPUMemMan.cpp:846-996); the per-brick table maps a brick of the LoD to its
 // slot.  Same arithmetic contract as k_raycast.cu (-fmad=false, explicit fmaf in lerps / dots / compositing).
@@ -82,7 +87,7 @@ __device__ __forceinline__ f4 tf_fetch(const ClassicConsts& P, float s, float t)
   return r;
 }
 
-// MODE: 0 = 1D TF, 1 = 2D TF
+// MODE: 0 = 1D TF, 1 = 2D TF, 2 = HQ MIP
 template <typename T, int MODE, bool LIT>
 __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ ClassicConsts P) {
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
   if (px >= P.width || py >= P.height) return;
   const size_t pix = (size_t)py * P.width + px;
   const uint32_t S = P.axis_stride;
-  f4 acc; acc.x = acc.y = acc.z = acc.w = 0.0f;
+  f4 acc; acc.x = acc.y = acc.z = acc.w = 0.0f;   // MIP: x = blended maximum, w = coverage (the blended alpha)
   unsigned long long n_samples = 0;
 
   // the eye ray through the pixel centre: eye-space points s * pn, world-space o + s * d
@@ -169,6 +174,20 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
           rd = F3(rd.x / len, rd.y / len, rd.z / len);
           const f3 inc = scl3(rd, ray_step);
           const T* vox = pool + (uint64_t)(slot1 - 1u) * P.slot_voxels;
+          if (MODE == 2) {   // GLRaycaster-MIP-Rot-FS.glsl:64-76, then glBlendEquation(GL_MAX)
+            float mx = 0.0f;
+            f3 ct = et;
+#pragma unroll 1
+            for (int s = 0; s < count; s++) {
+              BrickTex<T> tx;
+              tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+              mx = fmaxf(mx, tx.tap(0, 0, 0));
+              ct = add3(ct, inc_tex);
+            }
+            n_samples += (unsigned long long)count;
+            acc.x = fmaxf(acc.x, mx);
+            acc.w = 1.0f;
+          } else {
           f4 col; col.x = col.y = col.z = col.w = 0.0f;
           f3 ct = et, cp = entry;
 #pragma unroll 1
@@ -209,6 +228,7 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
           const float k = 1.0f - acc.w;
           acc.x = fmaf(k, col.x, acc.x); acc.y = fmaf(k, col.y, acc.y);
           acc.z = fmaf(k, col.z, acc.z); acc.w = fmaf(k, col.w, acc.w);
+          }   // DVR modes
         }
       }
       // leave the cell through the nearest of its far planes
@@ -225,14 +245,23 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
       if (cell[ax] < 0 || cell[ax] >= (int)lay[ax]) break;
     }
   }
-  P.out[pix] = make_float4(acc.x, acc.y, acc.z, acc.w);
+  if (MODE == 2) {   // Transfer-MIP-FS.glsl:43-52 (1D transfer function, opacity ignored; uncovered pixels black)
+    if (P.out_max) P.out_max[pix] = make_float2(acc.x, acc.w);
+    f4 t; t.x = t.y = t.z = 0.0f;
+    if (acc.w > 0.5f) t = tf_fetch(P, acc.x * P.trans_scale, 0.0f);
+    P.out[pix] = make_float4(t.x, t.y, t.z, 1.0f);
+  } else {
+    P.out[pix] = make_float4(acc.x, acc.y, acc.z, acc.w);
+  }
   if (P.count) atomicAdd(P.counters, n_samples);
 }
 
 template <typename T>
 void launch_t(const ClassicConsts& c, int mode, int lighting, cudaStream_t s) {
   const dim3 block(64), grid((c.width + 7) / 8, (c.height + 7) / 8);
-  if (mode == TVK_RM_1DTRANS) {
+  if (mode == TVK_CLASSIC_MIP) {
+    classic_kernel<T, 2, false><<<grid, block, 0, s>>>(c);
+  } else if (mode == TVK_RM_1DTRANS) {
     if (lighting) classic_kernel<T, 0, true><<<grid, block, 0, s>>>(c);
     else classic_kernel<T, 0, false><<<grid, block, 0, s>>>(c);
   } else {

@@ -92,8 +92,11 @@ struct ClassicConsts {
   const void* pool;
   uint64_t slot_voxels;
   float4* out;
+  float2* out_max;                  // HQ MIP only: (blended maximum, coverage) per pixel, the FBO Transfer-MIP reads
   unsigned long long* counters;
 };
+// mode: TVK_RM_1DTRANS / TVK_RM_2DTRANS, or TVK_CLASSIC_MIP for the HQ MIP frame
+#define TVK_CLASSIC_MIP 3
 void launch_classic(const ClassicConsts& c, int mode, int lighting, int dtype, cudaStream_t s);
 
 // page table / visibility (k_pool.cu)

@@ -1593,14 +1593,18 @@ int ensure_classic(tvk_ctx* ctx, size_t axis_words, size_t table_words) {
 
 extern "C" {
 
-int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
+// One frame of the per-brick renderer.  mip = false: the 3D view (GLRenderer::Render3DView); mip = true: the HQ MIP
+// frame of a 2D window (GLRenderer.cpp:1183-1253) -- the caller has put m_maMIPRotation * view into model_view
+// (GLRaycaster::RenderHQMIPPreLoop, GLRaycaster.cpp:481-492).
+static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use_mip_lod) {
   if (!ctx) return TVK_ERR_INVALID;
   cudaSetDevice(ctx->cfg.device);
   if (st) std::memset(st, 0, sizeof(*st));
   int rc = check_renderable(ctx);
   if (rc) return rc;
   const tvk_render_params& p = ctx->params;
-  if (p.mode == TVK_RM_ISOSURFACE) return fail(ctx, TVK_ERR_INVALID, "classic path: isosurface mode is not built yet");
+  if (!mip && p.mode == TVK_RM_ISOSURFACE) return fail(ctx, TVK_ERR_INVALID, "classic path: isosurface mode is not built yet");
+  if (mip && !ctx->tf1d_d) return fail(ctx, TVK_ERR_INVALID, "MIP: no 1D transfer function set (Transfer-MIP-FS needs it)");
   rc = ensure_frame(ctx, p.width, p.height);
   if (rc) return rc;
   // ---- AbstrRenderer::ComputeMinLODForCurrentView (AbstrRenderer.cpp:789-803, CullingLOD.cpp:126-138) ----
@@ -1613,6 +1617,19 @@ int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
   const float fz = std::fmax(z_near, -p.model_view[14]);
   int lod_i = (int)floorf(logf(p.lod_factor * fz / lzwse) / logf(2.0f));
   lod_i = std::max(0, std::min(lod_i, (int)ctx->pool_lod_count - 1));   // the brick store holds the pool LoDs
+  if (mip) {   // ---- AbstrRenderer::PlanHQMIPFrame (AbstrRenderer.cpp:1214-1245) ----
+    uint32_t vc[3] = {ctx->vol[0], ctx->vol[1], ctx->vol[2]};
+    uint64_t l = 0;
+    if (use_mip_lod) {
+      const uint32_t win = std::max(p.width, p.height);
+      while (std::min(vc[0], std::min(vc[1], vc[2])) >= win) {
+        for (int i = 0; i < 3; i++) vc[i] /= 2;
+        l++;
+      }
+    }
+    if (l > 0) l = std::min<uint64_t>(ctx->pool_lod_count - 1, l - 1);
+    lod_i = (int)l;
+  }
   const uint32_t lod = (uint32_t)lod_i;
 
   // ---- AbstrRenderer::BuildSubFrameBrickList (AbstrRenderer.cpp:999-1100) ----
@@ -1650,7 +1667,7 @@ int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
         for (int a = 0; a < 3; a++) { cm[a] = tab[a].center_md[ci[a]]; em[a] = tab[a].ext_md[ci[a]]; }
         // CullingLOD::IsVisible (CullingLOD.cpp:141-160) on the box scaled like RegionNeedsBrick does
         bool visible = true;
-        for (int i = 0; i < 6 && visible; i++) {
+        for (int i = 0; i < 6 && visible && !mip; i++) {   // HQ MIP: m_FrustumCullingLOD.SetPassAll(true)
           const float* pl = planes[i];
           const float cx = cm[0] * sc[0], cy = cm[1] * sc[1], cz = cm[2] * sc[2];
           const float hx = 0.5f * (em[0] * sc[0]), hy = 0.5f * (em[1] * sc[1]), hz = 0.5f * (em[2] * sc[2]);
@@ -1664,10 +1681,12 @@ int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
         const double* mm = &ctx->minmax_h[4 * (ctx->toc_offset[lod] + b.index)];
         bool has;
         if (p.mode == TVK_RM_1DTRANS) has = v1 >= mm[0] && v0 <= mm[1];
-        else has = (v1 >= mm[0] && v0 <= mm[1]) && (v3 >= mm[2] && v2 <= mm[3]);
+        else if (p.mode == TVK_RM_2DTRANS) has = (v1 >= mm[0] && v0 <= mm[1]) && (v3 >= mm[2] && v2 <= mm[3]);
+        else has = p.isovalue <= mm[1];   // legacy one-sided iso test (uvfDataset.cpp:1201-1210)
         b.empty = has ? 0 : 1;
         b.distance = 0.0f;
-        if (has) {   // brick_distance (AbstrRenderer.cpp:808-841)
+        // HQ MIP: BuildSubFrameBrickList(true) orders by residency only (0 / 1) and BE_MAX blending is order-free
+        if (has && !mip) {   // brick_distance (AbstrRenderer.cpp:808-841)
           float dmin = std::numeric_limits<float>::max();
           for (int k = 0; k < 8; k++) {
             float q[3];
@@ -1780,7 +1799,7 @@ int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
   c.step_scale = 1.0f / p.sample_rate_modifier *
                  std::fmax((float)ctx->vol[0] / (float)ctx->lod_size[lod][0],
                            std::fmax((float)ctx->vol[1] / (float)ctx->lod_size[lod][1], (float)ctx->vol[2] / (float)ctx->lod_size[lod][2]));
-  if (p.mode == TVK_RM_2DTRANS) { c.tf = ctx->tf2d_d; c.tf_w = ctx->tf2d_w; c.tf_h = ctx->tf2d_h; }
+  if (p.mode == TVK_RM_2DTRANS && !mip) { c.tf = ctx->tf2d_d; c.tf_w = ctx->tf2d_w; c.tf_h = ctx->tf2d_h; }
   else { c.tf = ctx->tf1d_d; c.tf_w = ctx->tf1d_n; c.tf_h = 1; }
   c.nearest = p.nearest;
   c.count = ctx->counters_on ? 1 : 0;
@@ -1793,9 +1812,10 @@ int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
   c.pool = ctx->pool_d;
   c.slot_voxels = ctx->slot_voxels;
   c.out = ctx->buf[0];
+  c.out_max = mip ? reinterpret_cast<float2*>(ctx->buf[1]) : nullptr;   // m_pFBO3DImageNext[1] of the MIP frame
   c.counters = ctx->counters_d;
   if (ctx->counters_on) CU(cudaMemsetAsync(ctx->counters_d, 0, 8 * sizeof(unsigned long long), s));
-  launch_classic(c, p.mode, p.lighting, ctx->dtype, s);
+  launch_classic(c, mip ? TVK_CLASSIC_MIP : p.mode, p.lighting, ctx->dtype, s);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], s));
   if (ctx->counters_on) CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -1810,6 +1830,19 @@ int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) {
     cudaEventElapsedTime(&st->ms_raycast, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[2]);
   }
+  return TVK_OK;
+}
+
+int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* st) { return render_per_brick(ctx, st, false, 0); }
+
+int tvk_render_mip(tvk_ctx* ctx, int use_mip_lod, tvk_frame_stats* st) { return render_per_brick(ctx, st, true, use_mip_lod); }
+
+int tvk_read_mip_max(tvk_ctx* ctx, float* dst) {
+  if (!ctx || !dst) return TVK_ERR_INVALID;
+  if (!ctx->buf[1]) return fail(ctx, TVK_ERR_INVALID, "no MIP frame rendered");
+  cudaSetDevice(ctx->cfg.device);
+  CU(cudaMemcpyAsync(dst, ctx->buf[1], (size_t)ctx->params.width * ctx->params.height * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return TVK_OK;
 }
 

@@ -43,6 +43,45 @@ def rotation_y(deg):
     return m
 
 
+def matmul4(a, b):
+    """FLOATMATRIX4::operator* (Basics/Vectors.h:936-946): row-vector product, fp32, summed left to right."""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    r = a[:, 0:1] * b[0:1, :]
+    for k in (1, 2, 3):
+        r = (r + a[:, k:k + 1] * b[k:k + 1, :]).astype(np.float32)
+    return r
+
+
+def mip_rotation(window_mode="coronal", angle_deg=0.0, flip=(False, False), region_rotation=None):
+    """m_maMIPRotation of GLRenderer::RenderHQMIPPreLoop (GLRenderer.cpp:1256-1285): matRotDir * region.rotation *
+    matFlipX * matFlipY * RotationY(angle); sines / cosines in double, then cast (FLOATMATRIX4::RotationX/Y)."""
+    def rx(a):
+        m = np.eye(4, dtype=np.float32)
+        c, s_ = np.float32(np.cos(a)), np.float32(np.sin(a))
+        m[1, 1] = c; m[1, 2] = s_; m[2, 1] = -s_; m[2, 2] = c
+        return m
+
+    def ry(a):
+        m = np.eye(4, dtype=np.float32)
+        c, s_ = np.float32(np.cos(a)), np.float32(np.sin(a))
+        m[0, 0] = c; m[0, 2] = -s_; m[2, 0] = s_; m[2, 2] = c
+        return m
+
+    pi = 3.141592653589793238462643383
+    if window_mode == "sagittal":
+        rot_dir = matmul4(rx(-pi / 2.0), ry(-pi / 2.0))
+    elif window_mode == "axial":
+        rot_dir = rx(-pi / 2.0)
+    elif window_mode == "coronal":
+        rot_dir = np.eye(4, dtype=np.float32)
+    else:
+        raise ValueError("Invalid windowmode set")
+    flip_y = np.diag([-1.0 if flip[0] else 1.0, 1.0, 1.0, 1.0]).astype(np.float32)
+    flip_x = np.diag([1.0, -1.0 if flip[1] else 1.0, 1.0, 1.0]).astype(np.float32)
+    reg = np.eye(4, dtype=np.float32) if region_rotation is None else np.asarray(region_rotation, np.float32)
+    return matmul4(matmul4(matmul4(matmul4(rot_dir, reg), flip_x), flip_y), ry(pi * float(angle_deg) / 180.0))
+
+
 def translation(x, y, z):
     m = np.eye(4, dtype=np.float32)
     m[3, :3] = (x, y, z)
@@ -386,6 +425,38 @@ class CudaGridLeaper:
         self.last_stats = st
         self._converged = True
         return st
+
+    def SetMIPRotationAngle(self, angle_deg):
+        """AbstrRenderer::SetMIPRotationAngle (AbstrRenderer.h:545-547)."""
+        self._mip_angle = float(angle_deg)
+
+    def SetMIPLOD(self, on):
+        """AbstrRenderer::SetMIPLOD (AbstrRenderer.h:385)."""
+        self._mip_lod = bool(on)
+
+    def PaintHQMIP(self, window_mode="coronal", flip=(False, False), region_rotation=None):
+        """One HQ MIP frame of a 2D window in MIP mode (GLRenderer.cpp:1183-1253): modelView = m_maMIPRotation * view
+        (GLRaycaster::RenderHQMIPPreLoop), PlanHQMIPFrame's LoD, per-brick maximum, BE_MAX blending, Transfer-MIP."""
+        keep = (self._rotation, self._translation)
+        self._rotation = mip_rotation(window_mode, getattr(self, "_mip_angle", 0.0), flip, region_rotation)
+        self._translation = np.eye(4, dtype=np.float32)
+        self._dirty = True
+        try:
+            self._push_params()
+            st = L.FrameStats()
+            self._ck(self._lib.tvk_render_mip(self._h, 1 if getattr(self, "_mip_lod", True) else 0, C.byref(st)))
+        finally:
+            self._rotation, self._translation = keep
+            self._dirty = True
+        self.last_stats = st
+        self._converged = True
+        return st
+
+    def mip_max_image(self):
+        """(h, w, 2) float32: blended maximum and coverage of the last MIP frame (parity tap)."""
+        out = np.empty((self.params.height, self.params.width, 2), np.float32)
+        self._ck(self._lib.tvk_read_mip_max(self._h, _ptr(out)))
+        return out
 
     def classic_brick_list(self):
         """(lod, ndarray [n, 2] of (BrickKey index, bIsEmpty), distances) of the last classic frame, depth sorted
