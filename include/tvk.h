@@ -303,6 +303,26 @@ int tvk_read_mip_max(tvk_ctx* ctx, float* dst);
 /* parity tap: the brick list of the last classic / MIP frame (depth sorted; MIP: key order) and its LoD */
 int tvk_get_classic_brick_list(tvk_ctx* ctx, uint32_t* lod, tvk_classic_brick* dst, uint32_t cap, uint32_t* n);
 
+/* ---- stereo (GLRenderer::ComputeViewAndProjection in stereo, GLRenderer::EndFrame) ------------------- */
+/* AbstrRenderer::EStereoMode (Renderer/AbstrRenderer.h:128-134) */
+typedef enum { TVK_SM_RB = 0, TVK_SM_SCANLINE = 1, TVK_SM_SBS = 2, TVK_SM_AF = 3 } tvk_stereo_mode;
+/* tvk_compute_view for the two eyes: FLOATMATRIX4::BuildStereoLookAtAndProjection (Basics/Vectors.h:1215-1248:
+ * off-centre frusta shifted by eye_dist * near / focal_length, views translated by +-eye_dist) as
+ * GLRenderer::ComputeViewAndProjection calls it (GLRenderer.cpp:904-910), then modelView[eye] = rotation *
+ * translation * view[eye].  Defaults of the reference: focal_length 1.0, eye_dist 0.02 (AbstrRenderer.cpp:142-143). */
+int tvk_compute_stereo_view(tvk_render_params* left, tvk_render_params* right, uint32_t width, uint32_t height,
+                            const float rotation[16], const float translation[16],
+                            const float eye[3], const float at[3], const float up[3],
+                            float fov_deg, float z_near, float z_far, float screen_space_error,
+                            float focal_length, float eye_dist);
+/* keeps the finished image of the current frame as eye 0 (left, m_pFBO3DImageNext[0]) or 1 (right, [1]) */
+int tvk_stereo_keep_eye(tvk_ctx* ctx, int eye);
+/* GLRenderer::EndFrame (GLRenderer.cpp:758-812): composes the two kept eye images with
+ * Compose-Anaglyphs-FS / Compose-Scanline-FS / Compose-SBS-FS (split_coord = fSplitCoord, 0.5 at full resolution) /
+ * Compose-AF-FS (alternating_frame_id = m_iAlternatingFrameID); eye_swap = m_bStereoEyeSwap.  The composed frame
+ * becomes the image tvk_read_rgba8 / tvk_read_rgba32f / tvk_get_device_image return until the next frame. */
+int tvk_stereo_compose(tvk_ctx* ctx, int mode, int eye_swap, int alternating_frame_id, float split_coord);
+
 /* ---- sort-last compositing (new) --------------------------------------- */
 /* out = front + (1-front.a)*back on n_pixels premultiplied RGBA32F device pixels
  * (Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153); a front pixel with alpha > 0.99

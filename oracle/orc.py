@@ -136,6 +136,8 @@ def lib():
                                                 C.c_uint32]),
         "orc_classic_render": (None, [C.POINTER(RenderParams), C.c_uint32, P, C.c_uint32, P, P, P,
                                       C.POINTER(RenderStats), C.c_int]),
+        "orc_stereo_view": (None, [P, P, P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, P, P, P, P]),
+        "orc_stereo_compose": (None, [C.c_int, P, P, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, P]),
         "orc_mip_lod": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_int]),
         "orc_mip_brick_list": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, P, C.c_double * 4, P,
                                             C.c_uint32]),
@@ -455,3 +457,24 @@ def mip_render(params, lod, bricks, n, brick_arrays, tf1d, threads=1):
     lib().orc_mip_render(C.byref(params), lod, C.cast(bricks, C.c_void_p), n, C.cast(ptrs, C.c_void_p), _p(tfb), len(tfb),
                          _p(mx), _p(out), C.byref(st), threads)
     return out, mx, st
+
+
+SM_RB, SM_SCANLINE, SM_SBS, SM_AF = 0, 1, 2, 3          # AbstrRenderer::EStereoMode
+
+
+def stereo_view(eye, at, up, fov_deg, aspect, z_near, z_far, focal_length, eye_dist):
+    """FLOATMATRIX4::BuildStereoLookAtAndProjection -> (view_left, view_right, proj_left, proj_right), 4x4 float32."""
+    e, a, u = (np.ascontiguousarray(v, np.float32) for v in (eye, at, up))
+    out = [np.zeros((4, 4), np.float32) for _ in range(4)]
+    lib().orc_stereo_view(_p(e), _p(a), _p(u), fov_deg, aspect, z_near, z_far, focal_length, eye_dist, *[_p(o) for o in out])
+    return tuple(out)
+
+
+def stereo_compose(mode, left, right, eye_swap=False, alternating_frame_id=0, split_coord=0.5):
+    """GLRenderer::EndFrame's eye composition (Compose-{Anaglyphs,Scanline,SBS,AF}-FS.glsl) of two (h, w, 4) images."""
+    l, r = np.ascontiguousarray(left, np.float32), np.ascontiguousarray(right, np.float32)
+    assert l.shape == r.shape and l.ndim == 3 and l.shape[2] == 4
+    out = np.zeros_like(l)
+    lib().orc_stereo_compose(mode, _p(l), _p(r), l.shape[1], l.shape[0], int(bool(eye_swap)), alternating_frame_id,
+                             split_coord, _p(out))
+    return out

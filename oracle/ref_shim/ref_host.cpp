@@ -12,6 +12,8 @@
 //     cull  fov aspect near far pixels_y  model[16] view[16] proj[16]  n  (cx cy cz ex ey ez vx vy vz)*n
 //     tf1d  n center inv_gradient
 //     uniforms mv[16] vol[3] scale[3] light_dir[3] eye[3]   (SetupRaycastShader / ComputeEyeToModelMatrix)
+//     stereo ex ey ez  ax ay az  ux uy uz  fov aspect near far focal_length eye_dist
+//           (FLOATMATRIX4::BuildStereoLookAtAndProjection as GLRenderer::ComputeViewAndProjection calls it)
 //     miprot window(0 sagittal,1 axial,2 coronal) flipx flipy angle_deg region_rotation[16] view[16]
 //           (the statements of GLRenderer::RenderHQMIPPreLoop + GLRaycaster::RenderHQMIPPreLoop on FLOATMATRIX4)
 #include <cstdio>
@@ -61,6 +63,13 @@ int main(int argc, char** argv) {
     } else if (op == "mul") {
       FLOATMATRIX4 a, b; read16(ls, a); read16(ls, b);
       put16(out, "mul", a * b);
+    } else if (op == "stereo") {
+      FLOATVECTOR3 e, a, u; float fov, aspect, n, f, focal, dist;
+      ls >> e.x >> e.y >> e.z >> a.x >> a.y >> a.z >> u.x >> u.y >> u.z >> fov >> aspect >> n >> f >> focal >> dist;
+      FLOATMATRIX4 vl, vr, pl, pr;
+      FLOATMATRIX4::BuildStereoLookAtAndProjection(e, a, u, fov, aspect, n, f, focal, dist, vl, vr, pl, pr);   // GLRenderer.cpp:905-910
+      put16(out, "view_left", vl); put16(out, "view_right", vr);
+      put16(out, "proj_left", pl); put16(out, "proj_right", pr);
     } else if (op == "miprot") {
       int wm, fx, fy; float angle;
       ls >> wm >> fx >> fy >> angle;

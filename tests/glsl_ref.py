@@ -635,3 +635,57 @@ def run_mip(exe, tmp, params, inv_proj, imv, norm, bricks, n_bricks, brick_array
     subprocess.check_call([exe, fin, fout])
     raw = np.fromfile(fout, np.float32).reshape(2, h * w, 4)
     return raw[0], raw[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Stereo eye composition (GLRenderer::EndFrame, GLRenderer.cpp:758-812): Compose-{Anaglyphs,Scanline,SBS,AF}-FS.glsl
+# executed over a full-screen quad on two RGBA32F eye images (GL_NEAREST FBOs).
+# ---------------------------------------------------------------------------------------------------------------------
+STEREO_DRIVER = r"""
+sampler2D texRightEye, texLeftEye; vec2 vScreensize; float fSplitCoord; int iAlternatingFrameID;
+vec4 gl_FragColor, gl_TexCoord[1];
+#include <cstdio>
+#include <cstdlib>
+int main(int argc, char** argv) {
+  FILE* f = fopen(argv[1], "rb");
+  uint32_t hd[5]; float split;
+  if (fread(hd, 4, 5, f) != 5 || fread(&split, 4, 1, f) != 1) abort();
+  const uint32_t W = hd[0], H = hd[1], mode = hd[2], swap = hd[3];
+  const size_t n = (size_t)W * H * 4;
+  std::vector<float> l(n), r(n), out(n);
+  if (fread(l.data(), 4, n, f) != n || fread(r.data(), 4, n, f) != n) abort();
+  fclose(f);
+  // m_bStereoEyeSwap exchanges the texture units the two FBOs are bound to (GLRenderer.cpp:773-779)
+  texLeftEye.f32 = swap ? r.data() : l.data(); texRightEye.f32 = swap ? l.data() : r.data();
+  texLeftEye.w = texRightEye.w = W; texLeftEye.h = texRightEye.h = H;
+  vScreensize = vec2((float)W, (float)H); fSplitCoord = split; iAlternatingFrameID = (int)hd[4];
+  for (uint32_t y = 0; y < H; y++)
+    for (uint32_t x = 0; x < W; x++) {
+      gl_TexCoord[0] = vec4(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H, 0.0f, 1.0f);
+      gl_FragColor = vec4();
+      if (mode == 0) rb_main(); else if (mode == 1) scan_main(); else if (mode == 2) sbs_main(); else af_main();
+      memcpy(&out[4 * ((size_t)y * W + x)], &gl_FragColor.x, 16);
+    }
+  f = fopen(argv[2], "wb"); fwrite(out.data(), 4, n, f); fclose(f);
+  return 0;
+}
+"""
+
+
+def build_stereo(tmp):
+    parts = [PRELUDE + "extern vec4 gl_FragColor, gl_TexCoord[1];\n"]
+    for n, main in (("Compose-Anaglyphs-FS.glsl", "rb_main"), ("Compose-Scanline-FS.glsl", "scan_main"),
+                    ("Compose-SBS-FS.glsl", "sbs_main"), ("Compose-AF-FS.glsl", "af_main")):
+        parts.append("// ---- %s\n" % n + rewrite(read_shader(n), main))
+    return _compile(tmp, "stereo_as_cpp", "\n".join(parts) + STEREO_DRIVER)
+
+
+def run_stereo(exe, tmp, mode, left, right, eye_swap=False, alternating_frame_id=0, split_coord=0.5):
+    h, w = left.shape[:2]
+    fin, fout = os.path.join(str(tmp), "stereo.bin"), os.path.join(str(tmp), "stereo_out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<5If", w, h, mode, int(bool(eye_swap)), alternating_frame_id, split_coord))
+        f.write(np.ascontiguousarray(left, np.float32).tobytes())
+        f.write(np.ascontiguousarray(right, np.float32).tobytes())
+    subprocess.check_call([exe, fin, fout])
+    return np.fromfile(fout, np.float32).reshape(h, w, 4)

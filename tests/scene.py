@@ -85,6 +85,11 @@ class Scene:
     def matrices(self):
         view = look_at(self.eye, (0, 0, 0), (0, 1, 0))
         proj = perspective(self.fov, F(self.width) / F(self.height), 0.01, 1000.0)
+        if getattr(self, "stereo_eye", None) is not None:   # (eye 0 = left / 1 = right, focal length, eye distance)
+            e, focal, dist = self.stereo_eye
+            vl, vr, pl, pr = orc.stereo_view(self.eye, (0, 0, 0), (0, 1, 0), self.fov, float(F(self.width) / F(self.height)),
+                                             0.01, 1000.0, focal, dist)
+            view, proj = (vl, pl) if e == 0 else (vr, pr)
         mv = ((self.rotation @ self.translation).astype(F) @ view).astype(F)
         return mv, proj
 

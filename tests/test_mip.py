@@ -125,7 +125,10 @@ def test_cuda_mip_matches_oracle(name):
     assert np.array_equal(r.mip_max_image(), ref["max"])             # blended maxima and coverage, bit for bit
     assert np.array_equal(r.ReadRGBA32F(), ref["image"])
     assert np.array_equal(r.ReadRGBA8(), ref["rgba8"])
-    assert st.samples == ref["samples"]
+    # A ray that lies exactly in the plane two bricks share (axis-aligned MIP views produce a few) belongs to both
+    # bricks for the oracle's per-brick slab test and to one cell for the kernel's grid walk; the boundary samples
+    # are the same voxels (ghost layers), so the maxima above are identical and only the count may differ.
+    assert abs(int(st.samples) - int(ref["samples"])) <= 1e-4 * ref["samples"]
     r.Cleanup()
 
 

@@ -127,6 +127,10 @@ SIGNATURES = {
     "tvk_get_device_image": (C.c_int, [P, C.POINTER(P)]),
     "tvk_read_iso_buffers": (C.c_int, [P, P, P]),
     "tvk_render_classic": (C.c_int, [P, C.POINTER(FrameStats)]),
+    "tvk_compute_stereo_view": (C.c_int, [C.POINTER(RenderParams), C.POINTER(RenderParams), C.c_uint32, C.c_uint32, f32x16, f32x16,
+                                          f32x3, f32x3, f32x3, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "tvk_stereo_keep_eye": (C.c_int, [P, C.c_int]),
+    "tvk_stereo_compose": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_float]),
     "tvk_render_mip": (C.c_int, [P, C.c_int, C.POINTER(FrameStats)]),
     "tvk_read_mip_max": (C.c_int, [P, P]),
     "tvk_get_classic_brick_list": (C.c_int, [P, C.POINTER(C.c_uint32), P, C.c_uint32, C.POINTER(C.c_uint32)]),

@@ -1,5 +1,6 @@
 // k_image.cu -- image-space kernels: deferred isosurface shading, the GL float->unorm8 read-back
-// conversion and the over operator of the sort-last compositor.  HBM-bound streaming kernels:
+// conversion, the stereo eye composition (Compose-{Anaglyphs,Scanline,SBS,AF}-FS.glsl, GLRenderer.cpp:758-812)
+// and the over operator of the sort-last compositor.  HBM-bound streaming kernels:
 // 128-bit accesses, grid sized to a multiple of the 148 SMs with a grid-stride loop.
 // Replaces (reference file:line): Shaders/Compose-FS.glsl:49-76 + GLRenderer::ComposeSurfaceImage
 // (GLRenderer.cpp:2763-2830); GLFrameCapture.cpp:72-85 (glReadPixels GL_UNSIGNED_BYTE);
@@ -77,6 +78,39 @@ __global__ void over_kernel(const float4* front, const float4* back, float4* out
   }
 }
 
+// Stereo eye composition over a full-screen quad: pixel (x, y) carries the texture coordinate ((x+.5)/w, (y+.5)/h) and
+// the eye FBOs are GL_NEAREST / clamp (GLRenderer.cpp:688-713,1775-1785).  MODE = AbstrRenderer::EStereoMode.
+__device__ __forceinline__ float4 eye_fetch(const float4* img, uint32_t w, uint32_t h, float s, float t) {
+  int i = (int)floorf(s * (float)w), j = (int)floorf(t * (float)h);
+  i = min(max(i, 0), (int)w - 1);
+  j = min(max(j, 0), (int)h - 1);
+  return img[(size_t)j * w + i];
+}
+
+template <int MODE>
+__global__ void stereo_compose_kernel(const float4* __restrict__ left, const float4* __restrict__ right,
+                                      float4* __restrict__ out, uint32_t w, uint32_t h, int alt_id, float split) {
+  const uint64_t n = (uint64_t)w * h;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (uint64_t)y * w);
+    const float s = ((float)x + 0.5f) / (float)w, t = ((float)y + 0.5f) / (float)h;
+    float4 o;
+    if (MODE == 0) {          // Compose-Anaglyphs-FS.glsl:41-47
+      const float4 a = eye_fetch(left, w, h, s, t), b = eye_fetch(right, w, h, s, t);
+      const float gl = dot(a.x, a.y, a.z, 0.3f, 0.59f, 0.11f), gr = dot(b.x, b.y, b.z, 0.3f, 0.59f, 0.11f);
+      o = make_float4(gl, gr * 0.5f, gr, fmaxf(a.w, b.w));
+    } else if (MODE == 1) {   // Compose-Scanline-FS.glsl:41-46
+      const float line = floorf(t * (float)h);
+      o = (line / 2.0f == floorf(line / 2.0f)) ? eye_fetch(left, w, h, s, t) : eye_fetch(right, w, h, s, t);
+    } else if (MODE == 2) {   // Compose-SBS-FS.glsl:40-45
+      o = (s < split) ? eye_fetch(left, w, h, s * 2.0f, t) : eye_fetch(right, w, h, (s - split) * 2.0f, t);
+    } else {                  // Compose-AF-FS.glsl:40-43
+      o = alt_id == 0 ? eye_fetch(left, w, h, s, t) : eye_fetch(right, w, h, s, t);
+    }
+    out[i] = o;
+  }
+}
+
 inline int grid_for(uint64_t n, int block) {
   uint64_t g = (n + block - 1) / block;
   const uint64_t cap = (uint64_t)kSMs * 8;   // 8 resident 256-thread CTAs per SM
@@ -96,6 +130,17 @@ void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rg
 
 void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s) {
   quantize_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
+}
+
+void launch_stereo_compose(int mode, const float4* left, const float4* right, float4* out, uint32_t w, uint32_t h,
+                           int alternating_frame_id, float split_coord, cudaStream_t s) {
+  const int g = grid_for((uint64_t)w * h, 256);
+  switch (mode) {
+    case 0: stereo_compose_kernel<0><<<g, 256, 0, s>>>(left, right, out, w, h, alternating_frame_id, split_coord); break;
+    case 1: stereo_compose_kernel<1><<<g, 256, 0, s>>>(left, right, out, w, h, alternating_frame_id, split_coord); break;
+    case 2: stereo_compose_kernel<2><<<g, 256, 0, s>>>(left, right, out, w, h, alternating_frame_id, split_coord); break;
+    default: stereo_compose_kernel<3><<<g, 256, 0, s>>>(left, right, out, w, h, alternating_frame_id, split_coord); break;
+  }
 }
 
 void launch_composite_over(const float4* front, const float4* back, float4* out, uint64_t n, cudaStream_t s) {

@@ -67,6 +67,9 @@ void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rg
                         const float amb[3], const float dif[3], const float spe[3], const float ldir[3],
                         cudaStream_t s);
 void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s);
+// GLRenderer::EndFrame's eye composition (Compose-{Anaglyphs,Scanline,SBS,AF}-FS.glsl); mode = tvk_stereo_mode
+void launch_stereo_compose(int mode, const float4* left, const float4* right, float4* out, uint32_t w, uint32_t h,
+                           int alternating_frame_id, float split_coord, cudaStream_t s);
 void launch_composite_over(const float4* front, const float4* back, float4* out, uint64_t n, cudaStream_t s);
 
 // classic per-brick raycaster (k_classic.cu): uniforms of GLRaycaster::SetBrickDepShaderVars / RenderBox plus the

@@ -142,6 +142,8 @@ void free_frame(tvk_ctx* c) {
   if (c->rgba8_d) cudaFree(c->rgba8_d);
   c->rgba8_d = nullptr;
   for (auto& b : c->rgba8_async_d) { if (b) cudaFree(b); b = nullptr; }
+  for (auto& b : c->stereo_d) { if (b) cudaFree(b); b = nullptr; }
+  c->result_buf = nullptr;
   c->img_w = c->img_h = 0;
   if (c->classic_axis_d) cudaFree(c->classic_axis_d);
   if (c->classic_table_d) cudaFree(c->classic_table_d);
@@ -152,7 +154,7 @@ int ensure_frame(tvk_ctx* ctx, uint32_t w, uint32_t h) {
   if (ctx->img_w == w && ctx->img_h == h) return TVK_OK;
   free_frame(ctx);
   const size_t n = (size_t)w * h;
-  for (int i = 0; i < 7; i++) CU(cudaMalloc(&ctx->buf[i], n * sizeof(float4)));
+  for (int i = 0; i < 8; i++) CU(cudaMalloc(&ctx->buf[i], n * sizeof(float4)));   // [7]: composed stereo frame
   CU(cudaMalloc(&ctx->rgba8_d, n * 4));
   ctx->img_w = w; ctx->img_h = h;
   ctx->blank = true;
@@ -627,7 +629,10 @@ int raycast_pass(tvk_ctx* ctx, bool with_hash) {
   return TVK_OK;
 }
 
-float4* result_image(tvk_ctx* ctx) { return ctx->params.mode == TVK_RM_ISOSURFACE ? ctx->buf[6] : ctx->buf[0]; }
+float4* result_image(tvk_ctx* ctx) {
+  if (ctx->result_buf) return ctx->result_buf;
+  return ctx->params.mode == TVK_RM_ISOSURFACE ? ctx->buf[6] : ctx->buf[0];
+}
 
 }  // namespace
 
@@ -1306,6 +1311,7 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
   if (st) std::memset(st, 0, sizeof(*st));
   int rc = check_renderable(ctx);
   if (rc) return rc;
+  ctx->result_buf = nullptr;
   // visibility follows TF / mode / isovalue changes (Changed1DTrans etc. -> RecomputeBrickVisibility)
   uint32_t counts[4];
   rc = recompute_visibility(ctx, 0, counts);
@@ -1821,6 +1827,7 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
   if (ctx->counters_on) CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));   // the host tables above must outlive their copies
   ctx->blank = true;              // the GridLeaper resume buffers no longer describe this image
+  ctx->result_buf = ctx->buf[0];  // (an isosurface-mode MIP frame does not end in the deferred-shading buffer)
   if (st) {
     st->converged = 1;
     st->bricks_paged = paged;
@@ -1843,6 +1850,74 @@ int tvk_read_mip_max(tvk_ctx* ctx, float* dst) {
   cudaSetDevice(ctx->cfg.device);
   CU(cudaMemcpyAsync(dst, ctx->buf[1], (size_t)ctx->params.width * ctx->params.height * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return TVK_OK;
+}
+
+// ---- stereo (GLRenderer::ComputeViewAndProjection in stereo, GLRenderer::EndFrame) ----------------------------
+int tvk_compute_stereo_view(tvk_render_params* left, tvk_render_params* right, uint32_t width, uint32_t height,
+                            const float rotation[16], const float translation[16], const float eye[3], const float at[3],
+                            const float up[3], float fov_deg, float z_near, float z_far, float screen_space_error,
+                            float focal_length, float eye_dist) {
+  if (!left || !right) return TVK_ERR_INVALID;
+  // the mono call fills lod_factor, width, height, eye and BuildLookAt's view (with identity rotation / translation)
+  const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  int rc = tvk_compute_view(left, width, height, ident, ident, eye, at, up, fov_deg, z_near, z_far, screen_space_error);
+  if (rc) return rc;
+  float view[16];
+  std::memcpy(view, left->model_view, 64);
+  *right = *left;
+  // FLOATMATRIX4::BuildStereoLookAtAndProjection (Basics/Vectors.h:1215-1248), float arithmetic like the reference
+  const float aspect = (float)width / (float)height;
+  const float radians = float(3.14159265358979323846 / 180.0) * fov_deg / 2;
+  const float wd2 = z_near * float(tan(radians));
+  const float nfdl = z_near / focal_length;
+  const float shift = eye_dist * nfdl;
+  auto off_center = [&](float l, float r, float b, float t, float* m) {   // MatrixPerspectiveOffCenter :1286-1291
+    std::memset(m, 0, 64);
+    m[0] = 2.0f * z_near / (r - l); m[8] = (r + l) / (r - l);
+    m[5] = 2.0f * z_near / (t - b); m[9] = (t + b) / (t - b);
+    m[10] = -(z_far + z_near) / (z_far - z_near); m[14] = -2.0f * (z_far * z_near) / (z_far - z_near);
+    m[11] = -1.0f;
+  };
+  off_center(-aspect * wd2 + shift, aspect * wd2 + shift, -wd2, wd2, left->projection);
+  off_center(-aspect * wd2 - shift, aspect * wd2 - shift, -wd2, wd2, right->projection);
+  auto mulf = [](const float* a, const float* b, float* o) {
+    float t[16];
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++)
+        t[r * 4 + c] = a[r * 4] * b[c] + a[r * 4 + 1] * b[4 + c] + a[r * 4 + 2] * b[8 + c] + a[r * 4 + 3] * b[12 + c];
+    std::memcpy(o, t, 64);
+  };
+  float tr[16], vl[16], vr[16], rt[16];
+  std::memcpy(tr, ident, 64);
+  tr[12] = eye_dist;  mulf(tr, view, vl);     // eye translation: mTranslate * mView
+  tr[12] = -eye_dist; mulf(tr, view, vr);
+  mulf(rotation, translation, rt);            // modelView[eye] = rotation * translation * view[eye] (GLRenderer.cpp:627-630)
+  mulf(rt, vl, left->model_view);
+  mulf(rt, vr, right->model_view);
+  return TVK_OK;
+}
+
+int tvk_stereo_keep_eye(tvk_ctx* ctx, int eye) {
+  if (!ctx || eye < 0 || eye > 1) return TVK_ERR_INVALID;
+  if (!ctx->img_w) return fail(ctx, TVK_ERR_INVALID, "nothing rendered");
+  cudaSetDevice(ctx->cfg.device);
+  const size_t bytes = (size_t)ctx->img_w * ctx->img_h * sizeof(float4);
+  if (!ctx->stereo_d[eye]) CU(cudaMalloc(&ctx->stereo_d[eye], bytes));
+  CU(cudaMemcpyAsync(ctx->stereo_d[eye], result_image(ctx), bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return TVK_OK;
+}
+
+int tvk_stereo_compose(tvk_ctx* ctx, int mode, int eye_swap, int alternating_frame_id, float split_coord) {
+  if (!ctx) return TVK_ERR_INVALID;
+  if (mode < TVK_SM_RB || mode > TVK_SM_AF) return fail(ctx, TVK_ERR_INVALID, "invalid stereo mode");
+  if (!ctx->img_w || !ctx->stereo_d[0] || !ctx->stereo_d[1]) return fail(ctx, TVK_ERR_INVALID, "stereo: both eye images must be kept first");
+  cudaSetDevice(ctx->cfg.device);
+  const float4* l = ctx->stereo_d[eye_swap ? 1 : 0];   // m_bStereoEyeSwap exchanges the bound units (GLRenderer.cpp:773-779)
+  const float4* r = ctx->stereo_d[eye_swap ? 0 : 1];
+  launch_stereo_compose(mode, l, r, ctx->buf[7], ctx->img_w, ctx->img_h, alternating_frame_id, split_coord, ctx->stream);
+  CU(cudaGetLastError());
+  ctx->result_buf = ctx->buf[7];
   return TVK_OK;
 }
 

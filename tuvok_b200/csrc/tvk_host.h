@@ -145,6 +145,8 @@ struct tvk_ctx {
   //      6 composed iso image, 7 unused
   int cur = 0;
   uchar4* rgba8_d = nullptr;
+  float4* result_buf = nullptr;   // set by frames whose result does not follow the mode rule of result_image() (MIP, stereo)
+  float4* stereo_d[2] = {nullptr, nullptr};   // kept eye images (m_pFBO3DImageNext[0 / 1]) of a stereo frame
   uchar4* rgba8_async_d[2] = {nullptr, nullptr};   // double-buffered unorm8 images of the async read-back
   cudaEvent_t read_ev[2] = {nullptr, nullptr}; cudaEvent_t quant_ev = nullptr;
   int read_slot = 0;

@@ -380,6 +380,61 @@ class CudaGridLeaper:
                                np.ascontiguousarray(projection, np.float32).reshape(4, 4), lod_factor)
         self._dirty = True
 
+    # ------------------------------------------------------------------ stereo (AbstrRenderer.cpp:1383-1412)
+    def SetStereo(self, on):
+        self._stereo = bool(on)
+        self._dirty = True
+
+    def SetStereoMode(self, mode):
+        """AbstrRenderer::EStereoMode: 0 SM_RB, 1 SM_SCANLINE, 2 SM_SBS, 3 SM_AF."""
+        self._stereo_mode = int(mode)
+
+    def SetStereoEyeDist(self, d):
+        self._stereo_eye_dist = float(d)
+        self._dirty = True
+
+    def SetStereoFocalLength(self, f):
+        self._stereo_focal = float(f)
+        self._dirty = True
+
+    def SetStereoEyeSwap(self, swap):
+        self._stereo_swap = bool(swap)
+
+    def ToggleStereoFrame(self):
+        """AbstrRenderer::ToggleStereoFrame (AbstrRenderer.cpp:1581-1584)."""
+        self._alt_frame = 1 - getattr(self, "_alt_frame", 0)
+
+    def stereo_params(self):
+        """(left, right) tvk_render_params of GLRenderer::ComputeViewAndProjection in stereo."""
+        p = self.params
+        left, right = L.RenderParams(), L.RenderParams()
+        C.memmove(C.byref(left), C.byref(p), C.sizeof(p))
+        rot = L.f32x16(*self._rotation.reshape(-1))
+        tra = L.f32x16(*self._translation.reshape(-1))
+        self._ck(self._lib.tvk_compute_stereo_view(C.byref(left), C.byref(right), p.width, p.height, rot, tra,
+                                                   L.f32x3(*self._eye), L.f32x3(*self._at), L.f32x3(*self._up), self._fov,
+                                                   self._znear, self._zfar, 1.0, getattr(self, "_stereo_focal", 1.0),
+                                                   getattr(self, "_stereo_eye_dist", 0.02)))
+        return left, right
+
+    def PaintStereoUntilConverged(self, max_subframes=0):
+        """A finished stereo frame: both eyes rendered to convergence (m_pFBO3DImageNext[0 / 1], GLGridLeaper renders
+        the eyes through the same pool), then GLRenderer::EndFrame's composition.  Returns the two eyes' frame stats."""
+        left, right = self.stereo_params()
+        stats = []
+        for eye, prm in ((0, left), (1, right)):
+            self._ck(self._lib.tvk_set_params(self._h, C.byref(prm)))
+            st = L.FrameStats()
+            self._ck(self._lib.tvk_paint(self._h, max_subframes, C.byref(st)))
+            self._ck(self._lib.tvk_stereo_keep_eye(self._h, eye))
+            stats.append(st)
+        self._ck(self._lib.tvk_stereo_compose(self._h, getattr(self, "_stereo_mode", 0), int(getattr(self, "_stereo_swap", False)),
+                                              getattr(self, "_alt_frame", 0), 0.5))
+        self._dirty = True          # the mono parameters are pushed again by the next mono frame
+        self.last_stats = stats[1]
+        self._converged = bool(stats[0].converged and stats[1].converged)
+        return stats
+
     def SetShardBox(self, clip_min, clip_max):
         """Sort-last: restrict rays to this rank's convex brick block (normalised volume coords)."""
         self.params.clip_min = L.f32x3(*clip_min)
