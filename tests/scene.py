@@ -180,13 +180,18 @@ class Scene:
             return np.ascontiguousarray(self.tf2d.GetByteArray())
         return np.ascontiguousarray(self.tf1d.GetByteArray())
 
-    def oracle_render(self, threads=8, max_subframes=64, single_pass=False):
-        """The reference's convergence loop on the CPU.  Returns dict(image, rgba8, pool, meta, stats, ...)."""
+    def oracle_render(self, threads=8, max_subframes=64, single_pass=False, warm=None):
+        """The reference's convergence loop on the CPU.  Returns dict(image, rgba8, pool, meta, stats, ...).
+        warm: the dict of an earlier frame of the same dataset -- the loop continues on its pool / page table (a new
+        view of a renderer that has already paged bricks in) instead of starting from an empty pool."""
         o = self.octree
-        pool, counts = self.oracle_pool()
+        if warm is None:
+            pool, counts = self.oracle_pool()
+        else:
+            pool, counts = warm["pool"], None
         p = self.oracle_params(pool)
         ps = pool.pool_size
-        atlas = np.zeros((ps[2], ps[1], ps[0]), orc.NP_DTYPE[self.dtype])
+        atlas = np.zeros((ps[2], ps[1], ps[0]), orc.NP_DTYPE[self.dtype]) if warm is None else warm["atlas"]
         b3 = self.brick
 
         def put(slot_coord, key):
@@ -197,7 +202,8 @@ class Scene:
                   sx * b3[0]:sx * b3[0] + b.shape[2]] = b
 
         last = pool.lod_count - 1
-        put(pool.capacity[0] * pool.capacity[1] * pool.capacity[2] - 1, (0, 0, 0, last))
+        if warm is None:
+            put(pool.capacity[0] * pool.capacity[1] * pool.capacity[2] - 1, (0, 0, 0, last))
         entry, exit_, cov = orc.ray_setup(p)
         ray_start, start_color = entry.copy(), np.zeros_like(entry)
         tf = self.tf_bytes()

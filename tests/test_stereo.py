@@ -95,11 +95,13 @@ STEREO_SCENES = [("c2_bricked36_1d_ert", orc.SM_RB, False, 0.02), ("c3_bricked36
 
 
 def oracle_stereo_frame(name, mode, swap, dist, focal=1.0, alt=0):
+    """Both eyes through ONE pool, left first (GLGridLeaper renders the eyes of a frame through the same GLVolumePool):
+    the right eye continues on the page table the left eye left behind."""
     eyes = []
     for e in (0, 1):
         s = golden_scenes.make(name)
         s.stereo_eye = (e, focal, dist)
-        eyes.append(s.oracle_render())
+        eyes.append(s.oracle_render(warm=eyes[0] if e == 1 else None))
     return eyes, orc.stereo_compose(mode, eyes[0]["image"], eyes[1]["image"], swap, alt, 0.5)
 
 
@@ -128,14 +130,24 @@ def test_cuda_stereo_frame_matches_oracle(name, mode, swap, dist):
     rd.SetStereoMode(mode)
     rd.SetStereoEyeSwap(swap)
     rd.SetStereoEyeDist(dist)
-    st = rd.PaintStereoUntilConverged()
-    assert st[0].converged and st[1].converged
+    assert rd.PaintStereoEye(0).converged
+    fl = rd.ReadRGBA32F()
+    assert np.array_equal(fl, l["image"])                            # fresh pool, same paging history: identical floats
+    assert rd.PaintStereoEye(1).converged
+    fr = rd.ReadRGBA32F()
+    assert np.array_equal(fr, r["image"])                            # continues on the left eye's pool, as the oracle does
+    assert np.array_equal(rd.page_table(), r["meta"])
+    rd.ComposeStereo()
     f = rd.ReadRGBA32F()
+    assert np.array_equal(f, orc.stereo_compose(mode, fl, fr, swap, 0, 0.5))   # the composition kernel, bit for bit
+    assert np.array_equal(rd.ReadRGBA8(), orc.rgba8(f))
     assert np.array_equal(f, ref)
-    assert np.array_equal(rd.ReadRGBA8(), orc.rgba8(ref))
     # a mono frame afterwards is the mono image again (the composed frame does not stick)
     assert rd.PaintUntilConverged().converged
-    assert np.array_equal(rd.ReadRGBA32F(), s.oracle_render()["image"])
+    mono = s.oracle_render(warm=r)
+    assert np.array_equal(rd.ReadRGBA32F(), mono["image"])
+    mx, psnr = image_diff(rd.ReadRGBA8(), s.oracle_render()["rgba8"])   # ... and, up to the paging history, the cold one
+    assert mx <= 2 and psnr >= 45.0, (mx, psnr)
     rd.Cleanup()
 
 

@@ -417,21 +417,28 @@ class CudaGridLeaper:
                                                    getattr(self, "_stereo_eye_dist", 0.02)))
         return left, right
 
-    def PaintStereoUntilConverged(self, max_subframes=0):
-        """A finished stereo frame: both eyes rendered to convergence (m_pFBO3DImageNext[0 / 1], GLGridLeaper renders
-        the eyes through the same pool), then GLRenderer::EndFrame's composition.  Returns the two eyes' frame stats."""
-        left, right = self.stereo_params()
-        stats = []
-        for eye, prm in ((0, left), (1, right)):
-            self._ck(self._lib.tvk_set_params(self._h, C.byref(prm)))
-            st = L.FrameStats()
-            self._ck(self._lib.tvk_paint(self._h, max_subframes, C.byref(st)))
-            self._ck(self._lib.tvk_stereo_keep_eye(self._h, eye))
-            stats.append(st)
+    def PaintStereoEye(self, eye, max_subframes=0):
+        """One eye (0 left / 1 right) rendered to convergence and kept as m_pFBO3DImageNext[eye]."""
+        prm = self.stereo_params()[eye]
+        self._ck(self._lib.tvk_set_params(self._h, C.byref(prm)))
+        st = L.FrameStats()
+        self._ck(self._lib.tvk_paint(self._h, max_subframes, C.byref(st)))
+        self._ck(self._lib.tvk_stereo_keep_eye(self._h, eye))
+        self._dirty = True          # the mono parameters are pushed again by the next mono frame
+        self.last_stats = st
+        self._converged = bool(st.converged)
+        return st
+
+    def ComposeStereo(self):
+        """GLRenderer::EndFrame's composition of the two kept eyes; the composed frame is what Read* return next."""
         self._ck(self._lib.tvk_stereo_compose(self._h, getattr(self, "_stereo_mode", 0), int(getattr(self, "_stereo_swap", False)),
                                               getattr(self, "_alt_frame", 0), 0.5))
-        self._dirty = True          # the mono parameters are pushed again by the next mono frame
-        self.last_stats = stats[1]
+
+    def PaintStereoUntilConverged(self, max_subframes=0):
+        """A finished stereo frame: both eyes rendered to convergence (GLGridLeaper renders the eyes through the same
+        pool), then the composition.  Returns the two eyes' frame stats."""
+        stats = [self.PaintStereoEye(0, max_subframes), self.PaintStereoEye(1, max_subframes)]
+        self.ComposeStereo()
         self._converged = bool(stats[0].converged and stats[1].converged)
         return stats
 
