@@ -39,8 +39,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="tvk", choices=["tvk", "reference"])
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4"])
-    ap.add_argument("--path", default="gridleaper", choices=["gridleaper", "classic"],
-                    help="gridleaper: GLGridLeaper page-table traversal (default); classic: per-brick GLRaycaster path")
+    ap.add_argument("--path", default="gridleaper", choices=["gridleaper", "classic", "mip"],
+                    help="gridleaper: GLGridLeaper page-table traversal (default); classic: per-brick GLRaycaster path; "
+                         "mip: HQ MIP frame of a 2D window (GLRaycaster-MIP-Rot-FS, rotating about Y)")
     ap.add_argument("--split", default="auto", choices=["auto", "screen", "depth", "depth2", "octant"],
                     help="sort-last partition policy (tuvok_b200/sortlast.py); auto = screen for N <= 4, octant for N = 8 "
                          "(measured best, DESIGN.md section 5)")
@@ -289,12 +290,18 @@ def run_tvk(args, rank, world, local_rank):
     split = args.split if args.split != "auto" else ("octant" if world >= 8 else "screen")
     sl = sortlast.SortLastRenderer(r, rank, world, finest, flayout, ext, policy=split) if world > 1 else None
     n_views = 36
-    classic = args.path == "classic"
+    mip = args.path == "mip"
+    classic = args.path in ("classic", "mip")          # the per-brick paths: one converged frame per call
     if classic and world > 1:
-        raise SystemExit("the classic path is single-GPU (sort-last shards the GridLeaper path)")
+        raise SystemExit("the classic / MIP paths are single-GPU (sort-last shards the GridLeaper path)")
+
+    def paint_per_brick():
+        return r.PaintHQMIP("coronal") if mip else r.PaintClassic()
 
     def set_view(i):
         r.SetRotation(workloads.orbit_rotation(i % n_views, n_views))
+        if mip:
+            r.SetMIPRotationAngle(10.0 * (i % n_views))    # GLRenderer::SetMIPRotationAngle: the 2D window's MIP turntable
         if sl is not None:
             sl.update_partition()     # view-dependent brick blocks (side by side on screen)
 
@@ -302,7 +309,7 @@ def run_tvk(args, rank, world, local_rank):
         """one step on this rank; returns the stats of the (single) subframe"""
         set_view(i)
         if sl is None:
-            return r.PaintClassic() if classic else r.Paint()
+            return paint_per_brick() if classic else r.Paint()
         lo, hi, img, st = sl.render()
         sl.gather(lo, hi, img)
         return st
@@ -311,7 +318,7 @@ def run_tvk(args, rank, world, local_rank):
     paged = 0
     for i in range(n_views):
         set_view(i)
-        st = r.PaintClassic() if classic else r.PaintUntilConverged()
+        st = paint_per_brick() if classic else r.PaintUntilConverged()
         paged += st.bricks_paged
         if not st.converged:
             raise RuntimeError("view %d did not converge (pool too small?)" % i)
@@ -324,7 +331,7 @@ def run_tvk(args, rank, world, local_rank):
     alive_it, warp_it = 0, 0
     for i in range(n_views):
         set_view(i)
-        st = r.PaintClassic() if classic else r.Paint()
+        st = paint_per_brick() if classic else r.Paint()
         samples.append(st.samples); rays.append(st.rays); touched.append(st.bricks_touched); visits.append(st.brick_visits)
         alive_it += st.alive_lane_iters; warp_it += st.warp_iters
     r.enable_counters(False)
@@ -368,7 +375,7 @@ def run_tvk(args, rank, world, local_rank):
             # PBO-style double-buffered read-back: frame i is copied to pinned host memory while frame i+1 renders;
             # every frame's RGBA8 image is in host memory (and touched) before the timed region ends
             if classic:
-                r.PaintClassic()
+                paint_per_brick()
             else:
                 r.Paint()
             r.ReadRGBA8Async(pinned[i % 2])
@@ -418,13 +425,14 @@ def run_tvk(args, rank, world, local_rank):
         slot_bytes = brick ** 3 * esize
         # algorithmic HBM bytes per launch: every sampled brick once + page-table entries of the
         # visited bricks + the kernel's per-pixel outputs (acc colour, resume colour, resume position)
-        alg_bytes = (step_touched * slot_bytes + step_touched * 4 + k * n_pixels * 48.0) / k / world
+        out_bytes = 48.0 if not classic else (24.0 if mip else 16.0)   # per pixel: 3 MRTs / colour (+ MIP maximum image)
+        alg_bytes = (step_touched * slot_bytes + step_touched * 4 + k * n_pixels * out_bytes) / k / world
         ray_ms = ms_ray / k
         peak, which = peaks()
         achieved = alg_bytes / (ray_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "raycast_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and not classic:
             try:
                 traffic = json.load(open(tp)).get(args.config)
             except Exception:
@@ -437,7 +445,8 @@ def run_tvk(args, rank, world, local_rank):
             "config": {"workload": w["label"], "volume": "V_noise seed 0x5EED" if w["kind"] == 1 else "V_sph",
                        "camera": "36-step orbit (Ry 10deg steps, Rx 20deg), eye (0,0,1.6) fov 50",
                        "parallelism": "sort-last x%d (binary swap, %s partition)" % (world, split) if world > 1 else "single GPU",
-                       "path": "classic per-brick GLRaycaster" if classic else "GridLeaper page-table traversal",
+                       "path": ("HQ MIP frame (per-brick GLRaycaster-MIP-Rot-FS + Transfer-MIP, PlanHQMIPFrame LoD)" if mip else
+                                "classic per-brick GLRaycaster") if classic else "GridLeaper page-table traversal",
                        "l2_policy": "inputs larger than L2 (pool %.1f GB, %.0f MB of bricks touched per frame)" %
                                     (info.pool_capacity[0] * info.pool_capacity[1] * info.pool_capacity[2] * slot_bytes / 1e9,
                                      step_touched / k * slot_bytes / 1e6),
@@ -450,7 +459,7 @@ def run_tvk(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which, "kernel": "classic_kernel" if classic else "raycast_kernel",
                          "kernel_ms": ray_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "fetch_gbs": step_samples / k * (7 if (w["lighting"] or w["mode"] == 1) else 1) * 8 * esize
+                         "fetch_gbs": step_samples / k * (7 if ((w["lighting"] or w["mode"] == 1) and not mip) else 1) * 8 * esize
                                       / (ray_ms * 1e-3) / 1e9 / world},
             "e2e": {"value": k / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(C_sizeof_params()),
                     "d2h_bytes_per_step": n_pixels * 4 + 8},

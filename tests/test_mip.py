@@ -148,3 +148,28 @@ def test_cuda_mip_2d_mode_callback_source_and_coexistence():
     assert r.PaintUntilConverged().converged
     assert image_diff(r.ReadRGBA8(), ref_g["rgba8"])[0] <= 2
     r.Cleanup()
+
+
+@pytest.mark.gpu
+def test_cuda_mip_turntable_reuses_the_plan_and_follows_tf_changes():
+    """A MIP turntable: the frame plan (brick list, per-brick tables) does not depend on the view and is kept across
+    frames; a transfer-function change, a classic frame in between or a resize re-plan.  Every frame equals the oracle."""
+    from tuvok_b200.tf import TransferFunction1D
+    base = dict(width=72, height=60)
+    r = None
+    for step, (angle, tf_c) in enumerate([(0.0, 0.4), (33.0, 0.4), (66.0, 0.4), (66.0, 0.7), (120.0, 0.7)]):
+        s = golden_scenes.make("c2_bricked36_1d_ert", rotation=tb.mip_rotation("sagittal", angle), translation=None,
+                               tf_center=tf_c, **base)
+        ref = s.oracle_mip()
+        if r is None:
+            r = s.make_renderer("device")
+        else:
+            r.Set1DTrans(s.tf1d)
+        if step == 2:
+            r.PaintClassic()                                          # overwrites the brick list: the next MIP frame re-plans
+        r.SetMIPRotationAngle(angle)
+        r.PaintHQMIP("sagittal")
+        assert np.array_equal(r.classic_brick_list()[1], ref["order"])
+        assert np.array_equal(r.mip_max_image(), ref["max"])
+        assert np.array_equal(r.ReadRGBA32F(), ref["image"])
+    r.Cleanup()

@@ -148,6 +148,7 @@ void free_frame(tvk_ctx* c) {
   if (c->classic_axis_d) cudaFree(c->classic_axis_d);
   if (c->classic_table_d) cudaFree(c->classic_table_d);
   c->classic_axis_d = nullptr; c->classic_table_d = nullptr; c->classic_axis_cap = c->classic_table_cap = 0;
+  c->mip_plan.valid = false;      // its device tables are gone
 }
 
 int ensure_frame(tvk_ctx* ctx, uint32_t w, uint32_t h) {
@@ -769,7 +770,7 @@ int tvk_set_volume(tvk_ctx* ctx, const tvk_volume_desc* d, tvk_brick_cb cb, void
   CU(cudaMalloc(&ctx->minmax_d, ctx->minmax_h.size() * sizeof(double)));
   CU(cudaMemcpy(ctx->minmax_d, ctx->minmax_h.data(), ctx->minmax_h.size() * sizeof(double), cudaMemcpyHostToDevice));
   ctx->cb = cb; ctx->cb_user = user;
-  ctx->have_volume = true;
+  ctx->have_volume = true; ctx->data_gen++;
   return TVK_OK;
 }
 
@@ -886,7 +887,7 @@ int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64
     CU(cudaMemcpy(ctx->minmax_h.data(), ctx->minmax_d, ctx->minmax_h.size() * sizeof(double), cudaMemcpyDeviceToHost));
   }
   if (info) { fill_file_info(*ctx->file, info); info->dtype = dtype; }
-  ctx->have_volume = true;
+  ctx->have_volume = true; ctx->data_gen++;
   return TVK_OK;
 }
 
@@ -1002,7 +1003,7 @@ int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uin
   }
   ctx->minmax_h.resize(4 * (size_t)ctx->n_bricks_all);
   CU(cudaMemcpy(ctx->minmax_h.data(), ctx->minmax_d, ctx->minmax_h.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  ctx->have_volume = true;
+  ctx->have_volume = true; ctx->data_gen++;
   return TVK_OK;
 }
 
@@ -1078,6 +1079,7 @@ int tvk_set_tf1d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t n, uint64_t nz_lo, 
     CU(cudaMemcpy(ctx->tf1d_d, f.data(), f.size() * sizeof(float4), cudaMemcpyHostToDevice));
   }
   ctx->tf1d_n = n; ctx->tf1d_nz[0] = nz_lo; ctx->tf1d_nz[1] = nz_hi;
+  ctx->tf_gen++;
   ctx->blank = true;
   return TVK_OK;
 }
@@ -1097,6 +1099,7 @@ int tvk_set_tf2d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, cons
   }
   ctx->tf2d_w = w; ctx->tf2d_h = h;
   for (int i = 0; i < 4; i++) ctx->tf2d_nz[i] = nz[i];
+  ctx->tf_gen++;
   ctx->blank = true;
   return TVK_OK;
 }
@@ -1664,6 +1667,14 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
   else { v0 = double(ctx->tf2d_nz[0]) * rescale; v1 = double(ctx->tf2d_nz[1]) * rescale; v2 = double(ctx->tf2d_nz[2]); v3 = double(ctx->tf2d_nz[3]); }
   const uint32_t* lay = ctx->layout[lod];
   std::vector<tvk_classic_brick>& list = ctx->classic_list;
+  tvk_ctx::MipPlan key;
+  key.valid = true; key.lod = lod; key.mode = p.mode; key.tf_gen = ctx->tf_gen; key.data_gen = ctx->data_gen;
+  key.iso = p.isovalue; key.sample_rate = p.sample_rate_modifier;
+  const tvk_ctx::MipPlan& have = ctx->mip_plan;
+  const bool plan_hit = mip && have.valid && have.lod == key.lod && have.mode == key.mode && have.tf_gen == key.tf_gen &&
+                        have.data_gen == key.data_gen && have.iso == key.iso && have.sample_rate == key.sample_rate;
+  ctx->mip_plan.valid = false;
+  if (!plan_hit) {
   list.clear();
   for (uint32_t z = 0; z < lay[2]; z++)
     for (uint32_t y = 0; y < lay[1]; y++)
@@ -1712,6 +1723,7 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
       }
   // depth sort; bricks at the same distance keep key order (the reference's std::sort leaves ties open)
   std::stable_sort(list.begin(), list.end(), [](const tvk_classic_brick& a, const tvk_classic_brick& b) { return a.distance < b.distance; });
+  }   // !plan_hit
   ctx->classic_lod = lod;
 
   // ---- residency: every listed, non-empty brick must sit in the pool (GPUMemMan::GetVolume's job) ----
@@ -1767,18 +1779,23 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
     }
   }
   const size_t n_cells = (size_t)lay[0] * lay[1] * lay[2];
-  std::vector<uint32_t> table(n_cells, 0u);
+  std::vector<uint32_t>& table = ctx->classic_table_h;
+  bool table_changed = !plan_hit || table.size() != n_cells;
+  if (table_changed) table.assign(n_cells, 0u);
   for (const tvk_classic_brick& b : list) {
     if (b.empty) continue;
     const uint32_t m = ctx->meta_h[brick_id(ctx, b.x, b.y, b.z, lod)];
     if (m < TVK_BI_FLAG_COUNT) return fail(ctx, TVK_ERR_OOM, "classic path: brick (%u,%u,%u,%u) could not be paged in", b.x, b.y, b.z, lod);
-    table[b.index] = (m - TVK_BI_FLAG_COUNT) + 1u;
+    const uint32_t v = (m - TVK_BI_FLAG_COUNT) + 1u;
+    if (table[b.index] != v) { table[b.index] = v; table_changed = true; }   // a cached plan whose bricks moved slots
   }
   rc = ensure_classic(ctx, ax.size() + nv.size(), n_cells);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->classic_axis_d, ax.data(), ax.size() * 4, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(ctx->classic_axis_d + ax.size(), nv.data(), nv.size() * 4, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(ctx->classic_table_d, table.data(), n_cells * 4, cudaMemcpyHostToDevice, s));
+  if (!plan_hit) {
+    CU(cudaMemcpyAsync(ctx->classic_axis_d, ax.data(), ax.size() * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->classic_axis_d + ax.size(), nv.data(), nv.size() * 4, cudaMemcpyHostToDevice, s));
+  }
+  if (table_changed) CU(cudaMemcpyAsync(ctx->classic_table_d, table.data(), n_cells * 4, cudaMemcpyHostToDevice, s));
 
   ClassicConsts c;
   std::memset(&c, 0, sizeof(c));
@@ -1827,6 +1844,7 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
   if (ctx->counters_on) CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));   // the host tables above must outlive their copies
   ctx->blank = true;              // the GridLeaper resume buffers no longer describe this image
+  if (mip) ctx->mip_plan = key;   // list + device tables describe this plan (a classic frame leaves it invalid)
   ctx->result_buf = ctx->buf[0];  // (an isosurface-mode MIP frame does not end in the deferred-shading buffer)
   if (st) {
     st->converged = 1;

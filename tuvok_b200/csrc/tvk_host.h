@@ -132,6 +132,11 @@ struct tvk_ctx {
   // ---- classic per-brick path (GLRaycaster) ----
   std::vector<tvk_classic_brick> classic_list;   // last planned brick list (depth sorted)
   uint32_t classic_lod = 0;
+  // plan of the last HQ MIP frame: its brick list depends on (LoD, mode, transfer function, isovalue, dataset) only --
+  // not on the view -- so a MIP turntable re-plans nothing (AbstrRenderer re-plans every frame; same list)
+  struct MipPlan { bool valid = false; uint32_t lod = 0; int mode = 0; uint64_t tf_gen = 0, data_gen = 0; double iso = 0; float sample_rate = 0; } mip_plan;
+  uint64_t tf_gen = 0, data_gen = 0;              // bumped by tvk_set_tf1d/2d and by every dataset registration
+  std::vector<uint32_t> classic_table_h;          // host copy of the brick -> slot table on the device
   float* classic_axis_d = nullptr; size_t classic_axis_cap = 0;   // per-axis tables (floats + nvox)
   uint32_t* classic_table_d = nullptr; size_t classic_table_cap = 0;
 
