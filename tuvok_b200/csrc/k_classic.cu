@@ -36,14 +36,20 @@ __device__ __forceinline__ float half_round(float v) { return __half2float(__flo
 
 // texture3D(texVolume, tc) of ONE brick: GL_LINEAR / GL_NEAREST, clamp-to-edge on the brick's own size,
 // voxels at slot strides.  Gradient taps sit +-1 texel from the centre and share its filter fractions.
-template <typename T>
+// Interior samples (the whole footprint inside the brick: always, apart from the first / last samples of a segment,
+// when the ghost layer is >= 2 voxels) need no clamping: one centre address + uniform strides, and with GRAD the 32
+// distinct voxels of the 7 overlapping footprints are loaded once (as in k_raycast.cu).  Samples whose footprint
+// touches the brick border take the clamped path; both paths read the same voxels, so the results are identical.
+template <typename T, bool GRAD>
 struct BrickTex {
   const T* base;
+  const T* c;            // interior: voxel (X, Y, Z)
   uint32_t xo[4], yo[4], zo[4];
+  int sy, sz;
   float fx, fy, fz, norm;
-  bool nearest;
-  __device__ __forceinline__ void set(const T* b, const uint32_t n[3], uint32_t sy, uint32_t sz, f3 tc, bool nn, float nrm) {
-    base = b; nearest = nn; norm = nrm;
+  bool nearest, interior;
+  __device__ __forceinline__ void set(const T* b, const uint32_t n[3], uint32_t sy_, uint32_t sz_, f3 tc, bool nn, float nrm) {
+    base = b; nearest = nn; norm = nrm; sy = (int)sy_; sz = (int)sz_;
     int X, Y, Z;
     if (nn) {
       X = (int)floorf(tc.x * (float)n[0]); Y = (int)floorf(tc.y * (float)n[1]); Z = (int)floorf(tc.z * (float)n[2]);
@@ -54,18 +60,30 @@ struct BrickTex {
       fx = ux - x0; fy = uy - y0; fz = uz - z0;
       X = (int)x0; Y = (int)y0; Z = (int)z0;
     }
+    const int lo = GRAD ? 1 : 0, hi = GRAD ? 3 : 2;   // footprint [X-lo, X+hi-1] must lie in [0, n-1]
+    interior = !nn && X >= lo && Y >= lo && Z >= lo && X <= (int)n[0] - hi && Y <= (int)n[1] - hi && Z <= (int)n[2] - hi;
+    if (interior) {
+      c = b + (X + Y * sy + Z * sz);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      xo[i] = (uint32_t)min(max(X - 1 + i, 0), (int)n[0] - 1);
-      yo[i] = (uint32_t)min(max(Y - 1 + i, 0), (int)n[1] - 1) * sy;
-      zo[i] = (uint32_t)min(max(Z - 1 + i, 0), (int)n[2] - 1) * sz;
+      for (int i = 0; i < 4; i++) {
+        xo[i] = (uint32_t)min(max(X - 1 + i, 0), (int)n[0] - 1);
+        yo[i] = (uint32_t)min(max(Y - 1 + i, 0), (int)n[1] - 1) * sy_;
+        zo[i] = (uint32_t)min(max(Z - 1 + i, 0), (int)n[2] - 1) * sz_;
+      }
     }
   }
   __device__ __forceinline__ float v(int i, int j, int k) const { return cvt(__ldg(base + (xo[1 + i] + yo[1 + j] + zo[1 + k]))); }
+  __device__ __forceinline__ float vi(int i, int j, int k) const { return cvt(__ldg(c + (i + j * sy + k * sz))); }
   __device__ __forceinline__ float tap(int dx, int dy, int dz) const {
     if (nearest) return v(dx, dy, dz) * norm;
     return tri(v(dx, dy, dz), v(dx + 1, dy, dz), v(dx, dy + 1, dz), v(dx + 1, dy + 1, dz), v(dx, dy, dz + 1),
                v(dx + 1, dy, dz + 1), v(dx, dy + 1, dz + 1), v(dx + 1, dy + 1, dz + 1), fx, fy, fz) * norm;
+  }
+  // texture3D(texVolume, tc).x
+  __device__ __forceinline__ float centre() const {
+    if (!interior) return tap(0, 0, 0);
+    return tri(vi(0, 0, 0), vi(1, 0, 0), vi(0, 1, 0), vi(1, 1, 0), vi(0, 0, 1), vi(1, 0, 1), vi(0, 1, 1), vi(1, 1, 1), fx, fy, fz) * norm;
   }
   // ComputeGradient (Volume3D.glsl:43-53; the "Yp" tap is fetched at -delta)
   __device__ __forceinline__ f3 gradient() const {
@@ -73,6 +91,38 @@ struct BrickTex {
     const float yp = tap(0, -1, 0), ym = tap(0, 1, 0);
     const float zp = tap(0, 0, 1), zm = tap(0, 0, -1);
     return F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+  }
+  // centre value + gradient; interior samples load each of the 32 voxels of the 7 footprints once
+  __device__ __forceinline__ void centre_and_gradient(float& data, f3& grad) const {
+    if (!interior) { data = tap(0, 0, 0); grad = gradient(); return; }
+    float cc[2][2][2];   // [z][y][x] centre block
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int i = 0; i < 2; i++) cc[k][j][i] = vi(i, j, k);
+    float xl[2][2], xh[2][2], yl[2][2], yh[2][2], zl[2][2], zh[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        xl[a][b] = vi(-1, b, a);   // [z][y]
+        xh[a][b] = vi(2, b, a);
+        yl[a][b] = vi(b, -1, a);   // [z][x]
+        yh[a][b] = vi(b, 2, a);
+        zl[a][b] = vi(b, a, -1);   // [y][x]
+        zh[a][b] = vi(b, a, 2);
+      }
+    const float n = norm;
+    data = tri(cc[0][0][0], cc[0][0][1], cc[0][1][0], cc[0][1][1], cc[1][0][0], cc[1][0][1], cc[1][1][0], cc[1][1][1], fx, fy, fz) * n;
+    const float xp = tri(cc[0][0][1], xh[0][0], cc[0][1][1], xh[0][1], cc[1][0][1], xh[1][0], cc[1][1][1], xh[1][1], fx, fy, fz) * n;
+    const float xm = tri(xl[0][0], cc[0][0][0], xl[0][1], cc[0][1][0], xl[1][0], cc[1][0][0], xl[1][1], cc[1][1][0], fx, fy, fz) * n;
+    const float ym = tri(cc[0][1][0], cc[0][1][1], yh[0][0], yh[0][1], cc[1][1][0], cc[1][1][1], yh[1][0], yh[1][1], fx, fy, fz) * n;   // +y
+    const float yp = tri(yl[0][0], yl[0][1], cc[0][0][0], cc[0][0][1], yl[1][0], yl[1][1], cc[1][0][0], cc[1][0][1], fx, fy, fz) * n;   // -y
+    const float zp = tri(cc[1][0][0], cc[1][0][1], cc[1][1][0], cc[1][1][1], zh[0][0], zh[0][1], zh[1][0], zh[1][1], fx, fy, fz) * n;
+    const float zm = tri(zl[0][0], zl[0][1], zl[1][0], zl[1][1], cc[0][0][0], cc[0][0][1], cc[0][1][0], cc[0][1][1], fx, fy, fz) * n;
+    grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
   }
 };
 
@@ -179,9 +229,9 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
             f3 ct = et;
 #pragma unroll 1
             for (int s = 0; s < count; s++) {
-              BrickTex<T> tx;
+              BrickTex<T, false> tx;
               tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
-              mx = fmaxf(mx, tx.tap(0, 0, 0));
+              mx = fmaxf(mx, tx.centre());
               ct = add3(ct, inc_tex);
             }
             n_samples += (unsigned long long)count;
@@ -193,14 +243,16 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
 #pragma unroll 1
           for (int s = 0; s < count; s++) {
             n_samples++;
-            BrickTex<T> tx;
+            BrickTex<T, (MODE != 0 || LIT)> tx;
             tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
-            const float data = tx.tap(0, 0, 0);
             f4 sc;
             if (MODE == 0 && !LIT) {
+              const float data = tx.centre();
               sc = tf_fetch(P, data * P.trans_scale, 0.0f);
             } else {
-              const f3 g = tx.gradient();
+              float data;
+              f3 g;
+              tx.centre_and_gradient(data, g);
               if (MODE == 0) sc = tf_fetch(P, data * P.trans_scale, 0.0f);
               else sc = tf_fetch(P, data * P.trans_scale, 1.0f - len3(g) * P.gradient_scale);
               if (LIT) {
