@@ -227,12 +227,38 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
           if (MODE == 2) {   // GLRaycaster-MIP-Rot-FS.glsl:64-76, then glBlendEquation(GL_MAX)
             float mx = 0.0f;
             f3 ct = et;
+            // A segment whose two ends have interior footprints (with a margin far above the drift of the position
+            // accumulation) has only interior samples: a branch-free loop, unrolled so that the loads of several
+            // (independent) samples are in flight.  Same arithmetic as BrickTex::set + centre().
+            const f3 nf = F3((float)nv[0], (float)nv[1], (float)nv[2]);
+            const f3 ue = F3(fmaf(et.x, nf.x, -0.5f), fmaf(et.y, nf.y, -0.5f), fmaf(et.z, nf.z, -0.5f));
+            const f3 ux = F3(fmaf(xt.x, nf.x, -0.5f), fmaf(xt.y, nf.y, -0.5f), fmaf(xt.z, nf.z, -0.5f));
+            const bool all_interior = P.nearest == 0 &&
+                fminf(ue.x, ux.x) >= 0.01f && fmaxf(ue.x, ux.x) <= nf.x - 1.01f &&
+                fminf(ue.y, ux.y) >= 0.01f && fmaxf(ue.y, ux.y) <= nf.y - 1.01f &&
+                fminf(ue.z, ux.z) >= 0.01f && fmaxf(ue.z, ux.z) <= nf.z - 1.01f;
+            if (all_interior) {
+              const int isy = (int)sy, isz = (int)sz;
+#pragma unroll 4
+              for (int s = 0; s < count; s++) {
+                const float vx = fmaf(ct.x, nf.x, -0.5f), vy = fmaf(ct.y, nf.y, -0.5f), vz = fmaf(ct.z, nf.z, -0.5f);
+                const float x0 = floorf(vx), y0 = floorf(vy), z0 = floorf(vz);
+                const float fx = vx - x0, fy = vy - y0, fz = vz - z0;
+                const T* c = vox + ((int)x0 + (int)y0 * isy + (int)z0 * isz);
+                const float v = tri(cvt(__ldg(c)), cvt(__ldg(c + 1)), cvt(__ldg(c + isy)), cvt(__ldg(c + isy + 1)),
+                                    cvt(__ldg(c + isz)), cvt(__ldg(c + isz + 1)), cvt(__ldg(c + isz + isy)),
+                                    cvt(__ldg(c + isz + isy + 1)), fx, fy, fz) * P.norm;
+                mx = fmaxf(mx, v);
+                ct = add3(ct, inc_tex);
+              }
+            } else {
 #pragma unroll 1
-            for (int s = 0; s < count; s++) {
-              BrickTex<T, false> tx;
-              tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
-              mx = fmaxf(mx, tx.centre());
-              ct = add3(ct, inc_tex);
+              for (int s = 0; s < count; s++) {
+                BrickTex<T, false> tx;
+                tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+                mx = fmaxf(mx, tx.centre());
+                ct = add3(ct, inc_tex);
+              }
             }
             n_samples += (unsigned long long)count;
             acc.x = fmaxf(acc.x, mx);
