@@ -285,7 +285,10 @@ typedef struct {
  * (AbstrRenderer.cpp:789-803,1125-1212), BuildSubFrameBrickList (:999-1100: frustum culling, legacy
  * ContainsData, depth sort), then GLRenderer::Render3DView's brick loop with GLRaycaster::Render3DPreLoop /
  * Render3DInLoop per brick (GLRenderer.cpp:2663-2748, GLRaycaster.cpp:348-478) and GL under-blending.
- * 1D / 2D transfer function modes with and without lighting; the result is read with tvk_read_rgba8/32f. */
+ * 1D / 2D transfer function modes with and without lighting, and the isosurface mode (RM_ISOSURFACE branch of
+ * Render3DInLoop, GLRaycaster.cpp:383-446: GLRaycaster-ISO-FS.glsl + RefineIsosurface.glsl per brick, nearest hit
+ * kept by the depth test, then GLRenderer::ComposeSurfaceImage; tvk_read_iso_buffers returns the two hit targets).
+ * The result is read with tvk_read_rgba8/32f. */
 int tvk_render_classic(tvk_ctx* ctx, tvk_frame_stats* stats);
 /* One HQ MIP frame of a 2D window (RenderRegion2D with GetUseMIP()): AbstrRenderer::PlanHQMIPFrame
  * (AbstrRenderer.cpp:1214-1245: no frustum culling; LoD 0, or with use_mip_lod = m_bMIPLOD the coarsest LoD whose

@@ -39,7 +39,7 @@ struct ivec2 { int x, y; ivec2() : x(0), y(0) {} ivec2(int a, int b) : x(a), y(b
 struct uvec2 { uint x, y; uvec2() : x(0), y(0) {} uvec2(uint a, uint b) : x(a), y(b) {} };
 
 struct vec3 {
-  union { struct { float x, y, z; }; struct { float r, g, b; }; swz<vec2, float, 2> xy; };
+  union { struct { float x, y, z; }; struct { float r, g, b; }; swz<vec2, float, 2> xy; swz<vec3, float, 3> xyz; };
   vec3() : x(0), y(0), z(0) {}
   vec3(float a, float b, float c) : x(a), y(b), z(c) {}
   explicit vec3(float a) : x(a), y(a), z(a) {}

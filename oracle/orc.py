@@ -138,6 +138,8 @@ def lib():
                                       C.POINTER(RenderStats), C.c_int]),
         "orc_stereo_view": (None, [P, P, P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, P, P, P, P]),
         "orc_stereo_compose": (None, [C.c_int, P, P, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, P]),
+        "orc_classic_iso_render": (None, [C.POINTER(RenderParams), C.c_uint32, P, C.c_uint32, P, P, P,
+                                          C.POINTER(RenderStats), C.c_int]),
         "orc_mip_lod": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_int]),
         "orc_mip_brick_list": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, P, C.c_double * 4, P,
                                             C.c_uint32]),
@@ -478,3 +480,15 @@ def stereo_compose(mode, left, right, eye_swap=False, alternating_frame_id=0, sp
     lib().orc_stereo_compose(mode, _p(l), _p(r), l.shape[1], l.shape[0], int(bool(eye_swap)), alternating_frame_id,
                              split_coord, _p(out))
     return out
+
+
+def classic_iso_render(params, lod, bricks, n, brick_arrays, threads=1):
+    """Classic isosurface frame -> (hit_pos [h*w, 4], hit_normal [h*w, 4], stats); compose with iso_compose()."""
+    keep = [np.ascontiguousarray(a) if a is not None else None for a in brick_arrays]
+    ptrs = (C.c_void_p * max(n, 1))(*[(a.ctypes.data if a is not None else None) for a in keep])
+    hp = np.zeros((params.height * params.width, 4), np.float32)
+    hn = np.zeros((params.height * params.width, 4), np.float32)
+    st = RenderStats()
+    lib().orc_classic_iso_render(C.byref(params), lod, C.cast(bricks, C.c_void_p), n, C.cast(ptrs, C.c_void_p), _p(hp), _p(hn),
+                                 C.byref(st), threads)
+    return hp, hn, st

@@ -610,4 +610,128 @@ void orc_mip_render(const orc_render_params* p, uint32_t lod, const orc_classic_
   if (stats) { memset(stats, 0, sizeof(*stats)); stats->samples = samples; }
 }
 
+
+/* Classic isosurface frame (GLRaycaster::Render3DInLoop, RM_ISOSURFACE branch, GLRaycaster.cpp:383-446): per
+ * non-empty brick in list order the front faces go into the RGBA16F entry FBO and the back-face pass runs
+ * GLRaycaster-ISO-FS.glsl:56-105 -- first sample with value >= fIsoval, RefineIsosurface.glsl:37-52 (5 bisection
+ * steps), eye-space hit position by interpolation between ray entry and exit, normal = ComputeNormal
+ * (Volume3D.glsl:55-60), gl_FragDepth = vProjParam.x + vProjParam.y / -z -- into the two iso-hit targets under the
+ * depth test DF_LESS of the base state (GLRenderer.cpp:139; cleared to 1), so the nearest hit of all bricks stays.
+ * hit_pos: w*h*(x, y, z, fInterpolParam); hit_normal: w*h*(nx, ny, nz, brick number in the list).  The image is then
+ * orc_iso_compose (Compose-FS.glsl, which treats hit_pos.w == 0 as "no hit" -- a hit exactly at the ray entry is
+ * dropped there, in the reference as well).  vProjParam = (far / (far - near), far * near / (near - far)) with near
+ * and far recovered from the projection matrix (m33 = -(f+n)/(f-n), m43 = -2fn/(f-n)) in double. */
+void orc_classic_iso_render(const orc_render_params* p, uint32_t lod, const orc_classic_brick* list, uint32_t n_bricks,
+                            const void* const* brick_data, float* hit_pos, float* hit_normal, orc_render_stats* stats,
+                            int n_threads) {
+  (void)lod;
+  double mv[16], pr[16], imv_d[16], ipr_d[16];
+  float imv[16], inv_proj[16];
+  for (int i = 0; i < 16; i++) { mv[i] = p->model_view[i]; pr[i] = p->projection[i]; }
+  inv4d(mv, imv_d); inv4d(pr, ipr_d);
+  for (int i = 0; i < 16; i++) { imv[i] = (float)imv_d[i]; inv_proj[i] = (float)ipr_d[i]; }
+  const float norm = p->dtype == ORC_U8 ? 1.0f / 255.0f : p->dtype == ORC_U16 ? 1.0f / 65535.0f : 1.0f;
+  const float mn = fminf(p->scale[0], fminf(p->scale[1], p->scale[2]));
+  const v3 dscale = V3(1.0f / (p->scale[0] / mn), 1.0f / (p->scale[1] / mn), 1.0f / (p->scale[2] / mn));
+  const double zn = pr[14] / (pr[10] - 1.0), zf = pr[14] / (pr[10] + 1.0);
+  const float ppx = (float)(zf / (zf - zn)), ppy = (float)(zf * zn / (zn - zf));
+  const size_t n_pix = (size_t)p->width * p->height;
+  memset(hit_pos, 0, n_pix * 16);
+  memset(hit_normal, 0, n_pix * 16);
+  std::vector<float> depth(n_pix, 1.0f), fbo(n_pix * 3), near_pt(n_pix * 3);
+  for (uint32_t y = 0; y < p->height; y++)
+    for (uint32_t x = 0; x < p->width; x++) {
+      float nx = ((float)x + 0.5f) / (float)p->width * 2.0f - 1.0f;
+      float ny = ((float)y + 0.5f) / (float)p->height * 2.0f - 1.0f;
+      v4 nr = xform4(inv_proj, nx, ny, -1.0f, 1.0f);
+      size_t i = (size_t)y * p->width + x;
+      near_pt[3 * i] = nr.x / nr.w; near_pt[3 * i + 1] = nr.y / nr.w; near_pt[3 * i + 2] = nr.z / nr.w;
+      for (int k = 0; k < 3; k++) fbo[3 * i + k] = half_round(near_pt[3 * i + k]);
+    }
+  uint64_t samples = 0;
+  const v4 o4 = xform4(imv, 0.0f, 0.0f, 0.0f, 1.0f);
+  for (uint32_t bi = 0; bi < n_bricks; bi++) {
+    const orc_classic_brick& b = list[bi];
+    if (b.empty) continue;
+    btex T; T.data = brick_data[bi]; T.dtype = p->dtype; T.nearest = p->nearest;
+    for (int i = 0; i < 3; i++) T.n[i] = b.n_vox[i];
+    const v3 c = V3(b.center[0], b.center[1], b.center[2]), e = V3(b.ext[0], b.ext[1], b.ext[2]);
+    const v3 pmin = sub3(c, V3(e.x / 2.0f, e.y / 2.0f, e.z / 2.0f)), pmax = add3(c, V3(e.x / 2.0f, e.y / 2.0f, e.z / 2.0f));
+    const v3 tmin = V3(b.tex_min[0], b.tex_min[1], b.tex_min[2]), tmax = V3(b.tex_max[0], b.tex_max[1], b.tex_max[2]);
+    const v3 tsc = div3(sub3(tmin, tmax), sub3(pmin, pmax));
+    const v3 vstep = V3(1.0f / (float)b.n_vox[0], 1.0f / (float)b.n_vox[1], 1.0f / (float)b.n_vox[2]);
+    const float ray_step = min3(scl3(mul3(e, vstep), 0.5f * 1.0f / p->sample_rate_modifier));
+    const float lo[3] = {pmin.x, pmin.y, pmin.z}, hi[3] = {pmax.x, pmax.y, pmax.z};
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads < 1 ? 1 : n_threads) reduction(+ : samples)
+    for (int64_t py = 0; py < (int64_t)p->height; py++)
+      for (uint32_t px = 0; px < p->width; px++) {
+        const size_t i = (size_t)py * p->width + px;
+        const v3 pn = V3(near_pt[3 * i], near_pt[3 * i + 1], near_pt[3 * i + 2]);
+        const v4 n4 = xform4(imv, pn.x, pn.y, pn.z, 1.0f);
+        const float o[3] = {o4.x, o4.y, o4.z}, d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
+        float s_in = -INFINITY, s_out = INFINITY;
+        bool miss = false;
+        for (int k = 0; k < 3; k++) {
+          if (d[k] == 0.0f) { if (o[k] < lo[k] || o[k] > hi[k]) miss = true; continue; }
+          float t0 = (lo[k] - o[k]) / d[k], t1 = (hi[k] - o[k]) / d[k];
+          s_in = fmaxf(s_in, fminf(t0, t1));
+          s_out = fminf(s_out, fmaxf(t0, t1));
+        }
+        if (miss || !(s_out > fmaxf(s_in, 1.0f))) continue;
+        if (s_in > 1.0f) {
+          const v3 fe = scl3(pn, s_in);
+          fbo[3 * i] = half_round(fe.x); fbo[3 * i + 1] = half_round(fe.y); fbo[3 * i + 2] = half_round(fe.z);
+        }
+        const v3 entry = V3(fbo[3 * i], fbo[3 * i + 1], fbo[3 * i + 2]);
+        const v3 exit_ = scl3(pn, s_out);
+        auto to_tex = [&](v3 q) {
+          v4 w = xform4(imv, q.x, q.y, q.z, 1.0f);
+          return add3(mul3(sub3(V3(w.x, w.y, w.z), pmax), tsc), tmax);
+        };
+        const v3 et = to_tex(entry), xt = to_tex(exit_);
+        const float len = len3(sub3(exit_, entry));
+        const float len_tex = len3(sub3(xt, et));
+        const float nsteps = len / ray_step;
+        const int count = (int)nsteps + 1;
+        const v3 inc_tex = V3((xt.x - et.x) / nsteps, (xt.y - et.y) / nsteps, (xt.z - et.z) / nsteps);
+        v3 ct = et;
+        bool hit = false;
+        for (int s = 0; s < count; s++) {
+          samples++;
+          if (T.sample(ct, 0, 0, 0, norm) >= p->isoval) { hit = true; break; }
+          ct = add3(ct, inc_tex);
+        }
+        if (!hit) continue;                                   /* discard */
+        v3 rd = V3(inc_tex.x / 2.0f, inc_tex.y / 2.0f, inc_tex.z / 2.0f);   /* RefineIsosurface */
+        ct = sub3(ct, rd);
+        for (int k = 0; k < 5; k++) {
+          rd = V3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
+          samples++;
+          if (T.sample(ct, 0, 0, 0, norm) >= p->isoval) ct = sub3(ct, rd); else ct = add3(ct, rd);
+        }
+        const float f = len3(sub3(ct, et)) / len_tex;
+        const float omf = 1.0f - f;
+        const v3 hp = add3(scl3(entry, omf), scl3(exit_, f));
+        float dz = ppx + (ppy / -hp.z);
+        dz = fminf(fmaxf(dz, 0.0f), 1.0f);                    /* GL clamps the written depth to the depth range */
+        if (!(dz < depth[i])) continue;                       /* DF_LESS */
+        depth[i] = dz;
+        const float xp = T.sample(ct, +1, 0, 0, norm), xm = T.sample(ct, -1, 0, 0, norm);
+        const float yp = T.sample(ct, 0, -1, 0, norm), ym = T.sample(ct, 0, +1, 0, norm);
+        const float zp = T.sample(ct, 0, 0, +1, norm), zm = T.sample(ct, 0, 0, -1, norm);
+        const v3 g = V3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+        const v3 gs = mul3(g, dscale);
+        const float* m = imv;
+        v3 nr = V3(m[0] * gs.x + m[1] * gs.y + m[2] * gs.z, m[4] * gs.x + m[5] * gs.y + m[6] * gs.z,
+                   m[8] * gs.x + m[9] * gs.y + m[10] * gs.z);
+        const float l = len3(nr);
+        if (l > 0.0f) nr = scl3(nr, 1.0f / l);
+        float* hp_o = hit_pos + 4 * i; float* hn_o = hit_normal + 4 * i;
+        hp_o[0] = hp.x; hp_o[1] = hp.y; hp_o[2] = hp.z; hp_o[3] = f;
+        hn_o[0] = nr.x; hn_o[1] = nr.y; hn_o[2] = nr.z; hn_o[3] = (float)bi;
+      }
+  }
+  if (stats) { memset(stats, 0, sizeof(*stats)); stats->samples = samples; }
+}
+
 }  // extern "C"

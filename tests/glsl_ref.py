@@ -689,3 +689,79 @@ def run_stereo(exe, tmp, mode, left, right, eye_swap=False, alternating_frame_id
         f.write(np.ascontiguousarray(right, np.float32).tobytes())
     subprocess.check_call([exe, fin, fout])
     return np.fromfile(fout, np.float32).reshape(h, w, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Classic isosurface frames: GLRaycaster-ISO-FS.glsl + RefineIsosurface.glsl + Volume3D.glsl executed per
+# brick with the pass setup of GLRaycaster::Render3DInLoop's RM_ISOSURFACE branch: two float targets, gl_FragDepth
+# under the depth test DF_LESS (cleared to 1), no blending.  The classic driver with the output stage exchanged.
+# ---------------------------------------------------------------------------------------------------------------------
+def _classic_iso_driver():
+    d = CLASSIC_DRIVER.replace("@TF_TYPE@", "sampler1D")
+    subs = [
+        ("vec4 gl_FragCoord, gl_FragColor; mat4x4 gl_TextureMatrix[1]; mat3 gl_NormalMatrix;",
+         "vec4 gl_FragCoord, gl_FragColor, gl_FragData[2]; mat4x4 gl_TextureMatrix[1]; mat3 gl_NormalMatrix;\n"
+         "float fIsoval, gl_FragDepth; vec2 vProjParam; int iTileID; bool g_discarded;"),
+        ("  ScaleMethod = 0; TFuncBias = 0.0f;\n",
+         "  ScaleMethod = 0; TFuncBias = 0.0f;\n"
+         "  fIsoval = fTransScale; vProjParam = vec2(fGradientScale, fStepScale);   // carried in the unused header slots\n"),
+        ("  std::vector<float> out(npx * 4, 0.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3);",
+         "  std::vector<float> out(npx * 4, 0.0f), out2(npx * 4, 0.0f), depthb(npx, 1.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3);"),
+        ("        gl_FragColor = vec4();\n        classic_main();\n",
+         "        gl_FragData[0] = vec4(); gl_FragData[1] = vec4(); g_discarded = false; iTileID = (int)bi;\n        iso_main();\n"),
+        ("        float* dst = &out[4 * i];                               // GL blending ONE_MINUS_DST_ALPHA, ONE\n"
+         "        const float k = 1.0f - dst[3];\n"
+         "        dst[0] = fmaf(k, gl_FragColor.x, dst[0]); dst[1] = fmaf(k, gl_FragColor.y, dst[1]);\n"
+         "        dst[2] = fmaf(k, gl_FragColor.z, dst[2]); dst[3] = fmaf(k, gl_FragColor.w, dst[3]);\n",
+         "        if (g_discarded) continue;\n"
+         "        const float dz = fminf(fmaxf(gl_FragDepth, 0.0f), 1.0f);   // depth range clamp, then DF_LESS\n"
+         "        if (!(dz < depthb[i])) continue;\n"
+         "        depthb[i] = dz;\n"
+         "        memcpy(&out[4 * i], &gl_FragData[0].x, 16); memcpy(&out2[4 * i], &gl_FragData[1].x, 16);\n"),
+        ("  fwrite(out.data(), 4, out.size(), f);\n", "  fwrite(out.data(), 4, out.size(), f);\n  fwrite(out2.data(), 4, out2.size(), f);\n"),
+    ]
+    for a, b in subs:
+        assert a in d, a
+        d = d.replace(a, b, 1)
+    return d
+
+
+def build_classic_iso(tmp):
+    pre = PRELUDE + ("#define discard { g_discarded = true; return; }\n"
+                     "extern vec4 gl_FragCoord, gl_FragColor, gl_FragData[2]; extern mat4x4 gl_TextureMatrix[1]; extern mat3 gl_NormalMatrix;\n"
+                     "extern float gl_FragDepth; extern bool g_discarded;\n")
+    parts = [pre]
+    for n, main in (("Volume3D.glsl", "unused_main"), ("RefineIsosurface.glsl", "unused_main2"), ("GLRaycaster-ISO-FS.glsl", "iso_main")):
+        parts.append("// ---- %s\n" % n + rewrite(read_shader(n), main))
+    src = "\n".join(parts)
+    # a swizzle passed as an `inout` argument: GLSL copies in and out, a C++ reference cannot bind to the proxy
+    call = "RefineIsosurface(vRayIncTex, vHitPosTex.xyz, fIsoval)"
+    assert src.count(call) == 1
+    src = src.replace(call, "[&] { vec3 io_ = vHitPosTex.xyz; vec3 r_ = RefineIsosurface(vRayIncTex, io_, fIsoval); "
+                            "vHitPosTex.xyz = io_; return r_; }()")
+    return _compile(tmp, "classic_iso_as_cpp", src + _classic_iso_driver())
+
+
+def run_classic_iso(exe, tmp, params, inv_proj, imv, norm, domain_scale, proj_param, bricks, n_bricks, brick_arrays):
+    """Returns (hit_pos [h*w, 4], hit_normal [h*w, 4]) of the executed GLRaycaster-ISO-FS brick loop."""
+    w, h = params.width, params.height
+    zero3 = [0.0, 0.0, 0.0]
+    buf = [struct.pack("<II", w, h), np.asarray(inv_proj, np.float32).tobytes(), np.asarray(imv, np.float32).tobytes(),
+           struct.pack("<5f", params.isoval, proj_param[0], proj_param[1], params.sample_rate_modifier, norm),
+           np.asarray(domain_scale, np.float32).tobytes()]
+    for _ in range(4):
+        buf.append(np.asarray(zero3, np.float32).tobytes())
+    buf.append(struct.pack("<5I", params.dtype, params.nearest, 1, 1, n_bricks))
+    buf.append(np.zeros(4, np.uint8).tobytes())                    # a 1-texel transfer function nobody reads
+    for i in range(n_bricks):
+        b = bricks[i]
+        buf.append(np.asarray(list(b.center) + list(b.ext) + list(b.tex_min) + list(b.tex_max), np.float32).tobytes())
+        buf.append(struct.pack("<4I", b.n_vox[0], b.n_vox[1], b.n_vox[2], int(b.empty)))
+        if not b.empty:
+            buf.append(np.ascontiguousarray(brick_arrays[i]).tobytes())
+    fin, fout = os.path.join(str(tmp), "ciso.bin"), os.path.join(str(tmp), "ciso_out.bin")
+    with open(fin, "wb") as f:
+        f.write(b"".join(buf))
+    subprocess.check_call([exe, fin, fout])
+    raw = np.fromfile(fout, np.float32).reshape(2, h * w, 4)
+    return raw[0], raw[1]

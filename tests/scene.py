@@ -253,11 +253,18 @@ class Scene:
         vis = self.visibility_args()
         bricks, n = orc.classic_brick_list(p, lod, self.overlap, mm, vis)
         data = [None if bricks[i].empty else o.brick(*bricks[i].coord, lod) for i in range(n)]
-        img, st = orc.classic_render(p, lod, bricks, n, data, self.tf_bytes(), threads)
+        extra = {}
+        if self.mode == orc.RM_ISOSURFACE:
+            hp, hn, st = orc.classic_iso_render(p, lod, bricks, n, data, threads)
+            img = orc.iso_compose(p, hp, hn)
+            extra = dict(hit_pos=hp, hit_normal=hn)
+        else:
+            img, st = orc.classic_render(p, lod, bricks, n, data, self.tf_bytes(), threads)
         img = img.reshape(self.height, self.width, 4)
         order = np.array([[bricks[i].index, bricks[i].empty] for i in range(n)], np.int64).reshape(-1, 2)
         dist = np.array([bricks[i].distance for i in range(n)], np.float32)
-        return dict(image=img, rgba8=orc.rgba8(img), lod=lod, order=order, distance=dist, samples=st.samples)
+        return dict(image=img, rgba8=orc.rgba8(img), lod=lod, order=order, distance=dist, samples=st.samples, bricks=bricks,
+                    n=n, data=data, params=p, **extra)
 
     def oracle_mip(self, use_mip_lod=True, threads=8):
         """One HQ MIP frame (AbstrRenderer::PlanHQMIPFrame + GLRaycaster::RenderHQMIPInLoop per brick + Transfer-MIP)."""

@@ -19,6 +19,11 @@ CLASSIC_SCENES = {
     "c2_far_lod1": dict(base="c2_bricked36_1d_ert", translation=tb.translation(0.0, 0.0, -2.2)),
     # 2D TF + lighting on ragged u8 bricks, off-axis
     "ragged_2d_lit": dict(base="ragged_1d_lit", mode=orc.RM_2DTRANS, lighting=True),
+    # isosurface mode (GLRaycaster-ISO-FS + RefineIsosurface, nearest hit of all bricks by the depth test, Compose-FS)
+    "iso_f32": dict(base="c4_f32_iso"),
+    "iso_u16_noise": dict(base="c2_bricked36_1d_ert", mode=orc.RM_ISOSURFACE),
+    "iso_u8_ragged": dict(base="ragged_1d_lit", mode=orc.RM_ISOSURFACE, isovalue=90.0),
+    "iso_inside_aniso": dict(base="inside_aniso_2d", mode=orc.RM_ISOSURFACE),
 }
 
 
@@ -77,7 +82,13 @@ def test_cuda_classic_matches_oracle(name):
     mx, psnr = image_diff(img, ref["rgba8"])
     assert mx <= 2 and psnr >= 45.0, (mx, psnr)
     f = r.ReadRGBA32F()
-    if ref["lod"] == 0:                                            # no powf (libm vs CUDA) involved: identical floats
+    if s.mode == orc.RM_ISOSURFACE:
+        hp, hn = r.ReadIsoBuffers()
+        assert np.array_equal(hp.reshape(-1, 4), ref["hit_pos"])    # hit position + fInterpolParam of the winning brick
+        assert np.array_equal(hn.reshape(-1, 4), ref["hit_normal"]) # normal + iTileID
+        assert np.array_equal(f, ref["image"])
+        assert 0 < st.samples <= ref["samples"]                    # bricks behind the kept hit are not marched
+    elif ref["lod"] == 0:                                          # no powf (libm vs CUDA) involved: identical floats
         assert np.array_equal(f, ref["image"])
         assert st.samples == ref["samples"]
     else:
@@ -98,3 +109,16 @@ def test_cuda_classic_callback_source_and_gridleaper_coexist():
     assert r.PaintUntilConverged().converged
     assert image_diff(r.ReadRGBA8(), ref_g["rgba8"])[0] <= 2
     r.Cleanup()
+
+
+def test_classic_isosurface_agrees_with_the_gridleaper_isosurface():
+    """Two different traversals of the same surface (per-brick first hit under the depth test vs the page-table walk):
+    hit masks agree up to silhouette pixels and the shaded images are close."""
+    s = make("iso_f32")
+    c, g = s.oracle_classic(), s.oracle_render()
+    hc, hg = c["hit_pos"][:, 3] != 0, g["outs"][0].reshape(-1, 4)[:, 3] != 0
+    assert hc.sum() > 100 and float((hc != hg).mean()) < 0.01
+    assert float(np.abs(c["image"] - g["image"]).max()) < 2.0 / 255.0
+    # every hit carries the list position of a non-empty brick
+    tiles = c["hit_normal"][hc, 3].astype(int)
+    assert (c["order"][tiles, 1] == 0).all()

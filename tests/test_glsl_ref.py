@@ -201,3 +201,37 @@ def test_openmp_baseline_binary_equals_sequential_execution(tmp_path):
     npx = p.width * p.height
     img = np.fromfile(fout, np.float32, count=npx * 12).reshape(3, npx, 4)
     assert np.array_equal(img[0], g0) and np.array_equal(img[1], g1) and np.array_equal(img[2], g2)
+
+
+CLASSIC_ISO = [("c4_f32_iso", {}), ("c2_bricked36_1d_ert", dict(mode=orc.RM_ISOSURFACE)),
+               ("ragged_1d_lit", dict(mode=orc.RM_ISOSURFACE, isovalue=90.0)), ("inside_aniso_2d", dict(mode=orc.RM_ISOSURFACE))]
+
+
+@pytest.mark.parametrize("name,over", CLASSIC_ISO)
+def test_classic_isosurface_shaders_executed(tmp_path, name, over):
+    """GLRaycaster-ISO-FS.glsl + RefineIsosurface.glsl + Volume3D.glsl executed per brick in the oracle's
+    brick order with the RM_ISOSURFACE pass setup of GLRaycaster::Render3DInLoop (two float targets, gl_FragDepth under
+    DF_LESS), vs orc_classic_iso_render: the same pixels hit, the same brick wins the depth test, positions and normals
+    to rounding (a bisection step of RefineIsosurface may flip on the noise volume: <= 1/32 of a sample step)."""
+    s = golden_scenes.make(name, **over)
+    r = s.oracle_classic()
+    p = r["params"]
+    u = orc.uniforms(p)
+    pr = np.array(list(p.projection), np.float64)
+    zn, zf = pr[14] / (pr[10] - 1.0), pr[14] / (pr[10] + 1.0)
+    pp = (np.float32(zf / (zf - zn)), np.float32(zf * zn / (zn - zf)))
+    exe = glsl_ref.build_classic_iso(tmp_path)
+    hp, hn = glsl_ref.run_classic_iso(exe, tmp_path, p, u["inv_proj"], u["mv_inv"], u["norm"], u["domain_scale"], pp, r["bricks"],
+                                      r["n"], r["data"])
+    a, b = r["hit_pos"], r["hit_normal"]
+    hit_o, hit_g = a[:, 3] != 0, hp[:, 3] != 0
+    assert np.array_equal(hit_o, hit_g)
+    if hit_o.any():
+        assert np.array_equal(b[hit_o, 3], hn[hit_o, 3])                       # iTileID of the winning brick
+        assert float(np.abs(a[hit_o] - hp[hit_o]).max()) <= 2e-3
+        assert float(np.abs(b[hit_o, :3] - hn[hit_o, :3]).max()) <= 2e-2
+        assert float((np.abs(a[hit_o] - hp[hit_o]).max(axis=1) > 1e-5).mean()) <= 0.02
+    img_o = orc.iso_compose(p, a, b)
+    img_g = orc.iso_compose(p, hp, hn)
+    mx, psnr = image_diff(orc.rgba8(img_o.reshape(s.height, s.width, 4)), orc.rgba8(img_g.reshape(s.height, s.width, 4)))
+    assert mx <= 2 and psnr >= 45.0

@@ -21,6 +21,11 @@
 // GLRaycaster-MIP-Rot-FS.glsl:47-77 (maximum of texture3D(texVolume).x along the ray), bricks are blended with
 // BE_MAX (order-free, so the cell walk needs no sorting argument at all), and Transfer-MIP-FS.glsl:43-52
 // maps the blended maximum through the 1D transfer function (opacity ignored) -- fused into the same thread.
+// MODE 3 is the RM_ISOSURFACE branch of Render3DInLoop (GLRaycaster.cpp:383-446): the back-face pass runs
+// GLRaycaster-ISO-FS.glsl:56-105 (first sample >= fIsoval, RefineIsosurface.glsl:37-52, eye-space hit position
+// interpolated between ray entry and exit, ComputeNormal, gl_FragDepth) into the two iso-hit targets under the
+// base state's depth test DF_LESS (GLRenderer.cpp:139), so the nearest hit of all bricks stays; the image is then
+// composed by iso_compose_kernel (Compose-FS.glsl) like the GridLeaper isosurface frame.
 // The bricks live in the same slot-linear pool as the GridLeaper path (the reference keeps one 3D texture per
 // brick in GPUMemMan's LRU cache, GPUMemMan.cpp:846-996); the per-brick table maps a brick of the LoD to its
 // slot.  Same arithmetic contract as k_raycast.cu (-fmad=false, explicit fmaf in lerps / dots / compositing).
@@ -137,7 +142,7 @@ __device__ __forceinline__ f4 tf_fetch(const ClassicConsts& P, float s, float t)
   return r;
 }
 
-// MODE: 0 = 1D TF, 1 = 2D TF, 2 = HQ MIP
+// MODE: 0 = 1D TF, 1 = 2D TF, 2 = HQ MIP, 3 = isosurface (first hit, nearest of all bricks by the depth test)
 template <typename T, int MODE, bool LIT>
 __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ ClassicConsts P) {
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -148,6 +153,9 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
   const uint32_t S = P.axis_stride;
   f4 acc; acc.x = acc.y = acc.z = acc.w = 0.0f;   // MIP: x = blended maximum, w = coverage (the blended alpha)
   unsigned long long n_samples = 0;
+  float best_depth = 1.0f, best_negz = 0.0f;          // MODE 3: the depth buffer texel (cleared to 1) and -z of its hit
+  f4 hit_p, hit_n;                                    // MODE 3: the two iso-hit targets (cleared to 0)
+  hit_p.x = hit_p.y = hit_p.z = hit_p.w = 0.0f; hit_n = hit_p;
 
   // the eye ray through the pixel centre: eye-space points s * pn, world-space o + s * d
   const float nx = ((float)px + 0.5f) / (float)P.width * 2.0f - 1.0f;
@@ -224,7 +232,55 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
           rd = F3(rd.x / len, rd.y / len, rd.z / len);
           const f3 inc = scl3(rd, ray_step);
           const T* vox = pool + (uint64_t)(slot1 - 1u) * P.slot_voxels;
-          if (MODE == 2) {   // GLRaycaster-MIP-Rot-FS.glsl:64-76, then glBlendEquation(GL_MAX)
+          if (MODE == 3) {
+            // A fragment's hit lies between its ray entry and exit, so a brick whose (half-rounded) entry is clearly
+            // behind the kept hit cannot pass the depth test -- and neither can any brick after it on the ray.
+            if (best_depth < 1.0f && -entry.z > best_negz * 1.002f) break;
+            f3 ct = et;
+            bool hit = false;
+#pragma unroll 1
+            for (int s = 0; s < count; s++) {          // GLRaycaster-ISO-FS.glsl:80-87
+              n_samples++;
+              BrickTex<T, false> tx;
+              tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+              if (tx.centre() >= P.isoval) { hit = true; break; }
+              ct = add3(ct, inc_tex);
+            }
+            if (hit) {
+              f3 rdir = F3(inc_tex.x / 2.0f, inc_tex.y / 2.0f, inc_tex.z / 2.0f);   // RefineIsosurface.glsl:40-51
+              ct = sub3(ct, rdir);
+#pragma unroll 1
+              for (int k = 0; k < 5; k++) {
+                rdir = F3(rdir.x / 2.0f, rdir.y / 2.0f, rdir.z / 2.0f);
+                n_samples++;
+                BrickTex<T, false> tx;
+                tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+                if (tx.centre() >= P.isoval) ct = sub3(ct, rdir); else ct = add3(ct, rdir);
+              }
+              const float len_tex = len3(sub3(xt, et));
+              const float f = len3(sub3(ct, et)) / len_tex;
+              const float omf = 1.0f - f;
+              const f3 hp = add3(scl3(entry, omf), scl3(exit_, f));
+              float dz = P.proj_param[0] + (P.proj_param[1] / -hp.z);
+              dz = fminf(fmaxf(dz, 0.0f), 1.0f);       // depth-range clamp, then DF_LESS
+              if (dz < best_depth) {
+                best_depth = dz; best_negz = -hp.z;
+                BrickTex<T, true> tg;
+                tg.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+                float unused;
+                f3 g;
+                tg.centre_and_gradient(unused, g);
+                const f3 gs = mul3(g, dscale);           // ComputeNormal (Volume3D.glsl:55-60)
+                const float* m = P.imv;
+                f3 nrm = F3(m[0] * gs.x + m[1] * gs.y + m[2] * gs.z, m[4] * gs.x + m[5] * gs.y + m[6] * gs.z,
+                            m[8] * gs.x + m[9] * gs.y + m[10] * gs.z);
+                const float l = len3(nrm);
+                if (l > 0.0f) nrm = scl3(nrm, 1.0f / l);
+                hit_p.x = hp.x; hit_p.y = hp.y; hit_p.z = hp.z; hit_p.w = f;
+                hit_n.x = nrm.x; hit_n.y = nrm.y; hit_n.z = nrm.z; hit_n.w = (float)__ldg(P.list_pos + ((size_t)cell[2] * lay[1] + cell[1]) * lay[0] + cell[0]);
+              }
+            }
+          } else if (MODE == 2) {   // GLRaycaster-MIP-Rot-FS.glsl:64-76, then glBlendEquation(GL_MAX)
             float mx = 0.0f;
             f3 ct = et;
             // A segment whose two ends have interior footprints (with a margin far above the drift of the position
@@ -323,7 +379,10 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
       if (cell[ax] < 0 || cell[ax] >= (int)lay[ax]) break;
     }
   }
-  if (MODE == 2) {   // Transfer-MIP-FS.glsl:43-52 (1D transfer function, opacity ignored; uncovered pixels black)
+  if (MODE == 3) {
+    P.out[pix] = make_float4(hit_p.x, hit_p.y, hit_p.z, hit_p.w);
+    P.out_nrm[pix] = make_float4(hit_n.x, hit_n.y, hit_n.z, hit_n.w);
+  } else if (MODE == 2) {   // Transfer-MIP-FS.glsl:43-52 (1D transfer function, opacity ignored; uncovered pixels black)
     if (P.out_max) P.out_max[pix] = make_float2(acc.x, acc.w);
     f4 t; t.x = t.y = t.z = 0.0f;
     if (acc.w > 0.5f) t = tf_fetch(P, acc.x * P.trans_scale, 0.0f);
@@ -339,6 +398,8 @@ void launch_t(const ClassicConsts& c, int mode, int lighting, cudaStream_t s) {
   const dim3 block(64), grid((c.width + 7) / 8, (c.height + 7) / 8);
   if (mode == TVK_CLASSIC_MIP) {
     classic_kernel<T, 2, false><<<grid, block, 0, s>>>(c);
+  } else if (mode == TVK_RM_ISOSURFACE) {
+    classic_kernel<T, 3, false><<<grid, block, 0, s>>>(c);
   } else if (mode == TVK_RM_1DTRANS) {
     if (lighting) classic_kernel<T, 0, true><<<grid, block, 0, s>>>(c);
     else classic_kernel<T, 0, false><<<grid, block, 0, s>>>(c);

@@ -95,6 +95,9 @@ struct ClassicConsts {
   const void* pool;
   uint64_t slot_voxels;
   float4* out;
+  float isoval, proj_param[2];      // isosurface mode: fIsoval (normalised), vProjParam = (f/(f-n), f*n/(n-f))
+  float4* out_nrm;                  // isosurface mode: second iso-hit target (normal, brick number in the list)
+  const uint32_t* list_pos;         // isosurface mode: per brick of the LoD, its position in the frame's brick list (iTileID)
   float2* out_max;                  // HQ MIP only: (blended maximum, coverage) per pixel, the FBO Transfer-MIP reads
   unsigned long long* counters;
 };

@@ -1612,7 +1612,6 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
   int rc = check_renderable(ctx);
   if (rc) return rc;
   const tvk_render_params& p = ctx->params;
-  if (!mip && p.mode == TVK_RM_ISOSURFACE) return fail(ctx, TVK_ERR_INVALID, "classic path: isosurface mode is not built yet");
   if (mip && !ctx->tf1d_d) return fail(ctx, TVK_ERR_INVALID, "MIP: no 1D transfer function set (Transfer-MIP-FS needs it)");
   rc = ensure_frame(ctx, p.width, p.height);
   if (rc) return rc;
@@ -1789,8 +1788,15 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
     const uint32_t v = (m - TVK_BI_FLAG_COUNT) + 1u;
     if (table[b.index] != v) { table[b.index] = v; table_changed = true; }   // a cached plan whose bricks moved slots
   }
-  rc = ensure_classic(ctx, ax.size() + nv.size(), n_cells);
+  const bool iso = !mip && p.mode == TVK_RM_ISOSURFACE;
+  rc = ensure_classic(ctx, ax.size() + nv.size(), 2 * n_cells);
   if (rc) return rc;
+  if (iso) {   // iTileID = position in m_vCurrentBrickList (GLRaycaster.cpp:285-288), empty bricks counted
+    std::vector<uint32_t> pos(n_cells, 0u);
+    for (size_t i = 0; i < list.size(); i++) pos[list[i].index] = (uint32_t)i;
+    CU(cudaMemcpyAsync(ctx->classic_table_d + n_cells, pos.data(), n_cells * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));   // `pos` is a local
+  }
   if (!plan_hit) {
     CU(cudaMemcpyAsync(ctx->classic_axis_d, ax.data(), ax.size() * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(ctx->classic_axis_d + ax.size(), nv.data(), nv.size() * 4, cudaMemcpyHostToDevice, s));
@@ -1836,16 +1842,36 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
   c.slot_voxels = ctx->slot_voxels;
   c.out = ctx->buf[0];
   c.out_max = mip ? reinterpret_cast<float2*>(ctx->buf[1]) : nullptr;   // m_pFBO3DImageNext[1] of the MIP frame
+  c.out_nrm = ctx->buf[5];                                             // m_pFBOIsoHit, second target
+  c.list_pos = ctx->classic_table_d + n_cells;
+  // fIsoval = GetNormalizedIsovalue (AbstrRenderer.cpp:412-424); vProjParam (GLRaycaster.cpp:213-217) with near / far
+  // recovered from the projection matrix
+  c.isoval = ctx->dtype == TVK_U8 ? (float)(p.isovalue / 256.0) : ctx->dtype == TVK_U16 ? (float)(p.isovalue / 65536.0) : (float)p.isovalue;
+  {
+    const double zn = pr[14] / (pr[10] - 1.0), zf = pr[14] / (pr[10] + 1.0);
+    c.proj_param[0] = (float)(zf / (zf - zn));
+    c.proj_param[1] = (float)(zf * zn / (zn - zf));
+  }
   c.counters = ctx->counters_d;
   if (ctx->counters_on) CU(cudaMemsetAsync(ctx->counters_d, 0, 8 * sizeof(unsigned long long), s));
   launch_classic(c, mip ? TVK_CLASSIC_MIP : p.mode, p.lighting, ctx->dtype, s);
   CU(cudaGetLastError());
+  if (iso) {   // GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2763-2830)
+    float a[3], d[3], sp[3];
+    for (int i = 0; i < 3; i++) {
+      a[i] = p.ambient[i] * p.ambient[3];
+      d[i] = p.diffuse[i] * p.diffuse[3] * p.iso_color[i];
+      sp[i] = p.specular[i] * p.specular[3];
+    }
+    launch_iso_compose(ctx->buf[0], ctx->buf[5], ctx->buf[6], p.width, p.height, a, d, sp, p.light_dir, s);
+    CU(cudaGetLastError());
+  }
   CU(cudaEventRecord(ctx->ev[2], s));
   if (ctx->counters_on) CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));   // the host tables above must outlive their copies
   ctx->blank = true;              // the GridLeaper resume buffers no longer describe this image
   if (mip) ctx->mip_plan = key;   // list + device tables describe this plan (a classic frame leaves it invalid)
-  ctx->result_buf = ctx->buf[0];  // (an isosurface-mode MIP frame does not end in the deferred-shading buffer)
+  ctx->result_buf = mip ? ctx->buf[0] : nullptr;   // (an isosurface-mode MIP frame does not end in the deferred-shading buffer)
   if (st) {
     st->converged = 1;
     st->bricks_paged = paged;
