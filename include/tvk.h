@@ -303,6 +303,16 @@ int tvk_render_mip(tvk_ctx* ctx, int use_mip_lod, tvk_frame_stats* stats);
 /* parity tap: the blended maximum image of the last MIP frame, width*height*(maximum, coverage) floats --
  * what Transfer-MIP-FS reads from m_pFBO3DImageNext[1] */
 int tvk_read_mip_max(tvk_ctx* ctx, float* dst);
+/* ClearView state of the isosurface mode (AbstrRenderer::SetCV / SetCVIsoValue / SetCVColor / SetCVSize /
+ * SetCVContextScale / SetCVBorderScale / SetCVFocusPos, AbstrRenderer.cpp:1247-1360; defaults :131-136,171: colour
+ * (1,0,0), size 5.5, context scale 1, border scale 60, focus position (0,0,0.5,1) in object space).  With ClearView
+ * on, tvk_render_classic in isosurface mode runs GLRaycaster-ISO-CV-FS.glsl as a second pass per brick with the
+ * focus isovalue (GLRaycaster.cpp:429-444) and composes with Compose-CV-FS.glsl (GLRenderer.cpp:2777-2795).
+ * GLGridLeaper does not support ClearView (GLGridLeaper.h:47), so tvk_render ignores this state. */
+int tvk_set_clearview(tvk_ctx* ctx, int enable, double cv_isovalue, const float color[3], float size,
+                      float context_scale, float border_scale, const float focus_pos[4]);
+/* parity tap: m_pFBOCVHit's two targets of the last ClearView frame */
+int tvk_read_cv_buffers(tvk_ctx* ctx, float* cv_pos, float* cv_normal);
 /* parity tap: the brick list of the last classic / MIP frame (depth sorted; MIP: key order) and its LoD */
 int tvk_get_classic_brick_list(tvk_ctx* ctx, uint32_t* lod, tvk_classic_brick* dst, uint32_t cap, uint32_t* n);
 

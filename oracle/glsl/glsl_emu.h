@@ -27,6 +27,7 @@ template <typename V, typename S, int N> struct swz {
   swz& operator+=(const V& o) { for (int i = 0; i < N; i++) v[i] = v[i] + (&o.x)[i]; return *this; }
   swz& operator-=(const V& o) { for (int i = 0; i < N; i++) v[i] = v[i] - (&o.x)[i]; return *this; }
   swz& operator*=(const V& o) { for (int i = 0; i < N; i++) v[i] = v[i] * (&o.x)[i]; return *this; }
+  swz& operator-=(S o) { for (int i = 0; i < N; i++) v[i] = v[i] - o; return *this; }   // vector -= scalar
 };
 
 struct vec2 {
@@ -147,6 +148,11 @@ inline int max(int a, int b) { return a > b ? a : b; }
 inline uint min(uint a, uint b) { return a < b ? a : b; }
 inline uint min(int a, uint b) { return (uint)a < b ? (uint)a : b; }
 inline float abs(float a) { return fabsf(a); }
+// component-wise forms used by Compose-CV-FS.glsl
+inline vec3 abs(const vec3& a) { return vec3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+inline vec4 max(const vec4& a, float b) { return vec4(fmaxf(a.x, b), fmaxf(a.y, b), fmaxf(a.z, b), fmaxf(a.w, b)); }
+inline vec4 min(const vec4& a, float b) { return vec4(fminf(a.x, b), fminf(a.y, b), fminf(a.z, b), fminf(a.w, b)); }
+inline vec2 operator+(const vec2& a, const vec2& b) { return vec2(a.x + b.x, a.y + b.y); }
 inline float ceil(float a) { return ceilf(a); }
 inline float floor(float a) { return floorf(a); }
 inline float pow(float x, float e) {

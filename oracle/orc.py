@@ -140,6 +140,9 @@ def lib():
         "orc_stereo_compose": (None, [C.c_int, P, P, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float, P]),
         "orc_classic_iso_render": (None, [C.POINTER(RenderParams), C.c_uint32, P, C.c_uint32, P, P, P,
                                           C.POINTER(RenderStats), C.c_int]),
+        "orc_classic_cv_render": (None, [C.POINTER(RenderParams), C.c_uint32, P, C.c_uint32, P, C.c_float, P, P, P, P,
+                                         C.POINTER(RenderStats), C.c_int]),
+        "orc_cv_compose": (None, [C.POINTER(RenderParams), P, P, P, P, P, P, P, P]),
         "orc_mip_lod": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_int]),
         "orc_mip_brick_list": (C.c_uint32, [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, P, C.c_double * 4, P,
                                             C.c_uint32]),
@@ -492,3 +495,22 @@ def classic_iso_render(params, lod, bricks, n, brick_arrays, threads=1):
     lib().orc_classic_iso_render(C.byref(params), lod, C.cast(bricks, C.c_void_p), n, C.cast(ptrs, C.c_void_p), _p(hp), _p(hn),
                                  C.byref(st), threads)
     return hp, hn, st
+
+
+def classic_cv_render(params, lod, bricks, n, brick_arrays, cv_isoval, threads=1):
+    """Classic isosurface frame with ClearView -> (hit_pos, hit_normal, cv_pos, cv_normal, stats), each [h*w, 4]."""
+    keep = [np.ascontiguousarray(a) if a is not None else None for a in brick_arrays]
+    ptrs = (C.c_void_p * max(n, 1))(*[(a.ctypes.data if a is not None else None) for a in keep])
+    bufs = [np.zeros((params.height * params.width, 4), np.float32) for _ in range(4)]
+    st = RenderStats()
+    lib().orc_classic_cv_render(C.byref(params), lod, C.cast(bricks, C.c_void_p), n, C.cast(ptrs, C.c_void_p), cv_isoval,
+                                _p(bufs[0]), _p(bufs[1]), _p(bufs[2]), _p(bufs[3]), C.byref(st), threads)
+    return bufs[0], bufs[1], bufs[2], bufs[3], st
+
+
+def cv_compose(params, hit_pos, hit_normal, cv_pos, cv_normal, cv_color, cv_param, pick):
+    """Compose-CV-FS.glsl -> rgba [h*w, 4]."""
+    out = np.zeros_like(hit_pos)
+    col, prm, pk = (np.ascontiguousarray(v, np.float32) for v in (cv_color, cv_param, pick))
+    lib().orc_cv_compose(C.byref(params), _p(hit_pos), _p(hit_normal), _p(cv_pos), _p(cv_normal), _p(col), _p(prm), _p(pk), _p(out))
+    return out

@@ -621,9 +621,9 @@ void orc_mip_render(const orc_render_params* p, uint32_t lod, const orc_classic_
  * orc_iso_compose (Compose-FS.glsl, which treats hit_pos.w == 0 as "no hit" -- a hit exactly at the ray entry is
  * dropped there, in the reference as well).  vProjParam = (far / (far - near), far * near / (near - far)) with near
  * and far recovered from the projection matrix (m33 = -(f+n)/(f-n), m43 = -2fn/(f-n)) in double. */
-void orc_classic_iso_render(const orc_render_params* p, uint32_t lod, const orc_classic_brick* list, uint32_t n_bricks,
-                            const void* const* brick_data, float* hit_pos, float* hit_normal, orc_render_stats* stats,
-                            int n_threads) {
+static void classic_iso_impl(const orc_render_params* p, uint32_t lod, const orc_classic_brick* list, uint32_t n_bricks,
+                             const void* const* brick_data, float* hit_pos, float* hit_normal, float cv_isoval,
+                             float* cv_pos, float* cv_normal, orc_render_stats* stats, int n_threads) {
   (void)lod;
   double mv[16], pr[16], imv_d[16], ipr_d[16];
   float imv[16], inv_proj[16];
@@ -638,7 +638,8 @@ void orc_classic_iso_render(const orc_render_params* p, uint32_t lod, const orc_
   const size_t n_pix = (size_t)p->width * p->height;
   memset(hit_pos, 0, n_pix * 16);
   memset(hit_normal, 0, n_pix * 16);
-  std::vector<float> depth(n_pix, 1.0f), fbo(n_pix * 3), near_pt(n_pix * 3);
+  std::vector<float> depth(n_pix, 1.0f), depth2(n_pix, 1.0f), fbo(n_pix * 3), near_pt(n_pix * 3);
+  if (cv_pos) { memset(cv_pos, 0, n_pix * 16); memset(cv_normal, 0, n_pix * 16); }
   for (uint32_t y = 0; y < p->height; y++)
     for (uint32_t x = 0; x < p->width; x++) {
       float nx = ((float)x + 0.5f) / (float)p->width * 2.0f - 1.0f;
@@ -689,49 +690,159 @@ void orc_classic_iso_render(const orc_render_params* p, uint32_t lod, const orc_
           return add3(mul3(sub3(V3(w.x, w.y, w.z), pmax), tsc), tmax);
         };
         const v3 et = to_tex(entry), xt = to_tex(exit_);
-        const float len = len3(sub3(exit_, entry));
-        const float len_tex = len3(sub3(xt, et));
-        const float nsteps = len / ray_step;
-        const int count = (int)nsteps + 1;
-        const v3 inc_tex = V3((xt.x - et.x) / nsteps, (xt.y - et.y) / nsteps, (xt.z - et.z) / nsteps);
-        v3 ct = et;
-        bool hit = false;
-        for (int s = 0; s < count; s++) {
-          samples++;
-          if (T.sample(ct, 0, 0, 0, norm) >= p->isoval) { hit = true; break; }
-          ct = add3(ct, inc_tex);
-        }
-        if (!hit) continue;                                   /* discard */
-        v3 rd = V3(inc_tex.x / 2.0f, inc_tex.y / 2.0f, inc_tex.z / 2.0f);   /* RefineIsosurface */
-        ct = sub3(ct, rd);
-        for (int k = 0; k < 5; k++) {
-          rd = V3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
-          samples++;
-          if (T.sample(ct, 0, 0, 0, norm) >= p->isoval) ct = sub3(ct, rd); else ct = add3(ct, rd);
-        }
-        const float f = len3(sub3(ct, et)) / len_tex;
-        const float omf = 1.0f - f;
-        const v3 hp = add3(scl3(entry, omf), scl3(exit_, f));
-        float dz = ppx + (ppy / -hp.z);
-        dz = fminf(fmaxf(dz, 0.0f), 1.0f);                    /* GL clamps the written depth to the depth range */
-        if (!(dz < depth[i])) continue;                       /* DF_LESS */
-        depth[i] = dz;
-        const float xp = T.sample(ct, +1, 0, 0, norm), xm = T.sample(ct, -1, 0, 0, norm);
-        const float yp = T.sample(ct, 0, -1, 0, norm), ym = T.sample(ct, 0, +1, 0, norm);
-        const float zp = T.sample(ct, 0, 0, +1, norm), zm = T.sample(ct, 0, 0, -1, norm);
-        const v3 g = V3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
-        const v3 gs = mul3(g, dscale);
-        const float* m = imv;
-        v3 nr = V3(m[0] * gs.x + m[1] * gs.y + m[2] * gs.z, m[4] * gs.x + m[5] * gs.y + m[6] * gs.z,
-                   m[8] * gs.x + m[9] * gs.y + m[10] * gs.z);
-        const float l = len3(nr);
-        if (l > 0.0f) nr = scl3(nr, 1.0f / l);
+        auto normal_at = [&](v3 q) {                            /* ComputeNormal, Volume3D.glsl:43-60 */
+          const float xp = T.sample(q, +1, 0, 0, norm), xm = T.sample(q, -1, 0, 0, norm);
+          const float yp = T.sample(q, 0, -1, 0, norm), ym = T.sample(q, 0, +1, 0, norm);
+          const float zp = T.sample(q, 0, 0, +1, norm), zm = T.sample(q, 0, 0, -1, norm);
+          const v3 g = V3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+          const v3 gs = mul3(g, dscale);
+          const float* m = imv;
+          v3 nr = V3(m[0] * gs.x + m[1] * gs.y + m[2] * gs.z, m[4] * gs.x + m[5] * gs.y + m[6] * gs.z,
+                     m[8] * gs.x + m[9] * gs.y + m[10] * gs.z);
+          const float l = len3(nr);
+          if (l > 0.0f) nr = scl3(nr, 1.0f / l);
+          return nr;
+        };
+        /* march + RefineIsosurface from (e_eye, e_tex); returns false for `discard` */
+        auto first_hit = [&](v3 e_eye, v3 e_tex, float iso, v3& hp, float& f, v3& hit_tex) {
+          const float len = len3(sub3(exit_, e_eye));
+          const float len_tex = len3(sub3(xt, e_tex));
+          const float nsteps = len / ray_step;
+          const int count = (int)nsteps + 1;
+          const v3 inc_tex = V3((xt.x - e_tex.x) / nsteps, (xt.y - e_tex.y) / nsteps, (xt.z - e_tex.z) / nsteps);
+          v3 ct = e_tex;
+          bool hit = false;
+          for (int s = 0; s < count; s++) {
+            samples++;
+            if (T.sample(ct, 0, 0, 0, norm) >= iso) { hit = true; break; }
+            ct = add3(ct, inc_tex);
+          }
+          if (!hit) return false;
+          v3 rd = V3(inc_tex.x / 2.0f, inc_tex.y / 2.0f, inc_tex.z / 2.0f);   /* RefineIsosurface */
+          ct = sub3(ct, rd);
+          for (int k = 0; k < 5; k++) {
+            rd = V3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
+            samples++;
+            if (T.sample(ct, 0, 0, 0, norm) >= iso) ct = sub3(ct, rd); else ct = add3(ct, rd);
+          }
+          f = len3(sub3(ct, e_tex)) / len_tex;
+          const float omf = 1.0f - f;
+          hp = add3(scl3(e_eye, omf), scl3(exit_, f));
+          hit_tex = ct;
+          return true;
+        };
         float* hp_o = hit_pos + 4 * i; float* hn_o = hit_normal + 4 * i;
-        hp_o[0] = hp.x; hp_o[1] = hp.y; hp_o[2] = hp.z; hp_o[3] = f;
-        hn_o[0] = nr.x; hn_o[1] = nr.y; hn_o[2] = nr.z; hn_o[3] = (float)bi;
+        {                                                       /* GLRaycaster-ISO-FS.glsl into m_pFBOIsoHit */
+          v3 hp, ht; float f;
+          if (first_hit(entry, et, p->isoval, hp, f, ht)) {
+            float dz = ppx + (ppy / -hp.z);
+            dz = fminf(fmaxf(dz, 0.0f), 1.0f);                  /* GL clamps the written depth to the depth range */
+            if (dz < depth[i]) {                                /* DF_LESS */
+              depth[i] = dz;
+              const v3 nr = normal_at(ht);
+              hp_o[0] = hp.x; hp_o[1] = hp.y; hp_o[2] = hp.z; hp_o[3] = f;
+              hn_o[0] = nr.x; hn_o[1] = nr.y; hn_o[2] = nr.z; hn_o[3] = (float)bi;
+            }
+          }
+        }
+        if (cv_pos) {                                           /* GLRaycaster-ISO-CV-FS.glsl into m_pFBOCVHit */
+          v3 e2 = entry, et2 = et;
+          if ((float)bi == hn_o[3]) {                           /* the kept first-pass hit lies in this brick: resume there */
+            const float fl = hp_o[3], om = 1.0f - fl;
+            e2 = add3(scl3(entry, om), scl3(entry, fl));        /* sic: the shader blends the entry with itself (:68) */
+            et2 = add3(scl3(et, om), scl3(xt, fl));
+          }
+          v3 hp, ht; float f;
+          if (first_hit(e2, et2, cv_isoval, hp, f, ht)) {
+            float dz = ppx + (ppy / -exit_.z);                  /* depth of the ray EXIT (:99) */
+            dz = fminf(fmaxf(dz, 0.0f), 1.0f);
+            if (dz < depth2[i]) {
+              depth2[i] = dz;
+              const v3 nr = normal_at(ht);
+              float* q = cv_pos + 4 * i; float* qn = cv_normal + 4 * i;
+              q[0] = hp.x; q[1] = hp.y; q[2] = hp.z; q[3] = f;
+              qn[0] = nr.x; qn[1] = nr.y; qn[2] = nr.z; qn[3] = (float)bi;
+            }
+          }
+        }
       }
   }
   if (stats) { memset(stats, 0, sizeof(*stats)); stats->samples = samples; }
+}
+
+
+void orc_classic_iso_render(const orc_render_params* p, uint32_t lod, const orc_classic_brick* list, uint32_t n_bricks,
+                            const void* const* brick_data, float* hit_pos, float* hit_normal, orc_render_stats* stats,
+                            int n_threads) {
+  classic_iso_impl(p, lod, list, n_bricks, brick_data, hit_pos, hit_normal, 0.0f, nullptr, nullptr, stats, n_threads);
+}
+
+/* ClearView (m_bDoClearView, GLRaycaster.cpp:429-444): right after a brick's first pass the same back faces run
+ * GLRaycaster-ISO-CV-FS.glsl:56-105 with the focus isovalue (GetNormalizedCVIsovalue) into m_pFBOCVHit -- the ray
+ * resumes at the kept first-pass hit when that hit lies in this brick (texLastHit / texLastHitPos), and the depth
+ * written is that of the ray exit, so the first brick along the ray with a focus hit stays. */
+void orc_classic_cv_render(const orc_render_params* p, uint32_t lod, const orc_classic_brick* list, uint32_t n_bricks,
+                           const void* const* brick_data, float cv_isoval, float* hit_pos, float* hit_normal,
+                           float* cv_pos, float* cv_normal, orc_render_stats* stats, int n_threads) {
+  classic_iso_impl(p, lod, list, n_bricks, brick_data, hit_pos, hit_normal, cv_isoval, cv_pos, cv_normal, stats, n_threads);
+}
+
+/* Compose-CV-FS.glsl:57-98 over the four hit targets; light colours and parameters GLRenderer.cpp:2772-2795:
+ * cv_param = (m_fCVSize, m_fCVContextScale, m_fCVBorderScale), pick = m_vCVPos * modelView (eye space).
+ * The targets are GL_NEAREST / clamped; neighbours for the curvature estimate at +-1 pixel. */
+void orc_cv_compose(const orc_render_params* p, const float* hit_pos, const float* hit_normal, const float* cv_pos,
+                    const float* cv_normal, const float cv_color[3], const float cv_param[3], const float pick[3],
+                    float* rgba) {
+  const int w = (int)p->width, h = (int)p->height;
+  const v3 a = V3(p->ambient[0] * p->ambient[3], p->ambient[1] * p->ambient[3], p->ambient[2] * p->ambient[3]);
+  const v3 dd = V3(p->diffuse[0] * p->diffuse[3], p->diffuse[1] * p->diffuse[3], p->diffuse[2] * p->diffuse[3]);
+  const v3 d1 = V3(dd.x * p->iso_color[0], dd.y * p->iso_color[1], dd.z * p->iso_color[2]);
+  const v3 d2 = V3(dd.x * cv_color[0], dd.y * cv_color[1], dd.z * cv_color[2]);
+  const v3 sp = V3(p->specular[0] * p->specular[3], p->specular[1] * p->specular[3], p->specular[2] * p->specular[3]);
+  const v3 l = V3(p->light_dir[0], p->light_dir[1], p->light_dir[2]);
+  auto light = [&](v3 pos, v3 nrm, v3 dif) {
+    nrm.z = fabsf(nrm.z);
+    v3 view = norm3(V3(0.0f - pos.x, 0.0f - pos.y, 0.0f - pos.z));
+    float dn = dot3(nrm, view);
+    v3 refl = norm3(sub3(view, scl3(nrm, 2.0f * dn)));
+    float dl = fmaxf(fabsf(dot3(nrm, V3(-l.x, -l.y, -l.z))), 0.0f);
+    float s8 = pow8(fmaxf(dot3(refl, l), 0.0f));
+    return V3(clampf(a.x + dif.x * dl + sp.x * s8, 0.0f, 1.0f), clampf(a.y + dif.y * dl + sp.y * s8, 0.0f, 1.0f),
+              clampf(a.z + dif.z * dl + sp.z * s8, 0.0f, 1.0f));
+  };
+  auto nrm_at = [&](int x, int y) {
+    x = x < 0 ? 0 : x >= w ? w - 1 : x; y = y < 0 ? 0 : y >= h ? h - 1 : y;
+    const float* q = hit_normal + 4 * ((size_t)y * w + x);
+    return V3(q[0], q[1], q[2]);
+  };
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const size_t i = (size_t)y * w + x;
+      float* o = rgba + 4 * i;
+      o[0] = o[1] = o[2] = o[3] = 0.0f;
+      const float* hp = hit_pos + 4 * i;
+      if (hp[3] == 0.0f) continue;
+      const v3 pos = V3(hp[0], hp[1], hp[2]);
+      const v3 n = nrm_at(x, y);
+      const v3 ctx = light(pos, n, d1);
+      auto absd = [&](v3 q) { return V3(fabsf(q.x - n.x), fabsf(q.y - n.y), fabsf(q.z - n.z)); };
+      const v3 cs = add3(add3(add3(absd(nrm_at(x + 1, y)), absd(nrm_at(x - 1, y))), absd(nrm_at(x, y + 1))), absd(nrm_at(x, y - 1)));
+      const float curv = len3(cs);
+      const float dist_w = len3(sub3(pos, V3(pick[0], pick[1], pick[2]))) * cv_param[0];
+      const float blend = clampf(fmaxf(curv * cv_param[1], clampf(dist_w, 0.0f, 1.0f)), 0.0f, 1.0f);
+      v4 focus = {0, 0, 0, 0};
+      const float* hp2 = cv_pos + 4 * i;
+      if (hp2[3] != 0.0f) {
+        const v3 f3_ = light(V3(hp2[0], hp2[1], hp2[2]), V3(cv_normal[4 * i], cv_normal[4 * i + 1], cv_normal[4 * i + 2]), d2);
+        focus.x = f3_.x; focus.y = f3_.y; focus.z = f3_.z; focus.w = 1.0f;
+      }
+      const float omb = 1.0f - blend;
+      float c[4] = {ctx.x * blend + focus.x * omb, ctx.y * blend + focus.y * omb, ctx.z * blend + focus.z * omb,
+                    1.0f * blend + focus.w * omb};
+      for (int k = 0; k < 4; k++) c[k] = fminf(fmaxf(c[k], 0.0f), 1.0f);
+      const float border = 0.5f * (1.0f - fminf(fmaxf(fabsf(dist_w - 1.0f) * cv_param[2], 0.0f), 1.0f));
+      o[0] = c[0] - border; o[1] = c[1] - border; o[2] = c[2] - border; o[3] = c[3];
+    }
 }
 
 }  // extern "C"

@@ -765,3 +765,108 @@ def run_classic_iso(exe, tmp, params, inv_proj, imv, norm, domain_scale, proj_pa
     subprocess.check_call([exe, fin, fout])
     raw = np.fromfile(fout, np.float32).reshape(2, h * w, 4)
     return raw[0], raw[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ClearView: after a brick's GLRaycaster-ISO-FS pass the same back faces run GLRaycaster-ISO-CV-FS.glsl
+# into m_pFBOCVHit (reading the first pass's targets as texLastHit / texLastHitPos), and Compose-CV-FS.glsl shades the
+# four targets.  The classic isosurface driver with the second pass and the composition added; the ClearView
+# parameters travel in the (otherwise unused) transfer-function block of the scene file.
+# ---------------------------------------------------------------------------------------------------------------------
+def _classic_cv_driver():
+    d = _classic_iso_driver()
+    subs = [
+        ("float fIsoval, gl_FragDepth; vec2 vProjParam; int iTileID; bool g_discarded;",
+         "float fIsoval, gl_FragDepth; vec2 vProjParam; int iTileID; bool g_discarded;\n"
+         "sampler2D texLastHit, texLastHitPos, texRayHitPos, texRayHitNormal, texRayHitPos2, texRayHitNormal2;\n"
+         "vec3 vLightDiffuse2, vCVParam, vCVPickPos;"),
+        ("  std::vector<float> out(npx * 4, 0.0f), out2(npx * 4, 0.0f), depthb(npx, 1.0f),",
+         "  const float* cvp = (const float*)texTrans.rgba8;              // cv isovalue, diffuse2, (size, context, border), pick\n"
+         "  const float iso1 = fIsoval, iso2 = cvp[0];\n"
+         "  vLightDiffuse2 = vec3(cvp[1], cvp[2], cvp[3]); vCVParam = vec3(cvp[4], cvp[5], cvp[6]); vCVPickPos = vec3(cvp[7], cvp[8], cvp[9]);\n"
+         "  std::vector<float> out3(npx * 4, 0.0f), out4(npx * 4, 0.0f), depthb2(npx, 1.0f), fin(npx * 4, 0.0f);\n"
+         "  std::vector<float> out(npx * 4, 0.0f), out2(npx * 4, 0.0f), depthb(npx, 1.0f),"),
+        ("        gl_FragData[0] = vec4(); gl_FragData[1] = vec4(); g_discarded = false; iTileID = (int)bi;\n        iso_main();\n"
+         "        frags++;\n",
+         "        gl_FragData[0] = vec4(); gl_FragData[1] = vec4(); g_discarded = false; iTileID = (int)bi; fIsoval = iso1;\n        iso_main();\n"
+         "        frags++;\n"),
+        ("        if (g_discarded) continue;\n"
+         "        const float dz = fminf(fmaxf(gl_FragDepth, 0.0f), 1.0f);   // depth range clamp, then DF_LESS\n"
+         "        if (!(dz < depthb[i])) continue;\n"
+         "        depthb[i] = dz;\n"
+         "        memcpy(&out[4 * i], &gl_FragData[0].x, 16); memcpy(&out2[4 * i], &gl_FragData[1].x, 16);\n",
+         "        if (!g_discarded) {\n"
+         "          const float dz = fminf(fmaxf(gl_FragDepth, 0.0f), 1.0f);   // depth range clamp, then DF_LESS\n"
+         "          if (dz < depthb[i]) { depthb[i] = dz; memcpy(&out[4 * i], &gl_FragData[0].x, 16); memcpy(&out2[4 * i], &gl_FragData[1].x, 16); }\n"
+         "        }\n"
+         "        // second pass of the same brick (GLRaycaster.cpp:429-444): m_pFBOIsoHit bound as texLastHit / texLastHitPos\n"
+         "        texLastHit.f32 = out.data(); texLastHit.w = W; texLastHit.h = H;\n"
+         "        texLastHitPos.f32 = out2.data(); texLastHitPos.w = W; texLastHitPos.h = H;\n"
+         "        gl_FragData[0] = vec4(); gl_FragData[1] = vec4(); g_discarded = false; fIsoval = iso2;\n"
+         "        cv_main();\n"
+         "        if (!g_discarded) {\n"
+         "          const float dz = fminf(fmaxf(gl_FragDepth, 0.0f), 1.0f);\n"
+         "          if (dz < depthb2[i]) { depthb2[i] = dz; memcpy(&out3[4 * i], &gl_FragData[0].x, 16); memcpy(&out4[4 * i], &gl_FragData[1].x, 16); }\n"
+         "        }\n"),
+        ("  fwrite(out.data(), 4, out.size(), f);\n  fwrite(out2.data(), 4, out2.size(), f);\n",
+         "  texRayHitPos.f32 = out.data(); texRayHitNormal.f32 = out2.data(); texRayHitPos2.f32 = out3.data(); texRayHitNormal2.f32 = out4.data();\n"
+         "  texRayHitPos.w = texRayHitNormal.w = texRayHitPos2.w = texRayHitNormal2.w = W;\n"
+         "  texRayHitPos.h = texRayHitNormal.h = texRayHitPos2.h = texRayHitNormal2.h = H;\n"
+         "  for (uint32_t y = 0; y < H; y++)\n"
+         "    for (uint32_t x = 0; x < W; x++) {                          // GLRenderer::ComposeSurfaceImage, ClearView branch\n"
+         "      gl_FragCoord = vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);\n"
+         "      gl_FragColor = vec4(); g_discarded = false;\n"
+         "      compose_cv_main();\n"
+         "      if (!g_discarded) memcpy(&fin[4 * ((size_t)y * W + x)], &gl_FragColor.x, 16);\n"
+         "    }\n"
+         "  fwrite(out.data(), 4, out.size(), f);\n  fwrite(out2.data(), 4, out2.size(), f);\n"
+         "  fwrite(out3.data(), 4, out3.size(), f);\n  fwrite(out4.data(), 4, out4.size(), f);\n  fwrite(fin.data(), 4, fin.size(), f);\n"),
+    ]
+    for a, b in subs:
+        assert a in d, a
+        d = d.replace(a, b, 1)
+    # the FILE* f of the output stage is opened before the composition loop writes: move the declaration up
+    return d
+
+
+def build_classic_cv(tmp):
+    pre = PRELUDE + ("#define discard { g_discarded = true; return; }\n"
+                     "extern vec4 gl_FragCoord, gl_FragColor, gl_FragData[2]; extern mat4x4 gl_TextureMatrix[1]; extern mat3 gl_NormalMatrix;\n"
+                     "extern float gl_FragDepth; extern bool g_discarded;\n")
+    parts = [pre]
+    for n, main in (("Volume3D.glsl", "unused_main"), ("RefineIsosurface.glsl", "unused_main2"), ("GLRaycaster-ISO-FS.glsl", "iso_main"),
+                    ("GLRaycaster-ISO-CV-FS.glsl", "cv_main"), ("Compose-CV-FS.glsl", "compose_cv_main")):
+        parts.append("// ---- %s\n" % n + rewrite(read_shader(n), main))
+    src = "\n".join(parts)
+    call = "RefineIsosurface(vRayIncTex, vHitPosTex.xyz, fIsoval)"      # inout swizzle argument: copy in, copy out
+    assert src.count(call) == 2
+    src = src.replace(call, "[&] { vec3 io_ = vHitPosTex.xyz; vec3 r_ = RefineIsosurface(vRayIncTex, io_, fIsoval); "
+                            "vHitPosTex.xyz = io_; return r_; }()")
+    return _compile(tmp, "classic_cv_as_cpp", src + _classic_cv_driver())
+
+
+def run_classic_cv(exe, tmp, params, inv_proj, imv, norm, domain_scale, proj_param, light, cv_isoval, diffuse2, cv_param, pick,
+                   bricks, n_bricks, brick_arrays):
+    """Returns (hit_pos, hit_normal, cv_pos, cv_normal, rgba), each [h*w, 4]."""
+    w, h = params.width, params.height
+    buf = [struct.pack("<II", w, h), np.asarray(inv_proj, np.float32).tobytes(), np.asarray(imv, np.float32).tobytes(),
+           struct.pack("<5f", params.isoval, proj_param[0], proj_param[1], params.sample_rate_modifier, norm),
+           np.asarray(domain_scale, np.float32).tobytes()]
+    for k in ("ambient", "diffuse", "specular", "dir"):
+        buf.append(np.asarray(light[k], np.float32).tobytes())
+    cv = np.zeros(12, np.float32)
+    cv[0] = cv_isoval; cv[1:4] = diffuse2; cv[4:7] = cv_param; cv[7:10] = pick
+    buf.append(struct.pack("<5I", params.dtype, params.nearest, 12, 1, n_bricks))
+    buf.append(cv.tobytes())                                       # 12 "texels" of the transfer-function block
+    for i in range(n_bricks):
+        b = bricks[i]
+        buf.append(np.asarray(list(b.center) + list(b.ext) + list(b.tex_min) + list(b.tex_max), np.float32).tobytes())
+        buf.append(struct.pack("<4I", b.n_vox[0], b.n_vox[1], b.n_vox[2], int(b.empty)))
+        if not b.empty:
+            buf.append(np.ascontiguousarray(brick_arrays[i]).tobytes())
+    fin, fout = os.path.join(str(tmp), "ccv.bin"), os.path.join(str(tmp), "ccv_out.bin")
+    with open(fin, "wb") as f:
+        f.write(b"".join(buf))
+    subprocess.check_call([exe, fin, fout])
+    raw = np.fromfile(fout, np.float32).reshape(5, h * w, 4)
+    return raw[0], raw[1], raw[2], raw[3], raw[4]

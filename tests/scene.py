@@ -254,7 +254,18 @@ class Scene:
         bricks, n = orc.classic_brick_list(p, lod, self.overlap, mm, vis)
         data = [None if bricks[i].empty else o.brick(*bricks[i].coord, lod) for i in range(n)]
         extra = {}
-        if self.mode == orc.RM_ISOSURFACE:
+        cv = getattr(self, "clearview", None)
+        if self.mode == orc.RM_ISOSURFACE and cv:
+            # AbstrRenderer ClearView state: m_fCVIsovalue, m_vCVColor, m_fCVSize, m_fCVContextScale, m_fCVBorderScale, m_vCVPos
+            iso2 = {orc.U8: F(cv["isovalue"] / 256.0), orc.U16: F(cv["isovalue"] / 65536.0), orc.F32: F(cv["isovalue"])}[self.dtype]
+            hp, hn, cp, cn, st = orc.classic_cv_render(p, lod, bricks, n, data, float(iso2), threads)
+            mv = np.array(list(p.model_view), F).reshape(4, 4)
+            q = np.asarray(cv.get("pos", (0.0, 0.0, 0.5, 1.0)), F)
+            pick = [F(F(F(q[0] * mv[0, c] + q[1] * mv[1, c]) + q[2] * mv[2, c]) + q[3] * mv[3, c]) for c in range(3)]
+            prm = (cv.get("size", 5.5), cv.get("context_scale", 1.0), cv.get("border_scale", 60.0))
+            img = orc.cv_compose(p, hp, hn, cp, cn, cv.get("color", (1.0, 0.0, 0.0)), prm, pick)
+            extra = dict(hit_pos=hp, hit_normal=hn, cv_pos=cp, cv_normal=cn, cv_isoval=float(iso2), pick=pick, cv_param=prm)
+        elif self.mode == orc.RM_ISOSURFACE:
             hp, hn, st = orc.classic_iso_render(p, lod, bricks, n, data, threads)
             img = orc.iso_compose(p, hp, hn)
             extra = dict(hit_pos=hp, hit_normal=hn)

@@ -122,3 +122,52 @@ def test_classic_isosurface_agrees_with_the_gridleaper_isosurface():
     # every hit carries the list position of a non-empty brick
     tiles = c["hit_normal"][hc, 3].astype(int)
     assert (c["order"][tiles, 1] == 0).all()
+
+
+CLEARVIEW = [("c4_f32_iso", {}, dict(isovalue=0.8, size=2.5)),
+             ("c2_bricked36_1d_ert", dict(mode=orc.RM_ISOSURFACE), dict(isovalue=45000.0, color=(0.2, 0.9, 0.1), context_scale=2.0)),
+             ("ragged_1d_lit", dict(mode=orc.RM_ISOSURFACE, isovalue=90.0), dict(isovalue=140.0, size=3.0, border_scale=20.0,
+                                                                              pos=(0.1, -0.1, 0.3, 1.0))),
+             ("inside_aniso_2d", dict(mode=orc.RM_ISOSURFACE), dict(isovalue=50000.0))]
+
+
+def test_clearview_focus_surface_lies_behind_the_context_surface():
+    s = golden_scenes.make("c4_f32_iso")
+    s.clearview = dict(isovalue=0.8, size=2.5)
+    r = s.oracle_classic()
+    ctx, foc = r["hit_pos"][:, 3] != 0, r["cv_pos"][:, 3] != 0
+    assert foc.sum() > 0 and not (foc & ~ctx).any()                 # a focus hit needs iso_cv >= iso: the context is hit first
+    both = ctx & foc
+    assert (-r["cv_pos"][both, 2] >= -r["hit_pos"][both, 2] - 1e-4).all()   # ... and lies farther from the eye
+    plain = golden_scenes.make("c4_f32_iso").oracle_classic()
+    assert np.array_equal(plain["hit_pos"], r["hit_pos"])            # the first pass does not depend on ClearView
+    assert not np.array_equal(plain["image"], r["image"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,over,cv", CLEARVIEW)
+def test_cuda_clearview_matches_oracle(name, over, cv):
+    s = golden_scenes.make(name, **over)
+    s.clearview = dict(cv)
+    ref = s.oracle_classic()
+    r = s.make_renderer("device")
+    r.SetCV(True)
+    r.SetCVIsoValue(cv["isovalue"])
+    if "color" in cv: r.SetCVColor(cv["color"])
+    if "size" in cv: r.SetCVSize(cv["size"])
+    if "context_scale" in cv: r.SetCVContextScale(cv["context_scale"])
+    if "border_scale" in cv: r.SetCVBorderScale(cv["border_scale"])
+    if "pos" in cv: r.SetCVFocusPos(cv["pos"])
+    r.PaintClassic()
+    hp, hn = r.ReadIsoBuffers()
+    cp, cn = r.ReadCVBuffers()
+    assert np.array_equal(hp.reshape(-1, 4), ref["hit_pos"]) and np.array_equal(hn.reshape(-1, 4), ref["hit_normal"])
+    assert np.array_equal(cp.reshape(-1, 4), ref["cv_pos"]) and np.array_equal(cn.reshape(-1, 4), ref["cv_normal"])
+    assert np.array_equal(r.ReadRGBA32F(), ref["image"])
+    assert np.array_equal(r.ReadRGBA8(), ref["rgba8"])
+    # ClearView off again: the plain isosurface frame
+    r.SetCV(False)
+    r.PaintClassic()
+    plain = golden_scenes.make(name, **over).oracle_classic()
+    assert np.array_equal(r.ReadRGBA32F(), plain["image"])
+    r.Cleanup()

@@ -235,3 +235,41 @@ def test_classic_isosurface_shaders_executed(tmp_path, name, over):
     img_g = orc.iso_compose(p, hp, hn)
     mx, psnr = image_diff(orc.rgba8(img_o.reshape(s.height, s.width, 4)), orc.rgba8(img_g.reshape(s.height, s.width, 4)))
     assert mx <= 2 and psnr >= 45.0
+
+
+CLASSIC_CV = [("c4_f32_iso", {}, 0.8), ("c2_bricked36_1d_ert", dict(mode=orc.RM_ISOSURFACE), 45000.0),
+              ("ragged_1d_lit", dict(mode=orc.RM_ISOSURFACE, isovalue=90.0), 140.0)]
+
+
+@pytest.mark.parametrize("name,over,cv_iso", CLASSIC_CV)
+def test_clearview_shaders_executed(tmp_path, name, over, cv_iso):
+    """GLRaycaster-ISO-FS.glsl and, right after it per brick, GLRaycaster-ISO-CV-FS.glsl (reading the first
+    pass's targets as texLastHit / texLastHitPos, depth of the ray exit under DF_LESS), then Compose-CV-FS.glsl, vs
+    orc_classic_cv_render + orc_cv_compose: the same pixels hit in both passes, the same bricks win, values to rounding."""
+    s = golden_scenes.make(name, **over)
+    s.clearview = dict(isovalue=cv_iso, size=2.5)
+    r = s.oracle_classic()
+    p = r["params"]
+    u = orc.uniforms(p)
+    pr = np.array(list(p.projection), np.float64)
+    zn, zf = pr[14] / (pr[10] - 1.0), pr[14] / (pr[10] + 1.0)
+    pp = (np.float32(zf / (zf - zn)), np.float32(zf * zn / (zn - zf)))
+    d = np.array(u["diffuse"], np.float32)
+    light = dict(ambient=u["ambient"], diffuse=d * np.array(list(p.iso_color), np.float32), specular=u["specular"],
+                 dir=list(p.light_dir))
+    d2 = d * np.array([1.0, 0.0, 0.0], np.float32)
+    exe = glsl_ref.build_classic_cv(tmp_path)
+    out = glsl_ref.run_classic_cv(exe, tmp_path, p, u["inv_proj"], u["mv_inv"], u["norm"], u["domain_scale"], pp, light,
+                                  r["cv_isoval"], d2, r["cv_param"], r["pick"], r["bricks"], r["n"], r["data"])
+    for k, (pos, nrm) in enumerate((("hit_pos", "hit_normal"), ("cv_pos", "cv_normal"))):
+        a, b, an, bn = r[pos], out[2 * k], r[nrm], out[2 * k + 1]
+        hit = a[:, 3] != 0
+        assert np.array_equal(hit, b[:, 3] != 0)
+        if hit.any():
+            assert np.array_equal(an[hit, 3], bn[hit, 3])                      # iTileID of the brick that won the depth test
+            assert float(np.abs(a[hit] - b[hit]).max()) <= 2e-3 and float(np.abs(an[hit, :3] - bn[hit, :3]).max()) <= 2e-2
+    assert r["cv_pos"][:, 3].any()
+    img = r["image"].reshape(-1, 4)
+    assert float(np.abs(img - out[4]).max()) <= 5e-3 and float((np.abs(img - out[4]).max(axis=1) > 1e-4).mean()) <= 0.01
+    mx, psnr = image_diff(orc.rgba8(r["image"]), orc.rgba8(out[4].reshape(s.height, s.width, 4)))
+    assert mx <= 2 and psnr >= 45.0

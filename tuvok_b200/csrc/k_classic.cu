@@ -142,7 +142,63 @@ __device__ __forceinline__ f4 tf_fetch(const ClassicConsts& P, float s, float t)
   return r;
 }
 
-// MODE: 0 = 1D TF, 1 = 2D TF, 2 = HQ MIP, 3 = isosurface (first hit, nearest of all bricks by the depth test)
+// GLRaycaster-ISO-FS.glsl:72-98 / -ISO-CV-FS.glsl:72-98 for one fragment: march from (e_eye, e_tex) to the brick exit,
+// first sample >= iso, RefineIsosurface.glsl:37-52, eye-space hit by interpolation.  false = `discard`.
+template <typename T>
+__device__ __forceinline__ bool iso_first_hit(const ClassicConsts& P, const T* vox, const uint32_t nv[3], uint32_t sy, uint32_t sz,
+                                              f3 e_eye, f3 exit_, f3 e_tex, f3 xt, float ray_step, float iso, f3& hp, float& f,
+                                              f3& hit_tex, unsigned long long& n_samples) {
+  const float len = len3(sub3(exit_, e_eye));
+  const float len_tex = len3(sub3(xt, e_tex));
+  const float nsteps = len / ray_step;
+  const int count = (int)nsteps + 1;
+  const f3 inc_tex = F3((xt.x - e_tex.x) / nsteps, (xt.y - e_tex.y) / nsteps, (xt.z - e_tex.z) / nsteps);
+  f3 ct = e_tex;
+  bool hit = false;
+#pragma unroll 1
+  for (int s = 0; s < count; s++) {
+    n_samples++;
+    BrickTex<T, false> tx;
+    tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+    if (tx.centre() >= iso) { hit = true; break; }
+    ct = add3(ct, inc_tex);
+  }
+  if (!hit) return false;
+  f3 rdir = F3(inc_tex.x / 2.0f, inc_tex.y / 2.0f, inc_tex.z / 2.0f);
+  ct = sub3(ct, rdir);
+#pragma unroll 1
+  for (int k = 0; k < 5; k++) {
+    rdir = F3(rdir.x / 2.0f, rdir.y / 2.0f, rdir.z / 2.0f);
+    n_samples++;
+    BrickTex<T, false> tx;
+    tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+    if (tx.centre() >= iso) ct = sub3(ct, rdir); else ct = add3(ct, rdir);
+  }
+  f = len3(sub3(ct, e_tex)) / len_tex;
+  const float omf = 1.0f - f;
+  hp = add3(scl3(e_eye, omf), scl3(exit_, f));
+  hit_tex = ct;
+  return true;
+}
+
+// ComputeNormal (Volume3D.glsl:43-60): gl_NormalMatrix * (gradient * domainScale), safe-normalised
+template <typename T>
+__device__ __forceinline__ f3 iso_normal(const ClassicConsts& P, const T* vox, const uint32_t nv[3], uint32_t sy, uint32_t sz, f3 ct,
+                                         f3 dscale) {
+  BrickTex<T, true> tg;
+  tg.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
+  float unused;
+  f3 g;
+  tg.centre_and_gradient(unused, g);
+  const f3 gs = mul3(g, dscale);
+  const float* m = P.imv;
+  f3 nrm = F3(m[0] * gs.x + m[1] * gs.y + m[2] * gs.z, m[4] * gs.x + m[5] * gs.y + m[6] * gs.z, m[8] * gs.x + m[9] * gs.y + m[10] * gs.z);
+  const float l = len3(nrm);
+  if (l > 0.0f) nrm = scl3(nrm, 1.0f / l);
+  return nrm;
+}
+
+// MODE: 0 = 1D TF, 1 = 2D TF, 2 = HQ MIP, 3 = isosurface, 4 = isosurface + ClearView second pass (first hit, nearest of all bricks by the depth test)
 template <typename T, int MODE, bool LIT>
 __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ ClassicConsts P) {
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -154,8 +210,11 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
   f4 acc; acc.x = acc.y = acc.z = acc.w = 0.0f;   // MIP: x = blended maximum, w = coverage (the blended alpha)
   unsigned long long n_samples = 0;
   float best_depth = 1.0f, best_negz = 0.0f;          // MODE 3: the depth buffer texel (cleared to 1) and -z of its hit
-  f4 hit_p, hit_n;                                    // MODE 3: the two iso-hit targets (cleared to 0)
+  f4 hit_p, hit_n;                                    // MODE 3/4: the two iso-hit targets (cleared to 0)
   hit_p.x = hit_p.y = hit_p.z = hit_p.w = 0.0f; hit_n = hit_p;
+  f4 cv_p = hit_p, cv_n = hit_p;                      // MODE 4: m_pFBOCVHit's two targets and its depth texel
+  float cv_depth = 1.0f;
+  bool first_done = false, cv_done = false;
 
   // the eye ray through the pixel centre: eye-space points s * pn, world-space o + s * d
   const float nx = ((float)px + 0.5f) / (float)P.width * 2.0f - 1.0f;
@@ -232,52 +291,46 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
           rd = F3(rd.x / len, rd.y / len, rd.z / len);
           const f3 inc = scl3(rd, ray_step);
           const T* vox = pool + (uint64_t)(slot1 - 1u) * P.slot_voxels;
-          if (MODE == 3) {
-            // A fragment's hit lies between its ray entry and exit, so a brick whose (half-rounded) entry is clearly
-            // behind the kept hit cannot pass the depth test -- and neither can any brick after it on the ray.
-            if (best_depth < 1.0f && -entry.z > best_negz * 1.002f) break;
-            f3 ct = et;
-            bool hit = false;
-#pragma unroll 1
-            for (int s = 0; s < count; s++) {          // GLRaycaster-ISO-FS.glsl:80-87
-              n_samples++;
-              BrickTex<T, false> tx;
-              tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
-              if (tx.centre() >= P.isoval) { hit = true; break; }
-              ct = add3(ct, inc_tex);
-            }
-            if (hit) {
-              f3 rdir = F3(inc_tex.x / 2.0f, inc_tex.y / 2.0f, inc_tex.z / 2.0f);   // RefineIsosurface.glsl:40-51
-              ct = sub3(ct, rdir);
-#pragma unroll 1
-              for (int k = 0; k < 5; k++) {
-                rdir = F3(rdir.x / 2.0f, rdir.y / 2.0f, rdir.z / 2.0f);
-                n_samples++;
-                BrickTex<T, false> tx;
-                tx.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
-                if (tx.centre() >= P.isoval) ct = sub3(ct, rdir); else ct = add3(ct, rdir);
+          if (MODE == 3 || MODE == 4) {
+            // First pass (GLRaycaster-ISO-FS).  A fragment's hit lies between its ray entry and exit, so a brick whose
+            // (half-rounded) entry is clearly behind the kept hit cannot pass the depth test -- and neither can any
+            // brick after it on the ray.
+            if (best_depth < 1.0f && -entry.z > best_negz * 1.002f) first_done = true;
+            if (first_done && (MODE == 3 || cv_done)) break;
+            if (!first_done) {
+              f3 hp, ht; float f;
+              if (iso_first_hit<T>(P, vox, nv, sy, sz, entry, exit_, et, xt, ray_step, P.isoval, hp, f, ht, n_samples)) {
+                float dz = P.proj_param[0] + (P.proj_param[1] / -hp.z);
+                dz = fminf(fmaxf(dz, 0.0f), 1.0f);       // depth-range clamp, then DF_LESS
+                if (dz < best_depth) {
+                  best_depth = dz; best_negz = -hp.z;
+                  const f3 nrm = iso_normal<T>(P, vox, nv, sy, sz, ht, dscale);
+                  hit_p.x = hp.x; hit_p.y = hp.y; hit_p.z = hp.z; hit_p.w = f;
+                  hit_n.x = nrm.x; hit_n.y = nrm.y; hit_n.z = nrm.z;
+                  hit_n.w = (float)__ldg(P.list_pos + ((size_t)cell[2] * lay[1] + cell[1]) * lay[0] + cell[0]);
+                }
               }
-              const float len_tex = len3(sub3(xt, et));
-              const float f = len3(sub3(ct, et)) / len_tex;
-              const float omf = 1.0f - f;
-              const f3 hp = add3(scl3(entry, omf), scl3(exit_, f));
-              float dz = P.proj_param[0] + (P.proj_param[1] / -hp.z);
-              dz = fminf(fmaxf(dz, 0.0f), 1.0f);       // depth-range clamp, then DF_LESS
-              if (dz < best_depth) {
-                best_depth = dz; best_negz = -hp.z;
-                BrickTex<T, true> tg;
-                tg.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
-                float unused;
-                f3 g;
-                tg.centre_and_gradient(unused, g);
-                const f3 gs = mul3(g, dscale);           // ComputeNormal (Volume3D.glsl:55-60)
-                const float* m = P.imv;
-                f3 nrm = F3(m[0] * gs.x + m[1] * gs.y + m[2] * gs.z, m[4] * gs.x + m[5] * gs.y + m[6] * gs.z,
-                            m[8] * gs.x + m[9] * gs.y + m[10] * gs.z);
-                const float l = len3(nrm);
-                if (l > 0.0f) nrm = scl3(nrm, 1.0f / l);
-                hit_p.x = hp.x; hit_p.y = hp.y; hit_p.z = hp.z; hit_p.w = f;
-                hit_n.x = nrm.x; hit_n.y = nrm.y; hit_n.z = nrm.z; hit_n.w = (float)__ldg(P.list_pos + ((size_t)cell[2] * lay[1] + cell[1]) * lay[0] + cell[0]);
+            }
+            if (MODE == 4 && !cv_done) {
+              // Second pass of the same brick (GLRaycaster-ISO-CV-FS.glsl:56-105): resumes at the kept first-pass hit
+              // when that lies in this brick; its depth is the ray EXIT's, so the first brick with a focus hit stays.
+              const float tile = (float)__ldg(P.list_pos + ((size_t)cell[2] * lay[1] + cell[1]) * lay[0] + cell[0]);
+              f3 e2 = entry, et2 = et;
+              if (tile == hit_n.w) {
+                const float fl = hit_p.w, om = 1.0f - fl;
+                e2 = add3(scl3(entry, om), scl3(entry, fl));   // sic: the shader blends the entry with itself (:68)
+                et2 = add3(scl3(et, om), scl3(xt, fl));
+              }
+              f3 hp, ht; float f;
+              if (iso_first_hit<T>(P, vox, nv, sy, sz, e2, exit_, et2, xt, ray_step, P.cv_isoval, hp, f, ht, n_samples)) {
+                float dz = P.proj_param[0] + (P.proj_param[1] / -exit_.z);
+                dz = fminf(fmaxf(dz, 0.0f), 1.0f);
+                if (dz < cv_depth) {
+                  cv_depth = dz; cv_done = true;           // every later brick's exit is farther: it fails DF_LESS
+                  const f3 nrm = iso_normal<T>(P, vox, nv, sy, sz, ht, dscale);
+                  cv_p.x = hp.x; cv_p.y = hp.y; cv_p.z = hp.z; cv_p.w = f;
+                  cv_n.x = nrm.x; cv_n.y = nrm.y; cv_n.z = nrm.z; cv_n.w = tile;
+                }
               }
             }
           } else if (MODE == 2) {   // GLRaycaster-MIP-Rot-FS.glsl:64-76, then glBlendEquation(GL_MAX)
@@ -379,9 +432,13 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
       if (cell[ax] < 0 || cell[ax] >= (int)lay[ax]) break;
     }
   }
-  if (MODE == 3) {
+  if (MODE == 3 || MODE == 4) {
     P.out[pix] = make_float4(hit_p.x, hit_p.y, hit_p.z, hit_p.w);
     P.out_nrm[pix] = make_float4(hit_n.x, hit_n.y, hit_n.z, hit_n.w);
+    if (MODE == 4) {
+      P.out_cv[pix] = make_float4(cv_p.x, cv_p.y, cv_p.z, cv_p.w);
+      P.out_cv_nrm[pix] = make_float4(cv_n.x, cv_n.y, cv_n.z, cv_n.w);
+    }
   } else if (MODE == 2) {   // Transfer-MIP-FS.glsl:43-52 (1D transfer function, opacity ignored; uncovered pixels black)
     if (P.out_max) P.out_max[pix] = make_float2(acc.x, acc.w);
     f4 t; t.x = t.y = t.z = 0.0f;
@@ -399,7 +456,8 @@ void launch_t(const ClassicConsts& c, int mode, int lighting, cudaStream_t s) {
   if (mode == TVK_CLASSIC_MIP) {
     classic_kernel<T, 2, false><<<grid, block, 0, s>>>(c);
   } else if (mode == TVK_RM_ISOSURFACE) {
-    classic_kernel<T, 3, false><<<grid, block, 0, s>>>(c);
+    if (c.out_cv) classic_kernel<T, 4, false><<<grid, block, 0, s>>>(c);   // ClearView: second (focus) pass per brick
+    else classic_kernel<T, 3, false><<<grid, block, 0, s>>>(c);
   } else if (mode == TVK_RM_1DTRANS) {
     if (lighting) classic_kernel<T, 0, true><<<grid, block, 0, s>>>(c);
     else classic_kernel<T, 0, false><<<grid, block, 0, s>>>(c);

@@ -78,6 +78,71 @@ __global__ void over_kernel(const float4* front, const float4* back, float4* out
   }
 }
 
+// Compose-CV-FS.glsl:57-98 (ClearView): context surface shaded with the isosurface colour, focus surface (second hit
+// targets) with the ClearView colour, blended by the distance to the pick position and by a curvature estimate from the
+// four neighbouring normals (targets are GL_NEAREST / clamped), darkened along the lens border.
+struct CvConsts { float amb[3], dif[3], dif2[3], spe[3], ldir[3], param[3], pick[3]; };
+
+__device__ __forceinline__ void cv_light(const CvConsts& C, const float* dif, float px, float py, float pz, float nx, float ny, float nz,
+                                         float& r, float& g, float& b) {
+  nz = fabsf(nz);
+  float vx = 0.0f - px, vy = 0.0f - py, vz = 0.0f - pz;
+  float inv = 1.0f / sqrtf(dot(vx, vy, vz, vx, vy, vz));
+  vx = vx * inv; vy = vy * inv; vz = vz * inv;
+  const float dn = dot(nx, ny, nz, vx, vy, vz);
+  const float k = 2.0f * dn;
+  float rx = vx - nx * k, ry = vy - ny * k, rz = vz - nz * k;
+  inv = 1.0f / sqrtf(dot(rx, ry, rz, rx, ry, rz));
+  rx = rx * inv; ry = ry * inv; rz = rz * inv;
+  const float dl = fmaxf(fabsf(dot(nx, ny, nz, -C.ldir[0], -C.ldir[1], -C.ldir[2])), 0.0f);
+  const float sp = pow8(fmaxf(dot(rx, ry, rz, C.ldir[0], C.ldir[1], C.ldir[2]), 0.0f));
+  r = clamp01(C.amb[0] + dif[0] * dl + C.spe[0] * sp);
+  g = clamp01(C.amb[1] + dif[1] * dl + C.spe[1] * sp);
+  b = clamp01(C.amb[2] + dif[2] * dl + C.spe[2] * sp);
+}
+
+__global__ void cv_compose_kernel(const float4* __restrict__ hit_pos, const float4* __restrict__ hit_nrm,
+                                  const float4* __restrict__ cv_pos, const float4* __restrict__ cv_nrm, float4* __restrict__ rgba,
+                                  int w, int h, const CvConsts C) {
+  const uint64_t n = (uint64_t)w * h;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / w), x = (int)(i - (uint64_t)y * w);
+    const float4 hp = hit_pos[i];
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hp.w != 0.0f) {
+      const float4 nn = hit_nrm[i];
+      float cr, cg, cb;
+      cv_light(C, C.dif, hp.x, hp.y, hp.z, nn.x, nn.y, nn.z, cr, cg, cb);
+      float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+      const int nbx[4] = {x + 1, x - 1, x, x}, nby[4] = {y, y, y + 1, y - 1};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int qx = min(max(nbx[k], 0), w - 1), qy = min(max(nby[k], 0), h - 1);
+        const float4 q = hit_nrm[(size_t)qy * w + qx];
+        const float ax = fabsf(q.x - nn.x), ay = fabsf(q.y - nn.y), az = fabsf(q.z - nn.z);
+        if (k == 0) { sx = ax; sy = ay; sz = az; } else { sx = sx + ax; sy = sy + ay; sz = sz + az; }
+      }
+      const float curv = sqrtf(dot(sx, sy, sz, sx, sy, sz));
+      const float dx = hp.x - C.pick[0], dy = hp.y - C.pick[1], dz = hp.z - C.pick[2];
+      const float dist_w = sqrtf(dot(dx, dy, dz, dx, dy, dz)) * C.param[0];
+      const float blend = clamp01(fmaxf(curv * C.param[1], clamp01(dist_w)));
+      float fr = 0.0f, fg = 0.0f, fb = 0.0f, fa = 0.0f;
+      const float4 hp2 = cv_pos[i];
+      if (hp2.w != 0.0f) {
+        const float4 n2 = cv_nrm[i];
+        cv_light(C, C.dif2, hp2.x, hp2.y, hp2.z, n2.x, n2.y, n2.z, fr, fg, fb);
+        fa = 1.0f;
+      }
+      const float omb = 1.0f - blend;
+      const float r = clamp01(cr * blend + fr * omb), g = clamp01(cg * blend + fg * omb), b = clamp01(cb * blend + fb * omb);
+      const float a = clamp01(1.0f * blend + fa * omb);
+      const float border = 0.5f * (1.0f - clamp01(fabsf(dist_w - 1.0f) * C.param[2]));
+      o = make_float4(r - border, g - border, b - border, a);
+    }
+    rgba[i] = o;
+  }
+}
+
 // Stereo eye composition over a full-screen quad: pixel (x, y) carries the texture coordinate ((x+.5)/w, (y+.5)/h) and
 // the eye FBOs are GL_NEAREST / clamp (GLRenderer.cpp:688-713,1775-1785).  MODE = AbstrRenderer::EStereoMode.
 __device__ __forceinline__ float4 eye_fetch(const float4* img, uint32_t w, uint32_t h, float s, float t) {
@@ -130,6 +195,17 @@ void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rg
 
 void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s) {
   quantize_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
+}
+
+void launch_cv_compose(const float4* hit_pos, const float4* hit_nrm, const float4* cv_pos, const float4* cv_nrm, float4* rgba,
+                       uint32_t w, uint32_t h, const float amb[3], const float dif[3], const float dif2[3], const float spe[3],
+                       const float ldir[3], const float cv_param[3], const float pick[3], cudaStream_t s) {
+  CvConsts C;
+  for (int i = 0; i < 3; i++) {
+    C.amb[i] = amb[i]; C.dif[i] = dif[i]; C.dif2[i] = dif2[i]; C.spe[i] = spe[i]; C.ldir[i] = ldir[i];
+    C.param[i] = cv_param[i]; C.pick[i] = pick[i];
+  }
+  cv_compose_kernel<<<grid_for((uint64_t)w * h, 256), 256, 0, s>>>(hit_pos, hit_nrm, cv_pos, cv_nrm, rgba, (int)w, (int)h, C);
 }
 
 void launch_stereo_compose(int mode, const float4* left, const float4* right, float4* out, uint32_t w, uint32_t h,

@@ -67,6 +67,10 @@ void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rg
                         const float amb[3], const float dif[3], const float spe[3], const float ldir[3],
                         cudaStream_t s);
 void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s);
+// Compose-CV-FS.glsl over the four hit targets (GLRenderer::ComposeSurfaceImage, ClearView branch)
+void launch_cv_compose(const float4* hit_pos, const float4* hit_nrm, const float4* cv_pos, const float4* cv_nrm, float4* rgba,
+                       uint32_t w, uint32_t h, const float amb[3], const float dif[3], const float dif2[3], const float spe[3],
+                       const float ldir[3], const float cv_param[3], const float pick[3], cudaStream_t s);
 // GLRenderer::EndFrame's eye composition (Compose-{Anaglyphs,Scanline,SBS,AF}-FS.glsl); mode = tvk_stereo_mode
 void launch_stereo_compose(int mode, const float4* left, const float4* right, float4* out, uint32_t w, uint32_t h,
                            int alternating_frame_id, float split_coord, cudaStream_t s);
@@ -97,6 +101,8 @@ struct ClassicConsts {
   float4* out;
   float isoval, proj_param[2];      // isosurface mode: fIsoval (normalised), vProjParam = (f/(f-n), f*n/(n-f))
   float4* out_nrm;                  // isosurface mode: second iso-hit target (normal, brick number in the list)
+  float cv_isoval;                  // ClearView: GetNormalizedCVIsovalue
+  float4* out_cv; float4* out_cv_nrm;   // ClearView: m_pFBOCVHit's two targets (nullptr = ClearView off)
   const uint32_t* list_pos;         // isosurface mode: per brick of the LoD, its position in the frame's brick list (iTileID)
   float2* out_max;                  // HQ MIP only: (blended maximum, coverage) per pixel, the FBO Transfer-MIP reads
   unsigned long long* counters;

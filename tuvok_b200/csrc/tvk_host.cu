@@ -1846,6 +1846,11 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
   c.list_pos = ctx->classic_table_d + n_cells;
   // fIsoval = GetNormalizedIsovalue (AbstrRenderer.cpp:412-424); vProjParam (GLRaycaster.cpp:213-217) with near / far
   // recovered from the projection matrix
+  const bool clearview = iso && ctx->cv.on;   // ClearView belongs to the isosurface mode (AbstrRenderer::SetCV)
+  if (clearview) {
+    c.out_cv = ctx->buf[1]; c.out_cv_nrm = ctx->buf[2];   // m_pFBOCVHit (the GridLeaper resume buffers are free: blank)
+    c.cv_isoval = ctx->dtype == TVK_U8 ? (float)(ctx->cv.iso / 256.0) : ctx->dtype == TVK_U16 ? (float)(ctx->cv.iso / 65536.0) : (float)ctx->cv.iso;
+  }
   c.isoval = ctx->dtype == TVK_U8 ? (float)(p.isovalue / 256.0) : ctx->dtype == TVK_U16 ? (float)(p.isovalue / 65536.0) : (float)p.isovalue;
   {
     const double zn = pr[14] / (pr[10] - 1.0), zf = pr[14] / (pr[10] + 1.0);
@@ -1863,9 +1868,22 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
       d[i] = p.diffuse[i] * p.diffuse[3] * p.iso_color[i];
       sp[i] = p.specular[i] * p.specular[3];
     }
-    launch_iso_compose(ctx->buf[0], ctx->buf[5], ctx->buf[6], p.width, p.height, a, d, sp, p.light_dir, s);
+    if (clearview) {   // m_pProgramCVCompose (GLRenderer.cpp:2777-2795)
+      float d2[3], prm[3] = {ctx->cv.size, ctx->cv.context, ctx->cv.border}, pick[3];
+      for (int i = 0; i < 3; i++) {
+        d2[i] = p.diffuse[i] * p.diffuse[3] * ctx->cv.color[i];
+        const float* m = p.model_view;   // m_vCVPos * modelView (FLOATVECTOR4 * FLOATMATRIX4, Vectors.h:434-439)
+        const float* q = ctx->cv.pos;
+        pick[i] = q[0] * m[i] + q[1] * m[4 + i] + q[2] * m[8 + i] + q[3] * m[12 + i];
+      }
+      launch_cv_compose(ctx->buf[0], ctx->buf[5], ctx->buf[1], ctx->buf[2], ctx->buf[6], p.width, p.height, a, d, d2, sp,
+                        p.light_dir, prm, pick, s);
+    } else {
+      launch_iso_compose(ctx->buf[0], ctx->buf[5], ctx->buf[6], p.width, p.height, a, d, sp, p.light_dir, s);
+    }
     CU(cudaGetLastError());
   }
+  ctx->cv_frame = clearview;
   CU(cudaEventRecord(ctx->ev[2], s));
   if (ctx->counters_on) CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));   // the host tables above must outlive their copies
@@ -1962,6 +1980,27 @@ int tvk_stereo_compose(tvk_ctx* ctx, int mode, int eye_swap, int alternating_fra
   launch_stereo_compose(mode, l, r, ctx->buf[7], ctx->img_w, ctx->img_h, alternating_frame_id, split_coord, ctx->stream);
   CU(cudaGetLastError());
   ctx->result_buf = ctx->buf[7];
+  return TVK_OK;
+}
+
+int tvk_set_clearview(tvk_ctx* ctx, int enable, double cv_isovalue, const float color[3], float size, float context_scale,
+                      float border_scale, const float focus_pos[4]) {
+  if (!ctx) return TVK_ERR_INVALID;
+  ctx->cv.on = enable != 0;
+  ctx->cv.iso = cv_isovalue;
+  if (color) for (int i = 0; i < 3; i++) ctx->cv.color[i] = color[i];
+  ctx->cv.size = size; ctx->cv.context = context_scale; ctx->cv.border = border_scale;
+  if (focus_pos) for (int i = 0; i < 4; i++) ctx->cv.pos[i] = focus_pos[i];
+  return TVK_OK;
+}
+
+int tvk_read_cv_buffers(tvk_ctx* ctx, float* cv_pos, float* cv_normal) {
+  if (!ctx || !ctx->img_w || !ctx->cv_frame) return fail(ctx, TVK_ERR_INVALID, "no ClearView frame");
+  cudaSetDevice(ctx->cfg.device);
+  const size_t bytes = (size_t)ctx->img_w * ctx->img_h * 16;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (cv_pos) CU(cudaMemcpy(cv_pos, ctx->buf[1], bytes, cudaMemcpyDeviceToHost));
+  if (cv_normal) CU(cudaMemcpy(cv_normal, ctx->buf[2], bytes, cudaMemcpyDeviceToHost));
   return TVK_OK;
 }
 

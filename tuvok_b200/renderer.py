@@ -488,6 +488,46 @@ class CudaGridLeaper:
         self._converged = True
         return st
 
+    # ------------------------------------------------------------------ ClearView (AbstrRenderer.cpp:1247-1360)
+    def _push_cv(self):
+        cv = self._cv = getattr(self, "_cv", dict(on=False, iso=0.8, color=(1.0, 0.0, 0.0), size=5.5, context=1.0, border=60.0,
+                                                  pos=(0.0, 0.0, 0.5, 1.0)))
+        self._ck(self._lib.tvk_set_clearview(self._h, int(cv["on"]), float(cv["iso"]), L.f32x3(*cv["color"]), cv["size"],
+                                             cv["context"], cv["border"], L.f32x4(*cv["pos"])))
+
+    def _set_cv(self, **kw):
+        self._push_cv()
+        self._cv.update(kw)
+        self._push_cv()
+
+    def SetCV(self, on):
+        self._set_cv(on=bool(on))
+
+    def SetCVIsoValue(self, v):
+        self._set_cv(iso=float(v))
+
+    def SetCVColor(self, rgb):
+        self._set_cv(color=tuple(float(c) for c in rgb))
+
+    def SetCVSize(self, v):
+        self._set_cv(size=float(v))
+
+    def SetCVContextScale(self, v):
+        self._set_cv(context=float(v))
+
+    def SetCVBorderScale(self, v):
+        self._set_cv(border=float(v))
+
+    def SetCVFocusPos(self, pos4):
+        self._set_cv(pos=tuple(float(c) for c in pos4))
+
+    def ReadCVBuffers(self):
+        """(cv_pos, cv_normal) of the last ClearView frame, each (h, w, 4) float32 (m_pFBOCVHit)."""
+        h, w = self.params.height, self.params.width
+        a, b = np.empty((h, w, 4), np.float32), np.empty((h, w, 4), np.float32)
+        self._ck(self._lib.tvk_read_cv_buffers(self._h, _ptr(a), _ptr(b)))
+        return a, b
+
     def SetMIPRotationAngle(self, angle_deg):
         """AbstrRenderer::SetMIPRotationAngle (AbstrRenderer.h:545-547)."""
         self._mip_angle = float(angle_deg)
