@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--path", default="gridleaper", choices=["gridleaper", "classic", "mip"],
                     help="gridleaper: GLGridLeaper page-table traversal (default); classic: per-brick GLRaycaster path; "
                          "mip: HQ MIP frame of a 2D window (GLRaycaster-MIP-Rot-FS, rotating about Y)")
-    ap.add_argument("--split", default="auto", choices=["auto", "screen", "depth", "depth2", "octant"],
+    ap.add_argument("--split", default="auto", choices=["auto", "screen", "depth", "depth2", "octant", "depthw", "octantw"],
                     help="sort-last partition policy (tuvok_b200/sortlast.py); auto = screen for N <= 4, octant for N = 8 "
                          "(measured best, DESIGN.md section 5)")
     ap.add_argument("--vol", type=int, default=0, help="override the cubic volume size (debugging)")
@@ -289,6 +289,11 @@ def run_tvk(args, rank, world, local_rank):
     flayout = [f - f * np.finfo(np.float32).eps if float(int(f)) == float(f) else f for f in flayout]
     split = args.split if args.split != "auto" else ("octant" if world >= 8 else "screen")
     sl = sortlast.SortLastRenderer(r, rank, world, finest, flayout, ext, policy=split) if world > 1 else None
+    if sl is not None and split.endswith("w"):
+        # balanced cuts: weights = non-empty finest-level bricks; the page table's emptiness flags exist after one frame
+        r.SetRotation(workloads.orbit_rotation(0, 36))
+        r.Paint()
+        sl.set_weights()
     n_views = 36
     mip = args.path == "mip"
     classic = args.path in ("classic", "mip")          # the per-brick paths: one converged frame per call

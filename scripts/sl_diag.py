@@ -20,6 +20,9 @@ t1, t2 = workloads.transfer_functions(w); r.Set1DTrans(t1); r.Set2DTrans(t2); r.
 r.Resize(w["width"], w["height"]); r.CreateVolumePool()
 fl = [np.float32(v) / np.float32(inner) for v in w["size"]]; fl = [f - f * np.finfo(np.float32).eps for f in fl]
 sl = sortlast.SortLastRenderer(r, rank, world, finest, fl, (1.0, 1.0, 1.0), view_dependent=bool(vd), policy=os.environ.get("SPLIT", "screen"))
+if os.environ.get("SPLIT", "screen").endswith("w"):
+    r.SetRotation(workloads.orbit_rotation(0)); r.Paint(); sl.set_weights()
+VIEWS = int(os.environ.get("VIEWS", "36"))
 rows = []
 for i in range(36):
     r.SetRotation(workloads.orbit_rotation(i)); sl.update_partition(); r.PaintUntilConverged()

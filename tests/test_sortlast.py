@@ -182,3 +182,32 @@ def test_binary_swap_over_gloo_world_size_2():
     assert sorted((lo, hi) for _, lo, hi, _ in got) == sorted(sortlast.final_ranges(world, n_pix))
     for rank, lo, hi, px in got:
         np.testing.assert_array_equal(px, expect[rank][lo:hi])
+
+
+def test_weighted_cuts_balance_the_visible_bricks():
+    """Policies "depthw" / "octantw": every cut halves the weight (non-empty bricks) of its block, blocks stay a disjoint
+    cover of the brick grid, and uniform weights reproduce the unweighted cuts."""
+    from tuvok_b200 import sortlast
+    finest = (16, 12, 10)
+    rng = np.random.default_rng(5)
+    x, y, z = np.meshgrid(np.arange(16), np.arange(12), np.arange(10), indexing="ij")
+    w = (((x - 11) ** 2 + (y - 6) ** 2 + (z - 5) ** 2) < 16).astype(np.float64)      # an off-centre ball of visible bricks
+    for n in (2, 4, 8):
+        for axes in (None, [0] * 3, [2, 2, 0]):
+            boxes, splits = sortlast.shard_boxes(finest, n, axes, weights=w)
+            cover = np.zeros(finest, int)
+            sums = []
+            for lo, hi in boxes:
+                cover[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] += 1
+                sums.append(w[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].sum())
+                assert all(hi[i] > lo[i] for i in range(3))
+            assert (cover == 1).all()
+            assert len(splits) == int(np.log2(n))
+            plain, _ = sortlast.shard_boxes(finest, n, axes)
+            psums = [w[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]].sum() for lo, hi in plain]
+            assert max(sums) <= max(psums)                          # never worse balanced than the midpoint cuts
+            if axes == [0] * 3:
+                assert max(sums) - min(sums) <= w.sum(axis=(1, 2)).max() + 1e-9    # within one brick layer of even
+    assert sortlast.shard_boxes(finest, 8, None, weights=np.ones(finest)) == sortlast.shard_boxes(finest, 8, None)
+    assert sortlast.shard_boxes(finest, 4, [1, 1], weights=np.zeros(finest)) == sortlast.shard_boxes(finest, 4, [1, 1])
+    assert sortlast.split_axes((0.1, 0.2, -0.9), 4, "depthw") == [2, 2] and sortlast.split_axes((1, 0, 0), 8, "octantw") is None

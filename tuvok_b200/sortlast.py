@@ -29,21 +29,26 @@ def split_axes(view_dir, n_ranks, policy="screen"):
     policy "depth": every cut along the axis most PARALLEL to the view: the blocks are slabs behind each other, each
     rank sees all pixels but only 1/G of every ray, which divides the critical path by G.  Costs the samples that a
     single GPU would have skipped behind an early-terminated front slab.
-    policy "octant": longest axis of the block at every level (view independent)."""
+    policy "octant": longest axis of the block at every level (view independent).
+    policy "depthw" / "octantw": as "depth" / "octant", but every cut is placed at the weighted median of the block
+    (SortLastRenderer.set_weights: non-empty finest-level bricks), so the slabs hold equal amounts of visible data
+    instead of equal numbers of bricks."""
     k = int(round(math.log2(n_ranks)))
-    if policy == "octant":
+    if policy in ("octant", "octantw"):
         return None
     order = sorted(range(3), key=lambda i: (abs(float(view_dir[i])), i))
-    if policy == "depth":
+    if policy in ("depth", "depthw"):
         return [order[2]] * k
     if policy == "depth2":      # two cuts in depth, the third across the screen
         return [order[2], order[2], order[0]][:k]
     return [order[0], order[1], order[0]][:k]
 
 
-def shard_boxes(finest_layout, n_ranks, axes=None):
+def shard_boxes(finest_layout, n_ranks, axes=None, weights=None):
     """Recursive bisection of the finest brick grid into n_ranks (power of two) blocks.  axes[level] = axis cut at
     that level (split_axes); None or an axis with fewer than 2 bricks left: the longest axis of the block.
+    weights: optional array [x, y, z] over the finest brick grid; a cut then halves the block's weight (weighted
+    median along the cut axis) instead of its brick count.
     Returns (boxes, splits): boxes[g] = (lo[3], hi[3]) in brick units; splits = list, one entry per
     bisection LEVEL l (0 = first cut) of dict{prefix -> (axis, cut_brick)} keyed by the rank's top-l bits."""
     k = int(round(math.log2(n_ranks)))
@@ -61,6 +66,14 @@ def shard_boxes(finest_layout, n_ranks, axes=None):
             if ext[axis] < 2:
                 raise ValueError("volume has too few bricks to shard %d ways" % n_ranks)
             cut = lo[axis] + (ext[axis] + 1) // 2
+            if weights is not None:
+                blk = np.asarray(weights, np.float64)[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+                layers = blk.sum(axis=tuple(a for a in range(3) if a != axis))
+                total = float(layers.sum())
+                if total > 0.0:
+                    cum = np.cumsum(layers)[:-1]                       # weight below a cut after layer i
+                    d = np.abs(cum - 0.5 * total)
+                    cut = lo[axis] + 1 + int(len(d) - 1 - np.argmin(d[::-1]))   # ties: the upper cut, like (ext + 1) // 2
             lvl[prefix] = (axis, cut)
             hi0 = list(hi); hi0[axis] = cut
             lo1 = list(lo); lo1[axis] = cut
@@ -163,9 +176,10 @@ class SortLastRenderer:
         self.r, self.rank, self.n = renderer, rank, n_ranks
         self.torch, self.dist = torch, dist
         self.finest, self.flayout, self.extent = tuple(finest_layout), tuple(float_layout), tuple(extent)
-        self.view_dependent = view_dependent and policy != "octant"
+        self.view_dependent = view_dependent and policy not in ("octant", "octantw")
         self.policy = policy
         self._axes = None
+        self.weights = None
         self._partition(None)
         self._img = None
         self._recv = None
@@ -179,9 +193,23 @@ class SortLastRenderer:
     def _partition(self, axes):
         """(Re)cut the brick grid; bricks of the new block are paged in by the renderer's normal miss path."""
         self._axes = axes
-        self.boxes, self.splits = shard_boxes(self.finest, self.n, axes)
+        self.boxes, self.splits = shard_boxes(self.finest, self.n, axes, self.weights if self.policy.endswith("w") else None)
         cmin, cmax = box_to_clip(self.boxes[self.rank], self.finest, self.flayout)
         self.r.SetShardBox(cmin, cmax)
+
+    def set_weights(self, weights=None):
+        """Per-brick weights of the finest level for the balanced policies ("depthw", "octantw").  Default: 1 for every
+        brick the page table does not flag empty (the flags come from brick min/max against the transfer function or
+        isovalue -- identical on every rank), 0 otherwise.  Call after the first frame (visibility is computed there)."""
+        if weights is None:
+            from . import _lib as L
+            n = int(self.finest[0]) * int(self.finest[1]) * int(self.finest[2])
+            off = int(self.r.info().lod_offset[0])
+            meta = self.r.page_table()[off:off + n]                      # finest level, x fastest
+            nonempty = (meta != L.BI_EMPTY) & (meta != L.BI_CHILD_EMPTY)
+            weights = nonempty.reshape(self.finest[2], self.finest[1], self.finest[0]).transpose(2, 1, 0).astype(np.float64)
+        self.weights = np.asarray(weights, np.float64)
+        self._partition(self._axes)
 
     def update_partition(self):
         """Re-cut the brick grid for the renderer's current view if the view-dependent axes changed; returns the
