@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--path", default="gridleaper", choices=["gridleaper", "classic", "mip"],
                     help="gridleaper: GLGridLeaper page-table traversal (default); classic: per-brick GLRaycaster path; "
                          "mip: HQ MIP frame of a 2D window (GLRaycaster-MIP-Rot-FS, rotating about Y)")
-    ap.add_argument("--split", default="auto", choices=["auto", "screen", "depth", "depth2", "octant", "depthw", "octantw"],
+    ap.add_argument("--split", default="auto", choices=["auto", "screen", "depth", "depth2", "octant", "depthw", "octantw", "pipeline"],
                     help="sort-last partition policy (tuvok_b200/sortlast.py); auto = screen for N <= 4, octant for N = 8 "
                          "(measured best, DESIGN.md section 5)")
     ap.add_argument("--vol", type=int, default=0, help="override the cubic volume size (debugging)")
@@ -288,7 +288,14 @@ def run_tvk(args, rank, world, local_rank):
     flayout = [np.float32(v) / np.float32(inner) for v in w["size"]]
     flayout = [f - f * np.finfo(np.float32).eps if float(int(f)) == float(f) else f for f in flayout]
     split = args.split if args.split != "auto" else ("octant" if world >= 8 else "screen")
-    sl = sortlast.SortLastRenderer(r, rank, world, finest, flayout, ext, policy=split) if world > 1 else None
+    pipe = None
+    if world > 1 and split == "pipeline":
+        # depth pipeline: rank s = stage s, slabs balanced by their non-empty bricks
+        pipe = sortlast.DepthPipeline(r, rank, world, finest, flayout, ext, align=1)
+        r.SetRotation(workloads.orbit_rotation(0, 36))
+        r.Paint()                      # the page table's emptiness flags exist after one frame
+        pipe.set_weights()
+    sl = sortlast.SortLastRenderer(r, rank, world, finest, flayout, ext, policy=split) if world > 1 and pipe is None else None
     if sl is not None and split.endswith("w"):
         # balanced cuts: weights = non-empty finest-level bricks; the page table's emptiness flags exist after one frame
         r.SetRotation(workloads.orbit_rotation(0, 36))
@@ -307,12 +314,16 @@ def run_tvk(args, rank, world, local_rank):
         r.SetRotation(workloads.orbit_rotation(i % n_views, n_views))
         if mip:
             r.SetMIPRotationAngle(10.0 * (i % n_views))    # GLRenderer::SetMIPRotationAngle: the 2D window's MIP turntable
+        if pipe is not None:
+            pipe.view_id = i % n_views                     # per-view measured slab cuts
         if sl is not None:
             sl.update_partition()     # view-dependent brick blocks (side by side on screen)
 
     def frame(i):
         """one step on this rank; returns the stats of the (single) subframe"""
         set_view(i)
+        if pipe is not None:
+            return pipe.render_frame()[0]
         if sl is None:
             return paint_per_brick() if classic else r.Paint()
         lo, hi, img, st = sl.render()
@@ -323,6 +334,33 @@ def run_tvk(args, rank, world, local_rank):
     paged = 0
     for i in range(n_views):
         set_view(i)
+        if pipe is not None:           # every stage pages its slab in; all ranks run the same number of frames
+            for rnd in range(6):       # load feedback: measured stage times -> new cuts (DepthPipeline.rebalance)
+                for _ in range(16):
+                    st = pipe.render_frame()[0]
+                    paged += st.bricks_paged
+                    ok = torch.tensor([1.0 if st.converged else 0.0], device="cuda")
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                    if float(ok.item()) > 0.5:
+                        break
+                else:
+                    raise RuntimeError("view %d did not converge on every stage" % i)
+                if rnd == 5:
+                    break
+                # feedback signal: the stage's sample count (default; measured at N = 2: 256 -> 276 fps) or, with
+                # TVK_PIPE_FEEDBACK=time, its kernel time -- a launch is bound by its throughput in the front slabs (most
+                # samples: early termination) but by its longest rays in the back slabs (experimental)
+                if os.environ.get("TVK_PIPE_FEEDBACK", "samples") == "time":
+                    cost = min(pipe.render_frame()[0].ms_raycast for _ in range(3))
+                else:
+                    r.enable_counters(True)
+                    cost = float(pipe.render_frame()[0].samples)
+                    r.enable_counters(False)
+                cnt = torch.zeros(world, dtype=torch.float64, device="cuda")
+                cnt[rank] = float(cost)
+                dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+                pipe.rebalance([float(v) for v in cnt.cpu()])
+            continue
         st = paint_per_brick() if classic else r.PaintUntilConverged()
         paged += st.bricks_paged
         if not st.converged:
@@ -336,7 +374,7 @@ def run_tvk(args, rank, world, local_rank):
     alive_it, warp_it = 0, 0
     for i in range(n_views):
         set_view(i)
-        st = paint_per_brick() if classic else r.Paint()
+        st = pipe.render_frame()[0] if pipe is not None else (paint_per_brick() if classic else r.Paint())
         samples.append(st.samples); rays.append(st.rays); touched.append(st.bricks_touched); visits.append(st.brick_visits)
         alive_it += st.alive_lane_iters; warp_it += st.warp_iters
     r.enable_counters(False)
@@ -365,18 +403,27 @@ def run_tvk(args, rank, world, local_rank):
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
-    if not_conv:
+    if not_conv and pipe is None:
         raise RuntimeError("%d timed frames were not converged" % not_conv)
 
     # ---- e2e: public API with host buffers (params in, RGBA8 image out to host) ----------------
     pinned = [r.host_alloc((w["height"], w["width"], 4)) for _ in range(2)] if sl is None else None
+    last_stage = pipe is not None and rank == world - 1
     pending = []
     checksum = 0
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         set_view(args.warmup + i)
-        if sl is None:
+        if pipe is not None:
+            # the finished frame leaves the LAST stage: PBO-style double-buffered read-back there, every frame
+            pipe.render_frame()
+            if last_stage:
+                r.ReadRGBA8Async(pinned[i % 2])
+                r.WaitRead(pending_allowed=1)
+                if i > 0:
+                    checksum += int(pinned[(i - 1) % 2][w["height"] // 2, w["width"] // 2, 3])
+        elif sl is None:
             # PBO-style double-buffered read-back: frame i is copied to pinned host memory while frame i+1 renders;
             # every frame's RGBA8 image is in host memory (and touched) before the timed region ends
             if classic:
@@ -401,18 +448,18 @@ def run_tvk(args, rank, world, local_rank):
     for img_h, ev in pending:
         ev.synchronize()
         checksum += int(img_h[(w["height"] // 2) * w["width"] + w["width"] // 2, 3])
-    if sl is None:
+    if sl is None and (pipe is None or last_stage):
         r.WaitRead(0)
         checksum += int(pinned[(args.steps - 1) % 2][w["height"] // 2, w["width"] // 2, 3])
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    times = torch.tensor([ms_total, ms_ray, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    times = torch.tensor([ms_total, ms_ray, e2e_s * 1e3, float(not_conv)], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(np.sum(samples)), float(np.sum(touched))], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_total, ms_ray, e2e_ms = (float(v) for v in times.cpu())
+    ms_total, ms_ray, e2e_ms, not_conv_max = (float(v) for v in times.cpu())
     samples_per_orbit, touched_per_orbit = (float(v) for v in tot.cpu())
 
     if rank == 0:
@@ -449,12 +496,15 @@ def run_tvk(args, rank, world, local_rank):
             "data": "synthetic", "gsamples_per_s": gsps,
             "config": {"workload": w["label"], "volume": "V_noise seed 0x5EED" if w["kind"] == 1 else "V_sph",
                        "camera": "36-step orbit (Ry 10deg steps, Rx 20deg), eye (0,0,1.6) fov 50",
-                       "parallelism": "sort-last x%d (binary swap, %s partition)" % (world, split) if world > 1 else "single GPU",
+                       "parallelism": ("depth pipeline x%d (rank s = slab s from the eye, hand-over of resume position + colour over NCCL, "
+                                       "slabs balanced by non-empty bricks; frames in flight = %d)" % (world, world)) if pipe is not None else
+                                      "sort-last x%d (binary swap, %s partition)" % (world, split) if world > 1 else "single GPU",
                        "path": ("HQ MIP frame (per-brick GLRaycaster-MIP-Rot-FS + Transfer-MIP, PlanHQMIPFrame LoD)" if mip else
                                 "classic per-brick GLRaycaster") if classic else "GridLeaper page-table traversal",
                        "l2_policy": "inputs larger than L2 (pool %.1f GB, %.0f MB of bricks touched per frame)" %
                                     (info.pool_capacity[0] * info.pool_capacity[1] * info.pool_capacity[2] * slot_bytes / 1e9,
                                      step_touched / k * slot_bytes / 1e6),
+                       "timed_frames_not_converged": int(not_conv_max),
                        "bricks_paged_in_setup": paged, "setup_s": round(setup_s, 2),
                        "samples_per_frame": step_samples / k, "rays_per_frame": float(np.mean(rays)),
                        "bricks_touched_per_frame": step_touched / k,
@@ -468,7 +518,7 @@ def run_tvk(args, rank, world, local_rank):
                                       / (ray_ms * 1e-3) / 1e9 / world},
             "e2e": {"value": k / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(C_sizeof_params()),
                     "d2h_bytes_per_step": n_pixels * 4 + 8},
-            "gpu_launches": k * (2 if sl is None else 2 + int(np.log2(world))),
+            "gpu_launches": k * (2 * world if pipe is not None else 2 if sl is None else 2 + int(np.log2(world))),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -336,6 +336,20 @@ int tvk_stereo_keep_eye(tvk_ctx* ctx, int eye);
  * becomes the image tvk_read_rgba8 / tvk_read_rgba32f / tvk_get_device_image return until the next frame. */
 int tvk_stereo_compose(tvk_ctx* ctx, int mode, int eye_swap, int alternating_frame_id, float split_coord);
 
+/* ---- depth pipeline (new; SURVEY 8e, alternative to binary swap) ------------------------- */
+/* One STAGE of a depth-pipelined frame.  The volume is cut into slabs behind each other along the view axis
+ * (clip_min / clip_max of the render params = this rank's slab); stage s marches every ray through slab s only, starting
+ * from the state the stage in front handed over -- resume position + accumulated colour, the same two images a
+ * resumed GLGridLeaper subframe starts from (GLGridLeaper-blend.glsl:130-137) -- and leaves the state for the next
+ * stage: resume_pos.w = 1000 marks a finished ray (early termination or volume exit), anything else the depth at which
+ * the next slab takes over.  in_resume_pos / in_resume_color: width*height float4 DEVICE images, NULL for the first
+ * stage.  The last stage's image is the frame.  Early ray termination works across ranks as on one GPU, and with
+ * consecutive frames in flight every rank traces 1/N of every ray.  1D / 2D transfer-function modes. */
+int tvk_render_stage(tvk_ctx* ctx, const void* in_resume_pos, const void* in_resume_color, tvk_frame_stats* stats);
+/* device images of the last stage: accumulated colour so far (= the frame after the last stage), and the two
+ * hand-over images for the next stage */
+int tvk_get_stage_outputs(tvk_ctx* ctx, void** image, void** resume_color, void** resume_pos);
+
 /* ---- sort-last compositing (new) --------------------------------------- */
 /* out = front + (1-front.a)*back on n_pixels premultiplied RGBA32F device pixels
  * (Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153); a front pixel with alpha > 0.99

@@ -133,6 +133,8 @@ SIGNATURES = {
     "tvk_stereo_compose": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_float]),
     "tvk_set_clearview": (C.c_int, [P, C.c_int, C.c_double, f32x3, C.c_float, C.c_float, C.c_float, f32x4]),
     "tvk_read_cv_buffers": (C.c_int, [P, P, P]),
+    "tvk_render_stage": (C.c_int, [P, P, P, C.POINTER(FrameStats)]),
+    "tvk_get_stage_outputs": (C.c_int, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
     "tvk_render_mip": (C.c_int, [P, C.c_int, C.POINTER(FrameStats)]),
     "tvk_read_mip_max": (C.c_int, [P, P]),
     "tvk_get_classic_brick_list": (C.c_int, [P, C.POINTER(C.c_uint32), P, C.c_uint32, C.POINTER(C.c_uint32)]),

@@ -313,7 +313,7 @@ __device__ __forceinline__ float opacity_correct(const RayConsts& P, float a) {
 
 // analytic ray/box entry + exit at the pixel centre (what the rasterised bbox front/back faces and
 // the near-plane quad deliver per fragment)
-__device__ __forceinline__ bool ray_setup(const RayConsts& P, uint32_t px, uint32_t py, f4& entry, f4& exit_) {
+__device__ __forceinline__ bool ray_setup(const RayConsts& P, uint32_t px, uint32_t py, f4& entry, f4& exit_, bool shard_test = true) {
   float nx = ((float)px + 0.5f) / (float)P.width * 2.0f - 1.0f;
   float ny = ((float)py + 0.5f) / (float)P.height * 2.0f - 1.0f;
   f4 nr = xform4(P.inv_proj, nx, ny, -1.0f, 1.0f);
@@ -335,7 +335,7 @@ __device__ __forceinline__ bool ray_setup(const RayConsts& P, uint32_t px, uint3
   }
   const float s0 = fmaxf(s_in, 1.0f);
   if (!(s_out > s0)) return false;
-  if (P.shard) {
+  if (P.shard && shard_test) {
     // sort-last: the ray keeps its whole-volume entry/exit (its sample positions are those of the single-GPU
     // ray); a pixel whose ray never meets this rank's brick block is simply not shaded
     float a_in = -INFINITY, a_out = INFINITY;
@@ -446,7 +446,12 @@ __device__ __forceinline__ void unpark(ChainSt& c, float (*m)[kThreads], int tid
 }
 
 // MODE: 0 = 1D TF, 1 = 2D TF, 2 = isosurface
-template <typename T, int MODE, bool LIT, bool FAST, int BS, bool COUNT>
+// PIPE (DVR modes): this launch is one STAGE of the depth pipeline: the rank's block is a slab
+// of the volume; a ray comes in with the colour the stages in front of it accumulated (start colour / resume position,
+// exactly the inputs of a resumed GridLeaper subframe), is marched through the slab, and leaves with its resume
+// position at the slab's far side -- or finished (w = 1000) if it terminated early or left the volume.  Early ray
+// termination therefore works across ranks as on one GPU.
+template <typename T, int MODE, bool LIT, bool FAST, int BS, bool COUNT, bool PIPE = false>
 __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) raycast_kernel(const __grid_constant__ RayConsts P) {
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   // CTAs are dispatched in blockIdx order (x fastest).  The rays through the middle of the volume are the
@@ -465,9 +470,9 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
 
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   f4 entry4, exit4;
-  const bool covered = ray_setup(P, px, py, entry4, exit4);
+  const bool covered = ray_setup(P, px, py, entry4, exit4, !PIPE);   // a stage takes every ray that meets the VOLUME
   if (!covered) {   // render targets are cleared where no back face is rasterised (GLGridLeaper.cpp:837)
-    P.out0[pix] = zero4; P.out1[pix] = zero4; P.out2[pix] = zero4;
+    P.out0[pix] = zero4; P.out1[pix] = zero4; P.out2[pix] = PIPE ? make_float4(0.f, 0.f, 0.f, 1000.0f) : zero4;
     if (ISO) P.out3[pix] = zero4;
     return;
   }
@@ -478,6 +483,8 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
   f4& resume_pos = c.resume_pos;
   f4 hit_pos = from4(zero4), hit_nrm = from4(zero4), resume_nrm = from4(zero4);
   bool done = false;
+  bool handoff = false;            // PIPE: the ray left this stage's slab alive
+  f4 hand_pos = from4(zero4);
   if (P.first_pass) {
     resume_pos = entry4;
     acc = from4(zero4);
@@ -559,7 +566,14 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
             const bool gone = (c.dir.x > 0.0f && c.cur.x >= P.sh_hi[0]) || (c.dir.x < 0.0f && c.cur.x <= P.sh_lo[0]) ||
                               (c.dir.y > 0.0f && c.cur.y >= P.sh_hi[1]) || (c.dir.y < 0.0f && c.cur.y <= P.sh_lo[1]) ||
                               (c.dir.z > 0.0f && c.cur.z >= P.sh_hi[2]) || (c.dir.z < 0.0f && c.cur.z <= P.sh_lo[2]);
-            if (gone) { chain = false; break; }
+            if (gone) {
+              if (PIPE) {   // where the next stage picks the ray up
+                handoff = true;
+                hand_pos.x = c.cur.x; hand_pos.y = c.cur.y; hand_pos.z = c.cur.z;
+                hand_pos.w = c.entry_depth * (1.0f - c.t) + c.exit_depth * c.t;
+              }
+              chain = false; break;
+            }
           }
           const float cur_depth = c.entry_depth * (1.0f - c.t) + c.exit_depth * c.t;
           uint32_t lod = compute_lod(P, cur_depth);
@@ -710,6 +724,20 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
               const f3 mq = mul3(sub3(pc, b_trans), b_inv);
               mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
                      mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
+              if (PIPE && !mine) {
+                // a brick of a coarser LoD straddles the slab's far side: the ray is handed on AT the side, not
+                // behind the brick, so the next stage takes the brick's remaining samples
+                const bool gone = (c.dir.x > 0.0f && mq.x >= P.sh_hi[0]) || (c.dir.x < 0.0f && mq.x < P.sh_lo[0]) ||
+                                  (c.dir.y > 0.0f && mq.y >= P.sh_hi[1]) || (c.dir.y < 0.0f && mq.y < P.sh_lo[1]) ||
+                                  (c.dir.z > 0.0f && mq.z >= P.sh_hi[2]) || (c.dir.z < 0.0f && mq.z < P.sh_lo[2]);
+                if (gone) {
+                  const float tq = len3(sub3(mq, c.entry)) / c.ray_len;
+                  handoff = true;
+                  hand_pos.x = mq.x; hand_pos.y = mq.y; hand_pos.z = mq.z;
+                  hand_pos.w = c.entry_depth * (1.0f - tq) + c.exit_depth * tq;
+                  terminated = true;   // leaves the loop; TerminateRay sees alpha <= 0.99 and hands the ray on
+                }
+              }
             }
             if (mine) {
               if (COUNT) n_samples++;
@@ -769,7 +797,11 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
     if (kPark) unpark_result(c, park, tid);
     // TerminateRay
     if (!ISO) {
-      if (c.optimal) { resume_pos.w = 1000.0f; resume_col = acc; }
+      if (c.optimal) {
+        // ray_live is false only after early termination; a ray that ran out of bricks in this slab is handed on
+        if (PIPE && handoff && !(acc.w > 0.99f)) { resume_pos = hand_pos; resume_col = acc; }
+        else { resume_pos.w = 1000.0f; resume_col = acc; }
+      }
     } else {
       if (c.optimal) resume_pos.w = hit_pos.w == 0.0f ? 1000.0f : 499.0f + hit_pos.w;
       resume_nrm = hit_nrm;
@@ -796,9 +828,16 @@ void launch_t(const RayConsts& rc, cudaStream_t s) {
   bool fast = !rc.nearest;
   for (int i = 0; i < 3; i++) fast = fast && rc.total[i] >= 4 && rc.ghost[i] >= 2;
   const bool b36 = rc.total[0] == 36 && rc.total[1] == 36 && rc.total[2] == 36;
-  if (rc.count) {
+  if (rc.count && rc.pipeline && MODE != 2) {
+    if (fast) raycast_kernel<T, MODE, LIT, true, 0, true, true><<<grid, block, 0, s>>>(rc);
+    else raycast_kernel<T, MODE, LIT, false, 0, true, true><<<grid, block, 0, s>>>(rc);
+  } else if (rc.count) {
     if (fast) raycast_kernel<T, MODE, LIT, true, 0, true><<<grid, block, 0, s>>>(rc);
     else raycast_kernel<T, MODE, LIT, false, 0, true><<<grid, block, 0, s>>>(rc);
+  } else if (rc.pipeline && MODE != 2) {   // depth-pipeline stage (DVR modes)
+    if (fast && b36) raycast_kernel<T, MODE, LIT, true, 36, false, true><<<grid, block, 0, s>>>(rc);
+    else if (fast) raycast_kernel<T, MODE, LIT, true, 0, false, true><<<grid, block, 0, s>>>(rc);
+    else raycast_kernel<T, MODE, LIT, false, 0, false, true><<<grid, block, 0, s>>>(rc);
   } else if (fast && b36) raycast_kernel<T, MODE, LIT, true, 36, false><<<grid, block, 0, s>>>(rc);
   else if (fast) raycast_kernel<T, MODE, LIT, true, 0, false><<<grid, block, 0, s>>>(rc);
   else raycast_kernel<T, MODE, LIT, false, 0, false><<<grid, block, 0, s>>>(rc);

@@ -44,6 +44,7 @@ struct RayConsts {
   float sh_lo[3], sh_hi[3];         // shard box with faces on the volume border pushed to -/+inf
   int32_t nearest;
   int32_t first_pass;   // region is blank: ray entry computed, start colour = 0
+  int32_t pipeline;     // this launch is a stage of the depth pipeline (k_raycast.cu PIPE)
   int32_t count;        // accumulate counters
   // device pointers
   const void* pool;       // slot-linear brick pool

@@ -612,8 +612,17 @@ int raycast_pass(tvk_ctx* ctx, bool with_hash) {
   u.out0 = ctx->buf[0];
   if (!iso) { u.out1 = ctx->buf[1 + nxt]; u.out2 = ctx->buf[3 + nxt]; u.out3 = nullptr; }
   else { u.out1 = ctx->buf[5]; u.out2 = ctx->buf[3 + nxt]; u.out3 = ctx->buf[1 + nxt]; }
+  if (ctx->stage_mode) {   // one stage of the depth pipeline (tvk_render_stage): inputs from the stage in front
+    if (iso) return fail(ctx, TVK_ERR_INVALID, "depth pipeline: transfer-function modes only");
+    u.pipeline = 1;
+    u.first_pass = ctx->stage_ray_start ? 0 : 1;
+    u.ray_start = ctx->stage_ray_start ? ctx->stage_ray_start : ctx->buf[3];
+    u.start_color = ctx->stage_color ? ctx->stage_color : ctx->buf[1];
+    u.out1 = ctx->buf[1]; u.out2 = ctx->buf[3];
+  }
   launch_raycast(u, ctx->params.mode, ctx->params.lighting, ctx->dtype, ctx->stream);
   CU(cudaGetLastError());
+  if (ctx->stage_mode) { ctx->blank = true; return TVK_OK; }   // no resume state of its own: every stage frame starts anew
   if (iso) {   // GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2763-2830)
     const tvk_render_params& p = ctx->params;
     float a[3], d[3], s[3];
@@ -1386,6 +1395,27 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
     cudaEventElapsedTime(&st->ms_upload_bricks, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
   }
+  return TVK_OK;
+}
+
+int tvk_render_stage(tvk_ctx* ctx, const void* in_resume_pos, const void* in_resume_color, tvk_frame_stats* st) {
+  if (!ctx) return TVK_ERR_INVALID;
+  if ((in_resume_pos == nullptr) != (in_resume_color == nullptr)) return fail(ctx, TVK_ERR_INVALID, "stage inputs come in pairs");
+  ctx->stage_mode = true;
+  ctx->stage_ray_start = static_cast<const float4*>(in_resume_pos);
+  ctx->stage_color = static_cast<const float4*>(in_resume_color);
+  ctx->blank = true;
+  const int rc = tvk_render(ctx, st);      // visibility, miss table, the stage launch, paging of what it missed
+  ctx->stage_mode = false;
+  ctx->stage_ray_start = ctx->stage_color = nullptr;
+  return rc;
+}
+
+int tvk_get_stage_outputs(tvk_ctx* ctx, void** image, void** resume_color, void** resume_pos) {
+  if (!ctx || !ctx->img_w) return fail(ctx, TVK_ERR_INVALID, "nothing rendered");
+  if (image) *image = ctx->buf[0];
+  if (resume_color) *resume_color = ctx->buf[1];
+  if (resume_pos) *resume_pos = ctx->buf[3];
   return TVK_OK;
 }
 

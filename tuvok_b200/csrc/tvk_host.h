@@ -154,6 +154,8 @@ struct tvk_ctx {
   struct ClearView { bool on = false; double iso = 0.8; float color[3] = {1, 0, 0}; float size = 5.5f, context = 1.0f, border = 60.0f;
                      float pos[4] = {0, 0, 0.5f, 1.0f}; } cv;
   bool cv_frame = false;          // the last classic frame filled the ClearView targets
+  bool stage_mode = false;        // tvk_render_stage in progress: raycast_pass launches a depth-pipeline stage
+  const float4* stage_ray_start = nullptr; const float4* stage_color = nullptr;   // its inputs (nullptr: first stage)
   float4* result_buf = nullptr;   // set by frames whose result does not follow the mode rule of result_image() (MIP, stereo)
   float4* stereo_d[2] = {nullptr, nullptr};   // kept eye images (m_pFBO3DImageNext[0 / 1]) of a stereo frame
   uchar4* rgba8_async_d[2] = {nullptr, nullptr};   // double-buffered unorm8 images of the async read-back

@@ -528,6 +528,23 @@ class CudaGridLeaper:
         self._ck(self._lib.tvk_read_cv_buffers(self._h, _ptr(a), _ptr(b)))
         return a, b
 
+    # ------------------------------------------------------------------ depth pipeline (tvk_render_stage)
+    def RenderStage(self, in_resume_pos=0, in_resume_color=0):
+        """One stage of a depth-pipelined frame on this renderer's slab (SetShardBox); inputs are DEVICE pointers of the
+        two hand-over images of the stage in front (0 for the first stage).  Pages in what the stage missed."""
+        self._push_params()
+        st = L.FrameStats()
+        self._ck(self._lib.tvk_render_stage(self._h, C.c_void_p(in_resume_pos or None), C.c_void_p(in_resume_color or None),
+                                            C.byref(st)))
+        self.last_stats = st
+        return st
+
+    def stage_output_ptrs(self):
+        """(image, resume_color, resume_pos) device pointers of the last stage."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self._lib.tvk_get_stage_outputs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def SetMIPRotationAngle(self, angle_deg):
         """AbstrRenderer::SetMIPRotationAngle (AbstrRenderer.h:545-547)."""
         self._mip_angle = float(angle_deg)

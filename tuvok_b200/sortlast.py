@@ -299,3 +299,138 @@ class SortLastRenderer:
             done.record(rb["copy"])
         rb["done"][k] = done
         return rb["host"][k].numpy(), done
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Depth pipeline: the alternative to binary swap for latency-bound frames.  The brick grid is cut into n slabs behind
+# each other along the axis most parallel to the view; rank s is STAGE s: it marches every ray through the s-th slab
+# from the eye only, starting from the colour and position the stage in front handed over (tvk_render_stage), and
+# passes both images on over NCCL.  Rays that terminated early stay terminated (no rank renders what a front slab hid),
+# the critical path of a launch is 1/n of the ray, and with consecutive frames in flight all ranks are busy.
+# ---------------------------------------------------------------------------------------------------------------------
+def depth_slabs(finest_layout, n, view_dir, weights=None, align=1, layer_weights=None):
+    """-> (axis, boxes): boxes[s] = (lo[3], hi[3]) in finest-brick units of the s-th slab FROM THE EYE for a camera looking
+    along view_dir (volume space).  weights [x, y, z]: cuts at the k/n quantiles of the weight along the axis (default:
+    equal thickness); align: cuts are multiples of `align` bricks (bricks of coarser LoDs must not straddle a cut:
+    a stage hands a ray on where it leaves its last brick)."""
+    axis = int(np.argmax(np.abs(np.asarray(view_dir, np.float64))))
+    L_ = int(finest_layout[axis])
+    if n > L_:
+        raise ValueError("volume has too few bricks to cut %d slabs" % n)
+    if layer_weights is not None and float(np.asarray(layer_weights).sum()) > 0.0:
+        layers = np.asarray(layer_weights, np.float64)          # per brick layer along the axis (measured, see rebalance)
+    elif weights is not None and float(np.asarray(weights).sum()) > 0.0:
+        layers = np.asarray(weights, np.float64).sum(axis=tuple(a for a in range(3) if a != axis))
+    else:
+        layers = np.ones(L_)
+    cum = np.concatenate([[0.0], np.cumsum(layers)])
+    cuts = [0]
+    for k in range(1, n):
+        c = int(np.argmin(np.abs(cum - cum[-1] * k / n)))
+        if align > 1:
+            c = int(round(c / align)) * align
+        c = max(c, cuts[-1] + 1)                  # every slab keeps at least one brick layer
+        c = min(c, L_ - (n - k))
+        cuts.append(c)
+    cuts.append(L_)
+    boxes = []
+    for k in range(n):
+        lo, hi = [0, 0, 0], [int(v) for v in finest_layout]
+        lo[axis], hi[axis] = cuts[k], cuts[k + 1]
+        boxes.append((lo, hi))
+    if float(view_dir[axis]) < 0.0:               # the camera looks down the axis: the far end comes first
+        boxes.reverse()
+    return axis, boxes
+
+
+class DepthPipeline:
+    """One rank (= stage) of the depth-pipelined renderer."""
+
+    def __init__(self, renderer, rank, n_ranks, finest_layout, float_layout, extent, align=4):
+        import torch
+        import torch.distributed as dist
+        self.r, self.rank, self.n = renderer, rank, n_ranks
+        self.torch, self.dist = torch, dist
+        self.finest, self.flayout, self.extent = tuple(finest_layout), tuple(float_layout), tuple(extent)
+        self.align = align
+        self.weights = None
+        self._in = None
+        self._key = None
+        self.view_id = None            # key of the per-view measured layer weights (rebalance)
+        self.measured = {}
+        self.stream = torch.cuda.current_stream()
+        renderer.set_stream(self.stream.cuda_stream)
+
+    def rebalance(self, stage_samples):
+        """Load feedback for the current view (self.view_id): stage_samples[s] = the cost stage s measured with the current
+        cuts -- its kernel time (or sample count) -- gathered from all ranks, identical everywhere.  Early ray
+        termination puts most samples into the front of the volume while the longest (never terminated) rays bound the
+        back slabs, which no view-independent weight can know; the measured cost of every stage is spread over its
+        brick layers and the cuts move to the new quantiles.  A few rounds converge; the result is kept per view."""
+        boxes = self.update_slab()
+        axis = self._key[0]
+        layers = np.zeros(int(self.finest[axis]))
+        for s_, (lo, hi) in enumerate(boxes):
+            layers[lo[axis]:hi[axis]] = float(stage_samples[s_]) / max(1, hi[axis] - lo[axis])
+        layers += 1e-6 * max(1.0, layers.max())                    # keep every layer cuttable
+        self.measured[self.view_id] = (axis, layers)
+        self._key = None
+
+    def set_weights(self, weights=None):
+        """Non-empty finest-level bricks (SortLastRenderer.set_weights); call after one frame."""
+        if weights is None:
+            from . import _lib as L
+            n = int(self.finest[0]) * int(self.finest[1]) * int(self.finest[2])
+            off = int(self.r.info().lod_offset[0])
+            meta = self.r.page_table()[off:off + n]
+            nonempty = (meta != L.BI_EMPTY) & (meta != L.BI_CHILD_EMPTY)
+            weights = nonempty.reshape(self.finest[2], self.finest[1], self.finest[0]).transpose(2, 1, 0).astype(np.float64)
+        self.weights = np.asarray(weights, np.float64)
+        self._key = None
+
+    def update_slab(self):
+        """This stage's slab for the renderer's current view (every rank derives the same cuts from the same view)."""
+        r = self.r
+        r._push_params()
+        eye = eye_in_volume(np.array(list(r.params.model_view)), self.extent)
+        view_dir = (0.5 - eye) * np.asarray(self.extent, np.float64)
+        lw = self.measured.get(self.view_id)
+        axis0 = int(np.argmax(np.abs(view_dir)))
+        axis, boxes = depth_slabs(self.finest, self.n, view_dir, self.weights, self.align,
+                                  lw[1] if lw is not None and lw[0] == axis0 else None)
+        key = (axis, tuple(map(tuple, boxes[self.rank])))
+        if key != self._key:
+            self._key = key
+            cmin, cmax = box_to_clip(boxes[self.rank], self.finest, self.flayout)
+            r.SetShardBox(cmin, cmax)
+        return boxes
+
+    def _wrap(self, ptr, n_pixels):
+        torch = self.torch
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (n_pixels, 4), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Dev(), device="cuda")
+
+    def render_frame(self):
+        """This stage's part of one frame: receive the hand-over images (stage > 0), march the slab, send them on
+        (stage < n-1).  Returns (stats, image): image is the finished frame (flat RGBA32F device tensor) on the last
+        stage, None elsewhere."""
+        r, torch, dist = self.r, self.torch, self.dist
+        self.update_slab()
+        n_pixels = r.params.width * r.params.height
+        pos_in = col_in = 0
+        if self.rank > 0:
+            if self._in is None or self._in[0].shape[0] != n_pixels:
+                self._in = [torch.empty((n_pixels, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+            dist.recv(self._in[0], src=self.rank - 1)
+            dist.recv(self._in[1], src=self.rank - 1)
+            self.stream.synchronize()             # the library launches on this stream, but pages from the host
+            pos_in, col_in = self._in[0].data_ptr(), self._in[1].data_ptr()
+        st = r.RenderStage(pos_in, col_in)
+        img, col, pos = r.stage_output_ptrs()
+        if self.rank < self.n - 1:
+            dist.send(self._wrap(pos, n_pixels), dst=self.rank + 1)
+            dist.send(self._wrap(col, n_pixels), dst=self.rank + 1)
+            return st, None
+        return st, self._wrap(img, n_pixels)
