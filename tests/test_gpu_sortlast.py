@@ -90,6 +90,7 @@ def test_depth_pipeline_stages_reproduce_the_single_gpu_frame(name, n, align):
     single.enable_counters(True)
     st1 = single.PaintUntilConverged()
     assert st1.converged
+    single.SetRotation(s.rotation)                                    # same view again: a whole frame on the resident bricks
     single_samples = single.Paint().samples
     ref32, ref8 = single.ReadRGBA32F().reshape(-1, 4).copy(), single.ReadRGBA8().copy()
     single.Cleanup()
@@ -133,6 +134,7 @@ def test_depth_pipeline_stages_reproduce_the_single_gpu_frame(name, n, align):
     # pixel differs by less than the 0.01 the cut leaves open (2.55/255) -- SURVEY 8e's bound
     assert float(d.max()) <= 0.0101 and psnr >= 60.0, (float(d.max()), psnr)
     assert mx <= 3
-    if single_samples > 0:                                            # no work behind terminated rays (binary swap: up to 1.6x)
+    # no work behind terminated rays (binary swap renders up to 1.6x the samples); a resumed ray may repeat a sample
+    if single_samples > 0:
         assert total_samples <= single_samples * 1.3 + n * n_pix, (total_samples, single_samples)
     ren.Cleanup()

@@ -211,3 +211,42 @@ def test_weighted_cuts_balance_the_visible_bricks():
     assert sortlast.shard_boxes(finest, 8, None, weights=np.ones(finest)) == sortlast.shard_boxes(finest, 8, None)
     assert sortlast.shard_boxes(finest, 4, [1, 1], weights=np.zeros(finest)) == sortlast.shard_boxes(finest, 4, [1, 1])
     assert sortlast.split_axes((0.1, 0.2, -0.9), 4, "depthw") == [2, 2] and sortlast.split_axes((1, 0, 0), 8, "octantw") is None
+
+
+def test_depth_slabs_order_cover_and_load_feedback():
+    """Depth pipeline planning (no GPU): slabs cover the grid once, come in front-to-back order for either viewing
+    direction, respect the alignment, and the load feedback (DepthPipeline.rebalance's arithmetic) equalises a
+    front-heavy cost profile within a few rounds."""
+    from tuvok_b200 import sortlast
+    finest = (64, 48, 32)
+    for n in (1, 2, 3, 4, 8):
+        for vd in ((0.9, 0.1, 0.2), (-0.9, 0.1, 0.2), (0.1, 0.2, -0.95)):
+            axis, boxes = sortlast.depth_slabs(finest, n, vd)
+            assert axis == int(np.argmax(np.abs(vd))) and len(boxes) == n
+            cover = np.zeros(finest, int)
+            for lo, hi in boxes:
+                cover[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] += 1
+                assert all(hi[i] > lo[i] for i in range(3))
+            assert (cover == 1).all()
+            starts = [b[0][axis] for b in boxes]
+            assert starts == sorted(starts, reverse=vd[axis] < 0)    # stage 0 is the slab nearest to the eye
+    _, boxes = sortlast.depth_slabs(finest, 4, (1, 0, 0), None, align=8)
+    assert all(b[0][0] % 8 == 0 for b in boxes)
+    with pytest.raises(ValueError):
+        sortlast.depth_slabs((3, 3, 3), 4, (1, 0, 0))
+    # weights: only the layers 20..49 hold visible bricks -> the cuts fall inside them
+    w = np.zeros(finest); w[20:50] = 1.0
+    _, boxes = sortlast.depth_slabs(finest, 3, (1, 0, 0), w)
+    assert [b[0][0] for b in boxes] == [0, 30, 40]
+    # load feedback: a cost profile that decays with depth (early ray termination)
+    cost = np.exp(-np.arange(64) / 6.0)
+    lw, spread = None, []
+    for _ in range(5):
+        _, boxes = sortlast.depth_slabs(finest, 4, (1.0, 0, 0), None, 1, lw)
+        stage = [cost[b[0][0]:b[1][0]].sum() for b in boxes]
+        spread.append(max(stage) / (sum(stage) / 4))
+        lw = np.zeros(64)
+        for s_, (lo, hi) in enumerate(boxes):
+            lw[lo[0]:hi[0]] = stage[s_] / (hi[0] - lo[0])
+        lw += 1e-6 * lw.max()
+    assert spread[0] > 3.0 and spread[-1] < 1.3                     # from one stage doing 93 % to within 30 % of even
