@@ -1,6 +1,6 @@
 """Writes tests/golden/octree_*.bin: ExtendedOctree files produced by the UNMODIFIED reference converter
 (oracle/_ref/ref_octree = ExtendedOctreeConverter compiled in place from /root/reference, with the reference's own
-zlib / LZ4 wrappers) from the seeded synthetic volume below.  The reader tests (tests/test_octree_file.py) open these
+zlib / LZ4 / LZMA / bzip2 wrappers and vendored codecs) from the seeded synthetic volume below.  The reader tests (tests/test_octree_file.py) open these
 on machines without the reference tree.  Run from the repo root:  python tests/golden/make_octree_golden.py"""
 import os
 import subprocess
@@ -17,6 +17,8 @@ CASES = {   # name: (kind, (x, y, z), dtype code, dtype name, brick, overlap, co
     "octree_u16_lz4_morton": (synth.V_NOISE, (44, 36, 28), 1, "u16", 16, 2, 3, 1),
     "octree_u8_zlib_hilbert": (synth.V_SPH, (40, 40, 24), 0, "u8", 12, 2, 1, 2),
     "octree_f32_none": (synth.V_SPH, (18, 14, 12), 2, "f32", 12, 2, 0, 0),
+    "octree_u16_lzma": (synth.V_NOISE, (40, 30, 26), 1, "u16", 16, 2, 2, 0),          # LZMA SDK (LzmaCompression.cpp)
+    "octree_u8_bzip2_morton": (synth.V_SPH, (36, 32, 28), 0, "u8", 12, 2, 4, 1),      # bzip2 (BzlibCompression.cpp)
 }
 
 

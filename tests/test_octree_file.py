@@ -53,7 +53,7 @@ def check_file(path, vol, brick, overlap, dtype, codec_slot=None):
 @pytest.mark.parametrize("name", sorted(golden.CASES))
 def test_golden_reference_written_files(name):
     kind, size, dt, dname, brick, ov, comp, layout = golden.CASES[name]
-    slot = {0: 0, 1: 1, 3: 3}[comp]
+    slot = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4}[comp]
     _, info = check_file(os.path.join(GOLDEN, name + ".bin"), golden.volume(name), brick, ov, dt, codec_slot=slot)
     if comp:
         # a compressor may store single bricks raw when they do not shrink; most must be compressed
@@ -66,6 +66,10 @@ def test_golden_reference_written_files(name):
     ((30, 26, 22), orc.U8, 14, 3, 1, 1),
     ((36, 36, 36), orc.U16, 10, 1, 0, 3),      # random brick order on disk
     ((32, 32, 32), orc.F32, 12, 2, 3, 2),
+    ((37, 29, 41), orc.U16, 14, 2, 2, 0),      # LZMA
+    ((32, 32, 32), orc.F32, 12, 2, 2, 1),      # LZMA, floats, Morton order
+    ((30, 26, 22), orc.U8, 14, 3, 4, 2),       # bzip2
+    ((64, 64, 64), orc.U16, 36, 2, 2, 0),      # LZMA, 36^3 bricks (93 KB each: long matches, many rep codes)
 ])
 def test_fresh_reference_files(ref_octree_bin, tmp_path, shape, dtype, brick, overlap, comp, layout):
     rng = np.random.default_rng(sum(shape) + comp)
@@ -132,6 +136,30 @@ def test_malformed_files_are_refused(tmp_path):
     assert bad >= 1
     with pytest.raises(L.TvkError):
         octree_file.read_brick(os.path.join(GOLDEN, "octree_u8_zlib_hilbert.bin"), 99, 0, 0, 0, info=info)
+
+
+@pytest.mark.parametrize("name", ["octree_u16_lzma", "octree_u8_bzip2_morton"])
+def test_corrupt_lzma_and_bzip2_streams_never_pass_silently(tmp_path, name):
+    """Damage inside a compressed brick: the decoder reports it or the voxels differ -- and nothing is written past the brick."""
+    src = bytearray(open(os.path.join(GOLDEN, name + ".bin"), "rb").read())
+    kind, size, dt, _, brick, ov, comp, _ = golden.CASES[name]
+    info = octree_file.probe(os.path.join(GOLDEN, name + ".bin"))
+    o = orc.Octree(golden.volume(name), brick, ov)
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        c = bytearray(src)
+        at = int(rng.integers(len(c) // 2, len(c) - 64))
+        c[at:at + 24] = bytes(int(v) for v in rng.integers(0, 256, 24))
+        t = tmp_path / ("corrupt%d.bin" % trial)
+        t.write_bytes(bytes(c))
+        bad = 0
+        for key in o.iter_bricks():
+            try:
+                if not np.array_equal(octree_file.read_brick(str(t), *key, info=info), o.brick(*key)):
+                    bad += 1
+            except L.TvkError:
+                bad += 1
+        assert bad >= 1, (trial, at)
 
 
 def test_lz4_decoder_against_python_roundtrip(tmp_path):

@@ -1,6 +1,7 @@
 // octree_file.cpp -- see octree_file.h.  Host-side IO of the streaming path (plain C++, no CUDA).
 #include "octree_file.h"
 
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -9,6 +10,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <vector>
 
 namespace tvk {
 
@@ -249,6 +251,173 @@ bool lz4_block_decode(const uint8_t* src, size_t src_len, uint8_t* dst, size_t d
   return op == oend;
 }
 
+// ---- LZMA (raw LZMA1 stream, no end marker, known output size) ------------------------------------------------------
+// The reference compresses bricks with the LZMA SDK's LzmaEncode (IO/UVF/ExtendedOctree/LzmaCompression.cpp:105-127,
+// writeEndMark = 0) and decodes them with LzmaDecode into a buffer of the brick's size (:129-149); the 5 property bytes
+// are not stored with the brick but re-derived from the compression level in the octree header
+// (ExtendedOctree::InitLzmaCompression, ExtendedOctree.cpp:51-55).  LzmaEncProps_Normalize leaves lc = 3, lp = 0,
+// pb = 2 at every level, and the dictionary size does not matter when the whole output buffer is the dictionary, so the
+// level is not needed here.  This is the LZMA decoder of the published specification, written for one-shot decoding.
+namespace {
+struct LzmaRange {
+  const uint8_t* p; const uint8_t* end;
+  uint32_t range = 0xFFFFFFFFu, code = 0;
+  bool bad = false;
+  uint8_t next() { if (p < end) return *p++; bad = true; return 0; }
+  void init() {
+    if (next() != 0) bad = true;
+    for (int i = 0; i < 4; i++) code = (code << 8) | next();
+  }
+  void normalize() { if (range < (1u << 24)) { range <<= 8; code = (code << 8) | next(); } }
+  unsigned bit(uint16_t* prob) {
+    const uint32_t bound = (range >> 11) * *prob;
+    unsigned b;
+    if (code < bound) { *prob = (uint16_t)(*prob + (((1u << 11) - *prob) >> 5)); range = bound; b = 0; }
+    else { *prob = (uint16_t)(*prob - (*prob >> 5)); code -= bound; range -= bound; b = 1; }
+    normalize();
+    return b;
+  }
+  uint32_t direct(unsigned n) {
+    uint32_t r = 0;
+    do {
+      range >>= 1; code -= range;
+      const uint32_t t = 0u - (code >> 31);
+      code += range & t;
+      if (code == range) bad = true;
+      normalize();
+      r = (r << 1) + t + 1;
+    } while (--n);
+    return r;
+  }
+  unsigned tree(uint16_t* probs, unsigned bits) {
+    unsigned m = 1;
+    for (unsigned i = 0; i < bits; i++) m = (m << 1) + bit(&probs[m]);
+    return m - (1u << bits);
+  }
+  unsigned rtree(uint16_t* probs, unsigned bits) {
+    unsigned m = 1, sym = 0;
+    for (unsigned i = 0; i < bits; i++) { const unsigned b = bit(&probs[m]); m = (m << 1) + b; sym |= b << i; }
+    return sym;
+  }
+};
+struct LzmaLen {
+  uint16_t choice, choice2, low[16][8], mid[16][8], high[256];
+  void init() {
+    choice = choice2 = 1024;
+    for (auto& r : low) for (auto& v : r) v = 1024;
+    for (auto& r : mid) for (auto& v : r) v = 1024;
+    for (auto& v : high) v = 1024;
+  }
+  unsigned decode(LzmaRange& rc, unsigned pos_state) {
+    if (rc.bit(&choice) == 0) return rc.tree(low[pos_state], 3);
+    if (rc.bit(&choice2) == 0) return 8 + rc.tree(mid[pos_state], 3);
+    return 16 + rc.tree(high, 8);
+  }
+};
+}  // namespace
+
+static bool lzma_decode(const uint8_t* src, size_t n_src, uint8_t* dst, size_t n_dst) {
+  const unsigned lc = 3, lp = 0, pb = 2;
+  LzmaRange rc; rc.p = src; rc.end = src + n_src;
+  rc.init();
+  std::vector<uint16_t> lit((size_t)0x300 << (lc + lp), 1024);
+  uint16_t is_match[12 << 4], is_rep[12], is_rep_g0[12], is_rep_g1[12], is_rep_g2[12], is_rep0_long[12 << 4];
+  uint16_t pos_slot[4][64], pos_dec[115], align[16];
+  for (auto& v : is_match) v = 1024; for (auto& v : is_rep0_long) v = 1024;
+  for (int i = 0; i < 12; i++) is_rep[i] = is_rep_g0[i] = is_rep_g1[i] = is_rep_g2[i] = 1024;
+  for (auto& r : pos_slot) for (auto& v : r) v = 1024;
+  for (auto& v : pos_dec) v = 1024; for (auto& v : align) v = 1024;
+  LzmaLen len_dec, rep_len_dec; len_dec.init(); rep_len_dec.init();
+  uint32_t rep0 = 0, rep1 = 0, rep2 = 0, rep3 = 0;
+  unsigned state = 0;
+  size_t pos = 0;
+  while (pos < n_dst && !rc.bad) {
+    const unsigned ps = (unsigned)pos & ((1u << pb) - 1);
+    if (rc.bit(&is_match[(state << 4) + ps]) == 0) {               // literal
+      const unsigned prev = pos ? dst[pos - 1] : 0;
+      uint16_t* probs = &lit[(size_t)0x300 * ((((unsigned)pos & ((1u << lp) - 1)) << lc) + (prev >> (8 - lc)))];
+      unsigned sym = 1;
+      if (state >= 7) {
+        unsigned mb = dst[pos - rep0 - 1];
+        do {
+          const unsigned mbit = (mb >> 7) & 1; mb <<= 1;
+          const unsigned b = rc.bit(&probs[((1 + mbit) << 8) + sym]);
+          sym = (sym << 1) | b;
+          if (mbit != b) break;
+        } while (sym < 0x100);
+      }
+      while (sym < 0x100) sym = (sym << 1) | rc.bit(&probs[sym]);
+      dst[pos++] = (uint8_t)sym;
+      state = state < 4 ? 0 : state < 10 ? state - 3 : state - 6;
+      continue;
+    }
+    unsigned len;
+    if (rc.bit(&is_rep[state]) != 0) {
+      if (pos == 0) return false;
+      if (rc.bit(&is_rep_g0[state]) == 0) {
+        if (rc.bit(&is_rep0_long[(state << 4) + ps]) == 0) {         // short rep
+          state = state < 7 ? 9 : 11;
+          if ((size_t)rep0 + 1 > pos) return false;
+          dst[pos] = dst[pos - rep0 - 1]; pos++;
+          continue;
+        }
+      } else {
+        uint32_t dist;
+        if (rc.bit(&is_rep_g1[state]) == 0) dist = rep1;
+        else {
+          if (rc.bit(&is_rep_g2[state]) == 0) dist = rep2;
+          else { dist = rep3; rep3 = rep2; }
+          rep2 = rep1;
+        }
+        rep1 = rep0; rep0 = dist;
+      }
+      len = rep_len_dec.decode(rc, ps);
+      state = state < 7 ? 8 : 11;
+    } else {
+      rep3 = rep2; rep2 = rep1; rep1 = rep0;
+      len = len_dec.decode(rc, ps);
+      state = state < 7 ? 7 : 10;
+      const unsigned len_state = len < 3 ? len : 3;
+      const unsigned slot = rc.tree(pos_slot[len_state], 6);
+      if (slot < 4) rep0 = slot;
+      else {
+        const unsigned nb = (slot >> 1) - 1;
+        uint32_t dist = (2u | (slot & 1u)) << nb;
+        if (slot < 14) dist += rc.rtree(pos_dec + dist - slot, nb);
+        else { dist += rc.direct(nb - 4) << 4; dist += rc.rtree(align, 4); }
+        rep0 = dist;
+      }
+      if (rep0 == 0xFFFFFFFFu) break;                                // end marker (not written by the reference)
+    }
+    if ((size_t)rep0 + 1 > pos) return false;
+    len += 2;
+    if (len > n_dst - pos) return false;                             // a match must not run past the brick
+    const uint8_t* m = dst + pos - rep0 - 1;
+    for (unsigned i = 0; i < len; i++) dst[pos + i] = m[i];          // byte-wise: the match may overlap its own output
+    pos += len;
+  }
+  return !rc.bad && pos == n_dst;
+}
+
+// ---- bzip2: the runtime library of the system (no header in the image: the one entry point is declared here) --------
+// BzlibCompression.cpp:38-52 calls BZ2_bzBuffToBuffDecompress(dst, &dstLen, src, srcLen, 0, 0).
+static bool bz2_decode(const uint8_t* src, size_t n_src, uint8_t* dst, size_t n_dst, std::string* err) {
+  typedef int (*fn_t)(char*, unsigned int*, char*, unsigned int, int, int);
+  static fn_t fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so"}) {
+      if (void* h = dlopen(name, RTLD_NOW | RTLD_LOCAL)) { fn = (fn_t)dlsym(h, "BZ2_bzBuffToBuffDecompress"); if (fn) break; }
+    }
+  }
+  if (!fn) { if (err) *err = "bzip2-compressed bricks need the system's libbz2 runtime library, which was not found"; return false; }
+  unsigned int n = (unsigned int)n_dst;
+  const int rc = fn((char*)dst, &n, (char*)src, (unsigned int)n_src, 0, 0);
+  if (rc != 0 || n != n_dst) { if (err) *err = "bzip2 stream is corrupt"; return false; }
+  return true;
+}
+
 // ExtendedOctree::GetBrickData (ExtendedOctree.cpp:313-360)
 bool OctreeFile::read_brick(uint64_t index, size_t uncompressed_bytes, void* dst, size_t cap, std::string* err) const {
   if (index >= toc.size()) { if (err) *err = "brick index out of range"; return false; }
@@ -275,8 +444,14 @@ bool OctreeFile::read_brick(uint64_t index, size_t uncompressed_bytes, void* dst
         return false;
       }
       return true;
-    case OC_LZMA: if (err) *err = "LZMA-compressed bricks are not supported by this reader"; return false;
-    case OC_BZLIB: if (err) *err = "bzip2-compressed bricks are not supported by this reader"; return false;
+    case OC_LZMA:
+      if (!lzma_decode(tmp.get(), (size_t)t.length, static_cast<uint8_t*>(dst), uncompressed_bytes)) {
+        if (err) *err = "LZMA stream is corrupt";
+        return false;
+      }
+      return true;
+    case OC_BZLIB:
+      return bz2_decode(tmp.get(), (size_t)t.length, static_cast<uint8_t*>(dst), uncompressed_bytes, err);
     default: if (err) *err = "unknown brick compression"; return false;
   }
 }
