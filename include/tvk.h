@@ -166,8 +166,8 @@ int tvk_synth_volume(tvk_ctx* ctx, void* dst_device, int kind, const uint32_t si
  * ExtendedOctreeConverter::Convert writes -- becomes the brick source of the streaming path.  Replaces
  * ExtendedOctree::Open / GetBrickData (IO/UVF/ExtendedOctree/ExtendedOctree.cpp:87-165,313-360) and
  * UVFDataset::GetBrick (IO/uvfDataset.cpp:1690-1712): header + table of contents are parsed once, bricks are
- * read with parallel pread() straight into the library's pinned staging memory (zlib / lz4 bricks are decoded
- * there; LZMA / bzip2 are refused) and copied to the pool on the side stream.  `offset` = byte offset of the
+ * read with parallel pread() straight into the library's pinned staging memory (zlib / lz4 / LZMA / bzip2 bricks
+ * are decoded there; bzip2 needs the system's libbz2 runtime) and copied to the pool on the side stream.  `offset` = byte offset of the
  * octree header in the file, `uvf_file_version` as UVF::ms_ulReaderVersion (>= 5: versioned octree header).
  * scale NULL: the octree's volume aspect.  minmax = MaxMinDataBlock contents (TOC order) or NULL: the table is then
  * computed on the device in one streaming pass over all bricks.  info may be NULL. */
