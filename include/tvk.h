@@ -195,6 +195,14 @@ int tvk_open_uvf(tvk_ctx* ctx, const char* path, uint64_t timestep, const float 
 /* host-only: container walk result; maxmin (4 doubles per brick, TOC order) is filled up to maxmin_cap bricks */
 int tvk_uvf_probe(const char* path, uint64_t timestep, uint64_t* toc_payload_offset, uint64_t* file_version,
                   uint64_t* n_blocks, uint64_t* n_timesteps, double* maxmin, uint64_t maxmin_cap, uint64_t* n_maxmin);
+/* host-only: what UVFDataset derives from the other blocks of the container -- the value range (ComputeRange,
+ * IO/uvfDataset.cpp:1120-1155: min / max over the LoD-0 bricks of the MaxMin block; range[1] < range[0] = unknown), the
+ * 1D histogram's length and filled size (index of the last non-zero bin + 1: the 1D transfer function's size,
+ * GLRenderer.cpp:188-196) and the 2D histogram's maximum gradient magnitude (fGradientScale = 1 / it) and size.
+ * tvk_open_uvf uses the range maximum and the gradient magnitude when it is called with range_max <= 0 /
+ * max_gradient_magnitude <= 0. */
+int tvk_uvf_probe_stats(const char* path, uint64_t timestep, double range[2], uint64_t* hist1d_size,
+                        uint64_t* hist1d_filled, float* max_gradient_magnitude, uint64_t hist2d_size[2]);
 /* host-only helpers (no device, no ctx; errors via tvk_last_error(NULL)): parse header + table of contents,
  * read one brick (x fastest, own size incl. ghost, decoded) into host memory */
 int tvk_octree_file_probe(const char* path, uint64_t offset, uint64_t uvf_file_version, tvk_octree_file_info* info);

@@ -61,7 +61,7 @@ def dump(tmp_path, vol, dtype, brick, overlap, comp=0, layout=0):
             head.update(lods=int(t[1]), largest_single=int(t[3]), bits=int(t[5]), overlap=tuple(int(v) for v in t[13:16]),
                         maxused=tuple(int(v) for v in t[17:20]))
         elif t[0] == "scale":
-            head.update(scale=hx(t[1:4]), range=hx(t[5:7]), total=int(t[10]))
+            head.update(scale=hx(t[1:4]), range=hx(t[5:7]), maxgrad=float.fromhex(t[8]), total=int(t[10]))
         elif t[0] == "lod":
             lods[int(t[1])] = dict(domain=tuple(int(v) for v in t[3:6]), layout=tuple(int(v) for v in t[7:10]))
         elif t[0] == "brick":
@@ -130,3 +130,22 @@ def test_oracle_and_file_source_match_reference_uvfdataset(tmp_path, kind, size,
             assert tuple(np.float32(v) for v in m.tex_min) == tuple(np.float32(v) for v in r["tmin"]), (lod, m.index)
             assert tuple(np.float32(v) for v in m.tex_max) == tuple(np.float32(v) for v in r["tmax"]), (lod, m.index)
             assert tuple(m.n_vox) == r["vox"]
+
+
+@pytest.mark.parametrize("dtype,shape,brick,overlap", [(orc.U8, (40, 36, 28), 16, 2), (orc.U16, (33, 47, 52), 20, 2)])
+def test_uvf_stats_match_what_uvfdataset_derives(tmp_path, dtype, shape, brick, overlap):
+    """tvk_uvf_probe_stats / the defaults of tvk_open_uvf: value range == UVFDataset::GetRange (ComputeRange over the
+    LoD-0 bricks of the MaxMin block), maximum gradient magnitude == UVFDataset::GetMaxGradMagnitude (2D histogram
+    block), 1D histogram filled size == index of the last non-zero bin + 1."""
+    from tuvok_b200 import octree_file
+    rng = np.random.default_rng(3)
+    top = 200 if dtype == orc.U8 else 3000
+    vol = (rng.integers(0, top, size=shape)).astype(orc.NP_DTYPE[dtype])
+    vol[5:20, 5:20, 5:20] //= 4                                   # some structure for the gradient histogram
+    uvf, head, _, _ = dump(tmp_path, vol, dtype, brick, overlap)
+    st = octree_file.uvf_stats(uvf)
+    assert st["range"] == (float(head["range"][0]), float(head["range"][1]))
+    assert st["range"] == (float(vol.min()), float(vol.max()))
+    assert np.float32(st["max_gradient_magnitude"]) == np.float32(head["maxgrad"]) and st["max_gradient_magnitude"] > 0
+    assert st["hist1d_filled"] == int(vol.max()) + 1 and st["hist1d_size"] >= st["hist1d_filled"]
+    assert st["hist2d_size"][0] > 0 and st["hist2d_size"][1] > 0

@@ -262,6 +262,16 @@ def test_golden_uvf_container():
     check_uvf(os.path.join(GOLDEN, "volume_u8_zlib.uvf"), golden.volume(case), brick, ov, dt, ts)
 
 
+def test_golden_uvf_stats():
+    """The container's other blocks (machines without the reference tree): range from the MaxMin block, 1D histogram."""
+    st = octree_file.uvf_stats(os.path.join(GOLDEN, "volume_u8_zlib.uvf"))
+    vol = golden.volume("octree_u8_zlib_hilbert")
+    assert st["range"] == (float(vol.min()), float(vol.max()))
+    assert st["hist1d_filled"] == int(vol.max()) + 1
+    with pytest.raises(L.TvkError):
+        octree_file.uvf_stats(os.path.join(GOLDEN, "octree_u16_none.bin"))
+
+
 def test_fresh_uvf_with_two_timesteps(tmp_path):
     tool = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "ref_uvf")
     if not os.path.exists(tool):
@@ -332,7 +342,8 @@ def test_uvf_file_renders_like_the_gpu_bricked_volume():
     dev = s.make_renderer("device")
     dev.PaintUntilConverged()
     r = tb.CudaGridLeaper(max_gpu_mem=s.max_gpu_mem, hash_table_size=s.hash_size(), brick_strategy=s.strategy)
-    info = r.OpenUVF(os.path.join(GOLDEN, "volume_u8_zlib.uvf"), max_gradient_magnitude=s.max_grad)
+    # (range_max given: left at 0, tvk_open_uvf would take the file's own value range, 0..249, as UVFDataset does)
+    info = r.OpenUVF(os.path.join(GOLDEN, "volume_u8_zlib.uvf"), range_max=s.range_max, max_gradient_magnitude=s.max_grad)
     assert info.brick_count == s.octree.total_bricks and info.bricks_by_codec[1] > 0
     n = r.info().total_bricks
     assert np.array_equal(r.minmax(n), s.octree.minmax[:n])          # from the file's MaxMin block

@@ -7,6 +7,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -176,7 +177,7 @@ bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out) {
   c.pos += cs_len;
   const uint64_t to_first = c.get<uint64_t>();
   uint64_t off = c.pos + to_first;                     // GlobalHeader::GetDataPos
-  uint64_t toc_seen = 0, mm_seen = 0;
+  uint64_t toc_seen = 0, mm_seen = 0, h1_seen = 0, h2_seen = 0;
   for (;;) {
     if (off + 32 > fsize) { out->error = "data block list runs past the end of the file"; ::close(fd); return false; }
     Cursor b{fd, off};
@@ -205,6 +206,25 @@ bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out) {
         out->have_maxmin = true;
       }
       mm_seen++;
+    } else if (semantics == 5) {                       // UVFTables::BS_1D_HISTOGRAM
+      if (h1_seen == timestep) {
+        const uint64_t n = b.get<uint64_t>();
+        if (!b.ok || n > (1ull << 32) || b.pos + n * 8 > fsize) { out->error = "corrupt 1D histogram block"; ::close(fd); return false; }
+        std::vector<uint64_t> bins((size_t)n);
+        if (n && !pread_all(fd, bins.data(), (size_t)n * 8, b.pos)) { out->error = "short read in the 1D histogram block"; ::close(fd); return false; }
+        out->hist1d_size = n;
+        for (uint64_t i = 0; i < n; i++) if (bins[(size_t)i] != 0) out->hist1d_filled = i + 1;
+        out->have_hist1d = true;
+      }
+      h1_seen++;
+    } else if (semantics == 6) {                       // UVFTables::BS_2D_HISTOGRAM
+      if (h2_seen == timestep) {
+        out->max_grad_magnitude = b.get<float>();
+        out->hist2d_size[0] = b.get<uint64_t>(); out->hist2d_size[1] = b.get<uint64_t>();
+        if (!b.ok) { out->error = "corrupt 2D histogram block"; ::close(fd); return false; }
+        out->have_hist2d = true;
+      }
+      h2_seen++;
     }
     if (to_next == 0) break;
     off += to_next;
@@ -212,6 +232,18 @@ bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out) {
   ::close(fd);
   out->n_toc = toc_seen;
   if (toc_seen <= timestep) { out->error = toc_seen ? "timestep out of range" : "no TOC block (legacy raster-data UVF: use the generic brick source)"; return false; }
+  return true;
+}
+
+bool uvf_range(const UvfScan& sc, uint64_t lod0_bricks, double* lo, double* hi) {
+  const uint64_t n = std::min<uint64_t>(lod0_bricks, sc.maxmin.size() / 4);
+  if (!sc.have_maxmin || n == 0) return false;
+  double a = sc.maxmin[0], b = sc.maxmin[1];
+  for (uint64_t i = 1; i < n; i++) {
+    a = std::min(a, sc.maxmin[(size_t)i * 4]);
+    b = std::max(b, sc.maxmin[(size_t)i * 4 + 1]);
+  }
+  *lo = a; *hi = b;
   return true;
 }
 

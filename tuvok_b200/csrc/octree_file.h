@@ -44,6 +44,7 @@ struct OctreeFile {
   bool open(const char* path, uint64_t offset, uint64_t uvf_file_version);
   void close();
   uint32_t lod_count() const { return (uint32_t)lod_first.size(); }
+  uint64_t lod0_brick_count() const { return lod_layout.size() >= 3 ? lod_layout[0] * lod_layout[1] * lod_layout[2] : 0; }
   size_t element_bytes() const;
   uint64_t brick_index(uint32_t x, uint32_t y, uint32_t z, uint32_t lod) const;
   void brick_size(uint32_t x, uint32_t y, uint32_t z, uint32_t lod, uint32_t out[3]) const;
@@ -62,9 +63,16 @@ struct UvfScan {
   bool have_maxmin = false;
   uint64_t maxmin_components = 0;
   std::vector<double> maxmin;        // 4 doubles per brick (component 0; component 3 of RGBA data), TOC order
+  // the `timestep`-th 1D / 2D histogram blocks (Histogram1DDataBlock.cpp:48-58, Histogram2DDataBlock.cpp:51-66)
+  bool have_hist1d = false, have_hist2d = false;
+  uint64_t hist1d_size = 0, hist1d_filled = 0;   // bins; index of the last non-zero bin + 1 (Grid1D::GetFilledSize)
+  float max_grad_magnitude = 0.0f;               // Histogram2DDataBlock::GetMaxGradMagnitude
+  uint64_t hist2d_size[2] = {0, 0};
   std::string error;
 };
 bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out);
+// UVFDataset::ComputeRange for a TOC-based file (IO/uvfDataset.cpp:1140-1155): min / max scalar over the LoD-0 bricks
+bool uvf_range(const UvfScan& sc, uint64_t lod0_bricks, double* lo, double* hi);
 
 // LZ4 block format (the reference calls LZ4_decompress_fast: the decoder knows only the output size)
 bool lz4_block_decode(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len);

@@ -905,9 +905,39 @@ int tvk_open_uvf(tvk_ctx* ctx, const char* path, uint64_t timestep, const float 
   if (!ctx || !path) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
   UvfScan sc;
   if (!uvf_scan(path, timestep, &sc)) return fail(ctx, TVK_ERR_SOURCE, "%s: %s", path, sc.error.c_str());
+  // what UVFDataset takes from the file when the caller does not override it: the 2D histogram block's maximum
+  // gradient magnitude (UVFDataset::GetMaxGradMagnitude -> fGradientScale of the 2D-TF shaders) and the value range
+  // (UVFDataset::ComputeRange, IO/uvfDataset.cpp:1120-1155: min / max over the LoD-0 bricks of the MaxMin block)
+  if (!(max_gradient_magnitude > 0.0f) && sc.have_hist2d) max_gradient_magnitude = sc.max_grad_magnitude;
+  if (!(range_max > 0.0) && sc.have_maxmin) {
+    OctreeFile f;
+    if (!f.open(path, sc.toc_payload_offset, sc.file_version)) return fail(ctx, TVK_ERR_SOURCE, "%s: %s", path, f.error.c_str());
+    double lo, hi;
+    if (uvf_range(sc, f.lod0_brick_count(), &lo, &hi)) range_max = hi;
+  }
   return tvk_open_octree_file(ctx, path, sc.toc_payload_offset, sc.file_version, scale,
                               sc.have_maxmin ? sc.maxmin.data() : nullptr, sc.maxmin.size() / 4, range_max,
                               max_gradient_magnitude, info);
+}
+
+int tvk_uvf_probe_stats(const char* path, uint64_t timestep, double range[2], uint64_t* hist1d_size, uint64_t* hist1d_filled,
+                        float* max_gradient_magnitude, uint64_t hist2d_size[2]) {
+  if (!path) return TVK_ERR_INVALID;
+  UvfScan sc;
+  if (!uvf_scan(path, timestep, &sc)) { g_create_err = std::string(path) + ": " + sc.error; return TVK_ERR_SOURCE; }
+  if (range) {
+    range[0] = 1.0; range[1] = -1.0;                  // "not known": second < first, the reference's convention
+    if (sc.have_maxmin) {
+      OctreeFile f;
+      if (!f.open(path, sc.toc_payload_offset, sc.file_version)) { g_create_err = std::string(path) + ": " + f.error; return TVK_ERR_SOURCE; }
+      uvf_range(sc, f.lod0_brick_count(), &range[0], &range[1]);
+    }
+  }
+  if (hist1d_size) *hist1d_size = sc.have_hist1d ? sc.hist1d_size : 0;
+  if (hist1d_filled) *hist1d_filled = sc.have_hist1d ? sc.hist1d_filled : 0;
+  if (max_gradient_magnitude) *max_gradient_magnitude = sc.have_hist2d ? sc.max_grad_magnitude : 0.0f;
+  if (hist2d_size) { hist2d_size[0] = sc.hist2d_size[0]; hist2d_size[1] = sc.hist2d_size[1]; }
+  return TVK_OK;
 }
 
 int tvk_uvf_probe(const char* path, uint64_t timestep, uint64_t* toc_payload_offset, uint64_t* file_version,

@@ -36,6 +36,19 @@ def read_brick(path, x, y, z, lod, info=None, offset=0, uvf_file_version=5):
     return np.frombuffer(buf.tobytes(), _NP[info.dtype], sx * sy * sz).reshape(sz, sy, sx)
 
 
+def uvf_stats(path, timestep=0):
+    """What UVFDataset derives from the MaxMin / histogram blocks: dict(range (lo, hi) or None, hist1d_size, hist1d_filled,
+    max_gradient_magnitude, hist2d_size)."""
+    rng = (C.c_double * 2)()
+    n1, f1, mg, h2 = C.c_uint64(), C.c_uint64(), C.c_float(), (C.c_uint64 * 2)()
+    lib = L.lib()
+    rc = lib.tvk_uvf_probe_stats(os.fsencode(path), int(timestep), C.byref(rng), C.byref(n1), C.byref(f1), C.byref(mg), C.byref(h2))
+    if rc:
+        raise L.TvkError(rc, (lib.tvk_last_error(None) or b"").decode())
+    return dict(range=(rng[0], rng[1]) if rng[1] >= rng[0] else None, hist1d_size=n1.value, hist1d_filled=f1.value,
+                max_gradient_magnitude=mg.value, hist2d_size=(h2[0], h2[1]))
+
+
 def uvf_probe(path, timestep=0):
     """Walk a .uvf container: dict(toc_payload_offset, file_version, n_blocks, n_timesteps, maxmin (n, 4) or None)."""
     off, ver, nb, nt, nm = (C.c_uint64() for _ in range(5))
