@@ -250,3 +250,91 @@ def test_depth_slabs_order_cover_and_load_feedback():
             lw[lo[0]:hi[0]] = stage[s_] / (hi[0] - lo[0])
         lw += 1e-6 * lw.max()
     assert spread[0] > 3.0 and spread[-1] < 1.3                     # from one stage doing 93 % to within 30 % of even
+
+
+class _StageStandIn:
+    """Plays CudaGridLeaper for DepthPipeline on the host: a stage adds (rank + 1) * tag to the accumulated colour it is
+    handed, counts the stages a ray went through in the resume position, and records the slab it was given."""
+
+    class _P:
+        width, height = 6, 4
+        model_view = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, -1.6, 1]
+
+    def __init__(self, rank):
+        self.rank, self.params, self.tag = rank, self._P(), 0.0
+        n = self.params.width * self.params.height
+        self.out = [np.zeros((n, 4), np.float32) for _ in range(3)]      # image, resume colour, resume position
+        self.boxes = []
+
+    def _push_params(self):
+        pass
+
+    def SetShardBox(self, cmin, cmax):
+        self.boxes.append((cmin, cmax))
+
+    def RenderStage(self, pos_ptr, col_ptr):
+        import ctypes
+        n = self.params.width * self.params.height
+
+        def view(ptr):
+            return np.frombuffer((ctypes.c_float * (n * 4)).from_address(ptr), np.float32).reshape(n, 4)
+        pos = view(pos_ptr).copy() if pos_ptr else np.zeros((n, 4), np.float32)
+        col = view(col_ptr).copy() if col_ptr else np.zeros((n, 4), np.float32)
+        self.out[1][:] = col + (self.rank + 1) * self.tag
+        self.out[2][:] = pos + 1.0
+        self.out[0][:] = self.out[1]
+
+        class _St:
+            converged, samples, ms_raycast, bricks_paged = 1, 0, 0.0, 0
+        return _St()
+
+    def stage_output_ptrs(self):
+        return tuple(o.ctypes.data for o in self.out)
+
+
+def _pipeline_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ren = _StageStandIn(rank)
+        pipe = sortlast.DepthPipeline(ren, rank, world, (8, 8, 8), (8.0, 8.0, 8.0), (1.0, 1.0, 1.0), align=1, device="cpu")
+        frames = []
+        for f in range(5):                                     # consecutive frames in flight
+            ren.tag = float(10 ** (f % 3))
+            st, img = pipe.render_frame()
+            if img is not None:
+                frames.append((img.numpy().copy(), ren.out[2].copy()))
+        q.put((rank, frames, ren.boxes))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_depth_pipeline_hand_over_over_gloo(world):
+    """The N > 1 orchestration of the depth pipeline on CPU: stage s receives the two hand-over images of stage s-1, the last
+    stage holds the frame, frames do not mix, and every rank cuts the same slabs (stage 0 nearest to the eye)."""
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        rank, frames, boxes = q.get(timeout=240)
+        got[rank] = (frames, boxes)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    frames = got[world - 1][0]
+    assert len(frames) == 5 and all(len(got[r][0]) == 0 for r in range(world - 1))     # only the last stage holds frames
+    for f, (img, pos) in enumerate(frames):
+        tag = float(10 ** (f % 3))
+        assert np.all(img == sum(r + 1 for r in range(world)) * tag)     # every stage added its part exactly once
+        assert np.all(pos == float(world))                                 # the ray went through all stages in order
+    # the eye is at z = +1.6 (model_view above): slabs along z, stage 0 = the slab with the largest z
+    zs = [got[r][1][0][0][2] for r in range(world)]
+    assert zs == sorted(zs, reverse=True) and all(len(got[r][1]) == 1 for r in range(world))

@@ -346,11 +346,13 @@ def depth_slabs(finest_layout, n, view_dir, weights=None, align=1, layer_weights
 class DepthPipeline:
     """One rank (= stage) of the depth-pipelined renderer."""
 
-    def __init__(self, renderer, rank, n_ranks, finest_layout, float_layout, extent, align=4):
+    def __init__(self, renderer, rank, n_ranks, finest_layout, float_layout, extent, align=4, device="cuda"):
+        """device "cpu" is for the host-logic tests (gloo, a stand-in renderer with host buffers)."""
         import torch
         import torch.distributed as dist
         self.r, self.rank, self.n = renderer, rank, n_ranks
         self.torch, self.dist = torch, dist
+        self.device = device
         self.finest, self.flayout, self.extent = tuple(finest_layout), tuple(float_layout), tuple(extent)
         self.align = align
         self.weights = None
@@ -358,8 +360,10 @@ class DepthPipeline:
         self._key = None
         self.view_id = None            # key of the per-view measured layer weights (rebalance)
         self.measured = {}
-        self.stream = torch.cuda.current_stream()
-        renderer.set_stream(self.stream.cuda_stream)
+        self.stream = None
+        if device == "cuda":
+            self.stream = torch.cuda.current_stream()
+            renderer.set_stream(self.stream.cuda_stream)
 
     def rebalance(self, stage_samples):
         """Load feedback for the current view (self.view_id): stage_samples[s] = the cost stage s measured with the current
@@ -407,6 +411,10 @@ class DepthPipeline:
 
     def _wrap(self, ptr, n_pixels):
         torch = self.torch
+        if self.device != "cuda":
+            import ctypes
+            buf = (ctypes.c_float * (n_pixels * 4)).from_address(ptr)
+            return torch.from_numpy(np.frombuffer(buf, np.float32).reshape(n_pixels, 4))
 
         class _Dev:
             __cuda_array_interface__ = {"shape": (n_pixels, 4), "typestr": "<f4", "data": (ptr, False), "version": 2}
@@ -422,10 +430,11 @@ class DepthPipeline:
         pos_in = col_in = 0
         if self.rank > 0:
             if self._in is None or self._in[0].shape[0] != n_pixels:
-                self._in = [torch.empty((n_pixels, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+                self._in = [torch.empty((n_pixels, 4), dtype=torch.float32, device=self.device) for _ in range(2)]
             dist.recv(self._in[0], src=self.rank - 1)
             dist.recv(self._in[1], src=self.rank - 1)
-            self.stream.synchronize()             # the library launches on this stream, but pages from the host
+            if self.stream is not None:
+                self.stream.synchronize()         # the library launches on this stream, but pages from the host
             pos_in, col_in = self._in[0].data_ptr(), self._in[1].data_ptr()
         st = r.RenderStage(pos_in, col_in)
         img, col, pos = r.stage_output_ptrs()
