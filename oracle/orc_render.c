@@ -211,7 +211,7 @@ static int ray_setup_px(const orc_render_params* p, const uni* u, uint32_t px, u
   if (!slab3(o, d, zero, one, &s_in, &s_out)) return 0;
   float s0 = fmaxf(s_in, 1.0f);              /* near plane where the camera is inside / in front */
   if (!(s_out > s0)) return 0;               /* no back-face fragment in front of the near plane */
-  if (shard_active(p)) {
+  if (shard_active(p) && !p->pipeline) {
     /* sort-last: the ray keeps its whole-volume entry/exit (so its sample positions are those of the
      * single-GPU ray); a pixel whose ray never meets this rank's brick block is simply not shaded */
     float a_in, a_out;
@@ -608,6 +608,8 @@ static void trace_pixel(ctx_t* c, const float* ray_start, const float* start_col
     v3 cur = entry;
     u4 last = {0, 0, 0, 9999};
     int terminated = 0;
+    int handoff = 0;              /* pipeline stage: the ray left this stage's slab alive, at hand */
+    v4 hand = {0, 0, 0, 0};
     if (ray_len > voxel_size) {
       for (uint32_t j = 0; j < 100 && !terminated; ++j) {
         if (c->shard) {   /* the block is convex: once the ray has left it, nothing more to do on this rank */
@@ -615,7 +617,14 @@ static void trace_pixel(ctx_t* c, const float* ray_start, const float* start_col
           int gone = 0;
           for (int i = 0; i < 3; i++)
             gone |= (dd[i] > 0.0f && cp[i] >= c->sh_hi[i]) || (dd[i] < 0.0f && cp[i] <= c->sh_lo[i]);
-          if (gone) break;
+          if (gone) {
+            if (p->pipeline) {   /* where the next stage picks the ray up */
+              handoff = 1;
+              hand.x = cur.x; hand.y = cur.y; hand.z = cur.z;
+              hand.w = entry_depth * (1.0f - t) + exit_depth * t;
+            }
+            break;
+          }
         }
         float cur_depth = entry_depth * (1.0f - t) + exit_depth * t;
         uint32_t lod = compute_lod(c, cur_depth);
@@ -644,6 +653,22 @@ static void trace_pixel(ctx_t* c, const float* ray_start, const float* start_col
               const float q[3] = {mq.x, mq.y, mq.z};
               int mine = 1;
               for (int a = 0; a < 3; a++) mine &= q[a] >= c->sh_lo[a] && q[a] < c->sh_hi[a];
+              if (!mine && p->pipeline) {
+                /* a brick of a coarser LoD straddles the slab's far side: the ray is handed on AT the side, so
+                 * the next stage takes the brick's remaining samples */
+                const float dd[3] = {dir.x, dir.y, dir.z};
+                int gone = 0;
+                for (int a = 0; a < 3; a++)
+                  gone |= (dd[a] > 0.0f && q[a] >= c->sh_hi[a]) || (dd[a] < 0.0f && q[a] < c->sh_lo[a]);
+                if (gone) {
+                  const float tq = len3(sub3(mq, entry)) / ray_len;
+                  handoff = 1;
+                  hand.x = mq.x; hand.y = mq.y; hand.z = mq.z;
+                  hand.w = entry_depth * (1.0f - tq) + exit_depth * tq;
+                  terminated = 1;
+                  break;
+                }
+              }
               if (!mine) { pc = add3(pc, vdir); continue; }
             }
             if (!iso) {
@@ -699,7 +724,10 @@ static void trace_pixel(ctx_t* c, const float* ray_start, const float* start_col
     }
     /* TerminateRay */
     if (!iso) {
-      if (optimal) { resume_pos.w = 1000.0f; resume_col = acc; }
+      if (optimal) {
+        if (p->pipeline && handoff && !(acc.w > 0.99f)) { resume_pos = hand; resume_col = acc; }
+        else { resume_pos.w = 1000.0f; resume_col = acc; }
+      }
     } else {
       if (optimal) resume_pos.w = hit_pos.w == 0.0f ? 1000.0f : 499.0f + hit_pos.w;
       resume_nrm = hit_nrm;
@@ -743,7 +771,10 @@ void orc_raycast(const orc_render_params* p, const void* pool, const uint32_t* m
     }
     for (uint32_t x = 0; x < p->width; x++) {
       size_t i = (size_t)y * p->width + x;
-      if (!covered[i]) continue;
+      if (!covered[i]) {
+        if (p->pipeline) out2[4 * i + 3] = 1000.0f;   /* a stage marks pixels outside the volume finished */
+        continue;
+      }
       rays++;
       trace_pixel(&c, ray_start + 4 * i, start_color + 4 * i, exit_ + 4 * i,
                   out0 + 4 * i, out1 + 4 * i, out2 + 4 * i, out3 ? out3 + 4 * i : NULL);

@@ -241,6 +241,66 @@ class Scene:
                     subframes=subframes, paged=paged_total, requests=requests, outs=outs, params=p, atlas=atlas,
                     covered=cov, entry=entry, exit=exit_, tf=tf, last_stats=st)
 
+    def oracle_pipeline(self, n_stages, align=1, threads=8):
+        """The depth pipeline on the oracle (orc_render.c `pipeline`): the stages of one frame run one after the other on
+        one pool, stage s on the s-th slab from the eye with the two hand-over images of stage s-1 as inputs.
+        Returns dict(image, rgba8, stages=[dict(outs, samples, box)], resume_pos of the last stage)."""
+        from tuvok_b200 import sortlast
+        o = self.octree
+        warm = self.oracle_render(threads=threads)          # a converged pool to start from
+        pool, atlas = warm["pool"], warm["atlas"]
+        b3 = self.brick
+
+        def put(slot_coord, key):
+            cap = pool.capacity
+            sx, sy, sz = slot_coord % cap[0], (slot_coord // cap[0]) % cap[1], slot_coord // (cap[0] * cap[1])
+            b = o.brick(*key)
+            atlas[sz * b3[2]:sz * b3[2] + b.shape[0], sy * b3[1]:sy * b3[1] + b.shape[1], sx * b3[0]:sx * b3[0] + b.shape[2]] = b
+
+        inner = [b - 2 * self.overlap for b in self.brick]
+        finest = [-(-v // i) for v, i in zip(self.size, inner)]
+        fl = [np.float32(v) / np.float32(i) for v, i in zip(self.size, inner)]
+        fl = [f - f * np.finfo(np.float32).eps if float(int(f)) == float(f) else f for f in fl]
+        mx = max(float(v) * float(s_) for v, s_ in zip(self.size, self.scale))
+        ext = np.array([float(v) * float(s_) / mx for v, s_ in zip(self.size, self.scale)], np.float64)
+        mv, _ = self.matrices()
+        eye = sortlast.eye_in_volume(mv, ext)
+        axis, boxes = sortlast.depth_slabs(finest, n_stages, (0.5 - eye) * ext, None, align)
+        tf = self.tf_bytes()
+        fin = o.brick_count(0)
+        pos = col = None
+        stages = []
+        for s_ in range(n_stages):
+            cmin, cmax = sortlast.box_to_clip(boxes[s_], finest, fl)
+            keep = self.clip
+            self.clip = (cmin, cmax)
+            p = self.oracle_params(pool)
+            self.clip = keep
+            p.pipeline = 1
+            entry, exit_, cov = orc.ray_setup(p)
+            rs = entry.copy() if pos is None else pos
+            sc = np.zeros_like(entry) if col is None else col
+            for _ in range(32):
+                hash_table = np.zeros(p.hash_size, np.uint32)
+                outs, st = orc.raycast(p, atlas, pool.meta, tf, rs, sc, exit_, cov, hash_table, threads)
+                ids = orc.hash_decode(hash_table, fin)
+                if len(ids) == 0:
+                    break
+                _, slots = pool.upload_bricks(ids)
+                for key, sl in zip(ids, slots):
+                    if sl != 0xFFFFFFFF:
+                        put(int(sl), tuple(int(v) for v in key))
+            else:
+                raise RuntimeError("stage %d did not converge" % s_)
+            stages.append(dict(outs=outs, samples=int(st.samples), box=boxes[s_], covered=cov))
+            pos, col = outs[2].copy(), outs[1].copy()
+        image = stages[-1]["outs"][0].reshape(self.height, self.width, 4)
+        # one whole frame on the same (now larger) pool: the single-renderer sample count to compare with
+        p1 = warm["params"]
+        _, st1 = orc.raycast(p1, atlas, pool.meta, tf, warm["entry"], np.zeros_like(warm["entry"]), warm["exit"], warm["covered"],
+                             None, threads)
+        return dict(image=image, rgba8=orc.rgba8(image), stages=stages, resume_pos=pos, single=warm, single_samples=int(st1.samples))
+
     def oracle_classic(self, threads=8):
         """The classic GLRaycaster frame (AbstrRenderer::PlanFrame at the converged LoD + per-brick passes)."""
         o = self.octree

@@ -338,3 +338,30 @@ def test_depth_pipeline_hand_over_over_gloo(world):
     # the eye is at z = +1.6 (model_view above): slabs along z, stage 0 = the slab with the largest z
     zs = [got[r][1][0][0][2] for r in range(world)]
     assert zs == sorted(zs, reverse=True) and all(len(got[r][1]) == 1 for r in range(world))
+
+
+@pytest.mark.parametrize("name,n", [("c2_bricked36_1d_ert", 2), ("c2_bricked36_1d_ert", 3), ("c3_bricked36_2d_lit", 2),
+                                    ("ragged_1d_lit", 3), ("inside_aniso_2d", 2), ("ragged_1d_lit", 2)])
+def test_oracle_depth_pipeline_equals_the_single_frame(name, n):
+    """The oracle's restatement of a pipeline stage (orc_render.c `pipeline`, the checker of raycast_kernel<PIPE>): the
+    stages of a frame, run one after the other with the hand-over images in between, end in the single-renderer frame
+    up to the resume arithmetic; every ray is finished after the last stage; rays that terminated early in a front slab
+    stay terminated, so the stages together take the single renderer's samples (binary swap: up to 1.6x)."""
+    s = golden_scenes.make(name)
+    r = s.oracle_pipeline(n)
+    single = r["single"]
+    d = np.abs(r["image"] - single["image"])
+    mx, psnr = image_diff(r["rgba8"], single["rgba8"])
+    assert float(d.max()) <= 0.0101 and mx <= 3 and psnr >= 60.0, (float(d.max()), mx, psnr)
+    assert (r["resume_pos"].reshape(-1, 4)[:, 3] == 1000.0).all()
+    total = sum(st["samples"] for st in r["stages"])
+    assert total <= r["single_samples"] * 1.02 + n * s.width * s.height, (total, r["single_samples"])
+    assert total >= r["single_samples"] * 0.98
+    # hand-over images of the first stage: a ray is either finished or waits at/behind the slab's far side
+    if n > 1:
+        pos = r["stages"][0]["outs"][2].reshape(-1, 4)
+        cov = r["stages"][0]["covered"].reshape(-1).astype(bool)
+        live = cov & (pos[:, 3] != 1000.0)
+        assert (pos[~cov, 3] == 1000.0).all()                       # pixels outside the volume are marked finished
+        if live.any():
+            assert (pos[live, 3] < 0).all()                         # a depth in front of the eye (eye-space z < 0)
