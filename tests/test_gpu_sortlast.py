@@ -90,9 +90,9 @@ def test_depth_pipeline_stages_reproduce_the_single_gpu_frame(name, n, align):
     single.enable_counters(True)
     st1 = single.PaintUntilConverged()
     assert st1.converged
+    ref32, ref8 = single.ReadRGBA32F().reshape(-1, 4).copy(), single.ReadRGBA8().copy()
     single.SetRotation(s.rotation)                                    # same view again: a whole frame on the resident bricks
     single_samples = single.Paint().samples
-    ref32, ref8 = single.ReadRGBA32F().reshape(-1, 4).copy(), single.ReadRGBA8().copy()
     single.Cleanup()
 
     mv, _ = s.matrices()
