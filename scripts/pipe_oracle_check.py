@@ -10,7 +10,7 @@ from test_sortlast import scene_layout
 
 for name, n in [("c2_bricked36_1d_ert", 2), ("c3_bricked36_2d_lit", 2), ("ragged_1d_lit", 3), ("c2_bricked36_1d_ert", 3)]:
     s = golden_scenes.make(name)
-    ref = s.oracle_pipeline(n)
+    ref = s.oracle_pipeline(n, fresh=True)     # the renderer below only ever runs stages: same paging history
     finest, fl, ext = scene_layout(s)
     ren = s.make_renderer("device")
     n_pix = s.width * s.height

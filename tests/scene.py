@@ -241,15 +241,22 @@ class Scene:
                     subframes=subframes, paged=paged_total, requests=requests, outs=outs, params=p, atlas=atlas,
                     covered=cov, entry=entry, exit=exit_, tf=tf, last_stats=st)
 
-    def oracle_pipeline(self, n_stages, align=1, threads=8):
+    def oracle_pipeline(self, n_stages, align=1, threads=8, fresh=False):
         """The depth pipeline on the oracle (orc_render.c `pipeline`): the stages of one frame run one after the other on
         one pool, stage s on the s-th slab from the eye with the two hand-over images of stage s-1 as inputs.
+        fresh = False: the stages run on the pool a whole single-renderer frame left behind; fresh = True: on an empty
+        pool that every stage pages its slab into, pass by pass -- the paging history of a renderer that only ever ran
+        stages (the converged floats depend on that history, like every resumed GridLeaper frame).
         Returns dict(image, rgba8, stages=[dict(outs, samples, box)], resume_pos of the last stage)."""
         from tuvok_b200 import sortlast
         o = self.octree
-        warm = self.oracle_render(threads=threads)          # a converged pool to start from
+        warm = self.oracle_render(threads=threads)          # the single-renderer frame (and, unless fresh, its pool)
         pool, atlas = warm["pool"], warm["atlas"]
         b3 = self.brick
+        if fresh:
+            pool, _ = self.oracle_pool()
+            ps = pool.pool_size
+            atlas = np.zeros((ps[2], ps[1], ps[0]), orc.NP_DTYPE[self.dtype])
 
         def put(slot_coord, key):
             cap = pool.capacity
@@ -257,6 +264,8 @@ class Scene:
             b = o.brick(*key)
             atlas[sz * b3[2]:sz * b3[2] + b.shape[0], sy * b3[1]:sy * b3[1] + b.shape[1], sx * b3[0]:sx * b3[0] + b.shape[2]] = b
 
+        if fresh:
+            put(pool.capacity[0] * pool.capacity[1] * pool.capacity[2] - 1, (0, 0, 0, pool.lod_count - 1))
         inner = [b - 2 * self.overlap for b in self.brick]
         finest = [-(-v // i) for v, i in zip(self.size, inner)]
         fl = [np.float32(v) / np.float32(i) for v, i in zip(self.size, inner)]
@@ -295,10 +304,10 @@ class Scene:
             stages.append(dict(outs=outs, samples=int(st.samples), box=boxes[s_], covered=cov))
             pos, col = outs[2].copy(), outs[1].copy()
         image = stages[-1]["outs"][0].reshape(self.height, self.width, 4)
-        # one whole frame on the same (now larger) pool: the single-renderer sample count to compare with
+        # one whole frame on the single renderer's pool: the sample count to compare with
         p1 = warm["params"]
-        _, st1 = orc.raycast(p1, atlas, pool.meta, tf, warm["entry"], np.zeros_like(warm["entry"]), warm["exit"], warm["covered"],
-                             None, threads)
+        _, st1 = orc.raycast(p1, warm["atlas"], warm["pool"].meta, tf, warm["entry"], np.zeros_like(warm["entry"]), warm["exit"],
+                             warm["covered"], None, threads)
         return dict(image=image, rgba8=orc.rgba8(image), stages=stages, resume_pos=pos, single=warm, single_samples=int(st1.samples))
 
     def oracle_classic(self, threads=8):

@@ -365,3 +365,19 @@ def test_oracle_depth_pipeline_equals_the_single_frame(name, n):
         assert (pos[~cov, 3] == 1000.0).all()                       # pixels outside the volume are marked finished
         if live.any():
             assert (pos[live, 3] < 0).all()                         # a depth in front of the eye (eye-space z < 0)
+
+
+def test_oracle_pipeline_paging_history():
+    """A renderer that only ever ran stages pages each slab in pass by pass; one that rendered a whole frame first has
+    every brick resident.  Both converge and both reproduce the single frame, but -- like every resumed GridLeaper frame
+    -- not to the same bits (this difference, 2.9e-3 on this scene, is exactly what the CUDA stages showed against the
+    warm-pool oracle: profiles/r1z_pipe_stage_check.txt)."""
+    s = golden_scenes.make("c2_bricked36_1d_ert")
+    warm, fresh = s.oracle_pipeline(2), golden_scenes.make("c2_bricked36_1d_ert").oracle_pipeline(2, fresh=True)
+    single = warm["single"]["image"]
+    for r in (warm, fresh):
+        assert float(np.abs(r["image"] - single).max()) <= 0.0101
+        assert (r["resume_pos"].reshape(-1, 4)[:, 3] == 1000.0).all()
+    d = float(np.abs(warm["image"] - fresh["image"]).max())
+    assert 1e-4 < d < 0.0101
+    assert sum(st["samples"] for st in fresh["stages"]) == 507713      # the count the CUDA stages reported
