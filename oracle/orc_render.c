@@ -531,7 +531,9 @@ static int get_brick(ctx_t* c, v3 pos, uint32_t* lod, v3 dir, brick_t* o) {
   if (o->empty) return found;
   o->where = foreign ? OUTSIDE_SHARD : classify_brick(c, c0, c1);
   /* NormCoordsToPoolCoords / BrickPoolCoords / InfoToCoords */
-  uint32_t index = foreign ? 0u : info - ORC_BI_FLAG_COUNT;
+  /* a brick outside the shard box is only stepped through: always in the pool coordinates of slot 0, resident or not,
+   * so the ray's positions behind it do not depend on what other views have paged into this pool */
+  uint32_t index = o->where == OUTSIDE_SHARD ? 0u : info - ORC_BI_FLAG_COUNT;
   uint32_t sx = index % p->capacity[0], sy = (index / p->capacity[0]) % p->capacity[1],
            sz = index / (p->capacity[0] * p->capacity[1]);
   v3 vp = V3((float)(sx * p->max_total_brick[0]), (float)(sy * p->max_total_brick[1]),

@@ -279,7 +279,9 @@ __device__ __forceinline__ int get_brick(const RayConsts& P, f3 pos, uint32_t& l
   o.where = foreign ? OUTSIDE_SHARD : classify_brick(P, c0, c1);
   o.id = brick_index(P, bx, by, bz, lod);   // only used by the counting kernels
   // InfoToCoords / BrickPoolCoords / NormCoordsToPoolCoords
-  const uint32_t index = foreign ? 0u : info - TVK_BI_FLAG_COUNT;
+  // a brick outside the shard box is only stepped through: always in the pool coordinates of slot 0, resident or not,
+  // so the ray's positions behind it do not depend on what other views have paged into this pool
+  const uint32_t index = o.where == OUTSIDE_SHARD ? 0u : info - TVK_BI_FLAG_COUNT;
   const uint32_t sx = index % P.capacity[0], sy = (index / P.capacity[0]) % P.capacity[1],
                  sz = index / (P.capacity[0] * P.capacity[1]);
   o.ox = sx * P.total[0]; o.oy = sy * P.total[1]; o.oz = sz * P.total[2];
