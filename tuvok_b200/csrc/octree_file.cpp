@@ -78,11 +78,20 @@ bool OctreeFile::open(const char* path, uint64_t offset, uint64_t uvf_file_versi
   total_size = version > 0 ? c.get<uint64_t>() : 0;
   compression_level = version > 1 ? c.get<uint32_t>() : 0;
   if (!c.ok) { error = "short read in the octree header"; return false; }
-  if (component_type >= 10 || component_count == 0 || vol[0] * vol[1] * vol[2] == 0 ||
-      aspect[0] * aspect[1] * aspect[2] == 0.0 || brick[0] * brick[1] * brick[2] == 0) {
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size < 0) { error = "cannot stat the file"; return false; }
+  const uint64_t fsize = (uint64_t)st.st_size;
+  if (offset > fsize) { error = "octree header offset beyond the end of the file"; return false; }
+  if (component_type >= 10 || component_count == 0 || vol[0] == 0 || vol[1] == 0 || vol[2] == 0 ||
+      aspect[0] * aspect[1] * aspect[2] == 0.0 || brick[0] == 0 || brick[1] == 0 || brick[2] == 0) {
     error = "zero field in the octree header";
     return false;
   }
+  // a hostile header must not drive allocations or wrap the arithmetic below: every field is bounded by what a
+  // 32-bit renderer geometry can address (tvk_open_octree_file refuses larger ones anyway)
+  for (int i = 0; i < 3; i++)
+    if (vol[i] > 0xffffffffull || brick[i] > 0xffffffffull) { error = "octree header: size field exceeds 32 bits"; return false; }
+  if (component_count > 16) { error = "octree header: more than 16 components"; return false; }
   if (precomputed_normals && component_count != 4) { error = "precomputed normals need 4 components"; return false; }
   for (int i = 0; i < 3; i++)
     if (brick[i] <= 2ull * overlap) { error = "brick size does not exceed twice the overlap"; return false; }
@@ -91,7 +100,11 @@ bool OctreeFile::open(const char* path, uint64_t offset, uint64_t uvf_file_versi
   lod_size.clear(); lod_layout.clear(); lod_first.clear();
   uint64_t s[3] = {vol[0], vol[1], vol[2]}, first = 0;
   bool start = true;
+  // every brick needs at least one table entry in the file (12 bytes in version 0, 40 bytes later)
+  const uint64_t toc_entry_bytes = version > 0 ? 40 : 12;
+  const uint64_t max_bricks = (fsize - offset) / toc_entry_bytes;
   do {
+    if (lod_first.size() >= 64) { error = "octree header: more than 64 levels of detail"; return false; }
     if (!start)
       for (int i = 0; i < 3; i++)
         if (s[i] > 1) s[i] = (uint64_t)std::ceil(s[i] / 2.0);
@@ -104,6 +117,12 @@ bool OctreeFile::open(const char* path, uint64_t offset, uint64_t uvf_file_versi
       n *= l;
     }
     lod_first.push_back(first);
+    // n < 2^96 cannot be formed: each factor is < 2^32 and the product is checked stepwise against the file size
+    if (lod_layout[lod_layout.size() - 3] > max_bricks || lod_layout[lod_layout.size() - 3] * lod_layout[lod_layout.size() - 2] > max_bricks ||
+        n > max_bricks || first + n > max_bricks) {
+      error = "octree header implies more bricks than the file can hold a table of contents for";
+      return false;
+    }
     first += n;
   } while (s[0] > 1 || s[1] > 1 || s[2] > 1);
 
@@ -130,14 +149,14 @@ bool OctreeFile::open(const char* path, uint64_t offset, uint64_t uvf_file_versi
       t.codec = c.get<uint32_t>();
       t.valid_length = t.length;
       t.atlas_w = t.atlas_h = 0;
+      if (t.length > fsize || off > fsize) { error = "a brick lies beyond the end of the file"; return false; }
       off += t.length;
     }
   }
   if (!c.ok) { error = "short read in the octree table of contents"; return false; }
-  struct stat st;
-  if (fstat(fd, &st) == 0)
-    for (const OctreeToc& t : toc)
-      if (base + t.offset + t.length > (uint64_t)st.st_size) { error = "a brick lies beyond the end of the file"; return false; }
+  const uint64_t room = fsize - base;      // base <= fsize was checked above
+  for (const OctreeToc& t : toc)           // overflow-safe: no sum of file-supplied values is formed
+    if (t.offset > room || t.length > room - t.offset) { error = "a brick lies beyond the end of the file"; return false; }
   error.clear();
   return true;
 }
@@ -176,10 +195,11 @@ bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out) {
   if (!c.ok || big_endian || cs_len > 1024) { out->error = big_endian ? "big-endian UVF files are not supported" : "corrupt global header"; ::close(fd); return false; }
   c.pos += cs_len;
   const uint64_t to_first = c.get<uint64_t>();
+  if (!c.ok || c.pos > fsize || to_first > fsize - c.pos) { out->error = "corrupt global header"; ::close(fd); return false; }
   uint64_t off = c.pos + to_first;                     // GlobalHeader::GetDataPos
   uint64_t toc_seen = 0, mm_seen = 0, h1_seen = 0, h2_seen = 0;
   for (;;) {
-    if (off + 32 > fsize) { out->error = "data block list runs past the end of the file"; ::close(fd); return false; }
+    if (off > fsize || fsize - off < 32) { out->error = "data block list runs past the end of the file"; ::close(fd); return false; }
     Cursor b{fd, off};
     const uint64_t id_len = b.get<uint64_t>();
     if (id_len > 65536) { out->error = "corrupt data block header"; ::close(fd); return false; }
@@ -195,7 +215,7 @@ bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out) {
     } else if (semantics == 7) {                       // UVFTables::BS_MAXMIN_VALUES (MaxMinDataBlock.cpp:67-95)
       if (mm_seen == timestep) {
         const uint64_t n = b.get<uint64_t>(), comps = b.get<uint64_t>();
-        if (!b.ok || comps == 0 || comps > 16 || b.pos + n * comps * 32 > fsize) { out->error = "corrupt MaxMin block"; ::close(fd); return false; }
+        if (!b.ok || comps == 0 || comps > 16 || b.pos > fsize || n > (fsize - b.pos) / (comps * 32)) { out->error = "corrupt MaxMin block"; ::close(fd); return false; }
         out->maxmin_components = comps;
         std::vector<double> all((size_t)(n * comps * 4));
         if (!pread_all(fd, all.data(), all.size() * 8, b.pos)) { out->error = "short read in the MaxMin block"; ::close(fd); return false; }
@@ -209,7 +229,7 @@ bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out) {
     } else if (semantics == 5) {                       // UVFTables::BS_1D_HISTOGRAM
       if (h1_seen == timestep) {
         const uint64_t n = b.get<uint64_t>();
-        if (!b.ok || n > (1ull << 32) || b.pos + n * 8 > fsize) { out->error = "corrupt 1D histogram block"; ::close(fd); return false; }
+        if (!b.ok || b.pos > fsize || n > (fsize - b.pos) / 8) { out->error = "corrupt 1D histogram block"; ::close(fd); return false; }
         std::vector<uint64_t> bins((size_t)n);
         if (n && !pread_all(fd, bins.data(), (size_t)n * 8, b.pos)) { out->error = "short read in the 1D histogram block"; ::close(fd); return false; }
         out->hist1d_size = n;
@@ -227,7 +247,9 @@ bool uvf_scan(const char* path, uint64_t timestep, UvfScan* out) {
       h2_seen++;
     }
     if (to_next == 0) break;
+    if (to_next > fsize - off) { out->error = "data block list runs past the end of the file"; ::close(fd); return false; }
     off += to_next;
+    if (out->n_blocks > (1u << 20)) { out->error = "data block list does not end"; ::close(fd); return false; }
   }
   ::close(fd);
   out->n_toc = toc_seen;

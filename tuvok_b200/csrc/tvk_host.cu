@@ -428,7 +428,30 @@ int upload_bricks(tvk_ctx* ctx, const uint32_t* ids, uint32_t n, uint32_t* out_s
   dedup_last(meta_kv);
   dedup_last(slot_kv);
   int rc = copy_bricks(ctx, reqs);
-  if (rc) return rc;
+  if (rc) {
+    // The brick source or a copy failed part-way: some target slots are already overwritten, none of the new bricks
+    // can be trusted.  Leave a CONSISTENT state behind: every brick that was evicted and every brick that was to be
+    // paged in is MISSING on the host mirror and on the device, the touched slots are empty ("never used"), so the next
+    // frame simply requests them again.  (The error text of the failure is kept.)
+    const std::string why = ctx->err;
+    std::vector<std::pair<uint32_t, uint32_t>> undo_meta, undo_slot;
+    for (const auto& kv : meta_kv) {
+      ctx->meta_h[kv.first] = TVK_BI_MISSING;
+      undo_meta.emplace_back(kv.first, (uint32_t)TVK_BI_MISSING);
+    }
+    for (size_t i = 0; i < reqs.size(); i++) {
+      Slot& sl = ctx->slots[i];          // slots [0, insert_pos) of the sorted table took the requests in order
+      sl.brick_id = -1; sl.time = 0;
+      undo_slot.emplace_back(pool_coord(ctx, sl), 0xFFFFFFFFu);
+    }
+    ctx->insert_pos = 0;
+    if (out_slots) for (uint32_t i = 0; i < n; i++) out_slots[i] = 0xFFFFFFFFu;
+    scatter_u32(ctx, ctx->meta_d, undo_meta);
+    scatter_u32(ctx, (uint32_t*)ctx->slot_brick_d, undo_slot);
+    ctx->blank = true;
+    ctx->err = why;
+    return rc;
+  }
   rc = scatter_u32(ctx, ctx->meta_d, meta_kv);
   if (rc) return rc;
   rc = scatter_u32(ctx, (uint32_t*)ctx->slot_brick_d, slot_kv);
@@ -850,7 +873,7 @@ static int minmax_from_source(tvk_ctx* ctx) {
   return TVK_OK;
 }
 
-int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64_t uvf_file_version, const float scale[3],
+static int tvk_open_octree_file_impl(tvk_ctx* ctx, const char* path, uint64_t offset, uint64_t uvf_file_version, const float scale[3],
                          const double* minmax, uint64_t n_minmax, double range_max, float max_gradient_magnitude,
                          tvk_octree_file_info* info) {
   if (!ctx || !path) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
@@ -899,8 +922,15 @@ int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64
   ctx->have_volume = true; ctx->data_gen++;
   return TVK_OK;
 }
+int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64_t uvf_file_version, const float scale[3],
+                         const double* minmax, uint64_t n_minmax, double range_max, float max_gradient_magnitude,
+                         tvk_octree_file_info* info) {
+  try { return tvk_open_octree_file_impl(ctx, path, offset, uvf_file_version, scale, minmax, n_minmax, range_max, max_gradient_magnitude, info); }
+  catch (const std::bad_alloc&) { return fail(ctx, TVK_ERR_OOM, "tvk_open_octree_file: out of host memory"); }
+  catch (const std::exception& e) { return fail(ctx, TVK_ERR_SOURCE, "tvk_open_octree_file: %s", e.what()); }
+}
 
-int tvk_open_uvf(tvk_ctx* ctx, const char* path, uint64_t timestep, const float scale[3], double range_max,
+static int tvk_open_uvf_impl(tvk_ctx* ctx, const char* path, uint64_t timestep, const float scale[3], double range_max,
                  float max_gradient_magnitude, tvk_octree_file_info* info) {
   if (!ctx || !path) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
   UvfScan sc;
@@ -919,8 +949,14 @@ int tvk_open_uvf(tvk_ctx* ctx, const char* path, uint64_t timestep, const float 
                               sc.have_maxmin ? sc.maxmin.data() : nullptr, sc.maxmin.size() / 4, range_max,
                               max_gradient_magnitude, info);
 }
+int tvk_open_uvf(tvk_ctx* ctx, const char* path, uint64_t timestep, const float scale[3], double range_max,
+                 float max_gradient_magnitude, tvk_octree_file_info* info) {
+  try { return tvk_open_uvf_impl(ctx, path, timestep, scale, range_max, max_gradient_magnitude, info); }
+  catch (const std::bad_alloc&) { return fail(ctx, TVK_ERR_OOM, "tvk_open_uvf: out of host memory"); }
+  catch (const std::exception& e) { return fail(ctx, TVK_ERR_SOURCE, "tvk_open_uvf: %s", e.what()); }
+}
 
-int tvk_uvf_probe_stats(const char* path, uint64_t timestep, double range[2], uint64_t* hist1d_size, uint64_t* hist1d_filled,
+static int tvk_uvf_probe_stats_impl(const char* path, uint64_t timestep, double range[2], uint64_t* hist1d_size, uint64_t* hist1d_filled,
                         float* max_gradient_magnitude, uint64_t hist2d_size[2]) {
   if (!path) return TVK_ERR_INVALID;
   UvfScan sc;
@@ -939,8 +975,14 @@ int tvk_uvf_probe_stats(const char* path, uint64_t timestep, double range[2], ui
   if (hist2d_size) { hist2d_size[0] = sc.hist2d_size[0]; hist2d_size[1] = sc.hist2d_size[1]; }
   return TVK_OK;
 }
+int tvk_uvf_probe_stats(const char* path, uint64_t timestep, double range[2], uint64_t* hist1d_size, uint64_t* hist1d_filled,
+                        float* max_gradient_magnitude, uint64_t hist2d_size[2]) {
+  try { return tvk_uvf_probe_stats_impl(path, timestep, range, hist1d_size, hist1d_filled, max_gradient_magnitude, hist2d_size); }
+  catch (const std::bad_alloc&) { g_create_err = "tvk_uvf_probe_stats: out of host memory"; return TVK_ERR_OOM; }
+  catch (const std::exception& e) { g_create_err = std::string("tvk_uvf_probe_stats: ") + e.what(); return TVK_ERR_SOURCE; }
+}
 
-int tvk_uvf_probe(const char* path, uint64_t timestep, uint64_t* toc_payload_offset, uint64_t* file_version,
+static int tvk_uvf_probe_impl(const char* path, uint64_t timestep, uint64_t* toc_payload_offset, uint64_t* file_version,
                   uint64_t* n_blocks, uint64_t* n_timesteps, double* maxmin, uint64_t maxmin_cap, uint64_t* n_maxmin) {
   if (!path) return TVK_ERR_INVALID;
   UvfScan sc;
@@ -952,6 +994,12 @@ int tvk_uvf_probe(const char* path, uint64_t timestep, uint64_t* toc_payload_off
   if (n_maxmin) *n_maxmin = sc.maxmin.size() / 4;
   if (maxmin && maxmin_cap) std::memcpy(maxmin, sc.maxmin.data(), std::min<size_t>(maxmin_cap, sc.maxmin.size() / 4) * 32);
   return TVK_OK;
+}
+int tvk_uvf_probe(const char* path, uint64_t timestep, uint64_t* toc_payload_offset, uint64_t* file_version,
+                  uint64_t* n_blocks, uint64_t* n_timesteps, double* maxmin, uint64_t maxmin_cap, uint64_t* n_maxmin) {
+  try { return tvk_uvf_probe_impl(path, timestep, toc_payload_offset, file_version, n_blocks, n_timesteps, maxmin, maxmin_cap, n_maxmin); }
+  catch (const std::bad_alloc&) { g_create_err = "tvk_uvf_probe: out of host memory"; return TVK_ERR_OOM; }
+  catch (const std::exception& e) { g_create_err = std::string("tvk_uvf_probe: ") + e.what(); return TVK_ERR_SOURCE; }
 }
 
 static void fill_file_info(const OctreeFile& g, tvk_octree_file_info* info) {
@@ -970,15 +1018,20 @@ static void fill_file_info(const OctreeFile& g, tvk_octree_file_info* info) {
 }
 
 // host-only helpers (no device, no ctx): header/TOC probe and single-brick read of an ExtendedOctree file
-int tvk_octree_file_probe(const char* path, uint64_t offset, uint64_t uvf_file_version, tvk_octree_file_info* info) {
+static int tvk_octree_file_probe_impl(const char* path, uint64_t offset, uint64_t uvf_file_version, tvk_octree_file_info* info) {
   if (!path || !info) return TVK_ERR_INVALID;
   OctreeFile f;
   if (!f.open(path, offset, uvf_file_version)) { g_create_err = std::string(path) + ": " + f.error; return TVK_ERR_SOURCE; }
   fill_file_info(f, info);
   return TVK_OK;
 }
+int tvk_octree_file_probe(const char* path, uint64_t offset, uint64_t uvf_file_version, tvk_octree_file_info* info) {
+  try { return tvk_octree_file_probe_impl(path, offset, uvf_file_version, info); }
+  catch (const std::bad_alloc&) { g_create_err = "tvk_octree_file_probe: out of host memory"; return TVK_ERR_OOM; }
+  catch (const std::exception& e) { g_create_err = std::string("tvk_octree_file_probe: ") + e.what(); return TVK_ERR_SOURCE; }
+}
 
-int tvk_octree_file_read_brick(const char* path, uint64_t offset, uint64_t uvf_file_version, uint32_t x, uint32_t y,
+static int tvk_octree_file_read_brick_impl(const char* path, uint64_t offset, uint64_t uvf_file_version, uint32_t x, uint32_t y,
                                uint32_t z, uint32_t lod, void* dst, size_t cap, uint32_t out_size[3]) {
   if (!path || !dst) return TVK_ERR_INVALID;
   OctreeFile f;
@@ -996,6 +1049,12 @@ int tvk_octree_file_read_brick(const char* path, uint64_t offset, uint64_t uvf_f
     return TVK_ERR_SOURCE;
   }
   return TVK_OK;
+}
+int tvk_octree_file_read_brick(const char* path, uint64_t offset, uint64_t uvf_file_version, uint32_t x, uint32_t y,
+                               uint32_t z, uint32_t lod, void* dst, size_t cap, uint32_t out_size[3]) {
+  try { return tvk_octree_file_read_brick_impl(path, offset, uvf_file_version, x, y, z, lod, dst, cap, out_size); }
+  catch (const std::bad_alloc&) { g_create_err = "tvk_octree_file_read_brick: out of host memory"; return TVK_ERR_OOM; }
+  catch (const std::exception& e) { g_create_err = std::string("tvk_octree_file_read_brick: ") + e.what(); return TVK_ERR_SOURCE; }
 }
 
 int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uint32_t size[3], int dtype,
@@ -1110,7 +1169,7 @@ int tvk_set_tf1d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t n, uint64_t nz_lo, 
   CU(cudaStreamSynchronize(ctx->stream));
   if (ctx->tf1d_n != n) {
     if (ctx->tf1d_d) cudaFree(ctx->tf1d_d);
-    ctx->tf1d_d = nullptr;
+    ctx->tf1d_d = nullptr; ctx->tf1d_n = 0;
     CU(cudaMalloc(&ctx->tf1d_d, (size_t)n * sizeof(float4)));
   }
   {
@@ -1129,7 +1188,7 @@ int tvk_set_tf2d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, cons
   CU(cudaStreamSynchronize(ctx->stream));
   if (ctx->tf2d_w != w || ctx->tf2d_h != h) {
     if (ctx->tf2d_d) cudaFree(ctx->tf2d_d);
-    ctx->tf2d_d = nullptr;
+    ctx->tf2d_d = nullptr; ctx->tf2d_w = ctx->tf2d_h = 0;
     CU(cudaMalloc(&ctx->tf2d_d, (size_t)w * h * sizeof(float4)));
   }
   {
@@ -1174,9 +1233,12 @@ int tvk_create_pool(tvk_ctx* ctx, const uint32_t* pool_size) {
   CU(cudaMalloc(&ctx->counts_d, 4 * sizeof(uint32_t)));
   CU(cudaMalloc(&ctx->visited_d, (ctx->meta_count / 32 + 1) * 4));
   ctx->visited_h.assign(ctx->meta_count / 32 + 1, 0);
-  CU(cudaMemset(ctx->meta_d, 0, ctx->meta_count * 4));
-  CU(cudaMemset(ctx->slot_brick_d, 0xFF, (size_t)ctx->n_slots * 4));
-  CU(cudaMemset(ctx->pool_d, 0, ((uint64_t)ctx->n_slots + 1) * ctx->slot_bytes));
+  // The clears run on the render stream; ctx->stream and copy_stream are non-blocking streams, so nothing orders them
+  // against the legacy NULL stream -- the first upload below (either stream) must not overtake a multi-GB memset.
+  CU(cudaMemsetAsync(ctx->meta_d, 0, ctx->meta_count * 4, ctx->stream));
+  CU(cudaMemsetAsync(ctx->slot_brick_d, 0xFF, (size_t)ctx->n_slots * 4, ctx->stream));
+  CU(cudaMemsetAsync(ctx->pool_d, 0, ((uint64_t)ctx->n_slots + 1) * ctx->slot_bytes, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   // miss-report table (GLGridLeaper::InitHashTable, GLGridLeaper.cpp:266-291)
   ctx->hash_size = ctx->cfg.hash_table_size;
   CU(cudaMalloc(&ctx->hash_d, (size_t)ctx->hash_size * 4));
@@ -1720,6 +1782,9 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
       for (int r = 0; r < 4; r++) planes[i][r] = sg[i] * mvp[r * 4 + col[i]] + mvp[r * 4 + 3];
   }
   // AbstrRenderer::ContainsData (AbstrRenderer.cpp:953-997) with the dataset's legacy tests (uvfDataset.cpp:1201-1227)
+  // the rescale factor always comes from the 1D table's size (GLGridLeaper.cpp:652-653 / AbstrRenderer.cpp:961), so a
+  // frame without one cannot be planned (tf1d_n - 1 would wrap and every brick would fail ContainsData)
+  if (!ctx->tf1d_d || ctx->tf1d_n < 2) return fail(ctx, TVK_ERR_INVALID, "no 1D transfer function (needed for the rescale factor)");
   const double rescale = ctx->range_max / double(ctx->tf1d_n - 1);
   double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
   if (p.mode == TVK_RM_1DTRANS) { v0 = double(ctx->tf1d_nz[0]) * rescale; v1 = double(ctx->tf1d_nz[1]) * rescale; }
