@@ -238,6 +238,10 @@ int tvk_upload_bricks(tvk_ctx* ctx, const uint32_t* ids, uint32_t n, uint32_t* o
 int tvk_get_page_table(tvk_ctx* ctx, uint32_t* dst, uint64_t n);
 int tvk_get_slots(tvk_ctx* ctx, int32_t* brick_ids, uint64_t* times, uint32_t* pos3, uint32_t n_slots);
 int tvk_read_pool_slot(tvk_ctx* ctx, uint32_t slot, void* dst, size_t cap);
+/* parity tap: page-table indices of the bricks the last counted subframe (tvk_enable_counters) took samples from --
+ * what tvk_frame_stats.bricks_touched counts.  ids may be NULL (size query); *n = number of touched bricks.  Together
+ * with tvk_get_page_table and tvk_read_pool_slot this is what a full-size frame is re-traced from on the CPU. */
+int tvk_get_touched_bricks(tvk_ctx* ctx, uint32_t* ids, uint64_t cap, uint64_t* n);
 /* GLHashTable::GetData of the last subframe (GLHashTable.cpp:90-105): ids[n][4] */
 int tvk_get_missing_list(tvk_ctx* ctx, uint32_t* ids, uint32_t cap, uint32_t* n);
 

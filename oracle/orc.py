@@ -123,6 +123,7 @@ def lib():
         "orc_pool_slots": (None, [P, P, P, P]),
         "orc_ray_setup": (None, [C.POINTER(RenderParams), P, P, P]),
         "orc_raycast": (None, [C.POINTER(RenderParams)] + [P] * 12 + [C.POINTER(RenderStats), C.c_int]),
+        "orc_raycast_slots": (None, [C.POINTER(RenderParams)] + [P] * 12 + [C.POINTER(RenderStats), C.POINTER(C.c_uint64), C.c_int]),
         "orc_iso_compose": (None, [C.POINTER(RenderParams), P, P, P]),
         "orc_ray_exit_eye": (None, [P, P]),
         "orc_classic_step_scale": (C.c_float, [P, C.c_uint32]),
@@ -373,6 +374,30 @@ def raycast(params, pool_atlas, meta, tf, ray_start, start_color, exit_, covered
                       _p(exit_), _p(covered), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]),
                       hp, C.byref(st), threads)
     return outs, st
+
+
+def raycast_slots(params, slots, meta, tf, ray_start, start_color, exit_, covered, threads=1):
+    """orc_raycast on a sparse slot-linear pool.  slots: {linear pool coordinate: ndarray of max_total_brick^3 voxels}.
+    Returns (outs, stats, absent_reads)."""
+    n = params.width * params.height
+    cap = params.capacity
+    n_slots = cap[0] * cap[1] * cap[2]
+    ptrs = (C.c_void_p * n_slots)()
+    keep = {}
+    for k, a in slots.items():
+        a = np.ascontiguousarray(a, NP_DTYPE[params.dtype])
+        assert a.size == params.max_total_brick[0] * params.max_total_brick[1] * params.max_total_brick[2]
+        keep[k] = a
+        ptrs[int(k)] = a.ctypes.data
+    outs = [np.zeros((n, 4), np.float32) for _ in range(4)]
+    st = RenderStats()
+    absent = C.c_uint64(0)
+    meta = np.ascontiguousarray(meta, np.uint32)
+    tf = np.ascontiguousarray(tf, np.uint8)
+    lib().orc_raycast_slots(C.byref(params), C.cast(ptrs, C.c_void_p), _p(meta), _p(tf), _p(ray_start), _p(start_color),
+                            _p(exit_), _p(covered), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]),
+                            None, C.byref(st), C.byref(absent), threads)
+    return outs, st, int(absent.value)
 
 
 def iso_compose(params, hit_pos, hit_normal):

@@ -290,6 +290,8 @@ typedef struct {
   const orc_render_params* p;
   const uni* u;
   const void* pool;
+  const void* const* slots;  /* orc_raycast_slots: slot-linear pool given as one pointer per slot (NULL = not supplied) */
+  uint64_t absent;           /* texel reads that hit a slot that was not supplied */
   const uint32_t* meta;
   const uint8_t* tf;
   uint32_t* hash;
@@ -304,11 +306,22 @@ static inline float texel(const ctx_t* c, int x, int y, int z) {
   x = x < 0 ? 0 : x >= (int)ps[0] ? (int)ps[0] - 1 : x;
   y = y < 0 ? 0 : y >= (int)ps[1] ? (int)ps[1] - 1 : y;
   z = z < 0 ? 0 : z >= (int)ps[2] ? (int)ps[2] - 1 : z;
-  size_t i = (size_t)x + (size_t)ps[0] * ((size_t)y + (size_t)ps[1] * (size_t)z);
+  const void* base = c->pool;
+  size_t i;
+  if (c->slots) {   /* the same atlas texel, addressed slot by slot (slot = the linear pool coordinate) */
+    const uint32_t* tb = c->p->max_total_brick;
+    const uint32_t* cap = c->p->capacity;
+    const uint32_t sx = (uint32_t)x / tb[0], sy = (uint32_t)y / tb[1], sz = (uint32_t)z / tb[2];
+    base = c->slots[(size_t)sx + (size_t)cap[0] * ((size_t)sy + (size_t)cap[1] * (size_t)sz)];
+    if (!base) { ((ctx_t*)c)->absent++; return 0.0f; }
+    i = (size_t)((uint32_t)x % tb[0]) + (size_t)tb[0] * ((size_t)((uint32_t)y % tb[1]) + (size_t)tb[1] * (size_t)((uint32_t)z % tb[2]));
+  } else {
+    i = (size_t)x + (size_t)ps[0] * ((size_t)y + (size_t)ps[1] * (size_t)z);
+  }
   switch (c->p->dtype) {
-    case ORC_U8: return (float)((const uint8_t*)c->pool)[i];
-    case ORC_U16: return (float)((const uint16_t*)c->pool)[i];
-    default: return ((const float*)c->pool)[i];
+    case ORC_U8: return (float)((const uint8_t*)base)[i];
+    case ORC_U16: return (float)((const uint16_t*)base)[i];
+    default: return ((const float*)base)[i];
   }
 }
 
@@ -744,26 +757,26 @@ done:
   }
 }
 
-void orc_raycast(const orc_render_params* p, const void* pool, const uint32_t* meta,
-                 const uint8_t* tf, const float* ray_start, const float* start_color,
-                 const float* exit_, const uint8_t* covered,
-                 float* out0, float* out1, float* out2, float* out3,
-                 uint32_t* hash, orc_render_stats* stats, int n_threads) {
+static void raycast_impl(const orc_render_params* p, const void* pool, const void* const* slots, const uint32_t* meta,
+                         const uint8_t* tf, const float* ray_start, const float* start_color,
+                         const float* exit_, const uint8_t* covered,
+                         float* out0, float* out1, float* out2, float* out3,
+                         uint32_t* hash, orc_render_stats* stats, uint64_t* absent_reads, int n_threads) {
   uni u;
   derive(p, &u);
   size_t n = (size_t)p->width * p->height;
   /* render targets are cleared (GLGridLeaper.cpp:837) */
   memset(out0, 0, n * 16); memset(out1, 0, n * 16); memset(out2, 0, n * 16);
   if (out3) memset(out3, 0, n * 16);
-  uint64_t samples = 0, rays = 0, bricks = 0;
+  uint64_t samples = 0, rays = 0, bricks = 0, absent = 0;
   uint32_t finest[3];
   for (int i = 0; i < 3; i++)
     finest[i] = (uint32_t)ceil((double)p->vol[i] / p->max_inner_brick[i]);
   if (n_threads < 1) n_threads = 1;
-#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads) reduction(+ : samples, rays, bricks)
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads) reduction(+ : samples, rays, bricks, absent)
   for (int64_t y = 0; y < (int64_t)p->height; y++) {
     ctx_t c;
-    c.p = p; c.u = &u; c.pool = pool; c.meta = meta; c.tf = tf; c.hash = hash;
+    c.p = p; c.u = &u; c.pool = pool; c.slots = slots; c.absent = 0; c.meta = meta; c.tf = tf; c.hash = hash;
     memcpy(c.finest, finest, sizeof(finest));
     c.samples = 0; c.bricks = 0;
     c.shard = shard_active(p);
@@ -783,13 +796,33 @@ void orc_raycast(const orc_render_params* p, const void* pool, const uint32_t* m
     }
     samples += c.samples;
     bricks += c.bricks;
+    absent += c.absent;
   }
+  if (absent_reads) *absent_reads = absent;
   if (stats) {
     stats->samples = samples; stats->rays = rays; stats->brick_visits = bricks;
     uint32_t e = 0;
     if (hash) for (uint32_t i = 0; i < p->hash_size; i++) e += hash[i] != 0;
     stats->hash_entries = e;
   }
+}
+
+void orc_raycast(const orc_render_params* p, const void* pool, const uint32_t* meta,
+                 const uint8_t* tf, const float* ray_start, const float* start_color,
+                 const float* exit_, const uint8_t* covered,
+                 float* out0, float* out1, float* out2, float* out3,
+                 uint32_t* hash, orc_render_stats* stats, int n_threads) {
+  raycast_impl(p, pool, NULL, meta, tf, ray_start, start_color, exit_, covered, out0, out1, out2, out3, hash, stats, NULL,
+               n_threads);
+}
+
+void orc_raycast_slots(const orc_render_params* p, const void* const* slots, const uint32_t* meta,
+                       const uint8_t* tf, const float* ray_start, const float* start_color,
+                       const float* exit_, const uint8_t* covered,
+                       float* out0, float* out1, float* out2, float* out3,
+                       uint32_t* hash, orc_render_stats* stats, uint64_t* absent_reads, int n_threads) {
+  raycast_impl(p, NULL, slots, meta, tf, ray_start, start_color, exit_, covered, out0, out1, out2, out3, hash, stats,
+               absent_reads, n_threads);
 }
 
 /* Compose-FS.glsl:49-76; light colours: GLRenderer.cpp:2772-2808 */

@@ -112,6 +112,7 @@ SIGNATURES = {
     "tvk_get_page_table": (C.c_int, [P, P, C.c_uint64]),
     "tvk_get_slots": (C.c_int, [P, P, P, P, C.c_uint32]),
     "tvk_read_pool_slot": (C.c_int, [P, C.c_uint32, P, C.c_size_t]),
+    "tvk_get_touched_bricks": (C.c_int, [P, P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "tvk_get_missing_list": (C.c_int, [P, P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "tvk_compute_view": (C.c_int, [C.POINTER(RenderParams), C.c_uint32, C.c_uint32, f32x16, f32x16, f32x3, f32x3,
                                    f32x3, C.c_float, C.c_float, C.c_float, C.c_float]),

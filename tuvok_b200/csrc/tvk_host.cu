@@ -1314,6 +1314,22 @@ int tvk_read_pool_slot(tvk_ctx* ctx, uint32_t slot, void* dst, size_t cap) {
   return TVK_OK;
 }
 
+int tvk_get_touched_bricks(tvk_ctx* ctx, uint32_t* ids, uint64_t cap, uint64_t* n) {
+  if (!ctx || !n || !ctx->have_pool) return fail(ctx, TVK_ERR_INVALID, "no pool");
+  uint64_t k = 0;
+  for (size_t w = 0; w < ctx->visited_h.size(); w++) {
+    uint32_t bits = ctx->visited_h[w];
+    while (bits) {
+      const uint32_t b = (uint32_t)__builtin_ctz(bits);
+      bits &= bits - 1;
+      if (ids && k < cap) ids[k] = (uint32_t)(w * 32 + b);
+      k++;
+    }
+  }
+  *n = k;
+  return TVK_OK;
+}
+
 int tvk_get_missing_list(tvk_ctx* ctx, uint32_t* ids, uint32_t cap, uint32_t* n) {
   if (!ctx || !n) return TVK_ERR_INVALID;
   const uint32_t have = (uint32_t)(ctx->last_missing.size() / 4);

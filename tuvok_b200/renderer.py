@@ -316,6 +316,15 @@ class CudaGridLeaper:
         self._ck(self._lib.tvk_read_pool_slot(self._h, slot, _ptr(out), out.nbytes))
         return out
 
+    def touched_bricks(self):
+        """Page-table indices of the bricks the last counted subframe sampled (enable_counters)."""
+        n = C.c_uint64()
+        self._ck(self._lib.tvk_get_touched_bricks(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self._lib.tvk_get_touched_bricks(self._h, _ptr(out), n.value, C.byref(n)))
+        return out
+
     def missing_list(self):
         n = C.c_uint32()
         self._ck(self._lib.tvk_get_missing_list(self._h, None, 0, C.byref(n)))
