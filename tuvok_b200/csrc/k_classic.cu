@@ -47,13 +47,14 @@ __device__ __forceinline__ float half_round(float v) { return __half2float(__flo
 // touches the brick border take the clamped path; both paths read the same voxels, so the results are identical.
 template <typename T, bool GRAD>
 struct BrickTex {
-  const T* base;
-  const T* c;            // interior: voxel (X, Y, Z)
+  typedef typename PairOf<T>::W W;   // pool element: the x-pair (voxel x, voxel x+1), k_pool.cu; this kernel reads the first half
+  const W* base;
+  const W* c;            // interior: element (X, Y, Z)
   uint32_t xo[4], yo[4], zo[4];
   int sy, sz;
   float fx, fy, fz, norm;
   bool nearest, interior;
-  __device__ __forceinline__ void set(const T* b, const uint32_t n[3], uint32_t sy_, uint32_t sz_, f3 tc, bool nn, float nrm) {
+  __device__ __forceinline__ void set(const W* b, const uint32_t n[3], uint32_t sy_, uint32_t sz_, f3 tc, bool nn, float nrm) {
     base = b; nearest = nn; norm = nrm; sy = (int)sy_; sz = (int)sz_;
     int X, Y, Z;
     if (nn) {
@@ -78,8 +79,8 @@ struct BrickTex {
       }
     }
   }
-  __device__ __forceinline__ float v(int i, int j, int k) const { return cvt(__ldg(base + (xo[1 + i] + yo[1 + j] + zo[1 + k]))); }
-  __device__ __forceinline__ float vi(int i, int j, int k) const { return cvt(__ldg(c + (i + j * sy + k * sz))); }
+  __device__ __forceinline__ float v(int i, int j, int k) const { return first_voxel<T>(__ldg(base + (xo[1 + i] + yo[1 + j] + zo[1 + k]))); }
+  __device__ __forceinline__ float vi(int i, int j, int k) const { return first_voxel<T>(__ldg(c + (i + j * sy + k * sz))); }
   __device__ __forceinline__ float tap(int dx, int dy, int dz) const {
     if (nearest) return v(dx, dy, dz) * norm;
     return tri(v(dx, dy, dz), v(dx + 1, dy, dz), v(dx, dy + 1, dz), v(dx + 1, dy + 1, dz), v(dx, dy, dz + 1),
@@ -137,15 +138,13 @@ __device__ __forceinline__ f4 tf_fetch(const ClassicConsts& P, float s, float t)
   ix = min(max(ix, 0), w - 1);
   int iy = 0;
   if (h > 1) { iy = (int)floorf(t * (float)h); iy = min(max(iy, 0), h - 1); }
-  const float4 q = __ldg(P.tf + (size_t)iy * w + ix);
-  f4 r; r.x = q.x; r.y = q.y; r.z = q.z; r.w = q.w;
-  return r;
+  return unorm8x4(__ldg(P.tf + ((uint32_t)iy * (uint32_t)w + (uint32_t)ix)));
 }
 
 // GLRaycaster-ISO-FS.glsl:72-98 / -ISO-CV-FS.glsl:72-98 for one fragment: march from (e_eye, e_tex) to the brick exit,
 // first sample >= iso, RefineIsosurface.glsl:37-52, eye-space hit by interpolation.  false = `discard`.
 template <typename T>
-__device__ __forceinline__ bool iso_first_hit(const ClassicConsts& P, const T* vox, const uint32_t nv[3], uint32_t sy, uint32_t sz,
+__device__ __forceinline__ bool iso_first_hit(const ClassicConsts& P, const typename PairOf<T>::W* vox, const uint32_t nv[3], uint32_t sy, uint32_t sz,
                                               f3 e_eye, f3 exit_, f3 e_tex, f3 xt, float ray_step, float iso, f3& hp, float& f,
                                               f3& hit_tex, unsigned long long& n_samples) {
   const float len = len3(sub3(exit_, e_eye));
@@ -183,7 +182,7 @@ __device__ __forceinline__ bool iso_first_hit(const ClassicConsts& P, const T* v
 
 // ComputeNormal (Volume3D.glsl:43-60): gl_NormalMatrix * (gradient * domainScale), safe-normalised
 template <typename T>
-__device__ __forceinline__ f3 iso_normal(const ClassicConsts& P, const T* vox, const uint32_t nv[3], uint32_t sy, uint32_t sz, f3 ct,
+__device__ __forceinline__ f3 iso_normal(const ClassicConsts& P, const typename PairOf<T>::W* vox, const uint32_t nv[3], uint32_t sy, uint32_t sz, f3 ct,
                                          f3 dscale) {
   BrickTex<T, true> tg;
   tg.set(vox, nv, sy, sz, ct, P.nearest != 0, P.norm);
@@ -250,7 +249,8 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
     }
     f3 fbo = F3(half_round(pn.x), half_round(pn.y), half_round(pn.z));   // near-plane pass (Render3DPreLoop)
     const f3 dscale = F3(P.domain_scale), la = F3(P.light_a), ld = F3(P.light_d), ls = F3(P.light_s), ldir = F3(P.light_dir);
-    const T* pool = (const T*)P.pool;
+    typedef typename PairOf<T>::W W;
+    const W* pool = (const W*)P.pool;
     const uint32_t sy = P.total[0], sz = P.total[0] * P.total[1];
     const int max_cells = (int)(lay[0] + lay[1] + lay[2]);
 #pragma unroll 1
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
           const f3 inc_tex = F3((xt.x - et.x) / nsteps, (xt.y - et.y) / nsteps, (xt.z - et.z) / nsteps);
           rd = F3(rd.x / len, rd.y / len, rd.z / len);
           const f3 inc = scl3(rd, ray_step);
-          const T* vox = pool + (uint64_t)(slot1 - 1u) * P.slot_voxels;
+          const W* vox = pool + (uint64_t)(slot1 - 1u) * P.slot_voxels;
           if (MODE == 3 || MODE == 4) {
             // First pass (GLRaycaster-ISO-FS).  A fragment's hit lies between its ray entry and exit, so a brick whose
             // (half-rounded) entry is clearly behind the kept hit cannot pass the depth test -- and neither can any
@@ -353,10 +353,11 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
                 const float vx = fmaf(ct.x, nf.x, -0.5f), vy = fmaf(ct.y, nf.y, -0.5f), vz = fmaf(ct.z, nf.z, -0.5f);
                 const float x0 = floorf(vx), y0 = floorf(vy), z0 = floorf(vz);
                 const float fx = vx - x0, fy = vy - y0, fz = vz - z0;
-                const T* c = vox + ((int)x0 + (int)y0 * isy + (int)z0 * isz);
-                const float v = tri(cvt(__ldg(c)), cvt(__ldg(c + 1)), cvt(__ldg(c + isy)), cvt(__ldg(c + isy + 1)),
-                                    cvt(__ldg(c + isz)), cvt(__ldg(c + isz + 1)), cvt(__ldg(c + isz + isy)),
-                                    cvt(__ldg(c + isz + isy + 1)), fx, fy, fz) * P.norm;
+                const W* c = vox + ((int)x0 + (int)y0 * isy + (int)z0 * isz);
+                const float v = tri(first_voxel<T>(__ldg(c)), first_voxel<T>(__ldg(c + 1)), first_voxel<T>(__ldg(c + isy)),
+                                    first_voxel<T>(__ldg(c + isy + 1)), first_voxel<T>(__ldg(c + isz)),
+                                    first_voxel<T>(__ldg(c + isz + 1)), first_voxel<T>(__ldg(c + isz + isy)),
+                                    first_voxel<T>(__ldg(c + isz + isy + 1)), fx, fy, fz) * P.norm;
                 mx = fmaxf(mx, v);
                 ct = add3(ct, inc_tex);
               }

@@ -9,6 +9,7 @@
 //   GLHashTable::GetData               Renderer/GL/GLHashTable.cpp:90-105 (device-side compaction
 //                                      instead of reading back the whole table)
 // All integer / fp64-compare work; HBM-bound, coalesced, grid-stride.
+#include <algorithm>
 #include "tvk_dev.h"
 
 namespace tvk {
@@ -97,36 +98,52 @@ __global__ void page_meta_kernel(uint32_t* meta, const PageOp* __restrict__ ops,
     meta[ops[i].new_id] = ops[i].slot;
 }
 
-// one CTA per paged brick: copy the brick (own size, x fastest) into its slot (strides of the max
-// brick size).  16-byte vector path when source and slot rows line up (full-size bricks).
-__global__ void page_copy_kernel(unsigned char* pool, const unsigned char* __restrict__ store,
-                                 const PageOp* __restrict__ ops, uint64_t slot_bytes, uint32_t esize,
+// One CTA per paged brick: move the brick (own size, x fastest) into its slot (strides of the max brick size).
+// POOL LAYOUT ("x-pair"): pool element x of a slot row holds the PAIR (voxel x, voxel x+1), so the
+// traversal kernel fetches both operands of every x-lerp of its trilinear filters with one load (16 loads per sample in
+// the 7-tap modes instead of 32).  The second half of a pair is exactly what the plain layout holds at x+1 -- also where
+// that texel is stale (a smaller brick written over a larger one leaves the old texels in place, as glTexSubImage3D
+// does in the reference's atlas) -- so every filter footprint reads the values it read before.
+template <typename T, typename W>
+__device__ __forceinline__ W make_pair(T lo, T hi);
+template <> __device__ __forceinline__ uint16_t make_pair<uint8_t, uint16_t>(uint8_t lo, uint8_t hi) { return (uint16_t)(lo | ((uint16_t)hi << 8)); }
+template <> __device__ __forceinline__ uint32_t make_pair<uint16_t, uint32_t>(uint16_t lo, uint16_t hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
+template <> __device__ __forceinline__ float2 make_pair<float, float2>(float lo, float hi) { return make_float2(lo, hi); }
+__device__ __forceinline__ uint8_t first_of(uint16_t w) { return (uint8_t)(w & 0xffu); }
+__device__ __forceinline__ uint16_t first_of(uint32_t w) { return (uint16_t)(w & 0xffffu); }
+__device__ __forceinline__ float first_of(float2 w) { return w.x; }
+
+template <typename T, typename W>
+__global__ void page_copy_kernel(W* pool, const T* __restrict__ store, const PageOp* __restrict__ ops, uint64_t slot_voxels,
                                  uint32_t tx, uint32_t ty, uint32_t tz, int src_is_slot_layout) {
   const PageOp op = ops[blockIdx.x];
-  unsigned char* dst = pool + (uint64_t)op.slot * slot_bytes;
-  const unsigned char* src = store + op.src_off;
-  const bool full = src_is_slot_layout || (op.size[0] == tx && op.size[1] == ty);
-  if (full) {
-    const uint64_t bytes = src_is_slot_layout ? slot_bytes : (uint64_t)op.size[0] * op.size[1] * op.size[2] * esize;
-    if (((uintptr_t)dst & 15) == 0 && ((uintptr_t)src & 15) == 0) {
-      const uint64_t n16 = bytes / 16;
-      const uint4* s4 = (const uint4*)src;
-      uint4* d4 = (uint4*)dst;
-      for (uint64_t i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
-      for (uint64_t i = n16 * 16 + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
-    } else {
-      for (uint64_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
-    }
-    return;
-  }
-  const uint32_t row = op.size[0] * esize;
-  const uint32_t rows = op.size[1] * op.size[2];
+  W* dst = pool + (uint64_t)op.slot * slot_voxels;
+  const T* src = (const T*)((const unsigned char*)store + op.src_off);
+  // source geometry: the device brick store keeps bricks padded to the slot shape, staged bricks come at their own size
+  const uint32_t sx = src_is_slot_layout ? tx : op.size[0], sy = src_is_slot_layout ? ty : op.size[1],
+                 sz = src_is_slot_layout ? tz : op.size[2];
+  const uint32_t rows = sy * sz;
   for (uint32_t r = threadIdx.x / 32; r < rows; r += blockDim.x / 32) {
-    const uint32_t y = r % op.size[1], z = r / op.size[1];
-    const unsigned char* s = src + (uint64_t)r * row;
-    unsigned char* d = dst + ((uint64_t)z * ty + y) * tx * esize;
-    for (uint32_t b = threadIdx.x % 32; b < row; b += 32) d[b] = s[b];
+    const uint32_t y = r % sy, z = r / sy;
+    const T* s = src + (uint64_t)r * sx;
+    W* d = dst + ((uint64_t)z * ty + y) * tx;
+    for (uint32_t x = threadIdx.x % 32; x < sx; x += 32) {
+      const T lo = s[x];
+      T hi;
+      if (x + 1 < sx) hi = s[x + 1];
+      else if (x + 1 < tx) hi = first_of(d[x + 1]);   // the texel behind a short row keeps what the slot held before
+      else hi = lo;                                   // last texel of the slot row: never the low operand of a lerp
+      d[x] = make_pair<T, W>(lo, hi);
+    }
+    // the pair in front of the row start is not touched: a row always starts at x = 0
   }
+}
+
+// parity tap (tvk_read_pool_slot): the plain voxels of one slot
+template <typename T, typename W>
+__global__ void slot_unpair_kernel(const W* __restrict__ slot, T* out, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = first_of(slot[i]);
 }
 
 // GLHashTable::GetData: gather the non-zero entries as (table index, value) pairs (the host orders
@@ -169,11 +186,24 @@ void launch_vis_level(uint32_t* meta, const double* minmax, const VisConsts& vc,
 void launch_page_meta(uint32_t* meta, const PageOp* ops, uint32_t n, cudaStream_t s) {
   if (n) page_meta_kernel<<<grid_for(n, 256), 256, 0, s>>>(meta, ops, n);
 }
-void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t n, uint64_t slot_bytes,
+void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t n, uint64_t slot_voxels,
                       uint32_t esize, const uint32_t total[3], int src_is_slot_layout, cudaStream_t s) {
-  if (n)
-    page_copy_kernel<<<n, 256, 0, s>>>((unsigned char*)pool, (const unsigned char*)store, ops, slot_bytes, esize,
-                                       total[0], total[1], total[2], src_is_slot_layout);
+  if (!n) return;
+  if (esize == 1)
+    page_copy_kernel<uint8_t, uint16_t><<<n, 256, 0, s>>>((uint16_t*)pool, (const uint8_t*)store, ops, slot_voxels, total[0],
+                                                          total[1], total[2], src_is_slot_layout);
+  else if (esize == 2)
+    page_copy_kernel<uint16_t, uint32_t><<<n, 256, 0, s>>>((uint32_t*)pool, (const uint16_t*)store, ops, slot_voxels, total[0],
+                                                           total[1], total[2], src_is_slot_layout);
+  else
+    page_copy_kernel<float, float2><<<n, 256, 0, s>>>((float2*)pool, (const float*)store, ops, slot_voxels, total[0], total[1],
+                                                      total[2], src_is_slot_layout);
+}
+void launch_slot_unpair(const void* slot, void* out, uint64_t n_voxels, uint32_t esize, cudaStream_t s) {
+  const unsigned g = (unsigned)std::min<uint64_t>((n_voxels + 255) / 256, 1184);
+  if (esize == 1) slot_unpair_kernel<uint8_t, uint16_t><<<g, 256, 0, s>>>((const uint16_t*)slot, (uint8_t*)out, n_voxels);
+  else if (esize == 2) slot_unpair_kernel<uint16_t, uint32_t><<<g, 256, 0, s>>>((const uint32_t*)slot, (uint16_t*)out, n_voxels);
+  else slot_unpair_kernel<float, float2><<<g, 256, 0, s>>>((const float2*)slot, (float*)out, n_voxels);
 }
 void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s) {
   hash_compact_kernel<<<grid_for(n, 256), 256, 0, s>>>(hash, n, out_list, out_count);

@@ -44,24 +44,31 @@ struct BrickRef {
   uint32_t slot;         // linear pool coordinate (slot s starts at voxel s * slot_voxels)
 };
 
-// Filter footprint of one sample position inside a slot.
+// Filter footprint of one sample position inside a slot.  The pool is in the x-pair layout (k_pool.cu): element x of a
+// row is the pair (voxel x, voxel x+1).
 //   FAST  (linear filter, ghost >= 2): the 4x4x4 neighbourhood [X-1..X+2]^3 always lies inside the
-//         slot, so one clamped centre address + uniform row strides address all 32 voxels.
+//         slot, so one clamped centre address + uniform row strides address everything.  A centre row of the
+//         footprint (voxels X-1..X+2) is the two pairs at X-1 and X+1, a side row (voxels X, X+1) the pair at X:
+//         16 loads fetch the 32 distinct voxels of the 7 overlapping trilinear footprints (4 loads for one footprint).
 //         BS != 0 bakes a cubic brick size in (like the #defines of the reference's generated GLSL,
-//         GLVolumePool.cpp:364-400), turning the 32 voxel addresses into immediate offsets.
+//         GLVolumePool.cpp:364-400), turning the addresses into immediate offsets.
+//         The lerp trees run on packed fp32 (two rows per instruction, tvk_math.cuh): every lerp has the operands and
+//         the rounding of tri(), so the result is bit-identical to seven independent tri() calls.
 //   !FAST (nearest filter or ghost < 2): texel indices are taken in the reference's VIRTUAL ATLAS
 //         (capacity * brick texels, clamp-to-edge at the atlas border like GL_CLAMP_TO_EDGE) and then
 //         split into (slot, texel-in-slot), so taps that leave a brick with a 1-voxel ghost read the
-//         atlas neighbour exactly as the reference's 3D texture does.
+//         atlas neighbour exactly as the reference's 3D texture does.  One voxel per load (the pair's first half).
 template <typename T, bool FAST, int BS>
 struct Foot {
-  const T* c;            // FAST: voxel (X, Y, Z); !FAST: first voxel of the pool
+  typedef typename PairOf<T>::W W;
+  typedef PairCvt<T> CV;
+  const W* c;            // FAST: pair element (X, Y, Z); !FAST: first element of the pool
   uint64_t xo[4], yo[4], zo[4];   // !FAST: element offsets (slot part + in-slot part) of X-1..X+2 etc.
   float fx, fy, fz;
   int sy, sz;            // row / slice stride in elements
   bool nearest;
 
-  __device__ __forceinline__ void set(const RayConsts& P, const T* pool, const T* vox, uint32_t ox, uint32_t oy,
+  __device__ __forceinline__ void set(const RayConsts& P, const W* pool, const W* vox, uint32_t ox, uint32_t oy,
                                       uint32_t oz, f3 tc) {
     int X, Y, Z;
     nearest = !FAST && P.nearest;
@@ -101,64 +108,89 @@ struct Foot {
       }
     }
   }
-  // voxel at texel offset (i, j, k) in [-1, 2]^3 from the footprint origin
-  __device__ __forceinline__ float v(int i, int j, int k) const {
-    if (FAST && BS) return cvt(__ldg(c + (i + j * BS + k * BS * BS)));   // immediate offsets
-    if (FAST) return cvt(__ldg(c + (i + j * sy + k * sz)));
-    return cvt(__ldg(c + (xo[1 + i] + yo[1 + j] + zo[1 + k])));
+  // FAST: the pair at element offset (i, j, k) from the footprint origin
+  __device__ __forceinline__ W ld(int i, int j, int k) const {
+    if (BS) return __ldg(c + (i + j * BS + k * BS * BS));   // immediate offsets
+    return __ldg(c + (i + j * sy + k * sz));
   }
-  // texture(volumePool, coords).r at texel offset (dx,dy,dz)
-  __device__ __forceinline__ float tap(const RayConsts& P, int dx, int dy, int dz) const {
+  // !FAST: voxel at texel offset (i, j, k) in [-1, 2]^3 from the footprint origin
+  __device__ __forceinline__ float v(int i, int j, int k) const {
+    return first_voxel<T>(__ldg(c + (xo[1 + i] + yo[1 + j] + zo[1 + k])));
+  }
+  // !FAST: texture(volumePool, coords).r at texel offset (dx,dy,dz)
+  __device__ __forceinline__ float tap_slow(const RayConsts& P, int dx, int dy, int dz) const {
     if (nearest) return v(dx, dy, dz) * P.norm;
     return tri(v(dx, dy, dz), v(dx + 1, dy, dz), v(dx, dy + 1, dz), v(dx + 1, dy + 1, dz), v(dx, dy, dz + 1),
                v(dx + 1, dy, dz + 1), v(dx, dy + 1, dz + 1), v(dx + 1, dy + 1, dz + 1), fx, fy, fz) * P.norm;
   }
+  // texture(volumePool, coords).r at the sample position
+  __device__ __forceinline__ float centre(const RayConsts& P) const {
+    if (!FAST) return tap_slow(P, 0, 0, 0);
+    // rows (y, z) of the footprint: pair = (voxel X, voxel X+1); the two z-slices share an instruction
+    const W w00 = ld(0, 0, 0), w10 = ld(0, 1, 0), w01 = ld(0, 0, 1), w11 = ld(0, 1, 1);   // w[y][z]
+    const f2 x0 = xlerp2<CV::kBiased>(F2(CV::lo(w00), CV::lo(w01)), F2(CV::hi(w00), CV::hi(w01)), fx);   // y = 0, z = (0, 1)
+    const f2 x1 = xlerp2<CV::kBiased>(F2(CV::lo(w10), CV::lo(w11)), F2(CV::hi(w10), CV::hi(w11)), fx);   // y = 1
+    const f2 y = lerp2(x0, x1, fy);
+    return lerp1(y.x, y.y, fz) * P.norm;
+  }
   // centre value + central-difference gradient (GLGridLeaper-GradientTools.glsl:6-16; the "Yp" tap is
   // fetched at -delta) from the 32 distinct voxels of the 7 overlapping footprints
   __device__ __forceinline__ void sample_with_gradient(const RayConsts& P, float& data, f3& grad) const {
-    if (nearest) {
-      data = tap(P, 0, 0, 0);
-      const float xp = tap(P, 1, 0, 0), xm = tap(P, -1, 0, 0);
-      const float yp = tap(P, 0, -1, 0), ym = tap(P, 0, 1, 0);
-      const float zp = tap(P, 0, 0, 1), zm = tap(P, 0, 0, -1);
+    const float n = P.norm;
+    if (!FAST) {
+      data = tap_slow(P, 0, 0, 0);
+      const float xp = tap_slow(P, 1, 0, 0), xm = tap_slow(P, -1, 0, 0);
+      const float yp = tap_slow(P, 0, -1, 0), ym = tap_slow(P, 0, 1, 0);
+      const float zp = tap_slow(P, 0, 0, 1), zm = tap_slow(P, 0, 0, -1);
       grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
       return;
     }
-    float cc[2][2][2];   // [z][y][x] centre block
+    constexpr bool B = CV::kBiased;
+    // ---- x-lerps.  Centre rows (y, z in {0,1}): voxels m, a, b, p at x = -1, 0, 1, 2 from the pairs at -1 and +1;
+    // the rows z = 0 and z = 1 of one y share the packed instructions.  xm / xc / xp = the x-lerps of the taps at
+    // x-1, x, x+1.
+    f2 xm[2], xc[2], xp[2];
 #pragma unroll
-    for (int k = 0; k < 2; k++)
+    for (int j = 0; j < 2; j++) {
+      const W l0 = ld(-1, j, 0), l1 = ld(-1, j, 1), h0 = ld(1, j, 0), h1 = ld(1, j, 1);
+      const f2 m = F2(CV::lo(l0), CV::lo(l1)), a = F2(CV::hi(l0), CV::hi(l1));
+      const f2 b = F2(CV::lo(h0), CV::lo(h1)), p = F2(CV::hi(h0), CV::hi(h1));
+      xm[j] = xlerp2<B>(m, a, fx);
+      xc[j] = xlerp2<B>(a, b, fx);
+      xp[j] = xlerp2<B>(b, p, fx);
+    }
+    // side rows: y = -1 and y = 2 (z = 0, 1 packed), z = -1 and z = 2 (packed with each other, per y)
+    f2 xyl, xyh, xz[2];
+    {
+      const W a0 = ld(0, -1, 0), a1 = ld(0, -1, 1), b0 = ld(0, 2, 0), b1 = ld(0, 2, 1);
+      xyl = xlerp2<B>(F2(CV::lo(a0), CV::lo(a1)), F2(CV::hi(a0), CV::hi(a1)), fx);   // row y = -1, z = (0, 1)
+      xyh = xlerp2<B>(F2(CV::lo(b0), CV::lo(b1)), F2(CV::hi(b0), CV::hi(b1)), fx);   // row y = 2
+    }
 #pragma unroll
-      for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int i = 0; i < 2; i++) cc[k][j][i] = v(i, j, k);
-    float xl[2][2], xh[2][2], yl[2][2], yh[2][2], zl[2][2], zh[2][2];
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-      for (int b = 0; b < 2; b++) {
-        xl[a][b] = v(-1, b, a);   // [z][y]
-        xh[a][b] = v(2, b, a);
-        yl[a][b] = v(b, -1, a);   // [z][x]
-        yh[a][b] = v(b, 2, a);
-        zl[a][b] = v(b, a, -1);   // [y][x]
-        zh[a][b] = v(b, a, 2);
-      }
-    const float n = P.norm;
-    data = tri(cc[0][0][0], cc[0][0][1], cc[0][1][0], cc[0][1][1], cc[1][0][0], cc[1][0][1], cc[1][1][0], cc[1][1][1],
-               fx, fy, fz) * n;
-    const float xp = tri(cc[0][0][1], xh[0][0], cc[0][1][1], xh[0][1], cc[1][0][1], xh[1][0], cc[1][1][1], xh[1][1], fx, fy, fz) * n;
-    const float xm = tri(xl[0][0], cc[0][0][0], xl[0][1], cc[0][1][0], xl[1][0], cc[1][0][0], xl[1][1], cc[1][1][0], fx, fy, fz) * n;
-    // +y footprint (fetched by the shader as "Ym"), -y footprint ("Yp")
-    const float ym = tri(cc[0][1][0], cc[0][1][1], yh[0][0], yh[0][1], cc[1][1][0], cc[1][1][1], yh[1][0], yh[1][1], fx, fy, fz) * n;
-    const float yp = tri(yl[0][0], yl[0][1], cc[0][0][0], cc[0][0][1], yl[1][0], yl[1][1], cc[1][0][0], cc[1][0][1], fx, fy, fz) * n;
-    const float zp = tri(cc[1][0][0], cc[1][0][1], cc[1][1][0], cc[1][1][1], zh[0][0], zh[0][1], zh[1][0], zh[1][1], fx, fy, fz) * n;
-    const float zm = tri(zl[0][0], zl[0][1], zl[1][0], zl[1][1], cc[0][0][0], cc[0][0][1], cc[0][1][0], cc[0][1][1], fx, fy, fz) * n;
-    grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+    for (int j = 0; j < 2; j++) {
+      const W lo_ = ld(0, j, -1), hi_ = ld(0, j, 2);
+      xz[j] = xlerp2<B>(F2(CV::lo(lo_), CV::lo(hi_)), F2(CV::hi(lo_), CV::hi(hi_)), fx);   // row y = j, z = (-1, 2)
+    }
+    // ---- y-lerps, lanes = z slices
+    const f2 yc = lerp2(xc[0], xc[1], fy);       // centre tap, z = (0, 1)
+    const f2 yxm = lerp2(xm[0], xm[1], fy);      // tap at x-1
+    const f2 yxp = lerp2(xp[0], xp[1], fy);      // tap at x+1
+    const f2 yym = lerp2(xc[1], xyh, fy);        // tap at y+1 (fetched by the shader as "Ym"): rows y = 1, 2
+    const f2 yyp = lerp2(xyl, xc[0], fy);        // tap at y-1 ("Yp"): rows y = -1, 0
+    const f2 yz = lerp2(xz[0], xz[1], fy);       // z = (-1, 2)
+    // ---- z-lerps
+    data = lerp1(yc.x, yc.y, fz) * n;
+    const float txm = lerp1(yxm.x, yxm.y, fz) * n, txp = lerp1(yxp.x, yxp.y, fz) * n;
+    const float tym = lerp1(yym.x, yym.y, fz) * n, typ = lerp1(yyp.x, yyp.y, fz) * n;
+    const float tzp = lerp1(yc.y, yz.y, fz) * n;     // tap at z+1: slices z = 1, 2
+    const float tzm = lerp1(yz.x, yc.x, fz) * n;     // tap at z-1: slices z = -1, 0
+    grad = F3((txm - txp) / 2.0f, (typ - tym) / 2.0f, (tzm - tzp) / 2.0f);
   }
 };
 
-// RGBA8 table, GL_NEAREST, clamp-to-edge (GPUMemMan.cpp:398-401, GLTexture1D.h:48-51).  The table is
-// kept as float4 = byte/255.0f (the unorm8 -> float conversion of the texture unit, done once on upload).
+// RGBA8 table, GL_NEAREST, clamp-to-edge (GPUMemMan.cpp:398-401, GLTexture1D.h:48-51).  The table stays RGBA8
+// (4 bytes per entry: a 4096 x 256 2D table is 4 MB and L2-resident); the texture unit's unorm8 -> float conversion
+// byte / 255.0f is done per fetch, exactly (unorm8x4, tvk_math.cuh).
 __device__ __forceinline__ f4 tf_lookup(const RayConsts& P, float s, float t) {
   const int w = (int)P.tf_w, h = (int)P.tf_h;
   int ix = (int)floorf(s * (float)w);
@@ -168,9 +200,7 @@ __device__ __forceinline__ f4 tf_lookup(const RayConsts& P, float s, float t) {
     iy = (int)floorf(t * (float)h);
     iy = min(max(iy, 0), h - 1);
   }
-  const float4 q = __ldg(P.tf + (size_t)iy * w + ix);
-  f4 r; r.x = q.x; r.y = q.y; r.z = q.z; r.w = q.w;
-  return r;
+  return unorm8x4(__ldg(P.tf + ((uint32_t)iy * (uint32_t)w + (uint32_t)ix)));
 }
 
 __device__ __forceinline__ void brick_coords(const RayConsts& P, f3 pos, uint32_t lod, uint32_t& x, uint32_t& y,
@@ -466,7 +496,8 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
   if (px >= P.width || py >= P.height) return;
   const size_t pix = (size_t)py * P.width + px;
   constexpr bool ISO = MODE == 2;
-  const T* pool = (const T*)P.pool;
+  typedef typename PairOf<T>::W W;           // pool element: the x-pair (voxel x, voxel x+1)
+  const W* pool = (const W*)P.pool;
   unsigned long long n_samples = 0, n_bricks = 0;
   unsigned long long n_alive_iters = 0, n_warp_iters = 0;   // lane-utilisation diagnostics (count mode)
 
@@ -551,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
     bool b_partial = false;  // sort-last: the current brick straddles the shard box (ownership per sample)
     f3 pc = c.entry, b_trans = c.entry, b_inv = c.entry;
     uint32_t b_ox = 0, b_oy = 0, b_oz = 0;
-    const T* vox = pool;
+    const W* vox = pool;
     unsigned long long pend = 0;   // COUNT: brick visits of the chain that the sampling has not reached yet
 
     if (kPark) { park_const(c, park, tid); park_var(c, park, tid); }
@@ -668,10 +699,10 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
             // finite, and opacity correction maps 0 to 0), so its normal, lighting -- and with a 1D table its six
             // gradient taps -- are not computed.  The shader cannot branch this cheaply; the result is identical.
             if (MODE == 0 && !LIT) {
-              const float data = f.tap(P, 0, 0, 0);
+              const float data = f.centre(P);
               col = tf_lookup(P, data * P.trans_scale, 0.0f);
             } else if (MODE == 0) {
-              col = tf_lookup(P, f.tap(P, 0, 0, 0) * P.trans_scale, 0.0f);
+              col = tf_lookup(P, f.centre(P) * P.trans_scale, 0.0f);
               if (kSkipClear && col.w == 0.0f) return col;
               float data; f3 g;
               f.sample_with_gradient(P, data, g);
@@ -686,12 +717,15 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
               f.sample_with_gradient(P, data, g);
               const float gm = len3(g);
               col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
-              if (kSkipClear && col.w == 0.0f) return col;
               if (LIT) {
+                // the normal, the view vector and both light terms do not depend on the table entry: they are computed
+                // while the fetch is in flight, and the colour enters in the last three operations only
                 const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
                 const f3 n = mul3(dscale, gn);
                 const f3 mp = mul3(sub3(q, b_trans), b_inv);
-                const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
+                float dl, sp;
+                light_terms(eye_m, mp, n, ldir, dl, sp);
+                const f3 lit = light_apply(la, mul3(F3(col.x, col.y, col.z), ld), ls, dl, sp);
                 col.x = lit.x; col.y = lit.y; col.z = lit.z;
               }
             }
@@ -758,7 +792,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
           Foot<T, FAST, BS> f;
           f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
           if (COUNT) n_samples++;
-          if (f.tap(P, 0, 0, 0) >= P.isoval) {
+          if (f.centre(P) >= P.isoval) {
             // RefineIsosurface
             f3 rd = F3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
             pc = sub3(pc, rd);
@@ -766,7 +800,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
             for (int k = 0; k < 5; k++) {
               rd = F3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
               f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
-              if (f.tap(P, 0, 0, 0) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
+              if (f.centre(P) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
             }
             const f3 hp = mul3(sub3(pc, b_trans), b_inv);
             hit_pos = xform4(P.m2e, hp.x, hp.y, hp.z, 1.0f);

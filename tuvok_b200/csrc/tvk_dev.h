@@ -47,10 +47,10 @@ struct RayConsts {
   int32_t pipeline;     // this launch is a stage of the depth pipeline (k_raycast.cu PIPE)
   int32_t count;        // accumulate counters
   // device pointers
-  const void* pool;       // slot-linear brick pool
+  const void* pool;       // slot-linear brick pool, x-pair layout: element x = (voxel x, voxel x+1) (k_pool.cu)
   uint64_t slot_voxels;   // voxels per slot
   const uint32_t* meta;   // page table
-  const float4* tf;       // RGBA8 table as float4 (byte / 255.0f)
+  const uint32_t* tf;     // RGBA8 table (byte / 255.0f is formed per fetch, tvk_math.cuh unorm8x4)
   uint32_t* hash;         // miss-report table
   const float4* ray_start;   // resume position (in), ignored when first_pass
   const float4* start_color; // resume colour / normal (in)
@@ -86,7 +86,7 @@ struct ClassicConsts {
   float domain_scale[3], light_a[3], light_d[3], light_s[3], light_dir[3];
   float norm, trans_scale, gradient_scale, step_scale;
   uint32_t tf_w, tf_h;
-  const float4* tf;
+  const uint32_t* tf;
   int32_t nearest, count;
   uint32_t layout[3];               // bricks per axis of the LoD
   uint32_t total[3];                // slot strides (max brick size)
@@ -127,8 +127,10 @@ void launch_vis_level(uint32_t* meta, const double* minmax, const VisConsts& vc,
                       uint32_t* counts, cudaStream_t s);
 struct PageOp { uint32_t evict_id; uint32_t new_id; uint32_t slot; uint32_t pad; uint64_t src_off; uint32_t size[3]; uint32_t pad2; };
 void launch_page_meta(uint32_t* meta, const PageOp* ops, uint32_t n, cudaStream_t s);
-void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t n, uint64_t slot_bytes,
+void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t n, uint64_t slot_voxels,
                       uint32_t esize, const uint32_t total[3], int src_is_slot_layout, cudaStream_t s);
+// plain voxels of one pool slot (the first halves of its pairs) -> out (device)
+void launch_slot_unpair(const void* slot, void* out, uint64_t n_voxels, uint32_t esize, cudaStream_t s);
 void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s);
 
 // bricker (k_bricker.cu)

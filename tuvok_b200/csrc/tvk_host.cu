@@ -49,14 +49,6 @@ int fail(tvk_ctx* c, int code, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-// RGBA8 texel -> the float4 a GL_RGBA8 texture fetch returns (byte / 255.0f, IEEE division)
-std::vector<float4> tf_to_float(const uint8_t* rgba, size_t n) {
-  std::vector<float4> f(n);
-  for (size_t i = 0; i < n; i++)
-    f[i] = make_float4((float)rgba[4 * i] / 255.0f, (float)rgba[4 * i + 1] / 255.0f, (float)rgba[4 * i + 2] / 255.0f,
-                       (float)rgba[4 * i + 3] / 255.0f);
-  return f;
-}
 
 uint32_t esize_of(int dtype) { return dtype == TVK_U8 ? 1u : dtype == TVK_U16 ? 2u : 4u; }
 
@@ -125,8 +117,9 @@ void free_dataset(tvk_ctx* c) {
 }
 
 void free_pool(tvk_ctx* c) {
-  void* p[] = {c->pool_d, c->meta_d, c->slot_brick_d, c->counts_d, c->ops_d, c->stage_d, c->hash_d, c->miss_d, c->visited_d};
-  c->visited_d = nullptr;
+  void* p[] = {c->pool_d, c->meta_d, c->slot_brick_d, c->counts_d, c->ops_d, c->stage_d, c->hash_d, c->miss_d, c->visited_d,
+               c->unpair_d};
+  c->visited_d = nullptr; c->unpair_d = nullptr;
   for (void* q : p) if (q) cudaFree(q);
   if (c->stage_h) cudaFreeHost(c->stage_h);
   if (c->miss_h) cudaFreeHost(c->miss_h);
@@ -311,7 +304,7 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
     int rc = ensure_ops(ctx, ops.size());
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->ops_d, ops.data(), ops.size() * sizeof(PageOp), cudaMemcpyHostToDevice, ctx->stream));
-    launch_page_copy(ctx->pool_d, ctx->store_d, ctx->ops_d, (uint32_t)ops.size(), ctx->slot_bytes, ctx->esize,
+    launch_page_copy(ctx->pool_d, ctx->store_d, ctx->ops_d, (uint32_t)ops.size(), ctx->slot_voxels, ctx->esize,
                      ctx->brick, 1, ctx->stream);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
@@ -358,7 +351,7 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
     std::memcpy(hops, ops.data(), n * sizeof(PageOp));
     cudaMemcpyAsync(db, hb, n * ctx->slot_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
     cudaMemcpyAsync(dops, hops, n * sizeof(PageOp), cudaMemcpyHostToDevice, ctx->copy_stream);
-    launch_page_copy(ctx->pool_d, db, dops, (uint32_t)n, ctx->slot_bytes, ctx->esize, ctx->brick, 0, ctx->copy_stream);
+    launch_page_copy(ctx->pool_d, db, dops, (uint32_t)n, ctx->slot_voxels, ctx->esize, ctx->brick, 0, ctx->copy_stream);
     cudaEventRecord(done[h], ctx->copy_stream);
     pos += n;
     h ^= 1;
@@ -1170,12 +1163,10 @@ int tvk_set_tf1d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t n, uint64_t nz_lo, 
   if (ctx->tf1d_n != n) {
     if (ctx->tf1d_d) cudaFree(ctx->tf1d_d);
     ctx->tf1d_d = nullptr; ctx->tf1d_n = 0;
-    CU(cudaMalloc(&ctx->tf1d_d, (size_t)n * sizeof(float4)));
+    CU(cudaMalloc(&ctx->tf1d_d, (size_t)n * 4));
   }
-  {
-    std::vector<float4> f = tf_to_float(rgba, n);
-    CU(cudaMemcpy(ctx->tf1d_d, f.data(), f.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  }
+  // the table stays RGBA8 on the device, like the reference's GL_RGBA8 texture (GPUMemMan.cpp:398-401)
+  CU(cudaMemcpy(ctx->tf1d_d, rgba, (size_t)n * 4, cudaMemcpyHostToDevice));
   ctx->tf1d_n = n; ctx->tf1d_nz[0] = nz_lo; ctx->tf1d_nz[1] = nz_hi;
   ctx->tf_gen++;
   ctx->blank = true;
@@ -1189,12 +1180,9 @@ int tvk_set_tf2d(tvk_ctx* ctx, const uint8_t* rgba, uint32_t w, uint32_t h, cons
   if (ctx->tf2d_w != w || ctx->tf2d_h != h) {
     if (ctx->tf2d_d) cudaFree(ctx->tf2d_d);
     ctx->tf2d_d = nullptr; ctx->tf2d_w = ctx->tf2d_h = 0;
-    CU(cudaMalloc(&ctx->tf2d_d, (size_t)w * h * sizeof(float4)));
+    CU(cudaMalloc(&ctx->tf2d_d, (size_t)w * h * 4));
   }
-  {
-    std::vector<float4> f = tf_to_float(rgba, (size_t)w * h);
-    CU(cudaMemcpy(ctx->tf2d_d, f.data(), f.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  }
+  CU(cudaMemcpy(ctx->tf2d_d, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice));
   ctx->tf2d_w = w; ctx->tf2d_h = h;
   for (int i = 0; i < 4; i++) ctx->tf2d_nz[i] = nz[i];
   ctx->tf_gen++;
@@ -1226,8 +1214,11 @@ int tvk_create_pool(tvk_ctx* ctx, const uint32_t* pool_size) {
     return fail(ctx, TVK_ERR_INVALID, "Unable to create brick metadata texture, as it needs more than the max texture size");
   ctx->meta_count = (uint64_t)ctx->meta_dim[0] * ctx->meta_dim[1] * ctx->meta_dim[2];
   ctx->meta_h.assign(ctx->meta_count, TVK_BI_MISSING);
+  // The pool is stored in the x-pair layout (k_pool.cu: element x = (voxel x, voxel x+1)): 2 * slot_bytes per slot.  The
+  // pool is still SIZED in voxels exactly as the reference sizes its atlas (same slot count and page table for the same
+  // budget); the second copy of each voxel is the price of halving the traversal kernel's load count.
   // one extra slot of padding so a vector load at the very end never leaves the allocation
-  CU(cudaMalloc(&ctx->pool_d, ((uint64_t)ctx->n_slots + 1) * ctx->slot_bytes));
+  CU(cudaMalloc(&ctx->pool_d, ((uint64_t)ctx->n_slots + 1) * 2 * ctx->slot_bytes));
   CU(cudaMalloc(&ctx->meta_d, ctx->meta_count * 4));
   CU(cudaMalloc(&ctx->slot_brick_d, (size_t)ctx->n_slots * 4));
   CU(cudaMalloc(&ctx->counts_d, 4 * sizeof(uint32_t)));
@@ -1237,7 +1228,7 @@ int tvk_create_pool(tvk_ctx* ctx, const uint32_t* pool_size) {
   // against the legacy NULL stream -- the first upload below (either stream) must not overtake a multi-GB memset.
   CU(cudaMemsetAsync(ctx->meta_d, 0, ctx->meta_count * 4, ctx->stream));
   CU(cudaMemsetAsync(ctx->slot_brick_d, 0xFF, (size_t)ctx->n_slots * 4, ctx->stream));
-  CU(cudaMemsetAsync(ctx->pool_d, 0, ((uint64_t)ctx->n_slots + 1) * ctx->slot_bytes, ctx->stream));
+  CU(cudaMemsetAsync(ctx->pool_d, 0, ((uint64_t)ctx->n_slots + 1) * 2 * ctx->slot_bytes, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   // miss-report table (GLGridLeaper::InitHashTable, GLGridLeaper.cpp:266-291)
   ctx->hash_size = ctx->cfg.hash_table_size;
@@ -1309,8 +1300,13 @@ int tvk_get_slots(tvk_ctx* ctx, int32_t* brick_ids, uint64_t* times, uint32_t* p
 int tvk_read_pool_slot(tvk_ctx* ctx, uint32_t slot, void* dst, size_t cap) {
   if (!ctx || !dst || !ctx->have_pool || slot >= ctx->n_slots || cap < ctx->slot_bytes)
     return fail(ctx, TVK_ERR_INVALID, "bad slot / buffer");
+  // the plain voxels of the slot: the first halves of its pairs, gathered on the device
+  if (!ctx->unpair_d) CU(cudaMalloc(&ctx->unpair_d, ctx->slot_bytes));
+  launch_slot_unpair((unsigned char*)ctx->pool_d + (uint64_t)slot * 2 * ctx->slot_bytes, ctx->unpair_d, ctx->slot_voxels, ctx->esize,
+                     ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(dst, ctx->unpair_d, ctx->slot_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpy(dst, (unsigned char*)ctx->pool_d + (uint64_t)slot * ctx->slot_bytes, ctx->slot_bytes, cudaMemcpyDeviceToHost));
   return TVK_OK;
 }
 

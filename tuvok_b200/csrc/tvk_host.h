@@ -98,8 +98,8 @@ struct tvk_ctx {
   uint64_t slot_voxels = 0, slot_bytes = 0;
 
   // ---- transfer functions ----
-  float4* tf1d_d = nullptr; uint32_t tf1d_n = 0; uint64_t tf1d_nz[2] = {0, 0};
-  float4* tf2d_d = nullptr; uint32_t tf2d_w = 0, tf2d_h = 0; uint64_t tf2d_nz[4] = {0, 0, 0, 0};
+  uint32_t* tf1d_d = nullptr; uint32_t tf1d_n = 0; uint64_t tf1d_nz[2] = {0, 0};
+  uint32_t* tf2d_d = nullptr; uint32_t tf2d_w = 0, tf2d_h = 0; uint64_t tf2d_nz[4] = {0, 0, 0, 0};
 
   // ---- pool ----
   bool have_pool = false;
@@ -166,6 +166,7 @@ struct tvk_ctx {
   unsigned long long* counters_h = nullptr;
   uint32_t* visited_d = nullptr;
   std::vector<uint32_t> visited_h;
+  void* unpair_d = nullptr;        // one slot of plain voxels (tvk_read_pool_slot)
 };
 
 #endif
