@@ -103,15 +103,16 @@ __global__ void page_meta_kernel(uint32_t* meta, const PageOp* __restrict__ ops,
 // traversal kernel fetches both operands of every x-lerp of its trilinear filters with one load (16 loads per sample in
 // the 7-tap modes instead of 32).  The second half of a pair is exactly what the plain layout holds at x+1 -- also where
 // that texel is stale (a smaller brick written over a larger one leaves the old texels in place, as glTexSubImage3D
-// does in the reference's atlas) -- so every filter footprint reads the values it read before.
+// does in the reference's atlas) -- so every filter footprint reads the values it read before.  8- and 16-bit volumes
+// only: float pools stay plain (tvk_math.cuh PairOf).
 template <typename T, typename W>
 __device__ __forceinline__ W make_pair(T lo, T hi);
 template <> __device__ __forceinline__ uint16_t make_pair<uint8_t, uint16_t>(uint8_t lo, uint8_t hi) { return (uint16_t)(lo | ((uint16_t)hi << 8)); }
 template <> __device__ __forceinline__ uint32_t make_pair<uint16_t, uint32_t>(uint16_t lo, uint16_t hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
-template <> __device__ __forceinline__ float2 make_pair<float, float2>(float lo, float hi) { return make_float2(lo, hi); }
+template <> __device__ __forceinline__ float make_pair<float, float>(float lo, float) { return lo; }   // float pools stay plain
 __device__ __forceinline__ uint8_t first_of(uint16_t w) { return (uint8_t)(w & 0xffu); }
 __device__ __forceinline__ uint16_t first_of(uint32_t w) { return (uint16_t)(w & 0xffffu); }
-__device__ __forceinline__ float first_of(float2 w) { return w.x; }
+__device__ __forceinline__ float first_of(float w) { return w; }
 
 template <typename T, typename W>
 __global__ void page_copy_kernel(W* pool, const T* __restrict__ store, const PageOp* __restrict__ ops, uint64_t slot_voxels,
@@ -196,14 +197,14 @@ void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t
     page_copy_kernel<uint16_t, uint32_t><<<n, 256, 0, s>>>((uint32_t*)pool, (const uint16_t*)store, ops, slot_voxels, total[0],
                                                            total[1], total[2], src_is_slot_layout);
   else
-    page_copy_kernel<float, float2><<<n, 256, 0, s>>>((float2*)pool, (const float*)store, ops, slot_voxels, total[0], total[1],
-                                                      total[2], src_is_slot_layout);
+    page_copy_kernel<float, float><<<n, 256, 0, s>>>((float*)pool, (const float*)store, ops, slot_voxels, total[0], total[1],
+                                                     total[2], src_is_slot_layout);
 }
 void launch_slot_unpair(const void* slot, void* out, uint64_t n_voxels, uint32_t esize, cudaStream_t s) {
   const unsigned g = (unsigned)std::min<uint64_t>((n_voxels + 255) / 256, 1184);
   if (esize == 1) slot_unpair_kernel<uint8_t, uint16_t><<<g, 256, 0, s>>>((const uint16_t*)slot, (uint8_t*)out, n_voxels);
   else if (esize == 2) slot_unpair_kernel<uint16_t, uint32_t><<<g, 256, 0, s>>>((const uint32_t*)slot, (uint16_t*)out, n_voxels);
-  else slot_unpair_kernel<float, float2><<<g, 256, 0, s>>>((const float2*)slot, (float*)out, n_voxels);
+  else slot_unpair_kernel<float, float><<<g, 256, 0, s>>>((const float*)slot, (float*)out, n_voxels);
 }
 void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s) {
   hash_compact_kernel<<<grid_for(n, 256), 256, 0, s>>>(hash, n, out_list, out_count);

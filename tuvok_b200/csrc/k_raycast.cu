@@ -44,9 +44,9 @@ struct BrickRef {
   uint32_t slot;         // linear pool coordinate (slot s starts at voxel s * slot_voxels)
 };
 
-// Filter footprint of one sample position inside a slot.  The pool is in the x-pair layout (k_pool.cu): element x of a
-// row is the pair (voxel x, voxel x+1).
-//   FAST  (linear filter, ghost >= 2): the 4x4x4 neighbourhood [X-1..X+2]^3 always lies inside the
+// Filter footprint of one sample position inside a slot.  Integer pools are in the x-pair layout (k_pool.cu): element x
+// of a row is the pair (voxel x, voxel x+1).
+//   FastFoot (linear filter, ghost >= 2): the 4x4x4 neighbourhood [X-1..X+2]^3 always lies inside the
 //         slot, so one clamped centre address + uniform row strides address everything.  A centre row of the
 //         footprint (voxels X-1..X+2) is the two pairs at X-1 and X+1, a side row (voxels X, X+1) the pair at X:
 //         16 loads fetch the 32 distinct voxels of the 7 overlapping trilinear footprints (4 loads for one footprint).
@@ -54,82 +54,55 @@ struct BrickRef {
 //         GLVolumePool.cpp:364-400), turning the addresses into immediate offsets.
 //         The lerp trees run on packed fp32 (two rows per instruction, tvk_math.cuh): every lerp has the operands and
 //         the rounding of tri(), so the result is bit-identical to seven independent tri() calls.
-//   !FAST (nearest filter or ghost < 2): texel indices are taken in the reference's VIRTUAL ATLAS
+//         The footprint is DATA (the loaded words + the three filter fractions): the kernel fetches the footprint of a
+//         ray's NEXT sample before it shades the current one, so the loads' L1 / L2 latency is covered by a whole
+//         sample of arithmetic instead of stalling the warp (software pipelining; the launch is latency-bound at four
+//         resident warps per scheduler).
+//   SlowFoot (nearest filter or ghost < 2): texel indices are taken in the reference's VIRTUAL ATLAS
 //         (capacity * brick texels, clamp-to-edge at the atlas border like GL_CLAMP_TO_EDGE) and then
 //         split into (slot, texel-in-slot), so taps that leave a brick with a 1-voxel ghost read the
 //         atlas neighbour exactly as the reference's 3D texture does.  One voxel per load (the pair's first half).
-template <typename T, bool FAST, int BS>
-struct Foot {
+template <typename T, int BS, bool GRAD>
+struct FastFoot {
   typedef typename PairOf<T>::W W;
+  typedef typename PairOf<T>::V V;
   typedef PairCvt<T> CV;
-  const W* c;            // FAST: pair element (X, Y, Z); !FAST: first element of the pool
-  uint64_t xo[4], yo[4], zo[4];   // !FAST: element offsets (slot part + in-slot part) of X-1..X+2 etc.
+  V w[GRAD ? 16 : 4];
   float fx, fy, fz;
-  int sy, sz;            // row / slice stride in elements
-  bool nearest;
 
-  __device__ __forceinline__ void set(const RayConsts& P, const W* pool, const W* vox, uint32_t ox, uint32_t oy,
-                                      uint32_t oz, f3 tc) {
-    int X, Y, Z;
-    nearest = !FAST && P.nearest;
-    if (nearest) {
-      X = (int)floorf(tc.x * P.pool_size_f[0]);
-      Y = (int)floorf(tc.y * P.pool_size_f[1]);
-      Z = (int)floorf(tc.z * P.pool_size_f[2]);
-      fx = fy = fz = 0.0f;
+  __device__ __forceinline__ void fetch(const RayConsts& P, const W* vox, uint32_t ox, uint32_t oy, uint32_t oz, f3 tc) {
+    const float ux = fmaf(tc.x, P.pool_size_f[0], -0.5f);
+    const float uy = fmaf(tc.y, P.pool_size_f[1], -0.5f);
+    const float uz = fmaf(tc.z, P.pool_size_f[2], -0.5f);
+    const float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
+    fx = ux - x0; fy = uy - y0; fz = uz - z0;
+    int X = (int)x0 - (int)ox, Y = (int)y0 - (int)oy, Z = (int)z0 - (int)oz;
+    const int sy = BS ? BS : (int)P.total[0];
+    const int sz = BS ? BS * BS : (int)(P.total[0] * P.total[1]);
+    X = min(max(X, 1), (BS ? BS : (int)P.total[0]) - 3);
+    Y = min(max(Y, 1), (BS ? BS : (int)P.total[1]) - 3);
+    Z = min(max(Z, 1), (BS ? BS : (int)P.total[2]) - 3);
+    const W* c = vox + (X + Y * sy + Z * sz);
+    // the pair at element offset (i, j, k) from the footprint origin (immediate offsets when BS is baked in)
+    auto ld = [&](int i, int j, int k) -> V { return load_pair(c + (i + j * sy + k * sz)); };
+    if (!GRAD) {
+      w[0] = ld(0, 0, 0); w[1] = ld(0, 1, 0); w[2] = ld(0, 0, 1); w[3] = ld(0, 1, 1);   // rows (y, z)
     } else {
-      const float ux = fmaf(tc.x, P.pool_size_f[0], -0.5f);
-      const float uy = fmaf(tc.y, P.pool_size_f[1], -0.5f);
-      const float uz = fmaf(tc.z, P.pool_size_f[2], -0.5f);
-      const float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
-      fx = ux - x0; fy = uy - y0; fz = uz - z0;
-      X = (int)x0; Y = (int)y0; Z = (int)z0;
-    }
-    sy = BS ? BS : (int)P.total[0];
-    sz = BS ? BS * BS : (int)(P.total[0] * P.total[1]);
-    if (FAST) {
-      X -= (int)ox; Y -= (int)oy; Z -= (int)oz;
-      X = min(max(X, 1), (BS ? BS : (int)P.total[0]) - 3);
-      Y = min(max(Y, 1), (BS ? BS : (int)P.total[1]) - 3);
-      Z = min(max(Z, 1), (BS ? BS : (int)P.total[2]) - 3);
-      c = vox + (X + Y * sy + Z * sz);
-    } else {
-      c = pool;
-      const int ax = (int)(P.capacity[0] * P.total[0]) - 1, ay = (int)(P.capacity[1] * P.total[1]) - 1,
-                az = (int)(P.capacity[2] * P.total[2]) - 1;
-      const uint64_t slot_y = (uint64_t)P.capacity[0] * P.slot_voxels, slot_z = slot_y * P.capacity[1];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const uint32_t gx = (uint32_t)min(max(X - 1 + i, 0), ax), gy = (uint32_t)min(max(Y - 1 + i, 0), ay),
-                       gz = (uint32_t)min(max(Z - 1 + i, 0), az);
-        xo[i] = (uint64_t)(gx / P.total[0]) * P.slot_voxels + gx % P.total[0];
-        yo[i] = (uint64_t)(gy / P.total[1]) * slot_y + (uint64_t)(gy % P.total[1]) * (uint32_t)sy;
-        zo[i] = (uint64_t)(gz / P.total[2]) * slot_z + (uint64_t)(gz % P.total[2]) * (uint32_t)sz;
+      for (int j = 0; j < 2; j++) {   // centre rows y = j: pairs at x = -1 and x = +1, z = 0 / 1
+        w[4 * j + 0] = ld(-1, j, 0); w[4 * j + 1] = ld(-1, j, 1); w[4 * j + 2] = ld(1, j, 0); w[4 * j + 3] = ld(1, j, 1);
       }
+      w[8] = ld(0, -1, 0); w[9] = ld(0, -1, 1); w[10] = ld(0, 2, 0); w[11] = ld(0, 2, 1);   // rows y = -1, y = 2
+#pragma unroll
+      for (int j = 0; j < 2; j++) { w[12 + 2 * j] = ld(0, j, -1); w[13 + 2 * j] = ld(0, j, 2); }   // rows z = -1, z = 2
     }
   }
-  // FAST: the pair at element offset (i, j, k) from the footprint origin
-  __device__ __forceinline__ W ld(int i, int j, int k) const {
-    if (BS) return __ldg(c + (i + j * BS + k * BS * BS));   // immediate offsets
-    return __ldg(c + (i + j * sy + k * sz));
-  }
-  // !FAST: voxel at texel offset (i, j, k) in [-1, 2]^3 from the footprint origin
-  __device__ __forceinline__ float v(int i, int j, int k) const {
-    return first_voxel<T>(__ldg(c + (xo[1 + i] + yo[1 + j] + zo[1 + k])));
-  }
-  // !FAST: texture(volumePool, coords).r at texel offset (dx,dy,dz)
-  __device__ __forceinline__ float tap_slow(const RayConsts& P, int dx, int dy, int dz) const {
-    if (nearest) return v(dx, dy, dz) * P.norm;
-    return tri(v(dx, dy, dz), v(dx + 1, dy, dz), v(dx, dy + 1, dz), v(dx + 1, dy + 1, dz), v(dx, dy, dz + 1),
-               v(dx + 1, dy, dz + 1), v(dx, dy + 1, dz + 1), v(dx + 1, dy + 1, dz + 1), fx, fy, fz) * P.norm;
-  }
-  // texture(volumePool, coords).r at the sample position
+  // texture(volumePool, coords).r at the sample position (!GRAD footprints)
   __device__ __forceinline__ float centre(const RayConsts& P) const {
-    if (!FAST) return tap_slow(P, 0, 0, 0);
+    static_assert(!GRAD, "a gradient footprint has no x = 0 pairs: use sample_with_gradient");
     // rows (y, z) of the footprint: pair = (voxel X, voxel X+1); the two z-slices share an instruction
-    const W w00 = ld(0, 0, 0), w10 = ld(0, 1, 0), w01 = ld(0, 0, 1), w11 = ld(0, 1, 1);   // w[y][z]
-    const f2 x0 = xlerp2<CV::kBiased>(F2(CV::lo(w00), CV::lo(w01)), F2(CV::hi(w00), CV::hi(w01)), fx);   // y = 0, z = (0, 1)
-    const f2 x1 = xlerp2<CV::kBiased>(F2(CV::lo(w10), CV::lo(w11)), F2(CV::hi(w10), CV::hi(w11)), fx);   // y = 1
+    const f2 x0 = xlerp2<CV::kBiased>(F2(CV::lo(w[0]), CV::lo(w[2])), F2(CV::hi(w[0]), CV::hi(w[2])), fx);   // y = 0, z = (0, 1)
+    const f2 x1 = xlerp2<CV::kBiased>(F2(CV::lo(w[1]), CV::lo(w[3])), F2(CV::hi(w[1]), CV::hi(w[3])), fx);   // y = 1
     const f2 y = lerp2(x0, x1, fy);
     return lerp1(y.x, y.y, fz) * P.norm;
   }
@@ -137,14 +110,6 @@ struct Foot {
   // fetched at -delta) from the 32 distinct voxels of the 7 overlapping footprints
   __device__ __forceinline__ void sample_with_gradient(const RayConsts& P, float& data, f3& grad) const {
     const float n = P.norm;
-    if (!FAST) {
-      data = tap_slow(P, 0, 0, 0);
-      const float xp = tap_slow(P, 1, 0, 0), xm = tap_slow(P, -1, 0, 0);
-      const float yp = tap_slow(P, 0, -1, 0), ym = tap_slow(P, 0, 1, 0);
-      const float zp = tap_slow(P, 0, 0, 1), zm = tap_slow(P, 0, 0, -1);
-      grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
-      return;
-    }
     constexpr bool B = CV::kBiased;
     // ---- x-lerps.  Centre rows (y, z in {0,1}): voxels m, a, b, p at x = -1, 0, 1, 2 from the pairs at -1 and +1;
     // the rows z = 0 and z = 1 of one y share the packed instructions.  xm / xc / xp = the x-lerps of the taps at
@@ -152,7 +117,7 @@ struct Foot {
     f2 xm[2], xc[2], xp[2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-      const W l0 = ld(-1, j, 0), l1 = ld(-1, j, 1), h0 = ld(1, j, 0), h1 = ld(1, j, 1);
+      const V l0 = w[4 * j + 0], l1 = w[4 * j + 1], h0 = w[4 * j + 2], h1 = w[4 * j + 3];
       const f2 m = F2(CV::lo(l0), CV::lo(l1)), a = F2(CV::hi(l0), CV::hi(l1));
       const f2 b = F2(CV::lo(h0), CV::lo(h1)), p = F2(CV::hi(h0), CV::hi(h1));
       xm[j] = xlerp2<B>(m, a, fx);
@@ -160,17 +125,12 @@ struct Foot {
       xp[j] = xlerp2<B>(b, p, fx);
     }
     // side rows: y = -1 and y = 2 (z = 0, 1 packed), z = -1 and z = 2 (packed with each other, per y)
-    f2 xyl, xyh, xz[2];
-    {
-      const W a0 = ld(0, -1, 0), a1 = ld(0, -1, 1), b0 = ld(0, 2, 0), b1 = ld(0, 2, 1);
-      xyl = xlerp2<B>(F2(CV::lo(a0), CV::lo(a1)), F2(CV::hi(a0), CV::hi(a1)), fx);   // row y = -1, z = (0, 1)
-      xyh = xlerp2<B>(F2(CV::lo(b0), CV::lo(b1)), F2(CV::hi(b0), CV::hi(b1)), fx);   // row y = 2
-    }
+    const f2 xyl = xlerp2<B>(F2(CV::lo(w[8]), CV::lo(w[9])), F2(CV::hi(w[8]), CV::hi(w[9])), fx);       // row y = -1, z = (0, 1)
+    const f2 xyh = xlerp2<B>(F2(CV::lo(w[10]), CV::lo(w[11])), F2(CV::hi(w[10]), CV::hi(w[11])), fx);   // row y = 2
+    f2 xz[2];
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const W lo_ = ld(0, j, -1), hi_ = ld(0, j, 2);
-      xz[j] = xlerp2<B>(F2(CV::lo(lo_), CV::lo(hi_)), F2(CV::hi(lo_), CV::hi(hi_)), fx);   // row y = j, z = (-1, 2)
-    }
+    for (int j = 0; j < 2; j++)   // row y = j, z = (-1, 2)
+      xz[j] = xlerp2<B>(F2(CV::lo(w[12 + 2 * j]), CV::lo(w[13 + 2 * j])), F2(CV::hi(w[12 + 2 * j]), CV::hi(w[13 + 2 * j])), fx);
     // ---- y-lerps, lanes = z slices
     const f2 yc = lerp2(xc[0], xc[1], fy);       // centre tap, z = (0, 1)
     const f2 yxm = lerp2(xm[0], xm[1], fy);      // tap at x-1
@@ -185,6 +145,79 @@ struct Foot {
     const float tzp = lerp1(yc.y, yz.y, fz) * n;     // tap at z+1: slices z = 1, 2
     const float tzm = lerp1(yz.x, yc.x, fz) * n;     // tap at z-1: slices z = -1, 0
     grad = F3((txm - txp) / 2.0f, (typ - tym) / 2.0f, (tzm - tzp) / 2.0f);
+  }
+};
+
+template <typename T>
+struct SlowFoot {
+  typedef typename PairOf<T>::W W;
+  const W* c;            // first element of the pool
+  uint64_t xo[4], yo[4], zo[4];   // element offsets (slot part + in-slot part) of X-1..X+2 etc.
+  float fx, fy, fz;
+  bool nearest;
+
+  __device__ __forceinline__ void fetch(const RayConsts& P, const W* pool, f3 tc) {
+    int X, Y, Z;
+    nearest = P.nearest != 0;
+    if (nearest) {
+      X = (int)floorf(tc.x * P.pool_size_f[0]);
+      Y = (int)floorf(tc.y * P.pool_size_f[1]);
+      Z = (int)floorf(tc.z * P.pool_size_f[2]);
+      fx = fy = fz = 0.0f;
+    } else {
+      const float ux = fmaf(tc.x, P.pool_size_f[0], -0.5f);
+      const float uy = fmaf(tc.y, P.pool_size_f[1], -0.5f);
+      const float uz = fmaf(tc.z, P.pool_size_f[2], -0.5f);
+      const float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
+      fx = ux - x0; fy = uy - y0; fz = uz - z0;
+      X = (int)x0; Y = (int)y0; Z = (int)z0;
+    }
+    const uint32_t sy = P.total[0], sz = P.total[0] * P.total[1];
+    c = pool;
+    const int ax = (int)(P.capacity[0] * P.total[0]) - 1, ay = (int)(P.capacity[1] * P.total[1]) - 1,
+              az = (int)(P.capacity[2] * P.total[2]) - 1;
+    const uint64_t slot_y = (uint64_t)P.capacity[0] * P.slot_voxels, slot_z = slot_y * P.capacity[1];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t gx = (uint32_t)min(max(X - 1 + i, 0), ax), gy = (uint32_t)min(max(Y - 1 + i, 0), ay),
+                     gz = (uint32_t)min(max(Z - 1 + i, 0), az);
+      xo[i] = (uint64_t)(gx / P.total[0]) * P.slot_voxels + gx % P.total[0];
+      yo[i] = (uint64_t)(gy / P.total[1]) * slot_y + (uint64_t)(gy % P.total[1]) * sy;
+      zo[i] = (uint64_t)(gz / P.total[2]) * slot_z + (uint64_t)(gz % P.total[2]) * sz;
+    }
+  }
+  // voxel at texel offset (i, j, k) in [-1, 2]^3 from the footprint origin
+  __device__ __forceinline__ float v(int i, int j, int k) const {
+    return first_voxel<T>(__ldg(c + (xo[1 + i] + yo[1 + j] + zo[1 + k])));
+  }
+  // texture(volumePool, coords).r at texel offset (dx,dy,dz)
+  __device__ __forceinline__ float tap(const RayConsts& P, int dx, int dy, int dz) const {
+    if (nearest) return v(dx, dy, dz) * P.norm;
+    return tri(v(dx, dy, dz), v(dx + 1, dy, dz), v(dx, dy + 1, dz), v(dx + 1, dy + 1, dz), v(dx, dy, dz + 1),
+               v(dx + 1, dy, dz + 1), v(dx, dy + 1, dz + 1), v(dx + 1, dy + 1, dz + 1), fx, fy, fz) * P.norm;
+  }
+  __device__ __forceinline__ float centre(const RayConsts& P) const { return tap(P, 0, 0, 0); }
+  __device__ __forceinline__ void sample_with_gradient(const RayConsts& P, float& data, f3& grad) const {
+    data = tap(P, 0, 0, 0);
+    const float xp = tap(P, 1, 0, 0), xm = tap(P, -1, 0, 0);
+    const float yp = tap(P, 0, -1, 0), ym = tap(P, 0, 1, 0);
+    const float zp = tap(P, 0, 0, 1), zm = tap(P, 0, 0, -1);
+    grad = F3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
+  }
+};
+
+// one footprint type for the kernel: GRAD selects what a FastFoot holds (the slow path loads at use)
+template <typename T, bool FAST, int BS, bool GRAD>
+struct Foot {
+  typedef typename PairOf<T>::W W;
+  FastFoot<T, BS, GRAD> fast;
+  SlowFoot<T> slow;
+  __device__ __forceinline__ void fetch(const RayConsts& P, const W* pool, const W* vox, uint32_t ox, uint32_t oy, uint32_t oz, f3 tc) {
+    if (FAST) fast.fetch(P, vox, ox, oy, oz, tc); else slow.fetch(P, pool, tc);
+  }
+  __device__ __forceinline__ float centre(const RayConsts& P) const { return FAST ? fast.centre(P) : slow.centre(P); }
+  __device__ __forceinline__ void sample_with_gradient(const RayConsts& P, float& data, f3& grad) const {
+    if (FAST) fast.sample_with_gradient(P, data, grad); else slow.sample_with_gradient(P, data, grad);
   }
 };
 
@@ -402,9 +435,10 @@ constexpr int kFetchLanes = TVK_FETCH_LANES;
 #ifndef TVK_MIN_BLOCKS
 #define TVK_MIN_BLOCKS 8
 #endif
-#ifndef TVK_ILP
-#define TVK_ILP 1
+#ifndef TVK_PREFETCH
+#define TVK_PREFETCH 0
 #endif
+constexpr bool kPrefetch = TVK_PREFETCH != 0;   // fetch the next sample's footprint before shading the current one
 // CTA = TVK_WX x TVK_WY warps, each an 8x4 pixel tile (CTA covers 8*WX x 4*WY pixels)
 #ifndef TVK_WX
 #define TVK_WX 1
@@ -413,7 +447,6 @@ constexpr int kFetchLanes = TVK_FETCH_LANES;
 #define TVK_WY 2
 #endif
 constexpr int kWX = TVK_WX, kWY = TVK_WY, kThreads = 32 * TVK_WX * TVK_WY;
-constexpr int kIlp = TVK_ILP;   // samples per lane per loop turn (1 or 2)
 #ifndef TVK_SKIP_CLEAR
 #define TVK_SKIP_CLEAR 1
 #endif
@@ -583,6 +616,9 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
     f3 pc = c.entry, b_trans = c.entry, b_inv = c.entry;
     uint32_t b_ox = 0, b_oy = 0, b_oz = 0;
     const W* vox = pool;
+    constexpr bool GRAD = !ISO && (MODE == 1 || LIT);   // what a sample needs: the 7-tap footprint or the centre tap
+    Foot<T, FAST, BS, GRAD> cur;   // footprint of the sample at pc, fetched one turn ahead
+    bool cur_ok = false;
     unsigned long long pend = 0;   // COUNT: brick visits of the chain that the sampling has not reached yet
 
     if (kPark) { park_const(c, park, tid); park_var(c, park, tid); }
@@ -671,6 +707,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
         steps_left = (int)seg_u[4][tid];
         b_partial = seg_u[5][tid] != 0u;
         have_next = false;
+        cur_ok = false;
         if (COUNT) {
           n_bricks += pend; pend = 0;
           if (P.visited) { const uint32_t id = seg_u[6][tid]; atomicOr(P.visited + (id >> 5), 1u << (id & 31)); }
@@ -684,130 +721,110 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
         n_alive_iters += ray_live ? 1 : 0;
         if (__ffs(__activemask()) - 1 == (tid & 31)) n_warp_iters++;
       }
-      // ---- sample phase: TVK_ILP samples for every lane that is inside a brick ----
+      // ---- sample phase: one sample for every lane that is inside a brick ----
       if (ray_live && steps_left > 0) {
         bool terminated = false;
-        int taken = 1;
-        if (!ISO) {
-          // ComputeColorFromVolume + OpacityCorrectColor at pool position q
-          auto shade = [&](f3 q) -> f4 {
-            Foot<T, FAST, BS> f;
-            f.set(P, pool, vox, b_ox, b_oy, b_oz, q);
+        // software pipeline: the footprint of THIS sample was fetched during the previous turn (cur_ok), the one of the
+        // next sample of the brick is fetched now, before this sample's arithmetic, so its load latency is covered
+        if (!kPrefetch || !FAST || !cur_ok) cur.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc);
+        const f3 pc_next = add3(pc, vdir);
+        const bool pf = kPrefetch && FAST && steps_left > 1;
+        Foot<T, FAST, BS, GRAD> nxt;
+        if (pf) nxt.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc_next);
+        bool mine = true;
+        if (b_partial) {
+          const f3 mq = mul3(sub3(pc, b_trans), b_inv);
+          mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
+                 mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
+          if (PIPE && !ISO && !mine) {
+            // a brick of a coarser LoD straddles the slab's far side: the ray is handed on AT the side, not
+            // behind the brick, so the next stage takes the brick's remaining samples
+            const bool gone = (c.dir.x > 0.0f && mq.x >= P.sh_hi[0]) || (c.dir.x < 0.0f && mq.x < P.sh_lo[0]) ||
+                              (c.dir.y > 0.0f && mq.y >= P.sh_hi[1]) || (c.dir.y < 0.0f && mq.y < P.sh_lo[1]) ||
+                              (c.dir.z > 0.0f && mq.z >= P.sh_hi[2]) || (c.dir.z < 0.0f && mq.z < P.sh_lo[2]);
+            if (gone) {
+              const float tq = len3(sub3(mq, c.entry)) / c.ray_len;
+              handoff = true;
+              hand_pos.x = mq.x; hand_pos.y = mq.y; hand_pos.z = mq.z;
+              hand_pos.w = c.entry_depth * (1.0f - tq) + c.exit_depth * tq;
+              terminated = true;   // leaves the loop; TerminateRay sees alpha <= 0.99 and hands the ray on
+            }
+          }
+        }
+        if constexpr (!ISO) {
+          if (mine) {
+            if (COUNT) n_samples++;
+            // ComputeColorFromVolume + OpacityCorrectColor at pool position pc
             f4 col;
-            // A sample whose transfer-function alpha is exactly 0 leaves the ray unchanged bit for bit
-            // (UnderCompositing adds colour * (1-a) * 0 = 0 to every channel; table colours and lit colours are
-            // finite, and opacity correction maps 0 to 0), so its normal, lighting -- and with a 1D table its six
-            // gradient taps -- are not computed.  The shader cannot branch this cheaply; the result is identical.
-            if (MODE == 0 && !LIT) {
-              const float data = f.centre(P);
-              col = tf_lookup(P, data * P.trans_scale, 0.0f);
-            } else if (MODE == 0) {
-              col = tf_lookup(P, f.centre(P) * P.trans_scale, 0.0f);
-              if (kSkipClear && col.w == 0.0f) return col;
+            bool clear = false;
+            if constexpr (MODE == 0 && !LIT) {
+              col = tf_lookup(P, cur.centre(P) * P.trans_scale, 0.0f);
+            } else if constexpr (MODE == 0) {
               float data; f3 g;
-              f.sample_with_gradient(P, data, g);
-              f3 n = mul3(g, dscale);   // ComputeNormal
-              const float l = len3(n);
-              if (l > 0.0f) n = scl3(n, 1.0f / l);
-              const f3 mp = mul3(sub3(q, b_trans), b_inv);
-              const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
-              col.x = lit.x; col.y = lit.y; col.z = lit.z;
+              cur.sample_with_gradient(P, data, g);
+              col = tf_lookup(P, data * P.trans_scale, 0.0f);
+              // A sample whose transfer-function alpha is exactly 0 leaves the ray unchanged bit for bit
+              // (UnderCompositing adds colour * (1-a) * 0 = 0 to every channel; table colours and lit colours are
+              // finite, and opacity correction maps 0 to 0), so its normal and lighting are not computed when the
+              // whole warp agrees.  The shader cannot branch this cheaply; the result is identical.
+              clear = kSkipClear && col.w == 0.0f;
+              if (!clear) {
+                f3 n = mul3(g, dscale);   // ComputeNormal
+                const float l = len3(n);
+                if (l > 0.0f) n = scl3(n, 1.0f / l);
+                const f3 mp = mul3(sub3(pc, b_trans), b_inv);
+                const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
+                col.x = lit.x; col.y = lit.y; col.z = lit.z;
+              }
             } else {
               float data; f3 g;
-              f.sample_with_gradient(P, data, g);
+              cur.sample_with_gradient(P, data, g);
               const float gm = len3(g);
               col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
               if (LIT) {
-                // the normal, the view vector and both light terms do not depend on the table entry: they are computed
-                // while the fetch is in flight, and the colour enters in the last three operations only
-                const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
-                const f3 n = mul3(dscale, gn);
-                const f3 mp = mul3(sub3(q, b_trans), b_inv);
-                float dl, sp;
-                light_terms(eye_m, mp, n, ldir, dl, sp);
-                const f3 lit = light_apply(la, mul3(F3(col.x, col.y, col.z), ld), ls, dl, sp);
-                col.x = lit.x; col.y = lit.y; col.z = lit.z;
-              }
-            }
-            col.w = opacity_correct(P, col.w);
-            return col;
-          };
-          auto blend = [&](f4 col) {   // UnderCompositing
-            const float oma = 1.0f - acc.w;
-            acc.x = fmaf(col.x * oma, col.w, acc.x);
-            acc.y = fmaf(col.y * oma, col.w, acc.y);
-            acc.z = fmaf(col.z * oma, col.w, acc.z);
-            acc.w = fmaf(col.w, oma, acc.w);
-          };
-          if (kIlp == 2 && !b_partial) {
-            // two consecutive samples of the ray are classified and shaded as independent instruction streams
-            // (the second one speculatively) and composited in order; a lane on the last sample of its brick
-            // shades that sample twice and drops the copy
-            const bool two = steps_left >= 2;
-            const f4 c0 = shade(pc);
-            const f4 c1 = shade(two ? add3(pc, vdir) : pc);
-            blend(c0);
-            if (acc.w > 0.99f) terminated = true;
-            else if (two) {
-              blend(c1);
-              taken = 2;
-              if (acc.w > 0.99f) terminated = true;
-            }
-            if (COUNT) n_samples += (unsigned long long)taken;
-          } else {
-            bool mine = true;
-            if (b_partial) {
-              const f3 mq = mul3(sub3(pc, b_trans), b_inv);
-              mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
-                     mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
-              if (PIPE && !mine) {
-                // a brick of a coarser LoD straddles the slab's far side: the ray is handed on AT the side, not
-                // behind the brick, so the next stage takes the brick's remaining samples
-                const bool gone = (c.dir.x > 0.0f && mq.x >= P.sh_hi[0]) || (c.dir.x < 0.0f && mq.x < P.sh_lo[0]) ||
-                                  (c.dir.y > 0.0f && mq.y >= P.sh_hi[1]) || (c.dir.y < 0.0f && mq.y < P.sh_lo[1]) ||
-                                  (c.dir.z > 0.0f && mq.z >= P.sh_hi[2]) || (c.dir.z < 0.0f && mq.z < P.sh_lo[2]);
-                if (gone) {
-                  const float tq = len3(sub3(mq, c.entry)) / c.ray_len;
-                  handoff = true;
-                  hand_pos.x = mq.x; hand_pos.y = mq.y; hand_pos.z = mq.z;
-                  hand_pos.w = c.entry_depth * (1.0f - tq) + c.exit_depth * tq;
-                  terminated = true;   // leaves the loop; TerminateRay sees alpha <= 0.99 and hands the ray on
+                clear = kSkipClear && col.w == 0.0f;
+                if (!clear) {
+                  const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
+                  const f3 n = mul3(dscale, gn);
+                  const f3 mp = mul3(sub3(pc, b_trans), b_inv);
+                  float dl, sp;
+                  light_terms(eye_m, mp, n, ldir, dl, sp);
+                  const f3 lit = light_apply(la, mul3(F3(col.x, col.y, col.z), ld), ls, dl, sp);
+                  col.x = lit.x; col.y = lit.y; col.z = lit.z;
                 }
               }
             }
-            if (mine) {
-              if (COUNT) n_samples++;
-              blend(shade(pc));
+            if (!clear) {
+              col.w = opacity_correct(P, col.w);
+              // UnderCompositing
+              const float oma = 1.0f - acc.w;
+              acc.x = fmaf(col.x * oma, col.w, acc.x);
+              acc.y = fmaf(col.y * oma, col.w, acc.y);
+              acc.z = fmaf(col.z * oma, col.w, acc.z);
+              acc.w = fmaf(col.w, oma, acc.w);
               if (acc.w > 0.99f) terminated = true;
             }
           }
-        } else {
-          bool mine = true;
-          if (b_partial) {
-            const f3 mq = mul3(sub3(pc, b_trans), b_inv);
-            mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
-                   mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
-          }
-          if (mine) {
-          Foot<T, FAST, BS> f;
-          f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
+        } else if (mine) {   // isosurface march
           if (COUNT) n_samples++;
-          if (f.centre(P) >= P.isoval) {
+          if (cur.centre(P) >= P.isoval) {
             // RefineIsosurface
             f3 rd = F3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
             pc = sub3(pc, rd);
+            Foot<T, FAST, BS, false> rf;
 #pragma unroll 1
             for (int k = 0; k < 5; k++) {
               rd = F3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
-              f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
-              if (f.centre(P) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
+              rf.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc);
+              if (rf.centre(P) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
             }
             const f3 hp = mul3(sub3(pc, b_trans), b_inv);
             hit_pos = xform4(P.m2e, hp.x, hp.y, hp.z, 1.0f);
             hit_pos.w = 1.0f + 1.0f;   // color.r + 1
-            f.set(P, pool, vox, b_ox, b_oy, b_oz, pc);
+            Foot<T, FAST, BS, true> gf;
+            gf.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc);
             float dummy; f3 g;
-            f.sample_with_gradient(P, dummy, g);
+            gf.sample_with_gradient(P, dummy, g);
             f3 n = mul3(g, dscale);
             const float l = len3(n);
             if (l > 0.0f) n = scl3(n, 1.0f / l);
@@ -820,13 +837,13 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
           } else {
             hit_pos = from4(zero4);
           }
-          }   // mine
         }
-        steps_left -= taken;
+        steps_left -= 1;
         if (terminated) ray_live = false;
         else {
-          pc = add3(pc, vdir);
-          if (taken == 2) pc = add3(pc, vdir);
+          pc = pc_next;
+          if (pf) cur = nxt;
+          cur_ok = pf;
         }
       }
     }

@@ -94,6 +94,7 @@ int compute_geometry(tvk_ctx* ctx) {
   ctx->total_bricks = ctx->lod_offset[ctx->pool_lod_count - 1] + 1;
   ctx->slot_voxels = (uint64_t)ctx->brick[0] * ctx->brick[1] * ctx->brick[2];
   ctx->slot_bytes = ctx->slot_voxels * ctx->esize;
+  ctx->pool_slot_bytes = ctx->slot_bytes * (ctx->dtype == TVK_F32 ? 1 : 2);   // x-pair layout of integer pools (k_pool.cu)
   return TVK_OK;
 }
 
@@ -1214,11 +1215,11 @@ int tvk_create_pool(tvk_ctx* ctx, const uint32_t* pool_size) {
     return fail(ctx, TVK_ERR_INVALID, "Unable to create brick metadata texture, as it needs more than the max texture size");
   ctx->meta_count = (uint64_t)ctx->meta_dim[0] * ctx->meta_dim[1] * ctx->meta_dim[2];
   ctx->meta_h.assign(ctx->meta_count, TVK_BI_MISSING);
-  // The pool is stored in the x-pair layout (k_pool.cu: element x = (voxel x, voxel x+1)): 2 * slot_bytes per slot.  The
+  // 8- and 16-bit pools are stored in the x-pair layout (k_pool.cu: element x = (voxel x, voxel x+1)): 2 * slot_bytes per slot.  The
   // pool is still SIZED in voxels exactly as the reference sizes its atlas (same slot count and page table for the same
   // budget); the second copy of each voxel is the price of halving the traversal kernel's load count.
   // one extra slot of padding so a vector load at the very end never leaves the allocation
-  CU(cudaMalloc(&ctx->pool_d, ((uint64_t)ctx->n_slots + 1) * 2 * ctx->slot_bytes));
+  CU(cudaMalloc(&ctx->pool_d, ((uint64_t)ctx->n_slots + 1) * ctx->pool_slot_bytes));
   CU(cudaMalloc(&ctx->meta_d, ctx->meta_count * 4));
   CU(cudaMalloc(&ctx->slot_brick_d, (size_t)ctx->n_slots * 4));
   CU(cudaMalloc(&ctx->counts_d, 4 * sizeof(uint32_t)));
@@ -1228,7 +1229,7 @@ int tvk_create_pool(tvk_ctx* ctx, const uint32_t* pool_size) {
   // against the legacy NULL stream -- the first upload below (either stream) must not overtake a multi-GB memset.
   CU(cudaMemsetAsync(ctx->meta_d, 0, ctx->meta_count * 4, ctx->stream));
   CU(cudaMemsetAsync(ctx->slot_brick_d, 0xFF, (size_t)ctx->n_slots * 4, ctx->stream));
-  CU(cudaMemsetAsync(ctx->pool_d, 0, ((uint64_t)ctx->n_slots + 1) * 2 * ctx->slot_bytes, ctx->stream));
+  CU(cudaMemsetAsync(ctx->pool_d, 0, ((uint64_t)ctx->n_slots + 1) * ctx->pool_slot_bytes, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   // miss-report table (GLGridLeaper::InitHashTable, GLGridLeaper.cpp:266-291)
   ctx->hash_size = ctx->cfg.hash_table_size;
@@ -1302,7 +1303,7 @@ int tvk_read_pool_slot(tvk_ctx* ctx, uint32_t slot, void* dst, size_t cap) {
     return fail(ctx, TVK_ERR_INVALID, "bad slot / buffer");
   // the plain voxels of the slot: the first halves of its pairs, gathered on the device
   if (!ctx->unpair_d) CU(cudaMalloc(&ctx->unpair_d, ctx->slot_bytes));
-  launch_slot_unpair((unsigned char*)ctx->pool_d + (uint64_t)slot * 2 * ctx->slot_bytes, ctx->unpair_d, ctx->slot_voxels, ctx->esize,
+  launch_slot_unpair((unsigned char*)ctx->pool_d + (uint64_t)slot * ctx->pool_slot_bytes, ctx->unpair_d, ctx->slot_voxels, ctx->esize,
                      ctx->stream);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(dst, ctx->unpair_d, ctx->slot_bytes, cudaMemcpyDeviceToHost, ctx->stream));

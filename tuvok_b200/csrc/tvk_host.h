@@ -95,7 +95,8 @@ struct tvk_ctx {
   tvk::OctreeFile* file = nullptr;        // ExtendedOctree file source (tvk_open_octree_file); cb then points at it
   uint32_t io_threads = 8;                // parallel pread/decode workers of the file source
   void* store_d = nullptr;                // device brick store (slot layout, TOC order) or null
-  uint64_t slot_voxels = 0, slot_bytes = 0;
+  uint64_t slot_voxels = 0, slot_bytes = 0;   // per slot: voxels, bytes of the plain brick (store / staging)
+  uint64_t pool_slot_bytes = 0;               // bytes of one POOL slot (x-pair layout: 2 x slot_bytes for 8 / 16-bit data)
 
   // ---- transfer functions ----
   uint32_t* tf1d_d = nullptr; uint32_t tf1d_n = 0; uint64_t tf1d_nz[2] = {0, 0};

@@ -91,10 +91,16 @@ __device__ __forceinline__ float cvt(uint16_t v) { return __uint_as_float(0x4B00
 __device__ __forceinline__ float cvt(float v) { return v; }
 
 // ---- x-pair pool layout (k_pool.cu page_copy_kernel): pool element x = (voxel x, voxel x+1)
+// W = the stored pool element, V = the pair a footprint row is built from.  8 / 16-bit volumes store the pair (one load
+// per pair); float volumes stay plain (a stored pair would be 8 bytes per voxel and halve what L1 holds: measured
+// slower on the 1024^3 float isosurface workload) and form the pair from two loads.
 template <typename T> struct PairOf;
-template <> struct PairOf<uint8_t> { typedef uint16_t W; };
-template <> struct PairOf<uint16_t> { typedef uint32_t W; };
-template <> struct PairOf<float> { typedef float2 W; };
+template <> struct PairOf<uint8_t> { typedef uint16_t W; typedef uint16_t V; };
+template <> struct PairOf<uint16_t> { typedef uint32_t W; typedef uint32_t V; };
+template <> struct PairOf<float> { typedef float W; typedef float2 V; };
+__device__ __forceinline__ uint16_t load_pair(const uint16_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t load_pair(const uint32_t* p) { return __ldg(p); }
+__device__ __forceinline__ float2 load_pair(const float* p) { return make_float2(__ldg(p), __ldg(p + 1)); }
 // The two voxels of a pair as floats that still carry the 2^23 conversion bias (integer types): one PRMT each.
 // The bias cancels exactly in differences of two such values (both are integers below 2^24) and is removed from the low
 // operand of a lerp with one (packed) add, so a voxel costs 1 - 1.5 instructions to convert instead of 2.
@@ -115,10 +121,11 @@ template <> struct PairCvt<float> {
   static __device__ __forceinline__ float hi(float2 w) { return w.y; }
 };
 // first voxel of a pair, fully converted (what cvt(plain voxel) returns)
+__device__ __forceinline__ float first_voxel_of(uint16_t w) { return PairCvt<uint8_t>::lo(w) - 8388608.0f; }
+__device__ __forceinline__ float first_voxel_of(uint32_t w) { return PairCvt<uint16_t>::lo(w) - 8388608.0f; }
+__device__ __forceinline__ float first_voxel_of(float w) { return w; }
 template <typename T>
-__device__ __forceinline__ float first_voxel(typename PairOf<T>::W w) {
-  return PairCvt<T>::kBiased ? PairCvt<T>::lo(w) - 8388608.0f : PairCvt<T>::lo(w);
-}
+__device__ __forceinline__ float first_voxel(typename PairOf<T>::W w) { return first_voxel_of(w); }
 // two x-lerps at once: lanes (a.x -> b.x) and (a.y -> b.y), operands still biased (see PairCvt)
 template <bool BIASED>
 __device__ __forceinline__ f2 xlerp2(f2 a, f2 b, float f) {
