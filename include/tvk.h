@@ -370,6 +370,70 @@ int tvk_composite_over(tvk_ctx* ctx, const void* front, const void* back, void* 
 /* float -> unorm8 (GL read-back conversion) on device buffers */
 int tvk_quantize_rgba8(tvk_ctx* ctx, const void* rgba32f, void* rgba8, uint64_t n_pixels);
 
+/* ---- measurement ---------------------------------------------------------------------------------------------------
+ * The ceiling of the traversal kernel's own fetch path: width*height rays in the kernel's warp tiles
+ * march `steps` 0.5-voxel steps along `dir` through the resident pool doing ONLY the footprint loads and the packed
+ * filter trees of the current mode (7-tap footprint for 2D-TF / lit modes, 1 tap otherwise) -- no page table,
+ * classification, shading, compositing.  Needs a pool with FAST-path geometry (linear filter, ghost >= 2).
+ * ms = device time of the probe launch; the rate is width*height*steps / ms. */
+int tvk_probe_fetch(tvk_ctx* ctx, uint32_t steps, const float dir[3], float* ms, uint64_t* samples);
+
+/* ---- sort-last across the GPUs of one box, inside the library (new) -----------------------------------
+ * One process (or thread) per GPU, one tvk_ctx each, all with the same dataset description.  The finest brick grid is
+ * cut into n_ranks convex blocks by recursive bisection; rank g traverses only its block (rays keep the single-GPU
+ * ray's sample positions, see tvk_render_params.clip_min), then the frame is composited by DIRECT SEND: the image is
+ * cut into n_ranks pixel slices, every rank sends slice p of its partial RGBA32F image to rank p and receives the
+ * n_ranks-1 partials of its own slice in ONE grouped ncclSend/ncclRecv exchange over NVLink, folds them front to back in
+ * the visibility order of the blocks with a hand-written kernel (over operator of Compositing.glsl:33-38 / the blend
+ * state of GLRenderer.cpp:151-153, GL read-back conversion fused in) and the RGBA8 slices are gathered on rank 0 --
+ * traversal, exchange, blend and gather are queued on one stream without host synchronisation in between.  NCCL
+ * (libnccl.so.2, loaded on first use) carries the image exchange only.  Transfer-function modes (1D / 2D). */
+#define TVK_COMM_ID_BYTES 128
+/* how the brick grid is cut: OCTANT = longest axis of the block at every level (view independent: a rank's bricks never
+ * change, the brick store can be sharded at the source); SCREEN = the axes most perpendicular to the view first (blocks
+ * lie side by side on screen; re-cut when the view's dominant axes change) */
+typedef enum { TVK_SL_OCTANT = 0, TVK_SL_SCREEN = 1 } tvk_sortlast_policy;
+typedef struct {
+  tvk_frame_stats frame;       /* this rank's subframe; frame.ms_raycast = its traversal kernel */
+  float ms_exchange;           /* device time from the end of the traversal to the gathered RGBA8 frame: slice exchange +
+                                  n-way blend + gather */
+  float ms_frame;              /* device time of the whole frame on this rank */
+  uint64_t bytes_sent;         /* image bytes this rank sent (exchange + gather) */
+  uint64_t slice_lo, slice_hi; /* the pixel range this rank composited */
+} tvk_sortlast_stats;
+/* rank 0 creates the id (ncclGetUniqueId) and hands it to the other ranks by whatever means the host has */
+int tvk_sortlast_unique_id(uint8_t id[TVK_COMM_ID_BYTES]);
+/* collective over all ranks: ncclCommInitRank on ctx's device.  n_ranks must be a power of two <= 16. */
+int tvk_sortlast_init(tvk_ctx* ctx, const uint8_t id[TVK_COMM_ID_BYTES], int rank, int n_ranks, int policy);
+int tvk_sortlast_shutdown(tvk_ctx* ctx);
+/* this rank's block for the current render params (normalised volume space), the front-to-back order of the ranks
+ * (order[0] = frontmost, n_ranks entries) and its pixel slice; any pointer may be NULL */
+int tvk_sortlast_get_block(tvk_ctx* ctx, float clip_min[3], float clip_max[3], int* order, uint64_t* slice_lo,
+                           uint64_t* slice_hi);
+/* collective: one subframe on every rank + compositing.  Bricks a rank missed are paged in afterwards as in tvk_render;
+ * st->frame.converged is this rank's flag (the host ANDs it over the ranks when it needs a global one). */
+int tvk_sortlast_frame(tvk_ctx* ctx, tvk_sortlast_stats* st);
+/* rank 0: the composited frame, bottom row first (GLFrameCapture.cpp:72-85); async: dst is page-locked, the copy runs
+ * on the library's copy stream, tvk_read_wait as for tvk_read_rgba8_async */
+int tvk_sortlast_read_rgba8(tvk_ctx* ctx, uint8_t* dst, size_t pitch);
+int tvk_sortlast_read_rgba8_async(tvk_ctx* ctx, uint8_t* dst_pinned, size_t pitch);
+/* parity tap: this rank's composited slice as RGBA32F, (slice_hi - slice_lo) * 4 floats */
+int tvk_sortlast_read_slice(tvk_ctx* ctx, float* dst);
+/* host-only (no device, ctx may be NULL): the partition and visibility order tvk_sortlast_frame uses.  finest = bricks
+ * per axis of the finest level, float_layout = vLODLayout[0] (GLVolumePool.cpp:89-107), extent = normalised volume
+ * extent (AbstrRenderer.cpp:1102-1109).  clip_min / clip_max: n_ranks x 3 floats, order: n_ranks ints. */
+int tvk_sortlast_plan(const uint32_t finest[3], const float float_layout[3], const double extent[3],
+                      const float model_view[16], int n_ranks, int policy, float* clip_min, float* clip_max, int* order);
+/* the n-way front-to-back fold on device images (slices[0] = frontmost): RGBA32F (may be NULL) and RGBA8 results */
+int tvk_composite_nway(tvk_ctx* ctx, const void* const* slices, int n, void* out_rgba32f, void* out_rgba8,
+                       uint64_t n_pixels);
+/* Sort-last at the SOURCE: keep only the bricks of tvk_build_volume's store that touch the box (normalised volume
+ * space; all LoDs -- coarser bricks that overlap several blocks are kept by each of them), so the memory of a rank's
+ * brick store falls with the rank count.  Call before tvk_build_volume; {0,0,0},{1,1,1} (the default) keeps everything.
+ * Min/max are still computed for every brick (visibility is global).  A request for a brick that was not kept fails
+ * with TVK_ERR_SOURCE -- the traversal never asks for one (bricks outside the shard box are stepped through). */
+int tvk_set_store_shard(tvk_ctx* ctx, const float clip_min[3], const float clip_max[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,3 +136,95 @@ def test_depth_pipeline_stages_reproduce_the_single_gpu_frame(name, n, align):
     if single_samples > 0:
         assert total_samples <= single_samples * 1.3 + n * n_pix, (total_samples, single_samples)
     ren.Cleanup()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the in-library path (tvk_sortlast_*): n-way fold kernel, a 1-rank sort-last frame, the sharded brick store.  The
+# multi-rank exchange itself needs one GPU per rank (NCCL): bench.py --gpus N checks it against the single-GPU frame.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 5, 8])
+def test_nway_fold_kernel_equals_the_oracle_fold(n):
+    import tuvok_b200 as tb
+    rng = np.random.default_rng(3 + n)
+    n_pix = 70001
+    parts = []
+    for r in range(n):
+        a = (rng.random((n_pix, 1), dtype=np.float32) * (rng.random((n_pix, 1)) < 0.6)).astype(np.float32)
+        if r == 0:
+            a[::7] = 0.995                      # early-terminated front pixels
+        parts.append(np.concatenate([rng.random((n_pix, 3), dtype=np.float32) * a, a], axis=1).astype(np.float32))
+    want = parts[0].copy()
+    for k in range(1, n):
+        want = orc.composite_over(want, parts[k])
+    ren = tb.CudaGridLeaper(device=0)
+    dev = [torch.from_numpy(p).cuda() for p in parts]
+    out_f = torch.empty((n_pix, 4), dtype=torch.float32, device="cuda")
+    out_8 = torch.empty((n_pix, 4), dtype=torch.uint8, device="cuda")
+    ren.composite_nway([d.data_ptr() for d in dev], out_f.data_ptr(), out_8.data_ptr(), n_pix)
+    ren.synchronize()
+    assert np.array_equal(out_f.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(out_8.cpu().numpy(), orc.rgba8(want))
+    ren.Cleanup()
+
+
+@pytest.mark.parametrize("name", ["c2_bricked36_1d_ert", "c3_bricked36_2d_lit"])
+def test_single_rank_sortlast_frame_is_the_plain_frame(name):
+    s = golden_scenes.make(name)
+    ren = s.make_renderer("device")
+    assert ren.PaintUntilConverged().converged
+    ref8 = ren.ReadRGBA8().copy()
+    ref_f = ren.ReadRGBA32F().reshape(-1, 4).copy()
+    sortlast.init_library_sortlast(ren, 0, 1)
+    cmin, cmax, order, lo, hi = ren.SortLastBlock()
+    assert cmin == (0.0, 0.0, 0.0) and cmax == (1.0, 1.0, 1.0) and order == [0] and (lo, hi) == (0, s.width * s.height)
+    ren._dirty = True
+    st = ren.SortLastFrame()
+    assert st.frame.converged and st.slice_lo == 0 and st.slice_hi == s.width * s.height and st.bytes_sent == 0
+    assert np.array_equal(ren.SortLastReadRGBA8(), ref8)
+    assert np.array_equal(ren.SortLastReadSlice(s.width * s.height).view(np.uint32), ref_f.view(np.uint32))
+    pinned = ren.host_alloc((s.height, s.width, 4))
+    ren.SortLastReadRGBA8Async(pinned)
+    ren.WaitRead(0)
+    assert np.array_equal(pinned, ref8)
+    ren.SortLastShutdown()
+    ren.Cleanup()
+
+
+@pytest.mark.parametrize("name,n,rank", [("c2_bricked36_1d_ert", 2, 1), ("c3_bricked36_2d_lit", 8, 5), ("ragged_1d_lit", 4, 0)])
+def test_sharded_brick_store_renders_the_rank_image_bit_for_bit(name, n, rank):
+    """tvk_set_store_shard: only the bricks that touch the rank's block are kept; the rank's partial image, its page
+    table and the global min/max table are those of the full store; a foreign brick cannot be requested."""
+    import tuvok_b200 as tb
+    from tuvok_b200 import _lib as L
+    s = golden_scenes.make(name)
+    finest, fl, ext = scene_layout(s)
+    mv, _ = s.matrices()
+    cmin, cmax, _ = sortlast.plan(finest, fl, ext, mv, n, 0)
+    clip = (tuple(float(v) for v in cmin[rank]), tuple(float(v) for v in cmax[rank]))
+    sr = golden_scenes.make(name, clip=clip)
+    full = sr.make_renderer("device")
+    assert full.PaintUntilConverged().converged
+    want_f, want_meta, want_mm = full.ReadRGBA32F().copy(), full.page_table().copy(), full.minmax().copy()
+    full.Cleanup()
+    # the same renderer set-up with the store sharded at the source
+    r = tb.CudaGridLeaper(device=0, max_gpu_mem=sr.max_gpu_mem, hash_table_size=sr.hash_size(), brick_strategy=sr.strategy)
+    r.SetStoreShard(*clip)
+    r.BuildVolume(sr.volume, sr.brick, sr.overlap, scale=sr.scale, clamp_to_edge=sr.clamp, max_gradient_magnitude=sr.max_grad)
+    r.Set1DTrans(sr.tf1d); r.Set2DTrans(sr.tf2d)
+    r.SetRendermode(sr.mode); r.SetUseLighting(sr.lighting); r.SetSampleRateModifier(sr.sample_rate)
+    r.SetIsoValue(sr.isovalue); r.SetInterpolant(sr.nearest)
+    r.Resize(sr.width, sr.height)
+    r.SetRotation(sr.rotation); r.SetTranslation(sr.translation)
+    r.SetViewParameters(sr.fov, 0.01, 1000.0, sr.eye, (0, 0, 0), (0, 1, 0))
+    r.SetShardBox(*clip)
+    r.CreateVolumePool(sr._pool_size)
+    assert r.PaintUntilConverged().converged
+    assert np.array_equal(r.ReadRGBA32F().view(np.uint32), want_f.view(np.uint32))
+    assert np.array_equal(r.page_table(), want_meta)
+    assert np.array_equal(r.minmax(), want_mm)
+    # a finest-level brick of the opposite corner is not in this rank's store
+    far = [0 if clip[0][i] > 0.0 else finest[i] - 1 for i in range(3)]
+    if any(clip[0][i] > 0.0 or clip[1][i] < 1.0 for i in range(3)):
+        with pytest.raises(L.TvkError):
+            r.UploadBricks([[far[0], far[1], far[2], 0]])
+    r.Cleanup()

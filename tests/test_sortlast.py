@@ -381,3 +381,133 @@ def test_oracle_pipeline_paging_history():
     d = float(np.abs(warm["image"] - fresh["image"]).max())
     assert 1e-4 < d < 0.0101
     assert sum(st["samples"] for st in fresh["stages"]) == 507713      # the count the CUDA stages reported
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the in-library sort-last path (csrc/tvk_sortlast.inc): its host-only plan against the Python mirror, and the
+# direct-send exchange + front-to-back fold (host mirror, oracle over operator) against the single renderer
+# ---------------------------------------------------------------------------------------------------------------------
+def _mirror_plan(finest, fl, ext, mv, n, policy):
+    eye = sortlast.eye_in_volume(mv, ext)
+    axes = None
+    if policy == 1:      # SCREEN: the axes most perpendicular to the view first (sortlast.split_axes, continued to k = 4)
+        vd = (0.5 - eye) * ext
+        o = sorted(range(3), key=lambda i: (abs(float(vd[i])), i))
+        axes = [o[0], o[1], o[0], o[1]][:int(round(np.log2(n)))]
+        assert axes[:3] == sortlast.split_axes(vd, min(n, 8), "screen")
+    boxes, splits = sortlast.shard_boxes(finest, n, axes)
+    clips = [sortlast.box_to_clip(b, finest, fl) for b in boxes]
+    return clips, sortlast.bsp_order(n, [[lvl[p] for p in sorted(lvl)] for lvl in splits], fl, eye), boxes, splits, eye
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("policy", [0, 1])
+def test_library_plan_equals_the_host_mirror(n, policy):
+    from tuvok_b200.renderer import rotation_x, rotation_y
+    import scene as sc
+    finest, ext = (64, 23, 17), np.array([1.0, 0.36, 0.27])
+    fl = [np.float32(63.99999), np.float32(22.6), np.float32(17.0) - np.float32(17.0) * np.finfo(np.float32).eps]
+    for step in range(0, 36, 5):
+        rot = (rotation_y(10.0 * step) @ rotation_x(20.0 + step)).astype(np.float32)
+        mv = (rot @ sc.look_at((0, 0, 1.6), (0, 0, 0), (0, 1, 0))).astype(np.float32)
+        cmin, cmax, order = sortlast.plan(finest, fl, ext, mv, n, policy)
+        clips, morder, boxes, _, _ = _mirror_plan(finest, fl, ext, mv, n, policy)
+        for r in range(n):
+            np.testing.assert_array_equal(cmin[r], np.array(clips[r][0], np.float32))
+            np.testing.assert_array_equal(cmax[r], np.array(clips[r][1], np.float32))
+        assert list(order) == morder and sorted(order) == list(range(n))
+        # the frontmost block holds the camera side of every cut: its box is the nearest to the eye
+        eye = sortlast.eye_in_volume(mv, ext)
+        centre = lambda r: np.array([(a + b) / 2 for a, b in zip(clips[r][0], clips[r][1])])
+        d = [np.linalg.norm((centre(r) - eye) * ext) for r in order]
+        assert d[0] == min(d)
+
+
+def test_library_plan_refuses_bad_rank_counts():
+    from tuvok_b200 import _lib as L
+    with pytest.raises(L.TvkError):
+        sortlast.plan((4, 4, 4), (4.0, 4.0, 4.0), (1.0, 1.0, 1.0), np.eye(4, dtype=np.float32), 3, 0)
+    with pytest.raises(L.TvkError):
+        sortlast.plan((1, 1, 2), (1.0, 1.0, 2.0), (1.0, 1.0, 1.0), np.eye(4, dtype=np.float32), 4, 0)
+
+
+def _direct_send_in_process(parts, order):
+    """The fold every rank performs on its slice, run for all ranks in this process."""
+    n, n_pix = len(parts), parts[0].shape[0]
+    final = np.zeros((n_pix, 4), np.float32)
+    for r in range(n):
+        lo, hi = sortlast.slice_range(n_pix, n, r)
+        acc = parts[order[0]][lo:hi].copy()
+        for k in order[1:]:
+            acc = orc.composite_over(acc, parts[k][lo:hi].copy())
+        final[lo:hi] = acc
+    return final
+
+
+@pytest.mark.parametrize("name,n,policy", [("c2_bricked36_1d_ert", 2, 0), ("ragged_1d_lit", 4, 1), ("inside_aniso_2d", 8, 0),
+                                            ("c3_bricked36_2d_lit", 4, 0), ("c3_bricked36_2d_lit", 8, 1)])
+def test_direct_send_image_matches_single_renderer(name, n, policy):
+    s = golden_scenes.make(name)
+    s._name = name
+    single = s.oracle_render()
+    finest, fl, ext = scene_layout(s)
+    mv, _ = s.matrices()
+    cmin, cmax, order = sortlast.plan(finest, fl, ext, mv, n, policy)
+    parts = []
+    for r in range(n):
+        sr = golden_scenes.make(name, clip=(tuple(float(v) for v in cmin[r]), tuple(float(v) for v in cmax[r])))
+        parts.append(sr.oracle_render()["image"].reshape(-1, 4).copy())
+    final = _direct_send_in_process(parts, list(order))
+    mx, psnr = image_diff(orc.rgba8(final), single["rgba8"].reshape(-1, 4))
+    assert mx <= 2 and psnr >= 45.0, (mx, psnr)
+    assert orc.rgba8(final)[:, 3].any()
+
+
+def _ds_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)           # every rank draws all partial images, keeps its own
+        parts = []
+        for r in range(world):
+            a = rng.random((1001, 1), dtype=np.float32) * (rng.random((1001, 1)) < 0.7)
+            parts.append(np.concatenate([rng.random((1001, 3), dtype=np.float32) * a, a], axis=1).astype(np.float32))
+        order = [1, 0] if world == 2 else list(range(world))[::-1]
+
+        def over(front, back):
+            return torch.from_numpy(orc.composite_over(front.numpy().copy(), back.numpy().copy()))
+
+        lo, hi, acc = sortlast.direct_send(torch.from_numpy(parts[rank].copy()), rank, world, order, dist, over)
+        q.put((rank, lo, hi, acc.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_direct_send_over_gloo(world):
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ds_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(11)
+    parts = []
+    for r in range(world):
+        a = rng.random((1001, 1), dtype=np.float32) * (rng.random((1001, 1)) < 0.7)
+        parts.append(np.concatenate([rng.random((1001, 3), dtype=np.float32) * a, a], axis=1).astype(np.float32))
+    order = [1, 0] if world == 2 else list(range(world))[::-1]
+    expect = _direct_send_in_process(parts, order)
+    covered = np.zeros(1001, bool)
+    for rank, lo, hi, px in got:
+        assert (lo, hi) == sortlast.slice_range(1001, world, rank)
+        np.testing.assert_array_equal(px, expect[lo:hi])
+        covered[lo:hi] = True
+    assert covered.all()

@@ -67,6 +67,15 @@ class OctreeFileInfo(C.Structure):
                 ("payload_bytes", C.c_uint64), ("bricks_by_codec", C.c_uint64 * 6)]
 
 
+class SortLastStats(C.Structure):
+    _fields_ = [("frame", FrameStats), ("ms_exchange", C.c_float), ("ms_frame", C.c_float), ("bytes_sent", C.c_uint64),
+                ("slice_lo", C.c_uint64), ("slice_hi", C.c_uint64)]
+
+
+COMM_ID_BYTES = 128
+SL_OCTANT, SL_SCREEN = 0, 1
+
+
 class ClassicBrick(C.Structure):
     _fields_ = [("index", C.c_uint32), ("x", C.c_uint32), ("y", C.c_uint32), ("z", C.c_uint32),
                 ("distance", C.c_float), ("empty", C.c_int32)]
@@ -142,6 +151,18 @@ SIGNATURES = {
     "tvk_read_mip_max": (C.c_int, [P, P]),
     "tvk_get_classic_brick_list": (C.c_int, [P, C.POINTER(C.c_uint32), P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "tvk_composite_over": (C.c_int, [P, P, P, P, C.c_uint64]),
+    "tvk_probe_fetch": (C.c_int, [P, C.c_uint32, f32x3, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
+    "tvk_sortlast_unique_id": (C.c_int, [C.c_uint8 * COMM_ID_BYTES]),
+    "tvk_sortlast_init": (C.c_int, [P, C.c_uint8 * COMM_ID_BYTES, C.c_int, C.c_int, C.c_int]),
+    "tvk_sortlast_shutdown": (C.c_int, [P]),
+    "tvk_sortlast_get_block": (C.c_int, [P, f32x3, f32x3, P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tvk_sortlast_frame": (C.c_int, [P, C.POINTER(SortLastStats)]),
+    "tvk_sortlast_read_rgba8": (C.c_int, [P, P, C.c_size_t]),
+    "tvk_sortlast_read_rgba8_async": (C.c_int, [P, P, C.c_size_t]),
+    "tvk_sortlast_read_slice": (C.c_int, [P, P]),
+    "tvk_sortlast_plan": (C.c_int, [u32x3, f32x3, C.c_double * 3, f32x16, C.c_int, C.c_int, P, P, P]),
+    "tvk_composite_nway": (C.c_int, [P, P, C.c_int, P, P, C.c_uint64]),
+    "tvk_set_store_shard": (C.c_int, [P, f32x3, f32x3]),
     "tvk_quantize_rgba8": (C.c_int, [P, P, P, C.c_uint64]),
 }
 

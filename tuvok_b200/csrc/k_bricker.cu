@@ -146,8 +146,8 @@ __global__ void downsample_u16x2_kernel(const uint2* __restrict__ src, uint32_t 
 // brick cutting + stats
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ vol, T* store, double* minmax,
-                                                         const CutConsts C, uint64_t slot_voxels) {
+__global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ vol, T* store, const int32_t* __restrict__ store_index,
+                                                         double* minmax, const CutConsts C, uint64_t slot_voxels) {
   const uint32_t b = blockIdx.x;
   const uint32_t bx = b % C.layout[0], by = (b / C.layout[0]) % C.layout[1], bz = b / (C.layout[0] * C.layout[1]);
   const uint32_t bc[3] = {bx, by, bz};
@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ v
   }
   const int64_t org[3] = {(int64_t)bx * (C.brick[0] - 2 * ov) - ov, (int64_t)by * (C.brick[1] - 2 * ov) - ov,
                           (int64_t)bz * (C.brick[2] - 2 * ov) - ov};
-  T* dst = store + (uint64_t)(C.first_brick + b) * slot_voxels;
+  // sharded store (sort-last at the source): a brick another rank owns is only measured (min/max are global), not kept
+  const int64_t at = store_index ? (int64_t)store_index[C.first_brick + b] : (int64_t)(C.first_brick + b);
+  const bool keep = at >= 0;
+  T* dst = store + (uint64_t)(keep ? at : 0) * slot_voxels;
   const uint32_t n = bs[0] * bs[1] * bs[2];
   T mn = 0, mx = 0;
   bool any = false;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ v
       const bool stale = C.lod > 0 && ((gx == 1 && gy == 1 && gz == -1) || (gx == 1 && gy == -1 && gz == 1) ||
                                        (gx == -1 && gy == 1 && gz == 1));
       const uint32_t v = stale ? 0u : __ldg(src32 + ((uint64_t)lz * C.lod_size[1] + ly) * row_words + i);
-      dst32[w] = v;
+      if (keep) dst32[w] = v;
       const uint32_t lo = v & 0xffffu, hi = v >> 16;
       wmn = min(wmn, min(lo, hi));
       wmx = max(wmx, max(lo, hi));
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ v
                                      (g[0] == -1 && g[1] == 1 && g[2] == 1));
     if (!outside && !stale)
       v = vol[(uint64_t)gc[0] + (uint64_t)C.lod_size[0] * ((uint64_t)gc[1] + (uint64_t)C.lod_size[1] * (uint64_t)gc[2])];
-    dst[di] = v;
+    if (keep) dst[di] = v;
     if (!any) { mn = mx = v; any = true; }
     else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
   }
@@ -328,13 +331,13 @@ void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, doub
   }
 }
 
-void launch_cut_bricks(const void* lod_vol, void* store, double* minmax, const CutConsts& cc, int dtype,
-                       uint64_t slot_bytes, cudaStream_t s) {
+void launch_cut_bricks(const void* lod_vol, void* store, const int32_t* store_index, double* minmax, const CutConsts& cc,
+                       int dtype, uint64_t slot_bytes, cudaStream_t s) {
   const uint32_t n = cc.layout[0] * cc.layout[1] * cc.layout[2];
   switch (dtype) {
-    case TVK_U8: cut_bricks_kernel<uint8_t><<<n, 256, 0, s>>>((const uint8_t*)lod_vol, (uint8_t*)store, minmax, cc, slot_bytes); break;
-    case TVK_U16: cut_bricks_kernel<uint16_t><<<n, 256, 0, s>>>((const uint16_t*)lod_vol, (uint16_t*)store, minmax, cc, slot_bytes / 2); break;
-    default: cut_bricks_kernel<float><<<n, 256, 0, s>>>((const float*)lod_vol, (float*)store, minmax, cc, slot_bytes / 4); break;
+    case TVK_U8: cut_bricks_kernel<uint8_t><<<n, 256, 0, s>>>((const uint8_t*)lod_vol, (uint8_t*)store, store_index, minmax, cc, slot_bytes); break;
+    case TVK_U16: cut_bricks_kernel<uint16_t><<<n, 256, 0, s>>>((const uint16_t*)lod_vol, (uint16_t*)store, store_index, minmax, cc, slot_bytes / 2); break;
+    default: cut_bricks_kernel<float><<<n, 256, 0, s>>>((const float*)lod_vol, (float*)store, store_index, minmax, cc, slot_bytes / 4); break;
   }
 }
 

@@ -441,7 +441,7 @@ constexpr int kFetchLanes = TVK_FETCH_LANES;
 constexpr bool kPrefetch = TVK_PREFETCH != 0;   // fetch the next sample's footprint before shading the current one
 // CTA = TVK_WX x TVK_WY warps, each an 8x4 pixel tile (CTA covers 8*WX x 4*WY pixels)
 #ifndef TVK_WX
-#define TVK_WX 1
+#define TVK_WX 2
 #endif
 #ifndef TVK_WY
 #define TVK_WY 2
@@ -873,6 +873,56 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
   }
 }
 
+// ---- fetch-path ceiling ------------------------------------------------------------------------------------------
+// What the traversal kernel's OWN fetch path can deliver when nothing else is in the loop: the same warp tiles (8x4
+// rays, one voxel apart), the same 0.5-voxel steps, the same FastFoot loads + packed filter trees on the resident pool,
+// but no page-table walk, classification, shading or compositing.  Rays march through a slot along `dir` and hop to
+// another slot when they leave it (so the working set is the whole pool, far larger than L2).  bench.py divides the
+// kernel's sample rate by this rate: the fetch fraction of the roofline object.
+template <typename T, int BS, bool GRAD>
+__global__ void __launch_bounds__(kThreads) fetch_probe_kernel(const __grid_constant__ RayConsts P, uint32_t n_slots, uint32_t steps,
+                                                               float dx, float dy, float dz, float* out) {
+  typedef typename PairOf<T>::W W;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const uint32_t px = blockIdx.x * (8 * kWX) + (wid % kWX) * 8 + (lane & 7);
+  const uint32_t py = blockIdx.y * (4 * kWY) + (wid / kWX) * 4 + (lane >> 3);
+  if (px >= P.width || py >= P.height) return;
+  const W* pool = (const W*)P.pool;
+  const uint32_t tile = (blockIdx.y * gridDim.x + blockIdx.x) * (kWX * kWY) + wid;
+  uint32_t slot = (tile * 2654435761u) % n_slots;
+  const float bs = (float)(BS ? BS : (int)P.total[0]);
+  // lane offsets across the ray bundle: perpendicular to the march direction's dominant axis
+  const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+  f3 u, v;
+  if (az >= ax && az >= ay) { u = F3(1.f, 0.f, 0.f); v = F3(0.f, 1.f, 0.f); }
+  else if (ay >= ax) { u = F3(1.f, 0.f, 0.f); v = F3(0.f, 0.f, 1.f); }
+  else { u = F3(0.f, 1.f, 0.f); v = F3(0.f, 0.f, 1.f); }
+  const float lu = (float)(lane & 7), lv = (float)(lane >> 3);
+  const float inv = 0.5f / sqrtf(dx * dx + dy * dy + dz * dz);
+  const f3 step = F3(dx * inv, dy * inv, dz * inv);                  // 0.5 voxel per step
+  const f3 start = F3(4.f + u.x * lu + v.x * lv, 4.f + u.y * lu + v.y * lv, 4.f + u.z * lu + v.z * lv);
+  f3 q = start;                                                       // voxel coordinates inside the slot
+  float acc = 0.0f;
+  for (uint32_t i = 0; i < steps; i++) {
+    if (q.x < 2.f || q.y < 2.f || q.z < 2.f || q.x > bs - 3.f || q.y > bs - 3.f || q.z > bs - 3.f) {
+      q = start;                                                      // left the brick: next slot (warp-coherent hop)
+      slot = (slot + 9973u) % n_slots;
+    }
+    const W* vox = pool + (uint64_t)slot * P.slot_voxels;
+    FastFoot<T, BS, GRAD> f;
+    f.fetch(P, vox, 0u, 0u, 0u, F3(q.x / bs, q.y / bs, q.z / bs));
+    if constexpr (GRAD) {
+      float data; f3 g;
+      f.sample_with_gradient(P, data, g);
+      acc += data + g.x + g.y + g.z;
+    } else {
+      acc += f.centre(P);
+    }
+    q = add3(q, step);
+  }
+  out[(size_t)py * P.width + px] = acc;
+}
+
 template <typename T, int MODE, bool LIT>
 void launch_t(const RayConsts& rc, cudaStream_t s) {
   dim3 block(kThreads);
@@ -904,6 +954,27 @@ void launch_d(const RayConsts& rc, int mode, int lighting, cudaStream_t s) {
 }
 
 }  // namespace
+
+// rc: pool, slot_voxels, total, norm, width, height are used; the pool is addressed as a one-slot atlas per brick
+void launch_fetch_probe(const RayConsts& rc_in, int dtype, bool grad, uint32_t n_slots, uint32_t steps, const float dir[3],
+                        float* out, cudaStream_t s) {
+  RayConsts rc = rc_in;
+  for (int i = 0; i < 3; i++) rc.pool_size_f[i] = (float)rc.total[i];
+  dim3 block(kThreads);
+  dim3 grid((rc.width + 8 * kWX - 1) / (8 * kWX), (rc.height + 4 * kWY - 1) / (4 * kWY));
+  const bool b36 = rc.total[0] == 36 && rc.total[1] == 36 && rc.total[2] == 36;
+#define TVK_PROBE(T, BSV)                                                                                              \
+  do {                                                                                                                 \
+    if (grad) fetch_probe_kernel<T, BSV, true><<<grid, block, 0, s>>>(rc, n_slots, steps, dir[0], dir[1], dir[2], out); \
+    else fetch_probe_kernel<T, BSV, false><<<grid, block, 0, s>>>(rc, n_slots, steps, dir[0], dir[1], dir[2], out);    \
+  } while (0)
+  switch (dtype) {
+    case TVK_U8: if (b36) TVK_PROBE(uint8_t, 36); else TVK_PROBE(uint8_t, 0); break;
+    case TVK_U16: if (b36) TVK_PROBE(uint16_t, 36); else TVK_PROBE(uint16_t, 0); break;
+    default: if (b36) TVK_PROBE(float, 36); else TVK_PROBE(float, 0); break;
+  }
+#undef TVK_PROBE
+}
 
 void launch_raycast(const RayConsts& rc, int mode, int lighting, int dtype, cudaStream_t s) {
   switch (dtype) {

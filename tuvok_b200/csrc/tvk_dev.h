@@ -64,6 +64,9 @@ struct RayConsts {
 
 // launchers (defined in the .cu files)
 void launch_raycast(const RayConsts& rc, int mode, int lighting, int dtype, cudaStream_t s);
+// fetch-path ceiling probe (k_raycast.cu): `steps` fetch + filter evaluations per ray on the resident pool, nothing else
+void launch_fetch_probe(const RayConsts& rc, int dtype, bool grad, uint32_t n_slots, uint32_t steps, const float dir[3],
+                        float* out, cudaStream_t s);
 void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rgba, uint32_t w, uint32_t h,
                         const float amb[3], const float dif[3], const float spe[3], const float ldir[3],
                         cudaStream_t s);
@@ -76,6 +79,10 @@ void launch_cv_compose(const float4* hit_pos, const float4* hit_nrm, const float
 void launch_stereo_compose(int mode, const float4* left, const float4* right, float4* out, uint32_t w, uint32_t h,
                            int alternating_frame_id, float split_coord, cudaStream_t s);
 void launch_composite_over(const float4* front, const float4* back, float4* out, uint64_t n, cudaStream_t s);
+// sort-last direct send: fold the n partial images of one pixel slice front to back (src[0] = frontmost) -> RGBA32F + RGBA8
+#define TVK_MAX_RANKS 16
+struct NWaySrc { const float4* src[TVK_MAX_RANKS]; int n; };
+void launch_nway_over(const NWaySrc& a, float4* out_f, uchar4* out8, uint64_t n, cudaStream_t s);
 
 // classic per-brick raycaster (k_classic.cu): uniforms of GLRaycaster::SetBrickDepShaderVars / RenderBox plus the
 // per-axis brick tables of the LoD (the brick boxes of one LoD are a tensor-product grid, so everything the
@@ -144,8 +151,9 @@ struct CutConsts {
 };
 // min/max of n staged bricks (ops[i]: src_off, size, new_id = TOC index) -> minmax[4 * new_id]
 void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, double* minmax, int dtype, cudaStream_t s);
-void launch_cut_bricks(const void* lod_vol, void* store, double* minmax, const CutConsts& cc, int dtype,
-                       uint64_t slot_bytes, cudaStream_t s);
+// store_index (device, TOC index -> store slot or -1) or nullptr: the store holds every brick at its TOC index
+void launch_cut_bricks(const void* lod_vol, void* store, const int32_t* store_index, double* minmax, const CutConsts& cc,
+                       int dtype, uint64_t slot_bytes, cudaStream_t s);
 
 }  // namespace tvk
 #endif

@@ -110,7 +110,9 @@ void brick_size(const tvk_ctx* ctx, const uint32_t co[3], uint32_t lod, uint32_t
 void free_dataset(tvk_ctx* c) {
   if (c->minmax_d) cudaFree(c->minmax_d);
   if (c->store_d) cudaFree(c->store_d);
-  c->minmax_d = nullptr; c->store_d = nullptr;
+  if (c->store_index_d) cudaFree(c->store_index_d);
+  c->minmax_d = nullptr; c->store_d = nullptr; c->store_index_d = nullptr;
+  c->store_index.clear(); c->store_count = 0;
   c->minmax_h.clear();
   if (c->file) { delete c->file; c->file = nullptr; }
   c->cb = nullptr; c->cb_user = nullptr;
@@ -300,7 +302,15 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
     for (size_t i = 0; i < reqs.size(); i++) {
       ops[i] = PageOp{};
       ops[i].slot = reqs[i].slot;
-      ops[i].src_off = (uint64_t)reqs[i].id * ctx->slot_bytes;   // pool id == TOC index for the pool LoDs
+      uint64_t at = reqs[i].id;                                   // pool id == TOC index for the pool LoDs
+      if (!ctx->store_index.empty()) {
+        const int32_t k = ctx->store_index[reqs[i].id];
+        if (k < 0)
+          return fail(ctx, TVK_ERR_SOURCE, "brick (%u,%u,%u,%u) is not in this rank's brick store (tvk_set_store_shard)",
+                      reqs[i].co[0], reqs[i].co[1], reqs[i].co[2], reqs[i].co[3]);
+        at = (uint64_t)k;
+      }
+      ops[i].src_off = at * ctx->slot_bytes;
     }
     int rc = ensure_ops(ctx, ops.size());
     if (rc) return rc;
@@ -718,6 +728,7 @@ void tvk_destroy(tvk_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
+  tvk_sortlast_shutdown(ctx);
   free_frame(ctx);
   free_pool(ctx);
   free_dataset(ctx);
@@ -1067,9 +1078,47 @@ int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uin
     CU(cudaMemcpyAsync(lod_own0, raw, n0 * ctx->esize, cudaMemcpyHostToDevice, ctx->stream));
     lod_prev = lod_own0;
   }
-  cudaError_t e = cudaMalloc(&ctx->store_d, ctx->n_bricks_all * ctx->slot_bytes);
+  // sort-last at the source (tvk_set_store_shard): keep only the bricks that touch this rank's box
+  ctx->store_count = ctx->n_bricks_all;
+  bool sharded = false;
+  for (int i = 0; i < 3; i++) sharded = sharded || ctx->store_clip_min[i] > 0.0f || ctx->store_clip_max[i] < 1.0f;
+  if (sharded) {
+    ctx->store_index.assign(ctx->n_bricks_all, -1);
+    uint64_t kept = 0;
+    for (uint32_t l = 0; l < ctx->pool_lod_count; l++) {
+      float lay[3];
+      for (int i = 0; i < 3; i++) {   // vLODLayout[l], as derive() hands it to the kernel
+        float c = (float)ctx->vol[i] / ctx->inner[i];
+        c = c / (float)(1u << l);
+        if ((float)(uint32_t)c == c) c = c - c * std::numeric_limits<float>::epsilon();
+        lay[i] = c;
+      }
+      const uint32_t* n = ctx->layout[l];
+      for (uint32_t z = 0; z < n[2]; z++)
+        for (uint32_t y = 0; y < n[1]; y++)
+          for (uint32_t x = 0; x < n[0]; x++) {
+            const uint32_t co[3] = {x, y, z};
+            bool outside = false;
+            for (int i = 0; i < 3; i++) {   // classify_brick of the traversal kernel: OUTSIDE_SHARD
+              const float c0 = (float)co[i] / lay[i], c1 = (float)(co[i] + 1) / lay[i];
+              const float lo = ctx->store_clip_min[i] > 0.0f ? ctx->store_clip_min[i] : -INFINITY;
+              const float hi = ctx->store_clip_max[i] < 1.0f ? ctx->store_clip_max[i] : INFINITY;
+              if (c1 <= lo || c0 >= hi) outside = true;
+            }
+            if (!outside) ctx->store_index[ctx->toc_offset[l] + x + (uint64_t)y * n[0] + (uint64_t)z * n[0] * n[1]] = (int32_t)kept++;
+          }
+    }
+    ctx->store_count = kept;
+  }
+  cudaError_t e = cudaMalloc(&ctx->store_d, std::max<uint64_t>(ctx->store_count, 1) * ctx->slot_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->minmax_d, ctx->n_bricks_all * 4 * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->store_d, 0, ctx->n_bricks_all * ctx->slot_bytes, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->store_d, 0, std::max<uint64_t>(ctx->store_count, 1) * ctx->slot_bytes, ctx->stream);
+  if (e == cudaSuccess && sharded) {
+    e = cudaMalloc(&ctx->store_index_d, ctx->store_index.size() * sizeof(int32_t));
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(ctx->store_index_d, ctx->store_index.data(), ctx->store_index.size() * sizeof(int32_t),
+                          cudaMemcpyHostToDevice, ctx->stream);
+  }
   void* lod_cur = nullptr;
   for (uint32_t l = 0; l < ctx->lod_count && e == cudaSuccess; l++) {
     if (l > 0) {
@@ -1083,7 +1132,7 @@ int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uin
     CutConsts cc{};
     for (int i = 0; i < 3; i++) { cc.lod_size[i] = ctx->lod_size[l][i]; cc.layout[i] = ctx->layout[l][i]; cc.brick[i] = ctx->brick[i]; }
     cc.overlap = overlap; cc.clamp = clamp_to_edge; cc.lod = (int32_t)l; cc.first_brick = ctx->toc_offset[l];
-    launch_cut_bricks(lod_prev, ctx->store_d, ctx->minmax_d, cc, dtype, ctx->slot_bytes, ctx->stream);
+    launch_cut_bricks(lod_prev, ctx->store_d, ctx->store_index_d, ctx->minmax_d, cc, dtype, ctx->slot_bytes, ctx->stream);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1106,6 +1155,15 @@ int tvk_synth_volume(tvk_ctx* ctx, void* dst_device, int kind, const uint32_t si
   launch_synth(dst_device, kind, size, dtype, seed, ctx->stream);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
+  return TVK_OK;
+}
+
+int tvk_set_store_shard(tvk_ctx* ctx, const float clip_min[3], const float clip_max[3]) {
+  if (!ctx || !clip_min || !clip_max) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  for (int i = 0; i < 3; i++)
+    if (!(clip_min[i] >= 0.0f && clip_max[i] <= 1.0f && clip_min[i] < clip_max[i])) return fail(ctx, TVK_ERR_INVALID, "bad shard box");
+  std::memcpy(ctx->store_clip_min, clip_min, 12);
+  std::memcpy(ctx->store_clip_max, clip_max, 12);
   return TVK_OK;
 }
 
@@ -1144,8 +1202,12 @@ int tvk_read_brick(tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lo
   if (!ctx->store_d) return fail(ctx, TVK_ERR_INVALID, "no device brick store (dataset comes from a callback)");
   const size_t bytes = (size_t)bs[0] * bs[1] * bs[2] * ctx->esize;
   if (cap < bytes) return fail(ctx, TVK_ERR_INVALID, "buffer too small");
-  const uint64_t idx = ctx->toc_offset[lod] + x + (uint64_t)y * ctx->layout[lod][0] +
-                       (uint64_t)z * ctx->layout[lod][0] * ctx->layout[lod][1];
+  uint64_t idx = ctx->toc_offset[lod] + x + (uint64_t)y * ctx->layout[lod][0] +
+                 (uint64_t)z * ctx->layout[lod][0] * ctx->layout[lod][1];
+  if (!ctx->store_index.empty()) {
+    if (ctx->store_index[idx] < 0) return fail(ctx, TVK_ERR_SOURCE, "brick is not in this rank's brick store");
+    idx = (uint64_t)ctx->store_index[idx];
+  }
   cudaMemcpy3DParms p{};
   p.srcPtr = make_cudaPitchedPtr((unsigned char*)ctx->store_d + idx * ctx->slot_bytes, ctx->brick[0] * ctx->esize,
                                  ctx->brick[0] * ctx->esize, ctx->brick[1]);
@@ -1413,6 +1475,32 @@ int tvk_set_params(tvk_ctx* ctx, const tvk_render_params* p) {
   return TVK_OK;
 }
 
+int tvk_probe_fetch(tvk_ctx* ctx, uint32_t steps, const float dir[3], float* ms, uint64_t* samples) {
+  if (!ctx || !dir || !ms || steps == 0) return fail(ctx, TVK_ERR_INVALID, "bad argument");
+  cudaSetDevice(ctx->cfg.device);
+  int rc = check_renderable(ctx);
+  if (rc) return rc;
+  if (dir[0] == 0.0f && dir[1] == 0.0f && dir[2] == 0.0f) return fail(ctx, TVK_ERR_INVALID, "zero direction");
+  for (int i = 0; i < 3; i++)
+    if (ctx->overlap < 2 || ctx->brick[i] < 12) return fail(ctx, TVK_ERR_INVALID, "the fetch probe needs the fast-path geometry (ghost >= 2)");
+  rc = ensure_frame(ctx, ctx->params.width, ctx->params.height);
+  if (rc) return rc;
+  RayConsts u;
+  rc = derive(ctx, u);
+  if (rc) return rc;
+  const bool grad = ctx->params.mode == TVK_RM_2DTRANS || (ctx->params.mode == TVK_RM_1DTRANS && ctx->params.lighting);
+  cudaStream_t s = ctx->stream;
+  launch_fetch_probe(u, ctx->dtype, grad, ctx->n_slots, 8, dir, (float*)ctx->buf[7], s);   // warm-up (instruction cache)
+  CU(cudaEventRecord(ctx->ev[0], s));
+  launch_fetch_probe(u, ctx->dtype, grad, ctx->n_slots, steps, dir, (float*)ctx->buf[7], s);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev[1], s));
+  CU(cudaEventSynchronize(ctx->ev[1]));
+  cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]);
+  if (samples) *samples = (uint64_t)ctx->params.width * ctx->params.height * steps;
+  return TVK_OK;
+}
+
 int tvk_raycast_only(tvk_ctx* ctx) {
   if (!ctx) return TVK_ERR_INVALID;
   cudaSetDevice(ctx->cfg.device);
@@ -1422,17 +1510,10 @@ int tvk_raycast_only(tvk_ctx* ctx) {
   return raycast_pass(ctx, false);
 }
 
-int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
-  if (!ctx) return TVK_ERR_INVALID;
-  cudaSetDevice(ctx->cfg.device);
-  if (st) std::memset(st, 0, sizeof(*st));
-  int rc = check_renderable(ctx);
-  if (rc) return rc;
-  ctx->result_buf = nullptr;
-  // visibility follows TF / mode / isovalue changes (Changed1DTrans etc. -> RecomputeBrickVisibility)
-  uint32_t counts[4];
-  rc = recompute_visibility(ctx, 0, counts);
-  if (rc) return rc;
+// One subframe in two halves, so that a caller (the sort-last frame) can queue more work behind the traversal before
+// the host waits for the miss table: render_enqueue puts the raycast pass, the miss-table compaction and the
+// read-backs of the bookkeeping on the stream; render_finish waits, decodes the requests, pages the bricks in.
+static int render_enqueue(tvk_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   CU(cudaEventRecord(ctx->ev[0], s));
   CU(cudaMemsetAsync(ctx->hash_d, 0, (size_t)ctx->hash_size * 4, s));           // GLHashTable::ClearData
@@ -1441,7 +1522,7 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
     CU(cudaMemsetAsync(ctx->counters_d, 0, 8 * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(ctx->visited_d, 0, ctx->visited_h.size() * 4, s));
   }
-  rc = raycast_pass(ctx, true);
+  int rc = raycast_pass(ctx, true);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[1], s));
   // GLHashTable::GetData: compact on the device, read back count + (index,value) pairs
@@ -1453,6 +1534,11 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
     CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters_d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(ctx->visited_h.data(), ctx->visited_d, ctx->visited_h.size() * 4, cudaMemcpyDeviceToHost, s));
   }
+  return TVK_OK;
+}
+
+static int render_finish(tvk_ctx* ctx, tvk_frame_stats* st) {
+  cudaStream_t s = ctx->stream;
   CU(cudaStreamSynchronize(s));
   const uint32_t n_miss = ctx->miss_h[2 * (size_t)ctx->hash_size];
   ctx->last_missing.clear();
@@ -1478,7 +1564,7 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
   CU(cudaEventRecord(ctx->ev[2], s));
   uint32_t paged = 0;
   if (n_miss) {
-    rc = upload_bricks(ctx, ctx->last_missing.data(), n_miss, nullptr, &paged);
+    int rc = upload_bricks(ctx, ctx->last_missing.data(), n_miss, nullptr, &paged);
     if (rc) return rc;
   }
   CU(cudaEventRecord(ctx->ev[3], s));
@@ -1501,6 +1587,22 @@ int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
     cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[3]);
   }
   return TVK_OK;
+}
+
+int tvk_render(tvk_ctx* ctx, tvk_frame_stats* st) {
+  if (!ctx) return TVK_ERR_INVALID;
+  cudaSetDevice(ctx->cfg.device);
+  if (st) std::memset(st, 0, sizeof(*st));
+  int rc = check_renderable(ctx);
+  if (rc) return rc;
+  ctx->result_buf = nullptr;
+  // visibility follows TF / mode / isovalue changes (Changed1DTrans etc. -> RecomputeBrickVisibility)
+  uint32_t counts[4];
+  rc = recompute_visibility(ctx, 0, counts);
+  if (rc) return rc;
+  rc = render_enqueue(ctx);
+  if (rc) return rc;
+  return render_finish(ctx, st);
 }
 
 int tvk_render_stage(tvk_ctx* ctx, const void* in_resume_pos, const void* in_resume_color, tvk_frame_stats* st) {
@@ -2151,3 +2253,5 @@ int tvk_get_classic_brick_list(tvk_ctx* ctx, uint32_t* lod, tvk_classic_brick* d
 }
 
 }  // extern "C"
+
+#include "tvk_sortlast.inc"

@@ -66,6 +66,8 @@ struct VisState {
 
 }  // namespace tvk
 
+struct tvk_sortlast;
+
 struct tvk_ctx {
   tvk_device_cfg cfg{};
   std::string err;
@@ -168,6 +170,12 @@ struct tvk_ctx {
   uint32_t* visited_d = nullptr;
   std::vector<uint32_t> visited_h;
   void* unpair_d = nullptr;        // one slot of plain voxels (tvk_read_pool_slot)
+  // ---- sort-last (tvk_sortlast.inc) ----
+  tvk_sortlast* sl = nullptr;
+  float store_clip_min[3] = {0.0f, 0.0f, 0.0f}, store_clip_max[3] = {1.0f, 1.0f, 1.0f};   // tvk_set_store_shard
+  std::vector<int32_t> store_index;   // sharded device brick store: TOC index -> store slot or -1 (empty: identity)
+  int32_t* store_index_d = nullptr;
+  uint64_t store_count = 0;           // bricks kept in the store
 };
 
 #endif

@@ -609,6 +609,13 @@ class CudaGridLeaper:
         self._converged = bool(st.converged)
         return st
 
+    def probe_fetch(self, steps=256, direction=(0.3, 0.2, 0.93)):
+        """Fetch-path ceiling of the traversal kernel on this pool: (samples / s, ms) of loads + filter trees only."""
+        self._push_params()
+        ms, n = C.c_float(), C.c_uint64()
+        self._ck(self._lib.tvk_probe_fetch(self._h, int(steps), L.f32x3(*direction), C.byref(ms), C.byref(n)))
+        return n.value / (ms.value * 1e-3), ms.value
+
     def RaycastOnly(self):
         self._push_params()
         self._ck(self._lib.tvk_raycast_only(self._h))
@@ -653,6 +660,66 @@ class CudaGridLeaper:
         p = C.c_void_p()
         self._ck(self._lib.tvk_get_device_image(self._h, C.byref(p)))
         return p.value
+
+    # ------------------------------------------------------------------ sort-last inside the library (tvk_sortlast_*)
+    @staticmethod
+    def sortlast_unique_id():
+        """ncclGetUniqueId through the library (rank 0; hand the 128 bytes to the other ranks)."""
+        buf = (C.c_uint8 * L.COMM_ID_BYTES)()
+        rc = L.lib().tvk_sortlast_unique_id(buf)
+        if rc != L.OK:
+            raise L.TvkError(rc, (L.lib().tvk_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def SortLastInit(self, comm_id, rank, n_ranks, policy=L.SL_OCTANT):
+        buf = (C.c_uint8 * L.COMM_ID_BYTES)(*comm_id)
+        self._ck(self._lib.tvk_sortlast_init(self._h, buf, int(rank), int(n_ranks), int(policy)))
+        self._sl_n = int(n_ranks)
+
+    def SortLastShutdown(self):
+        self._ck(self._lib.tvk_sortlast_shutdown(self._h))
+
+    def SortLastBlock(self):
+        """(clip_min, clip_max, order, slice_lo, slice_hi) of this rank for the current view."""
+        self._push_params()
+        a, b = L.f32x3(), L.f32x3()
+        order = (C.c_int * self._sl_n)()
+        lo, hi = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.tvk_sortlast_get_block(self._h, a, b, C.cast(order, C.c_void_p), C.byref(lo), C.byref(hi)))
+        return tuple(a), tuple(b), list(order), lo.value, hi.value
+
+    def SortLastFrame(self):
+        """One subframe on every rank + direct-send compositing + RGBA8 gather on rank 0 (collective)."""
+        self._push_params()
+        st = L.SortLastStats()
+        self._ck(self._lib.tvk_sortlast_frame(self._h, C.byref(st)))
+        self.last_stats = st.frame
+        self._converged = bool(st.frame.converged)
+        return st
+
+    def SortLastReadRGBA8(self, out=None):
+        w, h = self.params.width, self.params.height
+        if out is None:
+            out = np.zeros((h, w, 4), np.uint8)
+        self._ck(self._lib.tvk_sortlast_read_rgba8(self._h, _ptr(out), 0))
+        return out
+
+    def SortLastReadRGBA8Async(self, out_pinned):
+        self._ck(self._lib.tvk_sortlast_read_rgba8_async(self._h, _ptr(out_pinned), 0))
+
+    def SortLastReadSlice(self, n_pixels):
+        out = np.zeros((n_pixels, 4), np.float32)
+        self._ck(self._lib.tvk_sortlast_read_slice(self._h, _ptr(out)))
+        return out
+
+    def SetStoreShard(self, clip_min, clip_max):
+        """Sort-last at the source: BuildVolume keeps only the bricks that touch this box (call before BuildVolume)."""
+        self._ck(self._lib.tvk_set_store_shard(self._h, L.f32x3(*clip_min), L.f32x3(*clip_max)))
+
+    def composite_nway(self, slice_ptrs, out_f_ptr, out8_ptr, n_pixels):
+        arr = (C.c_void_p * len(slice_ptrs))(*slice_ptrs)
+        self._ck(self._lib.tvk_composite_nway(self._h, C.cast(arr, C.c_void_p), len(slice_ptrs), C.c_void_p(out_f_ptr or None),
+                                              C.c_void_p(out8_ptr), n_pixels))
 
     def composite_over(self, front_ptr, back_ptr, out_ptr, n_pixels):
         self._ck(self._lib.tvk_composite_over(self._h, C.c_void_p(front_ptr), C.c_void_p(back_ptr),

@@ -443,3 +443,87 @@ class DepthPipeline:
             dist.send(self._wrap(col, n_pixels), dst=self.rank + 1)
             return st, None
         return st, self._wrap(img, n_pixels)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The in-library path (tvk_sortlast_*, csrc/tvk_sortlast.inc): partition, direct-send exchange over NCCL, n-way blend and
+# RGBA8 gather all happen inside libtvkcuda.so on the renderer's stream.  What is left here is the rendezvous (the
+# NCCL unique id travels over whatever process group the host already has) and host-side mirrors of the plan for tests.
+# ---------------------------------------------------------------------------------------------------------------------
+def plan(finest_layout, float_layout, extent, model_view, n_ranks, policy=0):
+    """tvk_sortlast_plan: (clip_min [n,3], clip_max [n,3], order [n]) -- host only, no device."""
+    import ctypes as C
+    from . import _lib as L
+    cmin = np.zeros((n_ranks, 3), np.float32)
+    cmax = np.zeros((n_ranks, 3), np.float32)
+    order = np.zeros(n_ranks, np.int32)
+    mv = np.ascontiguousarray(model_view, np.float32).reshape(-1)
+    rc = L.lib().tvk_sortlast_plan(L.u32x3(*[int(v) for v in finest_layout]), L.f32x3(*[float(v) for v in float_layout]),
+                                   (C.c_double * 3)(*[float(v) for v in extent]), L.f32x16(*mv), int(n_ranks), int(policy),
+                                   cmin.ctypes.data_as(C.c_void_p), cmax.ctypes.data_as(C.c_void_p),
+                                   order.ctypes.data_as(C.c_void_p))
+    if rc != L.OK:
+        raise L.TvkError(rc, (L.lib().tvk_last_error(None) or b"").decode())
+    return cmin, cmax, order
+
+
+def bsp_order(n_ranks, splits, float_layout, eye_norm):
+    """Front-to-back order of the blocks of shard_boxes() for a camera at eye_norm (host mirror of sl_order)."""
+    k = len(splits)
+    out = []
+
+    def walk(level, prefix):
+        if level == k:
+            out.append(prefix)
+            return
+        axis, cut = splits[level][prefix]
+        plane = 0.0 if cut == 0 else float(np.float32(cut) / np.float32(float_layout[axis]))
+        low = eye_norm[axis] < plane
+        walk(level + 1, prefix * 2 + (0 if low else 1))
+        walk(level + 1, prefix * 2 + (1 if low else 0))
+
+    walk(0, 0)
+    return out
+
+
+def slice_range(n_pixels, n_ranks, rank):
+    return n_pixels * rank // n_ranks, n_pixels * (rank + 1) // n_ranks
+
+
+def direct_send(image, rank, n_ranks, order, dist, over):
+    """Host mirror of the library's exchange for the gloo tests: every rank sends slice p of its partial image to rank p,
+    receives the partials of its own slice and folds them front to back in `order` (over(front, back) -> tensor).
+    Returns (lo, hi, composited slice)."""
+    import torch
+    n_pixels = image.shape[0]
+    lo, hi = slice_range(n_pixels, n_ranks, rank)
+    recv = {p: torch.empty((hi - lo, image.shape[1]), dtype=image.dtype) for p in range(n_ranks) if p != rank}
+    ops = []
+    for p in range(n_ranks):
+        if p == rank:
+            continue
+        plo, phi = slice_range(n_pixels, n_ranks, p)
+        ops.append(dist.P2POp(dist.isend, image[plo:phi].contiguous(), p))
+        ops.append(dist.P2POp(dist.irecv, recv[p], p))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    acc = None
+    for r in order:
+        part = image[lo:hi] if r == rank else recv[r]
+        acc = part.clone() if acc is None else over(acc, part)
+    return lo, hi, acc
+
+
+def init_library_sortlast(renderer, rank, n_ranks, dist=None, policy=0):
+    """Rendezvous for tvk_sortlast_init: rank 0 creates the NCCL unique id, the host's process group (torch.distributed,
+    any backend) carries its 128 bytes to the other ranks."""
+    import torch
+    from .renderer import CudaGridLeaper
+    if n_ranks > 1:
+        ids = [CudaGridLeaper.sortlast_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        cid = ids[0]
+    else:
+        cid = bytes(128)
+    renderer.SortLastInit(cid, rank, n_ranks, policy)

@@ -17,6 +17,11 @@ WORKLOADS = {
     "c3": dict(kind=synth.V_NOISE, size=(2048, 2048, 2048), dtype=L.U16, brick=36, overlap=2, mode=L.RM_2DTRANS,
                lighting=True, width=1920, height=1080, tf=(0.3, 0.4),
                label="2048^3 u16 bricked 36^3 GridLeaper 2D-TF+lighting 1920x1080"),
+    # second reported workload: C3 with a TRANSLUCENT table (alpha_max 2/255 instead of 16/255): rays
+    # are not cut short by early termination, so frames/s and Gsamples/s are shown where rays are long
+    "c3t": dict(kind=synth.V_NOISE, size=(2048, 2048, 2048), dtype=L.U16, brick=36, overlap=2, mode=L.RM_2DTRANS,
+                lighting=True, width=1920, height=1080, tf=(0.3, 0.4), alpha_max=2,
+                label="2048^3 u16 bricked 36^3 GridLeaper 2D-TF (translucent, alpha_max 2/255)+lighting 1920x1080"),
     # configs[3]: 1024^3 f32 isosurface + lighting
     "c4": dict(kind=synth.V_SPH, size=(1024, 1024, 1024), dtype=L.F32, brick=36, overlap=2, mode=L.RM_ISOSURFACE,
                lighting=True, width=1920, height=1080, tf=(0.3, 0.4), iso=0.35,
@@ -38,7 +43,7 @@ def transfer_functions(w):
     n = 256 if w["dtype"] == L.U8 else 4096
     t1 = TransferFunction1D(n)
     t1.SetStdFunction(*w["tf"])
-    t2 = TransferFunction2D.rectangle(w=n, h=256, x0=0.02, x1=0.9, alpha_max=16)
+    t2 = TransferFunction2D.rectangle(w=n, h=256, x0=0.02, x1=0.9, alpha_max=w.get("alpha_max", 16))
     return t1, t2
 
 
