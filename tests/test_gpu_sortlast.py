@@ -172,6 +172,8 @@ def test_single_rank_sortlast_frame_is_the_plain_frame(name):
     s = golden_scenes.make(name)
     ren = s.make_renderer("device")
     assert ren.PaintUntilConverged().converged
+    ren._dirty = True                     # a new frame on the now resident pool: one pass, no resumed rays (the floats of a
+    assert ren.Paint().converged          # resumed frame depend on its paging history)
     ref8 = ren.ReadRGBA8().copy()
     ref_f = ren.ReadRGBA32F().reshape(-1, 4).copy()
     sortlast.init_library_sortlast(ren, 0, 1)
