@@ -257,6 +257,23 @@ int tvk_compute_view(tvk_render_params* p, uint32_t width, uint32_t height,
 int tvk_default_params(tvk_render_params* p, uint32_t width, uint32_t height);
 /* any view/mode change: marks the region blank (new ray-entry buffer, GLGridLeaper.cpp:925-945) */
 int tvk_set_params(tvk_ctx* ctx, const tvk_render_params* p);
+/* AbstrRenderer::SetClipPlane / EnableClipPlane / DisableClipPlane (Renderer/AbstrRenderer.h:215-219) as GLGridLeaper
+ * implements them (GLGridLeaper.cpp:506-532,1337-1356): the bounding box whose front / back faces give every ray its
+ * entry and exit is cut by the plane (Clipper::BoxPlane, Basics/Clipper.cpp:137-167); the part with
+ * dot(normal, p) + d <= 0 is kept.  plane_model = (normal.xyz normalised, d) in the box's MODEL space (centre 0, extent =
+ * GetVolumeAABB), i.e. what FillBBoxVBO passes to BoxPlane: m_ClipPlane.Plane() * inverse(rotation * translation).
+ * Here the clipped polytope is not tessellated: the ray interval is cut analytically per pixel.  Marks the region
+ * blank.  GridLeaper path (tvk_render / tvk_paint / tvk_sortlast_frame); the classic path ignores it. */
+int tvk_set_clip_plane(tvk_ctx* ctx, int enabled, const float plane_model[4]);
+/* host-only helper: PLANE<float>::operator*(inverse(rotation * translation)) + the renormalisation of FillBBoxVBO
+ * (Basics/Vectors.h:1459-1487, GLGridLeaper.cpp:518-524) for a world-space plane (ExtendedPlane::Plane()). */
+int tvk_clip_plane_to_model(const float plane_world[4], const float rotation[16], const float translation[16],
+                            float plane_model[4]);
+/* GLRenderer::Pick (GLRenderer.cpp:2856-2872; AbstrRenderer.h:245): the isosurface hit position under a window
+ * position (mouse coordinates: y counted from the TOP row, as the reference reads m_vWinSize.y - mousePos.y).
+ * TVK_ERR_INVALID outside isosurface mode ("Can only determine pick locations in isosurface rendering mode.") or when
+ * the ray hit nothing ("No intersection."); out = rayHitPos.xyz of the last frame (eye space). */
+int tvk_pick(tvk_ctx* ctx, uint32_t mouse_x, uint32_t mouse_y, float out[3]);
 /* one subframe of GLGridLeaper::Render3DRegion (GLGridLeaper.cpp:914-1154): clear hash table,
  * raycast, read + decode hash table, page missing bricks in.  stats may be NULL. */
 int tvk_render(tvk_ctx* ctx, tvk_frame_stats* stats);

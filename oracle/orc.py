@@ -44,6 +44,7 @@ class RenderParams(C.Structure):
         ("tf_w", C.c_uint32), ("tf_h", C.c_uint32),
         ("hash_size", C.c_uint32), ("rehash_count", C.c_uint32), ("strategy", C.c_int),
         ("clip_min", f32x3), ("clip_max", f32x3), ("nearest", C.c_int), ("pipeline", C.c_int),
+        ("clip_plane_on", C.c_int), ("clip_plane", f32x4),
     ]
 
 

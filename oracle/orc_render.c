@@ -209,6 +209,18 @@ static int ray_setup_px(const orc_render_params* p, const uni* u, uint32_t px, u
   const float zero[3] = {0.0f, 0.0f, 0.0f}, one[3] = {1.0f, 1.0f, 1.0f};
   float s_in, s_out;
   if (!slab3(o, d, zero, one, &s_in, &s_out)) return 0;
+  if (p->clip_plane_on) {
+    /* FillBBoxVBO: the box is cut by the plane, f <= 0 is kept (Basics/Clipper.cpp:76-101).  Model space (centre 0, extent
+     * ex) -> the [0,1]^3 coordinates of the rays: p_model = (p - 0.5) * ex; f(s) = a + s * b along the ray */
+    float q[4];
+    q[0] = p->clip_plane[0] * u->extend.x; q[1] = p->clip_plane[1] * u->extend.y; q[2] = p->clip_plane[2] * u->extend.z;
+    q[3] = p->clip_plane[3] - 0.5f * (q[0] + q[1] + q[2]);
+    const float a = fmaf(q[2], o[2], fmaf(q[1], o[1], q[0] * o[0])) + q[3];
+    const float b = fmaf(q[2], d[2], fmaf(q[1], d[1], q[0] * d[0]));
+    if (b > 0.0f) s_out = fminf(s_out, (0.0f - a) / b);
+    else if (b < 0.0f) s_in = fmaxf(s_in, (0.0f - a) / b);
+    else if (a > 0.0f) return 0;
+  }
   float s0 = fmaxf(s_in, 1.0f);              /* near plane where the camera is inside / in front */
   if (!(s_out > s0)) return 0;               /* no back-face fragment in front of the near plane */
   if (shard_active(p) && !p->pipeline) {

@@ -14,6 +14,9 @@
 //     uniforms mv[16] vol[3] scale[3] light_dir[3] eye[3]   (SetupRaycastShader / ComputeEyeToModelMatrix)
 //     stereo ex ey ez  ax ay az  ux uy uz  fov aspect near far focal_length eye_dist
 //           (FLOATMATRIX4::BuildStereoLookAtAndProjection as GLRenderer::ComputeViewAndProjection calls it)
+//     clipbox plane_world[4] rotation[16] translation[16] extent[3]
+//           (GLGridLeaper::FillBBoxVBO, GLGridLeaper.cpp:506-532: Plane() * inverse(rotation*translation), normal normalised,
+//            then Clipper::BoxPlane on the 12 triangles of the box [-extent/2, extent/2]; prints the plane and the triangles)
 //     miprot window(0 sagittal,1 axial,2 coronal) flipx flipy angle_deg region_rotation[16] view[16]
 //           (the statements of GLRenderer::RenderHQMIPPreLoop + GLRaycaster::RenderHQMIPPreLoop on FLOATMATRIX4)
 #include <cstdio>
@@ -29,6 +32,7 @@
 #include "Basics/Vectors.h"
 #include "IO/TransferFunction1D.h"
 #include "Renderer/CullingLOD.h"
+#include "Basics/Clipper.h"
 
 using namespace tuvok;
 
@@ -85,6 +89,37 @@ int main(int argc, char** argv) {
       maMIPRotation = matRotDir * region_rotation * matFlipX * matFlipY * maMIPRotation;
       put16(out, "miprot", maMIPRotation);
       put16(out, "mipmv", maMIPRotation * view);   // GLRaycaster::RenderHQMIPPreLoop, GLRaycaster.cpp:489 (perspective)
+    } else if (op == "clipbox") {
+      float pw[4]; FLOATMATRIX4 rot, tra; FLOATVECTOR3 ext;
+      ls >> pw[0] >> pw[1] >> pw[2] >> pw[3]; read16(ls, rot); read16(ls, tra); ls >> ext.x >> ext.y >> ext.z;
+      const PLANE<float> plane(pw[0], pw[1], pw[2], pw[3]);
+      // GLGridLeaper.cpp:518-524
+      FLOATMATRIX4 inv = (rot * tra).inverse();
+      PLANE<float> transformed = plane * inv;
+      const FLOATVECTOR3 normal(transformed.xyz().normalized());
+      const float d = transformed.d();
+      fprintf(out, "plane %a %a %a %a\n", (double)normal.x, (double)normal.y, (double)normal.z, (double)d);
+      // the box as 12 triangles (what MaxMinBoxToVector emits: two per face; winding plays no role for BoxPlane)
+      const FLOATVECTOR3 lo = FLOATVECTOR3(0, 0, 0) - ext / 2.0f, hi = FLOATVECTOR3(0, 0, 0) + ext / 2.0f;
+      std::vector<FLOATVECTOR3> pos;
+      for (int axis = 0; axis < 3; axis++)
+        for (int side = 0; side < 2; side++) {
+          FLOATVECTOR3 c[4];
+          for (int k = 0; k < 4; k++) {
+            float v[3];
+            v[axis] = side ? hi[axis] : lo[axis];
+            const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+            v[a1] = (k == 1 || k == 2) ? hi[a1] : lo[a1];
+            v[a2] = (k >= 2) ? hi[a2] : lo[a2];
+            c[k] = FLOATVECTOR3(v[0], v[1], v[2]);
+          }
+          pos.push_back(c[0]); pos.push_back(c[1]); pos.push_back(c[2]);
+          pos.push_back(c[2]); pos.push_back(c[3]); pos.push_back(c[0]);
+        }
+      Clipper::BoxPlane(pos, normal, d);
+      fprintf(out, "tris %zu", pos.size() / 3);
+      for (size_t i = 0; i < pos.size(); i++) fprintf(out, " %a %a %a", (double)pos[i].x, (double)pos[i].y, (double)pos[i].z);
+      fprintf(out, "\n");
     } else if (op == "inverse") {
       FLOATMATRIX4 a; read16(ls, a);
       put16(out, "inverse", a.inverse());

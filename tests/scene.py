@@ -58,7 +58,7 @@ class Scene:
                  tf_center=0.4, tf_inv_gradient=0.4, tf2d=None, isovalue=None, sample_rate=1.0,
                  max_gpu_mem=1 << 30, seed=0x5EED, scale=(1.0, 1.0, 1.0), pool_size=None, hash_size=None,
                  strategy=orc.BS_SKIP_TWO, clip=((0, 0, 0), (1, 1, 1)), nearest=False, eye=(0, 0, 1.6), fov=50.0,
-                 max_grad=0.25, clamp=False):
+                 max_grad=0.25, clamp=False, clip_plane_model=None):
         self.kind, self.size, self.dtype = kind, tuple(size), dtype
         self.brick = (brick,) * 3 if np.isscalar(brick) else tuple(brick)
         self.overlap, self.mode, self.lighting = overlap, mode, bool(lighting)
@@ -68,6 +68,8 @@ class Scene:
         self.sample_rate, self.seed, self.scale = sample_rate, seed, tuple(scale)
         self.max_gpu_mem, self.strategy, self.clip, self.nearest = max_gpu_mem, strategy, clip, nearest
         self.eye, self.fov, self.max_grad, self.clamp = tuple(eye), fov, max_grad, clamp
+        # user clip plane as GLGridLeaper::FillBBoxVBO hands it to Clipper::BoxPlane: (normal, d) in the box's model space
+        self.clip_plane_model = None if clip_plane_model is None else tuple(float(F(v)) for v in clip_plane_model)
         self.bits = {orc.U8: 8, orc.U16: 16, orc.F32: 32}[dtype]
         self.range_max = {orc.U8: 255.0, orc.U16: 65535.0, orc.F32: 1.0}[dtype]
         self.isovalue = isovalue if isovalue is not None else self.range_max / 2
@@ -173,6 +175,9 @@ class Scene:
         p.clip_min = orc.f32x3(*self.clip[0])
         p.clip_max = orc.f32x3(*self.clip[1])
         p.nearest = int(self.nearest)
+        if self.clip_plane_model is not None:
+            p.clip_plane_on = 1
+            p.clip_plane = orc.f32x4(*self.clip_plane_model)
         return p
 
     def tf_bytes(self):
@@ -390,6 +395,9 @@ class Scene:
         r.SetTranslation(self.translation)
         r.SetViewParameters(self.fov, 0.01, 1000.0, self.eye, (0, 0, 0), (0, 1, 0))
         r.SetShardBox(*self.clip)
+        if self.clip_plane_model is not None:
+            r.SetClipPlaneModel(self.clip_plane_model)
+            r.EnableClipPlane()
         r.CreateVolumePool(self._pool_size)
         return r
 

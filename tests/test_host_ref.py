@@ -168,3 +168,85 @@ def test_raycast_uniforms_follow_setupraycastshader(tmp_path, name):
     np.testing.assert_allclose(u["eye_m"], vecs[6:9], rtol=0, atol=2e-6)
     ext = np.array(s.size, np.float32) * np.array(s.scale, np.float32)
     assert np.float32(u["lzwse"]) == np.max((ext / ext.max()).astype(np.float32) / np.array(s.size, np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clip plane: GLGridLeaper::FillBBoxVBO cuts the bounding box with Clipper::BoxPlane and rasterises the
+# polytope's front / back faces; the library cuts the ray interval analytically.  Pinned here against the UNMODIFIED
+# Basics/Clipper.cpp + PLANE<float> (ref_host clipbox): the analytic entry / exit of every pixel lie on the reference's
+# triangles, and pixels the plane removes do not meet the clipped polytope at all.
+def _line_tri_hits(o, d, tris):
+    """Moeller-Trumbore for lines o + t*d (n, 3) against triangles (m, 3, 3): t (n, m), nan where the line misses."""
+    v0, e1, e2 = tris[:, 0][None], (tris[:, 1] - tris[:, 0])[None], (tris[:, 2] - tris[:, 0])[None]
+    dd, oo = d[:, None, :], o[:, None, :]
+    pv = np.cross(dd, e2)
+    det = np.einsum("nmk,nmk->nm", np.broadcast_to(e1, pv.shape), pv)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / det
+        tv = oo - v0
+        u = np.einsum("nmk,nmk->nm", tv, pv) * inv
+        qv = np.cross(tv, np.broadcast_to(e1, tv.shape))
+        v = np.einsum("nmk,nmk->nm", np.broadcast_to(dd, qv.shape), qv) * inv
+        t = np.einsum("nmk,nmk->nm", np.broadcast_to(e2, qv.shape), qv) * inv
+    eps = 1e-6
+    ok = (np.abs(det) > 1e-12) & (u >= -eps) & (v >= -eps) & (u + v <= 1 + eps)
+    return np.where(ok, t, np.nan)
+
+
+CLIP_CASES = [
+    # world-space plane (normal, d), rotation, translation, scene overrides
+    ((0.0, 0.0, 1.0, 0.0), ROT_ID := np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32), {}),
+    ((0.3, -0.5, 0.8, 0.1), (tb.rotation_y(33.0) @ tb.rotation_x(-12.0)).astype(np.float32), tb.translation(0.05, -0.02, 0.1), {}),
+    ((-0.7, 0.2, -0.4, -0.15), (tb.rotation_y(-60.0) @ tb.rotation_x(25.0)).astype(np.float32), np.eye(4, dtype=np.float32),
+     dict(size=(64, 40, 24), scale=(1.0, 1.0, 2.0))),
+    # camera inside the volume, in the removed half: every ray starts on the cap polygon ...
+    ((0.0, 0.3, 1.0, -1.2), np.eye(4, dtype=np.float32), tb.translation(0.0, 0.0, 1.3), {}),
+    # ... and in the kept half: every ray starts on the near plane, some leave through the cap
+    ((0.0, 0.3, -1.0, 1.45), np.eye(4, dtype=np.float32), tb.translation(0.0, 0.0, 1.3), {}),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CLIP_CASES)))
+def test_clip_plane_matches_reference_clipper(tmp_path, case):
+    plane_w, rot, tra, over = CLIP_CASES[case]
+    kw = dict(kind=0, size=(32, 32, 32), dtype=orc.U8, brick=20, overlap=2, width=72, height=56, rotation=rot, translation=tra)
+    kw.update(over)
+    s0 = scene.Scene(**kw)
+    ext = np.array(s0.size, np.float32) * np.array(s0.scale, np.float32)
+    ext = ext / ext.max()
+    rows = run(tmp_path, ["clipbox %s %s %s %s" % (fl(plane_w), fl(rot), fl(tra), fl(ext))])
+    ref_plane = hexf(rows[0][1:])
+    tris = hexf(rows[1][2:]).astype(np.float64).reshape(-1, 3, 3)
+    assert tris.shape[0] == int(rows[1][1]) and tris.shape[0] >= 4
+    # 1. the library's world -> model helper == PLANE<float> * inverse(rotation * translation), normal normalised
+    got = L.f32x4()
+    assert L.lib().tvk_clip_plane_to_model(L.f32x4(*plane_w), L.f32x16(*rot.reshape(-1)), L.f32x16(*tra.reshape(-1)), got) == L.OK
+    assert np.abs(np.array(got, np.float32) - ref_plane).max() <= 2e-6
+    # 2. the oracle's analytic ray interval against the reference's clipped polytope
+    s = scene.Scene(clip_plane_model=tuple(ref_plane), **kw)
+    pool, _ = s.oracle_pool()
+    e_c, x_c, cov_c = orc.ray_setup(s.oracle_params(pool))
+    e_b, x_b, cov_b = orc.ray_setup(s0.oracle_params(pool))
+    assert cov_b.sum() > 200 and 0 < cov_c.sum() <= cov_b.sum()
+    assert not np.any(cov_c & ~cov_b.astype(bool))                     # the plane only removes
+    tn = tris / ext[None, None, :].astype(np.float64) + 0.5             # model space -> the [0,1]^3 coordinates of the rays
+    sel = np.flatnonzero(cov_c)
+    o, d = e_c[sel, :3].astype(np.float64), (x_c[sel, :3] - e_c[sel, :3]).astype(np.float64)
+    t = _line_tri_hits(o, d, tn)
+    ln = np.linalg.norm(d, axis=1)                                       # distances in units of the volume's longest side
+    tmin, tmax = np.nanmin(t, axis=1) * ln, np.nanmax(t, axis=1) * ln
+    assert np.abs(tmax - ln).max() <= 1e-4                              # the exit lies on a back face of the polytope
+    near = np.abs(e_c[sel, 3] + 0.01) <= 1e-6                            # entry on the near plane (eye-space z = -near)
+    assert not (~near).any() or np.abs(tmin[~near]).max() <= 1e-4                            # otherwise the entry lies on a front face
+    assert np.all(tmin[near] <= 1e-4)
+    if case >= 3:
+        assert near.all() if case == 4 else not near.any()
+    # 3. pixels of the box that the plane removed: the line never meets the polytope in front of the near plane
+    gone = np.flatnonzero(cov_b.astype(bool) & ~cov_c.astype(bool))
+    o, d = e_b[gone, :3].astype(np.float64), (x_b[gone, :3] - e_b[gone, :3]).astype(np.float64)
+    t = _line_tri_hits(o, d, tn)
+    with np.errstate(invalid="ignore"):
+        inside = np.nanmax(np.where((t > 1e-3) & (t < 1 - 1e-3), 1.0, np.nan), axis=1) if t.size else np.array([])
+    span = np.nanmax(t, axis=1) - np.nanmin(t, axis=1) if t.size else np.array([])
+    bad = np.flatnonzero(np.nan_to_num(inside) * (np.nan_to_num(span) > 5e-3))
+    assert bad.size <= max(2, gone.size // 100), (bad.size, gone.size)  # grazing silhouette pixels aside

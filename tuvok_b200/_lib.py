@@ -127,6 +127,9 @@ SIGNATURES = {
                                    f32x3, C.c_float, C.c_float, C.c_float, C.c_float]),
     "tvk_default_params": (C.c_int, [C.POINTER(RenderParams), C.c_uint32, C.c_uint32]),
     "tvk_set_params": (C.c_int, [P, C.POINTER(RenderParams)]),
+    "tvk_set_clip_plane": (C.c_int, [P, C.c_int, f32x4]),
+    "tvk_clip_plane_to_model": (C.c_int, [f32x4, f32x16, f32x16, f32x4]),
+    "tvk_pick": (C.c_int, [P, C.c_uint32, C.c_uint32, f32x3]),
     "tvk_render": (C.c_int, [P, C.POINTER(FrameStats)]),
     "tvk_paint": (C.c_int, [P, C.c_uint32, C.POINTER(FrameStats)]),
     "tvk_raycast_only": (C.c_int, [P]),

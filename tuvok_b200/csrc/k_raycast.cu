@@ -398,6 +398,14 @@ __device__ __forceinline__ bool ray_setup(const RayConsts& P, uint32_t px, uint3
     s_in = fmaxf(s_in, fminf(t0, t1));
     s_out = fminf(s_out, fmaxf(t0, t1));
   }
+  if (P.clip_plane_on) {
+    // the bbox cut by the clip plane (Clipper::BoxPlane keeps f <= 0): f(s) = a + s * b along the ray
+    const float a = fmaf(P.clip_plane[2], o[2], fmaf(P.clip_plane[1], o[1], P.clip_plane[0] * o[0])) + P.clip_plane[3];
+    const float b = fmaf(P.clip_plane[2], d[2], fmaf(P.clip_plane[1], d[1], P.clip_plane[0] * d[0]));
+    if (b > 0.0f) s_out = fminf(s_out, (0.0f - a) / b);
+    else if (b < 0.0f) s_in = fmaxf(s_in, (0.0f - a) / b);
+    else if (a > 0.0f) return false;
+  }
   const float s0 = fmaxf(s_in, 1.0f);
   if (!(s_out > s0)) return false;
   if (P.shard && shard_test) {

@@ -42,6 +42,8 @@ struct RayConsts {
   float clip_min[3], clip_max[3];   // sort-last shard box (ray hit test)
   int32_t shard;                    // shard box != whole volume
   float sh_lo[3], sh_hi[3];         // shard box with faces on the volume border pushed to -/+inf
+  int32_t clip_plane_on;            // bbox cut by the user clip plane (GLGridLeaper::FillBBoxVBO)
+  float clip_plane[4];              // ... in the [0,1]^3 coordinates of the ray set-up: kept where dot(xyz, p) + w <= 0
   int32_t nearest;
   int32_t first_pass;   // region is blank: ray entry computed, start colour = 0
   int32_t pipeline;     // this launch is a stage of the depth pipeline (k_raycast.cu PIPE)

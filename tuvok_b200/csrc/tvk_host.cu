@@ -574,6 +574,13 @@ int derive(tvk_ctx* ctx, RayConsts& u) {
     u.sh_lo[i] = p.clip_min[i] > 0.0f ? p.clip_min[i] : -INFINITY;
     u.sh_hi[i] = p.clip_max[i] < 1.0f ? p.clip_max[i] : INFINITY;
   }
+  if (ctx->clip_plane_on) {
+    // model space (centre 0, extent ex) -> the [0,1]^3 coordinates of ray_setup: p_model = (p - 0.5) * ex
+    u.clip_plane_on = 1;
+    const float* q = ctx->clip_plane;
+    for (int i = 0; i < 3; i++) u.clip_plane[i] = q[i] * ex[i];
+    u.clip_plane[3] = q[3] - 0.5f * (u.clip_plane[0] + u.clip_plane[1] + u.clip_plane[2]);
+  }
   u.lod_count = ctx->pool_lod_count;
   for (uint32_t l = 0; l < ctx->pool_lod_count; l++) {
     u.lod_offset[l] = ctx->lod_offset[l];
@@ -1472,6 +1479,70 @@ int tvk_set_params(tvk_ctx* ctx, const tvk_render_params* p) {
   ctx->params = *p;
   ctx->have_params = true;
   ctx->blank = true;
+  return TVK_OK;
+}
+
+int tvk_set_clip_plane(tvk_ctx* ctx, int enabled, const float plane_model[4]) {
+  if (!ctx) return TVK_ERR_INVALID;
+  if (enabled) {
+    if (!plane_model) return fail(ctx, TVK_ERR_INVALID, "NULL clip plane");
+    const float len = sqrtf(plane_model[0] * plane_model[0] + plane_model[1] * plane_model[1] + plane_model[2] * plane_model[2]);
+    if (!(len > 0.0f) || !std::isfinite(len) || !std::isfinite(plane_model[3])) return fail(ctx, TVK_ERR_INVALID, "degenerate clip plane");
+    std::memcpy(ctx->clip_plane, plane_model, 16);
+  }
+  ctx->clip_plane_on = enabled != 0;
+  ctx->blank = true;
+  return TVK_OK;
+}
+
+// PLANE<T>::transform(m): this = this * transpose(inverse(m)), normalised by |xyz| (Basics/Vectors.h:1459-1478) with
+// m = inverse(rotation * translation) (GLGridLeaper.cpp:518-520), so transpose(inverse(m)) = transpose(rotation * translation);
+// FillBBoxVBO then normalises xyz once more and keeps d
+int tvk_clip_plane_to_model(const float plane_world[4], const float rotation[16], const float translation[16], float plane_model[4]) {
+  if (!plane_world || !rotation || !translation || !plane_model) return fail(nullptr, TVK_ERR_INVALID, "NULL argument");
+  float rt[16], inv[16], back[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      float a = 0.0f;
+      for (int k = 0; k < 4; k++) a += rotation[r * 4 + k] * translation[k * 4 + c];
+      rt[r * 4 + c] = a;
+    }
+  // the reference inverts twice in float (inverse() of the product, then transform() inverts its argument again)
+  double d1[16], d2[16], d3[16];
+  for (int i = 0; i < 16; i++) d1[i] = rt[i];
+  if (!inv4(d1, d2)) return fail(nullptr, TVK_ERR_INVALID, "singular rotation * translation");
+  for (int i = 0; i < 16; i++) { inv[i] = (float)d2[i]; d2[i] = inv[i]; }
+  if (!inv4(d2, d3)) return fail(nullptr, TVK_ERR_INVALID, "singular rotation * translation");
+  for (int i = 0; i < 16; i++) back[i] = (float)d3[i];
+  float v[4];
+  for (int c = 0; c < 4; c++) {   // row vector times transpose(back): v[c] = sum_k plane[k] * back[c][k]
+    float a = 0.0f;
+    for (int k = 0; k < 4; k++) a += plane_world[k] * back[c * 4 + k];
+    v[c] = a;
+  }
+  float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  if (!(len > 0.0f)) return fail(nullptr, TVK_ERR_INVALID, "degenerate clip plane");
+  for (int c = 0; c < 4; c++) v[c] = v[c] / len;
+  len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  for (int c = 0; c < 3; c++) plane_model[c] = v[c] / len;
+  plane_model[3] = v[3];
+  return TVK_OK;
+}
+
+int tvk_pick(tvk_ctx* ctx, uint32_t mouse_x, uint32_t mouse_y, float out[3]) {
+  if (!ctx || !out) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  if (!ctx->have_params || ctx->params.mode != TVK_RM_ISOSURFACE)
+    return fail(ctx, TVK_ERR_INVALID, "Can only determine pick locations in isosurface rendering mode.");
+  if (!ctx->img_w || !ctx->buf[0]) return fail(ctx, TVK_ERR_INVALID, "no frame");
+  // GL window coordinates: row m_vWinSize.y - mousePos.y counted from the bottom; rows outside the target read nothing
+  if (mouse_x >= ctx->img_w || mouse_y == 0 || mouse_y > ctx->img_h) return fail(ctx, TVK_ERR_INVALID, "No intersection.");
+  cudaSetDevice(ctx->cfg.device);
+  const size_t i = (size_t)(ctx->img_h - mouse_y) * ctx->img_w + mouse_x;
+  float v[4];
+  CU(cudaMemcpyAsync(v, ctx->buf[0] + i, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (v[3] == 0.0f) return fail(ctx, TVK_ERR_INVALID, "No intersection.");
+  out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
   return TVK_OK;
 }
 

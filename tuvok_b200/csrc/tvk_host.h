@@ -157,6 +157,7 @@ struct tvk_ctx {
   struct ClearView { bool on = false; double iso = 0.8; float color[3] = {1, 0, 0}; float size = 5.5f, context = 1.0f, border = 60.0f;
                      float pos[4] = {0, 0, 0.5f, 1.0f}; } cv;
   bool cv_frame = false;          // the last classic frame filled the ClearView targets
+  bool clip_plane_on = false; float clip_plane[4] = {0, 0, 1, 0};   // model-space clip plane of the bbox (tvk_set_clip_plane)
   bool stage_mode = false;        // tvk_render_stage in progress: raycast_pass launches a depth-pipeline stage
   const float4* stage_ray_start = nullptr; const float4* stage_color = nullptr;   // its inputs (nullptr: first stage)
   float4* result_buf = nullptr;   // set by frames whose result does not follow the mode rule of result_image() (MIP, stereo)

@@ -109,6 +109,7 @@ class CudaGridLeaper:
         self._fov, self._znear, self._zfar = 50.0, 0.01, 1000.0
         self._rotation, self._translation = IDENTITY.copy(), IDENTITY.copy()
         self._user_matrices = None
+        self._clip_plane, self._clip_on, self._clip_model = (0.0, 0.0, 1.0, 0.0), False, None   # ExtendedPlane default: z = 0, disabled
         self._dirty = True
         self._converged = False
         self.tf1d = None
@@ -451,6 +452,49 @@ class CudaGridLeaper:
         self._converged = bool(stats[0].converged and stats[1].converged)
         return stats
 
+    # ------------------------------------------------------------------ clip plane (AbstrRenderer.h:215-219)
+    def SetClipPlane(self, plane):
+        """AbstrRenderer::SetClipPlane: plane = ExtendedPlane::Plane() = (normal, d) in WORLD space; the kept side is
+        dot(normal, p) + d <= 0 (GLGridLeaper::FillBBoxVBO -> Clipper::BoxPlane)."""
+        self._clip_plane = tuple(float(v) for v in plane)
+        self._clip_model = None
+        self._dirty = True
+
+    def SetClipPlaneModel(self, plane):
+        """The plane already in the box's model space (what a C++ shim computes with the reference's own PLANE / FLOATMATRIX4
+        classes); overrides the world-space plane until SetClipPlane is called again."""
+        self._clip_model = tuple(float(v) for v in plane)
+        self._dirty = True
+
+    def EnableClipPlane(self):
+        self._clip_on = True
+        self._dirty = True
+
+    def DisableClipPlane(self):
+        self._clip_on = False
+        self._dirty = True
+
+    def IsClipPlaneEnabled(self):
+        return self._clip_on
+
+    def clip_plane_model(self):
+        """The plane FillBBoxVBO hands to Clipper::BoxPlane: Plane() * inverse(rotation * translation), normal normalised."""
+        if self._clip_model is not None:
+            return self._clip_model
+        out = L.f32x4()
+        rc = self._lib.tvk_clip_plane_to_model(L.f32x4(*self._clip_plane), L.f32x16(*self._rotation.reshape(-1)),
+                                               L.f32x16(*self._translation.reshape(-1)), out)
+        if rc != L.OK:
+            raise L.TvkError(rc, (self._lib.tvk_last_error(None) or b"").decode())
+        return tuple(out)
+
+    def Pick(self, mouse_pos):
+        """GLRenderer::Pick (GLRenderer.cpp:2856-2872): isosurface hit position under a window position (y from the top);
+        raises as the reference throws (wrong mode / no intersection)."""
+        out = L.f32x3()
+        self._ck(self._lib.tvk_pick(self._h, int(mouse_pos[0]), int(mouse_pos[1]), out))
+        return tuple(out)
+
     def SetShardBox(self, clip_min, clip_max):
         """Sort-last: restrict rays to this rank's convex brick block (normalised volume coords)."""
         self.params.clip_min = L.f32x3(*clip_min)
@@ -474,6 +518,7 @@ class CudaGridLeaper:
             if lf is not None:
                 p.lod_factor = lf
         self._ck(self._lib.tvk_set_params(self._h, C.byref(p)))
+        self._ck(self._lib.tvk_set_clip_plane(self._h, int(self._clip_on), L.f32x4(*self.clip_plane_model()) if self._clip_on else None))
         self._dirty = False
         self._converged = False
 
