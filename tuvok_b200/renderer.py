@@ -518,7 +518,7 @@ class CudaGridLeaper:
             if lf is not None:
                 p.lod_factor = lf
         self._ck(self._lib.tvk_set_params(self._h, C.byref(p)))
-        self._ck(self._lib.tvk_set_clip_plane(self._h, int(self._clip_on), L.f32x4(*self.clip_plane_model()) if self._clip_on else None))
+        self._ck(self._lib.tvk_set_clip_plane(self._h, int(self._clip_on), L.f32x4(*(self.clip_plane_model() if self._clip_on else (0.0, 0.0, 1.0, 0.0)))))
         self._dirty = False
         self._converged = False
 
