@@ -306,17 +306,19 @@ def merge_parity(results):
 
 # Sort-last composite against the single-GPU frame.  The chain that is checked BIT FOR BIT is: every rank's partial image ==
 # the oracle's partial image (`parity`, scope "every rank's partial image") and the n-way over kernel == orc_over
-# (tests/test_gpu_sortlast.py).  The composite itself cannot equal the single-GPU frame bit for bit: a back rank
-# accumulates its block without knowing the alpha in front of it, so where the single-GPU ray ends INSIDE a back block
-# (alpha crossing 0.99 there) the over operator can only cut the back image uniformly (colour error
-# up to 0.0086 = 2.2/255 before rounding when the near and far part of the back block differ in colour).  The gate is
-# therefore: PSNR >= 45 dB over all pixels, max |delta| <= 2/255 on all pixels but an outlier budget of 1e-5 of them,
-# and no pixel further off than 6/255; `ok_strict` says whether max <= 2/255 held on every pixel.
+# (tests/test_gpu_sortlast.py).  The composite itself cannot equal the single-GPU frame bit for bit, for two reasons the
+# reference shares (DESIGN.md sections 4, 5): (1) sample positions live in pool coordinates, i.e. relative to the slot a
+# brick happens to occupy, and a rank's pool holds other bricks in other slots than the single GPU's -- positions move
+# by an ulp and now and then a sample falls on the other side of a transfer-function edge (nearest-neighbour tables):
+# that pixel changes by up to ONE sample's contribution; (2) a back rank accumulates its block without knowing the
+# alpha in front of it, so where the single-GPU ray ends inside a back block the over operator can only cut the back
+# image uniformly (<= 0.0086 = 2.2/255 before rounding).  The gate is therefore: PSNR >= 45 dB over all pixels,
+# max |delta| <= 2/255 on all pixels but an outlier budget of 1e-5 of them, and no pixel further off than one sample's
+# largest contribution (the table's maximal opacity) + 2; `ok_strict` says whether max <= 2/255 held on every pixel.
 COMPOSITE_OUTLIER_FRACTION = 1e-5
-COMPOSITE_HARD_MAX_255 = 6
 
 
-def composite_gate(res, world):
+def composite_gate(res, world, hard_max):
     import math
     import parity_gate
     n = sum(x["pixels"] for x in res)
@@ -324,15 +326,16 @@ def composite_gate(res, world):
     psnr = min(x["psnr"] for x in res)
     over2 = sum(x["over_2"] for x in res)
     budget = int(math.ceil(COMPOSITE_OUTLIER_FRACTION * n))
-    ok = psnr >= parity_gate.MIN_PSNR_DB and over2 <= budget and mx <= COMPOSITE_HARD_MAX_255
+    ok = psnr >= parity_gate.MIN_PSNR_DB and over2 <= budget and mx <= hard_max
     return {"ok": bool(ok), "ok_strict": bool(ok and mx <= parity_gate.MAX_ABS_255), "max_abs_255": int(mx),
             "psnr_db": "inf" if math.isinf(psnr) else round(psnr, 2), "pixels": int(n), "views": len(res),
             "pixels_over_1": int(sum(x["over_1"] for x in res)), "pixels_over_2": int(over2), "outlier_budget": budget,
             "worst": [e for x in res for e in x["worst"]][:8],
             "checker": ("the gathered %d-rank frame (RGBA8, all pixels) against the frame of the same view rendered by ONE GPU "
                         "through the same library before the store was sharded; gate: PSNR >= 45 dB, max <= 2/255 on all but "
-                        "%g of the pixels (early ray termination across block faces, DESIGN.md section 5), none above %d/255"
-                        % (world, COMPOSITE_OUTLIER_FRACTION, COMPOSITE_HARD_MAX_255))}
+                        "%g of the pixels (slot-dependent sample positions at transfer-function edges, early ray termination across "
+                        "block faces: DESIGN.md section 5), none above one sample's largest contribution + 2 = %d/255"
+                        % (world, COMPOSITE_OUTLIER_FRACTION, hard_max))}
 
 
 def run_tvk(args, rank, world, local_rank):
@@ -610,7 +613,7 @@ def run_tvk(args, rank, world, local_rank):
                 res.append({"max_abs_255": mx, "psnr": psnr, "pixels": int(d8.size), "over_1": int((d8 > 1).sum()),
                             "over_2": int((d8 > parity_gate.MAX_ABS_255).sum()), "worst": worst})
         if rank == 0:
-            composite = composite_gate(res, world)
+            composite = composite_gate(res, world, int(w.get("alpha_max", 16)) + 2)
 
     times = torch.tensor([ms_total, ms_ray, e2e_s * 1e3, float(not_conv)], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(np.sum(samples)), float(np.sum(touched))], dtype=torch.float64, device="cuda")

@@ -208,6 +208,47 @@ int tvk_uvf_probe_stats(const char* path, uint64_t timestep, double range[2], ui
 int tvk_octree_file_probe(const char* path, uint64_t offset, uint64_t uvf_file_version, tvk_octree_file_info* info);
 int tvk_octree_file_read_brick(const char* path, uint64_t offset, uint64_t uvf_file_version, uint32_t x, uint32_t y,
                                uint32_t z, uint32_t lod, void* dst, size_t cap, uint32_t out_size[3]);
+/* ---- procedural multi-resolution dataset (BASELINE configs[4]: 8192^3 uint8 = 512 GiB, a volume that exists nowhere at
+ * once).  Level l of the hierarchy is the seeded analytic field of tvk_synth_volume sampled on that level's grid (domain
+ * size ceil-halved l times -- the level sizes of ExtendedOctree, ExtendedOctree.cpp:167-199), bricked like a converted
+ * file (max_brick_size incl. `overlap` ghost voxels per side, 0 outside the level's grid).  It stands where a
+ * UVFDataset would: Dataset::GetBrick (IO/uvfDataset.cpp:1690-1712) is answered by host threads that generate the
+ * requested brick into the library's pinned staging memory, from where it is paged in like any other brick
+ * (GLVolumePool::UploadBricks, GLVolumePool.cpp:1720-1789: pinned cudaMemcpyAsync on the copy stream, double buffered);
+ * only bricks the LOD-driven traversal asks for are ever produced.  host_cache_bytes > 0 keeps generated bricks in a
+ * host-side LRU cache in front of the generator (the role the OS page cache plays for a .uvf file), so a brick the device
+ * pool evicted streams back at memory speed.  minmax = the MaxMinDataBlock-equivalent table for all pool-LoD bricks in
+ * TOC order (4 doubles per brick; from tvk_procedural_minmax, possibly computed in slices by several ranks) or NULL: it
+ * is then computed on this device.  threads = host generator threads (0: all cores). */
+int tvk_set_procedural_volume(tvk_ctx* ctx, int kind, const uint32_t size[3], int dtype, uint32_t seed, const float scale[3],
+                              const uint32_t max_brick_size[3], uint32_t overlap, double range_max,
+                              float max_gradient_magnitude, const double* minmax, uint64_t n_minmax,
+                              uint64_t host_cache_bytes, uint32_t threads);
+/* host-only: number of bricks / LoDs of the pool LoDs (down to the first single-brick level) of such a dataset */
+int tvk_procedural_brick_count(const uint32_t size[3], const uint32_t max_brick_size[3], uint32_t overlap, uint64_t* n_bricks,
+                               uint32_t* n_lods);
+/* host-only parity tap: one brick of such a dataset exactly as the generator threads produce it (x fastest, tightly
+ * packed at its own size incl. ghost; out_size may be NULL) */
+int tvk_procedural_brick(int kind, const uint32_t size[3], int dtype, uint32_t seed, const uint32_t max_brick_size[3],
+                         uint32_t overlap, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, void* dst, size_t cap,
+                         uint32_t out_size[3]);
+/* per-brick min/max (incl. ghost; {min, max, -DBL_MAX, DBL_MAX} like tvk_build_volume) of the bricks [first, first+count)
+ * in TOC order, evaluated on the device without materialising the bricks; needs no dataset to be set */
+int tvk_procedural_minmax(tvk_ctx* ctx, int kind, const uint32_t size[3], int dtype, uint32_t seed,
+                          const uint32_t max_brick_size[3], uint32_t overlap, uint64_t first, uint64_t count, double* dst);
+/* totals of the streaming path since tvk_create (callback / file / procedural sources) */
+typedef struct {
+  uint64_t bricks_uploaded;        /* bricks that went host -> pool */
+  uint64_t h2d_bytes;              /* bytes of those copies (slot-sized) */
+  double   upload_ms;              /* host wall time inside the upload path (source + copy, overlapped) */
+  double   h2d_ms;                 /* device time of the pinned H2D brick copies alone (events on the copy stream) */
+  uint64_t bricks_generated;       /* procedural source: bricks produced by the generator */
+  uint64_t host_cache_hits;        /* ... served from the host cache instead */
+  uint64_t host_cache_evictions;
+  double   source_thread_ms;       /* ... thread-milliseconds spent producing / copying bricks on the host */
+  uint32_t source_threads;
+} tvk_stream_stats;
+int tvk_get_stream_stats(tvk_ctx* ctx, tvk_stream_stats* out);
 int tvk_get_info(const tvk_ctx* ctx, tvk_info* out);
 /* parity taps: MaxMinForKey table and one brick (x-fastest, own size incl. ghost) */
 int tvk_get_minmax(tvk_ctx* ctx, double* dst, uint64_t n_bricks);

@@ -86,6 +86,12 @@ LOG_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p)
 
 P = C.c_void_p
 # every symbol include/tvk.h declares: name -> (restype, argtypes)
+class StreamStats(C.Structure):
+    _fields_ = [("bricks_uploaded", C.c_uint64), ("h2d_bytes", C.c_uint64), ("upload_ms", C.c_double), ("h2d_ms", C.c_double),
+                ("bricks_generated", C.c_uint64), ("host_cache_hits", C.c_uint64), ("host_cache_evictions", C.c_uint64),
+                ("source_thread_ms", C.c_double), ("source_threads", C.c_uint32)]
+
+
 SIGNATURES = {
     "tvk_abi_version": (C.c_uint32, []),
     "tvk_create": (C.c_int, [C.POINTER(DeviceCfg), C.POINTER(P)]),
@@ -109,6 +115,13 @@ SIGNATURES = {
     "tvk_octree_file_read_brick": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                              C.c_uint32, P, C.c_size_t, u32x3]),
     "tvk_synth_volume": (C.c_int, [P, P, C.c_int, u32x3, C.c_int, C.c_uint32]),
+    "tvk_set_procedural_volume": (C.c_int, [P, C.c_int, u32x3, C.c_int, C.c_uint32, f32x3, u32x3, C.c_uint32, C.c_double, C.c_float,
+                                            P, C.c_uint64, C.c_uint64, C.c_uint32]),
+    "tvk_procedural_brick_count": (C.c_int, [u32x3, u32x3, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "tvk_procedural_brick": (C.c_int, [C.c_int, u32x3, C.c_int, C.c_uint32, u32x3, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, P, C.c_size_t, u32x3]),
+    "tvk_procedural_minmax": (C.c_int, [P, C.c_int, u32x3, C.c_int, C.c_uint32, u32x3, C.c_uint32, C.c_uint64, C.c_uint64, P]),
+    "tvk_get_stream_stats": (C.c_int, [P, C.POINTER(StreamStats)]),
     "tvk_get_info": (C.c_int, [P, C.POINTER(Info)]),
     "tvk_get_minmax": (C.c_int, [P, P, C.c_uint64]),
     "tvk_get_brick_size": (C.c_int, [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32x3]),

@@ -11,75 +11,12 @@
 // HBM-bound integer work: coalesced x-fastest reads/writes, one CTA per brick.
 #include <cfloat>
 #include "tvk_dev.h"
+#include "tvk_synth.cuh"
 
 namespace tvk {
 namespace {
 
 constexpr int kSMs = 148;
-
-// ---------------------------------------------------------------------------------------------
-// synthetic volumes -- integer arithmetic only, so tuvok_b200/synth.py reproduces them bit for bit
-// ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x, uint32_t y, uint32_t z, uint32_t seed) {
-  uint32_t h = seed ^ (x * 0x9E3779B1u) ^ (y * 0x85EBCA77u) ^ (z * 0xC2B2AE3Du);
-  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
-  return h;
-}
-
-__device__ __forceinline__ uint64_t lattice_noise(uint32_t x, uint32_t y, uint32_t z, uint32_t shift, uint32_t seed) {
-  const uint32_t ix = x >> shift, iy = y >> shift, iz = z >> shift;
-  const uint64_t one = 1ull << shift, m = one - 1;
-  const uint64_t fx = x & m, fy = y & m, fz = z & m;
-  uint64_t acc = 0;
-#pragma unroll
-  for (uint32_t dz = 0; dz < 2; dz++)
-#pragma unroll
-    for (uint32_t dy = 0; dy < 2; dy++)
-#pragma unroll
-      for (uint32_t dx = 0; dx < 2; dx++) {
-        const uint64_t v = hash32(ix + dx, iy + dy, iz + dz, seed) >> 16;
-        const uint64_t w = (dx ? fx : one - fx) * (dy ? fy : one - fy) * (dz ? fz : one - fz);
-        acc += v * w;
-      }
-  return acc >> (3 * shift);   // 0..65535
-}
-
-__device__ __forceinline__ uint32_t synth_u16(int kind, uint32_t x, uint32_t y, uint32_t z, uint32_t nx, uint32_t ny,
-                                              uint32_t nz, uint32_t shift0, uint32_t seed) {
-  if (kind == 2) return (x + 8u * y + 64u * z) & 0xFFFFu;
-  const int64_t cx = 2 * (int64_t)x + 1 - nx, cy = 2 * (int64_t)y + 1 - ny, cz = 2 * (int64_t)z + 1 - nz;
-  const uint64_t ax = (uint64_t)(cx < 0 ? -cx : cx) * 4096u / nx;
-  const uint64_t ay = (uint64_t)(cy < 0 ? -cy : cy) * 4096u / ny;
-  const uint64_t az = (uint64_t)(cz < 0 ? -cz : cz) * 4096u / nz;
-  const uint64_t d2 = ax * ax + ay * ay + az * az;
-  const uint64_t R2 = 13589545ull;   // (0.9 * 4096)^2
-  if (d2 >= R2) return 0;
-  const uint64_t w = ((R2 - d2) << 16) / R2;   // 0..65536 falloff
-  if (kind == 0) {
-    const uint64_t t = (d2 << 16) / R2;         // 0..65535
-    const int64_t ph = (int64_t)((t * 3) & 0xFFFFu) - 32768;
-    const uint64_t tri = (uint64_t)(ph < 0 ? -ph : ph) * 2;   // 0..65536
-    uint64_t v = (w * tri) >> 16;
-    return (uint32_t)(v > 65535 ? 65535 : v);
-  }
-  uint64_t sum = 0;
-#pragma unroll
-  for (uint32_t o = 0; o < 4; o++) {
-    const uint32_t s = shift0 > o ? shift0 - o : 0;
-    sum += lattice_noise(x, y, z, s, seed + o) >> o;
-  }
-  const uint64_t noise = sum * 8 / 15;          // 0..65535
-  const uint64_t v = (noise * w) >> 16;
-  const uint64_t t0 = 14000;
-  if (v <= t0) return 0;
-  const uint64_t r = (v - t0) * 2;
-  return (uint32_t)(r > 65535 ? 65535 : r);
-}
-
-template <typename T> __device__ __forceinline__ T from_u16(uint32_t v);
-template <> __device__ __forceinline__ uint8_t from_u16<uint8_t>(uint32_t v) { return (uint8_t)(v >> 8); }
-template <> __device__ __forceinline__ uint16_t from_u16<uint16_t>(uint32_t v) { return (uint16_t)v; }
-template <> __device__ __forceinline__ float from_u16<float>(uint32_t v) { return (float)v / 65535.0f; }
 
 template <typename T>
 __global__ void synth_kernel(T* dst, int kind, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t shift0, uint32_t seed) {
@@ -284,6 +221,69 @@ __global__ void __launch_bounds__(256) brick_minmax_kernel(const unsigned char* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// procedural dataset: min/max of a brick WITHOUT materialising it -- one CTA per brick evaluates the analytic field at
+// the brick's voxels (ghost included; 0 outside the level's grid) and reduces.  Compute-bound integer work (~500 integer
+// instructions per voxel); the table it fills is what MaxMinDataBlock holds for a converted file.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) proc_minmax_kernel(const ProcConsts C, uint32_t first, double* minmax) {
+  const uint32_t id = first + blockIdx.x;
+  uint32_t lod = 0;
+  while (lod + 1 < C.lod_count && id >= C.lod_offset[lod + 1]) lod++;
+  const uint32_t local = id - C.lod_offset[lod];
+  const uint32_t* L = C.layout[lod];
+  const uint32_t* N = C.lod_size[lod];
+  const uint32_t bc[3] = {local % L[0], (local / L[0]) % L[1], local / (L[0] * L[1])};
+  uint32_t bs[3];
+  int64_t org[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const uint32_t core = C.brick[i] - 2 * C.overlap;
+    const bool last = bc[i] == L[i] - 1;
+    const uint32_t rem = N[i] % core;
+    bs[i] = (last && rem) ? 2 * C.overlap + rem : C.brick[i];
+    org[i] = (int64_t)bc[i] * core - C.overlap;
+  }
+  const uint32_t shift0 = synth_shift0(max(N[0], max(N[1], N[2])));
+  const uint32_t n = bs[0] * bs[1] * bs[2];
+  T mn = 0, mx = 0;
+  bool any = false;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t x = org[0] + (int64_t)(i % bs[0]), y = org[1] + (int64_t)((i / bs[0]) % bs[1]), z = org[2] + (int64_t)(i / (bs[0] * bs[1]));
+    T v = 0;
+    if (x >= 0 && y >= 0 && z >= 0 && x < (int64_t)N[0] && y < (int64_t)N[1] && z < (int64_t)N[2])
+      v = from_u16<T>(synth_u16(C.kind, (uint32_t)x, (uint32_t)y, (uint32_t)z, N[0], N[1], N[2], shift0, C.seed));
+    if (!any) { mn = mx = v; any = true; }
+    else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+  }
+  __shared__ T s_mn[8], s_mx[8];
+  __shared__ int s_any[8];
+  const unsigned full = 0xffffffffu;
+  for (int o = 16; o > 0; o >>= 1) {
+    const T omn = __shfl_down_sync(full, mn, o), omx = __shfl_down_sync(full, mx, o);
+    const int oany = __shfl_down_sync(full, (int)any, o);
+    if (oany) {
+      if (!any) { mn = omn; mx = omx; any = true; }
+      else { mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx; }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; s_any[warp] = any; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool have = false;
+    T a = 0, c = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+      if (!s_any[w]) continue;
+      if (!have) { a = s_mn[w]; c = s_mx[w]; have = true; }
+      else { a = s_mn[w] < a ? s_mn[w] : a; c = s_mx[w] > c ? s_mx[w] : c; }
+    }
+    double* o = minmax + 4 * (uint64_t)blockIdx.x;
+    o[0] = (double)a; o[1] = (double)c; o[2] = -DBL_MAX; o[3] = DBL_MAX;
+  }
+}
+
 inline int grid_for(uint64_t n, int block) {
   uint64_t g = (n + block - 1) / block;
   const uint64_t cap = (uint64_t)kSMs * 16;
@@ -319,6 +319,15 @@ void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const u
     case TVK_U8: downsample_kernel<uint8_t><<<g, 256, 0, s>>>((const uint8_t*)src, ss[0], ss[1], ss[2], (uint8_t*)dst, ds[0], ds[1], ds[2]); break;
     case TVK_U16: downsample_kernel<uint16_t><<<g, 256, 0, s>>>((const uint16_t*)src, ss[0], ss[1], ss[2], (uint16_t*)dst, ds[0], ds[1], ds[2]); break;
     default: downsample_kernel<float><<<g, 256, 0, s>>>((const float*)src, ss[0], ss[1], ss[2], (float*)dst, ds[0], ds[1], ds[2]); break;
+  }
+}
+
+void launch_proc_minmax(const ProcConsts& pc, uint32_t first, uint32_t count, double* minmax, cudaStream_t s) {
+  if (!count) return;
+  switch (pc.dtype) {
+    case TVK_U8: proc_minmax_kernel<uint8_t><<<count, 256, 0, s>>>(pc, first, minmax); break;
+    case TVK_U16: proc_minmax_kernel<uint16_t><<<count, 256, 0, s>>>(pc, first, minmax); break;
+    default: proc_minmax_kernel<float><<<count, 256, 0, s>>>(pc, first, minmax); break;
   }
 }
 

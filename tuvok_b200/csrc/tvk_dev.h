@@ -151,6 +151,16 @@ struct CutConsts {
   int32_t clamp, lod;
   uint64_t first_brick;   // TOC index of brick (0,0,0) of this LOD
 };
+// procedural multi-resolution dataset (tvk_procedural.inc): the geometry of every pool LoD + the generator's parameters
+struct ProcConsts {
+  int32_t kind, dtype;
+  uint32_t seed, lod_count, overlap;
+  uint32_t brick[3];
+  uint32_t lod_size[TVK_MAX_LOD][3], layout[TVK_MAX_LOD][3];
+  uint32_t lod_offset[TVK_MAX_LOD];
+};
+// min/max (incl. ghost, 0 outside the level's grid) of the procedural bricks [first, first + count) -> minmax[4 * (id - first)]
+void launch_proc_minmax(const ProcConsts& pc, uint32_t first, uint32_t count, double* minmax, cudaStream_t s);
 // min/max of n staged bricks (ops[i]: src_off, size, new_id = TOC index) -> minmax[4 * new_id]
 void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, double* minmax, int dtype, cudaStream_t s);
 // store_index (device, TOC index -> store slot or -1) or nullptr: the store holds every brick at its TOC index

@@ -18,13 +18,18 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <chrono>
 #include "tvk_host.h"
+#include "tvk_synth.cuh"
 
 using namespace tvk;
 
 namespace {
 
 thread_local std::string g_create_err;
+
+void proc_free(tvk_ctx* ctx);   // tvk_procedural.inc
+int proc_brick_cb(void* user, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, void* dst, size_t cap);
 
 int fail(tvk_ctx* c, int code, const char* fmt, ...) {
   char buf[512];
@@ -115,6 +120,7 @@ void free_dataset(tvk_ctx* c) {
   c->store_index.clear(); c->store_count = 0;
   c->minmax_h.clear();
   if (c->file) { delete c->file; c->file = nullptr; }
+  proc_free(c);
   c->cb = nullptr; c->cb_user = nullptr;
   c->have_volume = false;
 }
@@ -277,7 +283,8 @@ long fill_stage(tvk_ctx* ctx, const CopyReq* reqs, size_t n, unsigned char* hb) 
     const CopyReq& r = reqs[i];
     return ctx->cb(ctx->cb_user, r.co[0], r.co[1], r.co[2], r.co[3], hb + i * ctx->slot_bytes, ctx->slot_bytes) == 0;
   };
-  const size_t workers = ctx->file ? std::min<size_t>(ctx->io_threads, n) : 1;
+  // the file source and the procedural source are thread-safe; a user callback (Dataset::GetBrick) is not assumed to be
+  const size_t workers = ctx->file ? std::min<size_t>(ctx->io_threads, n) : ctx->proc.on ? std::min<size_t>(ctx->proc.threads, n) : 1;
   if (workers <= 1) {
     for (size_t i = 0; i < n; i++) if (!one(i)) return (long)i;
     return -1;
@@ -325,9 +332,17 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
   // Dataset::GetBrick -> pinned staging -> async H2D on the copy stream -> scatter into slots.
   // Two half-buffers: the callback fills one half while the other is in flight.
   const size_t half = ctx->stage_bricks / 2;
-  cudaEvent_t done[2];
+  const auto wall0 = std::chrono::steady_clock::now();
+  cudaEvent_t done[2], c0[2], c1[2];
+  bool timed[2] = {false, false};
   CU(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) { CU(cudaEventCreate(&c0[i])); CU(cudaEventCreate(&c1[i])); }
+  auto harvest = [&](int i) {   // H2D time of the half's last brick copy (events on the copy stream)
+    float ms = 0.0f;
+    if (timed[i] && cudaEventElapsedTime(&ms, c0[i], c1[i]) == cudaSuccess) ctx->up_h2d_ms += ms;
+    timed[i] = false;
+  };
   std::vector<PageOp> ops;
   int rc = TVK_OK;
   size_t pos = 0;
@@ -335,6 +350,7 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
   while (pos < reqs.size() && rc == TVK_OK) {
     const size_t n = std::min(half, reqs.size() - pos);
     cudaEventSynchronize(done[h]);   // the kernels that read this half last time have finished
+    harvest(h);
     unsigned char* hb = (unsigned char*)ctx->stage_h + (size_t)h * half * ctx->slot_bytes;
     unsigned char* db = (unsigned char*)ctx->stage_d + (size_t)h * half * ctx->slot_bytes;
     ops.assign(n, PageOp{});
@@ -360,15 +376,22 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
     PageOp* hops = (PageOp*)((unsigned char*)ctx->stage_h + ops_off) + (size_t)h * half;
     PageOp* dops = (PageOp*)((unsigned char*)ctx->stage_d + ops_off) + (size_t)h * half;
     std::memcpy(hops, ops.data(), n * sizeof(PageOp));
+    cudaEventRecord(c0[h], ctx->copy_stream);
     cudaMemcpyAsync(db, hb, n * ctx->slot_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    cudaEventRecord(c1[h], ctx->copy_stream);
+    timed[h] = true;
     cudaMemcpyAsync(dops, hops, n * sizeof(PageOp), cudaMemcpyHostToDevice, ctx->copy_stream);
     launch_page_copy(ctx->pool_d, db, dops, (uint32_t)n, ctx->slot_voxels, ctx->esize, ctx->brick, 0, ctx->copy_stream);
     cudaEventRecord(done[h], ctx->copy_stream);
+    ctx->up_bricks += n; ctx->up_bytes += (uint64_t)n * ctx->slot_bytes;
     pos += n;
     h ^= 1;
   }
   cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+  harvest(0); harvest(1);
   cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(c0[i]); cudaEventDestroy(c1[i]); }
+  ctx->up_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, TVK_ERR_CUDA, "brick upload failed: %s", cudaGetErrorString(e));
   return TVK_OK;
@@ -1206,9 +1229,10 @@ int tvk_read_brick(tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lo
   uint32_t bs[3];
   if (!ctx || !dst) return TVK_ERR_INVALID;
   if (tvk_get_brick_size(ctx, x, y, z, lod, bs) != TVK_OK) return fail(ctx, TVK_ERR_INVALID, "bad brick coordinates");
-  if (!ctx->store_d) return fail(ctx, TVK_ERR_INVALID, "no device brick store (dataset comes from a callback)");
   const size_t bytes = (size_t)bs[0] * bs[1] * bs[2] * ctx->esize;
   if (cap < bytes) return fail(ctx, TVK_ERR_INVALID, "buffer too small");
+  if (ctx->proc.on) return proc_brick_cb(ctx, x, y, z, lod, dst, cap) == 0 ? TVK_OK : fail(ctx, TVK_ERR_SOURCE, "procedural brick failed");
+  if (!ctx->store_d) return fail(ctx, TVK_ERR_INVALID, "no device brick store (dataset comes from a callback)");
   uint64_t idx = ctx->toc_offset[lod] + x + (uint64_t)y * ctx->layout[lod][0] +
                  (uint64_t)z * ctx->layout[lod][0] * ctx->layout[lod][1];
   if (!ctx->store_index.empty()) {
@@ -2326,3 +2350,4 @@ int tvk_get_classic_brick_list(tvk_ctx* ctx, uint32_t* lod, tvk_classic_brick* d
 }  // extern "C"
 
 #include "tvk_sortlast.inc"
+#include "tvk_procedural.inc"

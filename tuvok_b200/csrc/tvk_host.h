@@ -2,8 +2,11 @@
 #ifndef TVK_HOST_H
 #define TVK_HOST_H
 #include <cmath>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "tvk_dev.h"
 #include "octree_file.h"
@@ -64,6 +67,23 @@ struct VisState {
   }
 };
 
+// procedural brick source (tvk_procedural.inc): generator parameters, the host-side brick cache in front of it, counters
+struct ProcState {
+  bool on = false;
+  int kind = 0;
+  uint32_t seed = 0, threads = 1;
+  unsigned char* arena = nullptr;          // cache_slots bricks of slot_bytes each (plain host memory)
+  uint32_t cache_slots = 0, used = 0;
+  std::mutex mu;
+  std::unordered_map<uint32_t, uint32_t> map;   // page-table index -> cache slot
+  std::vector<uint32_t> owner;
+  std::vector<uint64_t> stamp;
+  std::vector<uint8_t> ready;
+  std::vector<uint32_t> pins;
+  uint64_t clock = 0, evicted = 0;
+  std::atomic<uint64_t> generated{0}, hits{0}, bytes{0}, source_ns{0};
+};
+
 }  // namespace tvk
 
 struct tvk_sortlast;
@@ -96,6 +116,8 @@ struct tvk_ctx {
   void* cb_user = nullptr;
   tvk::OctreeFile* file = nullptr;        // ExtendedOctree file source (tvk_open_octree_file); cb then points at it
   uint32_t io_threads = 8;                // parallel pread/decode workers of the file source
+  tvk::ProcState proc;                    // procedural source (tvk_set_procedural_volume); cb then points at it
+  uint64_t up_bricks = 0, up_bytes = 0; double up_ms = 0, up_h2d_ms = 0;   // streaming totals (tvk_get_stream_stats)
   void* store_d = nullptr;                // device brick store (slot layout, TOC order) or null
   uint64_t slot_voxels = 0, slot_bytes = 0;   // per slot: voxels, bytes of the plain brick (store / staging)
   uint64_t pool_slot_bytes = 0;               // bytes of one POOL slot (x-pair layout: 2 x slot_bytes for 8 / 16-bit data)

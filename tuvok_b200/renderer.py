@@ -227,6 +227,36 @@ class CudaGridLeaper:
                                             max_gradient_magnitude))
         self._dirty = True
 
+    def SetProceduralVolume(self, kind, size, dtype, max_brick_size, overlap, seed=0x5EED, scale=(1, 1, 1), range_max=0.0,
+                            max_gradient_magnitude=0.0, minmax=None, host_cache_bytes=0, threads=0):
+        """Procedural multi-resolution dataset (tvk_set_procedural_volume): stands where a UVFDataset would; bricks are
+        generated on demand by host threads into pinned staging memory and paged in like any streamed brick."""
+        if np.isscalar(max_brick_size):
+            max_brick_size = (max_brick_size,) * 3
+        mm, n = None, 0
+        if minmax is not None:
+            mm = np.ascontiguousarray(minmax, np.float64).reshape(-1, 4)
+            n = mm.shape[0]
+            self._keep.append(mm)
+        self._ck(self._lib.tvk_set_procedural_volume(self._h, kind, L.u32x3(*size), dtype, seed, L.f32x3(*scale),
+                                                     L.u32x3(*max_brick_size), overlap, range_max, max_gradient_magnitude,
+                                                     _ptr(mm) if mm is not None else None, n, int(host_cache_bytes), threads))
+        self._dirty = True
+
+    def procedural_minmax(self, kind, size, dtype, max_brick_size, overlap, first, count, seed=0x5EED):
+        """min/max table slice [first, first + count) of a procedural dataset, evaluated on the device (no dataset needed)."""
+        if np.isscalar(max_brick_size):
+            max_brick_size = (max_brick_size,) * 3
+        out = np.zeros((int(count), 4), np.float64)
+        self._ck(self._lib.tvk_procedural_minmax(self._h, kind, L.u32x3(*size), dtype, seed, L.u32x3(*max_brick_size), overlap,
+                                                 int(first), int(count), _ptr(out)))
+        return out
+
+    def stream_stats(self):
+        st = L.StreamStats()
+        self._ck(self._lib.tvk_get_stream_stats(self._h, C.byref(st)))
+        return st
+
     def synth_volume(self, dst_device_ptr, kind, size, dtype, seed=0x5EED):
         self._ck(self._lib.tvk_synth_volume(self._h, C.c_void_p(int(dst_device_ptr)), kind, L.u32x3(*size), dtype, seed))
 

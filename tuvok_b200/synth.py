@@ -36,14 +36,13 @@ def _lattice_noise(x, y, z, shift, seed):
     return acc >> np.uint64(3 * shift)
 
 
-def synth_u16(kind, size, seed=0x5EED):
-    """size = (nx, ny, nz) -> uint32 array [z, y, x] with values 0..65535."""
+def field_u16(kind, x, y, z, size, seed=0x5EED):
+    """The analytic field at integer grid positions x, y, z (uint32 arrays, broadcastable, all inside the grid) of a grid of
+    size = (nx, ny, nz): uint32 values 0..65535."""
     nx, ny, nz = (int(v) for v in size)
-    x = np.arange(nx, dtype=np.uint32)[None, None, :]
-    y = np.arange(ny, dtype=np.uint32)[None, :, None]
-    z = np.arange(nz, dtype=np.uint32)[:, None, None]
+    shape = np.broadcast(x, y, z).shape
     if kind == V_RAMP:
-        return ((x + np.uint32(8) * y + np.uint32(64) * z) & np.uint32(0xFFFF)).astype(np.uint32)
+        return np.broadcast_to((x + np.uint32(8) * y + np.uint32(64) * z) & np.uint32(0xFFFF), shape).astype(np.uint32)
 
     def axis(c, n):
         a = np.abs(2 * c.astype(np.int64) + 1 - n).astype(np.uint64)
@@ -60,11 +59,11 @@ def synth_u16(kind, size, seed=0x5EED):
         ph = ((t * np.uint64(3)) & np.uint64(0xFFFF)).astype(np.int64) - 32768
         tri = np.abs(ph).astype(np.uint64) * np.uint64(2)
         v = np.minimum((w * tri) >> np.uint64(16), np.uint64(65535))
-        return np.where(inside, v, np.uint64(0)).astype(np.uint32)
+        return np.broadcast_to(np.where(inside, v, np.uint64(0)), shape).astype(np.uint32)
     mx = max(nx, ny, nz)
     lg = mx.bit_length() - 1
     shift0 = lg - 3 if lg > 3 else 0
-    total = np.zeros((nz, ny, nx), np.uint64)
+    total = np.zeros(shape, np.uint64)
     for o in range(4):
         s = shift0 - o if shift0 > o else 0
         total = total + (_lattice_noise(x, y, z, s, (seed + o) & 0xFFFFFFFF) >> np.uint64(o))
@@ -75,11 +74,60 @@ def synth_u16(kind, size, seed=0x5EED):
     return np.where(inside & (v > t0), r, np.uint64(0)).astype(np.uint32)
 
 
-def synth_volume(kind, size, dtype, seed=0x5EED):
-    """dtype: tvk dtype code (0 u8, 1 u16, 2 f32)."""
-    v = synth_u16(kind, size, seed)
+def synth_u16(kind, size, seed=0x5EED):
+    """size = (nx, ny, nz) -> uint32 array [z, y, x] with values 0..65535."""
+    nx, ny, nz = (int(v) for v in size)
+    x = np.arange(nx, dtype=np.uint32)[None, None, :]
+    y = np.arange(ny, dtype=np.uint32)[None, :, None]
+    z = np.arange(nz, dtype=np.uint32)[:, None, None]
+    return field_u16(kind, x, y, z, size, seed)
+
+
+def _to_dtype(v, dtype):
     if dtype == 0:
         return (v >> 8).astype(np.uint8)
     if dtype == 1:
         return v.astype(np.uint16)
     return (v.astype(np.float32) / np.float32(65535.0)).astype(np.float32)
+
+
+def procedural_geometry(size, brick, overlap):
+    """Level sizes, brick layouts and page-table offsets of the pool LoDs of a procedural dataset
+    (tvk_set_procedural_volume): sizes ceil-halve per level; the pool ends at the first single-brick level."""
+    brick = (brick,) * 3 if np.isscalar(brick) else tuple(brick)
+    s = [int(v) for v in size]
+    sizes, layouts, offsets = [], [], [0]
+    while True:
+        if sizes:
+            s = [(v + 1) // 2 if v > 1 else v for v in s]
+        lay = [-(-v // (b - 2 * overlap)) for v, b in zip(s, brick)]
+        sizes.append(tuple(s)); layouts.append(tuple(lay))
+        offsets.append(offsets[-1] + lay[0] * lay[1] * lay[2])
+        if lay[0] * lay[1] * lay[2] == 1:
+            return sizes, layouts, offsets
+
+
+def procedural_brick(kind, size, dtype, seed, brick, overlap, x, y, z, lod):
+    """Brick (x, y, z, lod) of the procedural multi-resolution dataset: the field sampled on level `lod`'s grid, `overlap`
+    ghost voxels per side, 0 outside the grid; array [z, y, x] at the brick's own size."""
+    brick = (brick,) * 3 if np.isscalar(brick) else tuple(brick)
+    sizes, layouts, _ = procedural_geometry(size, brick, overlap)
+    n, lay = sizes[lod], layouts[lod]
+    bs, org = [], []
+    for c, nn, l, b in zip((x, y, z), n, lay, brick):
+        inner = b - 2 * overlap
+        rem = nn % inner
+        bs.append(2 * overlap + rem if (c == l - 1 and rem) else b)
+        org.append(c * inner - overlap)
+    gx = org[0] + np.arange(bs[0], dtype=np.int64)[None, None, :]
+    gy = org[1] + np.arange(bs[1], dtype=np.int64)[None, :, None]
+    gz = org[2] + np.arange(bs[2], dtype=np.int64)[:, None, None]
+    ok = (gx >= 0) & (gx < n[0]) & (gy >= 0) & (gy < n[1]) & (gz >= 0) & (gz < n[2])
+    cx, cy, cz = (np.clip(g, 0, nn - 1).astype(np.uint32) for g, nn in zip((gx, gy, gz), n))
+    v = field_u16(kind, cx, cy, cz, n, seed)
+    return _to_dtype(np.where(ok, v, np.uint32(0)).astype(np.uint32), dtype)
+
+
+def synth_volume(kind, size, dtype, seed=0x5EED):
+    """dtype: tvk dtype code (0 u8, 1 u16, 2 f32)."""
+    return _to_dtype(synth_u16(kind, size, seed), dtype)
