@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=216)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="tvk", choices=["tvk", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c3t", "c4"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c3t", "c4", "c5"])
+    ap.add_argument("--no-stream", action="store_true", help="c5: skip the out-of-core orbit through the small pool")
     ap.add_argument("--path", default="gridleaper", choices=["gridleaper", "classic", "mip"],
                     help="gridleaper: GLGridLeaper page-table traversal (default); classic: per-brick GLRaycaster path; "
                          "mip: HQ MIP frame of a 2D window (GLRaycaster-MIP-Rot-FS, rotating about Y)")
@@ -257,7 +258,44 @@ def workload_geometry(w):
     return brick, inner, finest, n_lods, flayout, ext / ext.max()
 
 
-def make_renderer(w, device, stream, shard=None):
+def host_mem_available():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 64 << 30
+
+
+PROC_INFO = {}
+
+
+def procedural_minmax_table(r, w, brick, rank, world, dist):
+    """min/max table of a procedural workload: every rank evaluates a slice on its device, the slices are gathered"""
+    import ctypes
+    import torch
+    from tuvok_b200 import _lib as L
+    n, lods = ctypes.c_uint64(), ctypes.c_uint32()
+    L.lib().tvk_procedural_brick_count(L.u32x3(*w["size"]), L.u32x3(brick, brick, brick), w["overlap"], ctypes.byref(n), ctypes.byref(lods))
+    n = int(n.value)
+    per = -(-n // world)
+    first, count = min(n, rank * per), max(0, min(n, (rank + 1) * per) - min(n, rank * per))
+    t0 = time.perf_counter()
+    part = r.procedural_minmax(w["kind"], w["size"], w["dtype"], brick, w["overlap"], first, count)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        pad = np.zeros((per, 4), np.float64)
+        pad[:count] = part
+        mine = torch.from_numpy(pad).cuda()
+        allp = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        part = torch.cat(allp)[:n].cpu().numpy()
+    PROC_INFO.update(bricks=n, lods=int(lods.value), minmax_pass_s=round(dt, 2), minmax_bricks_per_rank=count)
+    return part
+
+
+def make_renderer(w, device, stream, shard=None, rank=0, world=1, dist=None, minmax=None):
     """The workload on one renderer: synthetic volume bricked on the device (tvk_build_volume), transfer functions, mode,
     pool.  shard = (clip_min, clip_max): only the bricks of that block are kept in the brick store (sort-last at the
     source, tvk_set_store_shard)."""
@@ -269,15 +307,28 @@ def make_renderer(w, device, stream, shard=None):
     nx, ny, nz = w["size"]
     esize = {L.U8: 1, L.U16: 2, L.F32: 4}[w["dtype"]]
     hash_size = finest[0] * finest[1] * finest[2] * n_lods + 8   # collision-free: one slot per serialised id
-    r = tb.CudaGridLeaper(device=device, max_gpu_mem=96 << 30, hash_table_size=hash_size)
+    # the pool budget counts voxels as the reference does; 8 / 16-bit pools take twice that in HBM (x-pair layout)
+    r = tb.CudaGridLeaper(device=device, max_gpu_mem=(40 << 30) if w.get("procedural") else (96 << 30), hash_table_size=hash_size)
     r.set_stream(stream.cuda_stream)
-    if shard is not None:
-        r.SetStoreShard(*shard)
-    raw = torch.empty(nx * ny * nz * esize, dtype=torch.uint8, device="cuda")
-    r.synth_volume(raw.data_ptr(), w["kind"], w["size"], w["dtype"], 0x5EED)
-    r.BuildVolume(raw.data_ptr(), brick, w["overlap"], size=w["size"], dtype=w["dtype"], max_gradient_magnitude=0.25)
-    del raw
-    torch.cuda.empty_cache()
+    if w.get("procedural"):
+        # the dataset is never materialised: bricks come from the host generator threads through the pinned streaming path
+        if minmax is None:
+            minmax = procedural_minmax_table(r, w, brick, rank, world, dist)
+        local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        cache = int(min(32 << 30, 0.4 * host_mem_available() / local))
+        threads = max(2, (os.cpu_count() or 8) // local)
+        r.SetProceduralVolume(w["kind"], w["size"], w["dtype"], brick, w["overlap"], minmax=minmax, host_cache_bytes=cache,
+                              threads=threads, max_gradient_magnitude=0.25)
+        PROC_INFO.update(host_cache_GiB=round(cache / 2 ** 30, 1), generator_threads=threads)
+        r._minmax_table = minmax
+    else:
+        if shard is not None:
+            r.SetStoreShard(*shard)
+        raw = torch.empty(nx * ny * nz * esize, dtype=torch.uint8, device="cuda")
+        r.synth_volume(raw.data_ptr(), w["kind"], w["size"], w["dtype"], 0x5EED)
+        r.BuildVolume(raw.data_ptr(), brick, w["overlap"], size=w["size"], dtype=w["dtype"], max_gradient_magnitude=0.25)
+        del raw
+        torch.cuda.empty_cache()
     t1, t2 = workloads.transfer_functions(w)
     r.Set1DTrans(t1)
     r.Set2DTrans(t2)
@@ -286,6 +337,8 @@ def make_renderer(w, device, stream, shard=None):
     if "iso" in w:
         r.SetIsoValue(w["iso"] * {L.U8: 255.0, L.U16: 65535.0, L.F32: 1.0}[w["dtype"]])
     r.Resize(w["width"], w["height"])
+    if "translate" in w:
+        r.SetTranslation(tb.translation(*w["translate"]))
     r.CreateVolumePool()
     return r
 
@@ -350,6 +403,10 @@ def run_tvk(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     w = dict(workloads.WORKLOADS[args.config])
+    if os.environ.get("TVK_TZ"):           # developer overrides for camera-path probes
+        w["translate"] = (0.0, 0.0, float(os.environ["TVK_TZ"]))
+    if os.environ.get("TVK_ALPHA_SCALE"):
+        w["alpha_scale"] = float(os.environ["TVK_ALPHA_SCALE"])
     if args.vol:
         w["size"] = (args.vol,) * 3
         w["label"] = w["label"].replace(str(workloads.WORKLOADS[args.config]["size"][0]) + "^3", "%d^3" % args.vol)
@@ -380,10 +437,17 @@ def run_tvk(args, rank, world, local_rank):
         return float(t.item()) > 0.5
 
     t_setup = time.perf_counter()
+    proc_table = None
+    if w.get("procedural"):      # min/max table first (collective: every rank evaluates a slice on its device)
+        import tuvok_b200 as tb
+        tmp = tb.CudaGridLeaper(device=local_rank)
+        proc_table = procedural_minmax_table(tmp, w, brick, rank, world, dist)
+        tmp.Cleanup()
+        del tmp
     # ---- N > 1: the single-GPU frames the composite is compared with (rank 0, whole store, before sharding) --------
     ref_frames = {}
     if world > 1 and do_parity and rank == 0:
-        r0 = make_renderer(w, local_rank, stream)
+        r0 = make_renderer(w, local_rank, stream, minmax=proc_table)
         for v in PARITY_VIEWS:
             r0.SetRotation(workloads.orbit_rotation(v, n_views))
             if not r0.PaintUntilConverged().converged:
@@ -399,11 +463,11 @@ def run_tvk(args, rank, world, local_rank):
     # ---- this rank's renderer -----------------------------------------------------------------------------------
     shard = None
     lib_sl = world > 1 and not legacy
-    if lib_sl and split == "octant":
+    if lib_sl and split == "octant" and not w.get("procedural"):
         # view-independent blocks: the brick store is sharded at the source (memory per GPU falls with N)
         cmin, cmax, _ = sortlast.plan(finest, flayout, ext, np.eye(4, dtype=np.float32) + 0, world, L.SL_OCTANT)
         shard = (tuple(float(v) for v in cmin[rank]), tuple(float(v) for v in cmax[rank]))
-    r = make_renderer(w, local_rank, stream, shard)
+    r = make_renderer(w, local_rank, stream, shard, rank, world, dist, minmax=proc_table)
     info = r.info()
     pipe = sl = None
     if lib_sl:
@@ -448,6 +512,23 @@ def run_tvk(args, rank, world, local_rank):
         lo, hi, img, st = sl.render()
         sl.gather(lo, hi, img)
         return st
+
+    # ---- out-of-core workloads: cold start = first frame to converged on an empty pool and an empty host cache ---------
+    cold = None
+    if w.get("procedural"):
+        barrier()
+        tc = time.perf_counter()
+        n_sub, n_paged = 0, 0
+        for _ in range(256):
+            st = frame(0)
+            n_sub += 1; n_paged += st.bricks_paged
+            if all_min(st.converged):
+                break
+        barrier()
+        ss = r.stream_stats()
+        cold = {"first_frame_to_converged_s": round(time.perf_counter() - tc, 3), "subframes": n_sub, "bricks_paged_this_rank": int(n_paged),
+                "bricks_generated_this_rank": int(ss.bricks_generated),
+                "generator_ms_per_brick_and_thread": round(ss.source_thread_ms / max(1, ss.bricks_generated), 2)}
 
     # ---- setup (untimed): page the working set of every orbit view in --------------------------
     paged = 0
@@ -592,6 +673,62 @@ def run_tvk(args, rank, world, local_rank):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- out-of-core workloads: what the streaming path moved, and (N = 1) an orbit through a pool that holds one view's
+    # working set but not the orbit's, so that every view change pages bricks in from host memory ---------------------
+    stream_obj = None
+    if w.get("procedural"):
+        ss = r.stream_stats()
+
+        def snap(st):
+            return {"bricks_uploaded": int(st.bricks_uploaded), "h2d_GB": round(st.h2d_bytes / 1e9, 3),
+                    "h2d_device_ms": round(st.h2d_ms, 2), "upload_wall_ms": round(st.upload_ms, 1),
+                    "h2d_GBps_while_copying": round(st.h2d_bytes / 1e9 / max(1e-9, st.h2d_ms * 1e-3), 2),
+                    "bricks_generated": int(st.bricks_generated), "host_cache_hits": int(st.host_cache_hits),
+                    "generator_thread_ms": round(st.source_thread_ms, 1), "generator_threads": int(st.source_threads),
+                    "host_cache_page_locked": bool(st.host_cache_pinned)}
+        stream_obj = {"setup_and_cold_start_this_rank": snap(ss)}
+        # pinned H2D peak of this box, measured the same way (1 GiB pinned -> device, events on the stream)
+        hp = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        dp = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+        dp.copy_(hp, non_blocking=True); torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(4):
+            dp.copy_(hp, non_blocking=True)
+        a1.record(); torch.cuda.synchronize()
+        stream_obj["pinned_h2d_peak_GBps"] = round(4 * (1 << 30) / 1e9 / (a0.elapsed_time(a1) * 1e-3), 2)
+        del hp, dp
+        if world == 1 and not args.no_stream:
+            slots = int(max(touched) * 1.5) + 64
+            side = int(np.ceil(slots ** (1.0 / 3.0)))
+            r.CreateVolumePool((brick * side, brick * side, brick * side))
+            for i in range(n_views):              # first lap: the host cache already holds the orbit's bricks (setup)
+                set_view(i)
+                r.PaintUntilConverged()
+            s0 = r.stream_stats()
+            torch.cuda.synchronize()
+            tq = time.perf_counter()
+            sub = 0
+            for i in range(n_views):
+                set_view(i)
+                st = r.PaintUntilConverged()
+                if not st.converged:
+                    raise RuntimeError("out-of-core lap: view %d did not converge in a pool of %d slots" % (i, side ** 3))
+            torch.cuda.synchronize()
+            lap = time.perf_counter() - tq
+            s1 = r.stream_stats()
+            nb = int(s1.bricks_uploaded - s0.bricks_uploaded)
+            by = s1.h2d_bytes - s0.h2d_bytes
+            stream_obj["out_of_core_orbit"] = {
+                "pool_slots": side ** 3, "pool_GB": round(side ** 3 * brick ** 3 * esize * (2 if w["dtype"] != L.F32 else 1) / 1e9, 2),
+                "largest_view_working_set_bricks": int(max(touched)), "frames_per_s": round(n_views / lap, 2),
+                "bricks_paged_per_view": round(nb / n_views, 1), "h2d_GB_per_view": round(by / 1e9 / n_views, 3),
+                "h2d_GBps_while_copying": round(by / 1e9 / max(1e-9, (s1.h2d_ms - s0.h2d_ms) * 1e-3), 2),
+                "h2d_GBps_over_upload_wall_time": round(by / 1e9 / max(1e-9, (s1.upload_ms - s0.upload_ms) * 1e-3), 2),
+                "host_cache_hit_fraction": round((s1.host_cache_hits - s0.host_cache_hits) / max(1, nb), 3),
+                "note": "converged frames (all subframes) of a 36-view orbit through a pool 1.5x the largest single-view working "
+                        "set; every view change pages its bricks in from the host brick cache through pinned staging"}
+
     # ---- N > 1: the gathered composite against the single-GPU frame of the same view (untimed) --------------------
     composite = None
     if lib_sl and do_parity:
@@ -685,7 +822,7 @@ def run_tvk(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_total / k, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": {L.U8: "u8", L.U16: "u16", L.F32: "f32"}[w["dtype"]] + "->f32",
             "data": "synthetic", "gsamples_per_s": gsps,
-            "config": {"workload": w["label"], "volume": "V_noise seed 0x5EED" if w["kind"] == 1 else "V_sph",
+            "config": {"workload": w["label"], "volume": ("procedural " if w.get("procedural") else "") + ("V_noise seed 0x5EED" if w["kind"] == 1 else "V_sph"),
                        "camera": "36-step orbit (Ry 10deg steps, Rx 20deg), eye (0,0,1.6) fov 50",
                        "parallelism": par,
                        "path": ("HQ MIP frame (per-brick GLRaycaster-MIP-Rot-FS + Transfer-MIP, PlanHQMIPFrame LoD)" if mip else
@@ -714,6 +851,8 @@ def run_tvk(args, rank, world, local_rank):
             "gpu_launches": k * (2 * world if pipe is not None else 3 * world if lib_sl else 2 if sl is None else 2 + int(np.log2(world))),
             "clocks": clocks,
         }
+        if stream_obj is not None:
+            line["out_of_core"] = dict(PROC_INFO, cold_start=cold, streaming=stream_obj)
         if composite is not None:
             line["parity_composite"] = composite
         if per_rank is not None:

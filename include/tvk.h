@@ -216,8 +216,9 @@ int tvk_octree_file_read_brick(const char* path, uint64_t offset, uint64_t uvf_f
  * requested brick into the library's pinned staging memory, from where it is paged in like any other brick
  * (GLVolumePool::UploadBricks, GLVolumePool.cpp:1720-1789: pinned cudaMemcpyAsync on the copy stream, double buffered);
  * only bricks the LOD-driven traversal asks for are ever produced.  host_cache_bytes > 0 keeps generated bricks in a
- * host-side LRU cache in front of the generator (the role the OS page cache plays for a .uvf file), so a brick the device
- * pool evicted streams back at memory speed.  minmax = the MaxMinDataBlock-equivalent table for all pool-LoD bricks in
+ * host-side LRU cache in front of the generator (the role the OS page cache plays for a .uvf file; page-locked when the
+ * system allows it, so that the copy engine reads a cached brick where it lies), so a brick the device pool evicted
+ * streams back at PCIe speed.  minmax = the MaxMinDataBlock-equivalent table for all pool-LoD bricks in
  * TOC order (4 doubles per brick; from tvk_procedural_minmax, possibly computed in slices by several ranks) or NULL: it
  * is then computed on this device.  threads = host generator threads (0: all cores). */
 int tvk_set_procedural_volume(tvk_ctx* ctx, int kind, const uint32_t size[3], int dtype, uint32_t seed, const float scale[3],
@@ -247,6 +248,7 @@ typedef struct {
   uint64_t host_cache_evictions;
   double   source_thread_ms;       /* ... thread-milliseconds spent producing / copying bricks on the host */
   uint32_t source_threads;
+  uint32_t host_cache_pinned;      /* the cache is page-locked: cached bricks are copied by DMA straight out of it */
 } tvk_stream_stats;
 int tvk_get_stream_stats(tvk_ctx* ctx, tvk_stream_stats* out);
 int tvk_get_info(const tvk_ctx* ctx, tvk_info* out);

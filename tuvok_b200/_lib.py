@@ -89,7 +89,7 @@ P = C.c_void_p
 class StreamStats(C.Structure):
     _fields_ = [("bricks_uploaded", C.c_uint64), ("h2d_bytes", C.c_uint64), ("upload_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("bricks_generated", C.c_uint64), ("host_cache_hits", C.c_uint64), ("host_cache_evictions", C.c_uint64),
-                ("source_thread_ms", C.c_double), ("source_threads", C.c_uint32)]
+                ("source_thread_ms", C.c_double), ("source_threads", C.c_uint32), ("host_cache_pinned", C.c_uint32)]
 
 
 SIGNATURES = {

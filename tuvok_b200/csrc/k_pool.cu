@@ -124,7 +124,8 @@ __global__ void page_copy_kernel(W* pool, const T* __restrict__ store, const Pag
   const uint32_t sx = src_is_slot_layout ? tx : op.size[0], sy = src_is_slot_layout ? ty : op.size[1],
                  sz = src_is_slot_layout ? tz : op.size[2];
   const uint32_t rows = sy * sz;
-  for (uint32_t r = threadIdx.x / 32; r < rows; r += blockDim.x / 32) {
+  // blockIdx.y = one of gridDim.y row chunks of the brick: a 128^3 brick is 16 384 rows, far too many for one CTA
+  for (uint32_t r = blockIdx.y * (blockDim.x / 32) + threadIdx.x / 32; r < rows; r += gridDim.y * (blockDim.x / 32)) {
     const uint32_t y = r % sy, z = r / sy;
     const T* s = src + (uint64_t)r * sx;
     W* d = dst + ((uint64_t)z * ty + y) * tx;
@@ -190,14 +191,17 @@ void launch_page_meta(uint32_t* meta, const PageOp* ops, uint32_t n, cudaStream_
 void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t n, uint64_t slot_voxels,
                       uint32_t esize, const uint32_t total[3], int src_is_slot_layout, cudaStream_t s) {
   if (!n) return;
+  // enough CTAs to fill the machine even for a handful of large bricks: one chunk per 64 rows, at most 32 per brick
+  const uint32_t rows = total[1] * total[2];
+  const dim3 g(n, std::max(1u, std::min(32u, rows / 64u)));
   if (esize == 1)
-    page_copy_kernel<uint8_t, uint16_t><<<n, 256, 0, s>>>((uint16_t*)pool, (const uint8_t*)store, ops, slot_voxels, total[0],
+    page_copy_kernel<uint8_t, uint16_t><<<g, 256, 0, s>>>((uint16_t*)pool, (const uint8_t*)store, ops, slot_voxels, total[0],
                                                           total[1], total[2], src_is_slot_layout);
   else if (esize == 2)
-    page_copy_kernel<uint16_t, uint32_t><<<n, 256, 0, s>>>((uint32_t*)pool, (const uint16_t*)store, ops, slot_voxels, total[0],
+    page_copy_kernel<uint16_t, uint32_t><<<g, 256, 0, s>>>((uint32_t*)pool, (const uint16_t*)store, ops, slot_voxels, total[0],
                                                            total[1], total[2], src_is_slot_layout);
   else
-    page_copy_kernel<float, float><<<n, 256, 0, s>>>((float*)pool, (const float*)store, ops, slot_voxels, total[0], total[1],
+    page_copy_kernel<float, float><<<g, 256, 0, s>>>((float*)pool, (const float*)store, ops, slot_voxels, total[0], total[1],
                                                      total[2], src_is_slot_layout);
 }
 void launch_slot_unpair(const void* slot, void* out, uint64_t n_voxels, uint32_t esize, cudaStream_t s) {

@@ -30,6 +30,9 @@ thread_local std::string g_create_err;
 
 void proc_free(tvk_ctx* ctx);   // tvk_procedural.inc
 int proc_brick_cb(void* user, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, void* dst, size_t cap);
+const unsigned char* proc_acquire(tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, uint32_t* cache_slot);
+void proc_release(tvk_ctx* ctx, const std::vector<uint32_t>& cache_slots);
+void proc_generate(const tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, void* dst);
 
 int fail(tvk_ctx* c, int code, const char* fmt, ...) {
   char buf[512];
@@ -344,13 +347,18 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
     timed[i] = false;
   };
   std::vector<PageOp> ops;
+  std::vector<uint32_t> held[2];   // host-cache slots the in-flight copies of each half read from
+  double t_wait = 0.0, t_src = 0.0;   // host time waiting for the device / producing bricks (TVK_UPLOAD_TRACE)
   int rc = TVK_OK;
   size_t pos = 0;
   int h = 0;
   while (pos < reqs.size() && rc == TVK_OK) {
     const size_t n = std::min(half, reqs.size() - pos);
+    const auto tw0 = std::chrono::steady_clock::now();
     cudaEventSynchronize(done[h]);   // the kernels that read this half last time have finished
+    t_wait += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
     harvest(h);
+    const auto ts0 = std::chrono::steady_clock::now();
     unsigned char* hb = (unsigned char*)ctx->stage_h + (size_t)h * half * ctx->slot_bytes;
     unsigned char* db = (unsigned char*)ctx->stage_d + (size_t)h * half * ctx->slot_bytes;
     ops.assign(n, PageOp{});
@@ -364,6 +372,35 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
     }
     // fill the pinned half: the file source reads (pread + decode) with several workers straight into pinned
     // memory; a user callback (Dataset::GetBrick) is called from this thread, one brick at a time
+    // procedural source with a page-locked host cache: the DMA reads the brick where the cache keeps it -- no staging
+    // copy on the host; bricks the cache cannot take (all slots busy) are generated into the pinned half as usual
+    const bool direct = ctx->proc.on && ctx->proc.pinned;
+    std::vector<const unsigned char*> src;
+    if (direct) {
+      proc_release(ctx, held[h]);
+      held[h].assign(n, 0xFFFFFFFFu);
+      src.assign(n, nullptr);
+      const CopyReq* rq = &reqs[pos];
+      std::atomic<size_t> next{0};
+      auto work = [&] {
+        for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+          const CopyReq& r = rq[i];
+          const auto g0 = std::chrono::steady_clock::now();
+          src[i] = proc_acquire(ctx, r.co[0], r.co[1], r.co[2], r.co[3], &held[h][i]);
+          if (!src[i]) {
+            proc_generate(ctx, r.co[0], r.co[1], r.co[2], r.co[3], hb + i * ctx->slot_bytes);
+            ctx->proc.generated.fetch_add(1);
+            src[i] = hb + i * ctx->slot_bytes;
+          }
+          ctx->proc.source_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - g0).count());
+        }
+      };
+      const size_t workers = std::min<size_t>(ctx->proc.threads, n);
+      std::vector<std::thread> tp;
+      for (size_t t = 1; t < workers; t++) tp.emplace_back(work);
+      work();
+      for (std::thread& th : tp) th.join();
+    } else {
     const long bad = fill_stage(ctx, &reqs[pos], n, hb);
     if (bad >= 0) {
       const CopyReq& r = reqs[pos + (size_t)bad];
@@ -371,13 +408,21 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
                 ctx->file ? ": " : "", ctx->file ? ctx->file->error.c_str() : "");
       break;
     }
+    }
+    t_src += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
     // ops travel in the same pinned half (tail) so the copy is truly asynchronous
     const size_t ops_off = (ctx->stage_bricks * ctx->slot_bytes + 15) & ~size_t(15);
     PageOp* hops = (PageOp*)((unsigned char*)ctx->stage_h + ops_off) + (size_t)h * half;
     PageOp* dops = (PageOp*)((unsigned char*)ctx->stage_d + ops_off) + (size_t)h * half;
     std::memcpy(hops, ops.data(), n * sizeof(PageOp));
     cudaEventRecord(c0[h], ctx->copy_stream);
-    cudaMemcpyAsync(db, hb, n * ctx->slot_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (direct) {
+      for (size_t i = 0; i < n; i++)
+        cudaMemcpyAsync(db + i * ctx->slot_bytes, src[i], (size_t)ops[i].size[0] * ops[i].size[1] * ops[i].size[2] * ctx->esize,
+                        cudaMemcpyHostToDevice, ctx->copy_stream);
+    } else {
+      cudaMemcpyAsync(db, hb, n * ctx->slot_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    }
     cudaEventRecord(c1[h], ctx->copy_stream);
     timed[h] = true;
     cudaMemcpyAsync(dops, hops, n * sizeof(PageOp), cudaMemcpyHostToDevice, ctx->copy_stream);
@@ -388,10 +433,14 @@ int copy_bricks(tvk_ctx* ctx, const std::vector<CopyReq>& reqs) {
     h ^= 1;
   }
   cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->proc.on) { proc_release(ctx, held[0]); proc_release(ctx, held[1]); }
   harvest(0); harvest(1);
   cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(c0[i]); cudaEventDestroy(c1[i]); }
-  ctx->up_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  ctx->up_ms += wall;
+  static const bool trace = std::getenv("TVK_UPLOAD_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[tvk upload] %zu bricks: wall %.2f ms, source %.2f ms, waiting for the device %.2f ms\n", reqs.size(), wall, t_src, t_wait);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, TVK_ERR_CUDA, "brick upload failed: %s", cudaGetErrorString(e));
   return TVK_OK;

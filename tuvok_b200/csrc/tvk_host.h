@@ -72,7 +72,8 @@ struct ProcState {
   bool on = false;
   int kind = 0;
   uint32_t seed = 0, threads = 1;
-  unsigned char* arena = nullptr;          // cache_slots bricks of slot_bytes each (plain host memory)
+  unsigned char* arena = nullptr;          // cache_slots bricks of slot_bytes each
+  bool pinned = false;                     // ... page-locked: brick copies DMA straight out of the cache
   uint32_t cache_slots = 0, used = 0;
   std::mutex mu;
   std::unordered_map<uint32_t, uint32_t> map;   // page-table index -> cache slot

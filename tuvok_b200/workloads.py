@@ -1,4 +1,6 @@
 """The BASELINE.json configurations as data (no oracle imports: bench.py's GPU arm uses this)."""
+import numpy as np
+
 from . import _lib as L
 from . import synth
 from .tf import TransferFunction1D, TransferFunction2D
@@ -26,6 +28,17 @@ WORKLOADS = {
     "c4": dict(kind=synth.V_SPH, size=(1024, 1024, 1024), dtype=L.F32, brick=36, overlap=2, mode=L.RM_ISOSURFACE,
                lighting=True, width=1920, height=1080, tf=(0.3, 0.4), iso=0.35,
                label="1024^3 f32 bricked 36^3 isosurface+lighting 1920x1080"),
+    # configs[4]: 8192^3 u8 (512 GiB), 128^3 bricks, multi-resolution LOD out-of-core.  The volume exists nowhere at once:
+    # it is the procedural dataset of tvk_set_procedural_volume (bricks generated on demand by host threads into pinned
+    # staging memory and streamed to the pool); sort-last shards the bricks across the ranks by construction (a rank only
+    # ever asks for the bricks of its block)
+    "c5": dict(kind=synth.V_NOISE, size=(8192, 8192, 8192), dtype=L.U8, brick=128, overlap=2, mode=L.RM_1DTRANS,
+               lighting=True, width=1920, height=1080, tf=(0.3, 0.4), procedural=True,
+               # the camera flies INSIDE the volume (the volume is moved towards the eye and turned about its centre), so the
+               # bricks near the eye are needed at the finest levels and every view needs other ones; a translucent table
+               # (alpha x 1/16) keeps rays alive through several LoD shells
+               translate=(0.0, 0.0, 1.2), alpha_scale=1.0 / 16.0,
+               label="8192^3 u8 (512 GiB) procedural, bricked 128^3, LOD out-of-core fly-through, 1D-TF+lighting 1920x1080"),
 }
 
 
@@ -43,6 +56,10 @@ def transfer_functions(w):
     n = 256 if w["dtype"] == L.U8 else 4096
     t1 = TransferFunction1D(n)
     t1.SetStdFunction(*w["tf"])
+    if "alpha_scale" in w:
+        c = t1.color.copy()
+        c[:, 3] *= np.float32(w["alpha_scale"])
+        t1.Set(c)
     t2 = TransferFunction2D.rectangle(w=n, h=256, x0=0.02, x1=0.9, alpha_max=w.get("alpha_max", 16))
     return t1, t2
 
