@@ -497,6 +497,7 @@ def run_tvk(args, rank, world, local_rank):
             sl.update_partition()
 
     sl_stats = []
+    sl_mode = [0]
 
     def frame(i):
         """one step on this rank; returns the stats of the (single) subframe"""
@@ -504,6 +505,7 @@ def run_tvk(args, rank, world, local_rank):
         if lib_sl:
             st = r.SortLastFrame()
             sl_stats.append((st.frame.ms_raycast, st.ms_exchange, st.ms_frame))
+            sl_mode[0] = int(st.peer_memory)
             return st.frame
         if pipe is not None:
             return pipe.render_frame()[0]
@@ -809,9 +811,11 @@ def run_tvk(args, rank, world, local_rank):
                                 "resident pool, nothing else in the loop (3 march directions, mean)"}
         par = "single GPU"
         if lib_sl:
-            par = ("sort-last x%d inside the library (tvk_sortlast_frame): %s brick blocks%s, direct-send RGBA32F slices in one NCCL "
-                   "group, n-way over kernel, RGBA8 gather on rank 0" %
-                   (world, split, ", brick store sharded at the source" if shard is not None else ""))
+            how = ("partial images read straight out of the peers' memory over NVLink by the n-way over kernel, RGBA8 slices stored "
+                   "into rank 0's frame by the same kernel, flag words instead of collectives (no NCCL call on the frame's path)"
+                   if sl_mode[0] else "direct-send RGBA32F slices in one NCCL group, n-way over kernel, RGBA8 gather on rank 0")
+            par = ("sort-last x%d inside the library (tvk_sortlast_frame): %s brick blocks%s, %s" %
+                   (world, split, ", brick store sharded at the source" if shard is not None else "", how))
         elif pipe is not None:
             par = ("depth pipeline x%d (rank s = slab s from the eye, hand-over of resume position + colour over NCCL, "
                    "slabs balanced by non-empty bricks; frames in flight = %d)" % (world, world))

@@ -157,6 +157,11 @@ int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uin
                      int dtype, const float scale[3], const uint32_t max_brick_size[3],
                      uint32_t overlap, int clamp_to_edge, double range_max,
                      float max_gradient_magnitude);
+/* The filter tvk_build_volume halves a level with: 0 = mean (default), 1 = median -- ExtendedOctreeConverter::Convert's
+ * bComputeMedian (ExtendedOctreeConverter.cpp:128, .inc:1-248; VolumeTools::Filter<T, F, true>, VolumeTools.h:168-262: the
+ * first of two, the median of the first three of four, a median of the first seven of eight).  Applies to the next
+ * tvk_build_volume. */
+int tvk_set_pyramid_filter(tvk_ctx* ctx, int median);
 /* seeded integer-arithmetic synthetic volumes (bit-identical to tuvok_b200.synth on the CPU);
  * kind 0 = V_sph (shells), 1 = V_noise (value noise x falloff), 2 = V_ramp (x + 8y + 64z).
  * Writes size[0]*size[1]*size[2] voxels to the DEVICE pointer dst. */
@@ -460,6 +465,8 @@ typedef struct {
   float ms_frame;              /* device time of the whole frame on this rank */
   uint64_t bytes_sent;         /* image bytes this rank sent (exchange + gather) */
   uint64_t slice_lo, slice_hi; /* the pixel range this rank composited */
+  int32_t  peer_memory;        /* 1: the frame went through peer memory (no NCCL call on its path), 0: NCCL exchange */
+  int32_t  pad_;
 } tvk_sortlast_stats;
 /* rank 0 creates the id (ncclGetUniqueId) and hands it to the other ranks by whatever means the host has */
 int tvk_sortlast_unique_id(uint8_t id[TVK_COMM_ID_BYTES]);

@@ -68,6 +68,29 @@ def test_gpu_bricker_matches_oracle(size, dtype, brick, overlap, clamp):
     r.Cleanup()
 
 
+@pytest.mark.parametrize("size,dtype,brick,overlap", [((70, 45, 58), tb.U16, 20, 2), ((40, 40, 40), tb.U8, 12, 2),
+                                                      ((48, 48, 48), tb.F32, 12, 2), ((160, 160, 128), tb.U16, 36, 2)])
+def test_gpu_median_pyramid_matches_oracle(size, dtype, brick, overlap):
+    """bComputeMedian (ExtendedOctreeConverter.inc:1-248): the oracle's median pyramid is pinned to the reference converter
+    in tests/test_octree_ref.py; the device pyramid must equal it brick for brick"""
+    rng = np.random.default_rng(hash((size, brick, 1)) & 0xFFFF)
+    shape = (size[2], size[1], size[0])
+    if dtype == tb.F32:
+        vol = rng.random(shape, dtype=np.float32)
+    else:
+        vol = rng.integers(1, 255 if dtype == tb.U8 else 65535, size=shape, endpoint=True).astype(orc.NP_DTYPE[dtype])
+    o = orc.Octree(vol, brick, overlap, median=True)
+    r = tb.CudaGridLeaper()
+    r.BuildVolume(vol, brick, overlap, median=True)
+    assert np.array_equal(r.minmax(o.total_bricks), o.minmax)
+    for (x, y, z, lod) in o.iter_bricks():
+        assert np.array_equal(r.brick(x, y, z, lod, dtype), o.brick(x, y, z, lod)), (x, y, z, lod)
+    r.BuildVolume(vol, brick, overlap)                   # and the filter is a per-build choice: back to the mean
+    mean = orc.Octree(vol, brick, overlap)
+    assert np.array_equal(r.minmax(mean.total_bricks), mean.minmax)
+    r.Cleanup()
+
+
 def test_rebricking_kat_on_gpu():
     # IO/test/rebricking.h: 8x8x1 ramp, brick 16 / overlap 2 -> 12x12x5; split in Y -> min/max incl. ghost
     ramp = np.arange(64, dtype=np.uint8).reshape(1, 8, 8)

@@ -80,6 +80,28 @@ def test_oracle_matches_reference_converter(ref_octree_bin, tmp_path, shape, dty
         assert (o.minmax[i, 0], o.minmax[i, 1]) == (mn, mx), (x, y, z, lod)
 
 
+@pytest.mark.parametrize("shape,dtype,brick,overlap", [((24, 20, 28), orc.U16, 12, 2), ((33, 17, 40), orc.U8, 12, 2),
+                                                       ((32, 32, 32), orc.F32, 12, 2), ((1, 8, 8), orc.U8, 16, 2)])
+def test_oracle_median_pyramid_matches_reference_converter(ref_octree_bin, tmp_path, shape, dtype, brick, overlap):
+    """bComputeMedian = true (ExtendedOctreeConverter.inc:1-248, VolumeTools.h:168-262): the coarser levels hold medians"""
+    vol = rand_volume(shape, dtype, seed=sum(shape) + 3 * brick)
+    lods, ref = run_reference(ref_octree_bin, tmp_path, vol, dtype, brick, overlap, False, median=True)
+    o = orc.Octree(vol, brick, overlap, median=True)
+    mean = orc.Octree(vol, brick, overlap)
+    assert o.lod_count == lods and o.total_bricks == len(ref)
+    inner = brick - 2 * overlap
+    differs = False
+    for (x, y, z, lod) in o.iter_bricks():
+        ls = o.lod_size(lod)
+        if any(0 < (ls[a] % inner) < overlap and o.brick_count(lod)[a] > 1 for a in range(3)):
+            continue
+        i = o.brick_index(x, y, z, lod)
+        assert np.array_equal(o.brick(x, y, z, lod), ref[i][3]), (x, y, z, lod)
+        assert (o.minmax[i, 0], o.minmax[i, 1]) == (ref[i][1], ref[i][2])
+        differs = differs or (lod > 0 and not np.array_equal(o.brick(x, y, z, lod), mean.brick(x, y, z, lod)))
+    assert differs or lods == 1            # the median pyramid is not the mean pyramid
+
+
 def test_ghost_corner_quirk_is_reference_behaviour(ref_octree_bin, tmp_path):
     """FillOverlap's copy order leaves three ghost corners of interior LOD>=1 bricks zero (Q1 in
     orc_octree.c).  Show it on the reference itself so the restatement is not an invention."""

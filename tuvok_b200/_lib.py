@@ -69,7 +69,7 @@ class OctreeFileInfo(C.Structure):
 
 class SortLastStats(C.Structure):
     _fields_ = [("frame", FrameStats), ("ms_exchange", C.c_float), ("ms_frame", C.c_float), ("bytes_sent", C.c_uint64),
-                ("slice_lo", C.c_uint64), ("slice_hi", C.c_uint64)]
+                ("slice_lo", C.c_uint64), ("slice_hi", C.c_uint64), ("peer_memory", C.c_int32), ("pad_", C.c_int32)]
 
 
 COMM_ID_BYTES = 128
@@ -140,6 +140,7 @@ SIGNATURES = {
                                    f32x3, C.c_float, C.c_float, C.c_float, C.c_float]),
     "tvk_default_params": (C.c_int, [C.POINTER(RenderParams), C.c_uint32, C.c_uint32]),
     "tvk_set_params": (C.c_int, [P, C.POINTER(RenderParams)]),
+    "tvk_set_pyramid_filter": (C.c_int, [P, C.c_int]),
     "tvk_set_clip_plane": (C.c_int, [P, C.c_int, f32x4]),
     "tvk_clip_plane_to_model": (C.c_int, [f32x4, f32x16, f32x16, f32x4]),
     "tvk_pick": (C.c_int, [P, C.c_uint32, C.c_uint32, f32x3]),

@@ -30,7 +30,26 @@ __global__ void synth_kernel(T* dst, int kind, uint32_t nx, uint32_t ny, uint32_
 // ---------------------------------------------------------------------------------------------
 // LOD pyramid: voxel of LOD l+1 = Filter over the existing voxels of the 2x2x2 block of LOD l
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+// VolumeTools::Filter<T, F, bComputeMedian = true> (VolumeTools.h:168-262): 2 values -> the first; 4 -> the median of the
+// first three; 8 -> a median of the first SEVEN (the eighth is ignored), by the reference's own compare-exchange network
+template <typename T> __device__ __forceinline__ void order2(T& a, T& b) { if (a > b) { const T x = a; a = b; b = x; } }
+template <typename T> __device__ __forceinline__ void insert_sorted4(T& a, T& b, T& c, T& d, T p) {
+  if (p > c) { order2(d, p); }
+  else if (p < b) { d = c; c = b; b = p; order2(a, b); }
+  else { d = c; c = p; }
+}
+template <typename T> __device__ __forceinline__ T median_of(const T* v, int n) {
+  if (n <= 2) return v[0];
+  if (n == 4) { T a = v[0], b = v[1], c = v[2]; order2(a, b); order2(b, c); return a > b ? a : b; }
+  T a = v[0], b = v[1], c = v[2], d = v[3];
+  order2(a, b); order2(c, d); order2(a, c); order2(b, d); order2(b, c);
+  insert_sorted4(a, b, c, d, v[4]);
+  insert_sorted4(a, b, c, d, v[5]);
+  const T m = d < v[6] ? d : v[6];
+  return m > c ? m : c;
+}
+
+template <typename T, bool MEDIAN = false>
 __global__ void downsample_kernel(const T* __restrict__ src, uint32_t sx, uint32_t sy, uint32_t sz, T* dst,
                                   uint32_t dx_, uint32_t dy_, uint32_t dz_) {
   const uint64_t n = (uint64_t)dx_ * dy_ * dz_;
@@ -43,15 +62,18 @@ __global__ void downsample_kernel(const T* __restrict__ src, uint32_t sx, uint32
     const uint32_t nz = (sz > 1 && bz + 1 < sz) ? 2 : 1;
     double s = 0.0;
     T first = 0;
+    T all[8];
     int cnt = 0;
     for (uint32_t a = 0; a < nx; a++)        // p0..p7 order of the reference: x-major, z-minor
       for (uint32_t b = 0; b < ny; b++)
         for (uint32_t c = 0; c < nz; c++) {
           const T v = src[(uint64_t)(bx + a) + (uint64_t)sx * ((by + b) + (uint64_t)sy * (bz + c))];
           if (cnt == 0) { first = v; s = (double)v; } else s = s + (double)v;
+          if (MEDIAN) all[cnt] = v;
           cnt++;
         }
-    dst[i] = cnt == 1 ? first : (T)(s / (double)cnt);
+    if (MEDIAN) dst[i] = median_of(all, cnt);
+    else dst[i] = cnt == 1 ? first : (T)(s / (double)cnt);
   }
 }
 
@@ -307,9 +329,18 @@ void launch_synth(void* dst, int kind, const uint32_t size[3], int dtype, uint32
   }
 }
 
-void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const uint32_t ds[3], int dtype,
+void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const uint32_t ds[3], int dtype, int median,
                        cudaStream_t s) {
   const uint64_t n = (uint64_t)ds[0] * ds[1] * ds[2];
+  if (median) {
+    const int g = grid_for(n, 256);
+    switch (dtype) {
+      case TVK_U8: downsample_kernel<uint8_t, true><<<g, 256, 0, s>>>((const uint8_t*)src, ss[0], ss[1], ss[2], (uint8_t*)dst, ds[0], ds[1], ds[2]); break;
+      case TVK_U16: downsample_kernel<uint16_t, true><<<g, 256, 0, s>>>((const uint16_t*)src, ss[0], ss[1], ss[2], (uint16_t*)dst, ds[0], ds[1], ds[2]); break;
+      default: downsample_kernel<float, true><<<g, 256, 0, s>>>((const float*)src, ss[0], ss[1], ss[2], (float*)dst, ds[0], ds[1], ds[2]); break;
+    }
+    return;
+  }
   if (dtype == TVK_U16 && ss[0] % 4 == 0 && ss[1] % 2 == 0 && ss[2] % 2 == 0 && ss[0] > 1 && ss[1] > 1 && ss[2] > 1) {
     downsample_u16x2_kernel<<<grid_for(n / 2, 256), 256, 0, s>>>((const uint2*)src, ss[0], ss[1], (uint32_t*)dst, ds[0], ds[1], ds[2]);
     return;

@@ -6,6 +6,7 @@
 // (GLRenderer.cpp:2763-2830); GLFrameCapture.cpp:72-85 (glReadPixels GL_UNSIGNED_BYTE);
 // Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153.
 // Compiled with -fmad=false (same arithmetic contract as k_raycast.cu).
+#include <algorithm>
 #include "tvk_dev.h"
 
 namespace tvk {
@@ -92,6 +93,66 @@ __global__ void nway_over_kernel(const NWaySrc a, float4* __restrict__ out_f, uc
     for (int k = 1; k < a.n; k++) acc = over1(acc, a.src[k][i]);
     if (out_f) out_f[i] = acc;
     out8[i] = make_uchar4(unorm8(acc.x), unorm8(acc.y), unorm8(acc.z), unorm8(acc.w));
+  }
+}
+
+// ---- peer-memory sort-last (tvk_dev.h SlPeer) -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t* sl_flag(const SlPeer& P, int owner, int kind, int from) {
+  return P.flags[owner] + kind * TVK_MAX_RANKS + from;
+}
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr long long kSlSpinCycles = 60000000000ll;   // ~30 s at 1.9 GHz (a peer may be paging bricks in for seconds); a peer that
+                                                     // never arrives must not hang the GPU for good
+
+// thread q waits until rank q's flag of `kind` in MY block has reached `frame`
+__device__ __forceinline__ void sl_wait_all(const SlPeer& P, int kind, uint32_t frame, uint32_t* local) {
+  if ((int)threadIdx.x < P.n) {
+    const uint32_t* f = sl_flag(P, P.self, kind, (int)threadIdx.x);
+    const long long t0 = clock64();
+    while ((int32_t)(ld_flag(f) - frame) < 0) {
+      if (clock64() - t0 > kSlSpinCycles) { atomicExch(&local[1], frame ? frame : 1u); break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void sl_wait_kernel(const SlPeer P, int kind, uint32_t frame, uint32_t* local) { sl_wait_all(P, kind, frame, local); }
+
+// thread q tells rank q: my flag of `kind` is now `frame` (everything this stream did before is visible first)
+__global__ void sl_signal_kernel(const SlPeer P, int kind, uint32_t frame) {
+  __threadfence_system();
+  if ((int)threadIdx.x < P.n) st_flag(sl_flag(P, (int)threadIdx.x, kind, P.self), frame);
+}
+
+__global__ void nway_over_peer_kernel(const NWaySrc a, float4* __restrict__ out_f, uchar4* out8, uint64_t n, const SlPeer P,
+                                      uint32_t frame, uint32_t* local) {
+  sl_wait_all(P, TVK_SLF_READY, frame, local);          // every partial image of this frame is complete
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    float4 acc = a.src[0][i];
+    for (int k = 1; k < a.n; k++) acc = over1(acc, a.src[k][i]);
+    if (out_f) out_f[i] = acc;
+    out8[i] = make_uchar4(unorm8(acc.x), unorm8(acc.y), unorm8(acc.z), unorm8(acc.w));   // rank 0's frame (peer store)
+  }
+  // the last block to finish tells the peers: I have read your images (they may render the next frame) and rank 0: my
+  // RGBA8 slice has landed
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(&local[0], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) local[0] = 0;
+    __threadfence_system();
+    if ((int)threadIdx.x < P.n) st_flag(sl_flag(P, (int)threadIdx.x, TVK_SLF_CONSUMED, P.self), frame);
+    if (threadIdx.x == 0) st_flag(sl_flag(P, 0, TVK_SLF_GATHERED, P.self), frame);
   }
 }
 
@@ -238,6 +299,17 @@ void launch_stereo_compose(int mode, const float4* left, const float4* right, fl
 
 void launch_composite_over(const float4* front, const float4* back, float4* out, uint64_t n, cudaStream_t s) {
   over_kernel<<<grid_for(n, 256), 256, 0, s>>>(front, back, out, n);
+}
+
+void launch_sl_wait(const SlPeer& P, int kind, uint32_t frame, uint32_t* local, cudaStream_t s) {
+  sl_wait_kernel<<<1, 32, 0, s>>>(P, kind, frame, local);
+}
+void launch_sl_signal(const SlPeer& P, int kind, uint32_t frame, cudaStream_t s) { sl_signal_kernel<<<1, 32, 0, s>>>(P, kind, frame); }
+void launch_nway_over_peer(const NWaySrc& a, float4* out_f, uchar4* out8, uint64_t n, const SlPeer& P, uint32_t frame,
+                           uint32_t* local, cudaStream_t s) {
+  // one CTA per SM x 4: every block must be resident while it spins on the flags (no block may wait for a slot)
+  const int g = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)kSMs * 4));
+  nway_over_peer_kernel<<<g, 256, 0, s>>>(a, out_f, out8, n, P, frame, local);
 }
 
 void launch_nway_over(const NWaySrc& a, float4* out_f, uchar4* out8, uint64_t n, cudaStream_t s) {

@@ -85,6 +85,18 @@ void launch_composite_over(const float4* front, const float4* back, float4* out,
 #define TVK_MAX_RANKS 16
 struct NWaySrc { const float4* src[TVK_MAX_RANKS]; int n; };
 void launch_nway_over(const NWaySrc& a, float4* out_f, uchar4* out8, uint64_t n, cudaStream_t s);
+// Peer-memory variant (all GPUs of one box, NVLink / NVSwitch): the partial images are read where the peers rendered
+// them and the RGBA8 slice is stored straight into rank 0's frame -- no copy, no NCCL call on the frame's path.  Ranks
+// synchronise through flag words in each other's memory: flags[p] = rank p's flag block (mapped into this process),
+// uint32 [3][TVK_MAX_RANKS]: READY[q] = last frame whose partial image rank q has finished, CONSUMED[q] = last frame
+// whose slices rank q has read out of rank p's image, GATHERED[q] = last frame whose RGBA8 slice rank q has stored (rank 0).
+enum { TVK_SLF_READY = 0, TVK_SLF_CONSUMED = 1, TVK_SLF_GATHERED = 2 };
+struct SlPeer { int n, self; uint32_t* flags[TVK_MAX_RANKS]; };
+// local[0] = block counter, local[1] = time-out marker (a peer never signalled: the frame is garbage, nothing hangs)
+void launch_sl_wait(const SlPeer& P, int kind, uint32_t frame, uint32_t* local, cudaStream_t s);
+void launch_sl_signal(const SlPeer& P, int kind, uint32_t frame, cudaStream_t s);
+void launch_nway_over_peer(const NWaySrc& a, float4* out_f, uchar4* out8, uint64_t n, const SlPeer& P, uint32_t frame,
+                           uint32_t* local, cudaStream_t s);
 
 // classic per-brick raycaster (k_classic.cu): uniforms of GLRaycaster::SetBrickDepShaderVars / RenderBox plus the
 // per-axis brick tables of the LoD (the brick boxes of one LoD are a tensor-product grid, so everything the
@@ -144,7 +156,7 @@ void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, u
 
 // bricker (k_bricker.cu)
 void launch_synth(void* dst, int kind, const uint32_t size[3], int dtype, uint32_t seed, cudaStream_t s);
-void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const uint32_t ds[3], int dtype,
+void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const uint32_t ds[3], int dtype, int median,
                        cudaStream_t s);
 struct CutConsts {
   uint32_t lod_size[3], layout[3], brick[3], overlap;

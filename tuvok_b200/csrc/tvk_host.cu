@@ -1204,7 +1204,7 @@ int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uin
       const uint64_t n = (uint64_t)ctx->lod_size[l][0] * ctx->lod_size[l][1] * ctx->lod_size[l][2];
       e = cudaMalloc(&lod_cur, n * ctx->esize);
       if (e != cudaSuccess) break;
-      launch_downsample(lod_prev, ctx->lod_size[l - 1], lod_cur, ctx->lod_size[l], dtype, ctx->stream);
+      launch_downsample(lod_prev, ctx->lod_size[l - 1], lod_cur, ctx->lod_size[l], dtype, ctx->pyramid_median ? 1 : 0, ctx->stream);
       if (lod_prev != raw) { cudaStreamSynchronize(ctx->stream); cudaFree(lod_prev); }
       lod_prev = lod_cur;
     }
@@ -1552,6 +1552,12 @@ int tvk_set_params(tvk_ctx* ctx, const tvk_render_params* p) {
   ctx->params = *p;
   ctx->have_params = true;
   ctx->blank = true;
+  return TVK_OK;
+}
+
+int tvk_set_pyramid_filter(tvk_ctx* ctx, int median) {
+  if (!ctx) return TVK_ERR_INVALID;
+  ctx->pyramid_median = median != 0;
   return TVK_OK;
 }
 

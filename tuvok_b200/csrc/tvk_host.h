@@ -117,6 +117,7 @@ struct tvk_ctx {
   void* cb_user = nullptr;
   tvk::OctreeFile* file = nullptr;        // ExtendedOctree file source (tvk_open_octree_file); cb then points at it
   uint32_t io_threads = 8;                // parallel pread/decode workers of the file source
+  bool pyramid_median = false;            // tvk_set_pyramid_filter: median instead of mean when tvk_build_volume halves a level
   tvk::ProcState proc;                    // procedural source (tvk_set_procedural_volume); cb then points at it
   uint64_t up_bricks = 0, up_bytes = 0; double up_ms = 0, up_h2d_ms = 0;   // streaming totals (tvk_get_stream_stats)
   void* store_d = nullptr;                // device brick store (slot layout, TOC order) or null

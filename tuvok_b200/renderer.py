@@ -210,7 +210,7 @@ class CudaGridLeaper:
         self._dirty = True
 
     def BuildVolume(self, raw, max_brick_size, overlap, scale=(1, 1, 1), clamp_to_edge=False, range_max=0.0,
-                    max_gradient_magnitude=0.0, size=None, dtype=None):
+                    max_gradient_magnitude=0.0, size=None, dtype=None, median=False):
         """Brick a raw volume on the GPU (replaces the offline ExtendedOctreeConverter).  `raw` is a
         numpy array [z, y, x] (host) or an int device pointer with `size=(nx,ny,nz)` and `dtype`."""
         if np.isscalar(max_brick_size):
@@ -222,6 +222,7 @@ class CudaGridLeaper:
             ptr, on_dev = _ptr(raw), 0
         else:
             ptr, on_dev = C.c_void_p(int(raw)), 1
+        self._ck(self._lib.tvk_set_pyramid_filter(self._h, int(median)))
         self._ck(self._lib.tvk_build_volume(self._h, ptr, on_dev, L.u32x3(*size), dtype, L.f32x3(*scale),
                                             L.u32x3(*max_brick_size), overlap, int(clamp_to_edge), range_max,
                                             max_gradient_magnitude))
