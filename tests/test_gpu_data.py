@@ -43,6 +43,14 @@ BRICK_CASES = [
     ((1, 8, 8)[::-1], tb.U8, 16, 2, False),    # 8x8x1, the rebricking.h volume
     ((40, 40, 40), tb.U8, 12, 2, True),        # clamp-to-edge, LOD 0 and the restated LOD >= 1 rule
     ((36, 36, 36), tb.U16, 10, 1, False),      # 1-voxel ghost
+    # 36^3 bricks of levels whose rows are 16-byte multiples: the TMA box-load path (cut_bricks_tma_kernel), all three voxel
+    # types, border bricks (ghost zero-filled by the TMA unit), ragged last bricks and clamped borders (generic path inside
+    # the same launch), LoD >= 1 (stale-corner rule)
+    ((144, 144, 112), tb.U8, 36, 2, False),
+    ((80, 112, 72), tb.F32, 36, 2, False),
+    ((176, 100, 96), tb.U16, 36, 2, False),
+    ((128, 128, 96), tb.U16, 36, 2, True),
+    ((144, 144, 144), tb.U8, 36, 4, False),    # 4-voxel ghost: inner 28
 ]
 
 

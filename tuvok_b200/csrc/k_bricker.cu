@@ -10,6 +10,7 @@
 //   MaxMinDataBlock::SetDataFromFlatVector                 IO/UVF/MaxMinDataBlock.cpp:175-195
 // HBM-bound integer work: coalesced x-fastest reads/writes, one CTA per brick.
 #include <cfloat>
+#include <cuda.h>
 #include "tvk_dev.h"
 #include "tvk_synth.cuh"
 
@@ -105,9 +106,8 @@ __global__ void downsample_u16x2_kernel(const uint2* __restrict__ src, uint32_t 
 // brick cutting + stats
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ vol, T* store, const int32_t* __restrict__ store_index,
-                                                         double* minmax, const CutConsts C, uint64_t slot_voxels) {
-  const uint32_t b = blockIdx.x;
+__device__ __forceinline__ void cut_brick_generic(const T* __restrict__ vol, T* store, const int32_t* __restrict__ store_index,
+                                                  double* minmax, const CutConsts& C, uint64_t slot_voxels, const uint32_t b) {
   const uint32_t bx = b % C.layout[0], by = (b / C.layout[0]) % C.layout[1], bz = b / (C.layout[0] * C.layout[1]);
   const uint32_t bc[3] = {bx, by, bz};
   uint32_t bs[3];
@@ -208,6 +208,144 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ v
     }
     double* o = minmax + 4 * (uint64_t)(C.first_brick + b);
     o[0] = (double)a; o[1] = (double)c; o[2] = -DBL_MAX; o[3] = DBL_MAX;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ vol, T* store, const int32_t* __restrict__ store_index,
+                                                         double* minmax, const CutConsts C, uint64_t slot_voxels) {
+  cut_brick_generic<T>(vol, store, store_index, minmax, C, slot_voxels, blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same brick cut through the TENSOR MEMORY ACCELERATOR (sm_100a; round 2).  A full 36^3 brick is
+// a 3-D box of the LoD volume whose origin is (brick * inner - ghost): exactly what one cp.async.bulk.tensor.3d
+// delivers -- with the ghost cells that hang over the domain border zero-filled by the TMA unit itself (out-of-bound box
+// elements read as 0 = the reference's border rule without clamping).  The box's inner extent has to be a multiple of
+// 16 bytes, so it is loaded KBX = 48 / 40 / 36 voxels wide (u8 / u16 / f32) and the 36 wanted voxels of each row are taken
+// from shared memory as ONE 4-voxel word per thread (36 = 9 x 4; 4 / 8 / 16-byte LDS + coalesced STG into the slot, which
+// is one contiguous block).  The brick moves in 6 z-chunks of 6 slices through a ring of kStages shared-memory stages,
+// each with its mbarrier: thread 0 issues the box loads, all 256 threads drain -- the copy engine fetches chunk c + kStages
+// while chunk c is stored.  Min/max (every stored voxel incl. ghost) and the stale-corner rule of FillOverlap for LoD >= 1
+// ride along in the drain loop.  Bricks the box cannot describe (ragged last bricks, clamped borders) take the generic path.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTB = 36, kChunkZ = 6, kChunks = kTB / kChunkZ, kStages = 3;
+template <typename T> struct Vec4;
+template <> struct Vec4<uint8_t> { using type = uchar4; };
+template <> struct Vec4<uint16_t> { using type = ushort4; };
+template <> struct Vec4<float> { using type = float4; };
+template <typename T> struct TmaBoxX { static constexpr int value = (int)(((kTB * sizeof(T) + 15) / 16 * 16) / sizeof(T)); };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cut_bricks_tma_kernel(const __grid_constant__ CUtensorMap tm, const T* __restrict__ vol, T* store,
+                                                             const int32_t* __restrict__ store_index, double* minmax,
+                                                             const CutConsts C, uint64_t slot_voxels) {
+  constexpr int KBX = TmaBoxX<T>::value;
+  constexpr uint32_t kStageBytes = KBX * kTB * kChunkZ * sizeof(T);
+  using V = typename Vec4<T>::type;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  const uint32_t b = blockIdx.x;
+  const uint32_t bx = b % C.layout[0], by = (b / C.layout[0]) % C.layout[1], bz = b / (C.layout[0] * C.layout[1]);
+  const uint32_t bc[3] = {bx, by, bz};
+  bool full = true, border = false;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const uint32_t core = C.brick[i] - 2 * C.overlap;
+    const bool last = bc[i] == C.layout[i] - 1;
+    full = full && !(last && (C.lod_size[i] % core));
+    border = border || bc[i] == 0 || last;
+  }
+  if (!full || (C.clamp && border)) {          // block-uniform: ragged or clamped bricks go the generic way
+    cut_brick_generic<T>(vol, store, store_index, minmax, C, slot_voxels, b);
+    return;
+  }
+  const int ov = (int)C.overlap;
+  const int x0 = (int)(bx * (kTB - 2 * ov)) - ov, y0 = (int)(by * (kTB - 2 * ov)) - ov, z0 = (int)(bz * (kTB - 2 * ov)) - ov;
+  const int64_t at = store_index ? (int64_t)store_index[C.first_brick + b] : (int64_t)(C.first_brick + b);
+  const bool keep = at >= 0;
+  V* dst = reinterpret_cast<V*>(store + (uint64_t)(keep ? at : 0) * slot_voxels);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int c = 0; c < kStages && c < kChunks; c++) {
+      mbar_expect_tx(&bars[c], kStageBytes);
+      tma_load_3d(tma_smem + (size_t)c * kStageBytes, &tm, x0, y0, z0 + c * kChunkZ, &bars[c]);
+    }
+  }
+  __syncthreads();
+  T mn = 0, mx = 0;
+  bool any = false;
+  const bool stale_rule = C.lod > 0;
+  constexpr uint32_t kWordsPerChunk = kTB * kChunkZ * (kTB / 4);   // 9 words per row
+  for (int c = 0; c < kChunks; c++) {
+    const int stage = c % kStages;
+    mbar_wait(&bars[stage], (uint32_t)((c / kStages) & 1));
+    const T* tile = reinterpret_cast<const T*>(tma_smem + (size_t)stage * kStageBytes);
+    for (uint32_t w = threadIdx.x; w < kWordsPerChunk; w += blockDim.x) {
+      const uint32_t row = w / (kTB / 4), g = w - row * (kTB / 4);
+      const uint32_t lz = (uint32_t)c * kChunkZ + row / kTB, ly = row % kTB;
+      V v = *reinterpret_cast<const V*>(tile + (size_t)row * KBX + g * 4);
+      if (stale_rule) {
+        // FillOverlap's copy order leaves three ghost corners of every LoD >= 1 brick zero (see the generic path)
+        const int gy = (int)ly < ov ? -1 : (int)ly >= kTB - ov ? 1 : 0, gz = (int)lz < ov ? -1 : (int)lz >= kTB - ov ? 1 : 0;
+        if (gy != 0 && gz != 0 && (g == 0 || g == kTB / 4 - 1)) {
+          T e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int lx = (int)g * 4 + k;
+            const int gx = lx < ov ? -1 : lx >= kTB - ov ? 1 : 0;
+            if ((gx == 1 && gy == 1 && gz == -1) || (gx == 1 && gy == -1 && gz == 1) || (gx == -1 && gy == 1 && gz == 1)) e[k] = 0;
+          }
+          v.x = e[0]; v.y = e[1]; v.z = e[2]; v.w = e[3];
+        }
+      }
+      if (keep) dst[(size_t)c * kWordsPerChunk + w] = v;
+      const T lo = min(min(v.x, v.y), min(v.z, v.w)), hi = max(max(v.x, v.y), max(v.z, v.w));
+      if (!any) { mn = lo; mx = hi; any = true; }
+      else { mn = lo < mn ? lo : mn; mx = hi > mx ? hi : mx; }
+    }
+    __syncthreads();                                         // every thread is done with this stage
+    if (threadIdx.x == 0 && c + kStages < kChunks) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy refill
+      mbar_expect_tx(&bars[stage], kStageBytes);
+      tma_load_3d(tma_smem + (size_t)stage * kStageBytes, &tm, x0, y0, z0 + (c + kStages) * kChunkZ, &bars[stage]);
+    }
+  }
+  // block min/max (every stored voxel incl. ghost), as in the generic path
+  __shared__ T t_mn[8], t_mx[8];
+  const unsigned fullm = 0xffffffffu;
+  for (int o = 16; o > 0; o >>= 1) {
+    const T omn = __shfl_down_sync(fullm, mn, o), omx = __shfl_down_sync(fullm, mx, o);
+    mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx;     // every thread holds at least one word (1944 words, 256 threads)
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { t_mn[warp] = mn; t_mx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T a = t_mn[0], cmax = t_mx[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { a = t_mn[w] < a ? t_mn[w] : a; cmax = t_mx[w] > cmax ? t_mx[w] : cmax; }
+    double* o = minmax + 4 * (uint64_t)(C.first_brick + b);
+    o[0] = (double)a; o[1] = (double)cmax; o[2] = -DBL_MAX; o[3] = DBL_MAX;
   }
 }
 
@@ -371,9 +509,65 @@ void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, doub
   }
 }
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {      // the driver entry point, without linking libcuda
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+template <typename T>
+bool launch_cut_tma(const void* lod_vol, void* store, const int32_t* store_index, double* minmax, const CutConsts& cc,
+                    uint64_t slot_voxels, CUtensorMapDataType dt, cudaStream_t s) {
+  constexpr int KBX = TmaBoxX<T>::value;
+  const uint64_t pitch = (uint64_t)cc.lod_size[0] * sizeof(T);
+  EncodeTiledFn enc = encode_tiled();
+  // what a tiled tensor map needs: 16-byte aligned base and strides, a box no larger than the tensor's rank allows
+  if (!enc || cc.brick[0] != kTB || cc.brick[1] != kTB || cc.brick[2] != kTB || pitch % 16 != 0 || ((uintptr_t)lod_vol & 15) != 0 ||
+      cc.lod_size[0] < (uint32_t)KBX || 2 * cc.overlap >= (uint32_t)kTB)
+    return false;
+  static const bool off = std::getenv("TVK_BRICKER_TMA") && std::getenv("TVK_BRICKER_TMA")[0] == '0';
+  if (off) return false;
+  CUtensorMap tm;
+  const cuuint64_t dims[3] = {cc.lod_size[0], cc.lod_size[1], cc.lod_size[2]};
+  const cuuint64_t strides[2] = {pitch, pitch * cc.lod_size[1]};
+  const cuuint32_t box[3] = {(cuuint32_t)KBX, (cuuint32_t)kTB, (cuuint32_t)kChunkZ};
+  const cuuint32_t es[3] = {1, 1, 1};
+  if (enc(&tm, dt, 3, const_cast<void*>(lod_vol), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  const size_t smem = (size_t)kStages * KBX * kTB * kChunkZ * sizeof(T);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cut_bricks_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set = true;
+  }
+  const uint32_t n = cc.layout[0] * cc.layout[1] * cc.layout[2];
+  cut_bricks_tma_kernel<T><<<n, 256, smem, s>>>(tm, (const T*)lod_vol, (T*)store, store_index, minmax, cc, slot_voxels);
+  return true;
+}
+}  // namespace
+
 void launch_cut_bricks(const void* lod_vol, void* store, const int32_t* store_index, double* minmax, const CutConsts& cc,
                        int dtype, uint64_t slot_bytes, cudaStream_t s) {
   const uint32_t n = cc.layout[0] * cc.layout[1] * cc.layout[2];
+  // 36^3 bricks of a level whose rows are 16-byte multiples: 3-D box loads through the TMA unit
+  if (dtype == TVK_U8 && launch_cut_tma<uint8_t>(lod_vol, store, store_index, minmax, cc, slot_bytes, CU_TENSOR_MAP_DATA_TYPE_UINT8, s)) return;
+  if (dtype == TVK_U16 && launch_cut_tma<uint16_t>(lod_vol, store, store_index, minmax, cc, slot_bytes / 2, CU_TENSOR_MAP_DATA_TYPE_UINT16, s)) return;
+  if (dtype == TVK_F32 && launch_cut_tma<float>(lod_vol, store, store_index, minmax, cc, slot_bytes / 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, s)) return;
   switch (dtype) {
     case TVK_U8: cut_bricks_kernel<uint8_t><<<n, 256, 0, s>>>((const uint8_t*)lod_vol, (uint8_t*)store, store_index, minmax, cc, slot_bytes); break;
     case TVK_U16: cut_bricks_kernel<uint16_t><<<n, 256, 0, s>>>((const uint16_t*)lod_vol, (uint16_t*)store, store_index, minmax, cc, slot_bytes / 2); break;
