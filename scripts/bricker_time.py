@@ -33,3 +33,4 @@ for n, dt in ((2048, "u16"), (1024, "f32"), (2048, "u8")):
         e = dict(os.environ, TVK_BRICKER_TMA=env)
         out = subprocess.run([sys.executable, __file__, mode, str(n), dt], capture_output=True, text=True, env=e)
         print(out.stdout.strip() or out.stderr[-800:])
+        print("\n".join(l for l in out.stderr.splitlines() if "level 0" in l or "level 1:" in l)[-400:])

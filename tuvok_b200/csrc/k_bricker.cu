@@ -219,22 +219,30 @@ __global__ void __launch_bounds__(256) cut_bricks_kernel(const T* __restrict__ v
 
 // ---------------------------------------------------------------------------------------------
 // The same brick cut through the TENSOR MEMORY ACCELERATOR (sm_100a; round 2).  A full 36^3 brick is
-// a 3-D box of the LoD volume whose origin is (brick * inner - ghost): exactly what one cp.async.bulk.tensor.3d
-// delivers -- with the ghost cells that hang over the domain border zero-filled by the TMA unit itself (out-of-bound box
-// elements read as 0 = the reference's border rule without clamping).  The box's inner extent has to be a multiple of
-// 16 bytes, so it is loaded KBX = 48 / 40 / 36 voxels wide (u8 / u16 / f32) and the 36 wanted voxels of each row are taken
-// from shared memory as ONE 4-voxel word per thread (36 = 9 x 4; 4 / 8 / 16-byte LDS + coalesced STG into the slot, which
-// is one contiguous block).  The brick moves in 6 z-chunks of 6 slices through a ring of kStages shared-memory stages,
-// each with its mbarrier: thread 0 issues the box loads, all 256 threads drain -- the copy engine fetches chunk c + kStages
-// while chunk c is stored.  Min/max (every stored voxel incl. ghost) and the stale-corner rule of FillOverlap for LoD >= 1
-// ride along in the drain loop.  Bricks the box cannot describe (ragged last bricks, clamped borders) take the generic path.
+// a 3-D box of the LoD volume whose origin is (brick * inner - ghost): what one cp.async.bulk.tensor.3d delivers -- with
+// the ghost cells that hang over the domain border zero-filled by the TMA unit itself (out-of-bound box elements read as 0
+// = the reference's border rule without clamping).  Two alignment rules of the unit shape the kernel, the second one
+// MEASURED on the B200 (scripts/probes/tma_probe.cu, profiles/r2o_tma_probe.txt): the box's inner extent must be a multiple
+// of 16 bytes, and so must the inner START coordinate (x = 8 u16 voxels loads, x = 4 or x = -2 raises "illegal
+// instruction"; y and z are free, negative included).  The box therefore starts at x0 rounded down to 16 bytes and is
+// KBX = 64 / 48 / 40 voxels wide (u8 / u16 / f32); the 36 wanted voxels of a row begin `skip` voxels into the box row
+// (skip is even for an even ghost width) and leave shared memory as 4-voxel words assembled from two 2-voxel reads,
+// stored coalesced into the slot, which is one contiguous block.  The brick moves in 6 z-chunks of 6 slices through a ring
+// of kStages shared-memory stages, each with its mbarrier: thread 0 issues the box loads, all 256 threads drain -- the copy
+// engine fetches chunk c + kStages while chunk c is stored.  Min/max (every stored voxel incl. ghost) and the stale-corner
+// rule of FillOverlap for LoD >= 1 ride along in the drain loop.  Bricks the box cannot describe (ragged last bricks,
+// clamped borders) take the generic path inside the same launch.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTB = 36, kChunkZ = 6, kChunks = kTB / kChunkZ, kStages = 3;
 template <typename T> struct Vec4;
-template <> struct Vec4<uint8_t> { using type = uchar4; };
-template <> struct Vec4<uint16_t> { using type = ushort4; };
-template <> struct Vec4<float> { using type = float4; };
-template <typename T> struct TmaBoxX { static constexpr int value = (int)(((kTB * sizeof(T) + 15) / 16 * 16) / sizeof(T)); };
+template <> struct Vec4<uint8_t> { using type = uchar4; using half = uchar2; };
+template <> struct Vec4<uint16_t> { using type = ushort4; using half = ushort2; };
+template <> struct Vec4<float> { using type = float4; using half = float2; };
+// voxels per 16 bytes; box width = 36 + the largest even skip, rounded up to 16 bytes
+template <typename T> struct TmaBoxX {
+  static constexpr int align = (int)(16 / sizeof(T));
+  static constexpr int value = (kTB + align - 2 + align - 1) / align * align;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -256,12 +264,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) cut_bricks_tma_kernel(const __grid_constant__ CUtensorMap tm, const T* __restrict__ vol, T* store,
+__global__ void __launch_bounds__(256) cut_bricks_tma_kernel(const CUtensorMap* __restrict__ tmp, const T* __restrict__ vol, T* store,
                                                              const int32_t* __restrict__ store_index, double* minmax,
                                                              const CutConsts C, uint64_t slot_voxels) {
   constexpr int KBX = TmaBoxX<T>::value;
   constexpr uint32_t kStageBytes = KBX * kTB * kChunkZ * sizeof(T);
+  constexpr int KA = TmaBoxX<T>::align;
   using V = typename Vec4<T>::type;
+  using H = typename Vec4<T>::half;
   extern __shared__ __align__(128) unsigned char tma_smem[];
   __shared__ __align__(8) uint64_t bars[kStages];
   const uint32_t b = blockIdx.x;
@@ -280,7 +290,9 @@ __global__ void __launch_bounds__(256) cut_bricks_tma_kernel(const __grid_consta
     return;
   }
   const int ov = (int)C.overlap;
-  const int x0 = (int)(bx * (kTB - 2 * ov)) - ov, y0 = (int)(by * (kTB - 2 * ov)) - ov, z0 = (int)(bz * (kTB - 2 * ov)) - ov;
+  const int xw = (int)(bx * (kTB - 2 * ov)) - ov, y0 = (int)(by * (kTB - 2 * ov)) - ov, z0 = (int)(bz * (kTB - 2 * ov)) - ov;
+  const int skip = ((xw % KA) + KA) % KA;      // the wanted row starts `skip` voxels into the 16-byte aligned box row
+  const int x0 = xw - skip;
   const int64_t at = store_index ? (int64_t)store_index[C.first_brick + b] : (int64_t)(C.first_brick + b);
   const bool keep = at >= 0;
   V* dst = reinterpret_cast<V*>(store + (uint64_t)(keep ? at : 0) * slot_voxels);
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(256) cut_bricks_tma_kernel(const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int c = 0; c < kStages && c < kChunks; c++) {
       mbar_expect_tx(&bars[c], kStageBytes);
-      tma_load_3d(tma_smem + (size_t)c * kStageBytes, &tm, x0, y0, z0 + c * kChunkZ, &bars[c]);
+      tma_load_3d(tma_smem + (size_t)c * kStageBytes, tmp, x0, y0, z0 + c * kChunkZ, &bars[c]);
     }
   }
   __syncthreads();
@@ -297,16 +309,21 @@ __global__ void __launch_bounds__(256) cut_bricks_tma_kernel(const __grid_consta
   bool any = false;
   const bool stale_rule = C.lod > 0;
   constexpr uint32_t kWordsPerChunk = kTB * kChunkZ * (kTB / 4);   // 9 words per row
+  const uint32_t trow = threadIdx.x / (kTB / 4), g = threadIdx.x - trow * (kTB / 4);
   for (int c = 0; c < kChunks; c++) {
     const int stage = c % kStages;
     mbar_wait(&bars[stage], (uint32_t)((c / kStages) & 1));
     const T* tile = reinterpret_cast<const T*>(tma_smem + (size_t)stage * kStageBytes);
-    for (uint32_t w = threadIdx.x; w < kWordsPerChunk; w += blockDim.x) {
-      const uint32_t row = w / (kTB / 4), g = w - row * (kTB / 4);
-      const uint32_t lz = (uint32_t)c * kChunkZ + row / kTB, ly = row % kTB;
-      V v = *reinterpret_cast<const V*>(tile + (size_t)row * KBX + g * 4);
+    // 252 of the 256 threads: thread = (row within a group of 28 rows, word of the row); no division in the loop
+    for (uint32_t row = trow; row < (uint32_t)(kTB * kChunkZ) && threadIdx.x < 252u; row += 28u) {
+      const uint32_t w = row * (kTB / 4) + g;
+      const T* src = tile + (size_t)row * KBX + skip + g * 4;
+      const H h0 = *reinterpret_cast<const H*>(src), h1 = *reinterpret_cast<const H*>(src + 2);
+      V v;
+      v.x = h0.x; v.y = h0.y; v.z = h1.x; v.w = h1.y;
       if (stale_rule) {
         // FillOverlap's copy order leaves three ghost corners of every LoD >= 1 brick zero (see the generic path)
+        const uint32_t lz = (uint32_t)c * kChunkZ + row / kTB, ly = row % kTB;
         const int gy = (int)ly < ov ? -1 : (int)ly >= kTB - ov ? 1 : 0, gz = (int)lz < ov ? -1 : (int)lz >= kTB - ov ? 1 : 0;
         if (gy != 0 && gz != 0 && (g == 0 || g == kTB / 4 - 1)) {
           T e[4] = {v.x, v.y, v.z, v.w};
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(256) cut_bricks_tma_kernel(const __grid_consta
     if (threadIdx.x == 0 && c + kStages < kChunks) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy refill
       mbar_expect_tx(&bars[stage], kStageBytes);
-      tma_load_3d(tma_smem + (size_t)stage * kStageBytes, &tm, x0, y0, z0 + (c + kStages) * kChunkZ, &bars[stage]);
+      tma_load_3d(tma_smem + (size_t)stage * kStageBytes, tmp, x0, y0, z0 + (c + kStages) * kChunkZ, &bars[stage]);
     }
   }
   // block min/max (every stored voxel incl. ghost), as in the generic path
@@ -336,10 +353,14 @@ __global__ void __launch_bounds__(256) cut_bricks_tma_kernel(const __grid_consta
   const unsigned fullm = 0xffffffffu;
   for (int o = 16; o > 0; o >>= 1) {
     const T omn = __shfl_down_sync(fullm, mn, o), omx = __shfl_down_sync(fullm, mx, o);
-    mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx;     // every thread holds at least one word (1944 words, 256 threads)
+    const int oany = __shfl_down_sync(fullm, (int)any, o);
+    if (oany) {                                            // threads 252..255 hold no word
+      if (!any) { mn = omn; mx = omx; any = true; }
+      else { mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx; }
+    }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { t_mn[warp] = mn; t_mx[warp] = mx; }
+  if (lane == 0) { t_mn[warp] = mn; t_mx[warp] = mx; }   // lane 0 of every warp holds words (thread 224 < 252)
   __syncthreads();
   if (threadIdx.x == 0) {
     T a = t_mn[0], cmax = t_mx[0];
@@ -534,7 +555,7 @@ bool launch_cut_tma(const void* lod_vol, void* store, const int32_t* store_index
   EncodeTiledFn enc = encode_tiled();
   // what a tiled tensor map needs: 16-byte aligned base and strides, a box no larger than the tensor's rank allows
   if (!enc || cc.brick[0] != kTB || cc.brick[1] != kTB || cc.brick[2] != kTB || pitch % 16 != 0 || ((uintptr_t)lod_vol & 15) != 0 ||
-      cc.lod_size[0] < (uint32_t)KBX || 2 * cc.overlap >= (uint32_t)kTB)
+      cc.lod_size[0] < (uint32_t)KBX || 2 * cc.overlap >= (uint32_t)kTB || (cc.overlap & 1u))
     return false;
   static const bool off = std::getenv("TVK_BRICKER_TMA") && std::getenv("TVK_BRICKER_TMA")[0] == '0';
   if (off) return false;
@@ -555,8 +576,15 @@ bool launch_cut_tma(const void* lod_vol, void* store, const int32_t* store_index
     }
     attr_set = true;
   }
+  // the descriptor lives in global memory (a small ring: one per level in flight), written by a stream-ordered copy
+  static CUtensorMap* ring = nullptr;
+  static int next = 0;
+  constexpr int kRing = 32;
+  if (!ring && cudaMalloc(&ring, kRing * sizeof(CUtensorMap)) != cudaSuccess) { cudaGetLastError(); ring = nullptr; return false; }
+  CUtensorMap* slot = ring + (next++ % kRing);
+  if (cudaMemcpyAsync(slot, &tm, sizeof(tm), cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); return false; }
   const uint32_t n = cc.layout[0] * cc.layout[1] * cc.layout[2];
-  cut_bricks_tma_kernel<T><<<n, 256, smem, s>>>(tm, (const T*)lod_vol, (T*)store, store_index, minmax, cc, slot_voxels);
+  cut_bricks_tma_kernel<T><<<n, 256, smem, s>>>(slot, (const T*)lod_vol, (T*)store, store_index, minmax, cc, slot_voxels);
   return true;
 }
 }  // namespace
