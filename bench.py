@@ -504,7 +504,7 @@ def run_tvk(args, rank, world, local_rank):
         set_view(i)
         if lib_sl:
             st = r.SortLastFrame()
-            sl_stats.append((st.frame.ms_raycast, st.ms_exchange, st.ms_frame))
+            sl_stats.append((st.frame.ms_raycast, st.ms_exchange, st.ms_frame, st.ms_wait_peers))
             sl_mode[0] = int(st.peer_memory)
             return st.frame
         if pipe is not None:
@@ -761,8 +761,9 @@ def run_tvk(args, rank, world, local_rank):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         if timed_sl:
-            mine = torch.tensor([float(np.mean([a for a, _, _ in timed_sl])), float(np.mean([b for _, b, _ in timed_sl])),
-                                 float(np.mean([c for _, _, c in timed_sl])), float(np.sum(samples)) / n_views,
+            mine = torch.tensor([float(np.mean([x[0] for x in timed_sl])), float(np.mean([x[1] for x in timed_sl])),
+                                 float(np.mean([x[2] for x in timed_sl])), float(np.mean([x[3] for x in timed_sl])),
+                                 float(np.sum(samples)) / n_views,
                                  float(torch.cuda.max_memory_allocated() / 2 ** 30)], dtype=torch.float64, device="cuda")
             allr = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allr, mine)
@@ -860,8 +861,9 @@ def run_tvk(args, rank, world, local_rank):
         if composite is not None:
             line["parity_composite"] = composite
         if per_rank is not None:
-            line["per_rank"] = {"columns": ["kernel_ms", "exchange_ms (slices + blend + gather)", "frame_ms", "samples_per_frame",
-                                            "peak_device_GiB"], "rows": per_rank}
+            line["per_rank"] = {"columns": ["kernel_ms", "exchange_ms (slices + blend + gather, incl. waiting for the slowest rank)",
+                                            "frame_ms", "of exchange_ms: waiting for the peers' partial images (peer-memory path)",
+                                            "samples_per_frame", "peak_device_GiB"], "rows": per_rank}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             cs = CpuSample(args.config, args.cpu_vol, threads)

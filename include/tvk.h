@@ -466,7 +466,7 @@ typedef struct {
   uint64_t bytes_sent;         /* image bytes this rank sent (exchange + gather) */
   uint64_t slice_lo, slice_hi; /* the pixel range this rank composited */
   int32_t  peer_memory;        /* 1: the frame went through peer memory (no NCCL call on its path), 0: NCCL exchange */
-  int32_t  pad_;
+  float    ms_wait_peers;      /* peer-memory path: the part of ms_exchange spent waiting for the slowest rank's partial image */
 } tvk_sortlast_stats;
 /* rank 0 creates the id (ncclGetUniqueId) and hands it to the other ranks by whatever means the host has */
 int tvk_sortlast_unique_id(uint8_t id[TVK_COMM_ID_BYTES]);

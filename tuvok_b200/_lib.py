@@ -69,7 +69,7 @@ class OctreeFileInfo(C.Structure):
 
 class SortLastStats(C.Structure):
     _fields_ = [("frame", FrameStats), ("ms_exchange", C.c_float), ("ms_frame", C.c_float), ("bytes_sent", C.c_uint64),
-                ("slice_lo", C.c_uint64), ("slice_hi", C.c_uint64), ("peer_memory", C.c_int32), ("pad_", C.c_int32)]
+                ("slice_lo", C.c_uint64), ("slice_hi", C.c_uint64), ("peer_memory", C.c_int32), ("ms_wait_peers", C.c_float)]
 
 
 COMM_ID_BYTES = 128
