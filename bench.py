@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--path", default="gridleaper", choices=["gridleaper", "classic", "mip"],
                     help="gridleaper: GLGridLeaper page-table traversal (default); classic: per-brick GLRaycaster path; "
                          "mip: HQ MIP frame of a 2D window (GLRaycaster-MIP-Rot-FS, rotating about Y)")
-    ap.add_argument("--split", default="auto", choices=["auto", "screen", "depth", "depth2", "octant", "depthw", "octantw", "pipeline"],
+    ap.add_argument("--split", default="auto", choices=["auto", "screen", "depth", "depth2", "octant", "paired", "depthw", "octantw", "pipeline"],
                     help="sort-last partition policy; auto = octant.  octant / screen run inside the library (tvk_sortlast_frame: "
                          "direct send over NCCL, octant also shards the brick store at the source); the others are the "
                          "round-1 host-driven variants (tuvok_b200/sortlast.py: binary swap, depth pipeline)")
@@ -424,7 +424,7 @@ def run_tvk(args, rank, world, local_rank):
     if classic and world > 1:
         raise SystemExit("the classic / MIP paths are single-GPU (sort-last shards the GridLeaper path)")
     split = args.split if args.split != "auto" else "octant"
-    legacy = world > 1 and split not in ("octant", "screen")     # round-1 host-driven policies (binary swap / pipeline)
+    legacy = world > 1 and split not in ("octant", "screen", "paired")     # round-1 host-driven policies (binary swap / pipeline)
     do_parity = not args.no_parity and not classic
 
     def barrier():
@@ -475,7 +475,7 @@ def run_tvk(args, rank, world, local_rank):
     info = r.info()
     pipe = sl = None
     if lib_sl:
-        sortlast.init_library_sortlast(r, rank, world, dist, L.SL_OCTANT if split == "octant" else L.SL_SCREEN)
+        sortlast.init_library_sortlast(r, rank, world, dist, {"octant": L.SL_OCTANT, "screen": L.SL_SCREEN, "paired": L.SL_PAIRED}[split])
     elif legacy and split == "pipeline":
         pipe = sortlast.DepthPipeline(r, rank, world, finest, flayout, ext, align=1)
         r.SetRotation(workloads.orbit_rotation(0, 36))
@@ -563,11 +563,12 @@ def run_tvk(args, rank, world, local_rank):
         res = []
         for v in PARITY_VIEWS:
             set_view(v)
-            if lib_sl:
-                bmin, bmax, _, _, _ = r.SortLastBlock()      # the rank's block for this view, as the library cuts it
-                r.SetShardBox(bmin, bmax)
-            res.append(parity_gate.check_frame(r, w["size"], w["dtype"], brick, w["overlap"], stride=args.parity_stride,
-                                               threads=max(1, (os.cpu_count() or 8) // max(1, world))))
+            for which in range(r._sl_blocks_per_rank if lib_sl else 1):
+                if lib_sl:
+                    bmin, bmax = r.SortLastBlockOf(which)    # the rank's block(s) for this view, as the library cuts them
+                    r.SetShardBox(bmin, bmax)
+                res.append(parity_gate.check_frame(r, w["size"], w["dtype"], brick, w["overlap"], stride=args.parity_stride,
+                                                   threads=max(1, (os.cpu_count() or 8) // max(1, world))))
         if lib_sl:
             r.SetShardBox((0, 0, 0), (1, 1, 1))
         parity = merge_parity(res)
@@ -858,7 +859,7 @@ def run_tvk(args, rank, world, local_rank):
                          "fetch": fetch},
             "e2e": {"value": k / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(C_sizeof_params()),
                     "d2h_bytes_per_step": n_pixels * 4 + 8},
-            "gpu_launches": k * (2 * world if pipe is not None else 3 * world if lib_sl else 2 if sl is None else 2 + int(np.log2(world))),
+            "gpu_launches": k * (2 * world if pipe is not None else (4 if split == "paired" else 3) * world if lib_sl else 2 if sl is None else 2 + int(np.log2(world))),
             "clocks": clocks,
         }
         if stream_obj is not None:

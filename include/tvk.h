@@ -457,7 +457,12 @@ int tvk_probe_fetch(tvk_ctx* ctx, uint32_t steps, const float dir[3], float* ms,
 /* how the brick grid is cut: OCTANT = longest axis of the block at every level (view independent: a rank's bricks never
  * change, the brick store can be sharded at the source); SCREEN = the axes most perpendicular to the view first (blocks
  * lie side by side on screen; re-cut when the view's dominant axes change) */
-typedef enum { TVK_SL_OCTANT = 0, TVK_SL_SCREEN = 1 } tvk_sortlast_policy;
+typedef enum { TVK_SL_OCTANT = 0, TVK_SL_SCREEN = 1, TVK_SL_PAIRED = 2 } tvk_sortlast_policy;
+/* PAIRED: the grid is cut into 2 x n_ranks blocks (longest axis at every level, view independent) and rank r renders block
+ * r AND the block with every cut side flipped -- its point mirror -- in two concurrent traversal launches.  For any camera
+ * outside the volume one of the two lies on the near side (many samples) and the other on the far side (few: hidden by
+ * early ray termination), so the load of every view is balanced by construction, and the blocks -- hence the longest
+ * rays -- are half as long.  2 x n_ranks partial images are folded per pixel slice (n_ranks <= 8). */
 typedef struct {
   tvk_frame_stats frame;       /* this rank's subframe; frame.ms_raycast = its traversal kernel */
   float ms_exchange;           /* device time from the end of the traversal to the gathered RGBA8 frame: slice exchange +
@@ -477,6 +482,9 @@ int tvk_sortlast_shutdown(tvk_ctx* ctx);
  * (order[0] = frontmost, n_ranks entries) and its pixel slice; any pointer may be NULL */
 int tvk_sortlast_get_block(tvk_ctx* ctx, float clip_min[3], float clip_max[3], int* order, uint64_t* slice_lo,
                            uint64_t* slice_hi);
+/* the `which`-th block of this rank (0, or 1 = its second block under TVK_SL_PAIRED) and the number of blocks in the
+ * plan (= entries of `order` above: n_ranks, or 2 x n_ranks when paired); any pointer may be NULL */
+int tvk_sortlast_get_block_of(tvk_ctx* ctx, int which, float clip_min[3], float clip_max[3], int* n_blocks);
 /* collective: one subframe on every rank + compositing.  Bricks a rank missed are paged in afterwards as in tvk_render;
  * st->frame.converged is this rank's flag (the host ANDs it over the ranks when it needs a global one). */
 int tvk_sortlast_frame(tvk_ctx* ctx, tvk_sortlast_stats* st);

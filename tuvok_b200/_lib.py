@@ -73,7 +73,7 @@ class SortLastStats(C.Structure):
 
 
 COMM_ID_BYTES = 128
-SL_OCTANT, SL_SCREEN = 0, 1
+SL_OCTANT, SL_SCREEN, SL_PAIRED = 0, 1, 2
 
 
 class ClassicBrick(C.Structure):
@@ -173,6 +173,7 @@ SIGNATURES = {
     "tvk_sortlast_init": (C.c_int, [P, C.c_uint8 * COMM_ID_BYTES, C.c_int, C.c_int, C.c_int]),
     "tvk_sortlast_shutdown": (C.c_int, [P]),
     "tvk_sortlast_get_block": (C.c_int, [P, f32x3, f32x3, P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tvk_sortlast_get_block_of": (C.c_int, [P, C.c_int, f32x3, f32x3, C.POINTER(C.c_int)]),
     "tvk_sortlast_frame": (C.c_int, [P, C.POINTER(SortLastStats)]),
     "tvk_sortlast_read_rgba8": (C.c_int, [P, P, C.c_size_t]),
     "tvk_sortlast_read_rgba8_async": (C.c_int, [P, P, C.c_size_t]),

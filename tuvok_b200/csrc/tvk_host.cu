@@ -29,6 +29,7 @@ namespace {
 thread_local std::string g_create_err;
 
 void proc_free(tvk_ctx* ctx);   // tvk_procedural.inc
+int sl_second_pass(tvk_ctx* ctx);   // tvk_sortlast.inc: the rank's second brick block (paired policy), concurrent with the first
 int proc_brick_cb(void* user, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, void* dst, size_t cap);
 const unsigned char* proc_acquire(tvk_ctx* ctx, uint32_t x, uint32_t y, uint32_t z, uint32_t lod, uint32_t* cache_slot);
 void proc_release(tvk_ctx* ctx, const std::vector<uint32_t>& cache_slots);
@@ -1685,6 +1686,8 @@ static int render_enqueue(tvk_ctx* ctx) {
     CU(cudaMemsetAsync(ctx->visited_d, 0, ctx->visited_h.size() * 4, s));
   }
   int rc = raycast_pass(ctx, true);
+  if (rc) return rc;
+  rc = sl_second_pass(ctx);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev[1], s));
   // GLHashTable::GetData: compact on the device, read back count + (index,value) pairs

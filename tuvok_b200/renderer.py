@@ -750,7 +750,8 @@ class CudaGridLeaper:
     def SortLastInit(self, comm_id, rank, n_ranks, policy=L.SL_OCTANT):
         buf = (C.c_uint8 * L.COMM_ID_BYTES)(*comm_id)
         self._ck(self._lib.tvk_sortlast_init(self._h, buf, int(rank), int(n_ranks), int(policy)))
-        self._sl_n = int(n_ranks)
+        self._sl_n = int(n_ranks) * (2 if int(policy) == L.SL_PAIRED else 1)     # blocks in the plan = entries of `order`
+        self._sl_blocks_per_rank = 2 if int(policy) == L.SL_PAIRED else 1
 
     def SortLastShutdown(self):
         self._ck(self._lib.tvk_sortlast_shutdown(self._h))
@@ -763,6 +764,14 @@ class CudaGridLeaper:
         lo, hi = C.c_uint64(), C.c_uint64()
         self._ck(self._lib.tvk_sortlast_get_block(self._h, a, b, C.cast(order, C.c_void_p), C.byref(lo), C.byref(hi)))
         return tuple(a), tuple(b), list(order), lo.value, hi.value
+
+    def SortLastBlockOf(self, which=0):
+        """(clip_min, clip_max) of this rank's `which`-th block (paired policy: 0 and 1) for the current view."""
+        self._push_params()
+        a, b = L.f32x3(), L.f32x3()
+        nb = C.c_int()
+        self._ck(self._lib.tvk_sortlast_get_block_of(self._h, int(which), a, b, C.byref(nb)))
+        return tuple(a), tuple(b)
 
     def SortLastFrame(self):
         """One subframe on every rank + direct-send compositing + RGBA8 gather on rank 0 (collective)."""
