@@ -459,10 +459,11 @@ int tvk_probe_fetch(tvk_ctx* ctx, uint32_t steps, const float dir[3], float* ms,
  * lie side by side on screen; re-cut when the view's dominant axes change) */
 typedef enum { TVK_SL_OCTANT = 0, TVK_SL_SCREEN = 1, TVK_SL_PAIRED = 2 } tvk_sortlast_policy;
 /* PAIRED: the grid is cut into 2 x n_ranks blocks (longest axis at every level, view independent) and rank r renders block
- * r AND the block with every cut side flipped -- its point mirror -- in two concurrent traversal launches.  For any camera
- * outside the volume one of the two lies on the near side (many samples) and the other on the far side (few: hidden by
- * early ray termination), so the load of every view is balanced by construction, and the blocks -- hence the longest
- * rays -- are half as long.  2 x n_ranks partial images are folded per pixel slice (n_ranks <= 8). */
+ * r AND its mirror block (the side flipped at the first cut of every axis) in two concurrent traversal launches.  For a
+ * camera outside the volume one of the two lies on the near side and the other on the far side, so a view's load is
+ * balanced by construction.  2 x n_ranks partial images are folded per pixel slice (n_ranks <= 8).  MEASURED SLOWER than
+ * OCTANT on C3 (a far block still takes all of its own samples -- early termination does not reach
+ * across blocks -- so pairing converts idle time into samples); kept as an option, not the default. */
 typedef struct {
   tvk_frame_stats frame;       /* this rank's subframe; frame.ms_raycast = its traversal kernel */
   float ms_exchange;           /* device time from the end of the traversal to the gathered RGBA8 frame: slice exchange +
