@@ -540,3 +540,28 @@ def cv_compose(params, hit_pos, hit_normal, cv_pos, cv_normal, cv_color, cv_para
     col, prm, pk = (np.ascontiguousarray(v, np.float32) for v in (cv_color, cv_param, pick))
     lib().orc_cv_compose(C.byref(params), _p(hit_pos), _p(hit_normal), _p(cv_pos), _p(cv_normal), _p(col), _p(prm), _p(pk), _p(out))
     return out
+
+
+# ---- value quantiser (IO/Quantize.h, AbstrConverter::Process8Bits) ------------------------------------------------
+ST_I8, ST_U8, ST_I16, ST_U16, ST_I32, ST_U32, ST_F32, ST_F64 = range(8)
+ST_OF = {np.dtype(np.int8): ST_I8, np.dtype(np.uint8): ST_U8, np.dtype(np.int16): ST_I16, np.dtype(np.uint16): ST_U16,
+         np.dtype(np.int32): ST_I32, np.dtype(np.uint32): ST_U32, np.dtype(np.float32): ST_F32, np.dtype(np.float64): ST_F64}
+
+
+class QuantizeInfo(C.Structure):
+    _fields_ = [("min", C.c_double), ("max", C.c_double), ("factor", C.c_double), ("bin_count", C.c_uint64),
+                ("changed", C.c_int32), ("hist_set", C.c_int32)]
+
+
+def quantize(src, out_bits=16):
+    """-> (dst or None when the input is used as is, histogram uint64[256 | 4096], QuantizeInfo)"""
+    src = np.ascontiguousarray(src).reshape(-1)
+    if src.dtype in (np.dtype(np.int8), np.dtype(np.uint8)):
+        out_bits = 8
+    dst = np.zeros(src.size, np.uint8 if out_bits == 8 else np.uint16)
+    hist = np.zeros(256 if out_bits == 8 else 4096, np.uint64)
+    info = QuantizeInfo()
+    rc = lib().orc_quantize(_p(src), ST_OF[src.dtype], C.c_uint64(src.size), out_bits, _p(dst), _p(hist), C.byref(info))
+    if rc:
+        raise ValueError("orc_quantize refused the input")
+    return (dst if info.changed else None), hist, info
