@@ -256,6 +256,28 @@ typedef struct {
   uint32_t host_cache_pinned;      /* the cache is page-locked: cached bricks are copied by DMA straight out of it */
 } tvk_stream_stats;
 int tvk_get_stream_stats(tvk_ctx* ctx, tvk_stream_stats* out);
+/* ---- value quantiser of the import path ---------------------------------------------------------------
+ * Quantize<T, U> (IO/Quantize.h:427-577) and AbstrConverter::Process8Bits (IO/AbstrConverter.cpp:73-157) as RAWConverter's
+ * quantize() calls them (IO/RAWConverter.cpp:205-300), for n values that are already in device memory: a range pass, then
+ * every value -> min(max_out, U((v - min) * factor)) (factor = max_out / (max - min), capped at 1 for integer input so
+ * that integers are only ever compressed, never stretched) plus the 1D histogram (256 bins for 8-bit output, 4096 for
+ * 16-bit) that becomes the Histogram1DDataBlock.  Signed bytes are biased by 128, unsigned bytes are only counted.
+ * Unsigned 16-bit data whose maximum is below 4096 needs no processing: info->changed = 0, dst is not written, and
+ * info->hist_set = 0 because the reference returns before it sets the histogram (hist then holds the direct value counts
+ * the bin count is taken from).  A constant input maps to 0 (the reference divides by zero).  src_device must be 16-byte
+ * aligned; dst_device: n values of uint8 / uint16; hist: HOST array of 256 / 4096 counters. */
+typedef enum { TVK_ST_I8 = 0, TVK_ST_U8 = 1, TVK_ST_I16 = 2, TVK_ST_U16 = 3, TVK_ST_I32 = 4, TVK_ST_U32 = 5, TVK_ST_F32 = 6,
+               TVK_ST_F64 = 7 } tvk_scalar_type;
+typedef struct {
+  double   min, max;      /* value range of the input */
+  double   factor;        /* fQuantFact */
+  uint64_t bin_count;     /* *iBinCount: non-zero bins (data used as is) or bins_needed */
+  int32_t  changed;       /* Quantize's return value: 1 = dst holds the quantised data, 0 = the input is used as is */
+  int32_t  hist_set;      /* 0: the reference leaves the Histogram1DDataBlock untouched (early return) */
+  float    ms_range, ms_map;   /* device time of the two passes (CUDA events) */
+} tvk_quantize_info;
+int tvk_quantize(tvk_ctx* ctx, const void* src_device, int scalar_type, uint64_t n, int out_bits, void* dst_device,
+                 uint64_t* hist, tvk_quantize_info* info);
 int tvk_get_info(const tvk_ctx* ctx, tvk_info* out);
 /* parity taps: MaxMinForKey table and one brick (x-fastest, own size incl. ghost) */
 int tvk_get_minmax(tvk_ctx* ctx, double* dst, uint64_t n_bricks);

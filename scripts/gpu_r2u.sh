@@ -1,0 +1,6 @@
+#!/bin/bash
+P=${1:-r2u}
+mkdir -p gpurun_out
+make -C oracle liborc.so > /dev/null 2>&1
+timeout 900 python -m pytest tests/test_gpu_quantize.py -m gpu -q -x 2>&1 | grep -v "warning\|orc_render.c\|^\s*[0-9]* |\|string_fortified\|~~\|In function\|inlined\|In file\|from \|^\s*|" | tail -20
+python scripts/quantize_time.py 2>&1 | tee gpurun_out/${P}_quantize.txt

@@ -92,6 +92,13 @@ class StreamStats(C.Structure):
                 ("source_thread_ms", C.c_double), ("source_threads", C.c_uint32), ("host_cache_pinned", C.c_uint32)]
 
 
+class QuantizeInfo(C.Structure):
+    _fields_ = [("min", C.c_double), ("max", C.c_double), ("factor", C.c_double), ("bin_count", C.c_uint64),
+                ("changed", C.c_int32), ("hist_set", C.c_int32), ("ms_range", C.c_float), ("ms_map", C.c_float)]
+
+
+ST_I8, ST_U8, ST_I16, ST_U16, ST_I32, ST_U32, ST_F32, ST_F64 = range(8)
+
 SIGNATURES = {
     "tvk_abi_version": (C.c_uint32, []),
     "tvk_create": (C.c_int, [C.POINTER(DeviceCfg), C.POINTER(P)]),
@@ -122,6 +129,7 @@ SIGNATURES = {
                                        C.c_uint32, P, C.c_size_t, u32x3]),
     "tvk_procedural_minmax": (C.c_int, [P, C.c_int, u32x3, C.c_int, C.c_uint32, u32x3, C.c_uint32, C.c_uint64, C.c_uint64, P]),
     "tvk_get_stream_stats": (C.c_int, [P, C.POINTER(StreamStats)]),
+    "tvk_quantize": (C.c_int, [P, P, C.c_int, C.c_uint64, C.c_int, P, P, C.POINTER(QuantizeInfo)]),
     "tvk_get_info": (C.c_int, [P, C.POINTER(Info)]),
     "tvk_get_minmax": (C.c_int, [P, P, C.c_uint64]),
     "tvk_get_brick_size": (C.c_int, [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32x3]),

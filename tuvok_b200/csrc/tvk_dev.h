@@ -179,5 +179,12 @@ void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, doub
 void launch_cut_bricks(const void* lod_vol, void* store, const int32_t* store_index, double* minmax, const CutConsts& cc,
                        int dtype, uint64_t slot_bytes, cudaStream_t s);
 
+// value quantiser (k_quantize.cu)
+struct QuantParams { double f, fh; uint32_t max_out, bins; int32_t mode, out_bits; };
+int quant_blocks();   // CTAs of the range pass = (min, max) pairs it writes
+void launch_quant_minmax(const void* src, int type, uint64_t n, void* part_d, cudaStream_t s);
+void launch_quant_map(const void* src, int type, uint64_t n, double mn, const QuantParams& P, void* dst, unsigned long long* hist,
+                      cudaStream_t s);
+
 }  // namespace tvk
 #endif

@@ -258,6 +258,16 @@ class CudaGridLeaper:
         self._ck(self._lib.tvk_get_stream_stats(self._h, C.byref(st)))
         return st
 
+    def Quantize(self, src_device_ptr, scalar_type, n, out_bits, dst_device_ptr):
+        """tvk_quantize: Quantize<T, U> / Process8Bits of the import path on data in device memory.
+        -> (histogram uint64[256 | 4096], QuantizeInfo)"""
+        bits = 8 if scalar_type in (L.ST_I8, L.ST_U8) else int(out_bits)
+        hist = np.zeros(256 if bits == 8 else 4096, np.uint64)
+        info = L.QuantizeInfo()
+        self._ck(self._lib.tvk_quantize(self._h, C.c_void_p(int(src_device_ptr)), int(scalar_type), int(n), bits,
+                                        C.c_void_p(int(dst_device_ptr)) if dst_device_ptr else None, _ptr(hist), C.byref(info)))
+        return hist, info
+
     def synth_volume(self, dst_device_ptr, kind, size, dtype, seed=0x5EED):
         self._ck(self._lib.tvk_synth_volume(self._h, C.c_void_p(int(dst_device_ptr)), kind, L.u32x3(*size), dtype, seed))
 
