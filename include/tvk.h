@@ -191,6 +191,20 @@ typedef struct {
 int tvk_open_octree_file(tvk_ctx* ctx, const char* path, uint64_t offset, uint64_t uvf_file_version,
                          const float scale[3], const double* minmax, uint64_t n_minmax, double range_max,
                          float max_gradient_magnitude, tvk_octree_file_info* info);
+/* DynamicBrickingDS on the device (IO/DynamicBrickingDS.cpp; IOManager::LoadRebrickedDataset, IO/IOManager.cpp:1281-1320):
+ * a file converted with LARGE bricks is re-cut into bricks of target_brick_size (incl. ghost; clamped to the source's) while
+ * it is loaded -- every source brick is streamed once (pinned, double buffered) and cut on the device into the brick store,
+ * which then serves the pool like a tvk_build_volume store; min / max per target brick are computed in the same pass
+ * (MinMaxMode MM_PRECOMPUTE).  The reference's rules hold: the target's inner size must divide the source's on every axis,
+ * the ghost width is the source's, a target brick is a sub-box of one source brick (ghost at a source brick's border =
+ * that brick's own ghost, DynamicBrickingDS::GetBrick), the levels are the file's own, target_brick_size is clamped to the
+ * source's (IOManager.cpp:1301-1305).  Scalar min / max equal DynamicBrickingDS::MaxMinForKey bit for bit.  One stated
+ * deviation: minmax_brick (BMinMax.cpp:13) stores the EMPTY gradient interval (DBL_MAX, -FLT_MAX), which hides every brick
+ * of a rebricked dataset from a 2D transfer function; the gradient interval stored here is the unbounded one, as for every
+ * other source of this library without gradient statistics. */
+int tvk_open_octree_file_rebricked(tvk_ctx* ctx, const char* path, uint64_t offset, uint64_t uvf_file_version,
+                                   const float scale[3], const uint32_t target_brick_size[3], double range_max,
+                                   float max_gradient_magnitude, tvk_octree_file_info* info);
 /* The same for a whole .uvf file: walks the container (magic, global header, data-block list; UVF.cpp:140-290,
  * GlobalHeader.cpp:39-47, DataBlock.cpp:60-72), takes the `timestep`-th TOC block as the brick source and the
  * `timestep`-th MaxMin block (if any) as the min/max table -- what UVFDataset::Open does for TOC-based files

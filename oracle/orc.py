@@ -233,6 +233,71 @@ class Octree:
                         yield (x, y, z, lod)
 
 
+class Rebricked:
+    """DynamicBrickingDS restatement (IO/DynamicBrickingDS.cpp) over a source `Octree`: the dataset a renderer sees when a
+    file converted with large bricks is opened through IOManager::LoadRebrickedDataset (IO/IOManager.cpp:1281-1320).
+    Pinned to the unmodified reference class by tests/test_rebrick.py (oracle/_ref/ref_dynbrick) and to the KATs of
+    IO/test/rebricking.h.  numpy, small cases only -- test infrastructure."""
+
+    def __init__(self, src, target_brick):
+        self.src = src
+        g = 2 * src.overlap                                             # ghost(), DynamicBrickingDS.cpp:105-111
+        if np.isscalar(target_brick):
+            target_brick = (target_brick,) * 3
+        # IOManager.cpp:1301-1305: the target is clamped to the source's brick size
+        self.max_brick = tuple(min(int(t), int(s)) for t, s in zip(target_brick, src.max_brick))
+        self.src_inner = tuple(b - g for b in src.max_brick)            # SourceMaxBrickSize, :348-355
+        self.inner = tuple(b - g for b in self.max_brick)                   # BrickSansGhost, :208-215
+        for a in range(3):                                              # Rebrick(), :1092-1105
+            if self.inner[a] <= 0 or self.src_inner[a] % self.inner[a] != 0:
+                raise ValueError("%s dimension is not an integer multiple of original brick size." % "xyz"[a])
+        self.ratio = tuple(s // t for s, t in zip(self.src_inner, self.inner))   # TargetBricksPerSource, :249-260
+        self.lod_count = src.lod_count                                  # no level below the source's, :1136-1139
+        self.ghost = g
+
+    def lod_size(self, lod):
+        return self.src.lod_size(lod)
+
+    def brick_count(self, lod):
+        # layout(): ceil in SINGLE precision, DynamicBrickingDS.cpp:113-121
+        v = self.lod_size(lod)
+        return tuple(int(np.ceil(np.float32(v[a]) / np.float32(self.inner[a]))) for a in range(3))
+
+    def total_bricks(self):
+        return sum(int(np.prod(self.brick_count(l))) for l in range(self.lod_count))
+
+    def brick_size(self, x, y, z, lod):
+        # ComputedTargetBrickSize, :414-434 (the "4 +" is the reference's literal: a ghost of 2 on either side)
+        v, bl, idx = self.lod_size(lod), self.brick_count(lod), (x, y, z)
+        out = []
+        for a in range(3):
+            extra = v[a] % self.inner[a]
+            out.append(4 + extra if (idx[a] == bl[a] - 1 and extra) else self.max_brick[a])
+        return tuple(out)
+
+    def brick(self, x, y, z, lod):
+        """CopyBrick (:495-538) of the sub-box at OffsetIntoSource (:305-335) of source brick SourceBrickIndex (:273-303)."""
+        idx = (x, y, z)
+        sb = tuple(idx[a] // self.ratio[a] for a in range(3))
+        off = tuple((idx[a] % self.ratio[a]) * self.inner[a] for a in range(3))
+        s = self.src.brick(sb[0], sb[1], sb[2], lod)
+        n = self.brick_size(x, y, z, lod)
+        return s[off[2]:off[2] + n[2], off[1]:off[1] + n[1], off[0]:off[0] + n[0]].copy()
+
+    def minmax(self, x, y, z, lod):
+        """MM_PRECOMPUTE / MM_DYNAMIC: minmax_brick (BMinMax.cpp:8-14) = extrema of every voxel GetBrick returns."""
+        b = self.brick(x, y, z, lod)
+        return float(b.min()), float(b.max())
+
+    def iter_bricks(self):
+        for lod in range(self.lod_count):
+            bc = self.brick_count(lod)
+            for z in range(bc[2]):
+                for y in range(bc[1]):
+                    for x in range(bc[0]):
+                        yield (x, y, z, lod)
+
+
 class Pool:
     """GLVolumePool bookkeeping restatement (orc_pool.cpp)."""
 

@@ -19,6 +19,9 @@ CASES = {   # name: (kind, (x, y, z), dtype code, dtype name, brick, overlap, co
     "octree_f32_none": (synth.V_SPH, (18, 14, 12), 2, "f32", 12, 2, 0, 0),
     "octree_u16_lzma": (synth.V_NOISE, (40, 30, 26), 1, "u16", 16, 2, 2, 0),          # LZMA SDK (LzmaCompression.cpp)
     "octree_u8_bzip2_morton": (synth.V_SPH, (36, 32, 28), 0, "u8", 12, 2, 4, 1),      # bzip2 (BzlibCompression.cpp)
+    # large bricks, to be re-cut on load (DynamicBrickingDS; tests/test_rebrick.py): ragged last source bricks on every axis
+    "octree_u8_b36_zlib": (synth.V_SPH, (80, 70, 50), 0, "u8", 36, 2, 1, 0),
+    "octree_u16_b28_lz4": (synth.V_NOISE, (60, 52, 30), 1, "u16", 28, 2, 3, 0),
 }
 
 

@@ -113,6 +113,7 @@ SIGNATURES = {
                                    C.c_double, C.c_float]),
     "tvk_open_octree_file": (C.c_int, [P, C.c_char_p, C.c_uint64, C.c_uint64, P, P, C.c_uint64, C.c_double, C.c_float,
                                        C.POINTER(OctreeFileInfo)]),
+    "tvk_open_octree_file_rebricked": (C.c_int, [P, C.c_char_p, C.c_uint64, C.c_uint64, P, u32x3, C.c_double, C.c_float, P]),
     "tvk_open_uvf": (C.c_int, [P, C.c_char_p, C.c_uint64, P, C.c_double, C.c_float, C.POINTER(OctreeFileInfo)]),
     "tvk_uvf_probe_stats": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_double * 2), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_float), C.POINTER(C.c_uint64 * 2)]),

@@ -465,6 +465,67 @@ __global__ void __launch_bounds__(256) proc_minmax_kernel(const ProcConsts C, ui
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// DynamicBrickingDS on the device (IO/DynamicBrickingDS.cpp): a dataset stored in LARGE bricks is re-cut
+// into the pool's small bricks when it is loaded.  A target brick (ghost included) is a sub-box of exactly ONE source
+// brick -- the target's inner size divides the source's and both carry the same ghost width (IOManager.cpp:1296-1313,
+// DynamicBrickingDS.cpp:1092-1105) -- so ghost voxels at a source brick's border come from that source brick's own
+// ghost, as in DynamicBrickingDS::GetBrick.  One CTA per target brick of the staged source brick: copy into the store
+// slot, min / max of every stored voxel (MinMaxMode MM_PRECOMPUTE: minmax_brick, BMinMax.cpp:8-14).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rebrick_kernel(const T* __restrict__ src, const RebrickConsts C, T* store, double* minmax,
+                                                      uint64_t slot_voxels) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t t[3] = {b % C.ratio[0], (b / C.ratio[0]) % C.ratio[1], b / (C.ratio[0] * C.ratio[1])};
+  uint32_t gt[3], bs[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    gt[i] = C.src_brick[i] * C.ratio[i] + t[i];
+    if (gt[i] >= C.layout[i]) return;                     // ragged source brick: fewer target bricks along this axis
+    const uint32_t core = C.brick[i] - 2 * C.overlap;
+    const uint32_t rem = C.lod_size[i] % core;
+    bs[i] = (gt[i] == C.layout[i] - 1 && rem) ? 2 * C.overlap + rem : C.brick[i];
+  }
+  const uint32_t core[3] = {C.brick[0] - 2 * C.overlap, C.brick[1] - 2 * C.overlap, C.brick[2] - 2 * C.overlap};
+  const uint64_t slot = C.first_brick + gt[0] + (uint64_t)C.layout[0] * (gt[1] + (uint64_t)C.layout[1] * gt[2]);
+  T* dst = store + slot * slot_voxels;
+  const uint32_t n = bs[0] * bs[1] * bs[2];
+  T mn = 0, mx = 0;
+  bool any = false;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t lx = i % bs[0], ly = (i / bs[0]) % bs[1], lz = i / (bs[0] * bs[1]);
+    const uint64_t si = (uint64_t)(t[0] * core[0] + lx) + (uint64_t)C.src_size[0] * ((t[1] * core[1] + ly) + (uint64_t)C.src_size[1] * (t[2] * core[2] + lz));
+    const T v = src[si];
+    dst[lx + C.brick[0] * (ly + C.brick[1] * lz)] = v;
+    if (!any) { mn = mx = v; any = true; }
+    else { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+  }
+  __shared__ T s_mn[8], s_mx[8];
+  __shared__ int s_any[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    const T omn = __shfl_down_sync(0xffffffffu, mn, o), omx = __shfl_down_sync(0xffffffffu, mx, o);
+    const int oany = __shfl_down_sync(0xffffffffu, (int)any, o);
+    if (oany) {
+      if (!any) { mn = omn; mx = omx; any = true; }
+      else { mn = omn < mn ? omn : mn; mx = omx > mx ? omx : mx; }
+    }
+  }
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; s_any[threadIdx.x >> 5] = any; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool have = false;
+    T a = 0, c = 0;
+    for (int w = 0; w < 8; w++) {
+      if (!s_any[w]) continue;
+      if (!have) { a = s_mn[w]; c = s_mx[w]; have = true; }
+      else { a = s_mn[w] < a ? s_mn[w] : a; c = s_mx[w] > c ? s_mx[w] : c; }
+    }
+    double* o = minmax + 4 * slot;
+    o[0] = (double)a; o[1] = (double)c; o[2] = -DBL_MAX; o[3] = DBL_MAX;
+  }
+}
+
 inline int grid_for(uint64_t n, int block) {
   uint64_t g = (n + block - 1) / block;
   const uint64_t cap = (uint64_t)kSMs * 16;
@@ -509,6 +570,15 @@ void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const u
     case TVK_U8: downsample_kernel<uint8_t><<<g, 256, 0, s>>>((const uint8_t*)src, ss[0], ss[1], ss[2], (uint8_t*)dst, ds[0], ds[1], ds[2]); break;
     case TVK_U16: downsample_kernel<uint16_t><<<g, 256, 0, s>>>((const uint16_t*)src, ss[0], ss[1], ss[2], (uint16_t*)dst, ds[0], ds[1], ds[2]); break;
     default: downsample_kernel<float><<<g, 256, 0, s>>>((const float*)src, ss[0], ss[1], ss[2], (float*)dst, ds[0], ds[1], ds[2]); break;
+  }
+}
+
+void launch_rebrick(const void* src, const RebrickConsts& C, void* store, double* minmax, int dtype, uint64_t slot_bytes, cudaStream_t s) {
+  const uint32_t n = C.ratio[0] * C.ratio[1] * C.ratio[2];
+  switch (dtype) {
+    case TVK_U8: rebrick_kernel<uint8_t><<<n, 256, 0, s>>>((const uint8_t*)src, C, (uint8_t*)store, minmax, slot_bytes); break;
+    case TVK_U16: rebrick_kernel<uint16_t><<<n, 256, 0, s>>>((const uint16_t*)src, C, (uint16_t*)store, minmax, slot_bytes / 2); break;
+    default: rebrick_kernel<float><<<n, 256, 0, s>>>((const float*)src, C, (float*)store, minmax, slot_bytes / 4); break;
   }
 }
 

@@ -179,6 +179,13 @@ void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, doub
 void launch_cut_bricks(const void* lod_vol, void* store, const int32_t* store_index, double* minmax, const CutConsts& cc,
                        int dtype, uint64_t slot_bytes, cudaStream_t s);
 
+// re-bricking of a staged source brick into the target bricks it holds (k_bricker.cu)
+struct RebrickConsts {
+  uint32_t lod_size[3], layout[3] /* target */, brick[3] /* target, incl. ghost */, overlap;
+  uint32_t src_size[3] /* this source brick's own size incl. ghost */, src_brick[3], src_inner[3], ratio[3];
+  uint64_t first_brick;   // first TOC index of the target level
+};
+void launch_rebrick(const void* src, const RebrickConsts& C, void* store, double* minmax, int dtype, uint64_t slot_bytes, cudaStream_t s);
 // value quantiser (k_quantize.cu)
 struct QuantParams { double f, fh; uint32_t max_out, bins; int32_t mode, out_bits; };
 int quant_blocks();   // CTAs of the range pass = (min, max) pairs it writes

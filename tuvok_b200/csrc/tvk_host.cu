@@ -2422,3 +2422,4 @@ int tvk_get_classic_brick_list(tvk_ctx* ctx, uint32_t* lod, tvk_classic_brick* d
 #include "tvk_sortlast.inc"
 #include "tvk_procedural.inc"
 #include "tvk_quantize.inc"
+#include "tvk_rebrick.inc"

@@ -166,6 +166,22 @@ class CudaGridLeaper:
         self._dirty = True
         return info
 
+    def OpenRebrickedOctreeFile(self, path, target_brick_size, offset=0, uvf_file_version=5, scale=None, range_max=0.0,
+                                max_gradient_magnitude=0.0):
+        """IOManager::LoadRebrickedDataset stand-in (IO/IOManager.cpp:1281-1320, DynamicBrickingDS with MM_PRECOMPUTE): the
+        file's large bricks are re-cut on the device into bricks of `target_brick_size` (ghost included) while it is
+        loaded; the result is a resident brick store with its min / max table."""
+        info = L.OctreeFileInfo()
+        sc = L.f32x3(*scale) if scale is not None else None
+        if np.isscalar(target_brick_size):
+            target_brick_size = (target_brick_size,) * 3
+        self._ck(self._lib.tvk_open_octree_file_rebricked(self._h, os.fsencode(path), int(offset), int(uvf_file_version),
+                                                          C.cast(sc, C.c_void_p) if sc is not None else None,
+                                                          L.u32x3(*[int(v) for v in target_brick_size]), float(range_max),
+                                                          float(max_gradient_magnitude), C.byref(info)))
+        self._dirty = True
+        return info
+
     def OpenUVF(self, path, timestep=0, scale=None, range_max=0.0, max_gradient_magnitude=0.0):
         """UVFDataset stand-in: walk the .uvf container and stream the `timestep`-th TOC block (with its MaxMin block)."""
         info = L.OctreeFileInfo()
