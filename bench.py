@@ -619,6 +619,8 @@ def run_tvk(args, rank, world, local_rank):
         st = frame(args.warmup + i)
         ms_ray += st.ms_raycast
         not_conv += 0 if st.converged else 1
+    if lib_sl:
+        r.SortLastFlush()      # overlapped exchange: the end event waits for the last frame's blend and gather as well
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -746,6 +748,15 @@ def run_tvk(args, rank, world, local_rank):
                 st = frame(v)
                 if all_min(st.converged):
                     break
+            # a frame must never be read one exchange late (overlapped exchange): render ANOTHER view, then exactly one frame
+            # of this one, and read that
+            for _ in range(64):
+                st = frame(v + 6)
+                if all_min(st.converged):
+                    break
+            st = frame(v)
+            if not all_min(st.converged):
+                raise RuntimeError("view %d pages bricks again after it had converged" % v)
             if rank == 0:
                 got = r.SortLastReadRGBA8()
                 ref = ref_frames[v]
@@ -821,6 +832,9 @@ def run_tvk(args, rank, world, local_rank):
             how = ("partial images read straight out of the peers' memory over NVLink by the n-way over kernel, RGBA8 slices stored "
                    "into rank 0's frame by the same kernel, flag words instead of collectives (no NCCL call on the frame's path)"
                    if sl_mode[0] else "direct-send RGBA32F slices in one NCCL group, n-way over kernel, RGBA8 gather on rank 0")
+            if sl_mode[0] == 2:
+                how += ("; the exchange of frame f runs on a second stream while frame f + 1 is traversed (a rank runs up to one "
+                        "frame ahead; the timed region ends after the last frame's gather)")
             par = ("sort-last x%d inside the library (tvk_sortlast_frame): %s brick blocks%s, %s" %
                    (world, split, ", brick store sharded at the source" if shard is not None else "", how))
         elif pipe is not None:

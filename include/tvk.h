@@ -507,7 +507,8 @@ typedef struct {
   float ms_frame;              /* device time of the whole frame on this rank */
   uint64_t bytes_sent;         /* image bytes this rank sent (exchange + gather) */
   uint64_t slice_lo, slice_hi; /* the pixel range this rank composited */
-  int32_t  peer_memory;        /* 1: the frame went through peer memory (no NCCL call on its path), 0: NCCL exchange */
+  int32_t  peer_memory;        /* 1: the frame went through peer memory (no NCCL call on its path), 2: the same with the
+                                  exchange overlapped with the next frame (see tvk_sortlast_flush), 0: NCCL exchange */
   float    ms_wait_peers;      /* peer-memory path: the part of ms_exchange spent waiting for the slowest rank's partial image */
 } tvk_sortlast_stats;
 /* rank 0 creates the id (ncclGetUniqueId) and hands it to the other ranks by whatever means the host has */
@@ -525,6 +526,15 @@ int tvk_sortlast_get_block_of(tvk_ctx* ctx, int which, float clip_min[3], float 
 /* collective: one subframe on every rank + compositing.  Bricks a rank missed are paged in afterwards as in tvk_render;
  * st->frame.converged is this rank's flag (the host ANDs it over the ranks when it needs a global one). */
 int tvk_sortlast_frame(tvk_ctx* ctx, tvk_sortlast_stats* st);
+/* Overlapped exchange (default on the peer-memory path with OCTANT / SCREEN; TVK_SL_OVERLAP=0 turns it off): the blend and
+ * gather of frame f run on an internal high-priority stream while the render stream already traverses frame f + 1 -- a
+ * rank runs up to one frame ahead, so waiting for the slowest rank of a view is hidden behind the next view's traversal.
+ * Results are unchanged (same kernels, same order of the fold).  Then st->peer_memory = 2, st->ms_exchange /
+ * st->ms_wait_peers describe the PREVIOUS frame's exchange (0 if it is still running) and st->ms_frame is the render
+ * stream's share of this frame (traversal + publication).  The tvk_sortlast_read_* calls order themselves behind the
+ * exchange; tvk_sortlast_flush makes the render stream (tvk_set_stream) wait for everything queued on the exchange stream
+ * -- call it before recording an event that is meant to mark "all frames so far are gathered". */
+int tvk_sortlast_flush(tvk_ctx* ctx);
 /* rank 0: the composited frame, bottom row first (GLFrameCapture.cpp:72-85); async: dst is page-locked, the copy runs
  * on the library's copy stream, tvk_read_wait as for tvk_read_rgba8_async */
 int tvk_sortlast_read_rgba8(tvk_ctx* ctx, uint8_t* dst, size_t pitch);

@@ -184,6 +184,7 @@ SIGNATURES = {
     "tvk_sortlast_get_block": (C.c_int, [P, f32x3, f32x3, P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tvk_sortlast_get_block_of": (C.c_int, [P, C.c_int, f32x3, f32x3, C.POINTER(C.c_int)]),
     "tvk_sortlast_frame": (C.c_int, [P, C.POINTER(SortLastStats)]),
+    "tvk_sortlast_flush": (C.c_int, [P]),
     "tvk_sortlast_read_rgba8": (C.c_int, [P, P, C.c_size_t]),
     "tvk_sortlast_read_rgba8_async": (C.c_int, [P, P, C.c_size_t]),
     "tvk_sortlast_read_slice": (C.c_int, [P, P]),

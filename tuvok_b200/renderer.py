@@ -808,6 +808,10 @@ class CudaGridLeaper:
         self._converged = bool(st.frame.converged)
         return st
 
+    def SortLastFlush(self):
+        """The render stream waits for everything queued on the exchange stream (overlapped exchange, tvk_sortlast_flush)."""
+        self._ck(self._lib.tvk_sortlast_flush(self._h))
+
     def SortLastReadRGBA8(self, out=None):
         w, h = self.params.width, self.params.height
         if out is None:
