@@ -40,9 +40,10 @@ struct ivec2 { int x, y; ivec2() : x(0), y(0) {} ivec2(int a, int b) : x(a), y(b
 struct uvec2 { uint x, y; uvec2() : x(0), y(0) {} uvec2(uint a, uint b) : x(a), y(b) {} };
 
 struct vec3 {
-  union { struct { float x, y, z; }; struct { float r, g, b; }; swz<vec2, float, 2> xy; swz<vec3, float, 3> xyz; };
+  union { struct { float x, y, z; }; struct { float r, g, b; }; swz<vec2, float, 2> xy; swz<vec3, float, 3> xyz; swz<vec3, float, 3> rgb; };
   vec3() : x(0), y(0), z(0) {}
   vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+  vec3(const vec2& v, float c) : x(v.x), y(v.y), z(c) {}
   explicit vec3(float a) : x(a), y(a), z(a) {}
   explicit vec3(const ivec3& v);
   explicit vec3(const uvec3& v);
@@ -205,15 +206,33 @@ inline uvec4 texelFetch(const usampler3D& s, const ivec3& p, int) {
   const uint32_t v = s.d[(size_t)p.x + (size_t)s.w * ((size_t)p.y + (size_t)s.h * (size_t)p.z)];
   return uvec4(v, 0u, 0u, 1u);
 }
-inline float pool_texel(const sampler3D& s, int x, int y, int z) {
+inline float pool_texel(const sampler3D& s, int x, int y, int z, int ch = 0) {
   x = x < 0 ? 0 : x >= s.w ? s.w - 1 : x;
   y = y < 0 ? 0 : y >= s.h ? s.h - 1 : y;
   z = z < 0 ? 0 : z >= s.z ? s.z - 1 : z;
   const size_t i = (size_t)x + (size_t)s.w * ((size_t)y + (size_t)s.h * (size_t)z);
+  if (s.dtype == 3) return (float)((const uint8_t*)s.d)[4 * i + (size_t)ch];   // GL_RGBA8 pool of a colour volume
   return s.dtype == 0 ? (float)((const uint8_t*)s.d)[i] : s.dtype == 1 ? (float)((const uint16_t*)s.d)[i] : ((const float*)s.d)[i];
+}
+// one channel of the filtered texel (the arithmetic of texture() below)
+inline float pool_filter(const sampler3D& s, const vec3& c, int ch) {
+  if (s.nearest)
+    return pool_texel(s, (int)floorf(c.x * (float)s.w), (int)floorf(c.y * (float)s.h), (int)floorf(c.z * (float)s.z), ch) * s.norm;
+  const float ux = fmaf(c.x, (float)s.w, -0.5f), uy = fmaf(c.y, (float)s.h, -0.5f), uz = fmaf(c.z, (float)s.z, -0.5f);
+  const float x0 = floorf(ux), y0 = floorf(uy), z0 = floorf(uz);
+  const float fx = ux - x0, fy = uy - y0, fz = uz - z0;
+  const int x = (int)x0, y = (int)y0, z = (int)z0;
+  const float v000 = pool_texel(s, x, y, z, ch), v100 = pool_texel(s, x + 1, y, z, ch), v010 = pool_texel(s, x, y + 1, z, ch),
+              v110 = pool_texel(s, x + 1, y + 1, z, ch), v001 = pool_texel(s, x, y, z + 1, ch), v101 = pool_texel(s, x + 1, y, z + 1, ch),
+              v011 = pool_texel(s, x, y + 1, z + 1, ch), v111 = pool_texel(s, x + 1, y + 1, z + 1, ch);
+  const float c00 = fmaf(fx, v100 - v000, v000), c10 = fmaf(fx, v110 - v010, v010);
+  const float c01 = fmaf(fx, v101 - v001, v001), c11 = fmaf(fx, v111 - v011, v011);
+  const float c0 = fmaf(fy, c10 - c00, c00), c1 = fmaf(fy, c11 - c01, c01);
+  return fmaf(fz, c1 - c0, c0) * s.norm;
 }
 // GL_LUMINANCE8/16/32F, GL_LINEAR (or GL_NEAREST), clamp-to-edge: luminance replicates to rgb, alpha = 1
 inline vec4 texture(const sampler3D& s, const vec3& c) {
+  if (s.dtype == 3) return vec4(pool_filter(s, c, 0), pool_filter(s, c, 1), pool_filter(s, c, 2), pool_filter(s, c, 3));   // GL_RGBA8
   float v;
   if (s.nearest) {
     v = pool_texel(s, (int)floorf(c.x * (float)s.w), (int)floorf(c.y * (float)s.h), (int)floorf(c.z * (float)s.z)) * s.norm;

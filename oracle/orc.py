@@ -13,12 +13,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-U8, U16, F32 = 0, 1, 2
+U8, U16, F32, RGBA8 = 0, 1, 2, 3        # RGBA8: 4 x 8 bit colour volume (render side; bricks are [z, y, x, 4] uint8)
 RM_1DTRANS, RM_2DTRANS, RM_ISOSURFACE = 0, 1, 2
 BI_MISSING, BI_CHILD_EMPTY, BI_EMPTY, BI_FLAG_COUNT = 0, 1, 2, 3
 BS_ONLY_NEEDED, BS_REQUEST_ALL, BS_SKIP_ONE, BS_SKIP_TWO = 0, 1, 2, 3
 MAX_LOD = 32
-NP_DTYPE = {U8: np.uint8, U16: np.uint16, F32: np.float32}
+NP_DTYPE = {U8: np.uint8, U16: np.uint16, F32: np.float32, RGBA8: np.dtype((np.uint8, 4))}
 DTYPE_OF = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.float32): F32}
 
 u32x3 = C.c_uint32 * 3
@@ -126,6 +126,7 @@ def lib():
         "orc_raycast": (None, [C.POINTER(RenderParams)] + [P] * 12 + [C.POINTER(RenderStats), C.c_int]),
         "orc_raycast_slots": (None, [C.POINTER(RenderParams)] + [P] * 12 + [C.POINTER(RenderStats), C.POINTER(C.c_uint64), C.c_int]),
         "orc_iso_compose": (None, [C.POINTER(RenderParams), P, P, P]),
+        "orc_iso_compose_color": (None, [C.POINTER(RenderParams), P, P, P]),
         "orc_ray_exit_eye": (None, [P, P]),
         "orc_classic_step_scale": (C.c_float, [P, C.c_uint32]),
         "orc_uniforms": (None, [P, P]),
@@ -231,6 +232,32 @@ class Octree:
                 for y in range(bc[1]):
                     for x in range(bc[0]):
                         yield (x, y, z, lod)
+
+
+class ColorOctree:
+    """A 4-component (RGBA, 8 bit) volume as four scalar conversions interleaved: the converter treats the components of a
+    voxel independently (same filter, same ghost rule), and the min / max a renderer sees for colour data is that of the
+    ALPHA component (UVFDataset::MaxMinForKey: GetValue(i, 3), uvfDataset.cpp:1144 / :1188).  Same interface as Octree;
+    bricks are [sz, sy, sx, 4].  The multi-component converter itself is not compiled against: parity of the colour BRICKS
+    with the reference converter is unpinned (the scalar conversion each channel goes through is pinned)."""
+
+    def __init__(self, rgba, max_brick, overlap, clamp=False):
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        assert rgba.ndim == 4 and rgba.shape[3] == 4, "colour volume is indexed [z, y, x, channel]"
+        self.ch = [Octree(np.ascontiguousarray(rgba[..., k]), max_brick, overlap, clamp=clamp) for k in range(4)]
+        a = self.ch[3]
+        self.dtype, self.vol, self.max_brick, self.overlap = RGBA8, a.vol, a.max_brick, a.overlap
+        self.lod_count, self.total_bricks, self.largest_single_brick_lod = a.lod_count, a.total_bricks, a.largest_single_brick_lod
+        self.minmax = a.minmax
+
+    def lod_size(self, lod): return self.ch[3].lod_size(lod)
+    def brick_count(self, lod): return self.ch[3].brick_count(lod)
+    def brick_index(self, x, y, z, lod): return self.ch[3].brick_index(x, y, z, lod)
+    def brick_size(self, x, y, z, lod): return self.ch[3].brick_size(x, y, z, lod)
+    def iter_bricks(self, max_lod=None): return self.ch[3].iter_bricks(max_lod)
+
+    def brick(self, x, y, z, lod):
+        return np.ascontiguousarray(np.stack([c.brick(x, y, z, lod) for c in self.ch], axis=-1))
 
 
 class Rebricked:
@@ -468,7 +495,10 @@ def raycast_slots(params, slots, meta, tf, ray_start, start_color, exit_, covere
 
 def iso_compose(params, hit_pos, hit_normal):
     out = np.zeros_like(hit_pos)
-    lib().orc_iso_compose(C.byref(params), _p(hit_pos), _p(hit_normal), _p(out))
+    if params.dtype == RGBA8:      # GLRenderer::ComposeSurfaceImage picks Compose-Color-FS for colour data
+        lib().orc_iso_compose_color(C.byref(params), _p(hit_pos), _p(hit_normal), _p(out))
+    else:
+        lib().orc_iso_compose(C.byref(params), _p(hit_pos), _p(hit_normal), _p(out))
     return out
 
 

@@ -167,7 +167,7 @@ static void derive(const orc_render_params* p, uni* u) {
     u->lod_layout_sz[l][0] = (uint32_t)ceilf(c[0]);
     u->lod_layout_sz[l][1] = (uint32_t)ceilf(c[0]) * (uint32_t)ceilf(c[1]);
   }
-  u->norm = p->dtype == ORC_U8 ? 1.0f / 255.0f : p->dtype == ORC_U16 ? 1.0f / 65535.0f : 1.0f;
+  u->norm = (p->dtype == ORC_U8 || p->dtype == ORC_RGBA8) ? 1.0f / 255.0f : p->dtype == ORC_U16 ? 1.0f / 65535.0f : 1.0f;
   u->oc = 1.0f / p->sample_rate_modifier;
 }
 
@@ -313,7 +313,7 @@ typedef struct {
   float sh_lo[3], sh_hi[3];  /* the shard box with faces on the volume border pushed to -/+inf */
 } ctx_t;
 
-static inline float texel(const ctx_t* c, int x, int y, int z) {
+static inline float texel_ch(const ctx_t* c, int x, int y, int z, int ch) {
   const uint32_t* ps = c->p->pool_size;
   x = x < 0 ? 0 : x >= (int)ps[0] ? (int)ps[0] - 1 : x;
   y = y < 0 ? 0 : y >= (int)ps[1] ? (int)ps[1] - 1 : y;
@@ -333,14 +333,17 @@ static inline float texel(const ctx_t* c, int x, int y, int z) {
   switch (c->p->dtype) {
     case ORC_U8: return (float)((const uint8_t*)base)[i];
     case ORC_U16: return (float)((const uint16_t*)base)[i];
+    case ORC_RGBA8: return (float)((const uint8_t*)base)[4 * i + (size_t)ch];   /* GL_RGBA8 pool of a colour volume */
     default: return ((const float*)base)[i];
   }
 }
+static inline float texel(const ctx_t* c, int x, int y, int z) { return texel_ch(c, x, y, z, 0); }
 
 /* texture(volumePool, coords + (dx,dy,dz)*sampleDelta).r -- GL_LINEAR, clamp-to-edge
  * (GLVolumePool.cpp:637-639).  sampleDelta = 1/poolSize is exactly one texel, so the offset
  * is applied to the texel index and the filter fractions of the centre are reused. */
-static float sample_pool_off(const ctx_t* c, v3 tc, int dx, int dy, int dz) {
+static float sample_pool_off_ch(const ctx_t* c, v3 tc, int dx, int dy, int dz, int ch) {
+#define texel(c_, x_, y_, z_) texel_ch(c_, x_, y_, z_, ch)
   const uni* u = c->u;
   if (c->p->nearest) {
     int x = (int)floorf(tc.x * u->pool_size_f.x), y = (int)floorf(tc.y * u->pool_size_f.y),
@@ -364,21 +367,33 @@ static float sample_pool_off(const ctx_t* c, v3 tc, int dx, int dy, int dz) {
   float c0 = fmaf(fy, c10 - c00, c00);
   float c1 = fmaf(fy, c11 - c01, c01);
   return fmaf(fz, c1 - c0, c0) * u->norm;
+#undef texel
 }
+/* samplePool = texture(volumePool, coords).r (GLVolumePool.cpp:637-639) */
+static float sample_pool_off(const ctx_t* c, v3 tc, int dx, int dy, int dz) { return sample_pool_off_ch(c, tc, dx, dy, dz, 0); }
 
 static float sample_pool(const ctx_t* c, v3 tc) { return sample_pool_off(c, tc, 0, 0, 0); }
+/* samplePool4 = texture(volumePool, coords) of a colour volume (GLVolumePool.cpp:649-651): every channel is filtered
+ * with the same fractions */
+static v4 sample_pool4(const ctx_t* c, v3 tc) {
+  v4 r = {sample_pool_off_ch(c, tc, 0, 0, 0, 0), sample_pool_off_ch(c, tc, 0, 0, 0, 1), sample_pool_off_ch(c, tc, 0, 0, 0, 2),
+          sample_pool_off_ch(c, tc, 0, 0, 0, 3)};
+  return r;
+}
 
 /* GLGridLeaper-GradientTools.glsl:6-16 (note the y taps: "Yp" is fetched at -delta) */
-static v3 gradient(const ctx_t* c, v3 ctr, v3 delta) {
+static v3 gradient_ch(const ctx_t* c, v3 ctr, v3 delta, int ch) {
   (void)delta;
-  float xp = sample_pool_off(c, ctr, +1, 0, 0);
-  float xm = sample_pool_off(c, ctr, -1, 0, 0);
-  float yp = sample_pool_off(c, ctr, 0, -1, 0);
-  float ym = sample_pool_off(c, ctr, 0, +1, 0);
-  float zp = sample_pool_off(c, ctr, 0, 0, +1);
-  float zm = sample_pool_off(c, ctr, 0, 0, -1);
+  float xp = sample_pool_off_ch(c, ctr, +1, 0, 0, ch);
+  float xm = sample_pool_off_ch(c, ctr, -1, 0, 0, ch);
+  float yp = sample_pool_off_ch(c, ctr, 0, -1, 0, ch);
+  float ym = sample_pool_off_ch(c, ctr, 0, +1, 0, ch);
+  float zp = sample_pool_off_ch(c, ctr, 0, 0, +1, ch);
+  float zm = sample_pool_off_ch(c, ctr, 0, 0, -1, ch);
   return V3((xm - xp) / 2.0f, (yp - ym) / 2.0f, (zm - zp) / 2.0f);
 }
+/* ComputeGradient: the .r channel; ComputeGradientAlpha (GradientTools.glsl:25-37): the same taps on .a */
+static v3 gradient(const ctx_t* c, v3 ctr, v3 delta) { return gradient_ch(c, ctr, delta, 0); }
 
 static v3 compute_normal(const ctx_t* c, v3 ctr, v3 delta, v3 domain_scale) {
   v3 g = gradient(c, ctr, delta);
@@ -421,6 +436,30 @@ static v4 color_from_volume(ctx_t* c, v3 pc, v3 model_pos, v3 delta) {
   const orc_render_params* p = c->p;
   const uni* u = c->u;
   c->samples++;
+  if (p->dtype == ORC_RGBA8) {
+    /* GLGridLeaper-Method-{1D,1D-L,2D,2D-L}-color.glsl: the volume's own colour, the transfer function only maps alpha.
+     * 1D-L takes its normal from ComputeNormal (the .r channel), the 2D methods their gradient from ComputeGradientAlpha. */
+    v4 data = sample_pool4(c, pc);
+    if (p->mode == ORC_RM_1DTRANS) {
+      data.w = tf_lookup(c, data.w * p->trans_scale, 0.0f).w;
+      if (!p->lighting) return data;
+      v3 n = compute_normal(c, pc, delta, u->domain_scale);
+      v3 lit = lighting(u->eye_m, model_pos, n, u->light_a, mul3(V3(data.x, data.y, data.z), u->light_d), u->light_s,
+                        u->light_dir_m);
+      data.x = lit.x; data.y = lit.y; data.z = lit.z;
+      return data;
+    }
+    v3 g = gradient_ch(c, pc, delta, 3);
+    float gm = len3(g);
+    data.w = tf_lookup(c, data.w * p->trans_scale, 1.0f - gm * p->gradient_scale).w;
+    if (!p->lighting) return data;
+    v3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
+    v3 n = mul3(u->domain_scale, gn);
+    v3 lit = lighting(u->eye_m, model_pos, n, u->light_a, mul3(V3(data.x, data.y, data.z), u->light_d), u->light_s,
+                      u->light_dir_m);
+    data.x = lit.x; data.y = lit.y; data.z = lit.z;
+    return data;
+  }
   float data = sample_pool(c, pc);
   v4 col;
   if (p->mode == ORC_RM_1DTRANS) {
@@ -711,24 +750,29 @@ static void trace_pixel(ctx_t* c, const float* ray_start, const float* start_col
               if (acc.w > 0.99f) { terminated = 1; break; }
             } else {
               c->samples++;
-              if (sample_pool(c, pc) >= p->isoval) {
+              /* GetVolumeHit: scalar volumes test .r and report white; colour volumes (GLGridLeaper-Method-iso-color.glsl)
+               * test .a and report the sampled colour; RefineIsosurface bisects on the same channel */
+              const int colour = p->dtype == ORC_RGBA8, ich = colour ? 3 : 0;
+              v4 hcol = {1.0f, 1.0f, 1.0f, 1.0f};
+              if (colour) hcol = sample_pool4(c, pc);
+              if ((colour ? hcol.w : sample_pool(c, pc)) >= p->isoval) {
                 /* RefineIsosurface */
                 v3 rd = V3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
                 pc = sub3(pc, rd);
                 for (int k = 0; k < 5; k++) {
                   rd = V3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
-                  if (sample_pool(c, pc) >= p->isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
+                  if (sample_pool_off_ch(c, pc, 0, 0, 0, ich) >= p->isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
                 }
                 cur = mul3(sub3(pc, b.trans), inv_scale);
                 hit_pos = xform4(u->model_to_eye, cur.x, cur.y, cur.z, 1.0f);
-                hit_pos.w = 1.0f + 1.0f;                 /* color.r + 1 */
+                hit_pos.w = hcol.x + 1.0f;               /* color.r + 1 */
                 v3 n = compute_normal(c, pc, delta, u->domain_scale);
                 /* mModelViewIT * vec4(n,0): column-vector product with inverse(modelView) */
                 const float* m = u->mv_inv;
                 hit_nrm.x = m[0] * n.x + m[1] * n.y + m[2] * n.z;
                 hit_nrm.y = m[4] * n.x + m[5] * n.y + m[6] * n.z;
                 hit_nrm.z = m[8] * n.x + m[9] * n.y + m[10] * n.z;
-                hit_nrm.w = floorf(1.0f * 512.0f) + 1.0f;  /* floor(color.g*512)+color.b */
+                hit_nrm.w = floorf(hcol.y * 512.0f) + hcol.z;  /* floor(color.g*512)+color.b */
                 terminated = 1;
                 break;
               } else {
@@ -850,6 +894,36 @@ void orc_iso_compose(const orc_render_params* p, const float* hit_pos, const flo
     float* o = rgba + 4 * i;
     o[0] = o[1] = o[2] = o[3] = 0.0f;
     if (hp[3] == 0.0f) continue;
+    v3 nrm = V3(hit_normal[4 * i], hit_normal[4 * i + 1], fabsf(hit_normal[4 * i + 2]));
+    v3 view = norm3(V3(0.0f - hp[0], 0.0f - hp[1], 0.0f - hp[2]));
+    float dn = dot3(nrm, view);
+    v3 refl = norm3(sub3(view, scl3(nrm, 2.0f * dn)));
+    float dl = fmaxf(fabsf(dot3(nrm, V3(-l.x, -l.y, -l.z))), 0.0f);
+    float sp = pow8(fmaxf(dot3(refl, l), 0.0f));
+    o[0] = clampf(a.x + d.x * dl + s.x * sp, 0.0f, 1.0f);
+    o[1] = clampf(a.y + d.y * dl + s.y * sp, 0.0f, 1.0f);
+    o[2] = clampf(a.z + d.z * dl + s.z * sp, 0.0f, 1.0f);
+    o[3] = 1.0f;
+  }
+}
+
+/* Compose-Color-FS.glsl:60-92 (colour volumes): as Compose-FS, but the diffuse colour is the hit's own colour, recovered from
+ * the two alpha channels -- r = pos.a - 1, g = floor(nrm.a / 2) / 256, b = fract(nrm.a) -- times vLightDiffuse (which
+ * GLRenderer sets WITHOUT the isosurface colour for colour data, GLRenderer.cpp:2796-2810) */
+void orc_iso_compose_color(const orc_render_params* p, const float* hit_pos, const float* hit_normal, float* rgba) {
+  size_t n = (size_t)p->width * p->height;
+  v3 a = V3(p->ambient[0] * p->ambient[3], p->ambient[1] * p->ambient[3], p->ambient[2] * p->ambient[3]);
+  v3 d0 = V3(p->diffuse[0] * p->diffuse[3], p->diffuse[1] * p->diffuse[3], p->diffuse[2] * p->diffuse[3]);
+  v3 s = V3(p->specular[0] * p->specular[3], p->specular[1] * p->specular[3], p->specular[2] * p->specular[3]);
+  v3 l = V3(p->light_dir[0], p->light_dir[1], p->light_dir[2]);
+  for (size_t i = 0; i < n; i++) {
+    const float* hp = hit_pos + 4 * i;
+    float* o = rgba + 4 * i;
+    o[0] = o[1] = o[2] = o[3] = 0.0f;
+    if (hp[3] == 0.0f) continue;
+    const float na = hit_normal[4 * i + 3];
+    v3 col = V3(hp[3] - 1.0f, floorf(na / 2.0f) / 256.0f, na - floorf(na));
+    v3 d = mul3(col, d0);
     v3 nrm = V3(hit_normal[4 * i], hit_normal[4 * i + 1], fabsf(hit_normal[4 * i + 2]));
     v3 view = norm3(V3(0.0f - hp[0], 0.0f - hp[1], 0.0f - hp[2]));
     float dn = dot3(nrm, view);

@@ -166,11 +166,14 @@ static void set_tf_height(sampler2D& s, uint32_t h) { s.h = (int)h; }
 """
 
 
-def build(tmp, mode, lighting, pool_glsl, hash_glsl):
-    """Translation unit = emulation header + rewritten reference shader text + driver; returns the executable."""
+def build(tmp, mode, lighting, pool_glsl, hash_glsl, color=False):
+    """Translation unit = emulation header + rewritten reference shader text + driver; returns the executable.
+    color: the GLGridLeaper-Method-*-color.glsl variants GLGridLeaper picks for 4-component data (GLGridLeaper.cpp:766-795)."""
     parts = [PRELUDE, rewrite(hash_glsl), rewrite(pool_glsl)]
-    names = ["Compositing.glsl", "lighting.glsl", "GLGridLeaper-GradientTools.glsl", METHOD[(mode, bool(lighting))],
-             "GLGridLeaper-blend.glsl"]
+    method = METHOD[(mode, bool(lighting))]
+    if color:
+        method = method.replace(".glsl", "-color.glsl")
+    names = ["Compositing.glsl", "lighting.glsl", "GLGridLeaper-GradientTools.glsl", method, "GLGridLeaper-blend.glsl"]
     for n in names:
         parts.append("// ---- %s (read from the reference tree, syntactic rewrite only)\n" % n + rewrite(read_shader(n)))
     tf_type = "sampler2D" if mode == 1 else "sampler1D"
@@ -311,10 +314,11 @@ def _compile(tmp, name, source):
     return exe
 
 
-def build_iso(tmp, pool_glsl, hash_glsl):
-    """GLGridLeaper-iso.glsl + Method-iso + GradientTools (+ generated pool / hash fragments) as one executable."""
+def build_iso(tmp, pool_glsl, hash_glsl, color=False):
+    """GLGridLeaper-iso.glsl + Method-iso(-color) + GradientTools (+ generated pool / hash fragments) as one executable."""
     parts = [PRELUDE, rewrite(hash_glsl), rewrite(pool_glsl)]
-    for n in ("Compositing.glsl", "GLGridLeaper-GradientTools.glsl", "GLGridLeaper-Method-iso.glsl", "GLGridLeaper-iso.glsl"):
+    for n in ("Compositing.glsl", "GLGridLeaper-GradientTools.glsl",
+              "GLGridLeaper-Method-iso-color.glsl" if color else "GLGridLeaper-Method-iso.glsl", "GLGridLeaper-iso.glsl"):
         parts.append("// ---- %s\n" % n + rewrite(read_shader(n)))
     return _compile(tmp, "iso_as_cpp", "\n".join(parts) + ISO_DRIVER)
 
@@ -343,10 +347,12 @@ def run_iso(exe, tmp, params, u, exit_eye, ray_start, start_normal, covered, met
     return [img[i].copy() for i in range(4)], hsh.copy()
 
 
-def build_compose(tmp):
-    """Compose-FS.glsl (deferred isosurface lighting, compatibility profile: texture2D, gl_FragColor, discard)."""
+def build_compose(tmp, color=False):
+    """Compose-FS.glsl / Compose-Color-FS.glsl (deferred isosurface lighting, compatibility profile: texture2D, gl_FragColor,
+    discard)."""
     pre = PRELUDE + "#define discard { g_discarded = true; return; }\nextern vec4 gl_FragCoord, gl_FragColor; extern float gl_FragDepth; extern bool g_discarded;\n"
-    return _compile(tmp, "compose_as_cpp", pre + rewrite(read_shader("Compose-FS.glsl"), "compose_main") + COMPOSE_DRIVER)
+    name = "Compose-Color-FS.glsl" if color else "Compose-FS.glsl"
+    return _compile(tmp, "compose_as_cpp", pre + rewrite(read_shader(name), "compose_main") + COMPOSE_DRIVER)
 
 
 def run_compose(exe, tmp, w, h, ambient, diffuse, specular, light_dir, hit_pos, hit_normal):

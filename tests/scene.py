@@ -155,11 +155,11 @@ class Scene:
         p.meta_dim = orc.u32x3(*pool.meta_dim)
         p.mode, p.lighting = self.mode, int(self.lighting)
         p.sample_rate_modifier = self.sample_rate
-        full = {orc.U8: 255.0, orc.U16: 65535.0, orc.F32: 1.0}[self.dtype]
+        full = {orc.U8: 255.0, orc.U16: 65535.0, orc.F32: 1.0, orc.RGBA8: 255.0}[self.dtype]
         p.trans_scale = F(full / self.range_max)
         p.gradient_scale = F(1.0) if self.max_grad == 0 else F(1.0) / F(self.max_grad)
         p.isoval = {orc.U8: F(self.isovalue / 256.0), orc.U16: F(self.isovalue / 65536.0),
-                    orc.F32: F(self.isovalue)}[self.dtype]
+                    orc.F32: F(self.isovalue), orc.RGBA8: F(self.isovalue / 256.0)}[self.dtype]
         p.ambient = orc.f32x4(1, 1, 1, 0.1)
         p.diffuse = orc.f32x4(1, 1, 1, 1)
         p.specular = orc.f32x4(1, 1, 1, 1)
@@ -400,6 +400,36 @@ class Scene:
             r.EnableClipPlane()
         r.CreateVolumePool(self._pool_size)
         return r
+
+
+class ColorScene(Scene):
+    """A 4-component (RGBA8) volume on the GridLeaper path (GLGridLeaper-Method-*-color.glsl, Compose-Color-FS.glsl): the
+    alpha channel is the scene's synthetic field, the colour channels are three other seeded fields.  Bricks, pool and page
+    table work as for scalar data with 4 bytes per voxel; visibility uses the alpha channel's min / max."""
+
+    def __init__(self, **kw):
+        kw["dtype"] = orc.U8
+        super().__init__(**kw)
+        self.dtype = orc.RGBA8
+        a = self.volume
+        chans = [synth.synth_volume(synth.V_NOISE, self.size, orc.U8, self.seed + 11 * (k + 1)) for k in range(3)]
+        self.volume = np.ascontiguousarray(np.stack(chans + [a], axis=-1))
+        self._oct = None
+
+    @property
+    def octree(self):
+        if self._oct is None:
+            self._oct = orc.ColorOctree(self.volume, self.brick, self.overlap, clamp=self.clamp)
+        return self._oct
+
+    def pool_size(self):
+        if self._pool_size is not None:
+            return tuple(self._pool_size)
+        return orc.pool_size(self.max_gpu_mem, 8, 4, self.brick, self.octree.total_bricks)
+
+    def make_renderer(self, source="callback", device=0):
+        assert source == "callback", "colour volumes come from a registered dataset (Dataset::GetBrick stand-in)"
+        return super().make_renderer("callback", device)
 
 
 def image_diff(a8, b8):

@@ -1,0 +1,176 @@
+"""Colour (RGBA, 4 x 8 bit) volumes on the GridLeaper path: GLGridLeaper-Method-{1D,1D-L,2D,2D-L,iso}-
+color.glsl (the volume's own colour, the transfer function maps alpha only; ComputeGradientAlpha; the 1D-L / iso normals
+from the .r channel as the shader text has it) and Compose-Color-FS.glsl (hit colour packed into the two alpha channels).
+
+  * CPU: the oracle's restatement (orc_render.c, dtype ORC_RGBA8) against the reference's OWN shader text executed through
+    oracle/glsl/glsl_emu.h -- the colour method files linked with the unmodified blend / iso main shaders and the GLSL the
+    unmodified GLVolumePool / GLHashTable generate,
+  * (-m gpu) the CUDA colour kernel (csrc/k_color.cu) against the oracle: float images, resume buffers, miss lists and
+    page tables bit-identical in all five modes."""
+import numpy as np
+import pytest
+
+import glsl_ref
+import tuvok_b200 as tb
+from oracle import orc
+from scene import ColorScene, image_diff
+from tuvok_b200 import synth
+
+ROT = (tb.rotation_y(30.0) @ tb.rotation_x(20.0)).astype(np.float32)
+MODES = [(orc.RM_1DTRANS, False), (orc.RM_1DTRANS, True), (orc.RM_2DTRANS, False), (orc.RM_2DTRANS, True)]
+
+
+def scene(mode, lighting, **kw):
+    args = dict(kind=synth.V_SPH, size=(48, 40, 36), brick=16, overlap=2, mode=mode, lighting=lighting, width=64, height=48,
+                rotation=ROT, isovalue=90, tf_center=0.3, tf_inv_gradient=0.35)
+    args.update(kw)
+    return ColorScene(**args)
+
+
+def test_colour_octree_is_four_scalar_conversions():
+    s = scene(orc.RM_1DTRANS, False)
+    o = s.octree
+    a = orc.Octree(np.ascontiguousarray(s.volume[..., 3]), s.brick, s.overlap)
+    assert np.array_equal(o.minmax, a.minmax)                      # visibility sees the alpha channel (uvfDataset.cpp:1144)
+    b = o.brick(1, 0, 1, 0)
+    assert b.shape[3] == 4 and np.array_equal(b[..., 3], a.brick(1, 0, 1, 0))
+    assert np.array_equal(b[2:-2, 2:-2, 2:-2, 0], s.volume[12:24, 0:12, 12:24, 0])     # inner voxels of brick (1, 0, 1)
+
+
+needs_glsl = pytest.mark.skipif(not glsl_ref.available(), reason="reference shaders / oracle/_ref tools absent")
+
+
+def _generated(tmp_path, s, pool, p):
+    o = s.octree
+    # the page-table walk / hash GLSL depends on the pool geometry only; the alpha channel's octree stands in for the data
+    return glsl_ref.generated_glsl(tmp_path, o.ch[3], s.size, s.brick[0], s.overlap, orc.U8, pool.pool_size, s.strategy,
+                                   o.brick_count(0), p.hash_size, p.rehash_count)
+
+
+@needs_glsl
+@pytest.mark.parametrize("mode,lighting", MODES)
+def test_colour_methods_match_executed_reference_shaders(tmp_path, mode, lighting):
+    s = scene(mode, lighting)
+    st = s.oracle_render()
+    p, pool = st["params"], st["pool"]
+    zeros = np.zeros_like(st["entry"])
+    hash_o = np.zeros(p.hash_size, np.uint32)
+    outs, _ = orc.raycast(p, st["atlas"], st["meta"], st["tf"], st["entry"], zeros, st["exit"], st["covered"], hash_o, 1)
+    pool_glsl, hash_glsl = _generated(tmp_path, s, pool, p)
+    exe = glsl_ref.build(tmp_path, s.mode, s.lighting, pool_glsl, hash_glsl, color=True)
+    u = orc.uniforms(p)
+    g0, g1, g2, hash_g = glsl_ref.run(exe, tmp_path, p, u["emm"], orc.ray_exit_eye(p), st["entry"], zeros, st["covered"],
+                                      st["meta"], pool.meta_dim, st["atlas"], st["tf"], u["norm"], u, u["domain_scale"])
+    # the pool of the converged frame holds every brick its RESUMED rays asked for; a fresh pass from the entry points (this
+    # one) can end a ray a sample later (resume arithmetic / unfused compositing update) and ask for one brick more
+    assert np.count_nonzero(hash_o) <= 2 and np.count_nonzero(hash_g) <= 2
+    a, b = outs[0].reshape(-1, 4), g0
+    assert a[:, 3].max() > 0.5 and (a[:, :3].max(axis=0) > 0.05).all()          # something coloured is on screen
+    d = np.abs(a - b).max(axis=1)
+    # rounding-level agreement; a pixel whose early termination trips one sample apart differs by that sample (as for scalar
+    # volumes, tests/test_glsl_ref.py)
+    assert float(d.max()) <= 4e-3 and float((d > 5e-5).mean()) <= 0.01, (float(d.max()), float((d > 5e-5).mean()))
+    mx, psnr = image_diff(orc.rgba8(a.reshape(s.height, s.width, 4)), orc.rgba8(b.reshape(s.height, s.width, 4)))
+    assert mx <= 1 and psnr >= 60.0
+    assert int((outs[2].reshape(-1, 4)[:, 3] != g2[:, 3]).sum()) <= 2          # resume depth: all but those one or two rays
+
+
+@needs_glsl
+def test_colour_first_pass_reports_the_same_missing_bricks(tmp_path):
+    s = scene(orc.RM_2DTRANS, True)
+    pool, _ = s.oracle_pool()
+    p = s.oracle_params(pool)
+    atlas = np.zeros((pool.pool_size[2], pool.pool_size[1], pool.pool_size[0]), orc.NP_DTYPE[orc.RGBA8])
+    o = s.octree
+    b = o.brick(0, 0, 0, pool.lod_count - 1)
+    cap = pool.capacity
+    z0, y0, x0 = (cap[2] - 1) * s.brick[2], (cap[1] - 1) * s.brick[1], (cap[0] - 1) * s.brick[0]
+    atlas[z0:z0 + b.shape[0], y0:y0 + b.shape[1], x0:x0 + b.shape[2]] = b
+    entry, exit_, cov = orc.ray_setup(p)
+    zeros = np.zeros_like(entry)
+    hash_o = np.zeros(p.hash_size, np.uint32)
+    outs, _ = orc.raycast(p, atlas, pool.meta, s.tf_bytes(), entry, zeros, exit_, cov, hash_o, 1)
+    pool_glsl, hash_glsl = _generated(tmp_path, s, pool, p)
+    exe = glsl_ref.build(tmp_path, s.mode, s.lighting, pool_glsl, hash_glsl, color=True)
+    u = orc.uniforms(p)
+    g0, g1, g2, hash_g = glsl_ref.run(exe, tmp_path, p, u["emm"], orc.ray_exit_eye(p), entry, zeros, cov, pool.meta,
+                                      pool.meta_dim, atlas, s.tf_bytes(), u["norm"], u, u["domain_scale"])
+    assert hash_o.any() and np.array_equal(np.sort(hash_o), np.sort(hash_g))      # the same bricks are requested
+    assert float(np.abs(outs[0].reshape(-1, 4) - g0).max()) <= 4e-3
+    assert np.array_equal(outs[2].reshape(-1, 4)[:, 3] == 1000.0, g2[:, 3] == 1000.0)
+
+
+@needs_glsl
+def test_colour_isosurface_and_compose_match_executed_reference_shaders(tmp_path):
+    s = scene(orc.RM_ISOSURFACE, False)
+    st = s.oracle_render()
+    p, pool = st["params"], st["pool"]
+    zeros = np.zeros_like(st["entry"])
+    outs, _ = orc.raycast(p, st["atlas"], st["meta"], st["tf"], st["entry"], zeros, st["exit"], st["covered"], None, 1)
+    pool_glsl, hash_glsl = _generated(tmp_path, s, pool, p)
+    exe = glsl_ref.build_iso(tmp_path, pool_glsl, hash_glsl, color=True)
+    u = orc.uniforms(p)
+    g, hash_g = glsl_ref.run_iso(exe, tmp_path, p, u, orc.ray_exit_eye(p), st["entry"], zeros, st["covered"], st["meta"],
+                                 pool.meta_dim, st["atlas"])
+    assert not hash_g.any()
+    hit_o, nrm_o = outs[0].reshape(-1, 4), outs[1].reshape(-1, 4)
+    assert np.array_equal(hit_o[:, 3] != 0, g[0][:, 3] != 0) and (hit_o[:, 3] != 0).sum() > 200
+    assert float(np.abs(hit_o[:, :3] - g[0][:, :3]).max()) <= 2e-5
+    assert float(np.abs(nrm_o[:, :3] - g[1][:, :3]).max()) <= 2e-4
+    # the colour packed into the two alpha channels: r + 1, floor(g * 512) + b
+    assert float(np.abs(hit_o[:, 3] - g[0][:, 3]).max()) <= 1e-5
+    hit = hit_o[:, 3] != 0
+    assert (np.floor(nrm_o[hit, 3]) == np.floor(g[1][hit, 3])).mean() > 0.995 and (hit_o[hit, 3] > 1.0).any()
+    assert np.array_equal(outs[2].reshape(-1, 4)[:, 3] == 1000.0, g[2][:, 3] == 1000.0)
+    # Compose-Color-FS on the SAME buffers (the oracle's), executed vs restated
+    cexe = glsl_ref.build_compose(tmp_path, color=True)
+    amb = [p.ambient[i] * p.ambient[3] for i in range(3)]
+    dif = [p.diffuse[i] * p.diffuse[3] for i in range(3)]             # no isosurface colour for colour data
+    spe = [p.specular[i] * p.specular[3] for i in range(3)]
+    img_g = glsl_ref.run_compose(cexe, tmp_path, s.width, s.height, amb, dif, spe, list(p.light_dir), outs[0], outs[1])
+    img_o = orc.iso_compose(p, outs[0], outs[1]).reshape(-1, 4)
+    assert float(np.abs(img_o - img_g).max()) <= 2e-4
+    assert img_o[:, :3].std(axis=0).min() > 0.01                      # the surface carries the volume's colours
+
+
+# ---------------------------------------------------------------------------------------------- the CUDA path
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,lighting", MODES + [(orc.RM_ISOSURFACE, False)])
+def test_cuda_colour_frames_are_bit_identical_to_the_oracle(mode, lighting):
+    s = scene(mode, lighting)
+    want = s.oracle_render()
+    r = s.make_renderer()
+    st = r.PaintUntilConverged()
+    assert st.converged
+    got = r.ReadRGBA32F()
+    assert np.array_equal(got, want["image"])
+    assert np.array_equal(r.ReadRGBA8(), want["rgba8"])
+    assert np.array_equal(r.page_table(), want["meta"])
+    r.Cleanup()
+
+
+@pytest.mark.gpu
+def test_cuda_colour_miss_lists_per_subframe_equal_the_oracle():
+    s = scene(orc.RM_2DTRANS, True, size=(64, 48, 40))
+    want = s.oracle_render()
+    r = s.make_renderer()
+    reqs = []
+    for _ in range(64):
+        st = r.Paint()
+        reqs.append(r.missing_list())
+        if st.converged:
+            break
+    assert len(reqs) == want["subframes"]
+    for a, b in zip(reqs, want["requests"]):
+        assert np.array_equal(np.asarray(a).reshape(-1, 4), np.asarray(b).reshape(-1, 4))
+    assert np.array_equal(r.ReadRGBA32F(), want["image"])
+    r.Cleanup()
+
+
+@pytest.mark.gpu
+def test_colour_volumes_are_refused_where_they_are_not_built():
+    s = scene(orc.RM_1DTRANS, False)
+    r = s.make_renderer()
+    with pytest.raises(tb.TvkError):
+        r.PaintPerBrick()              # the classic GLRaycaster path (GLRaycaster-Color-FS.glsl) is not built
+    r.Cleanup()

@@ -524,6 +524,425 @@ __device__ __forceinline__ void unpark(ChainSt& c, float (*m)[kThreads], int tid
 // exactly the inputs of a resumed GridLeaper subframe), is marched through the slab, and leaves with its resume
 // position at the slab's far side -- or finished (w = 1000) if it terminated early or left the volume.  Early ray
 // termination therefore works across ranks as on one GPU.
+// TVK_PERSIST (persistent warps that hand the pixels of a tile queue to their idle lanes) was built and MEASURED SLOWER on
+// B200 / C3 (profiles/r2x_persist_ab.txt): non-persistent 304 fps; persistent, a tile only when the whole warp is idle
+// (TVK_REFILL=32) 293 fps; refill as soon as 8 / 16 / 24 lanes are idle 178 / 185 / 180 fps -- images bit-identical in every
+// variant (208 GPU tests).  Lanes that start rays at different times need their brick-chain phases at different turns, and
+// the chain phase (page-table walk) runs for the whole warp whenever ONE lane needs it: refilling trades idle lanes for
+// many more, thinner chain phases.  Kept as a build switch, off by default.
+#ifndef TVK_PERSIST
+#define TVK_PERSIST 0
+#endif
+#ifndef TVK_REFILL
+#define TVK_REFILL 8
+#endif
+constexpr int kRefill = TVK_REFILL;
+constexpr int kSMs = 148;
+#if TVK_PERSIST
+// Persistent warps with lane refill (TVK_PERSIST=1, see the measurement above): the launch is one CTA slot per SM x resident CTAs, and a warp
+// does not own one 8x4 tile: it draws tiles from a global counter (the old dispatch order: 2x2 tile groups, centre-out)
+// and gives the pixels of the open tile to its IDLE lanes -- a lane whose ray has terminated (early ray termination,
+// left the volume) starts the next pixel while its neighbours are still marching, instead of idling until the slowest ray
+// of the tile is done (ncu before: 24.4 of 32 lanes active per issued instruction).  Rays, their arithmetic and their
+// outputs are unchanged: only WHICH lane traces WHICH pixel WHEN differs.  A warp interrupts its live rays for a refill
+// only when kRefill lanes are idle (the set-up runs with the idle lanes only).
+template <typename T, int MODE, bool LIT, bool FAST, int BS, bool COUNT, bool PIPE = false>
+__global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) raycast_kernel(const __grid_constant__ RayConsts P) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  constexpr bool ISO = MODE == 2;
+  typedef typename PairOf<T>::W W;           // pool element: the x-pair (voxel x, voxel x+1)
+  const W* pool = (const W*)P.pool;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  __shared__ float park[kPark ? kChainWords : 1][kThreads];
+  __shared__ float seg_f[9][kThreads];       // next segment: pool entry, trans, 1/scale
+  __shared__ uint32_t seg_u[COUNT ? 7 : 6][kThreads];    // slot origin (3), slot index, steps, flags (, page-table index)
+  // tile queue: 2x2 groups of 8x4 tiles, groups in the centre-out order of the non-persistent launch
+  const uint32_t gx = (P.width + 15u) / 16u, gy = (P.height + 7u) / 8u, n_tiles = gx * gy * 4u;
+  uint32_t open_tile = 0u, open_mask = 0u;   // warp-uniform: the tile being handed out, its pixels not yet taken
+  bool more = true;                          // warp-uniform: the global queue has not run dry
+  // ---- state of the lane's current ray
+  size_t pix = 0;
+  bool have_ray = false;           // a ray has been started and its outputs are not written yet
+  bool done = false;
+  unsigned long long n_samples = 0, n_bricks = 0;
+  unsigned long long n_alive_iters = 0, n_warp_iters = 0;   // lane-utilisation diagnostics (count mode)
+  ChainSt c;
+  f4 acc = from4(zero4);
+  f4& resume_col = c.resume_col;
+  f4& resume_pos = c.resume_pos;
+  f4 hit_pos = from4(zero4), hit_nrm = from4(zero4), resume_nrm = from4(zero4);
+  bool handoff = false;            // PIPE: the ray left this stage's slab alive
+  f4 hand_pos = from4(zero4);
+  f3 vdir = F3(0.f, 0.f, 0.f);
+  const float voxel_size = 0.125f / 2000.0f;
+  const f3 dscale = F3(P.domain_scale), eye_m = F3(P.eye_m), la = F3(P.light_a), ld = F3(P.light_d),
+           ls = F3(P.light_s), ldir = F3(P.light_dir_m);
+  bool ray_live = false;                  // the ray has not terminated (ERT / iso hit)
+  bool chain = false;                     // the brick chain has not reached the end of the ray
+  bool have_next = false;                 // a prefetched segment waits in shared memory
+  int steps_left = 0;      // samples left in the current brick
+  bool b_partial = false;  // sort-last: the current brick straddles the shard box (ownership per sample)
+  f3 pc = F3(0.f, 0.f, 0.f), b_trans = pc, b_inv = pc;
+  uint32_t b_ox = 0, b_oy = 0, b_oz = 0;
+  const W* vox = pool;
+  constexpr bool GRAD = !ISO && (MODE == 1 || LIT);   // what a sample needs: the 7-tap footprint or the centre tap
+  Foot<T, FAST, BS, GRAD> cur;   // footprint of the sample at pc, fetched one turn ahead
+  bool cur_ok = false;
+  unsigned long long pend = 0;   // COUNT: brick visits of the chain that the sampling has not reached yet
+
+  for (;;) {
+    // ---- refill: finished rays are written out, idle lanes take the next pixels
+    const unsigned full = 0xffffffffu;
+    const unsigned idle_m = __ballot_sync(full, !ray_live);
+    if (idle_m == full || ((more || open_mask != 0u) && __popc(idle_m) >= kRefill)) {
+      if (!ray_live && have_ray) {
+        have_ray = false;
+        if (!done) {
+          if (kPark) unpark_result(c, park, tid);
+          // TerminateRay
+          if (!ISO) {
+            if (c.optimal) {
+              // ray_live is false only after early termination; a ray that ran out of bricks in this slab is handed on
+              if (PIPE && handoff && !(acc.w > 0.99f)) { resume_pos = hand_pos; resume_col = acc; }
+              else { resume_pos.w = 1000.0f; resume_col = acc; }
+            }
+          } else {
+            if (c.optimal) resume_pos.w = hit_pos.w == 0.0f ? 1000.0f : 499.0f + hit_pos.w;
+            resume_nrm = hit_nrm;
+          }
+        }
+        if (!ISO) {
+          P.out0[pix] = to4(acc); P.out1[pix] = to4(resume_col); P.out2[pix] = to4(resume_pos);
+        } else {
+          P.out0[pix] = to4(hit_pos); P.out1[pix] = to4(hit_nrm); P.out2[pix] = to4(resume_pos);
+          P.out3[pix] = to4(resume_nrm);
+        }
+        if (COUNT) {
+          atomicAdd(P.counters + 0, n_samples); atomicAdd(P.counters + 1, 1ull); atomicAdd(P.counters + 2, n_bricks);
+          atomicAdd(P.counters + 3, n_alive_iters); atomicAdd(P.counters + 4, n_warp_iters);
+          atomicMax(P.counters + 5, n_alive_iters);
+        }
+      }
+      // the r-th waiting lane takes the r-th open pixel of the tile
+      unsigned want = idle_m;
+      bool got = false;
+      uint32_t px = 0, py = 0;
+      while (want != 0u) {
+        if (open_mask == 0u) {
+          if (!more) break;
+          uint32_t t = 0;
+          if (lane == 0) t = atomicAdd(P.tile_counter, 1u);
+          t = __shfl_sync(full, t, 0);
+          if (t >= n_tiles) { more = false; break; }
+          open_tile = t; open_mask = full;
+        }
+        const int n_take = min(__popc(open_mask), __popc(want));
+        const int r = __popc(want & ((1u << lane) - 1u));
+        const bool take = ((want >> lane) & 1u) != 0u && r < n_take;
+        uint32_t bit = 0;
+        if (take) {
+          bit = __fns(open_mask, 0, r + 1);
+          const uint32_t g = open_tile >> 2, sub = open_tile & 3u;
+          const uint32_t sx = g % gx, sy = g / gx;
+          const uint32_t tx = (kCentreOut ? centre_out(sx, gx) : sx) * 2u + (sub & 1u);
+          const uint32_t ty = (kCentreOut ? centre_out(sy, gy) : sy) * 2u + (sub >> 1);
+          px = tx * 8u + (bit & 7u); py = ty * 4u + (bit >> 3);
+          got = true;
+        }
+        open_mask &= ~__reduce_or_sync(full, take ? (1u << bit) : 0u);
+        want &= ~__ballot_sync(full, take);
+      }
+      if (got && px < P.width && py < P.height) {
+        pix = (size_t)py * P.width + px;
+        f4 entry4, exit4;
+        const bool covered = ray_setup(P, px, py, entry4, exit4, !PIPE);   // a stage takes every ray that meets the VOLUME
+        if (!covered) {   // render targets are cleared where no back face is rasterised (GLGridLeaper.cpp:837)
+          P.out0[pix] = zero4; P.out1[pix] = zero4; P.out2[pix] = PIPE ? make_float4(0.f, 0.f, 0.f, 1000.0f) : zero4;
+          if (ISO) P.out3[pix] = zero4;
+        } else {
+          have_ray = true; done = false; handoff = false;
+          hand_pos = from4(zero4); hit_pos = from4(zero4); hit_nrm = from4(zero4); resume_nrm = from4(zero4);
+          n_samples = 0; n_bricks = 0; n_alive_iters = 0; n_warp_iters = 0; pend = 0;
+          if (P.first_pass) {
+            resume_pos = entry4;
+            acc = from4(zero4);
+          } else {
+            resume_pos = from4(P.ray_start[pix]);
+            acc = from4(P.start_color[pix]);
+          }
+          if (!ISO) {
+            resume_col = acc;
+            if (resume_pos.w == 1000.0f) done = true;
+          } else {
+            if (floorf(resume_pos.w) == 1000.0f) done = true;
+            else if (floorf(resume_pos.w) == 500.0f) {
+              hit_pos = xform4(P.m2e, resume_pos.x, resume_pos.y, resume_pos.z, 1.0f);
+              hit_pos.w = resume_pos.w - floorf(resume_pos.w) + 1.0f;
+              hit_nrm = acc;   // rayStartNormal
+              resume_nrm = hit_nrm;
+              done = true;
+            }
+          }
+          if (!done) {
+            c.entry = F3(resume_pos.x, resume_pos.y, resume_pos.z);
+            c.entry_depth = resume_pos.w;
+            c.nexit = F3(exit4.x, exit4.y, exit4.z);
+            c.exit_depth = exit4.w;
+            c.dir = sub3(c.nexit, c.entry);
+            c.ray_len = len3(c.dir);
+            // TransformToPoolSpace
+            const f3 ps = F3(P.pool_size_f);
+            vdir = norm3(mul3(c.dir, F3(P.vol_f)));
+            vdir = div3(vdir, ps);
+            const float den = 2.0f * P.sample_rate;
+            vdir = F3(vdir.x / den, vdir.y / den, vdir.z / den);
+            c.step = len3(vdir);
+            c.t = 0.0f;
+            c.optimal = true;
+            c.cur = c.entry;
+            c.j = 0;   // bricks visited by the chain (the shader's j < 100 bound)
+            c.lbx = 0; c.lby = 0; c.lbz = 0; c.lbl = 9999;
+        
+            c.dv = F3(1.0f / c.dir.x, 1.0f / c.dir.y, 1.0f / c.dir.z);   // BrickExit's 1.0/dir
+            // the empty-brick advance voxelSize*direction/rayLength
+            c.nudge = F3(voxel_size * c.dir.x / c.ray_len, voxel_size * c.dir.y / c.ray_len, voxel_size * c.dir.z / c.ray_len);
+            ray_live = c.ray_len > voxel_size;
+            chain = ray_live; have_next = false; steps_left = 0; b_partial = false; cur_ok = false;
+            if (kPark) { park_const(c, park, tid); park_var(c, park, tid); }
+          }
+        }
+      }
+      if (__ballot_sync(full, ray_live || have_ray) == 0u && !more && open_mask == 0u) break;
+    }
+    if (ray_live) {
+      // ---- chain phase: runs for the whole warp when some lane can neither sample nor pick up a segment
+      const unsigned act = __activemask();
+      const bool need = steps_left == 0 && !have_next && chain;
+      if (__ballot_sync(act, need) != 0u && chain && !have_next) {
+        if (kPark) unpark(c, park, tid);
+#pragma unroll 1
+        for (int f = 0; f < 4 && chain && !have_next; f++) {
+          if (c.j >= 100) { chain = false; break; }
+          if (P.shard) {   // the block is convex: once the ray has left it there is nothing more to do on this rank
+            const bool gone = (c.dir.x > 0.0f && c.cur.x >= P.sh_hi[0]) || (c.dir.x < 0.0f && c.cur.x <= P.sh_lo[0]) ||
+                              (c.dir.y > 0.0f && c.cur.y >= P.sh_hi[1]) || (c.dir.y < 0.0f && c.cur.y <= P.sh_lo[1]) ||
+                              (c.dir.z > 0.0f && c.cur.z >= P.sh_hi[2]) || (c.dir.z < 0.0f && c.cur.z <= P.sh_lo[2]);
+            if (gone) {
+              if (PIPE) {   // where the next stage picks the ray up
+                handoff = true;
+                hand_pos.x = c.cur.x; hand_pos.y = c.cur.y; hand_pos.z = c.cur.z;
+                hand_pos.w = c.entry_depth * (1.0f - c.t) + c.exit_depth * c.t;
+              }
+              chain = false; break;
+            }
+          }
+          const float cur_depth = c.entry_depth * (1.0f - c.t) + c.exit_depth * c.t;
+          uint32_t lod = compute_lod(P, cur_depth);
+          BrickRef b;
+          int ok;
+          if (steps_left > 0) {   // look-ahead: the ray is still sampling the previous segment
+            ok = get_brick<true>(P, c.cur, lod, c.dir, c.dv, b);
+            if (ok < 0) break;    // missing brick: handled when the ray stands here
+          } else {
+            ok = get_brick<false>(P, c.cur, lod, c.dir, c.dv, b);
+            if (!ok && c.optimal) {
+              c.optimal = false;
+              resume_pos.x = c.cur.x; resume_pos.y = c.cur.y; resume_pos.z = c.cur.z; resume_pos.w = cur_depth;
+              if (!ISO) resume_col = acc;
+            }
+          }
+          if (COUNT) pend++;
+          if (!b.empty && !(c.lbx == b.bx && c.lby == b.by && c.lbz == b.bz && c.lbl == b.bl)) {
+            int steps = (int)ceilf(len3(sub3(b.pool_exit, b.pool_entry)) / c.step);
+            const int s2 = (int)ceilf(len3(mul3(sub3(c.nexit, c.cur), b.scale)) / c.step);
+            steps = min(steps, s2);
+            const f3 inv = F3(1.0f / b.scale.x, 1.0f / b.scale.y, 1.0f / b.scale.z);
+            f3 pe = b.pool_entry;
+            c.lbx = b.bx; c.lby = b.by; c.lbz = b.bz; c.lbl = b.bl;
+            if (b.where == OUTSIDE_SHARD) {   // another rank's brick: advance by its steps, take no sample
+              const float n = (float)max(steps, 0);
+              pe = F3(fmaf(n, vdir.x, pe.x), fmaf(n, vdir.y, pe.y), fmaf(n, vdir.z, pe.z));
+              steps = 0;
+            }
+            if (steps > 0) {
+              seg_f[0][tid] = pe.x; seg_f[1][tid] = pe.y; seg_f[2][tid] = pe.z;
+              seg_f[3][tid] = b.trans.x; seg_f[4][tid] = b.trans.y; seg_f[5][tid] = b.trans.z;
+              seg_f[6][tid] = inv.x; seg_f[7][tid] = inv.y; seg_f[8][tid] = inv.z;
+              seg_u[0][tid] = b.ox; seg_u[1][tid] = b.oy; seg_u[2][tid] = b.oz;
+              seg_u[3][tid] = b.slot; seg_u[4][tid] = (uint32_t)steps;
+              seg_u[5][tid] = b.where == PARTLY_IN_SHARD ? 1u : 0u;
+              if (COUNT) seg_u[6][tid] = b.id;
+              have_next = true;
+              // where the sample loop will leave pc: `steps` SEQUENTIAL adds (fp32 addition is not associative, so
+              // there is no closed form); 4x unrolled -- this loop was 6.5 % of the launch's warp instructions
+#pragma unroll 4
+              for (int i = 0; i < steps; i++) pe = add3(pe, vdir);
+            }
+            c.cur = mul3(sub3(pe, b.trans), inv);
+          } else {
+            c.cur = add3(b.norm_exit, c.nudge);
+            c.lbx = b.bx; c.lby = b.by; c.lbz = b.bz; c.lbl = b.bl;
+          }
+          c.t = len3(sub3(c.entry, b.norm_exit)) / c.ray_len;
+          c.j++;
+          if (c.t > 0.9999f) chain = false;
+        }
+        if (kPark) park_var(c, park, tid);
+      }
+      // ---- pick up the waiting segment
+      if (steps_left == 0 && have_next) {
+        pc = F3(seg_f[0][tid], seg_f[1][tid], seg_f[2][tid]);
+        b_trans = F3(seg_f[3][tid], seg_f[4][tid], seg_f[5][tid]);
+        b_inv = F3(seg_f[6][tid], seg_f[7][tid], seg_f[8][tid]);
+        b_ox = seg_u[0][tid]; b_oy = seg_u[1][tid]; b_oz = seg_u[2][tid];
+        vox = pool + (uint64_t)seg_u[3][tid] * P.slot_voxels;
+        steps_left = (int)seg_u[4][tid];
+        b_partial = seg_u[5][tid] != 0u;
+        have_next = false;
+        cur_ok = false;
+        if (COUNT) {
+          n_bricks += pend; pend = 0;
+          if (P.visited) { const uint32_t id = seg_u[6][tid]; atomicOr(P.visited + (id >> 5), 1u << (id & 31)); }
+        }
+      }
+      if (steps_left == 0 && !chain) {   // the ray left the volume (or its 100-brick budget) unterminated
+        if (COUNT) n_bricks += pend;
+        ray_live = false;
+      }
+      if (COUNT) {
+        n_alive_iters += ray_live ? 1 : 0;
+        if (__ffs(__activemask()) - 1 == (tid & 31)) n_warp_iters++;
+      }
+      // ---- sample phase: one sample for every lane that is inside a brick ----
+      if (ray_live && steps_left > 0) {
+        bool terminated = false;
+        // software pipeline: the footprint of THIS sample was fetched during the previous turn (cur_ok), the one of the
+        // next sample of the brick is fetched now, before this sample's arithmetic, so its load latency is covered
+        if (!kPrefetch || !FAST || !cur_ok) cur.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc);
+        const f3 pc_next = add3(pc, vdir);
+        const bool pf = kPrefetch && FAST && steps_left > 1;
+        Foot<T, FAST, BS, GRAD> nxt;
+        if (pf) nxt.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc_next);
+        bool mine = true;
+        if (b_partial) {
+          const f3 mq = mul3(sub3(pc, b_trans), b_inv);
+          mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
+                 mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
+          if (PIPE && !ISO && !mine) {
+            // a brick of a coarser LoD straddles the slab's far side: the ray is handed on AT the side, not
+            // behind the brick, so the next stage takes the brick's remaining samples
+            const bool gone = (c.dir.x > 0.0f && mq.x >= P.sh_hi[0]) || (c.dir.x < 0.0f && mq.x < P.sh_lo[0]) ||
+                              (c.dir.y > 0.0f && mq.y >= P.sh_hi[1]) || (c.dir.y < 0.0f && mq.y < P.sh_lo[1]) ||
+                              (c.dir.z > 0.0f && mq.z >= P.sh_hi[2]) || (c.dir.z < 0.0f && mq.z < P.sh_lo[2]);
+            if (gone) {
+              const float tq = len3(sub3(mq, c.entry)) / c.ray_len;
+              handoff = true;
+              hand_pos.x = mq.x; hand_pos.y = mq.y; hand_pos.z = mq.z;
+              hand_pos.w = c.entry_depth * (1.0f - tq) + c.exit_depth * tq;
+              terminated = true;   // leaves the loop; TerminateRay sees alpha <= 0.99 and hands the ray on
+            }
+          }
+        }
+        if constexpr (!ISO) {
+          if (mine) {
+            if (COUNT) n_samples++;
+            // ComputeColorFromVolume + OpacityCorrectColor at pool position pc
+            f4 col;
+            bool clear = false;
+            if constexpr (MODE == 0 && !LIT) {
+              col = tf_lookup(P, cur.centre(P) * P.trans_scale, 0.0f);
+            } else if constexpr (MODE == 0) {
+              float data; f3 g;
+              cur.sample_with_gradient(P, data, g);
+              col = tf_lookup(P, data * P.trans_scale, 0.0f);
+              // A sample whose transfer-function alpha is exactly 0 leaves the ray unchanged bit for bit
+              // (UnderCompositing adds colour * (1-a) * 0 = 0 to every channel; table colours and lit colours are
+              // finite, and opacity correction maps 0 to 0), so its normal and lighting are not computed when the
+              // whole warp agrees.  The shader cannot branch this cheaply; the result is identical.
+              clear = kSkipClear && col.w == 0.0f;
+              if (!clear) {
+                f3 n = mul3(g, dscale);   // ComputeNormal
+                const float l = len3(n);
+                if (l > 0.0f) n = scl3(n, 1.0f / l);
+                const f3 mp = mul3(sub3(pc, b_trans), b_inv);
+                const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
+                col.x = lit.x; col.y = lit.y; col.z = lit.z;
+              }
+            } else {
+              float data; f3 g;
+              cur.sample_with_gradient(P, data, g);
+              const float gm = len3(g);
+              col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
+              if (LIT) {
+                clear = kSkipClear && col.w == 0.0f;
+                if (!clear) {
+                  const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
+                  const f3 n = mul3(dscale, gn);
+                  const f3 mp = mul3(sub3(pc, b_trans), b_inv);
+                  float dl, sp;
+                  light_terms(eye_m, mp, n, ldir, dl, sp);
+                  const f3 lit = light_apply(la, mul3(F3(col.x, col.y, col.z), ld), ls, dl, sp);
+                  col.x = lit.x; col.y = lit.y; col.z = lit.z;
+                }
+              }
+            }
+            if (!clear) {
+              col.w = opacity_correct(P, col.w);
+              // UnderCompositing
+              const float oma = 1.0f - acc.w;
+              acc.x = fmaf(col.x * oma, col.w, acc.x);
+              acc.y = fmaf(col.y * oma, col.w, acc.y);
+              acc.z = fmaf(col.z * oma, col.w, acc.z);
+              acc.w = fmaf(col.w, oma, acc.w);
+              if (acc.w > 0.99f) terminated = true;
+            }
+          }
+        } else if (mine) {   // isosurface march
+          if (COUNT) n_samples++;
+          if (cur.centre(P) >= P.isoval) {
+            // RefineIsosurface
+            f3 rd = F3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
+            pc = sub3(pc, rd);
+            Foot<T, FAST, BS, false> rf;
+#pragma unroll 1
+            for (int k = 0; k < 5; k++) {
+              rd = F3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
+              rf.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc);
+              if (rf.centre(P) >= P.isoval) pc = sub3(pc, rd); else pc = add3(pc, rd);
+            }
+            const f3 hp = mul3(sub3(pc, b_trans), b_inv);
+            hit_pos = xform4(P.m2e, hp.x, hp.y, hp.z, 1.0f);
+            hit_pos.w = 1.0f + 1.0f;   // color.r + 1
+            Foot<T, FAST, BS, true> gf;
+            gf.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc);
+            float dummy; f3 g;
+            gf.sample_with_gradient(P, dummy, g);
+            f3 n = mul3(g, dscale);
+            const float l = len3(n);
+            if (l > 0.0f) n = scl3(n, 1.0f / l);
+            const float* m = P.mv_inv;   // mModelViewIT * vec4(n, 0)
+            hit_nrm.x = m[0] * n.x + m[1] * n.y + m[2] * n.z;
+            hit_nrm.y = m[4] * n.x + m[5] * n.y + m[6] * n.z;
+            hit_nrm.z = m[8] * n.x + m[9] * n.y + m[10] * n.z;
+            hit_nrm.w = floorf(1.0f * 512.0f) + 1.0f;   // floor(color.g*512)+color.b
+            terminated = true;
+          } else {
+            hit_pos = from4(zero4);
+          }
+        }
+        steps_left -= 1;
+        if (terminated) ray_live = false;
+        else {
+          pc = pc_next;
+          if (pf) cur = nxt;
+          cur_ok = pf;
+        }
+      }
+    }
+  }
+}
+
+#else
 template <typename T, int MODE, bool LIT, bool FAST, int BS, bool COUNT, bool PIPE = false>
 __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) raycast_kernel(const __grid_constant__ RayConsts P) {
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
@@ -881,6 +1300,8 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
   }
 }
 
+#endif
+
 // ---- fetch-path ceiling ------------------------------------------------------------------------------------------
 // What the traversal kernel's OWN fetch path can deliver when nothing else is in the loop: the same warp tiles (8x4
 // rays, one voxel apart), the same 0.5-voxel steps, the same FastFoot loads + packed filter trees on the resident pool,
@@ -934,7 +1355,15 @@ __global__ void __launch_bounds__(kThreads) fetch_probe_kernel(const __grid_cons
 template <typename T, int MODE, bool LIT>
 void launch_t(const RayConsts& rc, cudaStream_t s) {
   dim3 block(kThreads);
+#if TVK_PERSIST
+  // persistent warps: every CTA slot of the device once (launch bounds: TVK_MIN_BLOCKS * 64 / kThreads CTAs per SM), never
+  // more warps than there are tiles
+  const uint32_t n_tiles = ((rc.width + 15u) / 16u) * ((rc.height + 7u) / 8u) * 4u;
+  dim3 grid(std::max(1u, std::min((uint32_t)kSMs * (uint32_t)(TVK_MIN_BLOCKS * 64 / kThreads), (n_tiles + (kThreads / 32) - 1) / (kThreads / 32))));
+  cudaMemsetAsync(rc.tile_counter, 0, sizeof(uint32_t), s);
+#else
   dim3 grid((rc.width + 8 * kWX - 1) / (8 * kWX), (rc.height + 4 * kWY - 1) / (4 * kWY));
+#endif
   // FAST addressing needs the +-1 gradient taps of every legal sample position inside the slot
   bool fast = !rc.nearest;
   for (int i = 0; i < 3; i++) fast = fast && rc.total[i] >= 4 && rc.ghost[i] >= 2;

@@ -62,6 +62,7 @@ struct RayConsts {
   float4* out3;  // ISO rayResumeNormal
   unsigned long long* counters; // samples, rays, brick visits
   uint32_t* visited;            // bitmap over page-table indices of sampled bricks (counting only)
+  uint32_t* tile_counter;       // persistent traversal kernel: the next tile of the launch (zeroed by the launcher)
 };
 
 // launchers (defined in the .cu files)

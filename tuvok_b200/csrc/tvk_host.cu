@@ -690,6 +690,8 @@ int derive(tvk_ctx* ctx, RayConsts& u) {
   u.hash = ctx->hash_d;
   u.counters = ctx->counters_d;
   u.visited = ctx->visited_d;
+  // one tile counter per launch in flight (concurrent launches of the PAIRED policy must not share one)
+  u.tile_counter = reinterpret_cast<uint32_t*>(ctx->counters_d + 8) + (ctx->launch_seq++ & 15u);
   return TVK_OK;
 }
 
@@ -792,7 +794,7 @@ int tvk_create(const tvk_device_cfg* cfg, tvk_ctx** out) {
   ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto& ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
-  ok = ok && cudaMalloc(&ctx->counters_d, 8 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->counters_d, 8 * sizeof(unsigned long long) + 16 * sizeof(uint32_t)) == cudaSuccess;   // + tile counters
   ok = ok && cudaMallocHost(&ctx->counters_h, 8 * sizeof(unsigned long long)) == cudaSuccess;
   if (!ok) {
     fail(nullptr, TVK_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));

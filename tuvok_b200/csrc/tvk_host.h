@@ -97,6 +97,7 @@ struct tvk_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool counters_on = false;
+  uint32_t launch_seq = 0;         // traversal launches so far (selects the tile counter of a launch)
 
   // ---- dataset ----
   bool have_volume = false;
