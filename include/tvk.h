@@ -39,7 +39,13 @@ typedef enum {
 } tvk_status;
 
 /* ExtendedOctree::COMPONENT_TYPE subset on the hot path (ExtendedOctree.h:137-148) */
-typedef enum { TVK_U8 = 0, TVK_U16 = 1, TVK_F32 = 2 } tvk_dtype;
+typedef enum { TVK_U8 = 0, TVK_U16 = 1, TVK_F32 = 2,
+               /* colour volume: 4 x 8 bit per voxel, bricks are RGBA byte quadruples (UVF component count 4).  The renderer
+                * then runs GLGridLeaper-Method-{1D,1D-L,2D,2D-L,iso}-color.glsl / Compose-Color-FS.glsl (the transfer function
+                * maps alpha only; AbstrRenderer::ColorData).  min / max = the ALPHA component's (uvfDataset.cpp:1144, :1188).
+                * Registered datasets (tvk_set_volume) on the GridLeaper path only: the device bricker, the file readers, the
+                * classic per-brick path, MIP, sort-last and the depth pipeline refuse it. */
+               TVK_RGBA8 = 3 } tvk_dtype;
 /* AbstrRenderer::ERenderMode (Renderer/AbstrRenderer.h:142-147) */
 typedef enum { TVK_RM_1DTRANS = 0, TVK_RM_2DTRANS = 1, TVK_RM_ISOSURFACE = 2 } tvk_render_mode;
 /* RendererState::BrickStrategy (Controller/MasterController.h:61-67) */

@@ -172,5 +172,5 @@ def test_colour_volumes_are_refused_where_they_are_not_built():
     s = scene(orc.RM_1DTRANS, False)
     r = s.make_renderer()
     with pytest.raises(tb.TvkError):
-        r.PaintPerBrick()              # the classic GLRaycaster path (GLRaycaster-Color-FS.glsl) is not built
+        r.PaintClassic()               # the classic GLRaycaster path (GLRaycaster-Color-FS.glsl) is not built
     r.Cleanup()

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TVK_LIB") or os.path.join(_HERE, "libtvkcuda.so")
 
 TVK_MAX_LOD = 16
-U8, U16, F32 = 0, 1, 2
+U8, U16, F32, RGBA8 = 0, 1, 2, 3     # RGBA8: colour volume, bricks are [z, y, x, 4] uint8 (tvk.h TVK_RGBA8)
 RM_1DTRANS, RM_2DTRANS, RM_ISOSURFACE = 0, 1, 2
 BS_ONLY_NEEDED, BS_REQUEST_ALL, BS_SKIP_ONE_LEVEL, BS_SKIP_TWO_LEVELS = 0, 1, 2, 3
 BI_MISSING, BI_CHILD_EMPTY, BI_EMPTY, BI_FLAG_COUNT = 0, 1, 2, 3

@@ -24,6 +24,9 @@ __device__ __forceinline__ float dot(float ax, float ay, float az, float bx, flo
 
 struct ComposeConsts { float amb[3], dif[3], spe[3], ldir[3]; };
 
+// COLOR: Compose-Color-FS.glsl:60-92 -- the diffuse colour is the hit's own colour, unpacked from the two alpha channels
+// (r = pos.a - 1, g = floor(nrm.a / 2) / 256, b = fract(nrm.a)), times vLightDiffuse
+template <bool COLOR>
 __global__ void iso_compose_kernel(const float4* __restrict__ hit_pos, const float4* __restrict__ hit_nrm,
                                    float4* __restrict__ rgba, uint64_t n, const ComposeConsts C) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -42,9 +45,15 @@ __global__ void iso_compose_kernel(const float4* __restrict__ hit_pos, const flo
       rx = rx * inv; ry = ry * inv; rz = rz * inv;
       const float dl = fmaxf(fabsf(dot(nx, ny, nz, -C.ldir[0], -C.ldir[1], -C.ldir[2])), 0.0f);
       const float sp = pow8(fmaxf(dot(rx, ry, rz, C.ldir[0], C.ldir[1], C.ldir[2]), 0.0f));
-      o.x = clamp01(C.amb[0] + C.dif[0] * dl + C.spe[0] * sp);
-      o.y = clamp01(C.amb[1] + C.dif[1] * dl + C.spe[1] * sp);
-      o.z = clamp01(C.amb[2] + C.dif[2] * dl + C.spe[2] * sp);
+      float d0 = C.dif[0], d1 = C.dif[1], d2 = C.dif[2];
+      if (COLOR) {
+        d0 = (hp.w - 1.0f) * d0;
+        d1 = (floorf(hn.w / 2.0f) / 256.0f) * d1;
+        d2 = (hn.w - floorf(hn.w)) * d2;
+      }
+      o.x = clamp01(C.amb[0] + d0 * dl + C.spe[0] * sp);
+      o.y = clamp01(C.amb[1] + d1 * dl + C.spe[1] * sp);
+      o.z = clamp01(C.amb[2] + d2 * dl + C.spe[2] * sp);
       o.w = 1.0f;
     }
     rgba[i] = o;
@@ -264,11 +273,12 @@ inline int grid_for(uint64_t n, int block) {
 
 void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rgba, uint32_t w, uint32_t h,
                         const float amb[3], const float dif[3], const float spe[3], const float ldir[3],
-                        cudaStream_t s) {
+                        cudaStream_t s, bool color) {
   ComposeConsts C;
   for (int i = 0; i < 3; i++) { C.amb[i] = amb[i]; C.dif[i] = dif[i]; C.spe[i] = spe[i]; C.ldir[i] = ldir[i]; }
   const uint64_t n = (uint64_t)w * h;
-  iso_compose_kernel<<<grid_for(n, 256), 256, 0, s>>>(hit_pos, hit_nrm, rgba, n, C);
+  if (color) iso_compose_kernel<true><<<grid_for(n, 256), 256, 0, s>>>(hit_pos, hit_nrm, rgba, n, C);
+  else iso_compose_kernel<false><<<grid_for(n, 256), 256, 0, s>>>(hit_pos, hit_nrm, rgba, n, C);
 }
 
 void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s) {

@@ -72,7 +72,9 @@ void launch_fetch_probe(const RayConsts& rc, int dtype, bool grad, uint32_t n_sl
                         float* out, cudaStream_t s);
 void launch_iso_compose(const float4* hit_pos, const float4* hit_nrm, float4* rgba, uint32_t w, uint32_t h,
                         const float amb[3], const float dif[3], const float spe[3], const float ldir[3],
-                        cudaStream_t s);
+                        cudaStream_t s, bool color = false);
+// colour volumes (k_color.cu): GLGridLeaper-Method-*-color.glsl on a plain uchar4 pool
+void launch_raycast_color(const RayConsts& rc, int mode, int lighting, cudaStream_t s);
 void launch_quantize_rgba8(const float4* src, uchar4* dst, uint64_t n, cudaStream_t s);
 // Compose-CV-FS.glsl over the four hit targets (GLRenderer::ComposeSurfaceImage, ClearView branch)
 void launch_cv_compose(const float4* hit_pos, const float4* hit_nrm, const float4* cv_pos, const float4* cv_nrm, float4* rgba,

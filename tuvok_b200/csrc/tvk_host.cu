@@ -103,7 +103,8 @@ int compute_geometry(tvk_ctx* ctx) {
   ctx->total_bricks = ctx->lod_offset[ctx->pool_lod_count - 1] + 1;
   ctx->slot_voxels = (uint64_t)ctx->brick[0] * ctx->brick[1] * ctx->brick[2];
   ctx->slot_bytes = ctx->slot_voxels * ctx->esize;
-  ctx->pool_slot_bytes = ctx->slot_bytes * (ctx->dtype == TVK_F32 ? 1 : 2);   // x-pair layout of integer pools (k_pool.cu)
+  // x-pair layout of the scalar integer pools (k_pool.cu); float and colour (uchar4) pools are plain
+  ctx->pool_slot_bytes = ctx->slot_bytes * ((ctx->dtype == TVK_F32 || ctx->dtype == TVK_RGBA8) ? 1 : 2);
   return TVK_OK;
 }
 
@@ -667,15 +668,15 @@ int derive(tvk_ctx* ctx, RayConsts& u) {
     u.lod_layout_sz[l][0] = (uint32_t)ceilf(c[0]);
     u.lod_layout_sz[l][1] = (uint32_t)ceilf(c[0]) * (uint32_t)ceilf(c[1]);
   }
-  u.norm = ctx->dtype == TVK_U8 ? 1.0f / 255.0f : ctx->dtype == TVK_U16 ? 1.0f / 65535.0f : 1.0f;
+  u.norm = (ctx->dtype == TVK_U8 || ctx->dtype == TVK_RGBA8) ? 1.0f / 255.0f : ctx->dtype == TVK_U16 ? 1.0f / 65535.0f : 1.0f;
   u.sample_rate = p.sample_rate_modifier;
   u.oc = 1.0f / p.sample_rate_modifier;
   // GLRenderer::CalculateScaling (GLRenderer.cpp:1813-1819): (2^bits - 1) / maxValue; float data: 1/maxValue (H7)
-  const double full = ctx->dtype == TVK_U8 ? 255.0 : ctx->dtype == TVK_U16 ? 65535.0 : 1.0;
+  const double full = (ctx->dtype == TVK_U8 || ctx->dtype == TVK_RGBA8) ? 255.0 : ctx->dtype == TVK_U16 ? 65535.0 : 1.0;
   u.trans_scale = (float)(full / ctx->range_max);
   u.gradient_scale = ctx->max_grad == 0.0f ? 1.0f : 1.0f / ctx->max_grad;
   // GetNormalizedIsovalue (AbstrRenderer.cpp:412-424): iso / 2^bits; float data: iso itself (H7)
-  u.isoval = ctx->dtype == TVK_U8 ? (float)(p.isovalue / 256.0) : ctx->dtype == TVK_U16 ? (float)(p.isovalue / 65536.0)
+  u.isoval = (ctx->dtype == TVK_U8 || ctx->dtype == TVK_RGBA8) ? (float)(p.isovalue / 256.0) : ctx->dtype == TVK_U16 ? (float)(p.isovalue / 65536.0)
                                                                                        : (float)p.isovalue;
   if (p.mode == TVK_RM_2DTRANS) { u.tf = ctx->tf2d_d; u.tf_w = ctx->tf2d_w; u.tf_h = ctx->tf2d_h; }
   else { u.tf = ctx->tf1d_d; u.tf_w = ctx->tf1d_n; u.tf_h = 1; }
@@ -729,7 +730,13 @@ int raycast_pass(tvk_ctx* ctx, bool with_hash) {
     u.start_color = ctx->stage_color ? ctx->stage_color : ctx->buf[1];
     u.out1 = ctx->buf[1]; u.out2 = ctx->buf[3];
   }
-  launch_raycast(u, ctx->params.mode, ctx->params.lighting, ctx->dtype, ctx->stream);
+  if (ctx->dtype == TVK_RGBA8) {
+    if (u.shard || u.pipeline || ctx->counters_on)
+      return fail(ctx, TVK_ERR_INVALID, "colour volumes: sort-last shards, pipeline stages and counters are not built");
+    launch_raycast_color(u, ctx->params.mode, ctx->params.lighting, ctx->stream);
+  } else {
+    launch_raycast(u, ctx->params.mode, ctx->params.lighting, ctx->dtype, ctx->stream);
+  }
   CU(cudaGetLastError());
   if (ctx->stage_mode) { ctx->blank = true; return TVK_OK; }   // no resume state of its own: every stage frame starts anew
   if (iso) {   // GLRenderer::ComposeSurfaceImage (GLRenderer.cpp:2763-2830)
@@ -737,10 +744,13 @@ int raycast_pass(tvk_ctx* ctx, bool with_hash) {
     float a[3], d[3], s[3];
     for (int i = 0; i < 3; i++) {
       a[i] = p.ambient[i] * p.ambient[3];
-      d[i] = p.diffuse[i] * p.diffuse[3] * p.iso_color[i];
+      // colour data: Compose-Color-FS with the plain diffuse light, the surface colour comes out of the hit buffers
+      // (GLRenderer.cpp:2796-2810)
+      d[i] = p.diffuse[i] * p.diffuse[3] * (ctx->dtype == TVK_RGBA8 ? 1.0f : p.iso_color[i]);
       s[i] = p.specular[i] * p.specular[3];
     }
-    launch_iso_compose(ctx->buf[0], ctx->buf[5], ctx->buf[6], p.width, p.height, a, d, s, p.light_dir, ctx->stream);
+    launch_iso_compose(ctx->buf[0], ctx->buf[5], ctx->buf[6], p.width, p.height, a, d, s, p.light_dir, ctx->stream,
+                       ctx->dtype == TVK_RGBA8);
     CU(cudaGetLastError());
   }
   ctx->cur = nxt;      // swap current/next resume buffers (GLGridLeaper.cpp:861-862)
@@ -855,7 +865,7 @@ int tvk_enable_counters(tvk_ctx* ctx, int enable) {
 // ---- dataset ------------------------------------------------------------------------------------
 static int set_geometry(tvk_ctx* ctx, const uint32_t size[3], const float scale[3], const uint32_t max_brick[3],
                         uint32_t overlap, int dtype, double range_max, float max_grad) {
-  if (dtype < TVK_U8 || dtype > TVK_F32) return fail(ctx, TVK_ERR_INVALID, "unsupported dtype %d", dtype);
+  if (dtype < TVK_U8 || dtype > TVK_RGBA8) return fail(ctx, TVK_ERR_INVALID, "unsupported dtype %d", dtype);
   for (int i = 0; i < 3; i++) {
     if (size[i] == 0) return fail(ctx, TVK_ERR_INVALID, "empty domain");
     if (max_brick[i] <= 2 * overlap) return fail(ctx, TVK_ERR_INVALID, "brick size must exceed 2*overlap");
@@ -871,7 +881,7 @@ static int set_geometry(tvk_ctx* ctx, const uint32_t size[3], const float scale[
   ctx->overlap = overlap;
   ctx->dtype = dtype;
   ctx->esize = esize_of(dtype);
-  ctx->range_max = range_max > 0 ? range_max : (dtype == TVK_U8 ? 255.0 : dtype == TVK_U16 ? 65535.0 : 1.0);
+  ctx->range_max = range_max > 0 ? range_max : ((dtype == TVK_U8 || dtype == TVK_RGBA8) ? 255.0 : dtype == TVK_U16 ? 65535.0 : 1.0);
   ctx->max_grad = max_grad;
   return compute_geometry(ctx);
 }
@@ -1148,6 +1158,7 @@ int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uin
                      const float scale[3], const uint32_t max_brick_size[3], uint32_t overlap, int clamp_to_edge,
                      double range_max, float max_gradient_magnitude) {
   if (!ctx || !raw || !size || !max_brick_size) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
+  if (dtype == TVK_RGBA8) return fail(ctx, TVK_ERR_INVALID, "tvk_build_volume: colour volumes come from a registered dataset (tvk_set_volume)");
   int rc = set_geometry(ctx, size, scale, max_brick_size, overlap, dtype, range_max, max_gradient_magnitude);
   if (rc) return rc;
   ctx->cb = nullptr; ctx->cb_user = nullptr;
@@ -2015,6 +2026,8 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
   if (st) std::memset(st, 0, sizeof(*st));
   int rc = check_renderable(ctx);
   if (rc) return rc;
+  if (ctx->dtype == TVK_RGBA8)
+    return fail(ctx, TVK_ERR_INVALID, "colour volumes are rendered on the GridLeaper path (GLRaycaster-Color-FS is not built)");
   const tvk_render_params& p = ctx->params;
   if (mip && !ctx->tf1d_d) return fail(ctx, TVK_ERR_INVALID, "MIP: no 1D transfer function set (Transfer-MIP-FS needs it)");
   rc = ensure_frame(ctx, p.width, p.height);

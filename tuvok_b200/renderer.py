@@ -17,7 +17,7 @@ from . import _lib as L
 from .tf import TransferFunction1D, TransferFunction2D
 
 RM_1DTRANS, RM_2DTRANS, RM_ISOSURFACE = L.RM_1DTRANS, L.RM_2DTRANS, L.RM_ISOSURFACE
-_NP_OF = {L.U8: np.uint8, L.U16: np.uint16, L.F32: np.float32}
+_NP_OF = {L.U8: np.uint8, L.U16: np.uint16, L.F32: np.float32, L.RGBA8: np.uint8}
 _DT_OF = {np.dtype(np.uint8): L.U8, np.dtype(np.uint16): L.U16, np.dtype(np.float32): L.F32}
 IDENTITY = np.eye(4, dtype=np.float32)
 
@@ -205,7 +205,7 @@ class CudaGridLeaper:
         d.max_brick_size = L.u32x3(*max_brick_size)
         d.overlap = overlap
         d.dtype = dtype
-        d.range_max = range_max if range_max > 0 else {L.U8: 255.0, L.U16: 65535.0, L.F32: 1.0}[dtype]
+        d.range_max = range_max if range_max > 0 else {L.U8: 255.0, L.U16: 65535.0, L.F32: 1.0, L.RGBA8: 255.0}[dtype]
         d.max_gradient_magnitude = max_gradient_magnitude
         d.brick_count = mm.shape[0]
         d.minmax = mm.ctypes.data_as(C.POINTER(C.c_double))
