@@ -532,7 +532,13 @@ void orc_mip_render(const orc_render_params* p, uint32_t lod, const orc_classic_
   const float norm = p->dtype == ORC_U8 ? 1.0f / 255.0f : p->dtype == ORC_U16 ? 1.0f / 65535.0f : 1.0f;
   const size_t n_pix = (size_t)p->width * p->height;
   memset(out_max, 0, n_pix * 8);
-  std::vector<float> fbo(n_pix * 3), near_pt(n_pix * 3);
+  /* m_bOrthoView (GLRenderer.cpp:1183-1197, GLRaycaster.cpp:486-489): the projection is FLOATMATRIX4::Ortho and the model view
+   * the MIP rotation alone.  The shaders are projection-agnostic (entry FBO + interpolated back-face position); what changes is
+   * the ray a fragment lies on: eye-space points a + s * b with a = 0, b = the near-plane point for a perspective projection
+   * (s = 1 on the near plane), and b = far-plane point - near-plane point, a = near-plane point - b for a parallel one.
+   * A projection is parallel when w' does not depend on z (Vectors.h:1279-1284: array[11] = 0). */
+  const int ortho = inv_proj[11] == 0.0f;
+  std::vector<float> fbo(n_pix * 3), near_pt(n_pix * 3), org_pt(n_pix * 3, 0.0f), dir_pt(n_pix * 3);
   for (uint32_t y = 0; y < p->height; y++)
     for (uint32_t x = 0; x < p->width; x++) {
       float nx = ((float)x + 0.5f) / (float)p->width * 2.0f - 1.0f;
@@ -541,9 +547,17 @@ void orc_mip_render(const orc_render_params* p, uint32_t lod, const orc_classic_
       size_t i = (size_t)y * p->width + x;
       near_pt[3 * i] = nr.x / nr.w; near_pt[3 * i + 1] = nr.y / nr.w; near_pt[3 * i + 2] = nr.z / nr.w;
       for (int k = 0; k < 3; k++) fbo[3 * i + k] = half_round(near_pt[3 * i + k]);
+      for (int k = 0; k < 3; k++) dir_pt[3 * i + k] = near_pt[3 * i + k];
+      if (ortho) {
+        v4 fr = xform4(inv_proj, nx, ny, 1.0f, 1.0f);
+        const float far_pt[3] = {fr.x / fr.w, fr.y / fr.w, fr.z / fr.w};
+        for (int k = 0; k < 3; k++) {
+          dir_pt[3 * i + k] = far_pt[k] - near_pt[3 * i + k];
+          org_pt[3 * i + k] = near_pt[3 * i + k] - dir_pt[3 * i + k];
+        }
+      }
     }
   uint64_t samples = 0;
-  const v4 o4 = xform4(imv, 0.0f, 0.0f, 0.0f, 1.0f);
   for (uint32_t bi = 0; bi < n_bricks; bi++) {
     const orc_classic_brick& b = list[bi];
     if (b.empty) continue;                 /* "for MIP we do not consider empty bricks" GLRenderer.cpp:1209-1211 */
@@ -561,6 +575,8 @@ void orc_mip_render(const orc_render_params* p, uint32_t lod, const orc_classic_
       for (uint32_t px = 0; px < p->width; px++) {
         const size_t i = (size_t)py * p->width + px;
         const v3 pn = V3(near_pt[3 * i], near_pt[3 * i + 1], near_pt[3 * i + 2]);
+        const v3 pa = V3(org_pt[3 * i], org_pt[3 * i + 1], org_pt[3 * i + 2]), pb = V3(dir_pt[3 * i], dir_pt[3 * i + 1], dir_pt[3 * i + 2]);
+        const v4 o4 = xform4(imv, pa.x, pa.y, pa.z, 1.0f);
         const v4 n4 = xform4(imv, pn.x, pn.y, pn.z, 1.0f);
         const float o[3] = {o4.x, o4.y, o4.z}, d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
         float s_in = -INFINITY, s_out = INFINITY;
@@ -573,11 +589,11 @@ void orc_mip_render(const orc_render_params* p, uint32_t lod, const orc_classic_
         }
         if (miss || !(s_out > fmaxf(s_in, 1.0f))) continue;
         if (s_in > 1.0f) {
-          const v3 fe = scl3(pn, s_in);
+          const v3 fe = ortho ? add3(pa, scl3(pb, s_in)) : scl3(pn, s_in);
           fbo[3 * i] = half_round(fe.x); fbo[3 * i + 1] = half_round(fe.y); fbo[3 * i + 2] = half_round(fe.z);
         }
         const v3 entry = V3(fbo[3 * i], fbo[3 * i + 1], fbo[3 * i + 2]);
-        const v3 exit_ = scl3(pn, s_out);
+        const v3 exit_ = ortho ? add3(pa, scl3(pb, s_out)) : scl3(pn, s_out);
         auto to_tex = [&](v3 q) {
           v4 w = xform4(imv, q.x, q.y, q.z, 1.0f);
           return add3(mul3(sub3(V3(w.x, w.y, w.z), pmax), tsc), tmax);

@@ -18,6 +18,7 @@
 //           (GLGridLeaper::FillBBoxVBO, GLGridLeaper.cpp:506-532: Plane() * inverse(rotation*translation), normal normalised,
 //            then Clipper::BoxPlane on the 12 triangles of the box [-extent/2, extent/2]; prints the plane and the triangles)
 //     miprot window(0 sagittal,1 axial,2 coronal) flipx flipy angle_deg region_rotation[16] view[16]
+//     mipo width height                     (the parallel projection of an HQ MIP frame, m_bOrthoView)
 //           (the statements of GLRenderer::RenderHQMIPPreLoop + GLRaycaster::RenderHQMIPPreLoop on FLOATMATRIX4)
 #include <cstdio>
 #include <cstdlib>
@@ -89,6 +90,24 @@ int main(int argc, char** argv) {
       maMIPRotation = matRotDir * region_rotation * matFlipX * matFlipY * maMIPRotation;
       put16(out, "miprot", maMIPRotation);
       put16(out, "mipmv", maMIPRotation * view);   // GLRaycaster::RenderHQMIPPreLoop, GLRaycaster.cpp:489 (perspective)
+    } else if (op == "mipo") {
+      // the parallel projection of an HQ MIP frame under m_bOrthoView: the statement sequence of GLRenderer.cpp:1183-1197 on
+      // the reference's own vector / matrix classes
+      unsigned w, h;
+      ls >> w >> h;
+      UINTVECTOR2 m_vWinSize(w, h);
+      FLOATMATRIX4 maOrtho;
+      DOUBLEVECTOR2 vWinAspectRatio = 1.0 / DOUBLEVECTOR2(m_vWinSize);
+      vWinAspectRatio = vWinAspectRatio / vWinAspectRatio.maxVal();
+      float fRoot2Scale = (vWinAspectRatio.x < vWinAspectRatio.y) ?
+                          std::max(1.0f, 1.414213f * float(vWinAspectRatio.x/vWinAspectRatio.y)) :
+                          1.414213f;
+      maOrtho.Ortho(-0.5f*fRoot2Scale/float(vWinAspectRatio.x),
+                    +0.5f*fRoot2Scale/float(vWinAspectRatio.x),
+                    -0.5f*fRoot2Scale/float(vWinAspectRatio.y),
+                    +0.5f*fRoot2Scale/float(vWinAspectRatio.y),
+                    -100.0f, 100.0f);
+      put16(out, "mipo", maOrtho);
     } else if (op == "clipbox") {
       float pw[4]; FLOATMATRIX4 rot, tra; FLOATVECTOR3 ext;
       ls >> pw[0] >> pw[1] >> pw[2] >> pw[3]; read16(ls, rot); read16(ls, tra); ls >> ext.x >> ext.y >> ext.z;

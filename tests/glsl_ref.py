@@ -425,7 +425,8 @@ int main(int argc, char** argv) {
   for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gl_NormalMatrix.a[r * 3 + c] = imv[r * 4 + c];   // transpose(inverse(MV)) rows
   texTrans.rgba8 = (const uint8_t*)p; texTrans.w = tfw; set_tf_height(texTrans, tfh); p += (size_t)tfw * tfh * 4;
   const size_t npx = (size_t)W * H;
-  std::vector<float> out(npx * 4, 0.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3);
+  std::vector<float> out(npx * 4, 0.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3), org_pt(npx * 3, 0.0f), dir_pt(npx * 3);
+  const bool ortho = inv_proj[11] == 0.0f;           // parallel projection (m_bOrthoView): w' does not depend on z
   for (uint32_t y = 0; y < H; y++)
     for (uint32_t x = 0; x < W; x++) {               // Render3DPreLoop: the near plane fills the entry FBO first
       const float nx = ((float)x + 0.5f) / (float)W * 2.0f - 1.0f, ny = ((float)y + 0.5f) / (float)H * 2.0f - 1.0f;
@@ -435,6 +436,13 @@ int main(int argc, char** argv) {
       const size_t i = (size_t)y * W + x;
       near_pt[3 * i] = rx / rw; near_pt[3 * i + 1] = ry / rw; near_pt[3 * i + 2] = rz / rw;
       for (int k = 0; k < 3; k++) fbo[4 * i + k] = half_round(near_pt[3 * i + k]);
+      for (int k = 0; k < 3; k++) dir_pt[3 * i + k] = near_pt[3 * i + k];
+      if (ortho) {                                    // eye-space ray a + s * b through the near (s = 1) and far plane points
+        const float fx = nx * m[0] + ny * m[4] + 1.0f * m[8] + 1.0f * m[12], fy = nx * m[1] + ny * m[5] + 1.0f * m[9] + 1.0f * m[13];
+        const float fz = nx * m[2] + ny * m[6] + 1.0f * m[10] + 1.0f * m[14], fw = nx * m[3] + ny * m[7] + 1.0f * m[11] + 1.0f * m[15];
+        const float far_pt[3] = {fx / fw, fy / fw, fz / fw};
+        for (int k = 0; k < 3; k++) { dir_pt[3 * i + k] = far_pt[k] - near_pt[3 * i + k]; org_pt[3 * i + k] = near_pt[3 * i + k] - dir_pt[3 * i + k]; }
+      }
     }
   texRayExitPos.f32 = fbo.data(); texRayExitPos.w = W; texRayExitPos.h = H;
   auto xf = [&](const float* m, float x, float y, float z) { return vec3(x * m[0] + y * m[4] + z * m[8] + 1.0f * m[12], x * m[1] + y * m[5] + z * m[9] + 1.0f * m[13], x * m[2] + y * m[6] + z * m[10] + 1.0f * m[14]); };
@@ -465,7 +473,9 @@ int main(int argc, char** argv) {
       for (uint32_t x = 0; x < W; x++) {
         const size_t i = (size_t)y * W + x;
         const vec3 pn(near_pt[3 * i], near_pt[3 * i + 1], near_pt[3 * i + 2]);
+        const vec3 pa(org_pt[3 * i], org_pt[3 * i + 1], org_pt[3 * i + 2]), pb(dir_pt[3 * i], dir_pt[3 * i + 1], dir_pt[3 * i + 2]);
         const vec3 n4 = xf(imv, pn.x, pn.y, pn.z);
+        const vec3 o4 = xf(imv, pa.x, pa.y, pa.z);
         const float o[3] = {o4.x, o4.y, o4.z}, d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
         float s_in = -INFINITY, s_out = INFINITY; bool miss = false;
         for (int k = 0; k < 3; k++) {
@@ -474,8 +484,8 @@ int main(int argc, char** argv) {
           s_in = fmaxf(s_in, fminf(t0, t1_)); s_out = fminf(s_out, fmaxf(t0, t1_));
         }
         if (miss || !(s_out > fmaxf(s_in, 1.0f))) continue;
-        if (s_in > 1.0f) { const vec3 fe = pn * s_in; fbo[4 * i] = half_round(fe.x); fbo[4 * i + 1] = half_round(fe.y); fbo[4 * i + 2] = half_round(fe.z); }
-        vEyePos = pn * s_out;                                    // interpolated back-face position (eye space)
+        if (s_in > 1.0f) { const vec3 fe = ortho ? pa + pb * s_in : pn * s_in; fbo[4 * i] = half_round(fe.x); fbo[4 * i + 1] = half_round(fe.y); fbo[4 * i + 2] = half_round(fe.z); }
+        vEyePos = ortho ? pa + pb * s_out : pn * s_out;          // interpolated back-face position (eye space)
         gl_FragCoord = vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
         gl_FragColor = vec4();
         classic_main();
@@ -711,8 +721,8 @@ def _classic_iso_driver():
         ("  ScaleMethod = 0; TFuncBias = 0.0f;\n",
          "  ScaleMethod = 0; TFuncBias = 0.0f;\n"
          "  fIsoval = fTransScale; vProjParam = vec2(fGradientScale, fStepScale);   // carried in the unused header slots\n"),
-        ("  std::vector<float> out(npx * 4, 0.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3);",
-         "  std::vector<float> out(npx * 4, 0.0f), out2(npx * 4, 0.0f), depthb(npx, 1.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3);"),
+        ("  std::vector<float> out(npx * 4, 0.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3), org_pt(npx * 3, 0.0f), dir_pt(npx * 3);",
+         "  std::vector<float> out(npx * 4, 0.0f), out2(npx * 4, 0.0f), depthb(npx, 1.0f), fbo(npx * 4, 0.0f), near_pt(npx * 3), org_pt(npx * 3, 0.0f), dir_pt(npx * 3);"),
         ("        gl_FragColor = vec4();\n        classic_main();\n",
          "        gl_FragData[0] = vec4(); gl_FragData[1] = vec4(); g_discarded = false; iTileID = (int)bi;\n        iso_main();\n"),
         ("        float* dst = &out[4 * i];                               // GL blending ONE_MINUS_DST_ALPHA, ONE\n"

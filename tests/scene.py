@@ -92,6 +92,11 @@ class Scene:
             vl, vr, pl, pr = orc.stereo_view(self.eye, (0, 0, 0), (0, 1, 0), self.fov, float(F(self.width) / F(self.height)),
                                              0.01, 1000.0, focal, dist)
             view, proj = (vl, pl) if e == 0 else (vr, pr)
+        if getattr(self, "ortho_mip", False):
+            # m_bOrthoView: an HQ MIP frame's model view is the MIP rotation alone, its projection FLOATMATRIX4::Ortho
+            # (GLRaycaster.cpp:486-487, GLRenderer.cpp:1183-1197)
+            import tuvok_b200 as tb
+            return self.rotation.astype(F), tb.mip_ortho_projection(self.width, self.height)
         mv = ((self.rotation @ self.translation).astype(F) @ view).astype(F)
         return mv, proj
 

@@ -92,6 +92,79 @@ def test_oracle_mip_matches_executed_reference_shaders(tmp_path, name):
     assert (r["image"].reshape(-1, 4)[om[:, 1] == 0, :3] == 0).all()   # uncovered pixels are black
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_host")),
+                    reason="oracle/_ref/ref_host not built (reference tree absent)")
+@pytest.mark.parametrize("w,h", [(96, 96), (128, 72), (72, 128), (1920, 1080), (333, 777), (40, 36)])
+def test_mip_ortho_projection_matches_reference_statements(tmp_path, w, h):
+    """GLRenderer.cpp:1183-1197 run on the reference's own DOUBLEVECTOR2 / FLOATMATRIX4::Ortho (ref_host mipo)."""
+    import test_host_ref as hr
+    rows = hr.run(tmp_path, ["mipo %d %d" % (w, h)])
+    ref = hr.hexf(rows[0][1:]).reshape(4, 4)
+    got = tb.mip_ortho_projection(w, h)
+    assert np.array_equal(got, ref), np.abs(got - ref).max()
+    assert got[2, 3] == 0.0 and got[3, 3] == 1.0                    # parallel: w' does not depend on z
+
+
+ORTHO_SCENES = ["coronal_u16", "sagittal_rot_u8_ragged", "axial_flip_aniso", "coronal_small_window_lod1"]
+
+
+def make_ortho(name):
+    s, wm, flip, angle, mip_lod = make(name)
+    s.ortho_mip = True                                              # AbstrRenderer::SetOrthoView(true)
+    return s, wm, flip, angle, mip_lod
+
+
+@pytest.mark.skipif(not glsl_ref.available(), reason="reference shaders / oracle/_ref tools absent")
+@pytest.mark.parametrize("name", ORTHO_SCENES)
+def test_oracle_ortho_mip_matches_executed_reference_shaders(tmp_path, name):
+    """m_bOrthoView (GLRenderer.cpp:1183-1197, GLRaycaster.cpp:486-487): parallel rays, model view = the MIP rotation alone."""
+    s, *_rest, mip_lod = make_ortho(name)
+    r = s.oracle_mip(use_mip_lod=mip_lod)
+    p = r["params"]
+    u = orc.uniforms(p)
+    assert u["inv_proj"][11] == 0.0
+    exe = glsl_ref.build_mip(tmp_path)
+    img, mx = glsl_ref.run_mip(exe, tmp_path, p, u["inv_proj"], u["mv_inv"], u["norm"], r["bricks"], r["n"], r["data"],
+                               s.tf1d.GetByteArray())
+    om = r["max"].reshape(-1, 2)
+    assert 0.05 < om[:, 1].mean() < 1.0                             # the volume is on screen, with a margin around it
+    assert np.array_equal(om[:, 1], mx[:, 3])
+    assert float(np.abs(om[:, 0] - mx[:, 0]).max()) <= 5e-5
+    a8, b8 = orc.rgba8(r["image"]), orc.rgba8(img.reshape(s.height, s.width, 4))
+    d8, psnr = image_diff(a8, b8)
+    assert d8 <= 2 and psnr >= 45.0
+    # parallel rays: the covered region of an unrotated coronal view is an axis-aligned rectangle
+    if name == "coronal_u16":
+        cov = r["max"][..., 1] > 0
+        ys, xs = np.nonzero(cov)
+        assert cov[ys.min():ys.max() + 1, xs.min():xs.max() + 1].all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ORTHO_SCENES)
+def test_cuda_ortho_mip_matches_oracle(name):
+    s, wm, flip, angle, mip_lod = make_ortho(name)
+    ref = s.oracle_mip(use_mip_lod=mip_lod)
+    r = s.make_renderer("device")
+    r.SetMIPRotationAngle(angle)
+    r.SetMIPLOD(mip_lod)
+    r.SetOrthoView(True)
+    r.PaintHQMIP(wm, flip)
+    lod, order, _ = r.classic_brick_list()
+    assert lod == ref["lod"] and np.array_equal(order, ref["order"])
+    assert np.array_equal(r.mip_max_image(), ref["max"])
+    assert np.array_equal(r.ReadRGBA32F(), ref["image"])
+    # and back: the perspective frame of the same renderer is unchanged by the excursion
+    r.SetOrthoView(False)
+    s.ortho_mip = False
+    r.PaintHQMIP(wm, flip)
+    assert np.array_equal(r.mip_max_image(), s.oracle_mip(use_mip_lod=mip_lod)["max"])
+    with pytest.raises(tb.TvkError):                                # a parallel projection outside the MIP frame is refused
+        r.SetOrthoView(True)
+        r._push_params(); r._push_ortho_mip(np.eye(4, dtype=np.float32)); r._ck(r._lib.tvk_render_classic(r._h, None))
+    r.Cleanup()
+
+
 def test_mip_properties():
     s, *_ = make("sagittal_rot_u8_ragged")
     r = s.oracle_mip()

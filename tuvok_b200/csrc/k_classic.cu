@@ -198,7 +198,10 @@ __device__ __forceinline__ f3 iso_normal(const ClassicConsts& P, const typename 
 }
 
 // MODE: 0 = 1D TF, 1 = 2D TF, 2 = HQ MIP, 3 = isosurface, 4 = isosurface + ClearView second pass (first hit, nearest of all bricks by the depth test)
-template <typename T, int MODE, bool LIT>
+// ORTHO (HQ MIP frames only): a parallel projection, m_bOrthoView (GLRenderer.cpp:1183-1197, GLRaycaster.cpp:486-489) -- the
+// fragment's ray is a + s * b with b = far-plane point - near-plane point, a = near-plane point - b (s = 1 on the near plane,
+// as for the perspective ray s * pn)
+template <typename T, int MODE, bool LIT, bool ORTHO = false>
 __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ ClassicConsts P) {
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const uint32_t px = blockIdx.x * 8 + (lane & 7);
@@ -220,7 +223,14 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
   const float ny = ((float)py + 0.5f) / (float)P.height * 2.0f - 1.0f;
   const f4 nr = xform4(P.inv_proj, nx, ny, -1.0f, 1.0f);
   const f3 pn = F3(nr.x / nr.w, nr.y / nr.w, nr.z / nr.w);
-  const f4 o4 = xform4(P.imv, 0.0f, 0.0f, 0.0f, 1.0f);
+  f3 pa = F3(0.0f, 0.0f, 0.0f), pb = pn;
+  if (ORTHO) {
+    const f4 fr = xform4(P.inv_proj, nx, ny, 1.0f, 1.0f);
+    const f3 pf = F3(fr.x / fr.w, fr.y / fr.w, fr.z / fr.w);
+    pb = sub3(pf, pn);
+    pa = sub3(pn, pb);
+  }
+  const f4 o4 = xform4(P.imv, pa.x, pa.y, pa.z, 1.0f);
   const f4 n4 = xform4(P.imv, pn.x, pn.y, pn.z, 1.0f);
   const float o[3] = {o4.x, o4.y, o4.z};
   const float d[3] = {n4.x - o4.x, n4.y - o4.y, n4.z - o4.z};
@@ -271,10 +281,10 @@ __global__ void __launch_bounds__(64) classic_kernel(const __grid_constant__ Cla
         }
         if (!miss && s_out > fmaxf(s_in, 1.0f)) {
           if (s_in > 1.0f) {   // a visible front face overwrites the ray-entry FBO
-            const f3 fe = scl3(pn, s_in);
+            const f3 fe = ORTHO ? add3(pa, scl3(pb, s_in)) : scl3(pn, s_in);
             fbo = F3(half_round(fe.x), half_round(fe.y), half_round(fe.z));
           }
-          const f3 entry = fbo, exit_ = scl3(pn, s_out);
+          const f3 entry = fbo, exit_ = ORTHO ? add3(pa, scl3(pb, s_out)) : scl3(pn, s_out);
           const f3 pmax = F3(hi[0], hi[1], hi[2]);
           const f3 tsc = F3(P.tsc[cell[0]], P.tsc[S + cell[1]], P.tsc[2 * S + cell[2]]);
           const f3 tmax = F3(P.tmax[cell[0]], P.tmax[S + cell[1]], P.tmax[2 * S + cell[2]]);
@@ -455,7 +465,8 @@ template <typename T>
 void launch_t(const ClassicConsts& c, int mode, int lighting, cudaStream_t s) {
   const dim3 block(64), grid((c.width + 7) / 8, (c.height + 7) / 8);
   if (mode == TVK_CLASSIC_MIP) {
-    classic_kernel<T, 2, false><<<grid, block, 0, s>>>(c);
+    if (c.ortho) classic_kernel<T, 2, false, true><<<grid, block, 0, s>>>(c);
+    else classic_kernel<T, 2, false><<<grid, block, 0, s>>>(c);
   } else if (mode == TVK_RM_ISOSURFACE) {
     if (c.out_cv) classic_kernel<T, 4, false><<<grid, block, 0, s>>>(c);   // ClearView: second (focus) pass per brick
     else classic_kernel<T, 3, false><<<grid, block, 0, s>>>(c);

@@ -107,6 +107,7 @@ void launch_nway_over_peer(const NWaySrc& a, float4* out_f, uchar4* out8, uint64
 struct ClassicConsts {
   uint32_t width, height;
   float inv_proj[16], imv[16];      // inverse projection, inverse(modelView)
+  int32_t ortho;                    // the projection is parallel (w' independent of z): HQ MIP frames under m_bOrthoView
   float domain_scale[3], light_a[3], light_d[3], light_s[3], light_dir[3];
   float norm, trans_scale, gradient_scale, step_scale;
   uint32_t tf_w, tf_h;

@@ -2230,6 +2230,9 @@ static int render_per_brick(tvk_ctx* ctx, tvk_frame_stats* st, bool mip, int use
   for (int i = 0; i < 16; i++) { mv[i] = p.model_view[i]; pr[i] = p.projection[i]; }
   if (!inv4(mv, imv) || !inv4(pr, ipr)) return fail(ctx, TVK_ERR_INVALID, "singular view or projection matrix");
   for (int i = 0; i < 16; i++) { c.imv[i] = (float)imv[i]; c.inv_proj[i] = (float)ipr[i]; }
+  c.ortho = c.inv_proj[11] == 0.0f ? 1 : 0;   // FLOATMATRIX4::Ortho (Vectors.h:1279-1284): array[11] = 0
+  if (c.ortho && !mip)
+    return fail(ctx, TVK_ERR_INVALID, "a parallel projection is built for HQ MIP frames only (m_bOrthoView, GLRenderer.cpp:1183-1197)");
   const float mn = std::fmin(ctx->scale[0], std::fmin(ctx->scale[1], ctx->scale[2]));
   for (int i = 0; i < 3; i++) {
     c.domain_scale[i] = 1.0f / (ctx->scale[i] / mn);

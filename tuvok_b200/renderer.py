@@ -82,6 +82,26 @@ def mip_rotation(window_mode="coronal", angle_deg=0.0, flip=(False, False), regi
     return matmul4(matmul4(matmul4(matmul4(rot_dir, reg), flip_x), flip_y), ry(pi * float(angle_deg) / 180.0))
 
 
+def mip_ortho_projection(width, height):
+    """The parallel projection GLRenderer::Render2DView sets for an HQ MIP frame when m_bOrthoView is on
+    (GLRenderer.cpp:1183-1197): FLOATMATRIX4::Ortho (Vectors.h:1279-1284) over +-0.5 * root2scale / aspect, z in [-100, 100];
+    aspect ratios in double, the rest in single precision as written there."""
+    f = np.float32
+    ax, ay = 1.0 / float(width), 1.0 / float(height)
+    m = max(ax, ay)
+    ax, ay = ax / m, ay / m
+    root2 = max(f(1.0), f(f(1.414213) * f(ax / ay))) if ax < ay else f(1.414213)
+    l, r = f(f(f(-0.5) * root2) / f(ax)), f(f(f(0.5) * root2) / f(ax))
+    b, t = f(f(f(-0.5) * root2) / f(ay)), f(f(f(0.5) * root2) / f(ay))
+    n, fa = f(-100.0), f(100.0)
+    p = np.zeros((4, 4), np.float32)                   # array[4 * row + col], row-vector convention
+    p[0, 0] = f(2.0) / f(r - l); p[3, 0] = f(-f(r + l)) / f(r - l)
+    p[1, 1] = f(2.0) / f(t - b); p[3, 1] = f(-f(t + b)) / f(t - b)
+    p[2, 2] = f(-f(2.0)) / f(fa - n); p[3, 2] = f(-f(fa + n)) / f(fa - n)
+    p[3, 3] = f(1.0)
+    return p
+
+
 def translation(x, y, z):
     m = np.eye(4, dtype=np.float32)
     m[3, :3] = (x, y, z)
@@ -579,6 +599,13 @@ class CudaGridLeaper:
         self._dirty = False
         self._converged = False
 
+    def _push_ortho_mip(self, mip_rot):
+        """m_bOrthoView: projection = Ortho, model view = the MIP rotation alone (no view matrix)."""
+        p = self.params
+        p.model_view = L.f32x16(*np.asarray(mip_rot, np.float32).reshape(-1))
+        p.projection = L.f32x16(*mip_ortho_projection(p.width, p.height).reshape(-1))
+        self._ck(self._lib.tvk_set_params(self._h, C.byref(p)))
+
     # ------------------------------------------------------------------ frame
     def Paint(self):
         """One subframe (GLGridLeaper::Render3DRegion)."""
@@ -664,15 +691,24 @@ class CudaGridLeaper:
         """AbstrRenderer::SetMIPLOD (AbstrRenderer.h:385)."""
         self._mip_lod = bool(on)
 
+    def SetOrthoView(self, on=True):
+        """AbstrRenderer::SetOrthoView (AbstrRenderer.cpp:1264-1269): HQ MIP frames use a parallel projection."""
+        self._ortho = bool(on)
+        self._dirty = True
+
     def PaintHQMIP(self, window_mode="coronal", flip=(False, False), region_rotation=None):
         """One HQ MIP frame of a 2D window in MIP mode (GLRenderer.cpp:1183-1253): modelView = m_maMIPRotation * view
-        (GLRaycaster::RenderHQMIPPreLoop), PlanHQMIPFrame's LoD, per-brick maximum, BE_MAX blending, Transfer-MIP."""
+        (GLRaycaster::RenderHQMIPPreLoop), PlanHQMIPFrame's LoD, per-brick maximum, BE_MAX blending, Transfer-MIP.
+        Under SetOrthoView the projection is mip_ortho_projection and the model view the MIP rotation alone
+        (GLRaycaster.cpp:486-487)."""
         keep = (self._rotation, self._translation)
         self._rotation = mip_rotation(window_mode, getattr(self, "_mip_angle", 0.0), flip, region_rotation)
         self._translation = np.eye(4, dtype=np.float32)
         self._dirty = True
         try:
             self._push_params()
+            if getattr(self, "_ortho", False):
+                self._push_ortho_mip(self._rotation)
             st = L.FrameStats()
             self._ck(self._lib.tvk_render_mip(self._h, 1 if getattr(self, "_mip_lod", True) else 0, C.byref(st)))
         finally:
