@@ -77,6 +77,10 @@ bool CUDAGridLeaper::Initialize(std::shared_ptr<Context>) {
   }
   d.overlap = m_pToc->GetBrickOverlapSize()[0];                            // IO/Dataset.h:134
   d.dtype = m_pToc->GetIsFloat() ? TVK_F32 : m_pToc->GetBitWidth() == 8 ? TVK_U8 : TVK_U16;
+  // AbstrRenderer::ColorData (AbstrRenderer.cpp:1417-1425): four 8-bit components -> the "-color" methods (k_color.cu);
+  // MaxMinForKey already answers with the alpha component for such data (uvfDataset.cpp:1188)
+  if (m_pToc->GetComponentCount() == 4 && m_pToc->GetBitWidth() == 8) d.dtype = TVK_RGBA8;
+  else if (m_pToc->GetComponentCount() != 1) { T_ERROR("CUDAGridLeaper: %u-component data is not supported", unsigned(m_pToc->GetComponentCount())); return false; }
   d.range_max = MaxValue();                                                // AbstrRenderer.cpp:860-866
   d.max_gradient_magnitude = m_pToc->MaxGradientMagnitude();               // IO/Dataset.h:82
   // MaxMinForKey for all bricks of the pool LoDs in TOC order (what GLVolumePool.cpp:225-235 copies)
@@ -294,7 +298,28 @@ bool CUDAGridLeaper::PaintHQMIP(const FLOATMATRIX4& regionRotation, int windowMo
   m_maMIPRotation.RotationY(dPI * double(m_fMIPRotationAngle) / 180.0);
   m_maMIPRotation = matRotDir * regionRotation * matFlipX * matFlipY * m_maMIPRotation;
   tvk_render_params p = m_params;
-  std::memcpy(p.model_view, (m_maMIPRotation * m_mView[0]).array, 64);     // GLRaycaster.cpp:489 (perspective rays)
+  if (m_bOrthoView) {
+    // GLRenderer.cpp:1183-1197: the parallel projection of the MIP frame; GLRaycaster.cpp:486-487: model view = the rotation
+    FLOATMATRIX4 maOrtho;
+    DOUBLEVECTOR2 vWinAspectRatio = 1.0 / DOUBLEVECTOR2(m_vWinSize);
+    vWinAspectRatio = vWinAspectRatio / vWinAspectRatio.maxVal();
+    const float fRoot2Scale = (vWinAspectRatio.x < vWinAspectRatio.y)
+                                  ? std::max(1.0f, 1.414213f * float(vWinAspectRatio.x / vWinAspectRatio.y))
+                                  : 1.414213f;
+    // FLOATMATRIX4::Ortho (Vectors.h:1279-1284) is only declared under USEGL; this library-side renderer is GL-free, so the
+    // six entries are written out
+    const float l = -0.5f * fRoot2Scale / float(vWinAspectRatio.x), r = +0.5f * fRoot2Scale / float(vWinAspectRatio.x);
+    const float b = -0.5f * fRoot2Scale / float(vWinAspectRatio.y), t = +0.5f * fRoot2Scale / float(vWinAspectRatio.y);
+    const float zn = -100.0f, zf = 100.0f;
+    maOrtho.array[0] = 2.0f / (r - l); maOrtho.array[12] = -(r + l) / (r - l);
+    maOrtho.array[5] = 2.0f / (t - b); maOrtho.array[13] = -(t + b) / (t - b);
+    maOrtho.array[10] = -2.0f / (zf - zn); maOrtho.array[14] = -(zf + zn) / (zf - zn);
+    maOrtho.array[15] = 1.0f;
+    std::memcpy(p.projection, maOrtho.array, 64);
+    std::memcpy(p.model_view, m_maMIPRotation.array, 64);
+  } else {
+    std::memcpy(p.model_view, (m_maMIPRotation * m_mView[0]).array, 64);   // GLRaycaster.cpp:489 (perspective rays)
+  }
   tvk_frame_stats st;
   return !Fail(tvk_set_params(m_ctx, &p)) && !Fail(tvk_render_mip(m_ctx, m_bMIPLOD, &st));
 }
