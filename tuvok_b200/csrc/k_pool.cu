@@ -210,6 +210,25 @@ void launch_slot_unpair(const void* slot, void* out, uint64_t n_voxels, uint32_t
   else if (esize == 2) slot_unpair_kernel<uint16_t, uint32_t><<<g, 256, 0, s>>>((const uint32_t*)slot, (uint16_t*)out, n_voxels);
   else slot_unpair_kernel<float, float><<<g, 256, 0, s>>>((const float*)slot, (float*)out, n_voxels);
 }
+// LPT tile schedule of the traversal kernel: counting sort of the tiles by the cost measured in the previous frame,
+// largest first; one CTA (a frame has at most a few ten thousand tiles), ties in arrival order
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ order,
+                                                          uint32_t shift) {
+  __shared__ uint32_t hist[256], base[256];
+  if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(255u, cost[i] >> shift)], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int b = 255; b >= 0; b--) { base[b] = acc; acc += hist[b]; }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&base[min(255u, cost[i] >> shift)], 1u)] = i;
+}
+void launch_tile_order(const uint32_t* cost, uint32_t n, uint32_t* order, uint32_t shift, cudaStream_t s) {
+  if (n) tile_order_kernel<<<1, 1024, 0, s>>>(cost, n, order, shift);
+}
 void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s) {
   hash_compact_kernel<<<grid_for(n, 256), 256, 0, s>>>(hash, n, out_list, out_count);
 }

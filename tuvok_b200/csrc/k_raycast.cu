@@ -549,8 +549,15 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
   // CTAs are dispatched in blockIdx order (x fastest).  The rays through the middle of the volume are the
   // longest: tile rows / columns are mapped centre-out so those start first (measured: +1 % on C3, the launch
   // is bound by per-warp latency, not by its tail; kept because it costs nothing).
-  const uint32_t tx = kCentreOut ? centre_out(blockIdx.x, gridDim.x) : blockIdx.x;
-  const uint32_t ty = kCentreOut ? centre_out(blockIdx.y, gridDim.y) : blockIdx.y;
+  // Tile schedule (P.tile_order, optional): CTA k of the launch takes tile order[k] -- the tiles sorted by the cost the
+  // PREVIOUS frame measured for them, longest first (LPT), so that the CTAs with the longest rays do not start last and
+  // leave the device idle behind them.  Which CTA traces which tile does not change any ray.
+  uint32_t lin = blockIdx.y * gridDim.x + blockIdx.x;
+  if (P.tile_order) lin = __ldg(P.tile_order + lin);
+  const uint32_t bxi = lin % gridDim.x, byi = lin / gridDim.x;
+  const uint32_t tx = kCentreOut ? centre_out(bxi, gridDim.x) : bxi;
+  const uint32_t ty = kCentreOut ? centre_out(byi, gridDim.y) : byi;
+  uint32_t n_turns = 0;   // turns of the flat loop this ray took: the tile's cost is the maximum over its rays
   const uint32_t px = tx * (8 * kWX) + (wid % kWX) * 8 + (lane & 7);
   const uint32_t py = ty * (4 * kWY) + (wid / kWX) * 4 + (lane >> 3);
   if (px >= P.width || py >= P.height) return;
@@ -650,6 +657,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
 
     if (kPark) { park_const(c, park, tid); park_var(c, park, tid); }
     while (ray_live) {
+      n_turns++;
       // ---- chain phase: runs for the whole warp when some lane can neither sample nor pick up a segment
       const unsigned act = __activemask();
       const bool need = steps_left == 0 && !have_next && chain;
@@ -887,6 +895,11 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
       resume_nrm = hit_nrm;
     }
   }
+  if (P.tile_cost) {
+    const unsigned m = __activemask();
+    const uint32_t w = __reduce_max_sync(m, n_turns);
+    if ((uint32_t)(__ffs(m) - 1) == (uint32_t)lane) atomicMax(P.tile_cost + lin, w);
+  }
   if (!ISO) {
     P.out0[pix] = to4(acc); P.out1[pix] = to4(resume_col); P.out2[pix] = to4(resume_pos);
   } else {
@@ -1011,6 +1024,10 @@ void launch_fetch_probe(const RayConsts& rc_in, int dtype, bool grad, uint32_t n
     default: if (b36) TVK_PROBE(float, 36); else TVK_PROBE(float, 0); break;
   }
 #undef TVK_PROBE
+}
+
+uint32_t raycast_tiles(uint32_t width, uint32_t height) {
+  return ((width + 8 * kWX - 1) / (8 * kWX)) * ((height + 4 * kWY - 1) / (4 * kWY));
 }
 
 void launch_raycast(const RayConsts& rc, int mode, int lighting, int dtype, cudaStream_t s) {

@@ -63,6 +63,8 @@ struct RayConsts {
   unsigned long long* counters; // samples, rays, brick visits
   uint32_t* visited;            // bitmap over page-table indices of sampled bricks (counting only)
   uint32_t* tile_counter;       // persistent traversal kernel: the next tile of the launch (zeroed by the launcher)
+  const uint32_t* tile_order;   // tile schedule of this launch (CTA k -> tile order[k]) or NULL = dispatch order
+  uint32_t* tile_cost;          // per tile: the largest number of loop turns one of its rays took (input of the next schedule)
 };
 
 // launchers (defined in the .cu files)
@@ -156,6 +158,10 @@ void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t
                       uint32_t esize, const uint32_t total[3], int src_is_slot_layout, cudaStream_t s);
 // plain voxels of one pool slot (the first halves of its pairs) -> out (device)
 void launch_slot_unpair(const void* slot, void* out, uint64_t n_voxels, uint32_t esize, cudaStream_t s);
+// tile schedule: order = the n tiles sorted by cost, largest first (counting sort over cost >> shift, one CTA)
+void launch_tile_order(const uint32_t* cost, uint32_t n, uint32_t* order, uint32_t shift, cudaStream_t s);
+// CTAs of a traversal launch (k_raycast.cu)
+uint32_t raycast_tiles(uint32_t width, uint32_t height);
 void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s);
 
 // bricker (k_bricker.cu)

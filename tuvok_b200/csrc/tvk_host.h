@@ -97,6 +97,11 @@ struct tvk_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   bool counters_on = false;
+  // LPT tile schedule of the traversal kernel (TVK_TILE_LPT / tvk_set_tile_schedule): tiles sorted by last frame's cost
+  int tile_lpt = 0;
+  uint32_t* tile_cost_d = nullptr;
+  uint32_t* tile_order_d[2] = {nullptr, nullptr};
+  uint32_t tile_n = 0; int tile_cur = 0; bool tile_valid = false;
   uint32_t launch_seq = 0;         // traversal launches so far (selects the tile counter of a launch)
 
   // ---- dataset ----
