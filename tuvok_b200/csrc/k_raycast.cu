@@ -134,8 +134,19 @@ __device__ __forceinline__ void unpark(ChainSt& c, float (*m)[kThreads], int tid
 #define TVK_PERSIST 0
 #endif
 #ifndef TVK_REFILL
-#define TVK_REFILL 8
+#define TVK_REFILL 32   // 32: a warp takes its next tile only when all its lanes are idle (lanes without a ray help, TVK_HELP)
 #endif
+// TVK_HELP (persistent variant only): lanes without a ray shade later samples of a neighbour's brick segment.  Built,
+// bit-identical, MEASURED SLOWER (profiles/r3e_help_ab.txt: 313.7 -> 241.9 fps): the long rays of a frame are neighbours, so
+// the warps on the critical path have no idle lanes to help them.
+#ifndef TVK_HELP
+#define TVK_HELP 1
+#endif
+#ifndef TVK_HELP_MAX
+#define TVK_HELP_MAX 3
+#endif
+constexpr bool kHelp = TVK_HELP != 0;
+constexpr int kHelpMax = TVK_HELP_MAX;
 constexpr int kRefill = TVK_REFILL;
 constexpr int kSMs = 148;
 #if TVK_PERSIST
@@ -413,6 +424,8 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
         n_alive_iters += ray_live ? 1 : 0;
         if (__ffs(__activemask()) - 1 == (tid & 31)) n_warp_iters++;
       }
+    }   // if (ray_live): chain phase, segment pick-up, end-of-ray test
+    if constexpr (ISO || PIPE || !kHelp) {
       // ---- sample phase: one sample for every lane that is inside a brick ----
       if (ray_live && steps_left > 0) {
         bool terminated = false;
@@ -504,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
             f3 rd = F3(vdir.x / 2.0f, vdir.y / 2.0f, vdir.z / 2.0f);
             pc = sub3(pc, rd);
             Foot<T, FAST, BS, false> rf;
-#pragma unroll 1
+  #pragma unroll 1
             for (int k = 0; k < 5; k++) {
               rd = F3(rd.x / 2.0f, rd.y / 2.0f, rd.z / 2.0f);
               rf.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc);
@@ -538,10 +551,135 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
           cur_ok = pf;
         }
       }
+    } else {
+      // ---- sample phase with HELPER LANES.  The samples of one brick segment are independent until they are blended, and
+      // a launch cannot finish before its longest ray has walked the serial chain of one sample (load -> filter -> gradient ->
+      // table fetch -> Phong -> blend) hundreds of times.  So a lane WITHOUT a ray (finished, uncovered,
+      // waiting for the next tile) adopts a neighbour's segment for one turn and shades that ray's sample k + off at
+      // pc + off * vdir -- the very position the owner would reach by its own sequential adds -- with the owner's brick state;
+      // the owner then blends its own sample and its helpers' samples IN RAY ORDER, stopping at early termination exactly
+      // where it would have stopped alone.  Same samples, same arithmetic, same order: the ray's result is bit-identical,
+      // its critical path is up to kHelpMax + 1 times shorter.
+      const bool own = ray_live && steps_left > 0;
+      bool helper = false;
+      int hc = 0, first_rank = 0;   // owner: number of my helpers, rank of my first helper among the idle lanes
+      int h = 0;                    // warp-uniform: helpers per owner this turn
+      const unsigned idle_h = __ballot_sync(full, !ray_live);
+      const unsigned owner_m = __ballot_sync(full, own && steps_left >= 2 && !b_partial);
+      if (idle_h != 0u && owner_m != 0u) {
+        const int n_idle = __popc(idle_h), n_own = __popc(owner_m);
+        h = max(1, min(kHelpMax, n_idle / n_own));
+        const unsigned lt = (1u << lane) - 1u;
+        int src = lane, off = 0;
+        if (!ray_live) {
+          const int r = __popc(idle_h & lt);
+          if (r / h < n_own) { src = (int)__fns(owner_m, 0, r / h + 1); off = 1 + r % h; }
+        } else if (own && steps_left >= 2 && !b_partial) {
+          first_rank = __popc(owner_m & lt) * h;
+          hc = max(0, min(h, n_idle - first_rank));
+        }
+        // the owner's segment state travels to its helpers (every lane executes the shuffles; a lane that helps nobody reads itself)
+        const f3 o_pc = F3(__shfl_sync(full, pc.x, src), __shfl_sync(full, pc.y, src), __shfl_sync(full, pc.z, src));
+        const f3 o_vd = F3(__shfl_sync(full, vdir.x, src), __shfl_sync(full, vdir.y, src), __shfl_sync(full, vdir.z, src));
+        const f3 o_tr = F3(__shfl_sync(full, b_trans.x, src), __shfl_sync(full, b_trans.y, src), __shfl_sync(full, b_trans.z, src));
+        const f3 o_in = F3(__shfl_sync(full, b_inv.x, src), __shfl_sync(full, b_inv.y, src), __shfl_sync(full, b_inv.z, src));
+        const uint32_t o_ox = __shfl_sync(full, b_ox, src), o_oy = __shfl_sync(full, b_oy, src), o_oz = __shfl_sync(full, b_oz, src);
+        const int o_steps = __shfl_sync(full, steps_left, src);
+        const unsigned long long o_vox = __shfl_sync(full, (unsigned long long)vox, src);
+        if (off > 0 && off < o_steps) {
+          helper = true;
+          pc = o_pc;
+          for (int i = 0; i < off; i++) pc = add3(pc, o_vd);   // the owner's own sequence of adds
+          b_trans = o_tr; b_inv = o_in; b_ox = o_ox; b_oy = o_oy; b_oz = o_oz;
+          vox = (const W*)o_vox;
+        }
+      }
+      // ---- shade: a lane's own sample and an adopted sample run the same code
+      f4 col = from4(zero4);
+      bool clear = false, mine = true;
+      if (own || helper) {
+        cur.fetch(P, pool, vox, b_ox, b_oy, b_oz, pc);
+        if (own && b_partial) {
+          const f3 mq = mul3(sub3(pc, b_trans), b_inv);
+          mine = mq.x >= P.sh_lo[0] && mq.x < P.sh_hi[0] && mq.y >= P.sh_lo[1] && mq.y < P.sh_hi[1] &&
+                 mq.z >= P.sh_lo[2] && mq.z < P.sh_hi[2];
+        }
+        if (mine) {
+          // ComputeColorFromVolume + OpacityCorrectColor at pool position pc
+          if constexpr (MODE == 0 && !LIT) {
+            col = tf_lookup(P, cur.centre(P) * P.trans_scale, 0.0f);
+          } else if constexpr (MODE == 0) {
+            float data; f3 g;
+            cur.sample_with_gradient(P, data, g);
+            col = tf_lookup(P, data * P.trans_scale, 0.0f);
+            clear = kSkipClear && col.w == 0.0f;   // see the note in the single-lane path: the result is identical
+            if (!clear) {
+              f3 n = mul3(g, dscale);   // ComputeNormal
+              const float l = len3(n);
+              if (l > 0.0f) n = scl3(n, 1.0f / l);
+              const f3 mp = mul3(sub3(pc, b_trans), b_inv);
+              const f3 lit = lighting(eye_m, mp, n, la, mul3(F3(col.x, col.y, col.z), ld), ls, ldir);
+              col.x = lit.x; col.y = lit.y; col.z = lit.z;
+            }
+          } else {
+            float data; f3 g;
+            cur.sample_with_gradient(P, data, g);
+            const float gm = len3(g);
+            col = tf_lookup(P, data * P.trans_scale, 1.0f - gm * P.gradient_scale);
+            if (LIT) {
+              clear = kSkipClear && col.w == 0.0f;
+              if (!clear) {
+                const f3 gn = gm > 0.0f ? scl3(g, 1.0f / gm) : g;
+                const f3 n = mul3(dscale, gn);
+                const f3 mp = mul3(sub3(pc, b_trans), b_inv);
+                float dl, sp;
+                light_terms(eye_m, mp, n, ldir, dl, sp);
+                const f3 lit = light_apply(la, mul3(F3(col.x, col.y, col.z), ld), ls, dl, sp);
+                col.x = lit.x; col.y = lit.y; col.z = lit.z;
+              }
+            }
+          }
+          if (!clear) col.w = opacity_correct(P, col.w);
+        }
+      }
+      // ---- blend in ray order: the lane's own sample, then its helpers' samples (UnderCompositing)
+      if (own) {
+        if (mine) {
+          if (COUNT) n_samples++;
+          if (!clear) {
+            const float oma = 1.0f - acc.w;
+            acc.x = fmaf(col.x * oma, col.w, acc.x);
+            acc.y = fmaf(col.y * oma, col.w, acc.y);
+            acc.z = fmaf(col.z * oma, col.w, acc.z);
+            acc.w = fmaf(col.w, oma, acc.w);
+            if (acc.w > 0.99f) ray_live = false;
+          }
+        }
+        steps_left -= 1;
+        if (ray_live) pc = add3(pc, vdir);
+      }
+      for (int j = 0; j < h; j++) {   // warp-uniform trip count
+        const int hl = hc > j ? (int)__fns(idle_h, 0, first_rank + j + 1) : lane;
+        const float cx = __shfl_sync(full, col.x, hl), cy = __shfl_sync(full, col.y, hl), cz = __shfl_sync(full, col.z, hl),
+                    cw = __shfl_sync(full, col.w, hl);
+        const int fl = __shfl_sync(full, (helper ? 2 : 0) | (clear ? 1 : 0), hl);
+        if (hc > j && (fl & 2) != 0 && ray_live && steps_left > 0) {
+          if (COUNT) n_samples++;
+          if ((fl & 1) == 0) {
+            const float oma = 1.0f - acc.w;
+            acc.x = fmaf(cx * oma, cw, acc.x);
+            acc.y = fmaf(cy * oma, cw, acc.y);
+            acc.z = fmaf(cz * oma, cw, acc.z);
+            acc.w = fmaf(cw, oma, acc.w);
+            if (acc.w > 0.99f) ray_live = false;
+          }
+          steps_left -= 1;
+          if (ray_live) pc = add3(pc, vdir);
+        }
+      }
     }
   }
 }
-
 #else
 template <typename T, int MODE, bool LIT, bool FAST, int BS, bool COUNT, bool PIPE = false>
 __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) raycast_kernel(const __grid_constant__ RayConsts P) {
