@@ -472,7 +472,11 @@ int tvk_get_stage_outputs(tvk_ctx* ctx, void** image, void** resume_color, void*
 /* ---- sort-last compositing (new) --------------------------------------- */
 /* out = front + (1-front.a)*back on n_pixels premultiplied RGBA32F device pixels
  * (Compositing.glsl:33-38 / blend state GLRenderer.cpp:151-153); a front pixel with alpha > 0.99
- * (early ray termination, GLGridLeaper-blend.glsl:180) is kept as is. out may alias front or back. */
+ * (early ray termination, GLGridLeaper-blend.glsl:180) is kept as is, and a back image that would push alpha past 0.995 is
+ * scaled so that the result ends AT 0.995 -- the middle of the interval (0.99, 1] in which the single-GPU ray would have
+ * terminated inside the back block (alpha error <= 0.005).  The cut makes the operator non-associative: partial images
+ * must be folded front to back, ((s0 over s1) over s2) ..., which is what tvk_composite_nway and the sort-last frame do.
+ * out may alias front or back. */
 int tvk_composite_over(tvk_ctx* ctx, const void* front, const void* back, void* out, uint64_t n_pixels);
 /* float -> unorm8 (GL read-back conversion) on device buffers */
 int tvk_quantize_rgba8(tvk_ctx* ctx, const void* rgba32f, void* rgba8, uint64_t n_pixels);
