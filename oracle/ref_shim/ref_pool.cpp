@@ -15,6 +15,7 @@
 //   minmax <file>  f64[4] per brick, TOC order
 //   bricks <file>  optional: tightly packed voxels of every brick, TOC order
 //   create                                     (constructs the pool, DM_SYNC)
+//   autopool <bytes>                           (instead of create: the pool size GPUMemMan::GetVolumePool picks for that budget)
 //   first | vis1d a b | vis2d a b c d | visiso v | upload n (x y z lod)*n | dump | glsl <strategy 0..3> <out file>
 #include <cstdio>
 #include <cstdlib>
@@ -26,7 +27,12 @@
 #include <vector>
 
 #include "StdTuvokDefines.h"
+#define private public        // test shim only: MasterController::m_pSystemInfo is set by hand for the `autopool` directive
+#include "Controller/MasterController.h"
+#undef private
 #include "Controller/Controller.h"
+#include "Basics/SystemInfo.h"
+#include "Renderer/GPUMemMan/GPUMemMan.h"
 #include "IO/LinearIndexDataset.h"
 #include "Renderer/AbstrRenderer.h"
 #include "Renderer/VisibilityState.h"
@@ -172,6 +178,34 @@ int main(int argc, char** argv) {
     else if (op == "sizes") { std::string p; ls >> p; auto b = slurp(p); S.sizes.resize(b.size() / 4); memcpy(S.sizes.data(), b.data(), b.size()); }
     else if (op == "minmax") { std::string p; ls >> p; auto b = slurp(p); S.minmax.resize(b.size() / 8); memcpy(S.minmax.data(), b.data(), b.size()); }
     else if (op == "bricks") { std::string p; ls >> p; S.bricks = slurp(p); }
+    else if (op == "autopool") {
+      // the pool size the reference picks itself: the UNMODIFIED GPUMemMan::GetVolumePool (GPUMemMan.cpp:766-844, compiled in
+      // place, the rest of the class dropped by --gc-sections) with GetMaxUsableGPUMem = the given budget.  Neither
+      // GPUMemMan nor SystemInfo is constructed (their constructors pull in the whole renderer): the member function only
+      // reads m_iAllocatedGPUMemory (0) and the SystemInfo's usable-GPU-memory field, so both live in zeroed storage.
+      unsigned long long budget;
+      ls >> budget;
+      uint64_t first = 0, off = 0;
+      for (uint32_t l = 0; l < S.lods; l++) { S.lod_first.push_back(first); first += S.layout[l].volume(); }
+      for (size_t b = 0; b < S.sizes.size() / 3; b++) {
+        S.brick_off.push_back(off);
+        off += uint64_t(S.sizes[b * 3]) * S.sizes[b * 3 + 1] * S.sizes[b * 3 + 2] * (S.bits / 8);
+      }
+      ds = new ScenarioDataset(S);
+      static uint64_t si_store[(sizeof(SystemInfo) + 7) / 8], mm_store[(sizeof(GPUMemMan) + 7) / 8];
+      SystemInfo* si = reinterpret_cast<SystemInfo*>(si_store);
+      si->SetMaxUsableGPUMem(budget);
+      Controller::Instance().m_pSystemInfo = si;
+      GPUMemMan* mm = reinterpret_cast<GPUMemMan*>(mm_store);
+      GLVolumePool* ap = mm->GetVolumePool(ds, GL_LINEAR, 0);
+      if (!ap) { fprintf(out, "autopool failed\n"); }
+      else {
+        const UINTVECTOR3 cap = ap->GetPoolCapacity();
+        const UINTVECTOR3 mb = ds->GetMaxUsedBrickSizes();
+        fprintf(out, "autopool %u %u %u capacity %u %u %u\n", cap.x * mb.x, cap.y * mb.y, cap.z * mb.z, cap.x, cap.y, cap.z);
+      }
+      Controller::Instance().m_pSystemInfo = NULL;
+    }
     else if (op == "create") {
       uint64_t first = 0, off = 0;
       for (uint32_t l = 0; l < S.lods; l++) { S.lod_first.push_back(first); first += S.layout[l].volume(); }

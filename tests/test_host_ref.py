@@ -250,3 +250,45 @@ def test_clip_plane_matches_reference_clipper(tmp_path, case):
     span = np.nanmax(t, axis=1) - np.nanmin(t, axis=1) if t.size else np.array([])
     bad = np.flatnonzero(np.nan_to_num(inside) * (np.nan_to_num(span) > 5e-3))
     assert bad.size <= max(2, gone.size // 100), (bad.size, gone.size)  # grazing silhouette pixels aside
+
+
+BRICKDIST = os.path.join(ROOT, "oracle", "_ref", "ref_brickdist")
+
+
+@pytest.mark.skipif(not os.path.exists(BRICKDIST), reason="oracle/_ref/ref_brickdist not built (reference tree absent)")
+@pytest.mark.parametrize("name,over", [
+    ("c2_bricked36_1d_ert", {}),
+    ("ragged_1d_lit", dict(translation=tb.translation(-0.6, 0.5, 0.8))),
+    ("inside_aniso_2d", {}),
+])
+def test_brick_distance_and_depth_order_match_reference(tmp_path, name, over):
+    """the depth order of the classic per-brick path.  The oracle's brick distances (orc_classic.cpp) against the
+    reference's OWN file-static brick_distance (AbstrRenderer.cpp:808-841, reached by compiling its translation unit in
+    place: oracle/_ref/ref_brickdist), and the order std::sort(vBrickList) can produce from them (AbstrRenderer.h:104-106)."""
+    import subprocess
+    s = golden_scenes.make(name, **over)
+    o = s.octree
+    pool, _ = s.oracle_pool()
+    p = s.oracle_params(pool)
+    lod = orc.classic_lod(p, s.pool_lod_count())
+    bc = o.brick_count(lod)
+    first = o.brick_index(0, 0, 0, lod)
+    mm = o.minmax[first:first + bc[0] * bc[1] * bc[2]]
+    mine, n = orc.classic_brick_list(p, lod, s.overlap, mm, s.visibility_args())
+    live = [mine[i] for i in range(n) if not mine[i].empty]
+    assert len(live) >= 2
+    mv, _ = s.matrices()
+    with open(tmp_path / "in.txt", "w") as f:
+        f.write(fl(mv) + "\n")
+        for b in live:
+            f.write("%s %s\n" % (fl(b.center), fl(b.ext)))
+    subprocess.check_call([BRICKDIST, str(tmp_path / "in.txt"), str(tmp_path / "out.txt")])
+    ref = np.array([float.fromhex(l.split()[1]) for l in open(tmp_path / "out.txt")], np.float32)
+    got = np.array([b.distance for b in live], np.float32)
+    # the reference sums x*x + y*y + z*z in the order the compiler picks, the oracle (and the product) by the arithmetic
+    # contract's fma chain: the same number up to one rounding
+    assert np.all(np.abs(got - ref) <= np.spacing(np.maximum(got, ref))), float(np.abs(got - ref).max())
+    # the oracle's list is sorted by its distances; by the reference's distances it is sorted too, except where two bricks
+    # are closer together than that one rounding (std::sort leaves ties in unspecified order anyway)
+    d = np.diff(ref.astype(np.float64))
+    assert np.all(d >= -2.0 * np.spacing(ref[:-1]).astype(np.float64)), d.min()

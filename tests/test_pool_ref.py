@@ -157,3 +157,42 @@ def test_metadata_texture_folding(tmp_path):
         script = [("first",), ("vis", orc.RM_1DTRANS, (30.0, 200.0)), ("upload", keys[100:140])]
         pool = replay(tmp_path, vol, orc.U8, 12, 2, (48, 48, 48), script, max3d=max3d)
         assert pool.meta_dim[1] > 1
+
+
+AUTOPOOL_CASES = [   # (volume x, y, z), dtype, brick, usable GPU memory in bytes, GL_MAX_3D_TEXTURE_SIZE
+    ((44, 36, 28), orc.U8, 16, 1 << 20, 16384),          # budget below the dataset's need: the GPU layout wins
+    ((44, 36, 28), orc.U8, 16, 64 << 20, 16384),         # everything fits: the dataset layout wins
+    ((70, 45, 58), orc.U16, 20, 3 << 20, 16384),
+    ((70, 45, 58), orc.U16, 20, 200 << 20, 16384),
+    ((64, 64, 64), orc.U16, 36, 40 << 20, 16384),
+    ((64, 64, 64), orc.U16, 36, 40 << 20, 128),          # the 3D texture limit clamps every axis
+    ((96, 80, 40), orc.F32, 12, 5 << 20, 16384),
+    ((96, 80, 40), orc.F32, 12, 5 << 20, 60),
+]
+
+
+@pytest.mark.parametrize("size,dtype,brick,budget,max3d", AUTOPOOL_CASES)
+def test_pool_size_matches_reference_gpumemman(tmp_path, size, dtype, brick, budget, max3d):
+    """the pool size the renderer picks when the host gives none -- orc.pool_size (restated in the product's
+    size_pool) against the UNMODIFIED GPUMemMan::GetVolumePool (Renderer/GPUMemMan/GPUMemMan.cpp:766-844, compiled in place
+    into oracle/_ref/ref_pool, directive `autopool`) over the reference's own dataset classes."""
+    import subprocess
+    vol = synth.synth_volume(synth.V_NOISE, size, dtype, 0x5EED)
+    o = orc.Octree(vol, brick, 2)
+    bits = {orc.U8: 8, orc.U16: 16, orc.F32: 32}[dtype]
+    keys = list(o.iter_bricks())
+    np.array([o.brick_size(*k) for k in keys], np.uint32).tofile(str(tmp_path / "sizes.bin"))
+    np.ascontiguousarray(o.minmax, np.float64).tofile(str(tmp_path / "minmax.bin"))
+    lines = ["vol %d %d %d" % tuple(size), "brick %d" % brick, "overlap 2", "bits %d" % bits, "float %d" % int(dtype == orc.F32),
+             "pool 0 0 0", "max3d %d" % max3d, "lods %d" % o.lod_count]
+    lines += ["layout %d %d %d %d" % ((lod,) + tuple(o.brick_count(lod))) for lod in range(o.lod_count)]
+    lines += ["sizes %s" % (tmp_path / "sizes.bin"), "minmax %s" % (tmp_path / "minmax.bin"), "autopool %d" % budget]
+    (tmp_path / "scenario.txt").write_text("\n".join(lines) + "\n")
+    subprocess.check_call([pool_ref.BIN, str(tmp_path / "scenario.txt"), str(tmp_path / "result.txt"), str(tmp_path / "atlas.bin")],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    row = [l.split() for l in open(tmp_path / "result.txt") if l.startswith("autopool")][0]
+    ref = tuple(int(v) for v in row[1:4])
+    # GetMaxUsedBrickSizes: the largest brick that occurs (a volume smaller than one brick has smaller "max" bricks)
+    used = tuple(max(o.brick_size(*k)[a] for k in keys) for a in range(3))
+    got = tuple(orc.pool_size(budget, bits, 1, used, o.total_bricks, max3d))
+    assert got == ref, (got, ref)
