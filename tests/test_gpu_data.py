@@ -280,3 +280,21 @@ def test_paging_and_visibility_match_reference_glvolumepool(tmp_path, mode):
         want = atlas[z * 20:z * 20 + bz, y * 20:y * 20 + by, x * 20:x * 20 + bx]
         assert np.array_equal(r.pool_slot(slot, orc.U16, s.brick)[:bz, :by, :bx], want), "slot %d" % slot
     r.Cleanup()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,dtype,brick,budget", [((44, 36, 28), tb.U8, 16, 1 << 20), ((44, 36, 28), tb.U8, 16, 64 << 20),
+                                                     ((70, 45, 58), tb.U16, 20, 3 << 20), ((96, 80, 40), tb.F32, 12, 5 << 20)])
+def test_default_pool_size_is_the_reference_choice(size, dtype, brick, budget):
+    """SURVEY a12: tvk_create_pool(NULL) sizes the pool as GPUMemMan::GetVolumePool does -- the product's size_pool against the
+    oracle's pool_size, which tests/test_pool_ref.py pins to the unmodified reference function."""
+    vol = synth.synth_volume(synth.V_NOISE, size, dtype, 0x5EED)
+    o = orc.Octree(vol, brick, 2)
+    r = tb.CudaGridLeaper(max_gpu_mem=budget)
+    r.BuildVolume(vol, brick, 2)
+    r.CreateVolumePool()
+    bits = {tb.U8: 8, tb.U16: 16, tb.F32: 32}[dtype]
+    want = tuple(orc.pool_size(budget, bits, 1, (brick,) * 3, o.total_bricks))
+    cap = tuple(r.info().pool_capacity)
+    assert tuple(c * brick for c in cap) == want, (cap, want)
+    r.Cleanup()

@@ -213,7 +213,7 @@ void launch_slot_unpair(const void* slot, void* out, uint64_t n_voxels, uint32_t
 // LPT tile schedule of the traversal kernel: counting sort of the tiles by the cost measured in the previous frame,
 // largest first; one CTA (a frame has at most a few ten thousand tiles), ties in arrival order
 __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ order,
-                                                          uint32_t shift) {
+                                                          uint32_t shift, uint32_t split_cost) {
   __shared__ uint32_t hist[256], base[256];
   if (threadIdx.x < 256) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -225,9 +225,18 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __rest
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&base[min(255u, cost[i] >> shift)], 1u)] = i;
+  // order[n] = how many tiles (the first ones of the order) cost at least split_cost: the persistent kernel hands those
+  // out in quarter tiles with helper lanes; at most a quarter of the frame
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t cnt = 0;
+    const uint32_t b0 = min(255u, split_cost >> shift);
+    for (int b = 255; b >= (int)b0 && split_cost != 0u; b--) cnt += hist[b];
+    order[n] = min(cnt, n / 4u);
+  }
 }
-void launch_tile_order(const uint32_t* cost, uint32_t n, uint32_t* order, uint32_t shift, cudaStream_t s) {
-  if (n) tile_order_kernel<<<1, 1024, 0, s>>>(cost, n, order, shift);
+void launch_tile_order(const uint32_t* cost, uint32_t n, uint32_t* order, uint32_t shift, uint32_t split_cost, cudaStream_t s) {
+  if (n) tile_order_kernel<<<1, 1024, 0, s>>>(cost, n, order, shift, split_cost);
 }
 void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s) {
   hash_compact_kernel<<<grid_for(n, 256), 256, 0, s>>>(hash, n, out_list, out_count);

@@ -168,9 +168,18 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
   __shared__ float seg_f[9][kThreads];       // next segment: pool entry, trans, 1/scale
   __shared__ uint32_t seg_u[COUNT ? 7 : 6][kThreads];    // slot origin (3), slot index, steps, flags (, page-table index)
   // tile queue: 2x2 groups of 8x4 tiles, groups in the centre-out order of the non-persistent launch
-  const uint32_t gx = (P.width + 15u) / 16u, gy = (P.height + 7u) / 8u, n_tiles = gx * gy * 4u;
+  const uint32_t gx = (P.width + 15u) / 16u, gy = (P.height + 7u) / 8u;
   uint32_t open_tile = 0u, open_mask = 0u;   // warp-uniform: the tile being handed out, its pixels not yet taken
   bool more = true;                          // warp-uniform: the global queue has not run dry
+  // SPLIT work units (warp-uniform): the 2x2 tile groups whose rays were LONG in the previous frame (the first n_split entries
+  // of the cost-sorted order, tile_order_kernel) are handed out in quarter tiles -- 8 rays per warp -- so that the warp's
+  // other 24 lanes help (3 helpers per ray, 4 samples of a ray per turn) and four warps share what one warp would have
+  // walked alone: the critical path of the frame's longest rays is cut fourfold, every other tile runs the plain loop.
+  bool split = false;
+  const uint32_t n_groups = gx * gy;
+  const uint32_t n_split = (kHelp && !ISO && !PIPE && P.tile_order) ? min(__ldg(P.tile_order + n_groups), n_groups) : 0u;
+  const uint32_t n_units = 16u * n_split + 4u * (n_groups - n_split);
+  uint32_t ray_group = 0u, n_work = 0u;      // the ray's tile group and the work it took (samples + sample-less turns): next frame's cost
   // ---- state of the lane's current ray
   size_t pix = 0;
   bool have_ray = false;           // a ray has been started and its outputs are not written yet
@@ -233,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
           atomicAdd(P.counters + 3, n_alive_iters); atomicAdd(P.counters + 4, n_warp_iters);
           atomicMax(P.counters + 5, n_alive_iters);
         }
+        if (P.tile_cost) atomicMax(P.tile_cost + ray_group, n_work);
       }
       // the r-th waiting lane takes the r-th open pixel of the tile
       unsigned want = idle_m;
@@ -244,8 +254,18 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
           uint32_t t = 0;
           if (lane == 0) t = atomicAdd(P.tile_counter, 1u);
           t = __shfl_sync(full, t, 0);
-          if (t >= n_tiles) { more = false; break; }
-          open_tile = t; open_mask = full;
+          if (t >= n_units) { more = false; break; }
+          uint32_t j, sub;
+          if (t < 16u * n_split) {           // a quarter of a tile of a costly group
+            j = t >> 4; sub = (t >> 2) & 3u; split = true;
+            open_mask = 0xffu << (8u * (t & 3u));
+          } else {
+            const uint32_t u = t - 16u * n_split;
+            j = n_split + (u >> 2); sub = u & 3u; split = false;
+            open_mask = full;
+          }
+          const uint32_t g = P.tile_order ? __ldg(P.tile_order + j) : j;
+          open_tile = (g << 2) | sub;
         }
         const int n_take = min(__popc(open_mask), __popc(want));
         const int r = __popc(want & ((1u << lane) - 1u));
@@ -262,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
         }
         open_mask &= ~__reduce_or_sync(full, take ? (1u << bit) : 0u);
         want &= ~__ballot_sync(full, take);
+        if (split) break;   // a split unit is all this warp takes: its other lanes are the helpers
       }
       if (got && px < P.width && py < P.height) {
         pix = (size_t)py * P.width + px;
@@ -272,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
           if (ISO) P.out3[pix] = zero4;
         } else {
           have_ray = true; done = false; handoff = false;
+          ray_group = open_tile >> 2; n_work = 0u;
           hand_pos = from4(zero4); hit_pos = from4(zero4); hit_nrm = from4(zero4); resume_nrm = from4(zero4);
           n_samples = 0; n_bricks = 0; n_alive_iters = 0; n_warp_iters = 0; pend = 0;
           if (P.first_pass) {
@@ -564,8 +586,8 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
       bool helper = false;
       int hc = 0, first_rank = 0;   // owner: number of my helpers, rank of my first helper among the idle lanes
       int h = 0;                    // warp-uniform: helpers per owner this turn
-      const unsigned idle_h = __ballot_sync(full, !ray_live);
-      const unsigned owner_m = __ballot_sync(full, own && steps_left >= 2 && !b_partial);
+      const unsigned idle_h = split ? __ballot_sync(full, !ray_live) : 0u;
+      const unsigned owner_m = split ? __ballot_sync(full, own && steps_left >= 2 && !b_partial) : 0u;
       if (idle_h != 0u && owner_m != 0u) {
         const int n_idle = __popc(idle_h), n_own = __popc(owner_m);
         h = max(1, min(kHelpMax, n_idle / n_own));
@@ -643,6 +665,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
         }
       }
       // ---- blend in ray order: the lane's own sample, then its helpers' samples (UnderCompositing)
+      if (ray_live) n_work++;
       if (own) {
         if (mine) {
           if (COUNT) n_samples++;
@@ -664,6 +687,7 @@ __global__ void __launch_bounds__(kThreads, TVK_MIN_BLOCKS * 64 / kThreads) rayc
                     cw = __shfl_sync(full, col.w, hl);
         const int fl = __shfl_sync(full, (helper ? 2 : 0) | (clear ? 1 : 0), hl);
         if (hc > j && (fl & 2) != 0 && ray_live && steps_left > 0) {
+          n_work++;
           if (COUNT) n_samples++;
           if ((fl & 1) == 0) {
             const float oma = 1.0f - acc.w;

@@ -159,7 +159,7 @@ void launch_page_copy(void* pool, const void* store, const PageOp* ops, uint32_t
 // plain voxels of one pool slot (the first halves of its pairs) -> out (device)
 void launch_slot_unpair(const void* slot, void* out, uint64_t n_voxels, uint32_t esize, cudaStream_t s);
 // tile schedule: order = the n tiles sorted by cost, largest first (counting sort over cost >> shift, one CTA)
-void launch_tile_order(const uint32_t* cost, uint32_t n, uint32_t* order, uint32_t shift, cudaStream_t s);
+void launch_tile_order(const uint32_t* cost, uint32_t n, uint32_t* order, uint32_t shift, uint32_t split_cost, cudaStream_t s);
 // CTAs of a traversal launch (k_raycast.cu)
 uint32_t raycast_tiles(uint32_t width, uint32_t height);
 void launch_hash_compact(const uint32_t* hash, uint32_t n, uint32_t* out_list, uint32_t* out_count, cudaStream_t s);

@@ -741,7 +741,7 @@ int raycast_pass(tvk_ctx* ctx, bool with_hash) {
       for (auto& o : ctx->tile_order_d) { if (o) cudaFree(o); o = nullptr; }
       ctx->tile_cost_d = nullptr; ctx->tile_n = 0; ctx->tile_valid = false;
       CU(cudaMalloc(&ctx->tile_cost_d, (size_t)n_tiles * 4));
-      for (auto& o : ctx->tile_order_d) CU(cudaMalloc(&o, (size_t)n_tiles * 4));
+      for (auto& o : ctx->tile_order_d) CU(cudaMalloc(&o, ((size_t)n_tiles + 1) * 4));   // + the split count
       ctx->tile_n = n_tiles;
     }
     CU(cudaMemsetAsync(ctx->tile_cost_d, 0, (size_t)n_tiles * 4, ctx->stream));
@@ -756,7 +756,7 @@ int raycast_pass(tvk_ctx* ctx, bool with_hash) {
     launch_raycast(u, ctx->params.mode, ctx->params.lighting, ctx->dtype, ctx->stream);
   }
   if (lpt) {
-    launch_tile_order(ctx->tile_cost_d, ctx->tile_n, ctx->tile_order_d[ctx->tile_cur ^ 1], 2, ctx->stream);
+    launch_tile_order(ctx->tile_cost_d, ctx->tile_n, ctx->tile_order_d[ctx->tile_cur ^ 1], 2, ctx->tile_split_cost, ctx->stream);
     ctx->tile_cur ^= 1;
     ctx->tile_valid = true;
   }
@@ -823,6 +823,7 @@ int tvk_create(const tvk_device_cfg* cfg, tvk_ctx** out) {
   // LPT tile schedule of the traversal kernel: on unless TVK_TILE_LPT=0 (measured: C3 303.7 -> 313.5 fps on one GPU,
   // 735 -> 770 fps at N = 8, images bit-identical; profiles/r3a_lpt_ab.txt)
   { const char* e = std::getenv("TVK_TILE_LPT"); ctx->tile_lpt = (e && e[0] == '0') ? 0 : 1; }
+  { const char* e = std::getenv("TVK_SPLIT_COST"); ctx->tile_split_cost = e ? (uint32_t)std::atoi(e) : 0u; }
   if (ctx->cfg.hash_table_size == 0) ctx->cfg.hash_table_size = 509;
   if (ctx->cfg.rehash_count == 0) ctx->cfg.rehash_count = 10;
   if (!cfg) ctx->cfg.brick_strategy = TVK_BS_SKIP_TWO_LEVELS;

@@ -99,6 +99,7 @@ struct tvk_ctx {
   bool counters_on = false;
   // LPT tile schedule of the traversal kernel (TVK_TILE_LPT / tvk_set_tile_schedule): tiles sorted by last frame's cost
   int tile_lpt = 0;
+  uint32_t tile_split_cost = 0;     // persistent build: tiles that cost at least this many turns are split (0 = never)
   uint32_t* tile_cost_d = nullptr;
   uint32_t* tile_order_d[2] = {nullptr, nullptr};
   uint32_t tile_n = 0; int tile_cur = 0; bool tile_valid = false;
