@@ -54,8 +54,7 @@ int main(int argc, char** argv) {
     std::shared_ptr<MaxMinDataBlock> mm(new MaxMinDataBlock(1));
     std::shared_ptr<TOCBlock> toc(new TOCBlock(UVF::ms_ulReaderVersion));
     toc->strBlockID = "Volume converted by ref_uvf";
-    char tmp[64];
-    snprintf(tmp, sizeof(tmp), "%s.%d.tmp", out.c_str(), ts);
+    const std::string tmp = out + "." + std::to_string(ts) + ".tmp";    // (no fixed-size buffer: test paths are long)
     if (!toc->FlatDataToBrickedLOD(in, tmp, ct, 1, vol, DOUBLEVECTOR3(1, 1, 1), UINT64VECTOR3(brick, brick, brick), overlap,
                                    false, false, size_t(1) << 30, mm, &dbg, comp, comp == CT_LZ4 ? 1 : 6, layout)) {
       fprintf(stderr, "brick generation failed\n");
@@ -80,9 +79,8 @@ int main(int argc, char** argv) {
   if (!uvf.Create()) { fprintf(stderr, "UVF::Create failed\n"); return 1; }
   uvf.Close();
   for (int ts = 0; ts < timesteps; ts++) {
-    char tmp[64];
-    snprintf(tmp, sizeof(tmp), "%s.%d.tmp", out.c_str(), ts);
-    remove(tmp);
+    const std::string tmp = out + "." + std::to_string(ts) + ".tmp";
+    remove(tmp.c_str());
   }
   return 0;
 }
