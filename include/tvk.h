@@ -481,6 +481,16 @@ int tvk_composite_over(tvk_ctx* ctx, const void* front, const void* back, void* 
 /* float -> unorm8 (GL read-back conversion) on device buffers */
 int tvk_quantize_rgba8(tvk_ctx* ctx, const void* rgba32f, void* rgba8, uint64_t n_pixels);
 
+/* ---- environment switches (read once, at tvk_create / tvk_sortlast_init; all default to the measured-best setting) ----
+ *   TVK_TILE_LPT=0      traversal launches run their tiles in dispatch order instead of longest-first by the previous launch's
+ *                       per-tile cost (results never depend on the order)
+ *   TVK_SL_PEER=0       sort-last: NCCL slice exchange instead of reading the peers' images through CUDA IPC peer memory
+ *   TVK_SL_OVERLAP=0    sort-last: blend + gather of frame f in order on the render stream instead of on the internal stream
+ *                       while frame f + 1 is traversed
+ *   TVK_BRICKER_TMA=0   tvk_build_volume cuts bricks with the generic kernel instead of the TMA box loads
+ *   TVK_BUILD_TRACE=1 / TVK_UPLOAD_TRACE=1   per-level build times / per-batch upload times on stderr
+ *   TVK_SPLIT_COST=n    only in a -DTVK_PERSIST=1 build (measured slower): tiles above n turns are split */
+
 /* ---- measurement ---------------------------------------------------------------------------------------------------
  * The ceiling of the traversal kernel's own fetch path: width*height rays in the kernel's warp tiles
  * march `steps` 0.5-voxel steps along `dir` through the resident pool doing ONLY the footprint loads and the packed
