@@ -89,6 +89,7 @@ def lib():
         "orc_octree_new": (P, [u32x3, u32x3, C.c_uint32, C.c_int]),
         "orc_octree_free": (None, [P]),
         "orc_octree_build": (C.c_int, [P, P, C.c_int, C.c_int]),
+        "orc_octree_build_component": (C.c_int, [P, P, C.c_int, C.c_int, P]),
         "orc_octree_lod_count": (C.c_uint32, [P]),
         "orc_octree_largest_single_brick_lod": (C.c_uint32, [P]),
         "orc_octree_lod_size": (None, [P, C.c_uint32, u32x3]),
@@ -167,7 +168,8 @@ def _p(a):
 class Octree:
     """ExtendedOctree + converter restatement (orc_octree.c)."""
 
-    def __init__(self, flat, max_brick, overlap, clamp=False, median=False):
+    def __init__(self, flat, max_brick, overlap, clamp=False, median=False, chan0=None):
+        """chan0: the Octree of component 0 when `flat` is a further component of a multi-component volume."""
         flat = np.ascontiguousarray(flat)
         assert flat.ndim == 3, "flat volume is indexed [z, y, x]"
         self.dtype = DTYPE_OF[flat.dtype]
@@ -180,7 +182,12 @@ class Octree:
         self.h = L.orc_octree_new(u32x3(*self.vol), u32x3(*self.max_brick), self.overlap, self.dtype)
         if not self.h:
             raise ValueError("invalid octree geometry")
-        L.orc_octree_build(self.h, _p(flat), int(clamp), int(median))
+        if chan0 is None:
+            rc = L.orc_octree_build(self.h, _p(flat), int(clamp), int(median))
+        else:
+            rc = L.orc_octree_build_component(self.h, _p(flat), int(clamp), int(median), chan0.h)
+        if rc != 0:
+            raise ValueError("octree build failed (%d)" % rc)
         self.lod_count = L.orc_octree_lod_count(self.h)
         self.total_bricks = L.orc_octree_total_bricks(self.h)
         self.largest_single_brick_lod = L.orc_octree_largest_single_brick_lod(self.h)
@@ -235,16 +242,19 @@ class Octree:
 
 
 class ColorOctree:
-    """A 4-component (RGBA, 8 bit) volume as four scalar conversions interleaved: the converter treats the components of a
-    voxel independently (same filter, same ghost rule), and the min / max a renderer sees for colour data is that of the
-    ALPHA component (UVFDataset::MaxMinForKey: GetValue(i, 3), uvfDataset.cpp:1144 / :1188).  Same interface as Octree;
-    bricks are [sz, sy, sx, 4].  The multi-component converter itself is not compiled against: parity of the colour BRICKS
-    with the reference converter is unpinned (the scalar conversion each channel goes through is pinned)."""
+    """A 4-component (RGBA, 8 bit) volume as four scalar conversions interleaved: the converter filters the components of a
+    voxel alike (same filter, same ghost rule) -- except for its odd-corner rule, which writes component 0 into every
+    component (orc_octree.c build_impl) -- and the min / max a renderer sees for colour data is that of the ALPHA component
+    (UVFDataset::MaxMinForKey: GetValue(i, 3), uvfDataset.cpp:1144 / :1188).  Same interface as Octree; bricks are
+    [sz, sy, sx, 4].  Pinned to the unmodified converter run with four components
+    (tests/test_octree_ref.py::test_colour_octree_matches_reference_multi_component_converter)."""
 
     def __init__(self, rgba, max_brick, overlap, clamp=False):
         rgba = np.ascontiguousarray(rgba, np.uint8)
         assert rgba.ndim == 4 and rgba.shape[3] == 4, "colour volume is indexed [z, y, x, channel]"
-        self.ch = [Octree(np.ascontiguousarray(rgba[..., k]), max_brick, overlap, clamp=clamp) for k in range(4)]
+        self.ch = [Octree(np.ascontiguousarray(rgba[..., 0]), max_brick, overlap, clamp=clamp)]
+        for k in range(1, 4):      # the converter's odd-corner rule couples the components (orc_octree.c build_impl)
+            self.ch.append(Octree(np.ascontiguousarray(rgba[..., k]), max_brick, overlap, clamp=clamp, chan0=self.ch[0]))
         a = self.ch[3]
         self.dtype, self.vol, self.max_brick, self.overlap = RGBA8, a.vol, a.max_brick, a.overlap
         self.lod_count, self.total_bricks, self.largest_single_brick_lod = a.lod_count, a.total_bricks, a.largest_single_brick_lod

@@ -311,7 +311,12 @@ static void fill_overlap(orc_octree* t, uint32_t lod) {
 #undef BR
 }
 
-int orc_octree_build(orc_octree* t, const void* flat, int clamp_to_edge, int median) {
+/* chan0 != NULL: `t` holds component c > 0 of a multi-component volume whose component 0 is `chan0` (already built).  The
+ * converter filters every component alike -- except for the single voxel at the x/y/z corner of a source brick whose three
+ * inner sizes are odd, where DownsampleBricktoBrick writes COMPONENT 0 of the source voxel into every component
+ * (`*(pTargetData+c) = *p0;`, ExtendedOctreeConverter.inc:232-246).  Inner brick sizes are even here, so only the last brick
+ * of a level whose three sizes are odd has that corner: the last voxel of the next level. */
+static int build_impl(orc_octree* t, const void* flat, int clamp_to_edge, int median, const orc_octree* chan0) {
   const size_t es = esize(t->dtype);
   t->clamp = clamp_to_edge;
   for (int i = 0; i < 3; i++)
@@ -327,6 +332,9 @@ int orc_octree_build(orc_octree* t, const void* flat, int clamp_to_edge, int med
       case ORC_U16: downsample_u16((const uint16_t*)t->lod_vol[l - 1], t->lod_size[l - 1], (uint16_t*)t->lod_vol[l], t->lod_size[l], median); break;
       default:      downsample_f32((const float*)t->lod_vol[l - 1], t->lod_size[l - 1], (float*)t->lod_vol[l], t->lod_size[l], median); break;
     }
+    if (chan0 && (t->lod_size[l - 1][0] & 1u) && (t->lod_size[l - 1][1] & 1u) && (t->lod_size[l - 1][2] & 1u))
+      memcpy((uint8_t*)t->lod_vol[l] + (vol3(t->lod_size[l]) - 1) * es,
+             (const uint8_t*)chan0->lod_vol[l - 1] + (vol3(t->lod_size[l - 1]) - 1) * es, es);
   }
   for (uint32_t l = 1; l < t->lod_count; l++) fill_overlap(t, l);
   /* ComputeBrickStats: min/max over EVERY stored voxel of the brick incl. ghost, as double;
@@ -356,6 +364,15 @@ int orc_octree_build(orc_octree* t, const void* flat, int clamp_to_edge, int med
         }
   free(tmp);
   return 0;
+}
+
+int orc_octree_build(orc_octree* t, const void* flat, int clamp_to_edge, int median) {
+  return build_impl(t, flat, clamp_to_edge, median, NULL);
+}
+/* component c > 0 of a multi-component volume (see build_impl); same geometry and type as chan0 */
+int orc_octree_build_component(orc_octree* t, const void* flat, int clamp_to_edge, int median, const orc_octree* chan0) {
+  if (!chan0 || chan0->dtype != t->dtype || chan0->lod_count != t->lod_count) return -3;
+  return build_impl(t, flat, clamp_to_edge, median, chan0);
 }
 
 const double* orc_octree_minmax(const orc_octree* t) { return t->minmax; }

@@ -4,7 +4,9 @@
 // bit-exactly against the reference itself.  Test infrastructure only; built
 // into oracle/_ref/ (git-ignored).  No reference source is copied here.
 //
-// usage: ref_octree <in.raw> <out.bin> <dtype u8|u16|f32> X Y Z brick overlap clamp median
+// usage: ref_octree <in.raw> <out.bin> <dtype u8|u16|f32|rgba8> X Y Z brick overlap clamp median
+//        (rgba8: four interleaved 8-bit components per voxel; min / max are those of component 3, what a renderer
+//         sees for colour data, uvfDataset.cpp:1188)
 //                   [octree_out [compression 0 none|1 zlib|3 lz4 [layout 0 scanline|1 morton|2 hilbert|3 random]]]
 // octree_out: the ExtendedOctree file the converter wrote (= payload of a UVF TOC block) is kept there, so the
 // product's file reader (tvk_open_octree_file) can be tested on reference-written data.
@@ -33,7 +35,8 @@ int main(int argc, char** argv) {
   uint32_t overlap = (uint32_t)strtoul(argv[8], 0, 10);
   bool clamp = atoi(argv[9]) != 0, median = atoi(argv[10]) != 0;
   ExtendedOctree::COMPONENT_TYPE ct =
-      dt == "u8" ? ExtendedOctree::CT_UINT8 : dt == "u16" ? ExtendedOctree::CT_UINT16 : ExtendedOctree::CT_FLOAT32;
+      (dt == "u8" || dt == "rgba8") ? ExtendedOctree::CT_UINT8 : dt == "u16" ? ExtendedOctree::CT_UINT16 : ExtendedOctree::CT_FLOAT32;
+  const uint64_t comps = dt == "rgba8" ? 4 : 1;
 
   NullOut dbg;
   const bool keep = argc > 11;
@@ -43,7 +46,7 @@ int main(int argc, char** argv) {
   BrickStatVec stats;
   {
     ExtendedOctreeConverter c(UINT64VECTOR3(brick, brick, brick), overlap, 1ull << 30, dbg);
-    if (!c.Convert(in, 0, ct, 1, vol, DOUBLEVECTOR3(1, 1, 1), tmp, 0, &stats, comp, comp == CT_LZ4 ? 1 : 6,
+    if (!c.Convert(in, 0, ct, comps, vol, DOUBLEVECTOR3(1, 1, 1), tmp, 0, &stats, comp, comp == CT_LZ4 ? 1 : 6,
                    median, clamp, layout)) {
       fprintf(stderr, "convert failed\n");
       return 1;
@@ -65,11 +68,12 @@ int main(int argc, char** argv) {
         for (uint64_t x = 0; x < bc.x; x++, idx++) {
           UINT64VECTOR4 co(x, y, z, l);
           UINT64VECTOR3 bs = e.ComputeBrickSize(co);
-          size_t bytes = size_t(bs.volume() * e.GetComponentTypeSize());
+          size_t bytes = size_t(bs.volume() * e.GetComponentTypeSize() * comps);
           buf.resize(bytes);
           e.GetBrickData(&buf[0], co);
           uint64_t s[3] = {bs.x, bs.y, bs.z};
-          double mm[2] = {stats[idx].minScalar, stats[idx].maxScalar};
+          const size_t si = size_t(idx * comps + (comps - 1));
+          double mm[2] = {stats[si].minScalar, stats[si].maxScalar};
           fwrite(s, 8, 3, f);
           fwrite(mm, 8, 2, f);
           fwrite(&buf[0], 1, bytes, f);

@@ -116,3 +116,41 @@ def test_ghost_corner_quirk_is_reference_behaviour(ref_octree_bin, tmp_path):
     assert not vox[10:12, 0:2, 10:12].any()            # (right, top, back)
     assert not vox[10:12, 10:12, 0:2].any()            # (left, bottom, back)
     assert vox[10:12, 10:12, 10:12].all()              # the opposite corner is filled
+
+
+@pytest.mark.parametrize("shape,brick,overlap", [((24, 20, 28), 12, 2), ((33, 17, 40), 12, 2), ((40, 36, 44), 16, 2)])
+def test_colour_octree_matches_reference_multi_component_converter(ref_octree_bin, tmp_path, shape, brick, overlap):
+    """Colour (RGBA8) volumes: orc.ColorOctree -- four scalar conversions interleaved, min / max of the alpha component --
+    against the UNMODIFIED converter run with iComponentCount = 4 on the interleaved volume: every brick, every voxel of every
+    component incl. ghost cells, and the alpha statistics a renderer sees (uvfDataset.cpp:1188)."""
+    rng = np.random.default_rng(sum(shape) + brick)
+    vol = rng.integers(1, 255, size=shape + (4,), endpoint=True).astype(np.uint8)
+    raw, out = tmp_path / "in.raw", tmp_path / "out.bin"
+    vol.tofile(raw)
+    nz, ny, nx = shape
+    subprocess.check_call([ref_octree_bin, str(raw), str(out), "rgba8", str(nx), str(ny), str(nz), str(brick), str(overlap), "0", "0"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    data = out.read_bytes()
+    lods, total = struct.unpack_from("<QQ", data, 0)
+    off = 16
+    ref = []
+    for _ in range(total):
+        sx, sy, sz = struct.unpack_from("<QQQ", data, off); off += 24
+        mn, mx = struct.unpack_from("<dd", data, off); off += 16
+        n = sx * sy * sz * 4
+        ref.append(((sx, sy, sz), mn, mx, np.frombuffer(data, np.uint8, n, off).reshape(sz, sy, sx, 4))); off += n
+    o = orc.ColorOctree(vol, brick, overlap)
+    assert o.lod_count == lods and o.total_bricks == len(ref)
+    inner = brick - 2 * overlap
+    checked = 0
+    for (x, y, z, lod) in o.iter_bricks():
+        i = o.brick_index(x, y, z, lod)
+        size, mn, mx, vox = ref[i]
+        assert o.brick_size(x, y, z, lod) == size
+        ls = o.lod_size(lod)
+        if any(0 < (ls[a] % inner) < overlap and o.brick_count(lod)[a] > 1 for a in range(3)):
+            continue                                    # "Q2", as for scalar volumes
+        assert np.array_equal(o.brick(x, y, z, lod), vox), (x, y, z, lod)
+        assert (o.minmax[i, 0], o.minmax[i, 1]) == (mn, mx), (x, y, z, lod)
+        checked += 1
+    assert checked >= 3
