@@ -502,6 +502,7 @@ def run_tvk(args, rank, world, local_rank):
 
     sl_stats = []
     sl_mode = [0]
+    lpt_on = 0 if os.environ.get("TVK_TILE_LPT", "1").startswith("0") else 1
 
     def frame(i):
         """one step on this rank; returns the stats of the (single) subframe"""
@@ -873,7 +874,12 @@ def run_tvk(args, rank, world, local_rank):
                          "fetch": fetch},
             "e2e": {"value": k / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(C_sizeof_params()),
                     "d2h_bytes_per_step": n_pixels * 4 + 8},
-            "gpu_launches": k * (2 * world if pipe is not None else (4 if split == "paired" else 3) * world if lib_sl else 2 if sl is None else 2 + int(np.log2(world))),
+            # kernels of this library launched inside the timed region, per step: traversal + miss-table compaction (+ the LPT
+            # tile sort, on unless TVK_TILE_LPT=0); library sort-last per rank in addition: wait-consumed, signal, wait-ready
+            # and the n-way blend (+ rank 0's wait for the gathered slices); memsets / copies are not kernels and not counted
+            "gpu_launches": k * (2 * world if pipe is not None else
+                                 ((5 if split == "paired" else 2 + lpt_on + (4 if sl_mode[0] else 1)) * world + (1 if sl_mode[0] else 0)) if lib_sl else
+                                 (2 + (0 if classic else lpt_on)) if sl is None else 2 + int(np.log2(world))),
             "clocks": clocks,
         }
         if stream_obj is not None:
