@@ -22,11 +22,17 @@ CASES = {   # name: (kind, (x, y, z), dtype code, dtype name, brick, overlap, co
     # large bricks, to be re-cut on load (DynamicBrickingDS; tests/test_rebrick.py): ragged last source bricks on every axis
     "octree_u8_b36_zlib": (synth.V_SPH, (80, 70, 50), 0, "u8", 36, 2, 1, 0),
     "octree_u16_b28_lz4": (synth.V_NOISE, (60, 52, 30), 1, "u16", 28, 2, 3, 0),
+    # a colour (RGBA8, four interleaved components) file: the multi-component path of the converter (tests/test_color.py)
+    "octree_rgba8_zlib": (synth.V_SPH, (48, 40, 36), 3, "rgba8", 16, 2, 1, 0),
 }
 
 
 def volume(name):
     kind, size, dt, _, _, _, _, _ = CASES[name]
+    if dt == 3:      # RGBA8: the alpha channel is the case's field, the colour channels three seeded noise fields
+        import numpy as np
+        chans = [synth.synth_volume(synth.V_NOISE, size, 0, 0x5EED + 11 * (k + 1)) for k in range(3)]
+        return np.ascontiguousarray(np.stack(chans + [synth.synth_volume(kind, size, 0, 0x5EED)], axis=-1))
     return synth.synth_volume(kind, size, dt, 0x5EED)
 
 

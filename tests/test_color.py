@@ -37,6 +37,33 @@ def test_colour_octree_is_four_scalar_conversions():
     assert np.array_equal(b[2:-2, 2:-2, 2:-2, 0], s.volume[12:24, 0:12, 12:24, 0])     # inner voxels of brick (1, 0, 1)
 
 
+def _golden_colour_file():
+    import importlib.util
+    import os
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_octree_golden", os.path.join(golden, "make_octree_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return os.path.join(golden, "octree_rgba8_zlib.bin"), m.CASES["octree_rgba8_zlib"], m.volume("octree_rgba8_zlib")
+
+
+def test_colour_octree_file_written_by_the_reference_converter_reads_back():
+    """tests/golden/octree_rgba8_zlib.bin: an ExtendedOctree file with four 8-bit components written by the unmodified
+    converter (zlib bricks).  The product's file reader (host side, no device) delivers the interleaved bricks of the oracle."""
+    from tuvok_b200 import octree_file
+    path, (kind, size, dt, _, brick, ov, _, _), vol = _golden_colour_file()
+    info = octree_file.probe(path)
+    assert info.dtype == tb.RGBA8 and tuple(info.domain_size) == tuple(size) and info.overlap == ov
+    o = orc.ColorOctree(vol, brick, ov)
+    assert info.brick_count == o.total_bricks and info.lod_count == o.lod_count
+    n = 0
+    for key in o.iter_bricks():
+        got = octree_file.read_brick(path, *key, info=info)
+        assert got.shape[3] == 4 and np.array_equal(got, o.brick(*key)), key
+        n += 1
+    assert n == o.total_bricks
+
+
 needs_glsl = pytest.mark.skipif(not glsl_ref.available(), reason="reference shaders / oracle/_ref tools absent")
 
 
@@ -173,4 +200,26 @@ def test_colour_volumes_are_refused_where_they_are_not_built():
     r = s.make_renderer()
     with pytest.raises(tb.TvkError):
         r.PaintClassic()               # the classic GLRaycaster path (GLRaycaster-Color-FS.glsl) is not built
+    r.Cleanup()
+
+
+@pytest.mark.gpu
+def test_cuda_colour_file_source_renders_like_the_registered_dataset():
+    """A colour ExtendedOctree file on the streaming path (tvk_open_octree_file with the alpha min / max table, what
+    tvk_open_uvf hands over from the MaxMin block): frames and page table identical to the same bricks served by callback."""
+    path, (kind, size, dt, _, brick, ov, _, _), vol = _golden_colour_file()
+    s = scene(orc.RM_2DTRANS, True)
+    assert tuple(s.size) == tuple(size) and s.brick[0] == brick and np.array_equal(s.volume, vol)
+    want = s.oracle_render()
+    r = tb.CudaGridLeaper(max_gpu_mem=s.max_gpu_mem, hash_table_size=s.hash_size(), brick_strategy=s.strategy)
+    with pytest.raises(tb.TvkError, match="min / max"):
+        r.OpenOctreeFile(path, max_gradient_magnitude=s.max_grad)          # a colour file needs its table
+    info = r.OpenOctreeFile(path, minmax=s.octree.minmax, range_max=s.range_max, max_gradient_magnitude=s.max_grad)
+    assert info.dtype == tb.RGBA8
+    r.Set1DTrans(s.tf1d); r.Set2DTrans(s.tf2d); r.SetRendermode(s.mode); r.SetUseLighting(s.lighting)
+    r.Resize(s.width, s.height); r.SetRotation(s.rotation)
+    r.CreateVolumePool(s._pool_size)
+    assert r.PaintUntilConverged().converged
+    assert np.array_equal(r.ReadRGBA32F(), want["image"])
+    assert np.array_equal(r.page_table(), want["meta"])
     r.Cleanup()

@@ -28,7 +28,8 @@ _spec.loader.exec_module(golden)
 
 
 def check_file(path, vol, brick, overlap, dtype, codec_slot=None):
-    o = orc.Octree(vol, brick, overlap)
+    # (a colour file: four interleaved components, the oracle's ColorOctree)
+    o = orc.ColorOctree(vol, brick, overlap) if dtype == orc.RGBA8 else orc.Octree(vol, brick, overlap)
     info = octree_file.probe(path)
     assert tuple(info.domain_size) == (vol.shape[2], vol.shape[1], vol.shape[0])
     assert tuple(info.max_brick_size) == (brick,) * 3 and info.overlap == overlap and info.dtype == dtype

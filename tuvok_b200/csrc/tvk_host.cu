@@ -1012,9 +1012,15 @@ static int tvk_open_octree_file_impl(tvk_ctx* ctx, const char* path, uint64_t of
     case 8: dtype = TVK_F32; break;
     default: break;
   }
-  if (dtype < 0 || f->component_count != 1)
-    return fail(ctx, TVK_ERR_INVALID, "%s: component type %u x %llu is not on the hot path (u8 / u16 / f32 scalar)", path,
+  // colour data (AbstrRenderer::ColorData): four interleaved 8-bit components -> the colour kernels (k_color.cu)
+  if (f->component_type == 0 && f->component_count == 4) dtype = TVK_RGBA8;
+  else if (f->component_count != 1) dtype = -1;
+  if (dtype < 0)
+    return fail(ctx, TVK_ERR_INVALID, "%s: component type %u x %llu is not on the hot path (u8 / u16 / f32 scalar, 4 x u8 colour)", path,
                 f->component_type, (unsigned long long)f->component_count);
+  if (dtype == TVK_RGBA8 && !minmax)
+    return fail(ctx, TVK_ERR_INVALID, "%s: a colour file needs its min / max table (the alpha component's, as UVFDataset::MaxMinForKey "
+                "delivers it; tvk_open_uvf takes it from the MaxMin block)", path);
   uint32_t size[3], brick[3];
   float sc[3];
   for (int i = 0; i < 3; i++) {
@@ -1134,7 +1140,8 @@ static void fill_file_info(const OctreeFile& g, tvk_octree_file_info* info) {
     info->domain_size[i] = (uint32_t)g.vol[i]; info->aspect[i] = g.aspect[i]; info->max_brick_size[i] = (uint32_t)g.brick[i];
   }
   info->overlap = g.overlap; info->version = g.version; info->lod_count = g.lod_count();
-  info->dtype = g.component_count != 1 ? -1 : g.component_type == 0 ? TVK_U8 : g.component_type == 1 ? TVK_U16
+  info->dtype = (g.component_count == 4 && g.component_type == 0) ? TVK_RGBA8
+              : g.component_count != 1 ? -1 : g.component_type == 0 ? TVK_U8 : g.component_type == 1 ? TVK_U16
               : g.component_type == 8 ? TVK_F32 : -1;
   info->brick_count = g.toc.size();
   for (const OctreeToc& t : g.toc) {

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib as L
 
-_NP = {L.U8: np.uint8, L.U16: np.uint16, L.F32: np.float32}
+_NP = {L.U8: np.uint8, L.U16: np.uint16, L.F32: np.float32, L.RGBA8: np.dtype((np.uint8, 4))}
 
 
 def probe(path, offset=0, uvf_file_version=5):
@@ -21,7 +21,7 @@ def probe(path, offset=0, uvf_file_version=5):
 
 
 def read_brick(path, x, y, z, lod, info=None, offset=0, uvf_file_version=5):
-    """One decoded brick as ndarray [sz, sy, sx] (own size incl. ghost)."""
+    """One decoded brick as ndarray [sz, sy, sx] (own size incl. ghost; [sz, sy, sx, 4] for a colour file)."""
     info = info or probe(path, offset, uvf_file_version)
     if info.dtype not in _NP:
         raise ValueError("component type not on the hot path")
@@ -33,7 +33,8 @@ def read_brick(path, x, y, z, lod, info=None, offset=0, uvf_file_version=5):
     if rc:
         raise L.TvkError(rc, (L.lib().tvk_last_error(None) or b"").decode())
     sx, sy, sz = (int(v) for v in size)
-    return np.frombuffer(buf.tobytes(), _NP[info.dtype], sx * sy * sz).reshape(sz, sy, sx)
+    out = np.frombuffer(buf.tobytes(), _NP[info.dtype], sx * sy * sz)
+    return out.reshape((sz, sy, sx, 4) if info.dtype == L.RGBA8 else (sz, sy, sx))
 
 
 def uvf_stats(path, timestep=0):
