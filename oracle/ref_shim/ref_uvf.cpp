@@ -5,7 +5,9 @@
 // key/value block.  A 1D and a 2D histogram block accompany every TOC block: UVFDataset only accepts files whose block
 // counts match (IO/uvfDataset.cpp:484-497).  The 2D histogram is computed with 16 value bins to keep the file small.  The product's container walk (tvk_open_uvf) is tested on these files.  Test infrastructure only.
 //
-// usage: ref_uvf <in.raw> <out.uvf> <dtype u8|u16|f32> X Y Z brick overlap compression(0|1|3) layout(0..3) [timesteps]
+// usage: ref_uvf <in.raw> <out.uvf> <dtype u8|u16|f32|rgba8> X Y Z brick overlap compression(0|1|3) layout(0..3) [timesteps]
+//        (rgba8: four interleaved 8-bit components; TOC + MaxMin block with four components, no histogram blocks -- the
+//         histogram classes take scalar data only)
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -37,7 +39,8 @@ int main(int argc, char** argv) {
   const LAYOUT_TYPE layout = (LAYOUT_TYPE)atoi(argv[10]);
   const int timesteps = argc > 11 ? atoi(argv[11]) : 1;
   const ExtendedOctree::COMPONENT_TYPE ct =
-      dt == "u8" ? ExtendedOctree::CT_UINT8 : dt == "u16" ? ExtendedOctree::CT_UINT16 : ExtendedOctree::CT_FLOAT32;
+      (dt == "u8" || dt == "rgba8") ? ExtendedOctree::CT_UINT8 : dt == "u16" ? ExtendedOctree::CT_UINT16 : ExtendedOctree::CT_FLOAT32;
+  const uint64_t comps = dt == "rgba8" ? 4 : 1;
   NullOut dbg;
   remove(out.c_str());
   std::wstring wout(out.begin(), out.end());
@@ -51,17 +54,17 @@ int main(int argc, char** argv) {
   std::vector<std::shared_ptr<Histogram1DDataBlock>> hists;
   std::vector<std::shared_ptr<Histogram2DDataBlock>> hists2;
   for (int ts = 0; ts < timesteps; ts++) {
-    std::shared_ptr<MaxMinDataBlock> mm(new MaxMinDataBlock(1));
+    std::shared_ptr<MaxMinDataBlock> mm(new MaxMinDataBlock(size_t(comps)));
     std::shared_ptr<TOCBlock> toc(new TOCBlock(UVF::ms_ulReaderVersion));
     toc->strBlockID = "Volume converted by ref_uvf";
     const std::string tmp = out + "." + std::to_string(ts) + ".tmp";    // (no fixed-size buffer: test paths are long)
-    if (!toc->FlatDataToBrickedLOD(in, tmp, ct, 1, vol, DOUBLEVECTOR3(1, 1, 1), UINT64VECTOR3(brick, brick, brick), overlap,
+    if (!toc->FlatDataToBrickedLOD(in, tmp, ct, comps, vol, DOUBLEVECTOR3(1, 1, 1), UINT64VECTOR3(brick, brick, brick), overlap,
                                    false, false, size_t(1) << 30, mm, &dbg, comp, comp == CT_LZ4 ? 1 : 6, layout)) {
       fprintf(stderr, "brick generation failed\n");
       return 1;
     }
     uvf.AddDataBlock(toc);
-    if (dt != "f32") {
+    if (dt != "f32" && comps == 1) {
       std::shared_ptr<Histogram1DDataBlock> h(new Histogram1DDataBlock());
       if (h->Compute(toc.get(), 0)) {
         uvf.AddDataBlock(h);

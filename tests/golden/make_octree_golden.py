@@ -40,6 +40,7 @@ def volume(name):
 # KeyValuePairDataBlock classes (oracle/_ref/ref_uvf): name: (volume case, compression, layout, timesteps)
 UVF_CASES = {
     "volume_u8_zlib.uvf": ("octree_u8_zlib_hilbert", 1, 2, 1),
+    "volume_rgba8_zlib.uvf": ("octree_rgba8_zlib", 1, 0, 1),        # colour: TOC block + four-component MaxMin block
 }
 
 

@@ -64,6 +64,53 @@ def test_colour_octree_file_written_by_the_reference_converter_reads_back():
     assert n == o.total_bricks
 
 
+def test_colour_uvf_container_walk_takes_the_alpha_minmax():
+    """tests/golden/volume_rgba8_zlib.uvf: a complete UVF written by the reference's own UVF / TOCBlock / MaxMinDataBlock
+    classes for four-component data.  The product's container walk pairs the TOC block with the MaxMin block and takes
+    component 3 of every entry, as UVFDataset::MaxMinForKey does (uvfDataset.cpp:1188)."""
+    import os
+    from tuvok_b200 import octree_file
+    path, (kind, size, dt, _, brick, ov, _, _), vol = _golden_colour_file()
+    uvf = os.path.join(os.path.dirname(path), "volume_rgba8_zlib.uvf")
+    u = octree_file.uvf_probe(uvf)
+    o = orc.ColorOctree(vol, brick, ov)
+    assert u["n_timesteps"] == 1 and u["maxmin"].shape == (o.total_bricks, 4)
+    assert np.array_equal(u["maxmin"][:, :2], o.minmax[:, :2])
+    info = octree_file.probe(uvf, offset=u["toc_payload_offset"], uvf_file_version=u["file_version"])
+    assert info.dtype == tb.RGBA8 and info.brick_count == o.total_bricks
+    assert np.array_equal(octree_file.read_brick(uvf, 1, 2, 1, 0, info=info, offset=u["toc_payload_offset"]), o.brick(1, 2, 1, 0))
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))), "oracle", "_ref", "ref_dataset")),
+                    reason="oracle/_ref/ref_dataset not built (reference tree absent)")
+def test_reference_uvfdataset_sees_the_same_colour_dataset(tmp_path):
+    """The unmodified UVFDataset on the colour golden: four components, and MaxMinForKey = the oracle's alpha statistics."""
+    import os
+    import subprocess
+    path, (kind, size, dt, _, brick, ov, _, _), vol = _golden_colour_file()
+    uvf = os.path.join(os.path.dirname(path), "volume_rgba8_zlib.uvf")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "ds.txt"
+    subprocess.check_call([os.path.join(root, "oracle", "_ref", "ref_dataset"), uvf, str(out), "256"], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
+    o = orc.ColorOctree(vol, brick, ov)
+    rows = [l.split() for l in open(out)]
+    head = rows[0]
+    assert int(head[head.index("comps") + 1]) == 4 and int(head[head.index("bits") + 1]) == 8
+    n = 0
+    for r in rows:
+        if r[0] != "brick":
+            continue
+        lod, idx = int(r[1]), int(r[2])
+        bc = o.brick_count(lod)
+        x, y, z = idx % bc[0], (idx // bc[0]) % bc[1], idx // (bc[0] * bc[1])
+        i = o.brick_index(x, y, z, lod)
+        k = r.index("mm")
+        assert (float.fromhex(r[k + 1]), float.fromhex(r[k + 2])) == (o.minmax[i, 0], o.minmax[i, 1]), (lod, idx)
+        n += 1
+    assert n == o.total_bricks
+
+
 needs_glsl = pytest.mark.skipif(not glsl_ref.available(), reason="reference shaders / oracle/_ref tools absent")
 
 
@@ -222,4 +269,25 @@ def test_cuda_colour_file_source_renders_like_the_registered_dataset():
     assert r.PaintUntilConverged().converged
     assert np.array_equal(r.ReadRGBA32F(), want["image"])
     assert np.array_equal(r.page_table(), want["meta"])
+    r.Cleanup()
+
+
+@pytest.mark.gpu
+def test_cuda_colour_uvf_opens_and_renders():
+    """tvk_open_uvf on the colour golden container: TOC block + the MaxMin block's alpha component, then the colour kernels."""
+    import os
+    path, (kind, size, dt, _, brick, ov, _, _), vol = _golden_colour_file()
+    uvf = os.path.join(os.path.dirname(path), "volume_rgba8_zlib.uvf")
+    s = scene(orc.RM_1DTRANS, True)
+    want = s.oracle_render()
+    r = tb.CudaGridLeaper(max_gpu_mem=s.max_gpu_mem, hash_table_size=s.hash_size(), brick_strategy=s.strategy)
+    info = r.OpenUVF(uvf, range_max=s.range_max, max_gradient_magnitude=s.max_grad)
+    assert info.dtype == tb.RGBA8
+    n = r.info().total_bricks
+    assert np.array_equal(r.minmax(n)[:, :2], s.octree.minmax[:n, :2])
+    r.Set1DTrans(s.tf1d); r.Set2DTrans(s.tf2d); r.SetRendermode(s.mode); r.SetUseLighting(s.lighting)
+    r.Resize(s.width, s.height); r.SetRotation(s.rotation)
+    r.CreateVolumePool(s._pool_size)
+    assert r.PaintUntilConverged().converged
+    assert np.array_equal(r.ReadRGBA32F(), want["image"])
     r.Cleanup()
