@@ -1013,7 +1013,8 @@ static int tvk_open_octree_file_impl(tvk_ctx* ctx, const char* path, uint64_t of
     default: break;
   }
   // colour data (AbstrRenderer::ColorData): four interleaved 8-bit components -> the colour kernels (k_color.cu)
-  if (f->component_type == 0 && f->component_count == 4) dtype = TVK_RGBA8;
+  // (a four-component file with the precomputed-normals flag holds value + normal, not colour: refused)
+  if (f->component_type == 0 && f->component_count == 4 && !f->precomputed_normals) dtype = TVK_RGBA8;
   else if (f->component_count != 1) dtype = -1;
   if (dtype < 0)
     return fail(ctx, TVK_ERR_INVALID, "%s: component type %u x %llu is not on the hot path (u8 / u16 / f32 scalar, 4 x u8 colour)", path,
@@ -1140,7 +1141,7 @@ static void fill_file_info(const OctreeFile& g, tvk_octree_file_info* info) {
     info->domain_size[i] = (uint32_t)g.vol[i]; info->aspect[i] = g.aspect[i]; info->max_brick_size[i] = (uint32_t)g.brick[i];
   }
   info->overlap = g.overlap; info->version = g.version; info->lod_count = g.lod_count();
-  info->dtype = (g.component_count == 4 && g.component_type == 0) ? TVK_RGBA8
+  info->dtype = (g.component_count == 4 && g.component_type == 0 && !g.precomputed_normals) ? TVK_RGBA8
               : g.component_count != 1 ? -1 : g.component_type == 0 ? TVK_U8 : g.component_type == 1 ? TVK_U16
               : g.component_type == 8 ? TVK_F32 : -1;
   info->brick_count = g.toc.size();
