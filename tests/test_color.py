@@ -259,8 +259,10 @@ def test_cuda_colour_file_source_renders_like_the_registered_dataset():
     assert tuple(s.size) == tuple(size) and s.brick[0] == brick and np.array_equal(s.volume, vol)
     want = s.oracle_render()
     r = tb.CudaGridLeaper(max_gpu_mem=s.max_gpu_mem, hash_table_size=s.hash_size(), brick_strategy=s.strategy)
-    with pytest.raises(tb.TvkError, match="min / max"):
-        r.OpenOctreeFile(path, max_gradient_magnitude=s.max_grad)          # a colour file needs its table
+    info = r.OpenOctreeFile(path, range_max=s.range_max, max_gradient_magnitude=s.max_grad)   # alpha min / max computed on the device
+    assert info.dtype == tb.RGBA8
+    n = r.info().total_bricks
+    assert np.array_equal(r.minmax(n)[:, :2], s.octree.minmax[:n, :2])
     info = r.OpenOctreeFile(path, minmax=s.octree.minmax, range_max=s.range_max, max_gradient_magnitude=s.max_grad)
     assert info.dtype == tb.RGBA8
     r.Set1DTrans(s.tf1d); r.Set2DTrans(s.tf2d); r.SetRendermode(s.mode); r.SetUseLighting(s.lighting)

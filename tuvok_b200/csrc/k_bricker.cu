@@ -402,6 +402,30 @@ __global__ void __launch_bounds__(256) brick_minmax_kernel(const unsigned char* 
   }
 }
 
+// colour bricks (four interleaved 8-bit components): the statistics a renderer sees are the ALPHA component's
+// (UVFDataset::MaxMinForKey -> GetValue(i, 3), uvfDataset.cpp:1188)
+__global__ void __launch_bounds__(256) brick_minmax_alpha_kernel(const unsigned char* __restrict__ staged, const PageOp* ops,
+                                                                 double* minmax) {
+  const PageOp op = ops[blockIdx.x];
+  const uchar4* src = reinterpret_cast<const uchar4*>(staged + op.src_off);
+  const uint32_t n = op.size[0] * op.size[1] * op.size[2];
+  uint32_t mn = src[0].w, mx = src[0].w;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t v = src[i].w;
+    mn = min(mn, v); mx = max(mx, v);
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+  __shared__ uint32_t s_mn[8], s_mx[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { mn = min(mn, s_mn[w]); mx = max(mx, s_mx[w]); }
+    double* o = minmax + 4 * (uint64_t)op.new_id;
+    o[0] = (double)mn; o[1] = (double)mx; o[2] = -DBL_MAX; o[3] = DBL_MAX;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // procedural dataset: min/max of a brick WITHOUT materialising it -- one CTA per brick evaluates the analytic field at
 // the brick's voxels (ghost included; 0 outside the level's grid) and reduces.  Compute-bound integer work (~500 integer
@@ -596,6 +620,7 @@ void launch_brick_minmax(const void* staged, const PageOp* ops, uint32_t n, doub
   switch (dtype) {
     case TVK_U8: brick_minmax_kernel<uint8_t><<<n, 256, 0, s>>>(p, ops, minmax); break;
     case TVK_U16: brick_minmax_kernel<uint16_t><<<n, 256, 0, s>>>(p, ops, minmax); break;
+    case TVK_RGBA8: brick_minmax_alpha_kernel<<<n, 256, 0, s>>>(p, ops, minmax); break;
     default: brick_minmax_kernel<float><<<n, 256, 0, s>>>(p, ops, minmax); break;
   }
 }

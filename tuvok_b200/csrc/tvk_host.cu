@@ -1019,9 +1019,6 @@ static int tvk_open_octree_file_impl(tvk_ctx* ctx, const char* path, uint64_t of
   if (dtype < 0)
     return fail(ctx, TVK_ERR_INVALID, "%s: component type %u x %llu is not on the hot path (u8 / u16 / f32 scalar, 4 x u8 colour)", path,
                 f->component_type, (unsigned long long)f->component_count);
-  if (dtype == TVK_RGBA8 && !minmax)
-    return fail(ctx, TVK_ERR_INVALID, "%s: a colour file needs its min / max table (the alpha component's, as UVFDataset::MaxMinForKey "
-                "delivers it; tvk_open_uvf takes it from the MaxMin block)", path);
   uint32_t size[3], brick[3];
   float sc[3];
   for (int i = 0; i < 3; i++) {
