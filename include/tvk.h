@@ -44,7 +44,8 @@ typedef enum { TVK_U8 = 0, TVK_U16 = 1, TVK_F32 = 2,
                 * then runs GLGridLeaper-Method-{1D,1D-L,2D,2D-L,iso}-color.glsl / Compose-Color-FS.glsl (the transfer function
                 * maps alpha only; AbstrRenderer::ColorData).  min / max = the ALPHA component's (uvfDataset.cpp:1144, :1188).
                 * Registered datasets (tvk_set_volume) and four-component 8-bit ExtendedOctree / UVF files (without a table the alpha
-                * statistics are computed on the device like the scalar ones) on the GridLeaper path: the device bricker, the re-bricking loader, the classic
+                * statistics are computed on the device like the scalar ones) and tvk_build_volume (mean pyramid, unsharded store) on the GridLeaper
+                * path: the re-bricking loader, the classic
                 * per-brick path, MIP, sort-last and the depth pipeline refuse it. */
                TVK_RGBA8 = 3 } tvk_dtype;
 /* AbstrRenderer::ERenderMode (Renderer/AbstrRenderer.h:142-147) */

@@ -433,8 +433,8 @@ class ColorScene(Scene):
         return orc.pool_size(self.max_gpu_mem, 8, 4, self.brick, self.octree.total_bricks)
 
     def make_renderer(self, source="callback", device=0):
-        assert source == "callback", "colour volumes come from a registered dataset (Dataset::GetBrick stand-in)"
-        return super().make_renderer("callback", device)
+        """source: 'callback' = registered dataset fed from the oracle's colour octree, 'device' = the GPU bricker."""
+        return super().make_renderer(source, device)
 
 
 def image_diff(a8, b8):

@@ -402,6 +402,75 @@ __global__ void __launch_bounds__(256) brick_minmax_kernel(const unsigned char* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// colour (RGBA8) volumes on the device bricker.  A colour voxel is a 4-byte word: the brick CUT (gather with ghost, zero
+// fill, clamp, stale corners -- and the TMA box loads for 36^3 bricks) is the float instantiation used as a pure 4-byte
+// mover (no arithmetic touches the payload; its float min / max are meaningless and are overwritten by the pass below).
+// The pyramid filters every component like a scalar (mean in double, truncating cast) -- except at the single voxel whose
+// source block is ONE voxel (all three source sizes odd, last index), where the converter writes component 0 into every
+// component (ExtendedOctreeConverter.inc:232-246, orc_octree.c build_impl).
+// ---------------------------------------------------------------------------------------------
+__global__ void downsample_rgba_kernel(const uchar4* __restrict__ src, uint32_t sx, uint32_t sy, uint32_t sz, uchar4* dst,
+                                       uint32_t dx_, uint32_t dy_, uint32_t dz_) {
+  const uint64_t n = (uint64_t)dx_ * dy_ * dz_;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t x = (uint32_t)(i % dx_), y = (uint32_t)((i / dx_) % dy_), z = (uint32_t)(i / ((uint64_t)dx_ * dy_));
+    const uint32_t bx = sx > 1 ? 2 * x : x, by = sy > 1 ? 2 * y : y, bz = sz > 1 ? 2 * z : z;
+    const uint32_t nx = (sx > 1 && bx + 1 < sx) ? 2 : 1;
+    const uint32_t ny = (sy > 1 && by + 1 < sy) ? 2 : 1;
+    const uint32_t nz = (sz > 1 && bz + 1 < sz) ? 2 : 1;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    uchar4 first = make_uchar4(0, 0, 0, 0);
+    int cnt = 0;
+    for (uint32_t a = 0; a < nx; a++)
+      for (uint32_t b = 0; b < ny; b++)
+        for (uint32_t c = 0; c < nz; c++) {
+          const uchar4 v = src[(uint64_t)(bx + a) + (uint64_t)sx * ((by + b) + (uint64_t)sy * (bz + c))];
+          if (cnt == 0) { first = v; s0 = (double)v.x; s1 = (double)v.y; s2 = (double)v.z; s3 = (double)v.w; }
+          else { s0 = s0 + (double)v.x; s1 = s1 + (double)v.y; s2 = s2 + (double)v.z; s3 = s3 + (double)v.w; }
+          cnt++;
+        }
+    // cnt == 1 <=> every source size is odd (or 1) and this is the last voxel: the converter's corner rule
+    if (cnt == 1) dst[i] = make_uchar4(first.x, first.x, first.x, first.x);
+    else {
+      const double k = (double)cnt;
+      dst[i] = make_uchar4((unsigned char)(s0 / k), (unsigned char)(s1 / k), (unsigned char)(s2 / k), (unsigned char)(s3 / k));
+    }
+  }
+}
+
+// alpha statistics of the bricks of one level, read back from the brick store (every stored voxel incl. ghost)
+__global__ void __launch_bounds__(256) store_alpha_minmax_kernel(const uchar4* __restrict__ store, const CutConsts C, double* minmax,
+                                                                 uint64_t slot_voxels) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t bc[3] = {b % C.layout[0], (b / C.layout[0]) % C.layout[1], b / (C.layout[0] * C.layout[1])};
+  uint32_t bs[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {   // ExtendedOctree::ComputeBrickSize (ExtendedOctree.cpp:276-285)
+    const uint32_t core = C.brick[i] - 2 * C.overlap;
+    const uint32_t rem = C.lod_size[i] % core;
+    bs[i] = (bc[i] == C.layout[i] - 1 && rem) ? 2 * C.overlap + rem : C.brick[i];
+  }
+  const uchar4* src = store + (uint64_t)(C.first_brick + b) * slot_voxels;
+  const uint32_t n = bs[0] * bs[1] * bs[2];
+  uint32_t mn = 255u, mx = 0u;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t lx = i % bs[0], ly = (i / bs[0]) % bs[1], lz = i / (bs[0] * bs[1]);
+    const uint32_t v = src[lx + C.brick[0] * (ly + C.brick[1] * lz)].w;
+    mn = min(mn, v); mx = max(mx, v);
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+  __shared__ uint32_t s_mn[8], s_mx[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { mn = min(mn, s_mn[w]); mx = max(mx, s_mx[w]); }
+    double* o = minmax + 4 * (uint64_t)(C.first_brick + b);
+    o[0] = (double)mn; o[1] = (double)mx; o[2] = -DBL_MAX; o[3] = DBL_MAX;
+  }
+}
+
 // colour bricks (four interleaved 8-bit components): the statistics a renderer sees are the ALPHA component's
 // (UVFDataset::MaxMinForKey -> GetValue(i, 3), uvfDataset.cpp:1188)
 __global__ void __launch_bounds__(256) brick_minmax_alpha_kernel(const unsigned char* __restrict__ staged, const PageOp* ops,
@@ -576,6 +645,10 @@ void launch_synth(void* dst, int kind, const uint32_t size[3], int dtype, uint32
 void launch_downsample(const void* src, const uint32_t ss[3], void* dst, const uint32_t ds[3], int dtype, int median,
                        cudaStream_t s) {
   const uint64_t n = (uint64_t)ds[0] * ds[1] * ds[2];
+  if (dtype == TVK_RGBA8) {   // mean filter only (the host refuses the median for colour data)
+    downsample_rgba_kernel<<<grid_for(n, 256), 256, 0, s>>>((const uchar4*)src, ss[0], ss[1], ss[2], (uchar4*)dst, ds[0], ds[1], ds[2]);
+    return;
+  }
   if (median) {
     const int g = grid_for(n, 256);
     switch (dtype) {
@@ -687,6 +760,12 @@ bool launch_cut_tma(const void* lod_vol, void* store, const int32_t* store_index
 void launch_cut_bricks(const void* lod_vol, void* store, const int32_t* store_index, double* minmax, const CutConsts& cc,
                        int dtype, uint64_t slot_bytes, cudaStream_t s) {
   const uint32_t n = cc.layout[0] * cc.layout[1] * cc.layout[2];
+  if (dtype == TVK_RGBA8) {   // 4-byte voxels moved by the float instantiation, alpha statistics from the store (no shard)
+    if (!launch_cut_tma<float>(lod_vol, store, nullptr, minmax, cc, slot_bytes / 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, s))
+      cut_bricks_kernel<float><<<n, 256, 0, s>>>((const float*)lod_vol, (float*)store, nullptr, minmax, cc, slot_bytes / 4);
+    store_alpha_minmax_kernel<<<n, 256, 0, s>>>((const uchar4*)store, cc, minmax, slot_bytes / 4);
+    return;
+  }
   // 36^3 bricks of a level whose rows are 16-byte multiples: 3-D box loads through the TMA unit
   if (dtype == TVK_U8 && launch_cut_tma<uint8_t>(lod_vol, store, store_index, minmax, cc, slot_bytes, CU_TENSOR_MAP_DATA_TYPE_UINT8, s)) return;
   if (dtype == TVK_U16 && launch_cut_tma<uint16_t>(lod_vol, store, store_index, minmax, cc, slot_bytes / 2, CU_TENSOR_MAP_DATA_TYPE_UINT16, s)) return;

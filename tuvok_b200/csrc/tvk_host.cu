@@ -1192,7 +1192,12 @@ int tvk_build_volume(tvk_ctx* ctx, const void* raw, int raw_on_device, const uin
                      const float scale[3], const uint32_t max_brick_size[3], uint32_t overlap, int clamp_to_edge,
                      double range_max, float max_gradient_magnitude) {
   if (!ctx || !raw || !size || !max_brick_size) return fail(ctx, TVK_ERR_INVALID, "NULL argument");
-  if (dtype == TVK_RGBA8) return fail(ctx, TVK_ERR_INVALID, "tvk_build_volume: colour volumes come from a registered dataset (tvk_set_volume)");
+  if (dtype == TVK_RGBA8) {   // colour: mean pyramid, unsharded store (sort-last refuses colour data anyway)
+    if (ctx->pyramid_median) return fail(ctx, TVK_ERR_INVALID, "tvk_build_volume: the median pyramid is built for scalar volumes");
+    for (int i = 0; i < 3; i++)
+      if (ctx->store_clip_min[i] > 0.0f || ctx->store_clip_max[i] < 1.0f)
+        return fail(ctx, TVK_ERR_INVALID, "tvk_build_volume: a sharded brick store is built for scalar volumes");
+  }
   int rc = set_geometry(ctx, size, scale, max_brick_size, overlap, dtype, range_max, max_gradient_magnitude);
   if (rc) return rc;
   ctx->cb = nullptr; ctx->cb_user = nullptr;

@@ -248,13 +248,19 @@ class CudaGridLeaper:
     def BuildVolume(self, raw, max_brick_size, overlap, scale=(1, 1, 1), clamp_to_edge=False, range_max=0.0,
                     max_gradient_magnitude=0.0, size=None, dtype=None, median=False):
         """Brick a raw volume on the GPU (replaces the offline ExtendedOctreeConverter).  `raw` is a
-        numpy array [z, y, x] (host) or an int device pointer with `size=(nx,ny,nz)` and `dtype`."""
+        numpy array [z, y, x] (host; [z, y, x, 4] uint8 = a colour volume) or an int device pointer with `size=(nx,ny,nz)`
+        and `dtype`."""
         if np.isscalar(max_brick_size):
             max_brick_size = (max_brick_size,) * 3
         if isinstance(raw, np.ndarray):
             raw = np.ascontiguousarray(raw)
             size = (raw.shape[2], raw.shape[1], raw.shape[0])
-            dtype = _DT_OF[raw.dtype]
+            if raw.ndim == 4:
+                if raw.shape[3] != 4 or raw.dtype != np.uint8:
+                    raise ValueError("a colour volume is [z, y, x, 4] uint8")
+                dtype = L.RGBA8
+            else:
+                dtype = _DT_OF[raw.dtype]
             ptr, on_dev = _ptr(raw), 0
         else:
             ptr, on_dev = C.c_void_p(int(raw)), 1
@@ -325,7 +331,7 @@ class CudaGridLeaper:
 
     def brick(self, x, y, z, lod, dtype):
         s = self.brick_size(x, y, z, lod)
-        out = np.zeros((s[2], s[1], s[0]), _NP_OF[dtype])
+        out = np.zeros((s[2], s[1], s[0]) + ((4,) if dtype == L.RGBA8 else ()), _NP_OF[dtype])
         self._ck(self._lib.tvk_read_brick(self._h, x, y, z, lod, _ptr(out), out.nbytes))
         return out
 
